@@ -1,0 +1,167 @@
+/* walt_b200.h -- C ABI of the B200-native WALT mapping engine (libwaltb200.so).
+ *
+ * This is the drop-in boundary for the reference's mapping hot path.  The reference has no
+ * FFI of its own; the seam is the strand-loop body of its two batch drivers
+ *     ReadIndex(...) + #pragma omp parallel for { SingleEndMapping | PairEndMapping }
+ *     (src/walt/mapping.cpp:491-500, src/walt/paired.cpp:660-671)
+ * plus the index reader that feeds it (src/walt/reference.cpp:324-417).  Each entry point
+ * below names the reference interface it replaces.  Plain pointers and sizes only; no C++
+ * or torch types cross this boundary.  All functions return 0 on success and a non-zero
+ * WALT_E* code on failure; walt_last_error() returns a message for the calling thread.
+ * There is no CPU fallback: every mapping call runs on the CUDA device or fails.
+ *
+ * Conventions: caller owns all host buffers; calls are synchronous (internally the batch is
+ * double-buffered over CUDA streams); one engine per GPU per process; an engine is
+ * thread-compatible, not thread-safe.  Results are indexed by input read order.
+ */
+#ifndef WALT_B200_H_
+#define WALT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WALT_OK          0
+#define WALT_EINVAL      1   /* bad argument                                              */
+#define WALT_EIO         2   /* file missing / short read (reference: FREAD_CHECK, exit)  */
+#define WALT_ECUDA       3   /* CUDA runtime error, including "no device"                 */
+#define WALT_EFORMAT     4   /* index content violates the makedb invariants              */
+#define WALT_ENONACGT    5   /* read contains a non-ACGT byte (reference: util.hpp:117-120
+                                prints "[ERROR: NON-ACGT NUCLEOTIDE]" and exits)          */
+#define WALT_ENOTLOADED  6   /* needed sub-index not resident                             */
+
+/* Sub-index ids, in makedb order (src/walt/makedb.cpp:144-155). */
+#define WALT_CT00 0   /* C->T, forward genome            */
+#define WALT_CT01 1   /* C->T, reverse-complement genome */
+#define WALT_GA10 2   /* G->A, forward genome            */
+#define WALT_GA11 3   /* G->A, reverse-complement genome */
+
+typedef struct walt_engine walt_engine;
+
+/* == BestMatch (src/walt/mapping.hpp:39-52) with a fixed 16-byte layout. */
+typedef struct {
+  uint32_t genome_pos;
+  uint32_t times;
+  uint32_t mismatch;
+  char strand;
+  char pad[3];
+} walt_best;
+
+/* == CandidatePosition (src/walt/paired.hpp:35-46) with a fixed 12-byte layout. */
+typedef struct {
+  uint32_t genome_pos;
+  uint32_t mismatch;
+  char strand;
+  char pad[3];
+} walt_cand;
+
+/* Per-pair result of the pairing step (MergePairedEndResults, paired.cpp:472-513). */
+typedef struct {
+  uint32_t best_times;     /* 1 = unique pair, >=2 ambiguous, 0 none                     */
+  int32_t best_i, best_j;  /* indices into the ranked lists of mate 1 / mate 2, or -1    */
+  int32_t frag_len;        /* GetFragmentLength of the winning pair (valid if times>=1)  */
+} walt_pair;
+
+/* Work counters of the last mapping call (device-side, for the roofline model). */
+typedef struct {
+  uint64_t n_lookups;      /* table lookups with a non-empty 12-mer bucket               */
+  uint64_t n_candidates;   /* candidate windows compared against the genome              */
+  uint64_t n_literal;      /* lookups that took the literal IndexRegion emulation        */
+  uint64_t n_kernel_launches;
+} walt_stats;
+
+const char* walt_last_error(void);
+
+/* ---- engine lifetime ----------------------------------------------------------------- */
+int walt_engine_create(walt_engine** out, int device);
+void walt_engine_destroy(walt_engine* e);
+
+/* ---- index residency ------------------------------------------------------------------
+ * Replaces ReadIndexHeadInfo + the per-batch, per-strand ReadIndex calls
+ * (reference.cpp:324-417; call sites mapping.cpp:437,492 and paired.cpp:578,661): the header
+ * and the requested sub-indexes are read ONCE, packed to 2 bits/base and kept in HBM
+ * together with the derived lookup table. `which_mask` has bit WALT_CT00.. set for every
+ * sub-index to load (SE without -A: CT00|CT01; SE -A: GA10|GA11; PE: all four). */
+int walt_engine_load_dbindex(walt_engine* e, const char* dbindex_path, uint32_t which_mask);
+
+/* Same residency from caller memory (one sub-index per call): what ReadIndex would have
+ * put into Genome/HashTable.  `sequence` is the converted ASCII genome of that sub-index. */
+int walt_engine_set_chromosomes(walt_engine* e, uint32_t n_chr, const uint32_t* lengths);
+int walt_engine_load_subindex(walt_engine* e, int which, const char* sequence,
+                              const uint32_t* counter /* 4^12+1 */, const uint32_t* index,
+                              uint32_t index_size);
+
+/* Chromosome table as read from the header (names are NUL-terminated, owned by the engine). */
+int walt_engine_chromosomes(const walt_engine* e, uint32_t* n_chr, const uint32_t** lengths,
+                            const uint32_t** start_index, const char* const** names);
+uint64_t walt_engine_hbm_bytes(const walt_engine* e);
+
+/* ---- single-end mapping ---------------------------------------------------------------
+ * Replaces both strand passes of mapping.cpp:486-500 for one batch: out[j] is what
+ * map_results[j] holds after the '-' pass.  `seqs` is the concatenation of the reads as
+ * LoadReadsFromFastqFile left them (ACGT only), read j = seqs[offs[j] .. offs[j+1]).
+ * *n_short = 2 * #reads shorter than 38 (StatSingleReads::num_of_short_reads is bumped once
+ * per strand pass, mapping.cpp:230-232). */
+int walt_engine_map_se(walt_engine* e, const char* seqs, const uint64_t* offs, uint32_t n,
+                       int ag_wildcard, uint32_t max_mismatches, uint32_t b, walt_best* out,
+                       uint32_t* n_short);
+
+/* Same computation with every buffer already resident in device memory (kernel-only
+ * timing; no host<->device copies). */
+int walt_engine_map_se_device(walt_engine* e, const void* d_seqs, const void* d_offs, uint32_t n,
+                              uint32_t max_read_len, int ag_wildcard, uint32_t max_mismatches,
+                              uint32_t b, void* d_out, void* cuda_stream);
+
+/* ---- paired-end mapping ---------------------------------------------------------------
+ * Replaces, for one batch, the mate/strand loops of paired.cpp:642-672 (PairEndMapping into
+ * TopCandidates), the heap drain of paired.cpp:684-692 and the pairing loop of
+ * MergePairedEndResults (paired.cpp:472-513).  ranked1/ranked2 hold top_k slots per pair,
+ * worst first (ranked[j*top_k + 0]) to best (ranked[j*top_k + n_ranked[j]-1]).
+ * pbat != 0 swaps the bisulfite roles of the mates (mate 1 G->A, mate 2 C->T). */
+int walt_engine_map_pe(walt_engine* e, const char* seqs1, const uint64_t* offs1, const char* seqs2,
+                       const uint64_t* offs2, uint32_t n, uint32_t max_mismatches, uint32_t b,
+                       uint32_t top_k, int frag_range, int pbat, walt_cand* ranked1,
+                       uint32_t* n_ranked1, walt_cand* ranked2, uint32_t* n_ranked2,
+                       walt_pair* pairs, uint32_t* n_short1, uint32_t* n_short2);
+
+int walt_engine_last_stats(const walt_engine* e, walt_stats* out);
+
+/* Test hook: 0 = table-driven search (default), 1 = literal IndexRegion emulation for every
+ * lookup (the in-repo device oracle; same results, slower). */
+int walt_engine_set_search_mode(walt_engine* e, int mode);
+
+/* ---- pinned host memory for batch buffers --------------------------------------------- */
+void* walt_host_alloc(size_t bytes);
+void walt_host_free(void* p);
+
+/* ---- index builder (makedb) -----------------------------------------------------------
+ * Replaces BuildIndex x4 + WriteIndexHeadInfo (makedb.cpp:46-85,144-159): counting,
+ * bucketing and bucket sorting run on the GPU; the files written are the reference's
+ * format (reference.cpp:302-322,353-379).  `sequence` is the concatenated upper-case ACGT
+ * genome (N already replaced by the caller, as ReadGenome does). */
+int walt_makedb_write(int device, uint32_t n_chr, const char* const* names, const uint32_t* lengths,
+                      const char* sequence, const char* out_dbindex_path);
+
+/* Build the requested sub-indexes directly into an engine from a device-resident 2-bit
+ * genome (32 bases per 64-bit word, first base in the top bits, A0 C1 G2 T3), no files. */
+int walt_engine_build_from_device_genome(walt_engine* e, uint32_t n_chr, const uint32_t* lengths,
+                                         const void* d_packed_genome, uint32_t which_mask);
+
+/* Export a resident sub-index back to host arrays in the reference's in-memory form
+ * (ASCII converted genome, counter[4^12+1], index[index_size]); any pointer may be NULL. */
+int walt_engine_export_subindex(walt_engine* e, int which, char* sequence, uint32_t* counter,
+                                uint32_t* index, uint32_t* index_size);
+
+/* ---- synthetic workloads (bench only; SURVEY.md 8(d) shapes) --------------------------- */
+int walt_synth_genome_device(int device, uint64_t n_bases, uint64_t seed, void* d_packed_out);
+int walt_synth_reads_device(int device, const void* d_packed_genome, uint32_t n_chr,
+                            const uint32_t* lengths, uint32_t n_reads, uint32_t read_len,
+                            uint64_t seed, int a_rich, void* d_seqs_out /* n*read_len ASCII */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WALT_B200_H_ */

@@ -1,0 +1,443 @@
+// tests/emu/emu_driver.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Steps the lane-level kernel source (walt_b200/csrc/walt_core.cuh) on the CPU: every
+// emulated warp is 32 cooperative fibers that run in lock step between warp primitives
+// (ballot / shfl / reduce / sync), with hand-rolled x86-64 context switches.  This lets the
+// CPU-only test suite ("-m 'not gpu'") check the kernel logic -- table construction, taint
+// handling, k-ary search, ordered folds, heap pushes, pairing -- against the oracle without a
+// device.  It is NOT a product code path: libwaltb200.so contains none of this and fails
+// loudly without a GPU; nothing under walt_b200/ loads this library.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <thread>
+#include <vector>
+
+#include "../../walt_b200/csrc/walt_core.cuh"
+
+using namespace waltcore;
+
+// ------------------------------------------------------------------------------------------
+// fibers
+// ------------------------------------------------------------------------------------------
+extern "C" void emu_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.globl emu_switch
+.type emu_switch,@function
+emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size emu_switch,.-emu_switch
+)");
+
+namespace {
+
+constexpr size_t STACK_BYTES = 256 * 1024;
+
+struct WarpEmu;
+struct Fiber {
+  void* sp = nullptr;
+  char* stack = nullptr;
+  WarpEmu* warp = nullptr;
+  uint32_t lane = 0;
+  bool done = false;
+};
+
+typedef void (*LaneFn)(WarpEmu*, uint32_t lane, void* arg);
+
+struct WarpEmu {
+  Fiber fib[32];
+  void* main_sp = nullptr;
+  uint32_t slots[2][32];
+  uint32_t tags[2][32];
+  uint32_t cur = 0;       // running lane
+  uint32_t n_done = 0;
+  LaneFn fn = nullptr;
+  void* arg = nullptr;
+  bool diverged = false;
+
+  WarpEmu() {
+    for (int i = 0; i < 32; ++i) {
+      fib[i].stack = (char*)aligned_alloc(64, STACK_BYTES);
+      fib[i].warp = this;
+      fib[i].lane = i;
+    }
+  }
+  ~WarpEmu() { for (int i = 0; i < 32; ++i) free(fib[i].stack); }
+
+  static void trampoline();
+  void yield_next() {
+    uint32_t from = cur;
+    uint32_t to = (cur + 1) & 31u;
+    cur = to;
+    emu_switch(&fib[from].sp, fib[to].sp);
+  }
+  void run(LaneFn f, void* a) {
+    fn = f; arg = a; n_done = 0; cur = 0;
+    for (int i = 0; i < 32; ++i) {
+      fib[i].done = false;
+      // initial frame: 6 callee-saved registers + return address (trampoline)
+      void** top = (void**)(fib[i].stack + STACK_BYTES);
+      top -= 1;                      // after `ret` rsp == 8 (mod 16), as at a normal function entry
+      *--top = (void*)&WarpEmu::trampoline;
+      for (int r = 0; r < 6; ++r) *--top = nullptr;
+      fib[i].sp = top;
+    }
+    emu_switch(&main_sp, fib[0].sp);
+  }
+};
+
+thread_local WarpEmu* g_current = nullptr;
+
+void WarpEmu::trampoline() {
+  WarpEmu* w = g_current;
+  uint32_t lane = w->cur;
+  w->fn(w, lane, w->arg);
+  w->fib[lane].done = true;
+  w->n_done++;
+  if (w->n_done == 32) {
+    void* dummy;
+    emu_switch(&dummy, w->main_sp);
+  } else {
+    // lanes finish in order; the next one is parked at its last primitive
+    uint32_t to = (lane + 1) & 31u;
+    w->cur = to;
+    void* dummy;
+    emu_switch(&dummy, w->fib[to].sp);
+  }
+  abort();  // never resumed
+}
+
+// the warp policy handed to walt_core.cuh
+struct EmuWarp {
+  WarpEmu* w;
+  uint32_t my_lane;
+  uint32_t n_prim = 0;
+  uint32_t lane() const { return my_lane; }
+  // every lane deposits v, one full round later all 32 values are visible
+  const uint32_t* exchange(uint32_t v, uint32_t tag) {
+    uint32_t buf = n_prim & 1u;
+    ++n_prim;
+    w->slots[buf][my_lane] = v;
+    w->tags[buf][my_lane] = tag;
+    w->yield_next();
+    for (int i = 0; i < 32; ++i)
+      if (w->tags[buf][i] != tag) w->diverged = true;
+    return w->slots[buf];
+  }
+  uint32_t ballot(bool p) {
+    const uint32_t* s = exchange(p ? 1u : 0u, 1u);
+    uint32_t m = 0;
+    for (int i = 0; i < 32; ++i) m |= (s[i] & 1u) << i;
+    return m;
+  }
+  uint32_t shfl(uint32_t v, int src) { return exchange(v, 2u)[src & 31]; }
+  uint32_t reduce_add(uint32_t v) {
+    const uint32_t* s = exchange(v, 3u);
+    uint32_t a = 0;
+    for (int i = 0; i < 32; ++i) a += s[i];
+    return a;
+  }
+  uint32_t reduce_min(uint32_t v) {
+    const uint32_t* s = exchange(v, 4u);
+    uint32_t a = 0xFFFFFFFFu;
+    for (int i = 0; i < 32; ++i) a = std::min(a, s[i]);
+    return a;
+  }
+  void sync() { exchange(0u, 5u); }
+};
+
+// ------------------------------------------------------------------------------------------
+// host copy of the device-side index structures, built with the same per-element functions
+// the GPU kernels use
+// ------------------------------------------------------------------------------------------
+struct EmuSubIndex {
+  std::vector<uint64_t> genome;
+  std::vector<uint32_t> index, table, taint_bits, taint_key, taint_pos, taint_len;
+  uint32_t depth = 0, ag = 0;
+  uint32_t unsorted = 0;
+  SubIndexView view() const {
+    SubIndexView v;
+    v.genome = genome.data(); v.index = index.data(); v.table = table.data();
+    v.taint_bits = taint_bits.data(); v.taint_key = taint_key.data();
+    v.taint_pos = taint_pos.data(); v.taint_len = taint_len.data();
+    v.n_taint = (uint32_t)taint_key.size(); v.index_size = (uint32_t)index.size();
+    v.depth = depth; v.ag = ag;
+    return v;
+  }
+};
+
+struct EmuEngine {
+  std::vector<uint32_t> starts;
+  uint32_t n_chr = 0, genome_len = 0;
+  Pow3 p3;
+  EmuSubIndex sub[4];
+  ChromView cv() const { ChromView c; c.starts = starts.data(); c.n_chr = n_chr; c.genome_len = genome_len; return c; }
+};
+
+uint32_t choose_depth(uint32_t index_size) {
+  uint32_t d = KEY_WEIGHT;
+  uint64_t p = 531441;
+  while (d < MAX_DEPTH && p < index_size) { p *= 3; ++d; }
+  return d;
+}
+
+}  // namespace
+
+extern "C" {
+
+void* emu_engine_create(uint32_t n_chr, const uint32_t* lengths) {
+  EmuEngine* e = new EmuEngine;
+  e->n_chr = n_chr;
+  e->starts.resize(n_chr + 1);
+  e->starts[0] = 0;
+  for (uint32_t i = 0; i < n_chr; ++i) e->starts[i + 1] = e->starts[i] + lengths[i];
+  e->genome_len = e->starts[n_chr];
+  uint32_t p = 1;
+  for (uint32_t i = 0; i <= MAX_DEPTH; ++i) { e->p3.v[i] = p; p *= 3u; }
+  return e;
+}
+void emu_engine_destroy(void* h) { delete (EmuEngine*)h; }
+
+// returns 0 ok, 1 bad letter, 2 index not in makedb order
+int emu_engine_load_subindex(void* h, int which, const char* seq, const uint32_t* index,
+                             uint32_t index_size, int force_depth) {
+  EmuEngine* e = (EmuEngine*)h;
+  EmuSubIndex& s = e->sub[which];
+  s.ag = which >= 2;
+  const uint64_t L = e->genome_len;
+  const uint64_t words = (L + PAD_BASES + 31) / 32 + TAIL_PAD_WORDS;
+  s.genome.assign(words, 0);
+  for (uint64_t i = 0; i < L; ++i) {
+    uint32_t c = (uint8_t)seq[i];
+    if (!ascii_is_acgt(c)) return 1;
+    uint32_t code = ascii_code(c);
+    if (s.ag ? code == 2u : code == 1u) return 1;
+    uint64_t p = i + PAD_BASES;
+    s.genome[p >> 5] |= (uint64_t)code << (62 - 2 * (p & 31));
+  }
+  s.index.assign(index, index + index_size);
+  s.index.resize(index_size + 32, 0);  // readable pad like the device buffer
+  s.index.resize(index_size);
+  s.depth = force_depth > 0 ? (uint32_t)force_depth : choose_depth(index_size);
+  const uint32_t n_keys = e->p3.v[s.depth];
+  s.table.assign((size_t)n_keys + 1, 0);
+  // table fill == build_table_kernel
+  ChromView cv = e->cv();
+  uint32_t prev_key = 0;
+  s.unsorted = 0;
+  for (uint64_t i = 0; i <= index_size; ++i) {
+    uint32_t key;
+    if (i < index_size) {
+      uint32_t en = s.index[i];
+      uint32_t chr = chrom_of(cv.starts, cv.n_chr, en);
+      key = entry_table_key(s.genome.data(), en, cv.starts[chr + 1], s.depth, s.ag, e->p3);
+    } else {
+      key = n_keys;
+    }
+    uint32_t from = i ? prev_key + 1 : 0;
+    if (i && i < index_size && key < prev_key) s.unsorted++;
+    for (uint64_t k = from; k <= key; ++k) s.table[k] = (uint32_t)i;
+    if (i < index_size) prev_key = std::max(prev_key, key);
+  }
+  // taint list == taint_kernel + host sort
+  std::vector<std::pair<uint32_t, std::pair<uint32_t, uint32_t>>> t;
+  for (uint32_t c = 0; c < e->n_chr; ++c) {
+    uint32_t cs = e->starts[c], ce = e->starts[c + 1];
+    for (uint32_t d = MIN_SEED_LEN + 1; d <= TAINT_SPAN; ++d) {
+      if (ce - cs < d) break;
+      uint32_t pos = ce - d;
+      t.push_back({entry_key12(s.genome.data(), pos, s.ag, e->p3), {pos, d}});
+    }
+  }
+  std::sort(t.begin(), t.end());
+  s.taint_bits.assign((N_KEY12 + 31) / 32, 0);
+  s.taint_key.clear(); s.taint_pos.clear(); s.taint_len.clear();
+  for (auto& x : t) {
+    s.taint_key.push_back(x.first); s.taint_pos.push_back(x.second.first); s.taint_len.push_back(x.second.second);
+    s.taint_bits[x.first >> 5] |= 1u << (x.first & 31);
+  }
+  return s.unsorted ? 2 : 0;
+}
+
+uint32_t emu_engine_depth(void* h, int which) { return ((EmuEngine*)h)->sub[which].depth; }
+
+struct emu_best { uint32_t genome_pos, times, mismatch; char strand; char pad[3]; };
+struct emu_cand { uint32_t genome_pos, mismatch; char strand; char pad[3]; };
+struct emu_pair { uint32_t best_times; int32_t best_i, best_j, frag_len; };
+
+}  // extern "C"
+
+namespace {
+
+struct SeJob {
+  const EmuEngine* e; const char* seqs; const uint64_t* offs; uint32_t lo, hi;
+  int ag; uint32_t m, b; int literal; emu_best* out; uint32_t max_len;
+  uint64_t* scratch; uint32_t* cached_len; Counters* ctr; int* bad;
+};
+
+void se_lane(WarpEmu* w, uint32_t lane, void* arg) {
+  SeJob* j = (SeJob*)arg;
+  EmuWarp W{w, lane};
+  SubIndexView ix2[2] = {j->e->sub[j->ag ? 2 : 0].view(), j->e->sub[j->ag ? 3 : 1].view()};
+  ChromView cv = j->e->cv();
+  MapConfig cfg; cfg.b = j->b; cfg.literal_all = j->literal;
+  const uint32_t nwmax = (j->max_len + 31) / 32;
+  ReadScratch sc = carve_scratch(j->scratch, nwmax ? nwmax : 1);
+  uint32_t cached = *j->cached_len;  // lane-private copy, kept uniform
+  Counters ctr{0, 0, 0};
+  for (uint32_t r = j->lo; r < j->hi; ++r) {
+    BestState st;
+    uint32_t len = (uint32_t)(j->offs[r + 1] - j->offs[r]);
+    bool ok = map_read_se(W, ix2, cv, j->e->p3, cfg, j->seqs + j->offs[r], len, j->ag != 0, j->m, sc,
+                          cached, st, ctr);
+    if (lane == 0) {
+      if (!ok) *j->bad = 1;
+      j->out[r].genome_pos = st.pos; j->out[r].times = st.times; j->out[r].mismatch = st.mm;
+      j->out[r].strand = (char)st.strand; memset(j->out[r].pad, 0, 3);
+    }
+  }
+  if (lane == 0) { *j->ctr = ctr; }
+}
+
+struct PeJob {
+  const EmuEngine* e; const char* seqs; const uint64_t* offs; uint32_t lo, hi;
+  int ag; uint32_t m, b, top_k; int literal; emu_cand* ranked; uint32_t* n_ranked; uint32_t max_len;
+  uint64_t* scratch; HeapEntry* heap; int* bad;
+};
+
+void pe_lane(WarpEmu* w, uint32_t lane, void* arg) {
+  PeJob* j = (PeJob*)arg;
+  EmuWarp W{w, lane};
+  SubIndexView ix2[2] = {j->e->sub[j->ag ? 2 : 0].view(), j->e->sub[j->ag ? 3 : 1].view()};
+  ChromView cv = j->e->cv();
+  MapConfig cfg; cfg.b = j->b; cfg.literal_all = j->literal;
+  const uint32_t nwmax = (j->max_len + 31) / 32;
+  ReadScratch sc = carve_scratch(j->scratch, nwmax ? nwmax : 1);
+  uint32_t cached = 0;
+  Counters ctr{0, 0, 0};
+  for (uint32_t r = j->lo; r < j->hi; ++r) {
+    uint32_t len = (uint32_t)(j->offs[r + 1] - j->offs[r]);
+    uint32_t hsize = 0;
+    bool ok = map_read_pe(W, ix2, cv, j->e->p3, cfg, j->seqs + j->offs[r], len, j->ag != 0, j->m,
+                          j->top_k, sc, cached, j->heap, hsize, ctr);
+    if (lane == 0) {
+      if (!ok) *j->bad = 1;
+      // drain, paired.cpp:684-692
+      uint32_t c = 0, sz = hsize;
+      while (sz) {
+        HeapEntry t = heap_pop(j->heap, sz);
+        emu_cand& o = j->ranked[(size_t)r * j->top_k + c++];
+        o.genome_pos = t.pos; o.mismatch = he_mm(t); o.strand = (t.mm_strand & 0x10000u) ? '-' : '+';
+        memset(o.pad, 0, 3);
+      }
+      j->n_ranked[r] = c;
+    }
+    W.sync();
+  }
+}
+
+template <class Job, class Fn>
+int run_parallel(uint32_t n, int threads, Fn make_and_run) {
+  if (threads < 1) threads = 1;
+  std::vector<std::thread> pool;
+  std::atomic<int> diverged{0};
+  for (int t = 0; t < threads; ++t) {
+    pool.emplace_back([&, t]() {
+      uint32_t lo = (uint32_t)((uint64_t)n * t / threads), hi = (uint32_t)((uint64_t)n * (t + 1) / threads);
+      if (lo >= hi) return;
+      WarpEmu* w = new WarpEmu;
+      g_current = w;
+      make_and_run(w, lo, hi);
+      if (w->diverged) diverged = 1;
+      delete w;
+    });
+  }
+  for (auto& th : pool) th.join();
+  return diverged.load();
+}
+
+}  // namespace
+
+extern "C" {
+
+// returns 0 ok; 1 = warp primitives diverged (bug); 5 = non-ACGT read
+int emu_map_se(void* h, const char* seqs, const uint64_t* offs, uint32_t n, int ag, uint32_t m,
+               uint32_t b, int literal, emu_best* out, int threads, uint64_t* counters3) {
+  EmuEngine* e = (EmuEngine*)h;
+  uint32_t max_len = 1;
+  for (uint32_t r = 0; r < n; ++r) max_len = std::max<uint32_t>(max_len, (uint32_t)(offs[r + 1] - offs[r]));
+  if (max_len > MAX_READ_LEN) return 1;
+  std::atomic<int> bad{0};
+  std::atomic<uint64_t> c0{0}, c1{0}, c2{0};
+  int div = run_parallel<SeJob>(n, threads, [&](WarpEmu* w, uint32_t lo, uint32_t hi) {
+    std::vector<uint64_t> scratch(scratch_words((max_len + 31) / 32) + 8);
+    uint32_t cached = 0; Counters ctr{0, 0, 0}; int b_ = 0;
+    SeJob j{e, seqs, offs, lo, hi, ag, m, b, literal, out, max_len, scratch.data(), &cached, &ctr, &b_};
+    w->run(se_lane, &j);
+    if (b_) bad = 1;
+    c0 += ctr.lookups; c1 += ctr.candidates; c2 += ctr.literal;
+  });
+  if (counters3) { counters3[0] = c0; counters3[1] = c1; counters3[2] = c2; }
+  if (div) return 1;
+  return bad ? 5 : 0;
+}
+
+int emu_map_pe_mate(void* h, const char* seqs, const uint64_t* offs, uint32_t n, int ag, uint32_t m,
+                    uint32_t b, uint32_t top_k, int literal, emu_cand* ranked, uint32_t* n_ranked,
+                    int threads) {
+  EmuEngine* e = (EmuEngine*)h;
+  uint32_t max_len = 1;
+  for (uint32_t r = 0; r < n; ++r) max_len = std::max<uint32_t>(max_len, (uint32_t)(offs[r + 1] - offs[r]));
+  if (max_len > MAX_READ_LEN) return 1;
+  std::atomic<int> bad{0};
+  int div = run_parallel<PeJob>(n, threads, [&](WarpEmu* w, uint32_t lo, uint32_t hi) {
+    std::vector<uint64_t> scratch(scratch_words((max_len + 31) / 32) + 8);
+    std::vector<HeapEntry> heap(top_k + 1);
+    int b_ = 0;
+    PeJob j{e, seqs, offs, lo, hi, ag, m, b, top_k, literal, ranked, n_ranked, max_len, scratch.data(), heap.data(), &b_};
+    w->run(pe_lane, &j);
+    if (b_) bad = 1;
+  });
+  if (div) return 1;
+  return bad ? 5 : 0;
+}
+
+// pairing == pair_kernel (one thread per pair)
+void emu_pair(void* h, const emu_cand* r1, const uint32_t* n1, const uint64_t* offs1,
+              const emu_cand* r2, const uint32_t* n2, const uint64_t* offs2, uint32_t n,
+              uint32_t top_k, uint32_t m, int frag_range, emu_pair* out) {
+  EmuEngine* e = (EmuEngine*)h;
+  ChromView cv = e->cv();
+  for (uint32_t p = 0; p < n; ++p) {
+    const emu_cand* a = r1 + (size_t)p * top_k;
+    const emu_cand* b = r2 + (size_t)p * top_k;
+    auto g1 = [a](uint32_t i) { RankedCand c; c.pos = a[i].genome_pos; c.mm = a[i].mismatch; c.strand = (uint8_t)a[i].strand; return c; };
+    auto g2 = [b](uint32_t i) { RankedCand c; c.pos = b[i].genome_pos; c.mm = b[i].mismatch; c.strand = (uint8_t)b[i].strand; return c; };
+    // pair_candidates takes one functor type; wrap through a common lambda type
+    struct Get { const emu_cand* p; RankedCand operator()(uint32_t i) const { RankedCand c; c.pos = p[i].genome_pos; c.mm = p[i].mismatch; c.strand = (uint8_t)p[i].strand; return c; } };
+    (void)g1; (void)g2;
+    PairResult r = pair_candidates(cv, Get{a}, n1[p], (uint32_t)(offs1[p + 1] - offs1[p]), Get{b}, n2[p],
+                                   (uint32_t)(offs2[p + 1] - offs2[p]), m, frag_range);
+    out[p].best_times = r.best_times; out[p].best_i = r.best_i; out[p].best_j = r.best_j; out[p].frag_len = r.frag;
+  }
+}
+
+}  // extern "C"

@@ -36,11 +36,13 @@ def make_repeat_genome(lengths, seed, n_families=20, fam_len=(300, 2000), copies
     fams = [_ACGT[rng.integers(0, 4, size=rng.integers(*fam_len))] for _ in range(n_families)]
     for _, seq in chroms:
         budget = int(len(seq) * repeat_frac)
-        while budget > 0:
+        guard = 0
+        while budget > 0 and guard < 10000:
+            guard += 1
             f = fams[rng.integers(0, n_families)]
+            if len(seq) <= len(f) + 1:
+                f = f[: max(1, len(seq) // 2)]
             for _ in range(rng.integers(*copies)):
-                if len(seq) <= len(f) + 1:
-                    break
                 p = rng.integers(0, len(seq) - len(f))
                 c = f.copy()
                 m = rng.random(len(c)) < divergence

@@ -1,0 +1,746 @@
+// walt_core.cuh -- lane-level mapping logic of the B200 engine.
+//
+// Everything here is written against a tiny "warp policy" W (lane id, ballot, shfl, sync) so
+// that the very same source is (a) the body of the sm_100a kernels in walt_engine.cu, where W
+// maps 1:1 onto the hardware warp intrinsics, and (b) steppable on a CPU by the test-only
+// fiber harness in tests/emu/ (32 cooperative fibers per emulated warp), which lets the
+// "-m 'not gpu'" suite exercise the kernel logic against the oracle without a device.  The
+// product library (libwaltb200.so) contains only instantiation (a).
+//
+// Data model (one strand sub-index, all in HBM):
+//   genome : 2 bits/base (A0 C1 G2 T3), 32 bases per 64-bit word, first base in the top bits,
+//            so that masked word compares are lexicographic; PAD_BASES zero bases in front
+//            and >= TAIL_PAD_WORDS zero words behind.
+//   index  : the .dbindex position array, verbatim (reference.cpp:302-322).
+//   table  : T[k] = first slot of `index` whose first `depth` seed characters, read as a
+//            base-3 number (3-letter alphabet), are >= k.  depth >= 12, so T restricted to
+//            12-character prefixes IS the reference's counter[] (reference.cpp:192-229).
+//   taint  : positions within 148 bases of a chromosome end.  The reference's per-character
+//            binary search (mapping.cpp:166-222) reads past chromosome ends while the bucket
+//            sort truncated there (reference.cpp:258-288), so for a lookup whose read matches
+//            such an entry's in-chromosome prefix the search is replayed literally.
+//
+// Reference semantics reproduced here: SingleEndMapping (mapping.cpp:224-316), IndexRegion
+// (mapping.cpp:198-222), getChromID (reference.cpp:43-60), the seed tables including their
+// two reachable typos (seedpattern.hpp:448-455), PairEndMapping (paired.cpp:106-201) and
+// TopCandidates with libstdc++ heap mechanics (paired.hpp:51-74).
+#pragma once
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define WALT_HD __host__ __device__ __forceinline__
+#define WALT_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define WALT_HD inline
+#define WALT_HD_NOINLINE
+#endif
+
+namespace waltcore {
+
+constexpr uint32_t KEY_WEIGHT = 12;      // F2SEEDKEYWEIGHT
+constexpr uint32_t MIN_READ_LEN = 38;    // MINIMALREADLEN
+constexpr uint32_t MIN_SEED_LEN = 36;    // MINIMALSEEDLEN
+constexpr uint32_t MAX_REPEATS = 50;     // mapping.cpp:238
+constexpr uint32_t PAD_BASES = 32;       // zero bases in front of the packed genome
+constexpr uint32_t MAX_READ_LEN = 1024;  // fgets(.., 1000, ..) bounds reads below this
+constexpr uint32_t MAX_WORDS = MAX_READ_LEN / 32;
+constexpr uint32_t TAIL_PAD_WORDS = MAX_WORDS + 8;
+constexpr uint32_t TAINT_SPAN = 148;     // largest probed offset: 3*49+1 (seed_len 50)
+constexpr uint32_t MAX_DEPTH = 20;
+constexpr uint32_t N_KEY12 = 531441;     // 3^12 reachable 12-mers of a 3-letter genome
+constexpr uint32_t BUCKET_ERASE = 500000;  // reference.cpp:212
+
+// ------------------------------------------------------------------------------------------
+// portable bit helpers
+// ------------------------------------------------------------------------------------------
+WALT_HD uint32_t popc64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__popcll(x);
+#else
+  return (uint32_t)__builtin_popcountll(x);
+#endif
+}
+WALT_HD uint32_t popc32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__popc(x);
+#else
+  return (uint32_t)__builtin_popcount(x);
+#endif
+}
+WALT_HD uint32_t brev32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __brev(x);
+#else
+  x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+  x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+  x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+  x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
+  return (x >> 16) | (x << 16);
+#endif
+}
+WALT_HD int ffs32(uint32_t x) {  // 1-based index of lowest set bit, 0 if none
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)x);
+#else
+  return __builtin_ffs((int)x);
+#endif
+}
+WALT_HD int clz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __clz((int)x);
+#else
+  return x ? __builtin_clz(x) : 32;
+#endif
+}
+// bit j of x -> bit 2j of the result
+WALT_HD uint64_t spread32(uint32_t v) {
+  uint64_t x = v;
+  x = (x | (x << 16)) & 0x0000FFFF0000FFFFull;
+  x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
+  x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full;
+  x = (x | (x << 2)) & 0x3333333333333333ull;
+  x = (x | (x << 1)) & 0x5555555555555555ull;
+  return x;
+}
+
+// ------------------------------------------------------------------------------------------
+// alphabet
+// ------------------------------------------------------------------------------------------
+// ASCII -> 2-bit code A0 C1 G2 T3 (util.hpp:107-121); valid only for A,C,G,T
+WALT_HD uint32_t ascii_code(uint32_t c) {
+  uint32_t x = (c >> 1) & 3u;
+  return x ^ (x >> 1);
+}
+WALT_HD bool ascii_is_acgt(uint32_t c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+// read conversion (mapping.cpp:142-164): C->T, or G->A under the A/G wildcard
+WALT_HD uint32_t convert_code(uint32_t code, bool ag) {
+  if (ag) return code == 2u ? 0u : code;
+  return code == 1u ? 3u : code;
+}
+// rank of a converted code inside its 3-letter alphabet: CT {A,G,T} / GA {A,C,T} -> 0,1,2
+WALT_HD uint32_t ternary_digit(uint32_t code, bool ag) {
+  return ag ? code - (code >> 1) : code - (code != 0u);
+}
+// base at padded position p (p already includes PAD_BASES)
+WALT_HD uint32_t packed_base(const uint64_t* __restrict__ words, uint64_t p) {
+  return (uint32_t)(words[p >> 5] >> (62u - 2u * (uint32_t)(p & 31u))) & 3u;
+}
+
+// ------------------------------------------------------------------------------------------
+// seed geometry
+// ------------------------------------------------------------------------------------------
+WALT_HD uint32_t seed_repeats(uint32_t read_len) {  // mapping.cpp:236-239
+  uint32_t r = (read_len - 2u) / 3u;
+  return r < MAX_REPEATS ? r : MAX_REPEATS;
+}
+// is read position p one of the seed's cared positions for shift s (p = s + 3i + 1, i < spr)
+WALT_HD bool is_seed_position(uint32_t p, uint32_t s, uint32_t spr) {
+  if (p < s + 1u) return false;
+  uint32_t d = p - s - 1u;
+  return (d % 3u == 0u) && (d / 3u < spr);
+}
+// is read position p compared by the verification loops (mapping.cpp:288-304).  Regular rule:
+// every position that is not a cared one; F2NOCAREDPOSITION[2] deviates at entries 47 and 95
+// (seedpattern.hpp:448-455): 60 instead of 70 (reached when 2*spr+2 > 47) and 141 instead of
+// 142 (reached when 2*spr+2 > 95).
+WALT_HD bool is_verify_position(uint32_t p, uint32_t s, uint32_t spr, uint32_t read_len) {
+  if (p >= read_len) return false;
+  bool v = !is_seed_position(p, s, spr);
+  if (s == 2u) {
+    if (spr >= 23u) { if (p == 70u) v = false; if (p == 60u) v = true; }
+    if (spr >= 47u) { if (p == 142u) v = false; if (p == 141u) v = true; }
+  }
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// views
+// ------------------------------------------------------------------------------------------
+struct SubIndexView {
+  const uint64_t* genome;      // packed, PAD_BASES in front
+  const uint32_t* index;
+  const uint32_t* table;       // 3^depth + 1 entries
+  const uint32_t* taint_bits;  // N_KEY12 bits
+  const uint32_t* taint_key;   // sorted 12-mer keys (base 3) of tainted positions
+  const uint32_t* taint_pos;   // their genome positions
+  const uint32_t* taint_len;   // chromosome end - position
+  uint32_t n_taint;
+  uint32_t index_size;
+  uint32_t depth;
+  uint32_t ag;                 // 1 for the G->A sub-indexes
+};
+
+struct ChromView {
+  const uint32_t* starts;      // n_chr + 1 prefix sums (reference.cpp:407-410)
+  uint32_t n_chr;
+  uint32_t genome_len;
+};
+
+struct Pow3 { uint32_t v[MAX_DEPTH + 1]; };
+
+// getChromID, reference.cpp:43-60
+WALT_HD uint32_t chrom_of(const uint32_t* __restrict__ starts, uint32_t n_chr, uint32_t pos) {
+  uint32_t l = 0, h = n_chr;
+  while (l < h) {
+    uint32_t m = (l + h + 1u) >> 1;
+    if (pos >= starts[m]) l = m; else h = m - 1u;
+  }
+  return l;
+}
+
+// Key of index entry `e` over its first `depth` seed characters as a base-3 number, with the
+// builder's truncation rule (characters at or beyond the chromosome end sort lowest,
+// reference.cpp:272-277) mapped to digit 0.  Monotone non-decreasing along `index`.
+WALT_HD uint32_t entry_table_key(const uint64_t* __restrict__ genome, uint32_t e, uint32_t chrom_end,
+                                 uint32_t depth, bool ag, const Pow3& p3) {
+  uint32_t avail = chrom_end - e;  // characters e .. chrom_end-1 exist
+  uint32_t key = 0;
+  for (uint32_t i = 0; i < depth; ++i) {
+    uint32_t off = 3u * i + 1u;
+    uint32_t d = 0;
+    if (off < avail) d = ternary_digit(packed_base(genome, (uint64_t)e + PAD_BASES + off), ag);
+    key += d * p3.v[depth - 1u - i];
+  }
+  return key;
+}
+
+// 12-mer key (base 3) of a genome position; used for the taint list
+WALT_HD uint32_t entry_key12(const uint64_t* __restrict__ genome, uint32_t e, bool ag, const Pow3& p3) {
+  uint32_t key = 0;
+  for (uint32_t i = 0; i < KEY_WEIGHT; ++i)
+    key += ternary_digit(packed_base(genome, (uint64_t)e + PAD_BASES + 3u * i + 1u), ag) * p3.v[KEY_WEIGHT - 1u - i];
+  return key;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-warp scratch (shared memory on the device)
+// ------------------------------------------------------------------------------------------
+// layout in 64-bit words: R[nw] | VM[3][nw] | SM[3][nw]
+struct ReadScratch {
+  uint64_t* R;    // converted read, packed like the genome (no pad)
+  uint64_t* VM;   // verification masks (low bit of each 2-bit field), per shift
+  uint64_t* SM;   // seed (cared position) masks, per shift
+  uint32_t nw;    // stride = words reserved per array
+};
+WALT_HD uint32_t scratch_words(uint32_t nw) { return 7u * nw; }
+WALT_HD ReadScratch carve_scratch(uint64_t* base, uint32_t nw) {
+  ReadScratch s;
+  s.R = base; s.VM = base + nw; s.SM = base + 4u * nw; s.nw = nw;
+  return s;
+}
+
+// Pack + convert one ASCII read into sc.R (warp-cooperative). Returns false (uniformly) if a
+// byte is not A/C/G/T.
+template <class W>
+WALT_HD bool load_read(W& w, const char* __restrict__ seq, uint32_t read_len, bool ag, ReadScratch& sc) {
+  const uint32_t lane = w.lane();
+  const uint32_t nw = (read_len + 31u) >> 5;
+  bool bad = false;
+  for (uint32_t k = 0; k < nw; ++k) {
+    uint32_t p = 32u * k + lane;
+    uint32_t code = 0;
+    if (p < read_len) {
+      uint32_t c = (uint8_t)seq[p];
+      bad |= !ascii_is_acgt(c);
+      code = convert_code(ascii_code(c), ag);
+    }
+    uint32_t hi = brev32(w.ballot((code & 2u) != 0u));
+    uint32_t lo = brev32(w.ballot((code & 1u) != 0u));
+    if (lane == 0) sc.R[k] = (spread32(hi) << 1) | spread32(lo);
+  }
+  bool any_bad = w.ballot(bad) != 0u;
+  w.sync();
+  return !any_bad;
+}
+
+// Verification / seed masks for every shift (depend on read_len only).
+template <class W>
+WALT_HD void build_masks(W& w, uint32_t read_len, ReadScratch& sc) {
+  const uint32_t lane = w.lane();
+  const uint32_t nw = (read_len + 31u) >> 5;
+  const uint32_t spr = seed_repeats(read_len);
+  for (uint32_t s = 0; s < 3u; ++s) {
+    for (uint32_t k = 0; k < nw; ++k) {
+      uint32_t p = 32u * k + lane;
+      uint32_t vm = brev32(w.ballot(is_verify_position(p, s, spr, read_len)));
+      uint32_t sm = brev32(w.ballot(is_seed_position(p, s, spr)));
+      if (lane == 0) {
+        sc.VM[s * sc.nw + k] = spread32(vm);
+        sc.SM[s * sc.nw + k] = spread32(sm);
+      }
+    }
+  }
+  w.sync();
+}
+
+// ------------------------------------------------------------------------------------------
+// candidate window compare (one lane, one candidate)
+// ------------------------------------------------------------------------------------------
+struct WindowResult {
+  uint32_t mismatches;  // over the verification mask
+  bool seed_equal;      // all cared positions equal
+};
+
+// genome window aligned with read position 0 at padded base position gp
+WALT_HD WindowResult compare_window(const uint64_t* __restrict__ genome, uint64_t gp,
+                                    const uint64_t* R, const uint64_t* VM, const uint64_t* SM,
+                                    uint32_t nw) {
+  const uint64_t* g = genome + (gp >> 5);
+  const uint32_t sh = 2u * (uint32_t)(gp & 31u);
+  uint64_t cur = g[0];
+  uint32_t mm = 0;
+  uint64_t sdiff = 0;
+  for (uint32_t k = 0; k < nw; ++k) {
+    uint64_t nxt = g[k + 1];
+    uint64_t gw = sh ? ((cur << sh) | (nxt >> (64u - sh))) : cur;
+    uint64_t x = gw ^ R[k];
+    uint64_t d = x | (x >> 1);
+    mm += popc64(d & VM[k]);
+    sdiff |= d & SM[k];
+    cur = nxt;
+  }
+  WindowResult r;
+  r.mismatches = mm;
+  r.seed_equal = (sdiff == 0);
+  return r;
+}
+
+// three-way compare of the entry's seed characters against the read's: <0 entry smaller
+WALT_HD int compare_seed(const uint64_t* __restrict__ genome, uint64_t gp, const uint64_t* R,
+                         const uint64_t* SM, uint32_t nws) {
+  const uint64_t* g = genome + (gp >> 5);
+  const uint32_t sh = 2u * (uint32_t)(gp & 31u);
+  uint64_t cur = g[0];
+  for (uint32_t k = 0; k < nws; ++k) {
+    uint64_t nxt = g[k + 1];
+    uint64_t gw = sh ? ((cur << sh) | (nxt >> (64u - sh))) : cur;
+    uint64_t m3 = SM[k] * 3ull;
+    uint64_t a = gw & m3, b = R[k] & m3;
+    if (a != b) return a < b ? -1 : 1;
+    cur = nxt;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// literal IndexRegion (mapping.cpp:166-222), executed redundantly by every lane
+// ------------------------------------------------------------------------------------------
+// genome character as the reference's raw byte read sees it, as an ordered code:
+// 0 past the end of the sequence (below 'A'), else 1 + 2-bit code (A<C<G<T).
+WALT_HD uint32_t literal_char(const uint64_t* __restrict__ genome, uint64_t pos, uint32_t genome_len) {
+  if (pos >= genome_len) return 0u;
+  return 1u + packed_base(genome, pos + PAD_BASES);
+}
+
+WALT_HD void literal_index_region(const SubIndexView& ix, uint32_t genome_len, const uint64_t* R,
+                                  uint32_t seed_i, uint32_t seed_len, uint32_t& first,
+                                  uint32_t& second) {
+  uint32_t l = first, u = second - 1u;
+  for (uint32_t p = KEY_WEIGHT; p < seed_len; ++p) {
+    const uint32_t cp = 3u * p + 1u;
+    const uint32_t ch = 1u + packed_base(R, seed_i + cp);
+    {  // LowerBound
+      uint32_t low = l, high = u;
+      while (low < high) {
+        uint32_t mid = low + (high - low) / 2u;
+        uint32_t c = literal_char(ix.genome, (uint64_t)ix.index[mid] + cp, genome_len);
+        if (c >= ch) high = mid; else low = mid + 1u;
+      }
+      l = low;
+    }
+    {  // UpperBound
+      uint32_t low = l, high = u;
+      while (low < high) {
+        uint32_t mid = low + (high - low + 1u) / 2u;
+        uint32_t c = literal_char(ix.genome, (uint64_t)ix.index[mid] + cp, genome_len);
+        if (c <= ch) low = mid; else high = mid - 1u;
+      }
+      u = low;
+    }
+    if (l == u && ch != literal_char(ix.genome, (uint64_t)ix.index[l] + cp, genome_len)) {
+      first = 1u; second = 0u;
+      return;
+    }
+  }
+  if (l > u) { first = 1u; second = 0u; return; }
+  first = l; second = u;
+}
+
+// ------------------------------------------------------------------------------------------
+// sinks: what happens to each verified candidate, in reference order
+// ------------------------------------------------------------------------------------------
+// SE: BestMatch fold, mapping.cpp:306-313 (state is warp-uniform)
+struct BestState {
+  uint32_t pos, times, mm;
+  uint32_t strand;  // '+' or '-'
+};
+
+struct Counters {
+  uint32_t lookups, candidates, literal;
+};
+
+template <class W>
+struct BestSink {
+  BestState st;
+  WALT_HD bool stop_before_shift(uint32_t seed_i) const {  // mapping.cpp:250-256
+    return (st.mm == 0u && seed_i >= 1u) || (st.mm == 1u && seed_i >= 2u);
+  }
+  // candidates of lanes (ascending) with valid set, in index order; g are distinct per lookup
+  WALT_HD void consume(W& w, bool valid, uint32_t mm, uint32_t g, uint32_t strand) {
+    uint32_t below = w.ballot(valid && mm < st.mm);
+    uint32_t equal = w.ballot(valid && mm == st.mm);
+    if (below) {
+      // the minimum decides; every earlier improvement is overwritten by the first minimum
+      uint32_t mn = mm;
+      if (!(valid && mm < st.mm)) mn = 0xFFFFFFFFu;
+      mn = w.reduce_min(mn);
+      uint32_t e = w.ballot(valid && mm == mn);
+      int last = 31 - clz32(e);
+      st.pos = w.shfl(g, last);
+      st.times = popc32(e);
+      st.mm = mn;
+      st.strand = strand;
+    } else if (equal) {
+      int first = ffs32(equal) - 1;
+      int last = 31 - clz32(equal);
+      uint32_t g_first = w.shfl(g, first);
+      uint32_t g_last = w.shfl(g, last);
+      uint32_t acc = popc32(equal) - (g_first == st.pos ? 1u : 0u);
+      if (acc) { st.pos = g_last; st.strand = strand; st.times += acc; }
+    }
+  }
+};
+
+// PE: TopCandidates (paired.hpp:51-74) with libstdc++'s heap (stl_heap.h:135-147,224-267).
+// The heap lives in memory owned by the warp; lane 0 mutates it.
+struct HeapEntry { uint32_t pos; uint32_t mm_strand; };  // mm in the low 16 bits, strand bit 16
+WALT_HD uint32_t he_mm(const HeapEntry& e) { return e.mm_strand & 0xFFFFu; }
+
+WALT_HD void heap_sift_up(HeapEntry* a, uint32_t hole, uint32_t top, HeapEntry v) {
+  while (hole > top) {
+    uint32_t parent = (hole - 1u) >> 1;
+    if (!(he_mm(a[parent]) < he_mm(v))) break;
+    a[hole] = a[parent];
+    hole = parent;
+  }
+  a[hole] = v;
+}
+WALT_HD void heap_adjust(HeapEntry* a, uint32_t hole, uint32_t len, HeapEntry v) {
+  const uint32_t top = hole;
+  uint32_t child = hole;
+  while (len >= 2u && child < (len - 1u) / 2u) {
+    child = 2u * (child + 1u);
+    if (he_mm(a[child]) < he_mm(a[child - 1u])) --child;
+    a[hole] = a[child];
+    hole = child;
+  }
+  if ((len & 1u) == 0u && len >= 2u && child == (len - 2u) / 2u) {
+    child = 2u * (child + 1u);
+    a[hole] = a[child - 1u];
+    hole = child - 1u;
+  }
+  heap_sift_up(a, hole, top, v);
+}
+WALT_HD void heap_push_bounded(HeapEntry* a, uint32_t& size, uint32_t cap, HeapEntry v) {
+  if (size < cap) {
+    a[size] = v; ++size;
+    heap_sift_up(a, size - 1u, 0u, v);
+  } else if (he_mm(v) < he_mm(a[0])) {
+    uint32_t n = size;
+    if (n > 1u) { HeapEntry last = a[n - 1u]; a[n - 1u] = a[0]; heap_adjust(a, 0u, n - 1u, last); }
+    a[n - 1u] = v;
+    heap_sift_up(a, n - 1u, 0u, v);
+  }
+}
+WALT_HD HeapEntry heap_pop(HeapEntry* a, uint32_t& size) {
+  HeapEntry top = a[0];
+  uint32_t n = size;
+  if (n > 1u) { HeapEntry last = a[n - 1u]; a[n - 1u] = a[0]; heap_adjust(a, 0u, n - 1u, last); }
+  size = n - 1u;
+  return top;
+}
+
+template <class W>
+struct HeapSink {
+  HeapEntry* heap;     // capacity cap, visible to the whole warp
+  uint32_t size;       // warp-uniform copy
+  uint32_t cap;
+  uint32_t top_mm;     // warp-uniform copy of heap[0].mm (valid if size > 0)
+  uint32_t max_mm;
+  WALT_HD bool stop_before_shift(uint32_t seed_i) const {  // paired.cpp:127-137
+    bool full = size > 0u && size >= cap;
+    return full && ((top_mm == 0u && seed_i >= 1u) || (top_mm == 1u && seed_i >= 2u));
+  }
+  WALT_HD void consume(W& w, bool valid, uint32_t mm, uint32_t g, uint32_t strand) {
+    uint32_t take = w.ballot(valid && mm <= max_mm);
+    if (!take) return;
+    // pushes must happen one by one in lane order; lane 0 owns the heap
+    while (take) {
+      int src = ffs32(take) - 1;
+      take &= take - 1u;
+      uint32_t cg = w.shfl(g, src);
+      uint32_t cm = w.shfl(mm, src);
+      if (w.lane() == 0u) {
+        HeapEntry v; v.pos = cg; v.mm_strand = cm | (strand == '-' ? 0x10000u : 0u);
+        heap_push_bounded(heap, size, cap, v);
+      }
+    }
+    w.sync();
+    size = w.shfl(size, 0);
+    uint32_t t = 0;
+    if (w.lane() == 0u && size) t = he_mm(heap[0]);
+    top_mm = w.shfl(t, 0);
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// one seed lookup: table -> region -> candidates, fed to the sink in reference order
+// ------------------------------------------------------------------------------------------
+struct MapConfig {
+  uint32_t b;            // -b
+  uint32_t literal_all;  // test hook: replay IndexRegion literally for every lookup
+};
+
+// Is there a tainted entry in this 12-mer bucket whose in-chromosome seed characters all
+// match the read (so that the reference's search would look at its out-of-chromosome bytes)?
+template <class W>
+WALT_HD bool lookup_is_affected(W& w, const SubIndexView& ix, const uint64_t* R, uint32_t seed_i,
+                                uint32_t seed_len, uint32_t key12) {
+  // first taint slot with key >= key12 (uniform binary search)
+  uint32_t lo = 0, hi = ix.n_taint;
+  while (lo < hi) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (ix.taint_key[mid] < key12) lo = mid + 1u; else hi = mid;
+  }
+  const uint32_t lane = w.lane();
+  bool affected = false;
+  for (uint32_t t = lo; t < ix.n_taint && ix.taint_key[t] == key12; ++t) {
+    uint32_t avail = ix.taint_len[t];
+    uint32_t n_in = (avail + 1u) / 3u;  // seed characters with 3i+1 < avail
+    if (n_in >= seed_len) continue;     // every probed character is inside the chromosome
+    uint32_t e = ix.taint_pos[t];
+    bool differ = false;
+    for (uint32_t i = KEY_WEIGHT + lane; i < n_in; i += 32u) {
+      uint32_t off = 3u * i + 1u;
+      differ |= packed_base(ix.genome, (uint64_t)e + PAD_BASES + off) != packed_base(R, seed_i + off);
+    }
+    if (w.ballot(differ) == 0u) affected = true;
+  }
+  return affected;
+}
+
+template <class W, class Sink>
+WALT_HD void seed_lookup(W& w, const SubIndexView& ix, const ChromView& cv, const Pow3& p3,
+                         const MapConfig& cfg, const ReadScratch& sc, uint32_t read_len,
+                         uint32_t seed_i, uint32_t strand, Sink& sink, Counters& ctr) {
+  const uint32_t lane = w.lane();
+  const uint32_t spr = seed_repeats(read_len);
+  const uint32_t seed_len = spr;
+  const uint32_t nw = (read_len + 31u) >> 5;
+  const uint32_t nws = (3u * spr + seed_i + 31u) >> 5;  // words that hold seed positions
+  const bool ag = ix.ag != 0u;
+  const uint64_t* R = sc.R;
+  const uint64_t* VM = sc.VM + seed_i * sc.nw;
+  const uint64_t* SM = sc.SM + seed_i * sc.nw;
+
+  // base-3 key of the first min(depth, seed_len) seed characters, and of the first 12
+  const uint32_t n_pref = ix.depth < seed_len ? ix.depth : seed_len;
+  uint32_t digit = 0;
+  if (lane < n_pref) digit = ternary_digit(packed_base(R, seed_i + 3u * lane + 1u), ag);
+  uint32_t lo_key = w.reduce_add(lane < n_pref ? digit * p3.v[ix.depth - 1u - lane] : 0u);
+  uint32_t key12 = w.reduce_add(lane < KEY_WEIGHT ? digit * p3.v[KEY_WEIGHT - 1u - lane] : 0u);
+  uint32_t hi_key = lo_key + p3.v[ix.depth - n_pref];
+
+  // reference: counter[h] == counter[h+1] -> continue (mapping.cpp:268-272)
+  const uint32_t k12_span = p3.v[ix.depth - KEY_WEIGHT];
+  const uint32_t bucket_lo = ix.table[key12 * k12_span];
+  const uint32_t bucket_hi = ix.table[(key12 + 1u) * k12_span];
+  if (bucket_lo == bucket_hi) return;
+  ctr.lookups++;
+
+  bool literal = cfg.literal_all != 0u;
+  if (!literal && ((ix.taint_bits[key12 >> 5] >> (key12 & 31u)) & 1u))
+    literal = lookup_is_affected(w, ix, R, seed_i, seed_len, key12);
+
+  uint32_t first, last_excl;  // candidate slots [first, last_excl)
+  bool need_seed_check = false;
+  if (literal) {
+    ctr.literal++;
+    uint32_t f = bucket_lo, s = bucket_hi;
+    literal_index_region(ix, cv.genome_len, R, seed_i, seed_len, f, s);
+    if (s - f + 1u > cfg.b) return;      // mapping.cpp:275-277 (u32 arithmetic; (1,0) -> 0)
+    if (f > s) return;                   // failed search: empty candidate loop
+    first = f; last_excl = s + 1u;
+  } else {
+    uint32_t lo = ix.table[lo_key], hi = ix.table[hi_key];
+    if (lo == hi) return;
+    if (hi - lo <= 32u) {
+      first = lo; last_excl = hi; need_seed_check = true;
+    } else {
+      // warp-wide 33-ary lower bound, then upper bound, on whole-seed compares
+      uint32_t l = lo, h = hi;
+      while (h - l > 32u) {
+        uint32_t p = l + (uint32_t)(((uint64_t)(lane + 1u) * (h - l)) / 33u);
+        int c = compare_seed(ix.genome, (uint64_t)ix.index[p] + PAD_BASES - seed_i, R, SM, nws);
+        uint32_t cnt = popc32(w.ballot(c < 0));
+        uint32_t nl = cnt ? w.shfl(p, (int)cnt - 1) + 1u : l;
+        uint32_t nh = cnt < 32u ? w.shfl(p, (int)(cnt & 31u)) : h;
+        l = nl; h = nh;
+      }
+      {
+        bool lt = false;
+        if (l + lane < h)
+          lt = compare_seed(ix.genome, (uint64_t)ix.index[l + lane] + PAD_BASES - seed_i, R, SM, nws) < 0;
+        first = l + popc32(w.ballot(lt));
+      }
+      l = first; h = hi;
+      while (h - l > 32u) {
+        uint32_t p = l + (uint32_t)(((uint64_t)(lane + 1u) * (h - l)) / 33u);
+        int c = compare_seed(ix.genome, (uint64_t)ix.index[p] + PAD_BASES - seed_i, R, SM, nws);
+        uint32_t cnt = popc32(w.ballot(c <= 0));
+        uint32_t nl = cnt ? w.shfl(p, (int)cnt - 1) + 1u : l;
+        uint32_t nh = cnt < 32u ? w.shfl(p, (int)(cnt & 31u)) : h;
+        l = nl; h = nh;
+      }
+      {
+        bool le = false;
+        if (l + lane < h)
+          le = compare_seed(ix.genome, (uint64_t)ix.index[l + lane] + PAD_BASES - seed_i, R, SM, nws) <= 0;
+        last_excl = l + popc32(w.ballot(le));
+      }
+      if (last_excl <= first) return;
+      if (last_excl - first > cfg.b) return;
+    }
+  }
+
+  for (uint32_t base = first; base < last_excl; base += 32u) {
+    const uint32_t slot = base + lane;
+    bool valid = slot < last_excl;
+    uint32_t g = 0, mm = 0;
+    bool seed_eq = false;
+    if (valid) {
+      const uint32_t e = ix.index[slot];
+      WindowResult r = compare_window(ix.genome, (uint64_t)e + PAD_BASES - seed_i, R, VM, SM, nw);
+      mm = r.mismatches;
+      seed_eq = r.seed_equal;
+      // bounds, mapping.cpp:281-286 (all uint32 arithmetic, as the reference)
+      const uint32_t chr = chrom_of(cv.starts, cv.n_chr, e);
+      g = e - seed_i;
+      valid = (e - cv.starts[chr] >= seed_i) && !(g + read_len >= cv.starts[chr + 1u]);
+    }
+    if (need_seed_check) {
+      // single-chunk scan: the region is the set of seed-equal slots (contiguous)
+      uint32_t match = w.ballot(slot < last_excl && seed_eq);
+      if (popc32(match) > cfg.b) return;
+      valid = valid && seed_eq;
+    }
+    ctr.candidates += popc32(w.ballot(valid));
+    sink.consume(w, valid, mm, g, strand);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// whole reads
+// ------------------------------------------------------------------------------------------
+// SingleEndMapping for both strand passes of one read (mapping.cpp:486-500 order: all shifts
+// on the '+' sub-index, then all shifts on the '-' sub-index, state carried across).
+// Returns false if the read holds a non-ACGT byte.
+template <class W>
+WALT_HD bool map_read_se(W& w, const SubIndexView* ix2, const ChromView& cv, const Pow3& p3,
+                         const MapConfig& cfg, const char* seq, uint32_t read_len, bool ag,
+                         uint32_t max_mismatches, ReadScratch& sc, uint32_t& cached_len,
+                         BestState& out, Counters& ctr) {
+  BestSink<W> sink;
+  sink.st.pos = 0u; sink.st.times = 0u; sink.st.mm = max_mismatches; sink.st.strand = '+';
+  out = sink.st;
+  if (read_len < MIN_READ_LEN) return true;
+  if (!load_read(w, seq, read_len, ag, sc)) return false;
+  if (cached_len != read_len) { build_masks(w, read_len, sc); cached_len = read_len; }
+  for (uint32_t s = 0; s < 2u; ++s) {
+    const uint32_t strand = s ? '-' : '+';
+    for (uint32_t seed_i = 0; seed_i < 3u; ++seed_i) {
+      if (sink.stop_before_shift(seed_i)) break;
+      seed_lookup(w, ix2[s], cv, p3, cfg, sc, read_len, seed_i, strand, sink, ctr);
+    }
+  }
+  out = sink.st;
+  w.sync();  // scratch is reused by the next read
+  return true;
+}
+
+// PairEndMapping for both strand passes of one mate (paired.cpp:650-671); the heap persists
+// across the two passes.  On return heap[0..size) is the libstdc++ heap array.
+template <class W>
+WALT_HD bool map_read_pe(W& w, const SubIndexView* ix2, const ChromView& cv, const Pow3& p3,
+                         const MapConfig& cfg, const char* seq, uint32_t read_len, bool ag,
+                         uint32_t max_mismatches, uint32_t top_k, ReadScratch& sc,
+                         uint32_t& cached_len, HeapEntry* heap, uint32_t& heap_size, Counters& ctr) {
+  HeapSink<W> sink;
+  sink.heap = heap; sink.size = 0u; sink.cap = top_k; sink.top_mm = 0u; sink.max_mm = max_mismatches;
+  heap_size = 0u;
+  if (read_len < MIN_READ_LEN) return true;
+  if (!load_read(w, seq, read_len, ag, sc)) return false;
+  if (cached_len != read_len) { build_masks(w, read_len, sc); cached_len = read_len; }
+  for (uint32_t s = 0; s < 2u; ++s) {
+    const uint32_t strand = s ? '-' : '+';
+    for (uint32_t seed_i = 0; seed_i < 3u; ++seed_i) {
+      if (sink.stop_before_shift(seed_i)) break;
+      seed_lookup(w, ix2[s], cv, p3, cfg, sc, read_len, seed_i, strand, sink, ctr);
+    }
+  }
+  heap_size = sink.size;
+  w.sync();
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// pairing (MergePairedEndResults loop, paired.cpp:472-513) -- one lane per pair
+// ------------------------------------------------------------------------------------------
+struct RankedCand { uint32_t pos; uint32_t mm; uint32_t strand; };
+
+WALT_HD void forward_position(const uint32_t* __restrict__ starts, uint32_t pos, uint32_t strand,
+                              uint32_t chr, uint32_t read_len, uint32_t& s, uint32_t& e) {
+  // ForwardChromPosition, paired.cpp:98-104 (length[chr] = starts[chr+1]-starts[chr])
+  uint32_t v = pos - starts[chr];
+  if (strand != '+') v = (starts[chr + 1u] - starts[chr]) - v - read_len;
+  s = v; e = v + read_len;
+}
+
+struct PairResult { uint32_t best_times; int32_t best_i, best_j; int32_t frag; };
+
+template <class GetCand>
+WALT_HD PairResult pair_candidates(const ChromView& cv, GetCand get1, uint32_t n1, uint32_t len1,
+                                   GetCand get2, uint32_t n2, uint32_t len2,
+                                   uint32_t max_mismatches, int32_t frag_range) {
+  PairResult r; r.best_times = 0u; r.best_i = -1; r.best_j = -1; r.frag = 0;
+  uint32_t min_mm = max_mismatches;
+  uint64_t best_pos = 0;
+  for (int32_t i = (int32_t)n1 - 1; i >= 0; --i) {
+    const RankedCand a = get1((uint32_t)i);
+    const uint32_t c1 = chrom_of(cv.starts, cv.n_chr, a.pos);
+    uint32_t s1, e1;
+    forward_position(cv.starts, a.pos, a.strand, c1, len1, s1, e1);
+    for (int32_t j = (int32_t)n2 - 1; j >= 0; --j) {
+      const RankedCand bb = get2((uint32_t)j);
+      if (a.strand == bb.strand) continue;
+      const uint32_t sum = a.mm + bb.mm;
+      if (sum > min_mm) break;
+      const uint32_t c2 = chrom_of(cv.starts, cv.n_chr, bb.pos);
+      if (c1 != c2) continue;
+      uint32_t s2, e2;
+      forward_position(cv.starts, bb.pos, bb.strand, c2, len2, s2, e2);
+      const int32_t frag = a.strand == '+' ? (int32_t)(e2 - s1) : (int32_t)(e1 - s2);
+      if (frag <= 0 || frag > frag_range) continue;
+      const uint64_t cur = ((uint64_t)a.pos << 32) + bb.pos;
+      if (sum < min_mm) {
+        r.best_i = i; r.best_j = j; r.best_times = 1u; min_mm = sum; best_pos = cur; r.frag = frag;
+      } else if (sum == min_mm && cur != best_pos) {
+        r.best_i = i; r.best_j = j; r.best_times++; r.frag = frag;
+      }
+    }
+  }
+  return r;
+}
+
+}  // namespace waltcore

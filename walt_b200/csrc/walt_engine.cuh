@@ -1,0 +1,80 @@
+// walt_engine.cuh -- internal declarations shared by walt_engine.cu / walt_builder.cu.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/walt_b200.h"
+#include "walt_core.cuh"
+
+namespace waltb200 {
+
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define WALT_CUDA_TRY(expr)                                                                  \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      return ::waltb200::fail(WALT_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+// one strand sub-index resident in HBM
+struct DeviceSubIndex {
+  bool loaded = false;
+  uint64_t* genome = nullptr;     // packed words incl. front/tail pad
+  uint64_t genome_words = 0;
+  uint32_t* index = nullptr;
+  uint32_t index_size = 0;
+  uint32_t* table = nullptr;
+  uint32_t depth = 0;
+  uint32_t* taint_bits = nullptr;
+  uint32_t* taint_key = nullptr;
+  uint32_t* taint_pos = nullptr;
+  uint32_t* taint_len = nullptr;
+  uint32_t n_taint = 0;
+  uint32_t* counter = nullptr;    // optional 4^12+1 copy (kept by the builder for export)
+  uint64_t bytes = 0;
+  waltcore::SubIndexView view(int which) const;
+};
+
+struct BatchSlot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  char* d_seqs = nullptr;      size_t seqs_cap = 0;
+  uint64_t* d_offs = nullptr;  size_t offs_cap = 0;   // entries
+  void* d_out = nullptr;       size_t out_cap = 0;    // bytes
+};
+
+}  // namespace waltb200
+
+struct walt_engine {
+  int device = 0;
+  int sm_count = 0;
+  uint32_t n_chr = 0;
+  uint32_t genome_len = 0;
+  std::vector<uint32_t> lengths, starts;
+  std::vector<std::string> names;
+  std::vector<const char*> name_ptrs;
+  uint32_t* d_starts = nullptr;
+  waltb200::DeviceSubIndex sub[4];
+  waltcore::Pow3 pow3;
+  int search_mode = 0;
+  waltb200::BatchSlot slot[2];
+  uint32_t* d_flags = nullptr;     // [0] non-ACGT flag, [1..] spare
+  unsigned long long* d_counters = nullptr;  // lookups, candidates, literal
+  walt_stats stats{};
+  // PE scratch
+  void* d_pe = nullptr; size_t pe_cap = 0;
+};
+
+namespace waltb200 {
+waltcore::ChromView chrom_view(const walt_engine* e);
+int ensure_device(walt_engine* e);
+// after genome+index are resident: choose depth, build table and taint list
+int finalize_subindex(walt_engine* e, int which);
+int alloc_packed_genome(walt_engine* e, DeviceSubIndex& s);
+}  // namespace waltb200
