@@ -1,0 +1,84 @@
+"""walt_core.cuh (the kernels' lane-level source) stepped on the CPU fiber harness
+(tests/emu) against the golden vectors: table search, taint handling, ordered folds, heap and
+pairing logic, all without a device."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import goldenio
+import refio
+from emu import emu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    hdr, subs = goldenio.genome()
+    e = emu.EmuEngine(hdr.lengths)
+    for w, sfx in enumerate(refio.SUFFIXES):
+        assert e.load(w, subs[sfx].seq, subs[sfx].index) == 0
+    yield e
+    e.close()
+
+
+def _cmp_best(got, want):
+    for f in ("genome_pos", "times", "mismatch", "strand"):
+        bad = np.nonzero(got[f] != want[f])[0]
+        assert bad.size == 0, (f, bad[:5], got[bad[:5]], want[bad[:5]])
+
+
+@pytest.mark.parametrize("literal", [False, True])
+def test_se_emu_matches_reference(engine, literal):
+    for name, ag in (("se_ct.npz", False), ("se_ga.npz", True)):
+        z = goldenio.load(name)
+        buf, offs = refio.pack_reads(z["reads"])
+        for key in [k for k in z.files if k.startswith("best_")]:
+            m, b = (int(x[1:]) for x in key[5:].split("_"))
+            rc, out, _ = engine.map_se(buf, offs, refio.BEST_DT, ag=ag, m=m, b=b, literal=literal)
+            assert rc == 0
+            _cmp_best(out, z[key])
+
+
+@pytest.mark.parametrize("depth", [0, 12, 13, 16])
+def test_se_edge_emu(depth):
+    hdr, subs = goldenio.genome()
+    e = emu.EmuEngine(hdr.lengths)
+    for w, sfx in enumerate(refio.SUFFIXES):
+        assert e.load(w, subs[sfx].seq, subs[sfx].index, force_depth=depth) == 0
+    z = goldenio.load("se_edge.npz")
+    for ag, pre in ((False, "ct_best_"), (True, "ga_best_")):
+        for key in [k for k in z.files if k.startswith(pre)]:
+            m, b = (int(x[1:]) for x in key[len(pre):].split("_"))
+            rc, out, _ = e.map_se(z["buf"], z["offs"], refio.BEST_DT, ag=ag, m=m, b=b)
+            assert rc == 0
+            _cmp_best(out, z[key])
+    e.close()
+
+
+def test_pe_emu_matches_reference(engine):
+    hdr, _ = goldenio.genome()
+    z = goldenio.load("pe.npz")
+    L = refio.oracle_lib()
+    starts = np.ascontiguousarray(hdr.start_index, np.uint32)
+    lengths = np.ascontiguousarray(hdr.lengths, np.uint32)
+    chroms = refio.WoChroms(len(lengths), starts.ctypes.data, lengths.ctypes.data)
+    for m, k in ((6, 50), (8, 3), (4, 2)):
+        got = {}
+        for mate, ag in ((1, False), (2, True)):
+            buf, offs = refio.pack_reads(z[f"m{mate}"])
+            rc, ranked, sizes = engine.map_pe_mate(buf, offs, refio.CAND_DT, ag, m=m, top_k=k)
+            assert rc == 0
+            assert np.array_equal(sizes, z[f"sizes{mate}_m{m}_k{k}"])
+            want = z[f"ranked{mate}_m{m}_k{k}"]
+            for f in ("genome_pos", "mismatch", "strand"):
+                assert np.array_equal(ranked[f], want[f]), (m, k, mate, f)
+            got[mate] = (ranked, sizes, offs)
+        # pairing vs the oracle's MergePairedEndResults loop
+        pr = engine.pair(got[1][0], got[1][1], got[1][2], got[2][0], got[2][1], got[2][2], k, m, 500)
+        for j in range(len(pr)):
+            bi, bj = C.c_int32(-1), C.c_int32(-1)
+            r1 = np.ascontiguousarray(got[1][0][j]); r2 = np.ascontiguousarray(got[2][0][j])
+            t = L.wo_pe_pair(C.byref(chroms), r1.ctypes.data_as(C.c_void_p), C.c_uint32(int(got[1][1][j])),
+                             C.c_uint32(100), r2.ctypes.data_as(C.c_void_p), C.c_uint32(int(got[2][1][j])),
+                             C.c_uint32(100), C.c_uint32(m), C.c_int(500), C.byref(bi), C.byref(bj))
+            assert (t, bi.value, bj.value) == (pr[j]["best_times"], pr[j]["best_i"], pr[j]["best_j"]), j
