@@ -89,7 +89,8 @@ int walt_engine_load_dbindex(walt_engine* e, const char* dbindex_path, uint32_t 
 
 /* Same residency from caller memory (one sub-index per call): what ReadIndex would have
  * put into Genome/HashTable.  `sequence` is the converted ASCII genome of that sub-index. */
-int walt_engine_set_chromosomes(walt_engine* e, uint32_t n_chr, const uint32_t* lengths);
+int walt_engine_set_chromosomes(walt_engine* e, uint32_t n_chr, const uint32_t* lengths,
+                                const char* const* names /* may be NULL */);
 int walt_engine_load_subindex(walt_engine* e, int which, const char* sequence,
                               const uint32_t* counter /* 4^12+1 */, const uint32_t* index,
                               uint32_t index_size);
@@ -98,6 +99,10 @@ int walt_engine_load_subindex(walt_engine* e, int which, const char* sequence,
 int walt_engine_chromosomes(const walt_engine* e, uint32_t* n_chr, const uint32_t** lengths,
                             const uint32_t** start_index, const char* const** names);
 uint64_t walt_engine_hbm_bytes(const walt_engine* e);
+/* Residency facts of one sub-index: entries of index[], depth of the base-3 prefix table that
+ * supersedes counter[], number of positions within 148 bases of a chromosome end. */
+int walt_engine_subindex_info(const walt_engine* e, int which, uint32_t* index_size, uint32_t* depth,
+                              uint32_t* n_taint);
 
 /* ---- single-end mapping ---------------------------------------------------------------
  * Replaces both strand passes of mapping.cpp:486-500 for one batch: out[j] is what
@@ -132,34 +137,37 @@ int walt_engine_last_stats(const walt_engine* e, walt_stats* out);
 /* Test hook: 0 = table-driven search (default), 1 = literal IndexRegion emulation for every
  * lookup (the in-repo device oracle; same results, slower). */
 int walt_engine_set_search_mode(walt_engine* e, int mode);
+/* Tuning/test hooks: prefix-table depth for sub-indexes loaded afterwards (0 = auto, else
+ * 12..20) and the number of reads per double-buffered host chunk (default 2^20). */
+int walt_engine_set_table_depth(walt_engine* e, int depth);
+int walt_engine_set_chunk_reads(walt_engine* e, uint32_t n);
 
 /* ---- pinned host memory for batch buffers --------------------------------------------- */
 void* walt_host_alloc(size_t bytes);
 void walt_host_free(void* p);
 
-/* ---- index builder (makedb) -----------------------------------------------------------
- * Replaces BuildIndex x4 + WriteIndexHeadInfo (makedb.cpp:46-85,144-159): counting,
- * bucketing and bucket sorting run on the GPU; the files written are the reference's
- * format (reference.cpp:302-322,353-379).  `sequence` is the concatenated upper-case ACGT
- * genome (N already replaced by the caller, as ReadGenome does). */
-int walt_makedb_write(int device, uint32_t n_chr, const char* const* names, const uint32_t* lengths,
-                      const char* sequence, const char* out_dbindex_path);
+/* ---- index construction on the device (makedb) -------------------------------------------
+ * Replaces BuildIndex (makedb.cpp:46-85; reference.cpp:131-300): reverse complement,
+ * C->T / G->A conversion, bucket counting with the ">= 500000" erasure, bucketing and bucket
+ * sorting all run on the GPU and leave the requested sub-indexes resident in the engine.
+ * The forward genome is 2 bits/base (A0 C1 G2 T3), 32 bases per 64-bit word, first base in
+ * the top bits, one zero word in front; a buffer holds walt_packed_genome_bytes(n) bytes. */
+uint64_t walt_packed_genome_bytes(uint64_t n_bases);
+int walt_pack_genome_device(int device, const char* sequence /* upper-case ACGT */, uint64_t n_bases,
+                            void* d_packed_out);
+int walt_engine_build_from_device_genome(walt_engine* e, const void* d_packed_genome, uint32_t which_mask);
+int walt_engine_build_from_sequence(walt_engine* e, const char* sequence, uint32_t which_mask);
 
-/* Build the requested sub-indexes directly into an engine from a device-resident 2-bit
- * genome (32 bases per 64-bit word, first base in the top bits, A0 C1 G2 T3), no files. */
-int walt_engine_build_from_device_genome(walt_engine* e, uint32_t n_chr, const uint32_t* lengths,
-                                         const void* d_packed_genome, uint32_t which_mask);
-
-/* Export a resident sub-index back to host arrays in the reference's in-memory form
- * (ASCII converted genome, counter[4^12+1], index[index_size]); any pointer may be NULL. */
+/* Export a resident sub-index to host arrays in the reference's in-memory form (what ReadIndex
+ * fills, reference.cpp:324-351): converted ASCII genome, counter[4^12+1], index[index_size].
+ * Any pointer may be NULL. */
 int walt_engine_export_subindex(walt_engine* e, int which, char* sequence, uint32_t* counter,
                                 uint32_t* index, uint32_t* index_size);
 
-/* ---- synthetic workloads (bench only; SURVEY.md 8(d) shapes) --------------------------- */
+/* ---- synthetic workloads (bench only; SURVEY.md 8(d) shapes) ---------------------------- */
 int walt_synth_genome_device(int device, uint64_t n_bases, uint64_t seed, void* d_packed_out);
-int walt_synth_reads_device(int device, const void* d_packed_genome, uint32_t n_chr,
-                            const uint32_t* lengths, uint32_t n_reads, uint32_t read_len,
-                            uint64_t seed, int a_rich, void* d_seqs_out /* n*read_len ASCII */);
+int walt_synth_reads_device(walt_engine* e, const void* d_packed_genome, uint32_t n_reads, uint32_t read_len,
+                            uint64_t seed, int a_rich, void* d_seqs_out /* n_reads*read_len ASCII */);
 
 #ifdef __cplusplus
 }

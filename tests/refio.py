@@ -295,3 +295,34 @@ def ref_pe_mate(index_path, reads, ag, m=6, b=5000, top_k=50, threads=4):
     L.waltref_heaps_drain(heaps, C.c_uint32(n), C.c_uint32(top_k), _p(ranked), _p(sizes))
     L.waltref_heaps_free(heaps)
     return ranked, sizes
+
+
+# ----------------------------------------------------------------------------------------
+# in-memory index construction with the oracle's makedb restatement (reference.cpp:79-300)
+# ----------------------------------------------------------------------------------------
+_COMP = np.zeros(256, dtype=np.uint8)
+for _a, _b in zip(b"ACGT", b"TGCA"):
+    _COMP[_a] = _b
+
+
+def build_index_with_oracle(chroms):
+    """chroms: list of (name, uint8 ACGT array) -> (Header, {suffix: SubIndex}).  N's must
+    already be replaced (makedb does it with rand(); tests use N-free genomes here)."""
+    L = oracle_lib()
+    lengths = np.array([len(s) for _, s in chroms], dtype=np.uint32)
+    hdr = Header([n for n, _ in chroms], lengths, int(lengths.sum()), 0)
+    starts = np.ascontiguousarray(hdr.start_index, np.uint32)
+    fwd = np.concatenate([s for _, s in chroms])
+    rev = np.concatenate([_COMP[s[::-1]] for _, s in chroms])   # per chromosome, reference.cpp:131-146
+    subs = {}
+    for sfx, base, frm, to in (("_CT00", fwd, "C", "T"), ("_CT01", rev, "C", "T"),
+                               ("_GA10", fwd, "G", "A"), ("_GA11", rev, "G", "A")):
+        seq = base.copy()
+        seq[seq == ord(frm)] = ord(to)
+        counter = np.zeros(N_KEYS + 1, np.uint32)
+        index = np.zeros(max(1, hdr.genome_len), np.uint32)
+        n = L.wo_build_index(_p(seq), C.c_uint64(hdr.genome_len), C.c_uint32(len(lengths)), _p(starts),
+                             _p(counter), _p(index))
+        subs[sfx] = SubIndex("-" if sfx.endswith("1") else "+", seq, counter, index[:n].copy())
+        hdr.size_of_index = max(hdr.size_of_index, int(n))
+    return hdr, subs

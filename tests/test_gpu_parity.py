@@ -1,0 +1,217 @@
+"""GPU parity tests proper: the CUDA engine, called through the C ABI, against (a) the golden
+vectors produced by the unmodified reference and (b) the C oracle on fresh seeded inputs.
+Bit-exact: positions, strands, mismatch counts, times, heap contents and order."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import goldenio
+import refio
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _cmp_best(got, want, what=""):
+    for f in ("genome_pos", "times", "mismatch", "strand"):
+        bad = np.nonzero(got[f] != want[f])[0]
+        assert bad.size == 0, (what, f, bad[:5], got[bad[:5]], want[bad[:5]])
+
+
+def _load_golden_engine(depth=0):
+    import walt_b200
+    hdr, subs = goldenio.genome()
+    e = walt_b200.Engine(0)
+    if depth:
+        e.set_table_depth(depth)
+    e.set_chromosomes(hdr.lengths, hdr.names)
+    for w, sfx in enumerate(refio.SUFFIXES):
+        e.load_subindex(w, subs[sfx].seq, subs[sfx].counter, subs[sfx].index)
+    return e
+
+
+@pytest.fixture(scope="module")
+def engine():
+    e = _load_golden_engine()
+    yield e
+    e.close()
+
+
+def test_native_library_is_loaded(engine):
+    maps = open("/proc/self/maps").read()
+    assert "libwaltb200.so" in maps
+    assert engine.hbm_bytes() > 0
+    info = engine.subindex_info(0)
+    assert info["depth"] >= 12 and info["n_taint"] > 0
+
+
+@pytest.mark.parametrize("literal", [False, True])
+def test_se_golden(engine, literal):
+    engine.set_search_mode(literal)
+    try:
+        for name, ag in (("se_ct.npz", False), ("se_ga.npz", True)):
+            z = goldenio.load(name)
+            buf, offs = refio.pack_reads(z["reads"])
+            for key in [k for k in z.files if k.startswith("best_")]:
+                m, b = (int(x[1:]) for x in key[5:].split("_"))
+                out, short = engine.map_se(buf, offs, ag=ag, m=m, b=b)
+                _cmp_best(out, z[key], (name, key))
+                assert short == int(z[key.replace("best", "short")])
+                st = engine.stats()
+                assert st["n_kernel_launches"] >= 1 and st["n_lookups"] > 0
+                if literal:
+                    assert st["n_literal"] == st["n_lookups"]
+    finally:
+        engine.set_search_mode(False)
+
+
+@pytest.mark.parametrize("depth", [0, 12, 14, 17])
+def test_se_edge_golden(depth):
+    e = _load_golden_engine(depth)
+    z = goldenio.load("se_edge.npz")
+    for ag, pre in ((False, "ct_best_"), (True, "ga_best_")):
+        for key in [k for k in z.files if k.startswith(pre)]:
+            m, b = (int(x[1:]) for x in key[len(pre):].split("_"))
+            out, short = e.map_se(z["buf"], z["offs"], ag=ag, m=m, b=b)
+            _cmp_best(out, z[key], (depth, key))
+            assert short == int(z[key.replace("best", "short")])
+    e.close()
+
+
+def test_se_chunked_pipeline_matches_single_chunk(engine):
+    z = goldenio.load("se_ct.npz")
+    buf, offs = refio.pack_reads(z["reads"])
+    engine.set_chunk_reads(257)
+    try:
+        out, _ = engine.map_se(buf, offs, m=6, b=5000)
+    finally:
+        engine.set_chunk_reads(1 << 20)
+    _cmp_best(out, z["best_m6_b5000"])
+
+
+def test_se_empty_and_errors(engine):
+    import walt_b200
+    out, short = engine.map_se(np.zeros(1, np.uint8), np.zeros(1, np.uint64))
+    assert out.size == 0 and short == 0
+    buf, offs = refio.pack_reads([b"ACGTN" * 20])
+    with pytest.raises(walt_b200.WaltError) as ei:
+        engine.map_se(buf, offs)
+    assert ei.value.code == 5   # WALT_ENONACGT, util.hpp:117-120
+    # engine stays usable afterwards
+    z = goldenio.load("se_ct.npz")
+    buf, offs = refio.pack_reads(z["reads"][:50])
+    out, _ = engine.map_se(buf, offs)
+    _cmp_best(out, z["best_m6_b5000"][:50])
+
+
+def test_pe_golden(engine):
+    hdr, _ = goldenio.genome()
+    z = goldenio.load("pe.npz")
+    L = refio.oracle_lib()
+    starts = np.ascontiguousarray(hdr.start_index, np.uint32)
+    lengths = np.ascontiguousarray(hdr.lengths, np.uint32)
+    chroms = refio.WoChroms(len(lengths), starts.ctypes.data, lengths.ctypes.data)
+    b1, o1 = refio.pack_reads(z["m1"])
+    b2, o2 = refio.pack_reads(z["m2"])
+    for m, k in ((6, 50), (8, 3), (4, 2)):
+        for frag_range in (1000, 250):
+            r = engine.map_pe(b1, o1, b2, o2, m=m, top_k=k, frag_range=frag_range)
+            for mate in (1, 2):
+                assert np.array_equal(r[f"n{mate}"], z[f"sizes{mate}_m{m}_k{k}"])
+                want = z[f"ranked{mate}_m{m}_k{k}"]
+                for f in ("genome_pos", "mismatch", "strand"):
+                    assert np.array_equal(r[f"ranked{mate}"][f], want[f]), (m, k, mate, f)
+            pr = r["pairs"]
+            for j in range(len(pr)):
+                bi, bj = C.c_int32(-1), C.c_int32(-1)
+                r1 = np.ascontiguousarray(r["ranked1"][j]); r2 = np.ascontiguousarray(r["ranked2"][j])
+                t = L.wo_pe_pair(C.byref(chroms), r1.ctypes.data_as(C.c_void_p), C.c_uint32(int(r["n1"][j])),
+                                 C.c_uint32(100), r2.ctypes.data_as(C.c_void_p), C.c_uint32(int(r["n2"][j])),
+                                 C.c_uint32(100), C.c_uint32(m), C.c_int(frag_range), C.byref(bi), C.byref(bj))
+                assert (t, bi.value, bj.value) == (pr[j]["best_times"], pr[j]["best_i"], pr[j]["best_j"]), j
+
+
+def test_pe_pbat_is_mate_swap(engine):
+    z = goldenio.load("pe.npz")
+    b1, o1 = refio.pack_reads(z["m1"])
+    b2, o2 = refio.pack_reads(z["m2"])
+    a = engine.map_pe(b1, o1, b2, o2, m=6, top_k=10, frag_range=600)
+    s = engine.map_pe(b2, o2, b1, o1, m=6, top_k=10, frag_range=600, pbat=True)
+    assert np.array_equal(a["ranked1"], s["ranked2"]) and np.array_equal(a["ranked2"], s["ranked1"])
+    assert np.array_equal(a["pairs"]["best_i"], s["pairs"]["best_j"])
+    assert np.array_equal(a["pairs"]["best_times"], s["pairs"]["best_times"])
+
+
+def test_se_fresh_genome_vs_oracle():
+    """A bigger, freshly seeded case: index built by the oracle's makedb restatement, mapped
+    by the oracle and by the engine (default table depth and a forced shallow one)."""
+    import walt_b200
+    lengths = [400000, 250000, 90000, 1000, 37]
+    chroms = synth.make_repeat_genome(lengths, seed=101, n_families=10, fam_len=(200, 1500),
+                                      copies=(5, 40), divergence=0.02, repeat_frac=0.3)
+    hdr, subs = refio.build_index_with_oracle(chroms)
+    reads100 = synth.simulate_se_reads(chroms[:3], 20000, 100, seed=7, n_frac=0.0)
+    reads150a = synth.simulate_se_reads(chroms[:3], 10000, 150, seed=8, a_rich=True, n_frac=0.0)
+    for depth in (0, 13):
+        e = walt_b200.Engine(0)
+        e.set_table_depth(depth)
+        e.set_chromosomes(hdr.lengths, hdr.names)
+        for w, sfx in enumerate(refio.SUFFIXES):
+            e.load_subindex(w, subs[sfx].seq, subs[sfx].counter, subs[sfx].index)
+        for reads, ag, m, b in ((reads100, False, 6, 5000), (reads150a, True, 6, 5000), (reads100, False, 8, 20)):
+            want = refio.oracle_se_map(hdr, (subs["_GA10"], subs["_GA11"]) if ag else (subs["_CT00"], subs["_CT01"]),
+                                       reads, ag=ag, m=m, b=b)
+            buf, offs = refio.pack_reads(reads)
+            got, _ = e.map_se(buf, offs, ag=ag, m=m, b=b)
+            _cmp_best(got, want, (depth, ag, m, b))
+            assert (got["times"] == 1).mean() > 0.5
+        e.close()
+
+
+def test_device_makedb_matches_oracle_builder():
+    """walt_engine_build_from_sequence (makedb on the GPU) against the oracle's restatement of
+    CountBucketSize/HashToBucket/SortHashTableBucket: same converted genomes, same counter[],
+    same index[] (ties by ascending position in both), then mapping parity on top of it."""
+    import walt_b200
+    lengths = [300000, 180000, 36, 37, 120, 35, 60000]
+    chroms = synth.make_repeat_genome(lengths, seed=303, n_families=8, fam_len=(200, 1200),
+                                      copies=(5, 40), divergence=0.0, repeat_frac=0.3)
+    hdr, subs = refio.build_index_with_oracle(chroms)
+    e = walt_b200.Engine(0)
+    e.set_chromosomes(hdr.lengths, hdr.names)
+    e.build_from_sequence(np.concatenate([s for _, s in chroms]))
+    for w, sfx in enumerate(refio.SUFFIXES):
+        seq, counter, index = e.export_subindex(w, hdr.genome_len)
+        assert np.array_equal(seq, subs[sfx].seq), sfx
+        assert np.array_equal(counter, subs[sfx].counter), sfx
+        assert index.size == subs[sfx].index.size
+        assert np.array_equal(index, subs[sfx].index), sfx
+    reads = synth.simulate_se_reads([chroms[0], chroms[1], chroms[6]], 5000, 100, seed=9, n_frac=0.0)
+    want = refio.oracle_se_map(hdr, (subs["_CT00"], subs["_CT01"]), reads)
+    buf, offs = refio.pack_reads(reads)
+    got, _ = e.map_se(buf, offs)
+    _cmp_best(got, want)
+    e.close()
+
+
+def test_device_makedb_erases_large_buckets():
+    """A genome with a > 500000-fold repeated 12-mer: the bucket must vanish as in
+    reference.cpp:211-218 (checked against the oracle builder)."""
+    import walt_b200
+    rng = np.random.default_rng(5)
+    n = 1_700_000
+    seq = synth._ACGT[rng.integers(0, 4, size=n)].copy()
+    seq[100000:1_300_000] = ord("T")            # poly-T: one 12-mer ~1.2M times (C->T and G->A alike)
+    chroms = [("chr1", seq)]
+    hdr, subs = refio.build_index_with_oracle(chroms)
+    assert subs["_CT00"].index.size < n - 1_000_000
+    e = walt_b200.Engine(0)
+    e.set_chromosomes(hdr.lengths, hdr.names)
+    e.build_from_sequence(seq, which=(0, 1))
+    for w, sfx in ((0, "_CT00"), (1, "_CT01")):
+        _, counter, index = e.export_subindex(w, hdr.genome_len, want_seq=False)
+        assert np.array_equal(counter, subs[sfx].counter)
+        assert np.array_equal(index, subs[sfx].index)
+    e.close()

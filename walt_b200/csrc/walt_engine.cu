@@ -1,0 +1,876 @@
+// walt_engine.cu -- B200 (sm_100a) mapping engine behind the C ABI of include/walt_b200.h.
+//
+// Replaces the strand-loop bodies of the reference's batch drivers
+//   ReadIndex + #pragma omp parallel for { SingleEndMapping }   src/walt/mapping.cpp:486-500
+//   ReadIndex + #pragma omp parallel for { PairEndMapping }     src/walt/paired.cpp:642-672
+// and the pairing loop of MergePairedEndResults                 src/walt/paired.cpp:472-513
+// with CUDA kernels over an index that is loaded ONCE into HBM.  The per-lane logic lives in
+// walt_core.cuh (shared with the CPU fiber harness of tests/emu); this file owns device
+// memory, index residency (2-bit genome, position array, base-3 prefix table, taint list),
+// the kernels' warp policy and launch geometry, and the double-buffered host<->device batch
+// pipeline.  There is no CPU fallback: without a CUDA device every entry point fails.
+#include "walt_engine.cuh"
+
+#include <errno.h>
+#include <stdio.h>
+#include <string.h>
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <memory>
+#include <tuple>
+
+using namespace waltcore;
+
+namespace waltb200 {
+
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+int fail(int code, const std::string& msg) { g_error = msg; return code; }
+
+// ------------------------------------------------------------------------------------------
+// hardware warp policy for walt_core.cuh
+// ------------------------------------------------------------------------------------------
+struct HwWarp {
+  __device__ __forceinline__ uint32_t lane() const { return threadIdx.x & 31u; }
+  __device__ __forceinline__ uint32_t ballot(bool p) const { return __ballot_sync(0xFFFFFFFFu, p); }
+  __device__ __forceinline__ uint32_t shfl(uint32_t v, int src) const { return __shfl_sync(0xFFFFFFFFu, v, src); }
+  __device__ __forceinline__ uint32_t reduce_add(uint32_t v) const { return __reduce_add_sync(0xFFFFFFFFu, v); }
+  __device__ __forceinline__ uint32_t reduce_min(uint32_t v) const { return __reduce_min_sync(0xFFFFFFFFu, v); }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+};
+
+SubIndexView DeviceSubIndex::view(int which) const {
+  SubIndexView v;
+  v.genome = genome; v.index = index; v.table = table; v.taint_bits = taint_bits;
+  v.taint_key = taint_key; v.taint_pos = taint_key + n_taint; v.taint_len = taint_key + 2 * (size_t)n_taint;
+  v.n_taint = n_taint; v.index_size = index_size; v.depth = depth; v.ag = which >= 2 ? 1u : 0u;
+  return v;
+}
+
+void DeviceSubIndex::release() {
+  cudaFree(genome); cudaFree(index); cudaFree(table); cudaFree(taint_bits); cudaFree(taint_key);
+  *this = DeviceSubIndex();
+}
+
+ChromView chrom_view(const walt_engine* e) {
+  ChromView c; c.starts = e->d_starts; c.n_chr = e->n_chr; c.genome_len = e->genome_len;
+  return c;
+}
+
+int ensure_device(walt_engine* e) {
+  WALT_CUDA_TRY(cudaSetDevice(e->device));
+  return WALT_OK;
+}
+
+uint32_t choose_depth(uint32_t index_size) {
+  uint32_t d = KEY_WEIGHT;
+  uint64_t p = N_KEY12;
+  while (d < MAX_DEPTH && p < index_size) { p *= 3; ++d; }
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------
+// index residency kernels
+// ------------------------------------------------------------------------------------------
+// 32 ASCII bases -> one packed word.  `first_base` is a multiple of 32; genome word index is
+// (first_base + PAD_BASES) / 32 + w.  bad[0] counts bytes outside the sub-index's alphabet.
+__global__ void pack_ascii_kernel(const uint8_t* __restrict__ ascii, uint64_t n_bases, uint64_t* __restrict__ words,
+                                  uint32_t forbidden_code, uint32_t* __restrict__ bad) {
+  const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t b0 = w * 32u;
+  if (b0 >= n_bases) return;
+  uint64_t out = 0;
+  uint32_t nbad = 0;
+  const uint32_t cnt = (uint32_t)min((uint64_t)32, n_bases - b0);
+  if (cnt == 32u) {
+    const uint4* p = reinterpret_cast<const uint4*>(ascii + b0);
+    uint4 q[2] = {p[0], p[1]};
+    const uint32_t* u = reinterpret_cast<const uint32_t*>(q);
+#pragma unroll
+    for (uint32_t i = 0; i < 8; ++i) {
+#pragma unroll
+      for (uint32_t j = 0; j < 4; ++j) {
+        uint32_t c = (u[i] >> (8u * j)) & 0xFFu;
+        uint32_t code = ascii_code(c);
+        nbad += (!ascii_is_acgt(c) || code == forbidden_code) ? 1u : 0u;
+        out = (out << 2) | code;
+      }
+    }
+  } else {
+    for (uint32_t i = 0; i < 32u; ++i) {
+      uint32_t code = 0;
+      if (i < cnt) {
+        uint32_t c = ascii[b0 + i];
+        code = ascii_code(c);
+        nbad += (!ascii_is_acgt(c) || code == forbidden_code) ? 1u : 0u;
+      }
+      out = (out << 2) | code;
+    }
+  }
+  words[w] = out;
+  if (nbad) atomicAdd(bad, nbad);
+}
+
+__global__ void table_keys_kernel(SubIndexView ix, ChromView cv, Pow3 p3, uint32_t* __restrict__ keys) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ix.index_size) return;
+  const uint32_t e = ix.index[i];
+  const uint32_t chr = chrom_of(cv.starts, cv.n_chr, e);
+  keys[i] = entry_table_key(ix.genome, e, cv.starts[chr + 1u], ix.depth, ix.ag != 0u, p3);
+}
+
+// table[k] = first slot whose key >= k, for k in [0, n_keys]; slot i owns (key[i-1], key[i]]
+__global__ void table_fill_kernel(const uint32_t* __restrict__ keys, uint32_t index_size, uint32_t n_keys,
+                                  uint32_t* __restrict__ table, uint32_t* __restrict__ unsorted) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > index_size) return;
+  const uint32_t cur = i < index_size ? keys[i] : n_keys;
+  uint64_t from = 0;
+  if (i > 0) {
+    const uint32_t prev = keys[i - 1];
+    if (cur < prev) { atomicAdd(unsorted, 1u); return; }
+    from = (uint64_t)prev + 1u;
+  }
+  for (uint64_t k = from; k <= cur; ++k) table[k] = (uint32_t)i;
+}
+
+int pack_ascii_device(const uint8_t* d_ascii, uint64_t n, uint64_t* d_words, uint32_t forbidden, uint32_t* d_bad) {
+  const uint64_t words = (n + 31u) / 32u;
+  const uint32_t T = 256;
+  pack_ascii_kernel<<<(uint32_t)((words + T - 1) / T), T>>>(d_ascii, n, d_words, forbidden, d_bad);
+  WALT_CUDA_TRY(cudaGetLastError());
+  return WALT_OK;
+}
+
+int alloc_packed_genome(walt_engine* e, DeviceSubIndex& s) {
+  s.genome_words = ((uint64_t)e->genome_len + PAD_BASES + 31u) / 32u + TAIL_PAD_WORDS;
+  WALT_CUDA_TRY(cudaMalloc(&s.genome, s.genome_words * 8u));
+  WALT_CUDA_TRY(cudaMemset(s.genome, 0, s.genome_words * 8u));
+  s.bytes += s.genome_words * 8u;
+  return WALT_OK;
+}
+
+int finalize_subindex(walt_engine* e, int which) {
+  DeviceSubIndex& s = e->sub[which];
+  s.depth = e->force_depth > 0 ? (uint32_t)e->force_depth : choose_depth(s.index_size);
+  if (s.depth < KEY_WEIGHT || s.depth > MAX_DEPTH) return fail(WALT_EINVAL, "table depth out of range");
+  const uint32_t n_keys = e->pow3.v[s.depth];
+  WALT_CUDA_TRY(cudaMalloc(&s.table, ((size_t)n_keys + 1u) * 4u));
+  s.bytes += ((size_t)n_keys + 1u) * 4u;
+  // taint list first (host; <= 112 positions per chromosome): view() needs its pointers
+  {
+    std::vector<std::tuple<uint32_t, uint32_t, uint32_t>> t;
+    std::vector<uint64_t> win;
+    for (uint32_t c = 0; c < e->n_chr; ++c) {
+      const uint32_t cs = e->starts[c], ce = e->starts[c + 1];
+      if (ce - cs < MIN_SEED_LEN + 1u) continue;
+      const uint32_t span = std::min(ce - cs, TAINT_SPAN);
+      // packed words covering bases [ce - span, ce + 64)
+      const uint64_t p0 = (uint64_t)(ce - span) + PAD_BASES;
+      const uint64_t w0 = p0 >> 5, w1 = std::min<uint64_t>(s.genome_words, (((uint64_t)ce + PAD_BASES + 64u) >> 5) + 1u);
+      win.assign(w1 - w0, 0);
+      WALT_CUDA_TRY(cudaMemcpy(win.data(), s.genome + w0, (w1 - w0) * 8u, cudaMemcpyDeviceToHost));
+      // entry_key12 indexes from the genome base; hand it a shifted pointer
+      const uint64_t* base = win.data() - w0;
+      for (uint32_t d = MIN_SEED_LEN + 1u; d <= span; ++d) {
+        const uint32_t pos = ce - d;
+        t.emplace_back(entry_key12(base, pos, which >= 2, e->pow3), pos, d);
+      }
+    }
+    std::sort(t.begin(), t.end());
+    s.n_taint = (uint32_t)t.size();
+    std::vector<uint32_t> bits((N_KEY12 + 31u) / 32u, 0u), flat(3u * (size_t)s.n_taint + 1u, 0u);
+    for (uint32_t i = 0; i < s.n_taint; ++i) {
+      const uint32_t k = std::get<0>(t[i]);
+      bits[k >> 5] |= 1u << (k & 31u);
+      flat[i] = k; flat[s.n_taint + i] = std::get<1>(t[i]); flat[2u * (size_t)s.n_taint + i] = std::get<2>(t[i]);
+    }
+    WALT_CUDA_TRY(cudaMalloc(&s.taint_bits, bits.size() * 4u));
+    WALT_CUDA_TRY(cudaMemcpy(s.taint_bits, bits.data(), bits.size() * 4u, cudaMemcpyHostToDevice));
+    WALT_CUDA_TRY(cudaMalloc(&s.taint_key, flat.size() * 4u));
+    WALT_CUDA_TRY(cudaMemcpy(s.taint_key, flat.data(), flat.size() * 4u, cudaMemcpyHostToDevice));
+    s.bytes += bits.size() * 4u + flat.size() * 4u;
+  }
+  uint32_t* keys = nullptr;
+  WALT_CUDA_TRY(cudaMalloc(&keys, ((size_t)s.index_size + 1u) * 4u));
+  const SubIndexView v = s.view(which);
+  const uint32_t T = 256;
+  if (s.index_size)
+    table_keys_kernel<<<(uint32_t)(((uint64_t)s.index_size + T - 1) / T), T>>>(v, chrom_view(e), e->pow3, keys);
+  WALT_CUDA_TRY(cudaMemset(e->d_flags + 2, 0, 4));
+  table_fill_kernel<<<(uint32_t)(((uint64_t)s.index_size + 1u + T - 1) / T), T>>>(keys, s.index_size, n_keys, s.table,
+                                                                                 e->d_flags + 2);
+  uint32_t unsorted = 0;
+  cudaError_t ce = cudaMemcpy(&unsorted, e->d_flags + 2, 4, cudaMemcpyDeviceToHost);
+  cudaFree(keys);
+  if (ce != cudaSuccess) return fail(WALT_ECUDA, std::string("table build: ") + cudaGetErrorString(ce));
+  if (unsorted)
+    return fail(WALT_EFORMAT, "index[] is not in makedb order (" + std::to_string(unsorted) + " inversions)");
+  s.loaded = true;
+  return WALT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// mapping kernels: one warp owns a read
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t WARPS_PER_BLOCK = 8;
+constexpr uint32_t BLOCK_THREADS = WARPS_PER_BLOCK * 32;
+
+struct SeArgs {
+  SubIndexView ix[2];   // '+' then '-' sub-index
+  ChromView cv;
+  Pow3 p3;
+  MapConfig cfg;
+  const char* seqs;
+  const uint64_t* offs;   // n + 1, absolute; seqs[0] is byte `seq_base`
+  uint64_t seq_base;
+  uint32_t n;
+  uint32_t nw_max;        // scratch stride (words) for the longest read
+  uint32_t ag;
+  uint32_t max_mismatches;
+  walt_best* out;
+  uint32_t* flags;        // [0] non-ACGT
+  uint32_t* queue;        // work-queue head (zeroed before launch)
+  unsigned long long* counters;  // optional
+};
+
+__global__ void __launch_bounds__(BLOCK_THREADS)
+se_map_kernel(const __grid_constant__ SeArgs a) {
+  extern __shared__ uint64_t smem[];
+  HwWarp w;
+  const uint32_t lane = w.lane();
+  const uint32_t warp_in_block = threadIdx.x >> 5;
+  ReadScratch sc = carve_scratch(smem + (size_t)warp_in_block * scratch_words(a.nw_max), a.nw_max);
+  uint32_t cached_len = 0;
+  Counters ctr{0u, 0u, 0u};
+  bool bad = false;
+  for (;;) {
+    uint32_t r = 0;
+    if (lane == 0) r = atomicAdd(a.queue, 1u);
+    r = w.shfl(r, 0);
+    if (r >= a.n) break;
+    const uint64_t o0 = a.offs[r], o1 = a.offs[r + 1];
+    const uint32_t len = (uint32_t)(o1 - o0);
+    BestState st;
+    bool ok = map_read_se(w, a.ix, a.cv, a.p3, a.cfg, a.seqs + (o0 - a.seq_base), len, a.ag != 0u,
+                          a.max_mismatches, sc, cached_len, st, ctr);
+    bad |= !ok;
+    if (lane == 0) {
+      uint4 o;
+      o.x = st.pos; o.y = st.times; o.z = st.mm; o.w = st.strand & 0xFFu;
+      *reinterpret_cast<uint4*>(a.out + r) = o;
+    }
+  }
+  if (lane == 0) {
+    if (bad) atomicOr(a.flags, 1u);
+    if (a.counters) {
+      atomicAdd(a.counters + 0, (unsigned long long)ctr.lookups);
+      atomicAdd(a.counters + 1, (unsigned long long)ctr.candidates);
+      atomicAdd(a.counters + 2, (unsigned long long)ctr.literal);
+    }
+  }
+}
+
+struct PeArgs {
+  SubIndexView ix[2];
+  ChromView cv;
+  Pow3 p3;
+  MapConfig cfg;
+  const char* seqs;
+  const uint64_t* offs;
+  uint64_t seq_base;
+  uint32_t n;
+  uint32_t nw_max;
+  uint32_t ag;
+  uint32_t max_mismatches;
+  uint32_t top_k;
+  walt_cand* ranked;      // n * top_k, worst first
+  uint32_t* n_ranked;
+  uint32_t* flags;
+  uint32_t* queue;
+  unsigned long long* counters;
+};
+
+// PairEndMapping (paired.cpp:106-201) for one mate batch + the heap drain (paired.cpp:684-692)
+__global__ void __launch_bounds__(BLOCK_THREADS)
+pe_map_kernel(const __grid_constant__ PeArgs a) {
+  extern __shared__ uint64_t smem[];
+  HwWarp w;
+  const uint32_t lane = w.lane();
+  const uint32_t warp_in_block = threadIdx.x >> 5;
+  const uint32_t per_warp = scratch_words(a.nw_max) + a.top_k + 1u;  // HeapEntry is 8 bytes
+  uint64_t* mine = smem + (size_t)warp_in_block * per_warp;
+  ReadScratch sc = carve_scratch(mine, a.nw_max);
+  HeapEntry* heap = reinterpret_cast<HeapEntry*>(mine + scratch_words(a.nw_max));
+  uint32_t cached_len = 0;
+  Counters ctr{0u, 0u, 0u};
+  bool bad = false;
+  for (;;) {
+    uint32_t r = 0;
+    if (lane == 0) r = atomicAdd(a.queue, 1u);
+    r = w.shfl(r, 0);
+    if (r >= a.n) break;
+    const uint64_t o0 = a.offs[r], o1 = a.offs[r + 1];
+    const uint32_t len = (uint32_t)(o1 - o0);
+    uint32_t hsize = 0;
+    bool ok = map_read_pe(w, a.ix, a.cv, a.p3, a.cfg, a.seqs + (o0 - a.seq_base), len, a.ag != 0u,
+                          a.max_mismatches, a.top_k, sc, cached_len, heap, hsize, ctr);
+    bad |= !ok;
+    if (lane == 0) {
+      walt_cand* dst = a.ranked + (size_t)r * a.top_k;
+      uint32_t c = 0, sz = hsize;
+      while (sz) {
+        HeapEntry t = heap_pop(heap, sz);
+        walt_cand o;
+        o.genome_pos = t.pos; o.mismatch = he_mm(t); o.strand = (t.mm_strand & 0x10000u) ? '-' : '+';
+        o.pad[0] = o.pad[1] = o.pad[2] = 0;
+        dst[c++] = o;
+      }
+      a.n_ranked[r] = c;
+    }
+    w.sync();
+    {  // unused slots are defined (zero) so whole-array compares and copies are deterministic
+      const uint32_t used = w.shfl(hsize, 0);
+      uint32_t* z = reinterpret_cast<uint32_t*>(a.ranked + (size_t)r * a.top_k + used);
+      for (uint32_t i = lane; i < (a.top_k - used) * 3u; i += 32u) z[i] = 0u;
+    }
+  }
+  if (lane == 0) {
+    if (bad) atomicOr(a.flags, 1u);
+    if (a.counters) {
+      atomicAdd(a.counters + 0, (unsigned long long)ctr.lookups);
+      atomicAdd(a.counters + 1, (unsigned long long)ctr.candidates);
+      atomicAdd(a.counters + 2, (unsigned long long)ctr.literal);
+    }
+  }
+}
+
+struct GetRanked {
+  const walt_cand* p;
+  __device__ __forceinline__ RankedCand operator()(uint32_t i) const {
+    RankedCand c; c.pos = p[i].genome_pos; c.mm = p[i].mismatch; c.strand = (uint8_t)p[i].strand;
+    return c;
+  }
+};
+
+// pairing loop of MergePairedEndResults (paired.cpp:472-513): one thread per pair
+__global__ void pair_kernel(ChromView cv, const walt_cand* __restrict__ r1, const uint32_t* __restrict__ n1,
+                            const uint64_t* __restrict__ offs1, const walt_cand* __restrict__ r2,
+                            const uint32_t* __restrict__ n2, const uint64_t* __restrict__ offs2, uint32_t n,
+                            uint32_t top_k, uint32_t max_mismatches, int32_t frag_range, walt_pair* __restrict__ out) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  PairResult r = pair_candidates(cv, GetRanked{r1 + (size_t)p * top_k}, n1[p], (uint32_t)(offs1[p + 1] - offs1[p]),
+                                 GetRanked{r2 + (size_t)p * top_k}, n2[p], (uint32_t)(offs2[p + 1] - offs2[p]),
+                                 max_mismatches, frag_range);
+  walt_pair o; o.best_times = r.best_times; o.best_i = r.best_i; o.best_j = r.best_j; o.frag_len = r.frag;
+  out[p] = o;
+}
+
+// ------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------
+static size_t se_smem_bytes(uint32_t nw_max) { return (size_t)WARPS_PER_BLOCK * scratch_words(nw_max) * 8u; }
+static size_t pe_smem_bytes(uint32_t nw_max, uint32_t top_k) {
+  return (size_t)WARPS_PER_BLOCK * (scratch_words(nw_max) + top_k + 1u) * 8u;
+}
+
+template <class K>
+static int grid_for(walt_engine* e, K kernel, size_t smem, uint32_t n, uint32_t* grid) {
+  int per_sm = 0;
+  WALT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  WALT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)BLOCK_THREADS, smem));
+  if (per_sm < 1) return fail(WALT_ECUDA, "mapping kernel does not fit on an SM");
+  uint64_t g = (uint64_t)per_sm * (uint64_t)e->sm_count;   // persistent: a multiple of the SM count
+  const uint64_t need = ((uint64_t)n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+  if (need < g) g = need ? need : 1;
+  *grid = (uint32_t)g;
+  return WALT_OK;
+}
+
+static int check_pair(walt_engine* e, int ag) {
+  const int a = ag ? WALT_GA10 : WALT_CT00;
+  if (!e->sub[a].loaded || !e->sub[a + 1].loaded)
+    return fail(WALT_ENOTLOADED, ag ? "G->A sub-indexes (_GA10/_GA11) are not resident"
+                                    : "C->T sub-indexes (_CT00/_CT01) are not resident");
+  return WALT_OK;
+}
+
+static int launch_se(walt_engine* e, const char* d_seqs, const uint64_t* d_offs, uint64_t seq_base, uint32_t n,
+                     uint32_t max_read_len, int ag, uint32_t m, uint32_t b, walt_best* d_out, uint32_t* d_queue,
+                     cudaStream_t st) {
+  if (max_read_len > MAX_READ_LEN) return fail(WALT_EINVAL, "read longer than 1024 bases");
+  SeArgs a;
+  const int base = ag ? WALT_GA10 : WALT_CT00;
+  a.ix[0] = e->sub[base].view(base); a.ix[1] = e->sub[base + 1].view(base + 1);
+  a.cv = chrom_view(e); a.p3 = e->pow3;
+  a.cfg.b = b; a.cfg.literal_all = e->search_mode == 1 ? 1u : 0u;
+  a.seqs = d_seqs; a.offs = d_offs; a.seq_base = seq_base; a.n = n;
+  a.nw_max = std::max<uint32_t>(1u, (max_read_len + 31u) / 32u);
+  a.ag = ag ? 1u : 0u; a.max_mismatches = m; a.out = d_out; a.flags = e->d_flags; a.queue = d_queue;
+  a.counters = e->d_counters;
+  const size_t smem = se_smem_bytes(a.nw_max);
+  uint32_t grid = 0;
+  int rc = grid_for(e, se_map_kernel, smem, n, &grid);
+  if (rc) return rc;
+  WALT_CUDA_TRY(cudaMemsetAsync(d_queue, 0, 4, st));
+  se_map_kernel<<<grid, BLOCK_THREADS, smem, st>>>(a);
+  WALT_CUDA_TRY(cudaGetLastError());
+  e->stats.n_kernel_launches++;
+  return WALT_OK;
+}
+
+static int launch_pe_mate(walt_engine* e, const char* d_seqs, const uint64_t* d_offs, uint64_t seq_base, uint32_t n,
+                          uint32_t max_read_len, int ag, uint32_t m, uint32_t b, uint32_t top_k, walt_cand* d_ranked,
+                          uint32_t* d_nranked, uint32_t* d_queue, cudaStream_t st) {
+  if (max_read_len > MAX_READ_LEN) return fail(WALT_EINVAL, "read longer than 1024 bases");
+  PeArgs a;
+  const int base = ag ? WALT_GA10 : WALT_CT00;
+  a.ix[0] = e->sub[base].view(base); a.ix[1] = e->sub[base + 1].view(base + 1);
+  a.cv = chrom_view(e); a.p3 = e->pow3;
+  a.cfg.b = b; a.cfg.literal_all = e->search_mode == 1 ? 1u : 0u;
+  a.seqs = d_seqs; a.offs = d_offs; a.seq_base = seq_base; a.n = n;
+  a.nw_max = std::max<uint32_t>(1u, (max_read_len + 31u) / 32u);
+  a.ag = ag ? 1u : 0u; a.max_mismatches = m; a.top_k = top_k; a.ranked = d_ranked; a.n_ranked = d_nranked;
+  a.flags = e->d_flags; a.queue = d_queue; a.counters = e->d_counters;
+  const size_t smem = pe_smem_bytes(a.nw_max, top_k);
+  uint32_t grid = 0;
+  int rc = grid_for(e, pe_map_kernel, smem, n, &grid);
+  if (rc) return rc;
+  WALT_CUDA_TRY(cudaMemsetAsync(d_queue, 0, 4, st));
+  pe_map_kernel<<<grid, BLOCK_THREADS, smem, st>>>(a);
+  WALT_CUDA_TRY(cudaGetLastError());
+  e->stats.n_kernel_launches++;
+  return WALT_OK;
+}
+
+template <class T>
+static int reserve(T** p, size_t* cap, size_t need) {
+  if (need <= *cap) return WALT_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *cap = 0;
+  size_t want = need + need / 8 + 256;
+  WALT_CUDA_TRY(cudaMalloc(p, want * sizeof(T)));
+  *cap = want;
+  return WALT_OK;
+}
+static int reserve_bytes(void** p, size_t* cap, size_t need) {
+  return reserve(reinterpret_cast<char**>(p), cap, need);
+}
+
+static int fetch_status(walt_engine* e) {
+  uint32_t f = 0;
+  WALT_CUDA_TRY(cudaMemcpy(&f, e->d_flags, 4, cudaMemcpyDeviceToHost));
+  unsigned long long c[3];
+  WALT_CUDA_TRY(cudaMemcpy(c, e->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+  e->stats.n_lookups = c[0]; e->stats.n_candidates = c[1]; e->stats.n_literal = c[2];
+  if (f & 1u) {
+    cudaMemset(e->d_flags, 0, 4);
+    return fail(WALT_ENONACGT, "[ERROR: NON-ACGT NUCLEOTIDE] in a read handed to the mapping engine");
+  }
+  return WALT_OK;
+}
+
+static uint32_t max_len_of(const uint64_t* offs, uint32_t n, uint32_t* n_short) {
+  uint32_t mx = 0, sh = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint64_t l = offs[i + 1] - offs[i];
+    if (l > 0xFFFFFFFFull) return 0xFFFFFFFFu;
+    mx = std::max<uint32_t>(mx, (uint32_t)l);
+    sh += l < MIN_READ_LEN ? 1u : 0u;
+  }
+  if (n_short) *n_short = 2u * sh;   // once per strand pass (mapping.cpp:230-232, paired.cpp:112-115)
+  return mx;
+}
+
+}  // namespace waltb200
+
+using namespace waltb200;
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+extern "C" {
+
+const char* walt_last_error(void) { return g_error.c_str(); }
+
+int walt_engine_create(walt_engine** out, int device) {
+  if (!out) return fail(WALT_EINVAL, "out is NULL");
+  *out = nullptr;
+  int n_dev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&n_dev);
+  if (ce != cudaSuccess || n_dev == 0)
+    return fail(WALT_ECUDA, std::string("no CUDA device: ") + cudaGetErrorString(ce) +
+                                " (the engine has no CPU fallback)");
+  if (device < 0 || device >= n_dev) return fail(WALT_EINVAL, "device ordinal out of range");
+  std::unique_ptr<walt_engine> e(new walt_engine);
+  e->device = device;
+  WALT_CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  WALT_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  e->sm_count = prop.multiProcessorCount;
+  uint32_t p = 1;
+  for (uint32_t i = 0; i <= MAX_DEPTH; ++i) { e->pow3.v[i] = p; p *= 3u; }
+  WALT_CUDA_TRY(cudaMalloc(&e->d_flags, 8 * 4));
+  WALT_CUDA_TRY(cudaMemset(e->d_flags, 0, 8 * 4));
+  WALT_CUDA_TRY(cudaMalloc(&e->d_counters, 3 * 8));
+  WALT_CUDA_TRY(cudaMemset(e->d_counters, 0, 3 * 8));
+  for (auto& s : e->slot) {
+    WALT_CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    WALT_CUDA_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+  }
+  *out = e.release();
+  return WALT_OK;
+}
+
+void walt_engine_destroy(walt_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  for (auto& s : e->sub) s.release();
+  for (auto& s : e->slot) {
+    cudaFree(s.d_seqs); cudaFree(s.d_offs); cudaFree(s.d_out); cudaFree(s.d_seqs2); cudaFree(s.d_offs2);
+    cudaFree(s.d_pe);
+    if (s.stream) cudaStreamDestroy(s.stream);
+    if (s.done) cudaEventDestroy(s.done);
+  }
+  cudaFree(e->d_starts); cudaFree(e->d_flags); cudaFree(e->d_counters);
+  delete e;
+}
+
+int walt_engine_set_chromosomes(walt_engine* e, uint32_t n_chr, const uint32_t* lengths, const char* const* names) {
+  if (!e || !lengths || n_chr == 0) return fail(WALT_EINVAL, "bad chromosome table");
+  int rc = ensure_device(e);
+  if (rc) return rc;
+  uint64_t total = 0;
+  for (uint32_t i = 0; i < n_chr; ++i) total += lengths[i];
+  if (total >= 0xFFFFFFFFull - MAX_READ_LEN) return fail(WALT_EFORMAT, "genome does not fit 32-bit offsets");
+  e->n_chr = n_chr;
+  e->lengths.assign(lengths, lengths + n_chr);
+  e->starts.assign(n_chr + 1, 0);
+  for (uint32_t i = 0; i < n_chr; ++i) e->starts[i + 1] = e->starts[i] + lengths[i];   // reference.cpp:407-410
+  e->genome_len = e->starts[n_chr];
+  e->names.clear();
+  for (uint32_t i = 0; i < n_chr; ++i) e->names.emplace_back(names && names[i] ? names[i] : "");
+  e->name_ptrs.clear();
+  for (auto& s : e->names) e->name_ptrs.push_back(s.c_str());
+  cudaFree(e->d_starts); e->d_starts = nullptr;
+  WALT_CUDA_TRY(cudaMalloc(&e->d_starts, (n_chr + 1) * 4u));
+  WALT_CUDA_TRY(cudaMemcpy(e->d_starts, e->starts.data(), (n_chr + 1) * 4u, cudaMemcpyHostToDevice));
+  for (auto& s : e->sub) s.release();
+  return WALT_OK;
+}
+
+// pack `n` ASCII bases starting at genome base `first` (multiple of 32) from host memory
+static int upload_genome_chunk(walt_engine* e, DeviceSubIndex& s, int which, const char* host, uint64_t first,
+                               uint64_t n, uint8_t* d_stage) {
+  WALT_CUDA_TRY(cudaMemcpy(d_stage, host, n, cudaMemcpyHostToDevice));
+  const uint64_t words = (n + 31u) / 32u;
+  const uint32_t T = 256;
+  pack_ascii_kernel<<<(uint32_t)((words + T - 1) / T), T>>>(d_stage, n, s.genome + ((first + PAD_BASES) >> 5),
+                                                          which >= 2 ? 2u : 1u, e->d_flags + 3);
+  WALT_CUDA_TRY(cudaGetLastError());
+  return WALT_OK;
+}
+
+static const size_t STAGE_BYTES = 64u << 20;
+
+int walt_engine_load_subindex(walt_engine* e, int which, const char* sequence, const uint32_t* counter,
+                              const uint32_t* index, uint32_t index_size) {
+  if (!e || which < 0 || which > 3 || !sequence || (!index && index_size)) return fail(WALT_EINVAL, "bad argument");
+  if (!e->d_starts) return fail(WALT_EINVAL, "set the chromosome table first");
+  int rc = ensure_device(e);
+  if (rc) return rc;
+  if (counter && counter[1u << 24] != index_size)
+    return fail(WALT_EFORMAT, "counter[4^12] != index_size (reference.cpp:252-255)");
+  DeviceSubIndex& s = e->sub[which];
+  s.release();
+  if ((rc = alloc_packed_genome(e, s))) return rc;
+  uint8_t* d_stage = nullptr;
+  WALT_CUDA_TRY(cudaMalloc(&d_stage, STAGE_BYTES));
+  WALT_CUDA_TRY(cudaMemset(e->d_flags + 3, 0, 4));
+  for (uint64_t off = 0; off < e->genome_len; off += STAGE_BYTES) {
+    const uint64_t n = std::min<uint64_t>(STAGE_BYTES, e->genome_len - off);
+    if ((rc = upload_genome_chunk(e, s, which, sequence + off, off, n, d_stage))) { cudaFree(d_stage); return rc; }
+  }
+  uint32_t bad = 0;
+  WALT_CUDA_TRY(cudaMemcpy(&bad, e->d_flags + 3, 4, cudaMemcpyDeviceToHost));
+  cudaFree(d_stage);
+  if (bad) return fail(WALT_EFORMAT, std::to_string(bad) + " genome bytes outside the sub-index's 3-letter alphabet");
+  s.index_size = index_size;
+  WALT_CUDA_TRY(cudaMalloc(&s.index, ((size_t)index_size + 64u) * 4u));
+  WALT_CUDA_TRY(cudaMemset(s.index + index_size, 0, 64u * 4u));
+  if (index_size) WALT_CUDA_TRY(cudaMemcpy(s.index, index, (size_t)index_size * 4u, cudaMemcpyHostToDevice));
+  s.bytes += ((size_t)index_size + 64u) * 4u;
+  return finalize_subindex(e, which);
+}
+
+static int read_exact(FILE* f, void* dst, size_t n, const char* what) {
+  if (fread(dst, 1, n, f) != n) return fail(WALT_EIO, std::string("short read: ") + what);
+  return WALT_OK;
+}
+
+// ReadIndexHeadInfo (reference.cpp:381-417) + ReadIndex (reference.cpp:324-351), once.
+int walt_engine_load_dbindex(walt_engine* e, const char* path, uint32_t which_mask) {
+  if (!e || !path) return fail(WALT_EINVAL, "bad argument");
+  int rc = ensure_device(e);
+  if (rc) return rc;
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(WALT_EIO, std::string("cannot open ") + path + ": " + strerror(errno));
+  uint32_t n_chr = 0;
+  std::vector<std::string> names;
+  std::vector<uint32_t> lengths;
+  uint32_t genome_len = 0, size_of_index = 0;
+  rc = read_exact(f, &n_chr, 4, "chromosome count");
+  if (!rc && (n_chr == 0 || n_chr > (1u << 24))) rc = fail(WALT_EFORMAT, "implausible chromosome count");
+  for (uint32_t i = 0; !rc && i < n_chr; ++i) {
+    uint32_t ln = 0;
+    rc = read_exact(f, &ln, 4, "name length");
+    if (!rc && ln > 255) rc = fail(WALT_EFORMAT, "chromosome name longer than 255");
+    std::string nm(ln, '\0');
+    if (!rc && ln) rc = read_exact(f, &nm[0], ln, "chromosome name");
+    names.push_back(nm);
+  }
+  lengths.resize(n_chr);
+  if (!rc) rc = read_exact(f, lengths.data(), 4u * n_chr, "chromosome lengths");
+  if (!rc) rc = read_exact(f, &genome_len, 4, "genome length");
+  if (!rc) rc = read_exact(f, &size_of_index, 4, "index size");
+  fclose(f);
+  if (rc) return rc;
+  std::vector<const char*> np;
+  for (auto& s : names) np.push_back(s.c_str());
+  if ((rc = walt_engine_set_chromosomes(e, n_chr, lengths.data(), np.data()))) return rc;
+  if (e->genome_len != genome_len) return fail(WALT_EFORMAT, "length_of_genome != sum of chromosome lengths");
+
+  static const char* SFX[4] = {"_CT00", "_CT01", "_GA10", "_GA11"};
+  uint8_t* d_stage = nullptr;
+  char* h_stage = nullptr;
+  WALT_CUDA_TRY(cudaMalloc(&d_stage, STAGE_BYTES));
+  WALT_CUDA_TRY(cudaMallocHost(&h_stage, STAGE_BYTES));
+  for (int which = 0; which < 4 && !rc; ++which) {
+    if (!((which_mask >> which) & 1u)) continue;
+    const std::string sp = std::string(path) + SFX[which];
+    FILE* g = fopen(sp.c_str(), "rb");
+    if (!g) { rc = fail(WALT_EIO, "cannot open " + sp + ": " + strerror(errno)); break; }
+    DeviceSubIndex& s = e->sub[which];
+    s.release();
+    char strand = 0;
+    rc = read_exact(g, &strand, 1, "strand byte");
+    if (!rc && strand != ((which & 1) ? '-' : '+')) rc = fail(WALT_EFORMAT, sp + ": wrong strand byte");
+    if (!rc) rc = alloc_packed_genome(e, s);
+    if (!rc && cudaMemset(e->d_flags + 3, 0, 4) != cudaSuccess) rc = fail(WALT_ECUDA, "memset");
+    for (uint64_t off = 0; !rc && off < genome_len; off += STAGE_BYTES) {
+      const uint64_t n = std::min<uint64_t>(STAGE_BYTES, genome_len - off);
+      rc = read_exact(g, h_stage, n, "genome sequence");
+      if (!rc) rc = upload_genome_chunk(e, s, which, h_stage, off, n, d_stage);
+    }
+    uint32_t hdr[2] = {0, 0};
+    if (!rc) rc = read_exact(g, hdr, 8, "counter/index sizes");
+    if (!rc && hdr[0] != (1u << 24)) rc = fail(WALT_EFORMAT, sp + ": counter_size != 4^12");
+    if (!rc && hdr[1] > size_of_index) rc = fail(WALT_EFORMAT, sp + ": index_size exceeds the header's size_of_index");
+    // counter[] is superseded by the base-3 prefix table; only its last entry is checked
+    if (!rc && fseeko(g, (off_t)4 * (1u << 24), SEEK_CUR) != 0) rc = fail(WALT_EIO, "seek over counter[]");
+    uint32_t last = 0;
+    if (!rc) rc = read_exact(g, &last, 4, "counter[4^12]");
+    if (!rc && last != hdr[1]) rc = fail(WALT_EFORMAT, sp + ": counter[4^12] != index_size");
+    if (!rc) {
+      s.index_size = hdr[1];
+      if (cudaMalloc(&s.index, ((size_t)s.index_size + 64u) * 4u) != cudaSuccess) rc = fail(WALT_ECUDA, "cudaMalloc(index)");
+      else cudaMemset(s.index + s.index_size, 0, 64u * 4u);
+      s.bytes += ((size_t)s.index_size + 64u) * 4u;
+    }
+    for (uint64_t off = 0; !rc && off < (uint64_t)s.index_size * 4u; off += STAGE_BYTES) {
+      const uint64_t n = std::min<uint64_t>(STAGE_BYTES, (uint64_t)s.index_size * 4u - off);
+      rc = read_exact(g, h_stage, n, "index[]");
+      if (!rc && cudaMemcpy((char*)s.index + off, h_stage, n, cudaMemcpyHostToDevice) != cudaSuccess)
+        rc = fail(WALT_ECUDA, "index upload");
+    }
+    fclose(g);
+    if (!rc) {
+      uint32_t bad = 0;
+      cudaMemcpy(&bad, e->d_flags + 3, 4, cudaMemcpyDeviceToHost);
+      if (bad) rc = fail(WALT_EFORMAT, sp + ": genome bytes outside the 3-letter alphabet");
+    }
+    if (!rc) rc = finalize_subindex(e, which);
+  }
+  cudaFree(d_stage);
+  cudaFreeHost(h_stage);
+  return rc;
+}
+
+int walt_engine_chromosomes(const walt_engine* e, uint32_t* n_chr, const uint32_t** lengths,
+                            const uint32_t** start_index, const char* const** names) {
+  if (!e) return fail(WALT_EINVAL, "engine is NULL");
+  if (n_chr) *n_chr = e->n_chr;
+  if (lengths) *lengths = e->lengths.data();
+  if (start_index) *start_index = e->starts.data();
+  if (names) *names = e->name_ptrs.data();
+  return WALT_OK;
+}
+
+uint64_t walt_engine_hbm_bytes(const walt_engine* e) {
+  uint64_t t = 0;
+  if (e) for (auto& s : e->sub) t += s.bytes;
+  return t;
+}
+
+int walt_engine_subindex_info(const walt_engine* e, int which, uint32_t* index_size, uint32_t* depth,
+                              uint32_t* n_taint) {
+  if (!e || which < 0 || which > 3) return fail(WALT_EINVAL, "bad argument");
+  if (!e->sub[which].loaded) return fail(WALT_ENOTLOADED, "sub-index not resident");
+  if (index_size) *index_size = e->sub[which].index_size;
+  if (depth) *depth = e->sub[which].depth;
+  if (n_taint) *n_taint = e->sub[which].n_taint;
+  return WALT_OK;
+}
+
+int walt_engine_set_search_mode(walt_engine* e, int mode) {
+  if (!e || (mode != 0 && mode != 1)) return fail(WALT_EINVAL, "search mode must be 0 or 1");
+  e->search_mode = mode;
+  return WALT_OK;
+}
+
+int walt_engine_set_table_depth(walt_engine* e, int depth) {
+  if (!e || (depth != 0 && (depth < (int)KEY_WEIGHT || depth > (int)MAX_DEPTH)))
+    return fail(WALT_EINVAL, "table depth must be 0 (auto) or 12..20");
+  e->force_depth = depth;
+  return WALT_OK;
+}
+
+int walt_engine_set_chunk_reads(walt_engine* e, uint32_t n) {
+  if (!e || n == 0) return fail(WALT_EINVAL, "chunk size must be positive");
+  e->chunk_reads = n;
+  return WALT_OK;
+}
+
+int walt_engine_last_stats(const walt_engine* e, walt_stats* out) {
+  if (!e || !out) return fail(WALT_EINVAL, "bad argument");
+  *out = e->stats;
+  return WALT_OK;
+}
+
+// ---- single end ---------------------------------------------------------------------------
+int walt_engine_map_se_device(walt_engine* e, const void* d_seqs, const void* d_offs, uint32_t n,
+                              uint32_t max_read_len, int ag_wildcard, uint32_t max_mismatches, uint32_t b,
+                              void* d_out, void* cuda_stream) {
+  if (!e || (n && (!d_seqs || !d_offs || !d_out))) return fail(WALT_EINVAL, "bad argument");
+  int rc = ensure_device(e);
+  if (rc) return rc;
+  if ((rc = check_pair(e, ag_wildcard))) return rc;
+  if (n == 0) return WALT_OK;
+  return launch_se(e, (const char*)d_seqs, (const uint64_t*)d_offs, 0, n, max_read_len, ag_wildcard, max_mismatches,
+                   b, (walt_best*)d_out, e->d_flags + 1, (cudaStream_t)cuda_stream);
+}
+
+int walt_engine_map_se(walt_engine* e, const char* seqs, const uint64_t* offs, uint32_t n, int ag_wildcard,
+                       uint32_t max_mismatches, uint32_t b, walt_best* out, uint32_t* n_short) {
+  if (!e || !offs || (n && (!seqs || !out))) return fail(WALT_EINVAL, "bad argument");
+  int rc = ensure_device(e);
+  if (rc) return rc;
+  if ((rc = check_pair(e, ag_wildcard))) return rc;
+  const uint32_t max_len = max_len_of(offs, n, n_short);
+  if (max_len > MAX_READ_LEN) return fail(WALT_EINVAL, "read longer than 1024 bases");
+  e->stats = walt_stats{};
+  WALT_CUDA_TRY(cudaMemset(e->d_counters, 0, 3 * 8));
+  uint32_t k = 0;
+  for (uint32_t r0 = 0; r0 < n; r0 += e->chunk_reads, ++k) {
+    const uint32_t cn = std::min<uint32_t>(e->chunk_reads, n - r0);
+    BatchSlot& s = e->slot[k & 1u];
+    WALT_CUDA_TRY(cudaEventSynchronize(s.done));
+    const uint64_t sb = offs[r0], se = offs[r0 + cn];
+    if ((rc = reserve(&s.d_seqs, &s.seqs_cap, (size_t)(se - sb) + 16u))) return rc;
+    if ((rc = reserve(&s.d_offs, &s.offs_cap, (size_t)cn + 1u))) return rc;
+    if ((rc = reserve_bytes(&s.d_out, &s.out_cap, (size_t)cn * sizeof(walt_best)))) return rc;
+    if (se > sb) WALT_CUDA_TRY(cudaMemcpyAsync(s.d_seqs, seqs + sb, se - sb, cudaMemcpyHostToDevice, s.stream));
+    WALT_CUDA_TRY(cudaMemcpyAsync(s.d_offs, offs + r0, ((size_t)cn + 1u) * 8u, cudaMemcpyHostToDevice, s.stream));
+    if ((rc = launch_se(e, s.d_seqs, s.d_offs, sb, cn, max_len, ag_wildcard, max_mismatches, b, (walt_best*)s.d_out,
+                        e->d_flags + 4 + (k & 1u), s.stream)))
+      return rc;
+    WALT_CUDA_TRY(cudaMemcpyAsync(out + r0, s.d_out, (size_t)cn * sizeof(walt_best), cudaMemcpyDeviceToHost, s.stream));
+    WALT_CUDA_TRY(cudaEventRecord(s.done, s.stream));
+  }
+  for (auto& s : e->slot) WALT_CUDA_TRY(cudaStreamSynchronize(s.stream));
+  return fetch_status(e);
+}
+
+// ---- paired end ---------------------------------------------------------------------------
+int walt_engine_map_pe(walt_engine* e, const char* seqs1, const uint64_t* offs1, const char* seqs2,
+                       const uint64_t* offs2, uint32_t n, uint32_t max_mismatches, uint32_t b, uint32_t top_k,
+                       int frag_range, int pbat, walt_cand* ranked1, uint32_t* n_ranked1, walt_cand* ranked2,
+                       uint32_t* n_ranked2, walt_pair* pairs, uint32_t* n_short1, uint32_t* n_short2) {
+  if (!e || !offs1 || !offs2 || (n && (!seqs1 || !seqs2 || !ranked1 || !ranked2 || !n_ranked1 || !n_ranked2 || !pairs)))
+    return fail(WALT_EINVAL, "bad argument");
+  if (top_k < 2 || top_k > 300) return fail(WALT_EINVAL, "-k must be in [2, 300] (walt.cpp:245-249)");
+  int rc = ensure_device(e);
+  if (rc) return rc;
+  if ((rc = check_pair(e, 0)) || (rc = check_pair(e, 1))) return rc;
+  if (pbat) {
+    // PBAT swaps the bisulfite roles of the mates: run the directional protocol with the mates
+    // exchanged, then hand every per-mate result back to its owner.
+    rc = walt_engine_map_pe(e, seqs2, offs2, seqs1, offs1, n, max_mismatches, b, top_k, frag_range, 0, ranked2,
+                            n_ranked2, ranked1, n_ranked1, pairs, n_short2, n_short1);
+    if (rc) return rc;
+    for (uint32_t i = 0; i < n; ++i) std::swap(pairs[i].best_i, pairs[i].best_j);
+    return WALT_OK;
+  }
+  const uint32_t max1 = max_len_of(offs1, n, n_short1), max2 = max_len_of(offs2, n, n_short2);
+  if (max1 > MAX_READ_LEN || max2 > MAX_READ_LEN) return fail(WALT_EINVAL, "read longer than 1024 bases");
+  e->stats = walt_stats{};
+  WALT_CUDA_TRY(cudaMemset(e->d_counters, 0, 3 * 8));
+  // chunk so that the ranked lists of a slot stay below ~1 GiB
+  const uint32_t chunk = std::max<uint32_t>(1024u, std::min<uint32_t>(e->chunk_reads, (1u << 30) / (2u * top_k * 12u)));
+  uint32_t k = 0;
+  for (uint32_t r0 = 0; r0 < n; r0 += chunk, ++k) {
+    const uint32_t cn = std::min<uint32_t>(chunk, n - r0);
+    BatchSlot& s = e->slot[k & 1u];
+    WALT_CUDA_TRY(cudaEventSynchronize(s.done));
+    const uint64_t sb1 = offs1[r0], se1 = offs1[r0 + cn], sb2 = offs2[r0], se2 = offs2[r0 + cn];
+    if ((rc = reserve(&s.d_seqs, &s.seqs_cap, (size_t)(se1 - sb1) + 16u))) return rc;
+    if ((rc = reserve(&s.d_offs, &s.offs_cap, (size_t)cn + 1u))) return rc;
+    if ((rc = reserve(&s.d_seqs2, &s.seqs2_cap, (size_t)(se2 - sb2) + 16u))) return rc;
+    if ((rc = reserve(&s.d_offs2, &s.offs2_cap, (size_t)cn + 1u))) return rc;
+    const size_t rk = (size_t)cn * top_k * sizeof(walt_cand);
+    const size_t pe_bytes = 2u * rk + 2u * (size_t)cn * 4u + (size_t)cn * sizeof(walt_pair) + 64u;
+    if ((rc = reserve_bytes(&s.d_pe, &s.pe_cap, pe_bytes))) return rc;
+    char* base = (char*)s.d_pe;
+    walt_pair* d_pairs = (walt_pair*)base;
+    walt_cand* d_r1 = (walt_cand*)(base + (((size_t)cn * sizeof(walt_pair) + 15u) & ~(size_t)15u));
+    walt_cand* d_r2 = d_r1 + (size_t)cn * top_k;
+    uint32_t* d_n1 = (uint32_t*)(d_r2 + (size_t)cn * top_k);
+    uint32_t* d_n2 = d_n1 + cn;
+    if (se1 > sb1) WALT_CUDA_TRY(cudaMemcpyAsync(s.d_seqs, seqs1 + sb1, se1 - sb1, cudaMemcpyHostToDevice, s.stream));
+    if (se2 > sb2) WALT_CUDA_TRY(cudaMemcpyAsync(s.d_seqs2, seqs2 + sb2, se2 - sb2, cudaMemcpyHostToDevice, s.stream));
+    WALT_CUDA_TRY(cudaMemcpyAsync(s.d_offs, offs1 + r0, ((size_t)cn + 1u) * 8u, cudaMemcpyHostToDevice, s.stream));
+    WALT_CUDA_TRY(cudaMemcpyAsync(s.d_offs2, offs2 + r0, ((size_t)cn + 1u) * 8u, cudaMemcpyHostToDevice, s.stream));
+    uint32_t* q = e->d_flags + 4 + 2u * (k & 1u);
+    // mate 1: C->T against _CT00/_CT01; mate 2: G->A against _GA10/_GA11 (paired.cpp:642-672)
+    if ((rc = launch_pe_mate(e, s.d_seqs, s.d_offs, sb1, cn, max1, 0, max_mismatches, b, top_k, d_r1, d_n1, q, s.stream)))
+      return rc;
+    if ((rc = launch_pe_mate(e, s.d_seqs2, s.d_offs2, sb2, cn, max2, 1, max_mismatches, b, top_k, d_r2, d_n2, q + 1,
+                             s.stream)))
+      return rc;
+    pair_kernel<<<(cn + 127u) / 128u, 128, 0, s.stream>>>(chrom_view(e), d_r1, d_n1, s.d_offs, d_r2, d_n2, s.d_offs2, cn,
+                                                         top_k, max_mismatches, frag_range, d_pairs);
+    WALT_CUDA_TRY(cudaGetLastError());
+    e->stats.n_kernel_launches++;
+    WALT_CUDA_TRY(cudaMemcpyAsync(ranked1 + (size_t)r0 * top_k, d_r1, rk, cudaMemcpyDeviceToHost, s.stream));
+    WALT_CUDA_TRY(cudaMemcpyAsync(ranked2 + (size_t)r0 * top_k, d_r2, rk, cudaMemcpyDeviceToHost, s.stream));
+    WALT_CUDA_TRY(cudaMemcpyAsync(n_ranked1 + r0, d_n1, (size_t)cn * 4u, cudaMemcpyDeviceToHost, s.stream));
+    WALT_CUDA_TRY(cudaMemcpyAsync(n_ranked2 + r0, d_n2, (size_t)cn * 4u, cudaMemcpyDeviceToHost, s.stream));
+    WALT_CUDA_TRY(cudaMemcpyAsync(pairs + r0, d_pairs, (size_t)cn * sizeof(walt_pair), cudaMemcpyDeviceToHost, s.stream));
+    WALT_CUDA_TRY(cudaEventRecord(s.done, s.stream));
+  }
+  for (auto& s : e->slot) WALT_CUDA_TRY(cudaStreamSynchronize(s.stream));
+  return fetch_status(e);
+}
+
+// ---- pinned host memory ------------------------------------------------------------------------
+void* walt_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { set_error("cudaMallocHost failed"); return nullptr; }
+  return p;
+}
+void walt_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

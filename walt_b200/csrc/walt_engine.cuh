@@ -32,21 +32,24 @@ struct DeviceSubIndex {
   uint32_t* table = nullptr;
   uint32_t depth = 0;
   uint32_t* taint_bits = nullptr;
-  uint32_t* taint_key = nullptr;
-  uint32_t* taint_pos = nullptr;
-  uint32_t* taint_len = nullptr;
+  uint32_t* taint_key = nullptr;  // one allocation: key | pos | len
   uint32_t n_taint = 0;
-  uint32_t* counter = nullptr;    // optional 4^12+1 copy (kept by the builder for export)
   uint64_t bytes = 0;
   waltcore::SubIndexView view(int which) const;
+  void release();
 };
 
+// one in-flight chunk of a host batch (double buffered)
 struct BatchSlot {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
   char* d_seqs = nullptr;      size_t seqs_cap = 0;
   uint64_t* d_offs = nullptr;  size_t offs_cap = 0;   // entries
   void* d_out = nullptr;       size_t out_cap = 0;    // bytes
+  // paired-end: second mate + heaps' drained lists
+  char* d_seqs2 = nullptr;     size_t seqs2_cap = 0;
+  uint64_t* d_offs2 = nullptr; size_t offs2_cap = 0;
+  void* d_pe = nullptr;        size_t pe_cap = 0;     // bytes
 };
 
 }  // namespace waltb200
@@ -63,12 +66,12 @@ struct walt_engine {
   waltb200::DeviceSubIndex sub[4];
   waltcore::Pow3 pow3;
   int search_mode = 0;
+  int force_depth = 0;
+  uint32_t chunk_reads = 1u << 20;
   waltb200::BatchSlot slot[2];
-  uint32_t* d_flags = nullptr;     // [0] non-ACGT flag, [1..] spare
+  uint32_t* d_flags = nullptr;               // [0] non-ACGT flag, [1] work-queue head, [2..3] spare
   unsigned long long* d_counters = nullptr;  // lookups, candidates, literal
   walt_stats stats{};
-  // PE scratch
-  void* d_pe = nullptr; size_t pe_cap = 0;
 };
 
 namespace waltb200 {
@@ -77,4 +80,7 @@ int ensure_device(walt_engine* e);
 // after genome+index are resident: choose depth, build table and taint list
 int finalize_subindex(walt_engine* e, int which);
 int alloc_packed_genome(walt_engine* e, DeviceSubIndex& s);
+uint32_t choose_depth(uint32_t index_size);
+// 32 ASCII bases per packed word; `forbidden` = 2-bit code that must not occur (4 = none)
+int pack_ascii_device(const uint8_t* d_ascii, uint64_t n, uint64_t* d_words, uint32_t forbidden, uint32_t* d_bad);
 }  // namespace waltb200
