@@ -51,6 +51,7 @@ struct Sink {
   void maybe_flush() { if (buf.size() > (1u << 20) - 4096) flush(); }
   void close() { flush(); if (f) fclose(f); f = nullptr; }
   void str(const char* s, size_t n) { buf.append(s, n); }
+  template <size_t N> void lit(const char (&s)[N]) { buf.append(s, N - 1); }
   void str(const std::string& s) { buf.append(s); }
   void ch(char c) { buf.push_back(c); }
   void u32(uint32_t v) { char t[12]; int n = 0; do { t[n++] = (char)('0' + v % 10); v /= 10; } while (v); while (n) buf.push_back(t[--n]); }
@@ -185,28 +186,28 @@ void sam_single(Sink& o, const SingleOut& so, const walt_chroms& g, const walt_b
   if (!print_unmapped && !print_mapped) return;
   o.str(name, name_len); o.ch('\t'); o.i32(flag); o.ch('\t');
   if (print_unmapped) {
-    o.str("*\t0\t255\t*\t*\t0\t0\t", 18);
+    o.lit("*\t0\t255\t*\t*\t0\t0\t");
   } else {
     const uint32_t chr = g.chrom_of(bm.genome_pos);
     uint32_t start = bm.genome_pos - g.starts[chr];
     if (rev) start = g.lengths[chr] - start - len;
-    o.str(g.names[chr]); o.ch('\t'); o.u32(start + 1); o.str("\t255\t", 5); o.u32(len); o.str("M\t*\t0\t0\t", 8);
+    o.str(g.names[chr]); o.ch('\t'); o.u32(start + 1); o.lit("\t255\t"); o.u32(len); o.lit("M\t*\t0\t0\t");
   }
   if (rev) o.revcomp(seq, len); else o.str(seq, len);
   o.ch('\t');
   if (rev) o.rev(qual, qlen); else o.str(qual, qlen);
-  o.str("\tNM:i:", 6);
+  o.lit("\tNM:i:");
   o.u32(print_unmapped ? 0u : bm.mismatch);
   o.ch('\n');
   o.maybe_flush();
 }
 
 void sam_header(Sink& o, const walt_chroms& g) {
-  o.str("@HD\tVN:1.0\n");
+  o.lit("@HD\tVN:1.0\n");
   for (size_t i = 0; i < g.names.size(); ++i) {
-    o.str("@SQ\tSN:"); o.str(g.names[i]); o.str("\tLN:"); o.u32(g.lengths[i]); o.ch('\n');
+    o.lit("@SQ\tSN:"); o.str(g.names[i]); o.lit("\tLN:"); o.u32(g.lengths[i]); o.ch('\n');
   }
-  o.str("@PG\tID:WALT\tVN:1.0\tCL:walt\n");   // walt_version "1.0" (util.hpp:41); CL is the literal "walt"
+  o.lit("@PG\tID:WALT\tVN:1.0\tCL:walt\n");   // walt_version "1.0" (util.hpp:41); CL is the literal "walt"
 }
 
 }  // namespace
@@ -299,7 +300,7 @@ int best_pair_out(Sink& o, const walt_chroms& g, const walt_cand& r1, const walt
     }
   }
   const uint32_t start = plus ? s1 : s2;
-  o.str(g.names[c1]); o.ch('\t'); o.u32(start); o.ch('\t'); o.u32(start + (uint32_t)len); o.str("\tFRAG:", 6);
+  o.str(g.names[c1]); o.ch('\t'); o.u32(start); o.ch('\t'); o.u32(start + (uint32_t)len); o.lit("\tFRAG:");
   o.str(name, name_len); o.ch('\t'); o.u32(r1.mismatch + r2.mismatch); o.ch('\t'); o.ch(r1.strand); o.ch('\t');
   o.str(seq); o.ch('\t'); o.str(scr); o.ch('\n');
   o.maybe_flush();
@@ -322,15 +323,15 @@ void sam_mate_line(Sink& o, const SingleOut& so, const walt_chroms& g, const wal
   const bool rev = bm.strand == '-';
   o.str(name, name_len); o.ch('\t'); o.i32(flag); o.ch('\t');
   if (print_unmapped) {
-    o.str("*\t", 2); o.u32(pos); o.str("\t255\t*\t", 7);
+    o.lit("*\t"); o.u32(pos); o.lit("\t255\t*\t");
   } else {
-    o.str(g.names[chr]); o.ch('\t'); o.u32(pos); o.str("\t255\t", 5); o.u32(len); o.str("M\t", 2);
+    o.str(g.names[chr]); o.ch('\t'); o.u32(pos); o.lit("\t255\t"); o.u32(len); o.lit("M\t");
   }
   o.str(rnext); o.ch('\t'); o.u32(pnext); o.ch('\t'); o.i32(tlen); o.ch('\t');
   if (rev) o.revcomp(seq, len); else o.str(seq, len);
   o.ch('\t');
   if (rev) o.rev(qual, qlen); else o.str(qual, qlen);
-  o.str("\tNM:i:", 6); o.u32(nm); o.ch('\n');
+  o.lit("\tNM:i:"); o.u32(nm); o.ch('\n');
   o.maybe_flush();
 }
 
