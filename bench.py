@@ -357,10 +357,8 @@ def run_ours(args):
     same = bool(np.array_equal(h_out.array[:1000].view(np.uint8), wl.d_out[:16000].cpu().numpy()))
     barrier()
 
-    times = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t_dev, t_e2e = (float(x) for x in times.cpu())
+    from walt_b200.sharding import max_over_ranks
+    t_dev, t_e2e = max_over_ranks([t_dev, t_e2e], dist, dev)
     if rank == 0:
         total_reads = n * world * args.steps
         peak, peak_kind = measured_peak_gbs()
