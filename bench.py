@@ -139,6 +139,8 @@ class Workload:
         self.names = [f"chr{i + 1}" for i in range(22)] + ["chrX", "chrY"]
         t0 = time.time()
         self.e = walt_b200.Engine(device)
+        self.e.set_group_width(args.group_width)
+        self.e.set_table_depth(args.table_depth)
         self.e.set_chromosomes(self.lengths, self.names)
         d_fwd = torch.empty(eng.packed_genome_bytes(total), dtype=torch.uint8, device=f"cuda:{device}")
         eng.synth_genome_device(device, total, 3, d_fwd.data_ptr())
@@ -373,7 +375,8 @@ def run_ours(args):
                 "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": config_dict(args, {"index_build_s": round(wl.t_index, 1), "hbm_index_bytes": e.hbm_bytes(),
-                                             "table_depth": e.subindex_info(0)["depth"]}),
+                                             "table_depth": e.subindex_info(0)["depth"],
+                                             "group_width": args.group_width}),
                 "clocks": clocks,
                 "e2e": {"value": total_reads / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(n * rl + 8 * (n + 1)),
                         "d2h_bytes_per_step": int(16 * n), "ms_per_step": 1e3 * t_e2e / args.steps,
@@ -397,6 +400,8 @@ def main():
     ap.add_argument("--reads", type=int, default=10_000_000)
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--no-cpu", action="store_true", help="skip the oracle/reference side legs")
+    ap.add_argument("--group-width", type=int, default=8, help="lanes that own one read (8, 16, 32)")
+    ap.add_argument("--table-depth", type=int, default=0, help="prefix-table depth (0 = auto)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -141,6 +141,8 @@ int walt_engine_set_search_mode(walt_engine* e, int mode);
  * 12..20) and the number of reads per double-buffered host chunk (default 2^20). */
 int walt_engine_set_table_depth(walt_engine* e, int depth);
 int walt_engine_set_chunk_reads(walt_engine* e, uint32_t n);
+/* Lanes of a warp that cooperate on one read: 8 (default; four reads per warp), 16 or 32. */
+int walt_engine_set_group_width(walt_engine* e, uint32_t lanes);
 
 /* ---- pinned host memory for batch buffers --------------------------------------------- */
 void* walt_host_alloc(size_t bytes);

@@ -68,6 +68,7 @@ struct WarpEmu {
   uint32_t slots[2][32];
   uint32_t tags[2][32];
   uint32_t cur = 0;       // running lane
+  uint32_t nf = 32;       // lanes in the emulated group (8, 16 or 32)
   uint32_t n_done = 0;
   LaneFn fn = nullptr;
   void* arg = nullptr;
@@ -85,13 +86,13 @@ struct WarpEmu {
   static void trampoline();
   void yield_next() {
     uint32_t from = cur;
-    uint32_t to = (cur + 1) & 31u;
+    uint32_t to = (cur + 1) % nf;
     cur = to;
     emu_switch(&fib[from].sp, fib[to].sp);
   }
   void run(LaneFn f, void* a) {
     fn = f; arg = a; n_done = 0; cur = 0;
-    for (int i = 0; i < 32; ++i) {
+    for (uint32_t i = 0; i < nf; ++i) {
       fib[i].done = false;
       // initial frame: 6 callee-saved registers + return address (trampoline)
       void** top = (void**)(fib[i].stack + STACK_BYTES);
@@ -112,12 +113,12 @@ void WarpEmu::trampoline() {
   w->fn(w, lane, w->arg);
   w->fib[lane].done = true;
   w->n_done++;
-  if (w->n_done == 32) {
+  if (w->n_done == w->nf) {
     void* dummy;
     emu_switch(&dummy, w->main_sp);
   } else {
     // lanes finish in order; the next one is parked at its last primitive
-    uint32_t to = (lane + 1) & 31u;
+    uint32_t to = (lane + 1) % w->nf;
     w->cur = to;
     void* dummy;
     emu_switch(&dummy, w->fib[to].sp);
@@ -125,40 +126,42 @@ void WarpEmu::trampoline() {
   abort();  // never resumed
 }
 
-// the warp policy handed to walt_core.cuh
+// the group policy handed to walt_core.cuh: WD lanes own one read
+template <uint32_t WD>
 struct EmuWarp {
+  static constexpr uint32_t WIDTH = WD;
   WarpEmu* w;
   uint32_t my_lane;
   uint32_t n_prim = 0;
   uint32_t lane() const { return my_lane; }
-  // every lane deposits v, one full round later all 32 values are visible
+  // every lane deposits v, one full round later all WD values are visible
   const uint32_t* exchange(uint32_t v, uint32_t tag) {
     uint32_t buf = n_prim & 1u;
     ++n_prim;
     w->slots[buf][my_lane] = v;
     w->tags[buf][my_lane] = tag;
     w->yield_next();
-    for (int i = 0; i < 32; ++i)
+    for (uint32_t i = 0; i < WD; ++i)
       if (w->tags[buf][i] != tag) w->diverged = true;
     return w->slots[buf];
   }
   uint32_t ballot(bool p) {
     const uint32_t* s = exchange(p ? 1u : 0u, 1u);
     uint32_t m = 0;
-    for (int i = 0; i < 32; ++i) m |= (s[i] & 1u) << i;
+    for (uint32_t i = 0; i < WD; ++i) m |= (s[i] & 1u) << i;
     return m;
   }
-  uint32_t shfl(uint32_t v, int src) { return exchange(v, 2u)[src & 31]; }
+  uint32_t shfl(uint32_t v, int src) { return exchange(v, 2u)[(uint32_t)src % WD]; }
   uint32_t reduce_add(uint32_t v) {
     const uint32_t* s = exchange(v, 3u);
     uint32_t a = 0;
-    for (int i = 0; i < 32; ++i) a += s[i];
+    for (uint32_t i = 0; i < WD; ++i) a += s[i];
     return a;
   }
   uint32_t reduce_min(uint32_t v) {
     const uint32_t* s = exchange(v, 4u);
     uint32_t a = 0xFFFFFFFFu;
-    for (int i = 0; i < 32; ++i) a = std::min(a, s[i]);
+    for (uint32_t i = 0; i < WD; ++i) a = std::min(a, s[i]);
     return a;
   }
   void sync() { exchange(0u, 5u); }
@@ -293,9 +296,10 @@ struct SeJob {
   uint64_t* scratch; uint32_t* cached_len; Counters* ctr; int* bad;
 };
 
+template <uint32_t WD>
 void se_lane(WarpEmu* w, uint32_t lane, void* arg) {
   SeJob* j = (SeJob*)arg;
-  EmuWarp W{w, lane};
+  EmuWarp<WD> W{w, lane};
   SubIndexView ix2[2] = {j->e->sub[j->ag ? 2 : 0].view(), j->e->sub[j->ag ? 3 : 1].view()};
   ChromView cv = j->e->cv();
   MapConfig cfg; cfg.b = j->b; cfg.literal_all = j->literal;
@@ -323,9 +327,10 @@ struct PeJob {
   uint64_t* scratch; HeapEntry* heap; int* bad;
 };
 
+template <uint32_t WD>
 void pe_lane(WarpEmu* w, uint32_t lane, void* arg) {
   PeJob* j = (PeJob*)arg;
-  EmuWarp W{w, lane};
+  EmuWarp<WD> W{w, lane};
   SubIndexView ix2[2] = {j->e->sub[j->ag ? 2 : 0].view(), j->e->sub[j->ag ? 3 : 1].view()};
   ChromView cv = j->e->cv();
   MapConfig cfg; cfg.b = j->b; cfg.literal_all = j->literal;
@@ -355,7 +360,7 @@ void pe_lane(WarpEmu* w, uint32_t lane, void* arg) {
 }
 
 template <class Job, class Fn>
-int run_parallel(uint32_t n, int threads, Fn make_and_run) {
+int run_parallel(uint32_t n, int threads, uint32_t width, Fn make_and_run) {
   if (threads < 1) threads = 1;
   std::vector<std::thread> pool;
   std::atomic<int> diverged{0};
@@ -364,6 +369,7 @@ int run_parallel(uint32_t n, int threads, Fn make_and_run) {
       uint32_t lo = (uint32_t)((uint64_t)n * t / threads), hi = (uint32_t)((uint64_t)n * (t + 1) / threads);
       if (lo >= hi) return;
       WarpEmu* w = new WarpEmu;
+      w->nf = width;
       g_current = w;
       make_and_run(w, lo, hi);
       if (w->diverged) diverged = 1;
@@ -380,18 +386,19 @@ extern "C" {
 
 // returns 0 ok; 1 = warp primitives diverged (bug); 5 = non-ACGT read
 int emu_map_se(void* h, const char* seqs, const uint64_t* offs, uint32_t n, int ag, uint32_t m,
-               uint32_t b, int literal, emu_best* out, int threads, uint64_t* counters3) {
+               uint32_t b, int literal, emu_best* out, int threads, uint64_t* counters3, uint32_t width) {
+  if (width != 8 && width != 16 && width != 32) return 1;
   EmuEngine* e = (EmuEngine*)h;
   uint32_t max_len = 1;
   for (uint32_t r = 0; r < n; ++r) max_len = std::max<uint32_t>(max_len, (uint32_t)(offs[r + 1] - offs[r]));
   if (max_len > MAX_READ_LEN) return 1;
   std::atomic<int> bad{0};
   std::atomic<uint64_t> c0{0}, c1{0}, c2{0};
-  int div = run_parallel<SeJob>(n, threads, [&](WarpEmu* w, uint32_t lo, uint32_t hi) {
+  int div = run_parallel<SeJob>(n, threads, width, [&](WarpEmu* w, uint32_t lo, uint32_t hi) {
     std::vector<uint64_t> scratch(scratch_words((max_len + 31) / 32) + 8);
     uint32_t cached = 0; Counters ctr{0, 0, 0}; int b_ = 0;
     SeJob j{e, seqs, offs, lo, hi, ag, m, b, literal, out, max_len, scratch.data(), &cached, &ctr, &b_};
-    w->run(se_lane, &j);
+    w->run(width == 8 ? se_lane<8> : width == 16 ? se_lane<16> : se_lane<32>, &j);
     if (b_) bad = 1;
     c0 += ctr.lookups; c1 += ctr.candidates; c2 += ctr.literal;
   });
@@ -402,18 +409,19 @@ int emu_map_se(void* h, const char* seqs, const uint64_t* offs, uint32_t n, int 
 
 int emu_map_pe_mate(void* h, const char* seqs, const uint64_t* offs, uint32_t n, int ag, uint32_t m,
                     uint32_t b, uint32_t top_k, int literal, emu_cand* ranked, uint32_t* n_ranked,
-                    int threads) {
+                    int threads, uint32_t width) {
+  if (width != 8 && width != 16 && width != 32) return 1;
   EmuEngine* e = (EmuEngine*)h;
   uint32_t max_len = 1;
   for (uint32_t r = 0; r < n; ++r) max_len = std::max<uint32_t>(max_len, (uint32_t)(offs[r + 1] - offs[r]));
   if (max_len > MAX_READ_LEN) return 1;
   std::atomic<int> bad{0};
-  int div = run_parallel<PeJob>(n, threads, [&](WarpEmu* w, uint32_t lo, uint32_t hi) {
+  int div = run_parallel<PeJob>(n, threads, width, [&](WarpEmu* w, uint32_t lo, uint32_t hi) {
     std::vector<uint64_t> scratch(scratch_words((max_len + 31) / 32) + 8);
     std::vector<HeapEntry> heap(top_k + 1);
     int b_ = 0;
     PeJob j{e, seqs, offs, lo, hi, ag, m, b, top_k, literal, ranked, n_ranked, max_len, scratch.data(), heap.data(), &b_};
-    w->run(pe_lane, &j);
+    w->run(width == 8 ? pe_lane<8> : width == 16 ? pe_lane<16> : pe_lane<32>, &j);
     if (b_) bad = 1;
   });
   if (div) return 1;

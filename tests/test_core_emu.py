@@ -27,20 +27,20 @@ def _cmp_best(got, want):
         assert bad.size == 0, (f, bad[:5], got[bad[:5]], want[bad[:5]])
 
 
-@pytest.mark.parametrize("literal", [False, True])
-def test_se_emu_matches_reference(engine, literal):
+@pytest.mark.parametrize("literal,width", [(False, 32), (True, 32), (False, 8), (True, 8), (False, 16)])
+def test_se_emu_matches_reference(engine, literal, width):
     for name, ag in (("se_ct.npz", False), ("se_ga.npz", True)):
         z = goldenio.load(name)
         buf, offs = refio.pack_reads(z["reads"])
         for key in [k for k in z.files if k.startswith("best_")]:
             m, b = (int(x[1:]) for x in key[5:].split("_"))
-            rc, out, _ = engine.map_se(buf, offs, refio.BEST_DT, ag=ag, m=m, b=b, literal=literal)
+            rc, out, _ = engine.map_se(buf, offs, refio.BEST_DT, ag=ag, m=m, b=b, literal=literal, width=width)
             assert rc == 0
             _cmp_best(out, z[key])
 
 
-@pytest.mark.parametrize("depth", [0, 12, 13, 16])
-def test_se_edge_emu(depth):
+@pytest.mark.parametrize("depth,width", [(0, 32), (12, 32), (13, 8), (16, 8), (0, 8), (12, 16)])
+def test_se_edge_emu(depth, width):
     hdr, subs = goldenio.genome()
     e = emu.EmuEngine(hdr.lengths)
     for w, sfx in enumerate(refio.SUFFIXES):
@@ -49,13 +49,14 @@ def test_se_edge_emu(depth):
     for ag, pre in ((False, "ct_best_"), (True, "ga_best_")):
         for key in [k for k in z.files if k.startswith(pre)]:
             m, b = (int(x[1:]) for x in key[len(pre):].split("_"))
-            rc, out, _ = e.map_se(z["buf"], z["offs"], refio.BEST_DT, ag=ag, m=m, b=b)
+            rc, out, _ = e.map_se(z["buf"], z["offs"], refio.BEST_DT, ag=ag, m=m, b=b, width=width)
             assert rc == 0
             _cmp_best(out, z[key])
     e.close()
 
 
-def test_pe_emu_matches_reference(engine):
+@pytest.mark.parametrize("width", [32, 8])
+def test_pe_emu_matches_reference(engine, width):
     hdr, _ = goldenio.genome()
     z = goldenio.load("pe.npz")
     L = refio.oracle_lib()
@@ -66,7 +67,7 @@ def test_pe_emu_matches_reference(engine):
         got = {}
         for mate, ag in ((1, False), (2, True)):
             buf, offs = refio.pack_reads(z[f"m{mate}"])
-            rc, ranked, sizes = engine.map_pe_mate(buf, offs, refio.CAND_DT, ag, m=m, top_k=k)
+            rc, ranked, sizes = engine.map_pe_mate(buf, offs, refio.CAND_DT, ag, m=m, top_k=k, width=width)
             assert rc == 0
             assert np.array_equal(sizes, z[f"sizes{mate}_m{m}_k{k}"])
             want = z[f"ranked{mate}_m{m}_k{k}"]

@@ -47,9 +47,10 @@ def test_native_library_is_loaded(engine):
     assert info["depth"] >= 12 and info["n_taint"] > 0
 
 
-@pytest.mark.parametrize("literal", [False, True])
-def test_se_golden(engine, literal):
+@pytest.mark.parametrize("literal,width", [(False, 8), (True, 8), (False, 16), (False, 32), (True, 32)])
+def test_se_golden(engine, literal, width):
     engine.set_search_mode(literal)
+    engine.set_group_width(width)
     try:
         for name, ag in (("se_ct.npz", False), ("se_ga.npz", True)):
             z = goldenio.load(name)
@@ -65,11 +66,13 @@ def test_se_golden(engine, literal):
                     assert st["n_literal"] == st["n_lookups"]
     finally:
         engine.set_search_mode(False)
+        engine.set_group_width(8)
 
 
-@pytest.mark.parametrize("depth", [0, 12, 14, 17])
-def test_se_edge_golden(depth):
+@pytest.mark.parametrize("depth,width", [(0, 8), (12, 8), (14, 16), (17, 32), (12, 32), (15, 8)])
+def test_se_edge_golden(depth, width):
     e = _load_golden_engine(depth)
+    e.set_group_width(width)
     z = goldenio.load("se_edge.npz")
     for ag, pre in ((False, "ct_best_"), (True, "ga_best_")):
         for key in [k for k in z.files if k.startswith(pre)]:
@@ -106,7 +109,9 @@ def test_se_empty_and_errors(engine):
     _cmp_best(out, z["best_m6_b5000"][:50])
 
 
-def test_pe_golden(engine):
+@pytest.mark.parametrize("width", [8, 32])
+def test_pe_golden(engine, width):
+    engine.set_group_width(width)
     hdr, _ = goldenio.genome()
     z = goldenio.load("pe.npz")
     L = refio.oracle_lib()
@@ -154,9 +159,10 @@ def test_se_fresh_genome_vs_oracle():
     hdr, subs = refio.build_index_with_oracle(chroms)
     reads100 = synth.simulate_se_reads(chroms[:3], 20000, 100, seed=7, n_frac=0.0)
     reads150a = synth.simulate_se_reads(chroms[:3], 10000, 150, seed=8, a_rich=True, n_frac=0.0)
-    for depth in (0, 13):
+    for depth, width in ((0, 8), (13, 8), (13, 16), (0, 32)):
         e = walt_b200.Engine(0)
         e.set_table_depth(depth)
+        e.set_group_width(width)
         e.set_chromosomes(hdr.lengths, hdr.names)
         for w, sfx in enumerate(refio.SUFFIXES):
             e.load_subindex(w, subs[sfx].seq, subs[sfx].counter, subs[sfx].index)

@@ -230,24 +230,50 @@ WALT_HD ReadScratch carve_scratch(uint64_t* base, uint32_t nw) {
   return s;
 }
 
-// Pack + convert one ASCII read into sc.R (warp-cooperative). Returns false (uniformly) if a
-// byte is not A/C/G/T.
+// Pack + convert one ASCII read into sc.R (group-cooperative). Returns false (uniformly) if a
+// byte is not A/C/G/T.  A group of W::WIDTH lanes owns the read: with 8 lanes every lane turns
+// 4 consecutive characters into one byte of the packed word (no cross-lane traffic); other
+// widths assemble the word from ballots.
 template <class W>
 WALT_HD bool load_read(W& w, const char* __restrict__ seq, uint32_t read_len, bool ag, ReadScratch& sc) {
   const uint32_t lane = w.lane();
   const uint32_t nw = (read_len + 31u) >> 5;
   bool bad = false;
-  for (uint32_t k = 0; k < nw; ++k) {
-    uint32_t p = 32u * k + lane;
-    uint32_t code = 0;
-    if (p < read_len) {
-      uint32_t c = (uint8_t)seq[p];
-      bad |= !ascii_is_acgt(c);
-      code = convert_code(ascii_code(c), ag);
+  if (W::WIDTH == 8u) {
+    uint8_t* rb = reinterpret_cast<uint8_t*>(sc.R);
+    for (uint32_t k = 0; k < nw; ++k) {
+      uint32_t piece = 0;
+      for (uint32_t j = 0; j < 4u; ++j) {
+        const uint32_t p = 32u * k + 4u * lane + j;
+        uint32_t code = 0;
+        if (p < read_len) {
+          const uint32_t c = (uint8_t)seq[p];
+          bad |= !ascii_is_acgt(c);
+          code = convert_code(ascii_code(c), ag);
+        }
+        piece = (piece << 2) | code;
+      }
+      rb[8u * k + (7u - lane)] = (uint8_t)piece;   // little-endian u64: first base in the top byte
     }
-    uint32_t hi = brev32(w.ballot((code & 2u) != 0u));
-    uint32_t lo = brev32(w.ballot((code & 1u) != 0u));
-    if (lane == 0) sc.R[k] = (spread32(hi) << 1) | spread32(lo);
+  } else {
+    for (uint32_t k = 0; k < nw; ++k) {
+      uint64_t word = 0;
+      for (uint32_t j = 0; j < 32u / W::WIDTH; ++j) {
+        const uint32_t p = 32u * k + j * W::WIDTH + lane;
+        uint32_t code = 0;
+        if (p < read_len) {
+          const uint32_t c = (uint8_t)seq[p];
+          bad |= !ascii_is_acgt(c);
+          code = convert_code(ascii_code(c), ag);
+        }
+        const uint32_t sh = 32u - W::WIDTH;        // ballot bit l -> base j*WIDTH + l of the word
+        const uint32_t hi = brev32(w.ballot((code & 2u) != 0u)) >> sh;
+        const uint32_t lo = brev32(w.ballot((code & 1u) != 0u)) >> sh;
+        const uint64_t part = (spread32(hi) << 1) | spread32(lo);     // 2*WIDTH bits, first base on top
+        word |= part << (64u - 2u * W::WIDTH * (j + 1u));
+      }
+      if (lane == 0) sc.R[k] = word;
+    }
   }
   bool any_bad = w.ballot(bad) != 0u;
   w.sync();
@@ -261,14 +287,15 @@ WALT_HD void build_masks(W& w, uint32_t read_len, ReadScratch& sc) {
   const uint32_t nw = (read_len + 31u) >> 5;
   const uint32_t spr = seed_repeats(read_len);
   for (uint32_t s = 0; s < 3u; ++s) {
-    for (uint32_t k = 0; k < nw; ++k) {
-      uint32_t p = 32u * k + lane;
-      uint32_t vm = brev32(w.ballot(is_verify_position(p, s, spr, read_len)));
-      uint32_t sm = brev32(w.ballot(is_seed_position(p, s, spr)));
-      if (lane == 0) {
-        sc.VM[s * sc.nw + k] = spread32(vm);
-        sc.SM[s * sc.nw + k] = spread32(sm);
+    for (uint32_t k = lane; k < nw; k += W::WIDTH) {
+      uint64_t vm = 0, sm = 0;
+      for (uint32_t j = 0; j < 32u; ++j) {
+        const uint32_t p = 32u * k + j;
+        vm = (vm << 2) | (is_verify_position(p, s, spr, read_len) ? 1ull : 0ull);
+        sm = (sm << 2) | (is_seed_position(p, s, spr) ? 1ull : 0ull);
       }
+      sc.VM[s * sc.nw + k] = vm;
+      sc.SM[s * sc.nw + k] = sm;
     }
   }
   w.sync();
@@ -521,7 +548,7 @@ WALT_HD bool lookup_is_affected(W& w, const SubIndexView& ix, const uint64_t* R,
     if (n_in >= seed_len) continue;     // every probed character is inside the chromosome
     uint32_t e = ix.taint_pos[t];
     bool differ = false;
-    for (uint32_t i = KEY_WEIGHT + lane; i < n_in; i += 32u) {
+    for (uint32_t i = KEY_WEIGHT + lane; i < n_in; i += W::WIDTH) {
       uint32_t off = 3u * i + 1u;
       differ |= packed_base(ix.genome, (uint64_t)e + PAD_BASES + off) != packed_base(R, seed_i + off);
     }
@@ -534,6 +561,7 @@ template <class W, class Sink>
 WALT_HD void seed_lookup(W& w, const SubIndexView& ix, const ChromView& cv, const Pow3& p3,
                          const MapConfig& cfg, const ReadScratch& sc, uint32_t read_len,
                          uint32_t seed_i, uint32_t strand, Sink& sink, Counters& ctr) {
+  constexpr uint32_t WD = W::WIDTH;
   const uint32_t lane = w.lane();
   const uint32_t spr = seed_repeats(read_len);
   const uint32_t seed_len = spr;
@@ -546,26 +574,32 @@ WALT_HD void seed_lookup(W& w, const SubIndexView& ix, const ChromView& cv, cons
 
   // base-3 key of the first min(depth, seed_len) seed characters, and of the first 12
   const uint32_t n_pref = ix.depth < seed_len ? ix.depth : seed_len;
-  uint32_t digit = 0;
-  if (lane < n_pref) digit = ternary_digit(packed_base(R, seed_i + 3u * lane + 1u), ag);
-  uint32_t lo_key = w.reduce_add(lane < n_pref ? digit * p3.v[ix.depth - 1u - lane] : 0u);
-  uint32_t key12 = w.reduce_add(lane < KEY_WEIGHT ? digit * p3.v[KEY_WEIGHT - 1u - lane] : 0u);
-  uint32_t hi_key = lo_key + p3.v[ix.depth - n_pref];
+  uint32_t part = 0, part12 = 0;
+  for (uint32_t i = lane; i < n_pref; i += WD) {
+    const uint32_t d = ternary_digit(packed_base(R, seed_i + 3u * i + 1u), ag);
+    part += d * p3.v[ix.depth - 1u - i];
+    if (i < KEY_WEIGHT) part12 += d * p3.v[KEY_WEIGHT - 1u - i];
+  }
+  const uint32_t lo_key = w.reduce_add(part);
+  const uint32_t key12 = w.reduce_add(part12);
+  const uint32_t hi_key = lo_key + p3.v[ix.depth - n_pref];
 
-  // reference: counter[h] == counter[h+1] -> continue (mapping.cpp:268-272)
-  const uint32_t k12_span = p3.v[ix.depth - KEY_WEIGHT];
-  const uint32_t bucket_lo = ix.table[key12 * k12_span];
-  const uint32_t bucket_hi = ix.table[(key12 + 1u) * k12_span];
-  if (bucket_lo == bucket_hi) return;
-  ctr.lookups++;
+  // the table range of the read's seed prefix; an empty 12-mer bucket (reference:
+  // counter[h] == counter[h+1] -> continue, mapping.cpp:268-272) has an empty range too
+  const uint32_t lo = ix.table[lo_key], hi = ix.table[hi_key];
+  const uint32_t tainted = (ix.taint_bits[key12 >> 5] >> (key12 & 31u)) & 1u;
 
   bool literal = cfg.literal_all != 0u;
-  if (!literal && ((ix.taint_bits[key12 >> 5] >> (key12 & 31u)) & 1u))
-    literal = lookup_is_affected(w, ix, R, seed_i, seed_len, key12);
+  if (!literal && tainted) literal = lookup_is_affected(w, ix, R, seed_i, seed_len, key12);
 
   uint32_t first, last_excl;  // candidate slots [first, last_excl)
   bool need_seed_check = false;
   if (literal) {
+    const uint32_t k12_span = p3.v[ix.depth - KEY_WEIGHT];
+    const uint32_t bucket_lo = ix.table[key12 * k12_span];
+    const uint32_t bucket_hi = ix.table[(key12 + 1u) * k12_span];
+    if (bucket_lo == bucket_hi) return;
+    ctr.lookups++;
     ctr.literal++;
     uint32_t f = bucket_lo, s = bucket_hi;
     literal_index_region(ix, cv.genome_len, R, seed_i, seed_len, f, s);
@@ -573,19 +607,19 @@ WALT_HD void seed_lookup(W& w, const SubIndexView& ix, const ChromView& cv, cons
     if (f > s) return;                   // failed search: empty candidate loop
     first = f; last_excl = s + 1u;
   } else {
-    uint32_t lo = ix.table[lo_key], hi = ix.table[hi_key];
     if (lo == hi) return;
-    if (hi - lo <= 32u) {
+    ctr.lookups++;
+    if (hi - lo <= WD) {
       first = lo; last_excl = hi; need_seed_check = true;
     } else {
-      // warp-wide 33-ary lower bound, then upper bound, on whole-seed compares
+      // group-wide (WD+1)-ary lower bound, then upper bound, on whole-seed compares
       uint32_t l = lo, h = hi;
-      while (h - l > 32u) {
-        uint32_t p = l + (uint32_t)(((uint64_t)(lane + 1u) * (h - l)) / 33u);
+      while (h - l > WD) {
+        uint32_t p = l + (uint32_t)(((uint64_t)(lane + 1u) * (h - l)) / (WD + 1u));
         int c = compare_seed(ix.genome, (uint64_t)ix.index[p] + PAD_BASES - seed_i, R, SM, nws);
         uint32_t cnt = popc32(w.ballot(c < 0));
         uint32_t nl = cnt ? w.shfl(p, (int)cnt - 1) + 1u : l;
-        uint32_t nh = cnt < 32u ? w.shfl(p, (int)(cnt & 31u)) : h;
+        uint32_t nh = cnt < WD ? w.shfl(p, (int)(cnt & (WD - 1u))) : h;
         l = nl; h = nh;
       }
       {
@@ -595,12 +629,12 @@ WALT_HD void seed_lookup(W& w, const SubIndexView& ix, const ChromView& cv, cons
         first = l + popc32(w.ballot(lt));
       }
       l = first; h = hi;
-      while (h - l > 32u) {
-        uint32_t p = l + (uint32_t)(((uint64_t)(lane + 1u) * (h - l)) / 33u);
+      while (h - l > WD) {
+        uint32_t p = l + (uint32_t)(((uint64_t)(lane + 1u) * (h - l)) / (WD + 1u));
         int c = compare_seed(ix.genome, (uint64_t)ix.index[p] + PAD_BASES - seed_i, R, SM, nws);
         uint32_t cnt = popc32(w.ballot(c <= 0));
         uint32_t nl = cnt ? w.shfl(p, (int)cnt - 1) + 1u : l;
-        uint32_t nh = cnt < 32u ? w.shfl(p, (int)(cnt & 31u)) : h;
+        uint32_t nh = cnt < WD ? w.shfl(p, (int)(cnt & (WD - 1u))) : h;
         l = nl; h = nh;
       }
       {
@@ -614,7 +648,7 @@ WALT_HD void seed_lookup(W& w, const SubIndexView& ix, const ChromView& cv, cons
     }
   }
 
-  for (uint32_t base = first; base < last_excl; base += 32u) {
+  for (uint32_t base = first; base < last_excl; base += WD) {
     const uint32_t slot = base + lane;
     bool valid = slot < last_excl;
     uint32_t g = 0, mm = 0;

@@ -31,13 +31,25 @@ int fail(int code, const std::string& msg) { g_error = msg; return code; }
 // ------------------------------------------------------------------------------------------
 // hardware warp policy for walt_core.cuh
 // ------------------------------------------------------------------------------------------
-struct HwWarp {
-  __device__ __forceinline__ uint32_t lane() const { return threadIdx.x & 31u; }
-  __device__ __forceinline__ uint32_t ballot(bool p) const { return __ballot_sync(0xFFFFFFFFu, p); }
-  __device__ __forceinline__ uint32_t shfl(uint32_t v, int src) const { return __shfl_sync(0xFFFFFFFFu, v, src); }
-  __device__ __forceinline__ uint32_t reduce_add(uint32_t v) const { return __reduce_add_sync(0xFFFFFFFFu, v); }
-  __device__ __forceinline__ uint32_t reduce_min(uint32_t v) const { return __reduce_min_sync(0xFFFFFFFFu, v); }
-  __device__ __forceinline__ void sync() const { __syncwarp(); }
+// A group of WD lanes (8, 16 or 32) of a hardware warp owns one read; the groups of a warp run
+// independently (Volta+ independent thread scheduling), every collective names only the group's
+// lanes.  Ballots and shuffle sources are group-relative.
+template <uint32_t WD>
+struct HwGroup {
+  static constexpr uint32_t WIDTH = WD;
+  uint32_t base;    // first lane of the group inside the warp
+  uint32_t gmask;   // the group's lanes
+  __device__ __forceinline__ HwGroup() {
+    const uint32_t l = threadIdx.x & 31u;
+    base = l & ~(WD - 1u);
+    gmask = WD == 32u ? 0xFFFFFFFFu : (((1u << WD) - 1u) << base);
+  }
+  __device__ __forceinline__ uint32_t lane() const { return (threadIdx.x & 31u) - base; }
+  __device__ __forceinline__ uint32_t ballot(bool p) const { return (__ballot_sync(gmask, p) & gmask) >> base; }
+  __device__ __forceinline__ uint32_t shfl(uint32_t v, int src) const { return __shfl_sync(gmask, v, (int)base + src); }
+  __device__ __forceinline__ uint32_t reduce_add(uint32_t v) const { return __reduce_add_sync(gmask, v); }
+  __device__ __forceinline__ uint32_t reduce_min(uint32_t v) const { return __reduce_min_sync(gmask, v); }
+  __device__ __forceinline__ void sync() const { __syncwarp(gmask); }
 };
 
 SubIndexView DeviceSubIndex::view(int which) const {
@@ -235,13 +247,14 @@ struct SeArgs {
   unsigned long long* counters;  // optional
 };
 
+template <uint32_t WD>
 __global__ void __launch_bounds__(BLOCK_THREADS)
 se_map_kernel(const __grid_constant__ SeArgs a) {
   extern __shared__ uint64_t smem[];
-  HwWarp w;
+  HwGroup<WD> w;
   const uint32_t lane = w.lane();
-  const uint32_t warp_in_block = threadIdx.x >> 5;
-  ReadScratch sc = carve_scratch(smem + (size_t)warp_in_block * scratch_words(a.nw_max), a.nw_max);
+  const uint32_t group_in_block = threadIdx.x / WD;
+  ReadScratch sc = carve_scratch(smem + (size_t)group_in_block * scratch_words(a.nw_max), a.nw_max);
   uint32_t cached_len = 0;
   Counters ctr{0u, 0u, 0u};
   bool bad = false;
@@ -293,14 +306,15 @@ struct PeArgs {
 };
 
 // PairEndMapping (paired.cpp:106-201) for one mate batch + the heap drain (paired.cpp:684-692)
+template <uint32_t WD>
 __global__ void __launch_bounds__(BLOCK_THREADS)
 pe_map_kernel(const __grid_constant__ PeArgs a) {
   extern __shared__ uint64_t smem[];
-  HwWarp w;
+  HwGroup<WD> w;
   const uint32_t lane = w.lane();
-  const uint32_t warp_in_block = threadIdx.x >> 5;
-  const uint32_t per_warp = scratch_words(a.nw_max) + a.top_k + 1u;  // HeapEntry is 8 bytes
-  uint64_t* mine = smem + (size_t)warp_in_block * per_warp;
+  const uint32_t group_in_block = threadIdx.x / WD;
+  const uint32_t per_group = scratch_words(a.nw_max) + a.top_k + 1u;  // HeapEntry is 8 bytes
+  uint64_t* mine = smem + (size_t)group_in_block * per_group;
   ReadScratch sc = carve_scratch(mine, a.nw_max);
   HeapEntry* heap = reinterpret_cast<HeapEntry*>(mine + scratch_words(a.nw_max));
   uint32_t cached_len = 0;
@@ -333,7 +347,7 @@ pe_map_kernel(const __grid_constant__ PeArgs a) {
     {  // unused slots are defined (zero) so whole-array compares and copies are deterministic
       const uint32_t used = w.shfl(hsize, 0);
       uint32_t* z = reinterpret_cast<uint32_t*>(a.ranked + (size_t)r * a.top_k + used);
-      for (uint32_t i = lane; i < (a.top_k - used) * 3u; i += 32u) z[i] = 0u;
+      for (uint32_t i = lane; i < (a.top_k - used) * 3u; i += WD) z[i] = 0u;
     }
   }
   if (lane == 0) {
@@ -371,19 +385,20 @@ __global__ void pair_kernel(ChromView cv, const walt_cand* __restrict__ r1, cons
 // ------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------
-static size_t se_smem_bytes(uint32_t nw_max) { return (size_t)WARPS_PER_BLOCK * scratch_words(nw_max) * 8u; }
-static size_t pe_smem_bytes(uint32_t nw_max, uint32_t top_k) {
-  return (size_t)WARPS_PER_BLOCK * (scratch_words(nw_max) + top_k + 1u) * 8u;
+static size_t se_smem_bytes(uint32_t nw_max, uint32_t wd) { return (size_t)(BLOCK_THREADS / wd) * scratch_words(nw_max) * 8u; }
+static size_t pe_smem_bytes(uint32_t nw_max, uint32_t top_k, uint32_t wd) {
+  return (size_t)(BLOCK_THREADS / wd) * (scratch_words(nw_max) + top_k + 1u) * 8u;
 }
 
 template <class K>
-static int grid_for(walt_engine* e, K kernel, size_t smem, uint32_t n, uint32_t* grid) {
+static int grid_for(walt_engine* e, K kernel, size_t smem, uint32_t n, uint32_t wd, uint32_t* grid) {
   int per_sm = 0;
   WALT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   WALT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)BLOCK_THREADS, smem));
   if (per_sm < 1) return fail(WALT_ECUDA, "mapping kernel does not fit on an SM");
   uint64_t g = (uint64_t)per_sm * (uint64_t)e->sm_count;   // persistent: a multiple of the SM count
-  const uint64_t need = ((uint64_t)n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+  const uint32_t per_block = BLOCK_THREADS / wd;
+  const uint64_t need = ((uint64_t)n + per_block - 1) / per_block;
   if (need < g) g = need ? need : 1;
   *grid = (uint32_t)g;
   return WALT_OK;
@@ -410,12 +425,14 @@ static int launch_se(walt_engine* e, const char* d_seqs, const uint64_t* d_offs,
   a.nw_max = std::max<uint32_t>(1u, (max_read_len + 31u) / 32u);
   a.ag = ag ? 1u : 0u; a.max_mismatches = m; a.out = d_out; a.flags = e->d_flags; a.queue = d_queue;
   a.counters = e->d_counters;
-  const size_t smem = se_smem_bytes(a.nw_max);
+  const uint32_t wd = e->group_width;
+  const size_t smem = se_smem_bytes(a.nw_max, wd);
   uint32_t grid = 0;
-  int rc = grid_for(e, se_map_kernel, smem, n, &grid);
+  auto kernel = wd == 8u ? se_map_kernel<8> : wd == 16u ? se_map_kernel<16> : se_map_kernel<32>;
+  int rc = grid_for(e, kernel, smem, n, wd, &grid);
   if (rc) return rc;
   WALT_CUDA_TRY(cudaMemsetAsync(d_queue, 0, 4, st));
-  se_map_kernel<<<grid, BLOCK_THREADS, smem, st>>>(a);
+  kernel<<<grid, BLOCK_THREADS, smem, st>>>(a);
   WALT_CUDA_TRY(cudaGetLastError());
   e->stats.n_kernel_launches++;
   return WALT_OK;
@@ -434,12 +451,14 @@ static int launch_pe_mate(walt_engine* e, const char* d_seqs, const uint64_t* d_
   a.nw_max = std::max<uint32_t>(1u, (max_read_len + 31u) / 32u);
   a.ag = ag ? 1u : 0u; a.max_mismatches = m; a.top_k = top_k; a.ranked = d_ranked; a.n_ranked = d_nranked;
   a.flags = e->d_flags; a.queue = d_queue; a.counters = e->d_counters;
-  const size_t smem = pe_smem_bytes(a.nw_max, top_k);
+  const uint32_t wd = e->group_width;
+  const size_t smem = pe_smem_bytes(a.nw_max, top_k, wd);
   uint32_t grid = 0;
-  int rc = grid_for(e, pe_map_kernel, smem, n, &grid);
+  auto kernel = wd == 8u ? pe_map_kernel<8> : wd == 16u ? pe_map_kernel<16> : pe_map_kernel<32>;
+  int rc = grid_for(e, kernel, smem, n, wd, &grid);
   if (rc) return rc;
   WALT_CUDA_TRY(cudaMemsetAsync(d_queue, 0, 4, st));
-  pe_map_kernel<<<grid, BLOCK_THREADS, smem, st>>>(a);
+  kernel<<<grid, BLOCK_THREADS, smem, st>>>(a);
   WALT_CUDA_TRY(cudaGetLastError());
   e->stats.n_kernel_launches++;
   return WALT_OK;
@@ -735,6 +754,12 @@ int walt_engine_set_table_depth(walt_engine* e, int depth) {
   if (!e || (depth != 0 && (depth < (int)KEY_WEIGHT || depth > (int)MAX_DEPTH)))
     return fail(WALT_EINVAL, "table depth must be 0 (auto) or 12..20");
   e->force_depth = depth;
+  return WALT_OK;
+}
+
+int walt_engine_set_group_width(walt_engine* e, uint32_t lanes) {
+  if (!e || (lanes != 8u && lanes != 16u && lanes != 32u)) return fail(WALT_EINVAL, "group width must be 8, 16 or 32");
+  e->group_width = lanes;
   return WALT_OK;
 }
 

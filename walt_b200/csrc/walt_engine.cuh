@@ -67,6 +67,7 @@ struct walt_engine {
   waltcore::Pow3 pow3;
   int search_mode = 0;
   int force_depth = 0;
+  uint32_t group_width = 8;   // lanes that own one read (8, 16 or 32)
   uint32_t chunk_reads = 1u << 20;
   waltb200::BatchSlot slot[2];
   uint32_t* d_flags = nullptr;               // [0] non-ACGT flag, [1] work-queue head, [2..3] spare

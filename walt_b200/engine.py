@@ -192,6 +192,9 @@ class Engine:
     def set_table_depth(self, depth):
         self._check(self.L.walt_engine_set_table_depth(self.h, C.c_int(depth)))
 
+    def set_group_width(self, lanes):
+        self._check(self.L.walt_engine_set_group_width(self.h, C.c_uint32(lanes)))
+
     def set_chunk_reads(self, n):
         self._check(self.L.walt_engine_set_chunk_reads(self.h, C.c_uint32(n)))
 
