@@ -174,11 +174,12 @@ struct EmuWarp {
 struct EmuSubIndex {
   std::vector<uint64_t> genome;
   std::vector<uint32_t> index, table, taint_bits, taint_key, taint_pos, taint_len;
+  std::vector<Entry> entries;
   uint32_t depth = 0, ag = 0;
   uint32_t unsorted = 0;
   SubIndexView view() const {
     SubIndexView v;
-    v.genome = genome.data(); v.index = index.data(); v.table = table.data();
+    v.genome = genome.data(); v.entries = entries.data(); v.table = table.data();
     v.taint_bits = taint_bits.data(); v.taint_key = taint_key.data();
     v.taint_pos = taint_pos.data(); v.taint_len = taint_len.data();
     v.n_taint = (uint32_t)taint_key.size(); v.index_size = (uint32_t)index.size();
@@ -242,6 +243,7 @@ int emu_engine_load_subindex(void* h, int which, const char* seq, const uint32_t
   s.depth = force_depth > 0 ? (uint32_t)force_depth : choose_depth(index_size);
   const uint32_t n_keys = e->p3.v[s.depth];
   s.table.assign((size_t)n_keys + 1, 0);
+  s.entries.assign((size_t)index_size + 64, Entry{0u, 0u});
   // table fill == build_table_kernel
   ChromView cv = e->cv();
   uint32_t prev_key = 0;
@@ -252,6 +254,8 @@ int emu_engine_load_subindex(void* h, int which, const char* seq, const uint32_t
       uint32_t en = s.index[i];
       uint32_t chr = chrom_of(cv.starts, cv.n_chr, en);
       key = entry_table_key(s.genome.data(), en, cv.starts[chr + 1], s.depth, s.ag, e->p3);
+      s.entries[i].pos = en;
+      s.entries[i].fp = entry_fingerprint(s.genome.data(), en, cv.starts[chr + 1], s.depth, s.ag, e->p3);
     } else {
       key = n_keys;
     }

@@ -126,11 +126,11 @@ __global__ void unpack_ascii_kernel(const uint64_t* __restrict__ genome, uint64_
 }
 
 // reference hash value (util.hpp:175-182) of every index entry -> bucket sizes
-__global__ void hash_hist_kernel(const uint64_t* __restrict__ genome, const uint32_t* __restrict__ index, uint32_t n,
+__global__ void hash_hist_kernel(const uint64_t* __restrict__ genome, const Entry* __restrict__ entries, uint32_t n,
                                  uint32_t* __restrict__ counter) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint32_t e = index[i];
+  const uint32_t e = entries[i].pos;
   uint32_t h = 0;
   for (uint32_t k = 0; k < KEY_WEIGHT; ++k) h = (h << 2) | packed_base(genome, (uint64_t)e + PAD_BASES + 3u * k + 1u);
   atomicAdd(counter + h + 1u, 1u);   // shifted by one: an inclusive scan then yields bucket starts
@@ -271,7 +271,6 @@ static int build_subindex_device(walt_engine* e, int which, const uint64_t* d_fw
   cleanup();
   s.index_size = (uint32_t)n;
   WALT_CUDA_TRY(cudaMemset(s.index + n, 0, 64u * 4u));
-  s.bytes += (cap + 64u) * 4u;
   return finalize_subindex(e, which);
 }
 
@@ -338,7 +337,7 @@ int walt_engine_export_subindex(walt_engine* e, int which, char* sequence, uint3
     uint32_t* d = nullptr;
     WALT_CUDA_TRY(cudaMalloc(&d, NC * 4u));
     WALT_CUDA_TRY(cudaMemset(d, 0, NC * 4u));
-    if (s.index_size) hash_hist_kernel<<<blocks_for(s.index_size, T), T>>>(s.genome, s.index, s.index_size, d);
+    if (s.index_size) hash_hist_kernel<<<blocks_for(s.index_size, T), T>>>(s.genome, s.entries, s.index_size, d);
     size_t tb = 0;
     void* tmp = nullptr;
     cub::DeviceScan::InclusiveSum(nullptr, tb, d, d, (int)NC);
@@ -348,8 +347,8 @@ int walt_engine_export_subindex(walt_engine* e, int which, char* sequence, uint3
     cudaFree(tmp); cudaFree(d);
     if (ce != cudaSuccess) return fail(WALT_ECUDA, cudaGetErrorString(ce));
   }
-  if (index && s.index_size)
-    WALT_CUDA_TRY(cudaMemcpy(index, s.index, (size_t)s.index_size * 4u, cudaMemcpyDeviceToHost));
+  if (index && s.index_size)   // strided copy: the position half of every {position, fingerprint} entry
+    WALT_CUDA_TRY(cudaMemcpy2D(index, 4, s.entries, sizeof(Entry), 4, s.index_size, cudaMemcpyDeviceToHost));
   return WALT_OK;
 }
 

@@ -11,7 +11,10 @@
 //   genome : 2 bits/base (A0 C1 G2 T3), 32 bases per 64-bit word, first base in the top bits,
 //            so that masked word compares are lexicographic; PAD_BASES zero bases in front
 //            and >= TAIL_PAD_WORDS zero words behind.
-//   index  : the .dbindex position array, verbatim (reference.cpp:302-322).
+//   entries: the .dbindex position array, verbatim order (reference.cpp:302-322), each position
+//            paired with a 32-bit fingerprint = its seed characters depth..depth+19 as a base-3
+//            number (past-the-chromosome-end -> digit 0), so a table range is narrowed to the
+//            read's 40-character seed prefix by integer compares, without touching the genome.
 //   table  : T[k] = first slot of `index` whose first `depth` seed characters, read as a
 //            base-3 number (3-letter alphabet), are >= k.  depth >= 12, so T restricted to
 //            12-character prefixes IS the reference's counter[] (reference.cpp:192-229).
@@ -48,6 +51,7 @@ constexpr uint32_t MAX_WORDS = MAX_READ_LEN / 32;
 constexpr uint32_t TAIL_PAD_WORDS = MAX_WORDS + 8;
 constexpr uint32_t TAINT_SPAN = 148;     // largest probed offset: 3*49+1 (seed_len 50)
 constexpr uint32_t MAX_DEPTH = 20;
+constexpr uint32_t FP_DIGITS = 20;       // seed characters depth .. depth+19 kept beside each position
 constexpr uint32_t N_KEY12 = 531441;     // 3^12 reachable 12-mers of a 3-letter genome
 constexpr uint32_t BUCKET_ERASE = 500000;  // reference.cpp:212
 
@@ -157,9 +161,11 @@ WALT_HD bool is_verify_position(uint32_t p, uint32_t s, uint32_t spr, uint32_t r
 // ------------------------------------------------------------------------------------------
 // views
 // ------------------------------------------------------------------------------------------
+struct alignas(8) Entry { uint32_t pos; uint32_t fp; };
+
 struct SubIndexView {
   const uint64_t* genome;      // packed, PAD_BASES in front
-  const uint32_t* index;
+  const Entry* entries;        // index_size (+ readable pad)
   const uint32_t* table;       // 3^depth + 1 entries
   const uint32_t* taint_bits;  // N_KEY12 bits
   const uint32_t* taint_key;   // sorted 12-mer keys (base 3) of tainted positions
@@ -203,6 +209,21 @@ WALT_HD uint32_t entry_table_key(const uint64_t* __restrict__ genome, uint32_t e
     key += d * p3.v[depth - 1u - i];
   }
   return key;
+}
+
+// Fingerprint of index entry `e`: seed characters depth .. depth+FP_DIGITS-1 as a base-3 number,
+// same truncation rule.  Monotone non-decreasing inside a table range.
+WALT_HD uint32_t entry_fingerprint(const uint64_t* __restrict__ genome, uint32_t e, uint32_t chrom_end,
+                                   uint32_t depth, bool ag, const Pow3& p3) {
+  uint32_t avail = chrom_end - e;
+  uint32_t fp = 0;
+  for (uint32_t i = 0; i < FP_DIGITS; ++i) {
+    uint32_t off = 3u * (depth + i) + 1u;
+    uint32_t d = 0;
+    if (off < avail) d = ternary_digit(packed_base(genome, (uint64_t)e + PAD_BASES + off), ag);
+    fp += d * p3.v[FP_DIGITS - 1u - i];
+  }
+  return fp;
 }
 
 // 12-mer key (base 3) of a genome position; used for the taint list
@@ -371,7 +392,7 @@ WALT_HD void literal_index_region(const SubIndexView& ix, uint32_t genome_len, c
       uint32_t low = l, high = u;
       while (low < high) {
         uint32_t mid = low + (high - low) / 2u;
-        uint32_t c = literal_char(ix.genome, (uint64_t)ix.index[mid] + cp, genome_len);
+        uint32_t c = literal_char(ix.genome, (uint64_t)ix.entries[mid].pos + cp, genome_len);
         if (c >= ch) high = mid; else low = mid + 1u;
       }
       l = low;
@@ -380,12 +401,12 @@ WALT_HD void literal_index_region(const SubIndexView& ix, uint32_t genome_len, c
       uint32_t low = l, high = u;
       while (low < high) {
         uint32_t mid = low + (high - low + 1u) / 2u;
-        uint32_t c = literal_char(ix.genome, (uint64_t)ix.index[mid] + cp, genome_len);
+        uint32_t c = literal_char(ix.genome, (uint64_t)ix.entries[mid].pos + cp, genome_len);
         if (c <= ch) low = mid; else high = mid - 1u;
       }
       u = low;
     }
-    if (l == u && ch != literal_char(ix.genome, (uint64_t)ix.index[l] + cp, genome_len)) {
+    if (l == u && ch != literal_char(ix.genome, (uint64_t)ix.entries[l].pos + cp, genome_len)) {
       first = 1u; second = 0u;
       return;
     }
@@ -557,6 +578,21 @@ WALT_HD bool lookup_is_affected(W& w, const SubIndexView& ix, const uint64_t* R,
   return affected;
 }
 
+// (WD+1)-ary narrowing of [l, h) to at most WD slots around the first slot whose value is not
+// `below` (pred(slot) true for a prefix of the range).
+template <class W, class Pred>
+WALT_HD void kary_narrow(W& w, uint32_t& l, uint32_t& h, Pred below) {
+  constexpr uint32_t WD = W::WIDTH;
+  const uint32_t lane = w.lane();
+  while (h - l > WD) {
+    const uint32_t p = l + (uint32_t)(((uint64_t)(lane + 1u) * (h - l)) / (WD + 1u));
+    const uint32_t cnt = popc32(w.ballot(below(p)));
+    const uint32_t nl = cnt ? w.shfl(p, (int)cnt - 1) + 1u : l;
+    const uint32_t nh = cnt < WD ? w.shfl(p, (int)(cnt & (WD - 1u))) : h;
+    l = nl; h = nh;
+  }
+}
+
 template <class W, class Sink>
 WALT_HD void seed_lookup(W& w, const SubIndexView& ix, const ChromView& cv, const Pow3& p3,
                          const MapConfig& cfg, const ReadScratch& sc, uint32_t read_len,
@@ -572,17 +608,22 @@ WALT_HD void seed_lookup(W& w, const SubIndexView& ix, const ChromView& cv, cons
   const uint64_t* VM = sc.VM + seed_i * sc.nw;
   const uint64_t* SM = sc.SM + seed_i * sc.nw;
 
-  // base-3 key of the first min(depth, seed_len) seed characters, and of the first 12
+  // base-3 numbers of the read's seed characters: table key over the first min(depth, seed_len),
+  // 12-mer key, fingerprint over the next min(FP_DIGITS, seed_len - depth)
   const uint32_t n_pref = ix.depth < seed_len ? ix.depth : seed_len;
-  uint32_t part = 0, part12 = 0;
-  for (uint32_t i = lane; i < n_pref; i += WD) {
+  const uint32_t n_fp = seed_len > ix.depth ? (seed_len - ix.depth < FP_DIGITS ? seed_len - ix.depth : FP_DIGITS) : 0u;
+  uint32_t part = 0, part12 = 0, partfp = 0;
+  for (uint32_t i = lane; i < n_pref + n_fp; i += WD) {
     const uint32_t d = ternary_digit(packed_base(R, seed_i + 3u * i + 1u), ag);
-    part += d * p3.v[ix.depth - 1u - i];
+    if (i < n_pref) part += d * p3.v[ix.depth - 1u - i];
+    else partfp += d * p3.v[FP_DIGITS - 1u - (i - n_pref)];
     if (i < KEY_WEIGHT) part12 += d * p3.v[KEY_WEIGHT - 1u - i];
   }
   const uint32_t lo_key = w.reduce_add(part);
   const uint32_t key12 = w.reduce_add(part12);
   const uint32_t hi_key = lo_key + p3.v[ix.depth - n_pref];
+  const uint32_t fp_lo = w.reduce_add(partfp);
+  const uint32_t fp_span = p3.v[FP_DIGITS - n_fp] - 1u;   // fingerprints in [fp_lo, fp_lo + fp_span] match
 
   // the table range of the read's seed prefix; an empty 12-mer bucket (reference:
   // counter[h] == counter[h+1] -> continue, mapping.cpp:268-272) has an empty range too
@@ -593,7 +634,6 @@ WALT_HD void seed_lookup(W& w, const SubIndexView& ix, const ChromView& cv, cons
   if (!literal && tainted) literal = lookup_is_affected(w, ix, R, seed_i, seed_len, key12);
 
   uint32_t first, last_excl;  // candidate slots [first, last_excl)
-  bool need_seed_check = false;
   if (literal) {
     const uint32_t k12_span = p3.v[ix.depth - KEY_WEIGHT];
     const uint32_t bucket_lo = ix.table[key12 * k12_span];
@@ -609,65 +649,84 @@ WALT_HD void seed_lookup(W& w, const SubIndexView& ix, const ChromView& cv, cons
   } else {
     if (lo == hi) return;
     ctr.lookups++;
-    if (hi - lo <= WD) {
-      first = lo; last_excl = hi; need_seed_check = true;
-    } else {
-      // group-wide (WD+1)-ary lower bound, then upper bound, on whole-seed compares
-      uint32_t l = lo, h = hi;
-      while (h - l > WD) {
-        uint32_t p = l + (uint32_t)(((uint64_t)(lane + 1u) * (h - l)) / (WD + 1u));
-        int c = compare_seed(ix.genome, (uint64_t)ix.index[p] + PAD_BASES - seed_i, R, SM, nws);
-        uint32_t cnt = popc32(w.ballot(c < 0));
-        uint32_t nl = cnt ? w.shfl(p, (int)cnt - 1) + 1u : l;
-        uint32_t nh = cnt < WD ? w.shfl(p, (int)(cnt & (WD - 1u))) : h;
-        l = nl; h = nh;
+    // 1. narrow to the slots whose fingerprint matches (integer compares on the entry array)
+    uint32_t l = lo, h = hi;
+    kary_narrow(w, l, h, [&](uint32_t p) { return ix.entries[p].fp < fp_lo; });
+    Entry en; en.pos = 0u; en.fp = 0u;
+    const bool in_chunk = l + lane < h;
+    if (in_chunk) en = ix.entries[l + lane];
+    const uint32_t below = w.ballot(in_chunk && en.fp < fp_lo);
+    const uint32_t match = w.ballot(in_chunk && en.fp >= fp_lo && en.fp - fp_lo <= fp_span);
+    const uint32_t f0 = l + popc32(below);
+    const uint32_t n_match = popc32(match);
+    // the run of matches starts at f0; it is complete if it stops before the chunk does, or
+    // the chunk reaches the end of the table range
+    const bool complete = (f0 + n_match < h) || (h == hi);
+    if (complete) {
+      if (n_match == 0u) return;
+      // 2a. common case: the lanes already hold the candidates -- one genome window each
+      const bool cand = ((match >> lane) & 1u) != 0u;
+      uint32_t g = 0, mm = 0;
+      bool seed_eq = false, valid = false;
+      if (cand) {
+        const uint32_t e = en.pos;
+        WindowResult r = compare_window(ix.genome, (uint64_t)e + PAD_BASES - seed_i, R, VM, SM, nw);
+        mm = r.mismatches;
+        seed_eq = r.seed_equal;
+        const uint32_t chr = chrom_of(cv.starts, cv.n_chr, e);   // bounds, mapping.cpp:281-286
+        g = e - seed_i;
+        valid = seed_eq && (e - cv.starts[chr] >= seed_i) && !(g + read_len >= cv.starts[chr + 1u]);
       }
-      {
-        bool lt = false;
-        if (l + lane < h)
-          lt = compare_seed(ix.genome, (uint64_t)ix.index[l + lane] + PAD_BASES - seed_i, R, SM, nws) < 0;
-        first = l + popc32(w.ballot(lt));
-      }
-      l = first; h = hi;
-      while (h - l > WD) {
-        uint32_t p = l + (uint32_t)(((uint64_t)(lane + 1u) * (h - l)) / (WD + 1u));
-        int c = compare_seed(ix.genome, (uint64_t)ix.index[p] + PAD_BASES - seed_i, R, SM, nws);
-        uint32_t cnt = popc32(w.ballot(c <= 0));
-        uint32_t nl = cnt ? w.shfl(p, (int)cnt - 1) + 1u : l;
-        uint32_t nh = cnt < WD ? w.shfl(p, (int)(cnt & (WD - 1u))) : h;
-        l = nl; h = nh;
-      }
-      {
-        bool le = false;
-        if (l + lane < h)
-          le = compare_seed(ix.genome, (uint64_t)ix.index[l + lane] + PAD_BASES - seed_i, R, SM, nws) <= 0;
-        last_excl = l + popc32(w.ballot(le));
-      }
-      if (last_excl <= first) return;
-      if (last_excl - first > cfg.b) return;
+      // the reference's narrowed region = the seed-equal slots; -b applies to its size
+      if (popc32(w.ballot(seed_eq)) > cfg.b) return;
+      ctr.candidates += popc32(w.ballot(valid));
+      sink.consume(w, valid, mm, g, strand);
+      return;
     }
+    // 2b. long runs (repeats): finish the fingerprint range, then equal-range on the genome
+    uint32_t f1;
+    {
+      uint32_t l2 = f0 + n_match, h2 = hi;
+      kary_narrow(w, l2, h2, [&](uint32_t p) { const uint32_t f = ix.entries[p].fp; return f < fp_lo || f - fp_lo <= fp_span; });
+      bool in = false;
+      if (l2 + lane < h2) { const uint32_t f = ix.entries[l2 + lane].fp; in = f < fp_lo || f - fp_lo <= fp_span; }
+      f1 = l2 + popc32(w.ballot(in));
+    }
+    l = f0; h = f1;
+    kary_narrow(w, l, h, [&](uint32_t p) {
+      return compare_seed(ix.genome, (uint64_t)ix.entries[p].pos + PAD_BASES - seed_i, R, SM, nws) < 0; });
+    {
+      bool lt = false;
+      if (l + lane < h)
+        lt = compare_seed(ix.genome, (uint64_t)ix.entries[l + lane].pos + PAD_BASES - seed_i, R, SM, nws) < 0;
+      first = l + popc32(w.ballot(lt));
+    }
+    l = first; h = f1;
+    kary_narrow(w, l, h, [&](uint32_t p) {
+      return compare_seed(ix.genome, (uint64_t)ix.entries[p].pos + PAD_BASES - seed_i, R, SM, nws) <= 0; });
+    {
+      bool le = false;
+      if (l + lane < h)
+        le = compare_seed(ix.genome, (uint64_t)ix.entries[l + lane].pos + PAD_BASES - seed_i, R, SM, nws) <= 0;
+      last_excl = l + popc32(w.ballot(le));
+    }
+    if (last_excl <= first) return;
+    if (last_excl - first > cfg.b) return;
   }
 
+  // exact region [first, last_excl): every slot is a candidate
   for (uint32_t base = first; base < last_excl; base += WD) {
     const uint32_t slot = base + lane;
     bool valid = slot < last_excl;
     uint32_t g = 0, mm = 0;
-    bool seed_eq = false;
     if (valid) {
-      const uint32_t e = ix.index[slot];
+      const uint32_t e = ix.entries[slot].pos;
       WindowResult r = compare_window(ix.genome, (uint64_t)e + PAD_BASES - seed_i, R, VM, SM, nw);
       mm = r.mismatches;
-      seed_eq = r.seed_equal;
       // bounds, mapping.cpp:281-286 (all uint32 arithmetic, as the reference)
       const uint32_t chr = chrom_of(cv.starts, cv.n_chr, e);
       g = e - seed_i;
       valid = (e - cv.starts[chr] >= seed_i) && !(g + read_len >= cv.starts[chr + 1u]);
-    }
-    if (need_seed_check) {
-      // single-chunk scan: the region is the set of seed-equal slots (contiguous)
-      uint32_t match = w.ballot(slot < last_excl && seed_eq);
-      if (popc32(match) > cfg.b) return;
-      valid = valid && seed_eq;
     }
     ctr.candidates += popc32(w.ballot(valid));
     sink.consume(w, valid, mm, g, strand);

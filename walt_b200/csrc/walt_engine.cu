@@ -54,14 +54,14 @@ struct HwGroup {
 
 SubIndexView DeviceSubIndex::view(int which) const {
   SubIndexView v;
-  v.genome = genome; v.index = index; v.table = table; v.taint_bits = taint_bits;
+  v.genome = genome; v.entries = entries; v.table = table; v.taint_bits = taint_bits;
   v.taint_key = taint_key; v.taint_pos = taint_key + n_taint; v.taint_len = taint_key + 2 * (size_t)n_taint;
   v.n_taint = n_taint; v.index_size = index_size; v.depth = depth; v.ag = which >= 2 ? 1u : 0u;
   return v;
 }
 
 void DeviceSubIndex::release() {
-  cudaFree(genome); cudaFree(index); cudaFree(table); cudaFree(taint_bits); cudaFree(taint_key);
+  cudaFree(genome); cudaFree(index); cudaFree(entries); cudaFree(table); cudaFree(taint_bits); cudaFree(taint_key);
   *this = DeviceSubIndex();
 }
 
@@ -124,12 +124,18 @@ __global__ void pack_ascii_kernel(const uint8_t* __restrict__ ascii, uint64_t n_
   if (nbad) atomicAdd(bad, nbad);
 }
 
-__global__ void table_keys_kernel(SubIndexView ix, ChromView cv, Pow3 p3, uint32_t* __restrict__ keys) {
+// per slot: table key (first `depth` seed characters) and the {position, fingerprint} entry
+__global__ void table_keys_kernel(const uint64_t* __restrict__ genome, const uint32_t* __restrict__ index,
+                                  uint32_t index_size, uint32_t depth, uint32_t ag, ChromView cv, Pow3 p3,
+                                  uint32_t* __restrict__ keys, Entry* __restrict__ entries) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= ix.index_size) return;
-  const uint32_t e = ix.index[i];
+  if (i >= index_size) return;
+  const uint32_t e = index[i];
   const uint32_t chr = chrom_of(cv.starts, cv.n_chr, e);
-  keys[i] = entry_table_key(ix.genome, e, cv.starts[chr + 1u], ix.depth, ix.ag != 0u, p3);
+  const uint32_t ce = cv.starts[chr + 1u];
+  keys[i] = entry_table_key(genome, e, ce, depth, ag != 0u, p3);
+  Entry en; en.pos = e; en.fp = entry_fingerprint(genome, e, ce, depth, ag != 0u, p3);
+  entries[i] = en;
 }
 
 // table[k] = first slot whose key >= k, for k in [0, n_keys]; slot i owns (key[i-1], key[i]]
@@ -167,9 +173,20 @@ int finalize_subindex(walt_engine* e, int which) {
   DeviceSubIndex& s = e->sub[which];
   s.depth = e->force_depth > 0 ? (uint32_t)e->force_depth : choose_depth(s.index_size);
   if (s.depth < KEY_WEIGHT || s.depth > MAX_DEPTH) return fail(WALT_EINVAL, "table depth out of range");
+  if (e->force_depth == 0) {
+    // keep the table within what is left of HBM after the entry array and the key scratch;
+    // a shallower table only means one more narrowing step on the fingerprints
+    size_t free_b = 0, total_b = 0;
+    WALT_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    const size_t fixed = (size_t)s.index_size * 12u + (256u << 20);
+    while (s.depth > KEY_WEIGHT && ((size_t)e->pow3.v[s.depth] + 1u) * 4u + fixed > free_b) --s.depth;
+  }
   const uint32_t n_keys = e->pow3.v[s.depth];
   WALT_CUDA_TRY(cudaMalloc(&s.table, ((size_t)n_keys + 1u) * 4u));
   s.bytes += ((size_t)n_keys + 1u) * 4u;
+  WALT_CUDA_TRY(cudaMalloc(&s.entries, ((size_t)s.index_size + 64u) * sizeof(Entry)));
+  WALT_CUDA_TRY(cudaMemset(s.entries + s.index_size, 0, 64u * sizeof(Entry)));
+  s.bytes += ((size_t)s.index_size + 64u) * sizeof(Entry);
   // taint list first (host; <= 112 positions per chromosome): view() needs its pointers
   {
     std::vector<std::tuple<uint32_t, uint32_t, uint32_t>> t;
@@ -206,16 +223,17 @@ int finalize_subindex(walt_engine* e, int which) {
   }
   uint32_t* keys = nullptr;
   WALT_CUDA_TRY(cudaMalloc(&keys, ((size_t)s.index_size + 1u) * 4u));
-  const SubIndexView v = s.view(which);
   const uint32_t T = 256;
   if (s.index_size)
-    table_keys_kernel<<<(uint32_t)(((uint64_t)s.index_size + T - 1) / T), T>>>(v, chrom_view(e), e->pow3, keys);
+    table_keys_kernel<<<(uint32_t)(((uint64_t)s.index_size + T - 1) / T), T>>>(
+        s.genome, s.index, s.index_size, s.depth, which >= 2 ? 1u : 0u, chrom_view(e), e->pow3, keys, s.entries);
   WALT_CUDA_TRY(cudaMemset(e->d_flags + 2, 0, 4));
   table_fill_kernel<<<(uint32_t)(((uint64_t)s.index_size + 1u + T - 1) / T), T>>>(keys, s.index_size, n_keys, s.table,
                                                                                  e->d_flags + 2);
   uint32_t unsorted = 0;
   cudaError_t ce = cudaMemcpy(&unsorted, e->d_flags + 2, 4, cudaMemcpyDeviceToHost);
   cudaFree(keys);
+  cudaFree(s.index); s.index = nullptr;   // positions now live in the entry array
   if (ce != cudaSuccess) return fail(WALT_ECUDA, std::string("table build: ") + cudaGetErrorString(ce));
   if (unsorted)
     return fail(WALT_EFORMAT, "index[] is not in makedb order (" + std::to_string(unsorted) + " inversions)");
@@ -621,7 +639,6 @@ int walt_engine_load_subindex(walt_engine* e, int which, const char* sequence, c
   WALT_CUDA_TRY(cudaMalloc(&s.index, ((size_t)index_size + 64u) * 4u));
   WALT_CUDA_TRY(cudaMemset(s.index + index_size, 0, 64u * 4u));
   if (index_size) WALT_CUDA_TRY(cudaMemcpy(s.index, index, (size_t)index_size * 4u, cudaMemcpyHostToDevice));
-  s.bytes += ((size_t)index_size + 64u) * 4u;
   return finalize_subindex(e, which);
 }
 
@@ -697,7 +714,6 @@ int walt_engine_load_dbindex(walt_engine* e, const char* path, uint32_t which_ma
       s.index_size = hdr[1];
       if (cudaMalloc(&s.index, ((size_t)s.index_size + 64u) * 4u) != cudaSuccess) rc = fail(WALT_ECUDA, "cudaMalloc(index)");
       else cudaMemset(s.index + s.index_size, 0, 64u * 4u);
-      s.bytes += ((size_t)s.index_size + 64u) * 4u;
     }
     for (uint64_t off = 0; !rc && off < (uint64_t)s.index_size * 4u; off += STAGE_BYTES) {
       const uint64_t n = std::min<uint64_t>(STAGE_BYTES, (uint64_t)s.index_size * 4u - off);

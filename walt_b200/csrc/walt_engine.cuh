@@ -27,7 +27,8 @@ struct DeviceSubIndex {
   bool loaded = false;
   uint64_t* genome = nullptr;     // packed words incl. front/tail pad
   uint64_t genome_words = 0;
-  uint32_t* index = nullptr;
+  uint32_t* index = nullptr;      // staging only: positions as loaded/sorted, freed by finalize
+  waltcore::Entry* entries = nullptr;   // {position, fingerprint} per slot (+ 64 zero entries)
   uint32_t index_size = 0;
   uint32_t* table = nullptr;
   uint32_t depth = 0;
