@@ -322,7 +322,10 @@ void se_lane(WarpEmu* w, uint32_t lane, void* arg) {
       j->out[r].strand = (char)st.strand; memset(j->out[r].pad, 0, 3);
     }
   }
-  if (lane == 0) { *j->ctr = ctr; }
+  {  // counters are lane-local: sum them over the group
+    uint32_t a = W.reduce_add(ctr.lookups), b = W.reduce_add(ctr.candidates), c = W.reduce_add(ctr.literal);
+    if (lane == 0) { j->ctr->lookups = a; j->ctr->candidates = b; j->ctr->literal = c; }
+  }
 }
 
 struct PeJob {

@@ -34,9 +34,13 @@
 #if defined(__CUDACC__)
 #define WALT_HD __host__ __device__ __forceinline__
 #define WALT_HD_NOINLINE __host__ __device__ __noinline__
+#define WALT_UNROLL _Pragma("unroll")
+#define WALT_NO_UNROLL _Pragma("unroll 1")
 #else
 #define WALT_HD inline
 #define WALT_HD_NOINLINE
+#define WALT_UNROLL
+#define WALT_NO_UNROLL
 #endif
 
 namespace waltcore {
@@ -237,24 +241,79 @@ WALT_HD uint32_t entry_key12(const uint64_t* __restrict__ genome, uint32_t e, bo
 // ------------------------------------------------------------------------------------------
 // per-warp scratch (shared memory on the device)
 // ------------------------------------------------------------------------------------------
-// layout in 64-bit words: R[nw] | VM[3][nw] | SM[3][nw]
+// layout in 64-bit words: R[nw] | VM[3][nw] | SM[3][nw] | D[32*nw bytes] | C[LOOKUP_LANES*LANE_RUN_CAP]
+constexpr uint32_t LOOKUP_LANES = 6;   // 2 strands x 3 seed shifts, one lane each
+constexpr uint32_t LANE_RUN_CAP = 4;   // fingerprint-equal slots a single lane verifies itself
+struct LaneCand { uint32_t g; uint32_t mm; };   // mm == NO_HIT: empty slot
 struct ReadScratch {
   uint64_t* R;    // converted read, packed like the genome (no pad)
   uint64_t* VM;   // verification masks (low bit of each 2-bit field), per shift
   uint64_t* SM;   // seed (cared position) masks, per shift
+  uint8_t* D;     // base-3 digit of every converted read base (rank inside the 3-letter alphabet)
+  LaneCand* C;    // paired-end: candidates found by the lookup lanes, [lane][LANE_RUN_CAP]
   uint32_t nw;    // stride = words reserved per array
 };
-WALT_HD uint32_t scratch_words(uint32_t nw) { return 7u * nw; }
+WALT_HD uint32_t scratch_words(uint32_t nw) { return 11u * nw + LOOKUP_LANES * LANE_RUN_CAP; }
 WALT_HD ReadScratch carve_scratch(uint64_t* base, uint32_t nw) {
   ReadScratch s;
-  s.R = base; s.VM = base + nw; s.SM = base + 4u * nw; s.nw = nw;
+  s.R = base; s.VM = base + nw; s.SM = base + 4u * nw; s.D = reinterpret_cast<uint8_t*>(base + 7u * nw);
+  s.C = reinterpret_cast<LaneCand*>(base + 11u * nw); s.nw = nw;
   return s;
 }
 
-// Pack + convert one ASCII read into sc.R (group-cooperative). Returns false (uniformly) if a
-// byte is not A/C/G/T.  A group of W::WIDTH lanes owns the read: with 8 lanes every lane turns
-// 4 consecutive characters into one byte of the packed word (no cross-lane traffic); other
-// widths assemble the word from ballots.
+// Four consecutive read characters p..p+3 in one register, first character in the low byte,
+// zero at and beyond read_len.
+WALT_HD uint32_t load4_ascii(const char* __restrict__ seq, uint32_t p, uint32_t read_len) {
+  if (p >= read_len) return 0u;
+  const uint32_t nv = read_len - p;
+#if defined(__CUDA_ARCH__)
+  // two aligned 32-bit loads + funnel shift; the second word is touched only if it holds read bytes
+  const uintptr_t a = reinterpret_cast<uintptr_t>(seq + p);
+  const uint32_t* w0 = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  const uint32_t sh = (uint32_t)(a & 3u);
+  const uint32_t lo = w0[0];
+  uint32_t hi = 0u;
+  if (sh != 0u && 4u - sh < nv) hi = w0[1];
+  uint32_t v = __funnelshift_r(lo, hi, 8u * sh);
+#else
+  uint32_t v = 0u;
+  for (uint32_t j = 0; j < 4u && j < nv; ++j) v |= (uint32_t)(uint8_t)seq[p + j] << (8u * j);
+#endif
+  if (nv < 4u) v &= (1u << (8u * nv)) - 1u;
+  return v;
+}
+
+// The same four characters as 2-bit codes (one per byte), SIMD inside the register.
+// *bad is set if a byte in front of read_len is not A/C/G/T.
+WALT_HD uint32_t codes4(uint32_t ascii4, uint32_t n_valid, bool ag, bool& bad) {
+  const uint32_t x = (ascii4 >> 1) & 0x03030303u;
+  uint32_t code = x ^ ((x >> 1) & 0x01010101u);                       // A0 C1 G2 T3 (util.hpp:107-121)
+  // rebuild the letters from the codes; any difference is a non-ACGT byte
+  uint32_t letters = 0u;
+#if defined(__CUDA_ARCH__)
+  const uint32_t sel = (code & 0x3u) | ((code >> 4) & 0x30u) | ((code >> 8) & 0x300u) | ((code >> 12) & 0x3000u);
+  letters = __byte_perm(0x54474341u, 0u, sel);
+#else
+  for (uint32_t j = 0; j < 4u; ++j) letters |= (uint32_t)(uint8_t)"ACGT"[(code >> (8u * j)) & 3u] << (8u * j);
+#endif
+  const uint32_t keep = n_valid >= 4u ? 0xFFFFFFFFu : ((1u << (8u * n_valid)) - 1u);
+  bad |= ((letters ^ ascii4) & keep) != 0u;
+  // read conversion (mapping.cpp:142-164): C->T sets bit 1 where bit 0 is set; G->A clears bit 1
+  // where bit 0 is clear
+  const uint32_t b0 = code & 0x01010101u;
+  code = ag ? (code & ((b0 << 1) | 0x01010101u)) : (code | (b0 << 1));
+  return code & keep;
+}
+// rank of each converted code inside its 3-letter alphabet (== ternary_digit, four at a time)
+WALT_HD uint32_t digits4(uint32_t code4, bool ag) {
+  return ag ? (((code4 + 0x01010101u) >> 1) & 0x03030303u)
+            : (((code4 >> 1) & 0x01010101u) + (code4 & 0x01010101u));
+}
+
+// Pack + convert one ASCII read into sc.R and its base-3 digits into sc.D (group-cooperative).
+// Returns false (uniformly) if a byte is not A/C/G/T.  A group of W::WIDTH lanes owns the read:
+// with 8 lanes every lane turns 4 consecutive characters into one byte of the packed word (no
+// cross-lane traffic); other widths assemble the word from ballots.
 template <class W>
 WALT_HD bool load_read(W& w, const char* __restrict__ seq, uint32_t read_len, bool ag, ReadScratch& sc) {
   const uint32_t lane = w.lane();
@@ -262,19 +321,14 @@ WALT_HD bool load_read(W& w, const char* __restrict__ seq, uint32_t read_len, bo
   bool bad = false;
   if (W::WIDTH == 8u) {
     uint8_t* rb = reinterpret_cast<uint8_t*>(sc.R);
+    uint32_t* dw = reinterpret_cast<uint32_t*>(sc.D);
     for (uint32_t k = 0; k < nw; ++k) {
-      uint32_t piece = 0;
-      for (uint32_t j = 0; j < 4u; ++j) {
-        const uint32_t p = 32u * k + 4u * lane + j;
-        uint32_t code = 0;
-        if (p < read_len) {
-          const uint32_t c = (uint8_t)seq[p];
-          bad |= !ascii_is_acgt(c);
-          code = convert_code(ascii_code(c), ag);
-        }
-        piece = (piece << 2) | code;
-      }
-      rb[8u * k + (7u - lane)] = (uint8_t)piece;   // little-endian u64: first base in the top byte
+      const uint32_t p = 32u * k + 4u * lane;
+      const uint32_t a4 = load4_ascii(seq, p, read_len);
+      const uint32_t c4 = codes4(a4, p < read_len ? read_len - p : 0u, ag, bad);
+      // bytes c0..c3 (first character lowest) -> c0<<6 | c1<<4 | c2<<2 | c3
+      rb[8u * k + (7u - lane)] = (uint8_t)((c4 * 0x40100401u) >> 24);   // little-endian u64: first base on top
+      dw[8u * k + lane] = digits4(c4, ag);
     }
   } else {
     for (uint32_t k = 0; k < nw; ++k) {
@@ -287,6 +341,7 @@ WALT_HD bool load_read(W& w, const char* __restrict__ seq, uint32_t read_len, bo
           bad |= !ascii_is_acgt(c);
           code = convert_code(ascii_code(c), ag);
         }
+        sc.D[p] = (uint8_t)ternary_digit(code, ag);
         const uint32_t sh = 32u - W::WIDTH;        // ballot bit l -> base j*WIDTH + l of the word
         const uint32_t hi = brev32(w.ballot((code & 2u) != 0u)) >> sh;
         const uint32_t lo = brev32(w.ballot((code & 1u) != 0u)) >> sh;
@@ -424,9 +479,11 @@ struct BestState {
   uint32_t strand;  // '+' or '-'
 };
 
+// lane-local work counters (summed over lanes by the kernel epilogue)
 struct Counters {
   uint32_t lookups, candidates, literal;
 };
+constexpr uint32_t NO_HIT = 0xFFFFFFFFu;
 
 template <class W>
 struct BestSink {
@@ -455,6 +512,16 @@ struct BestSink {
       uint32_t g_first = w.shfl(g, first);
       uint32_t g_last = w.shfl(g, last);
       uint32_t acc = popc32(equal) - (g_first == st.pos ? 1u : 0u);
+      if (acc) { st.pos = g_last; st.strand = strand; st.times += acc; }
+    }
+  }
+  // the same fold for one lookup summarised by a single lane: `cnt` candidates (distinct
+  // positions, index order) share the lookup's minimum `mn`; first/last are their positions
+  WALT_HD void apply(uint32_t mn, uint32_t cnt, uint32_t g_first, uint32_t g_last, uint32_t strand) {
+    if (mn < st.mm) {
+      st.pos = g_last; st.times = cnt; st.mm = mn; st.strand = strand;
+    } else if (mn == st.mm) {
+      const uint32_t acc = cnt - (g_first == st.pos ? 1u : 0u);
       if (acc) { st.pos = g_last; st.strand = strand; st.times += acc; }
     }
   }
@@ -531,6 +598,20 @@ struct HeapSink {
       uint32_t cm = w.shfl(mm, src);
       if (w.lane() == 0u) {
         HeapEntry v; v.pos = cg; v.mm_strand = cm | (strand == '-' ? 0x10000u : 0u);
+        heap_push_bounded(heap, size, cap, v);
+      }
+    }
+    w.sync();
+    size = w.shfl(size, 0);
+    uint32_t t = 0;
+    if (w.lane() == 0u && size) t = he_mm(heap[0]);
+    top_mm = w.shfl(t, 0);
+  }
+  // n candidates (all with mm <= max_mm, index order) found by one lookup lane
+  WALT_HD void push_list(W& w, const LaneCand* c, uint32_t n, uint32_t strand) {
+    if (w.lane() == 0u) {
+      for (uint32_t k = 0; k < n; ++k) {
+        HeapEntry v; v.pos = c[k].g; v.mm_strand = c[k].mm | (strand == '-' ? 0x10000u : 0u);
         heap_push_bounded(heap, size, cap, v);
       }
     }
@@ -639,8 +720,7 @@ WALT_HD void seed_lookup(W& w, const SubIndexView& ix, const ChromView& cv, cons
     const uint32_t bucket_lo = ix.table[key12 * k12_span];
     const uint32_t bucket_hi = ix.table[(key12 + 1u) * k12_span];
     if (bucket_lo == bucket_hi) return;
-    ctr.lookups++;
-    ctr.literal++;
+    if (lane == 0u) { ctr.lookups++; ctr.literal++; }
     uint32_t f = bucket_lo, s = bucket_hi;
     literal_index_region(ix, cv.genome_len, R, seed_i, seed_len, f, s);
     if (s - f + 1u > cfg.b) return;      // mapping.cpp:275-277 (u32 arithmetic; (1,0) -> 0)
@@ -648,7 +728,7 @@ WALT_HD void seed_lookup(W& w, const SubIndexView& ix, const ChromView& cv, cons
     first = f; last_excl = s + 1u;
   } else {
     if (lo == hi) return;
-    ctr.lookups++;
+    if (lane == 0u) ctr.lookups++;
     // 1. narrow to the slots whose fingerprint matches (integer compares on the entry array)
     uint32_t l = lo, h = hi;
     kary_narrow(w, l, h, [&](uint32_t p) { return ix.entries[p].fp < fp_lo; });
@@ -679,7 +759,7 @@ WALT_HD void seed_lookup(W& w, const SubIndexView& ix, const ChromView& cv, cons
       }
       // the reference's narrowed region = the seed-equal slots; -b applies to its size
       if (popc32(w.ballot(seed_eq)) > cfg.b) return;
-      ctr.candidates += popc32(w.ballot(valid));
+      if (valid) ctr.candidates++;
       sink.consume(w, valid, mm, g, strand);
       return;
     }
@@ -728,9 +808,86 @@ WALT_HD void seed_lookup(W& w, const SubIndexView& ix, const ChromView& cv, cons
       g = e - seed_i;
       valid = (e - cv.starts[chr] >= seed_i) && !(g + read_len >= cv.starts[chr + 1u]);
     }
-    ctr.candidates += popc32(w.ballot(valid));
+    if (valid) ctr.candidates++;
     sink.consume(w, valid, mm, g, strand);
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// lane-per-lookup fast path
+// ------------------------------------------------------------------------------------------
+// The six lookups of a read (2 strand sub-indexes x 3 seed shifts) are independent until their
+// candidates are folded, so six lanes of the group run them concurrently -- one dependent chain
+// table -> entries -> genome window per lane instead of six in sequence -- and only the fold
+// (with the reference's early exits, mapping.cpp:248-257 / paired.cpp:127-137) is ordered.
+// A lane gives up (returns false) when the lookup needs the group: a tainted 12-mer bucket
+// (possible literal replay) or more than LANE_RUN_CAP fingerprint-equal slots (repeats).
+// `emit(g, mm)` receives the verified candidates in index order; `discard()` is called if the
+// lookup turns out to be filtered by -b after some were emitted.
+template <class Emit, class Discard>
+WALT_HD bool lane_lookup(const SubIndexView& ix, const ChromView& cv, const Pow3& p3, const MapConfig& cfg,
+                         const ReadScratch& sc, uint32_t read_len, uint32_t seed_i, Emit emit, Discard discard,
+                         Counters& ctr) {
+  const uint32_t seed_len = seed_repeats(read_len);
+  const uint32_t nw = (read_len + 31u) >> 5;
+  const uint32_t n_pref = ix.depth < seed_len ? ix.depth : seed_len;
+  const uint32_t n_fp = seed_len > ix.depth ? (seed_len - ix.depth < FP_DIGITS ? seed_len - ix.depth : FP_DIGITS) : 0u;
+  // base-3 numbers of the read's seed characters (Horner over the digit bytes)
+  const uint8_t* D = sc.D + seed_i + 1u;
+  uint32_t key = 0u, key12 = 0u, fp = 0u;
+  for (uint32_t i = 0; i < KEY_WEIGHT; ++i) key = key * 3u + D[3u * i];
+  key12 = key;
+  for (uint32_t i = KEY_WEIGHT; i < n_pref; ++i) key = key * 3u + D[3u * i];
+  for (uint32_t i = n_pref; i < n_pref + n_fp; ++i) fp = fp * 3u + D[3u * i];
+  const uint32_t lo_key = key * p3.v[ix.depth - n_pref];
+  const uint32_t hi_key = lo_key + p3.v[ix.depth - n_pref];
+  const uint32_t fp_lo = fp * p3.v[FP_DIGITS - n_fp];
+  const uint32_t fp_span = p3.v[FP_DIGITS - n_fp] - 1u;   // fingerprints in [fp_lo, fp_lo + fp_span] match
+
+  const uint32_t lo = ix.table[lo_key], hi = ix.table[hi_key];
+  if ((ix.taint_bits[key12 >> 5] >> (key12 & 31u)) & 1u) return false;
+  if (lo == hi) return true;
+  ctr.lookups++;
+  // first slot of [lo, hi) whose fingerprint is >= fp_lo: bisect down to a LANE_RUN_CAP window
+  uint32_t l = lo, h = hi;
+  // (the window [l, l + CAP) must hold slot h unless h is the end of the range)
+  while (h - l > LANE_RUN_CAP || (h - l == LANE_RUN_CAP && h < hi)) {
+    const uint32_t mid = l + ((h - l) >> 1);
+    if (ix.entries[mid].fp < fp_lo) l = mid + 1u; else h = mid;
+  }
+  Entry en[LANE_RUN_CAP];
+  WALT_UNROLL
+  for (uint32_t k = 0; k < LANE_RUN_CAP; ++k) en[k] = ix.entries[l + k];   // 64 readable pad entries behind index[]
+  uint32_t match = 0u;
+  WALT_UNROLL
+  for (uint32_t k = 0; k < LANE_RUN_CAP; ++k)
+    if (l + k < hi && en[k].fp - fp_lo <= fp_span) match |= 1u << k;      // unsigned: also rejects fp < fp_lo
+  if (match == 0u) return true;
+  // fingerprints are sorted inside a table range, so the matches are one run; it is complete
+  // unless it touches the end of the window and the range goes on
+  if ((match >> (LANE_RUN_CAP - 1u)) && l + LANE_RUN_CAP < hi) return false;
+  const uint64_t* R = sc.R;
+  const uint64_t* VM = sc.VM + seed_i * sc.nw;
+  const uint64_t* SM = sc.SM + seed_i * sc.nw;
+  uint32_t n_region = 0u;   // the reference's narrowed region = seed-equal slots (-b applies to it)
+  WALT_NO_UNROLL
+  for (uint32_t k = 0; k < LANE_RUN_CAP; ++k) {
+    if (!((match >> k) & 1u)) continue;
+    uint32_t e = 0u;   // en[k].pos without dynamic register indexing
+    WALT_UNROLL
+    for (uint32_t q = 0; q < LANE_RUN_CAP; ++q) if (q == k) e = en[q].pos;
+    const WindowResult r = compare_window(ix.genome, (uint64_t)e + PAD_BASES - seed_i, R, VM, SM, nw);
+    if (!r.seed_equal) continue;
+    ++n_region;
+    const uint32_t chr = chrom_of(cv.starts, cv.n_chr, e);   // bounds, mapping.cpp:281-286
+    const uint32_t g = e - seed_i;
+    if ((e - cv.starts[chr] >= seed_i) && !(g + read_len >= cv.starts[chr + 1u])) {
+      emit(g, r.mismatches);
+      ctr.candidates++;
+    }
+  }
+  if (n_region > cfg.b) discard();   // mapping.cpp:275-277
+  return true;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -744,17 +901,42 @@ WALT_HD bool map_read_se(W& w, const SubIndexView* ix2, const ChromView& cv, con
                          const MapConfig& cfg, const char* seq, uint32_t read_len, bool ag,
                          uint32_t max_mismatches, ReadScratch& sc, uint32_t& cached_len,
                          BestState& out, Counters& ctr) {
+  static_assert(W::WIDTH >= LOOKUP_LANES, "a group needs one lane per lookup");
   BestSink<W> sink;
   sink.st.pos = 0u; sink.st.times = 0u; sink.st.mm = max_mismatches; sink.st.strand = '+';
   out = sink.st;
   if (read_len < MIN_READ_LEN) return true;
   if (!load_read(w, seq, read_len, ag, sc)) return false;
   if (cached_len != read_len) { build_masks(w, read_len, sc); cached_len = read_len; }
+  // every lookup lane runs its own lookup and summarises it: minimum, how many candidates
+  // share it, the first and the last of them (all the ordered fold needs, see BestSink::apply)
+  const uint32_t lane = w.lane();
+  bool coop = false;
+  uint32_t mn = NO_HIT, cnt = 0u, g_first = 0u, g_last = 0u;
+  if (lane < LOOKUP_LANES) {
+    if (cfg.literal_all) {
+      coop = true;
+    } else {
+      coop = !lane_lookup(ix2[lane / 3u], cv, p3, cfg, sc, read_len, lane % 3u,
+                          [&](uint32_t g, uint32_t mmc) {
+                            if (mmc < mn) { mn = mmc; cnt = 1u; g_first = g_last = g; }
+                            else if (mmc == mn) { ++cnt; g_last = g; }
+                          },
+                          [&]() { mn = NO_HIT; cnt = 0u; }, ctr);
+    }
+  }
+  const uint32_t coop_mask = w.ballot(coop);
+  const uint32_t hit_mask = w.ballot(mn != NO_HIT);
   for (uint32_t s = 0; s < 2u; ++s) {
     const uint32_t strand = s ? '-' : '+';
     for (uint32_t seed_i = 0; seed_i < 3u; ++seed_i) {
       if (sink.stop_before_shift(seed_i)) break;
-      seed_lookup(w, ix2[s], cv, p3, cfg, sc, read_len, seed_i, strand, sink, ctr);
+      const uint32_t j = 3u * s + seed_i;
+      if ((coop_mask >> j) & 1u) {
+        seed_lookup(w, ix2[s], cv, p3, cfg, sc, read_len, seed_i, strand, sink, ctr);
+      } else if ((hit_mask >> j) & 1u) {
+        sink.apply(w.shfl(mn, (int)j), w.shfl(cnt, (int)j), w.shfl(g_first, (int)j), w.shfl(g_last, (int)j), strand);
+      }
     }
   }
   out = sink.st;
@@ -769,17 +951,47 @@ WALT_HD bool map_read_pe(W& w, const SubIndexView* ix2, const ChromView& cv, con
                          const MapConfig& cfg, const char* seq, uint32_t read_len, bool ag,
                          uint32_t max_mismatches, uint32_t top_k, ReadScratch& sc,
                          uint32_t& cached_len, HeapEntry* heap, uint32_t& heap_size, Counters& ctr) {
+  static_assert(W::WIDTH >= LOOKUP_LANES, "a group needs one lane per lookup");
   HeapSink<W> sink;
   sink.heap = heap; sink.size = 0u; sink.cap = top_k; sink.top_mm = 0u; sink.max_mm = max_mismatches;
   heap_size = 0u;
   if (read_len < MIN_READ_LEN) return true;
   if (!load_read(w, seq, read_len, ag, sc)) return false;
   if (cached_len != read_len) { build_masks(w, read_len, sc); cached_len = read_len; }
+  // lookup lanes leave their candidates (index order) in the group's scratch; lane 0 pushes
+  // them in reference order
+  const uint32_t lane = w.lane();
+  bool coop = false;
+  uint32_t n_mine = 0u;
+  if (lane < LOOKUP_LANES) {
+    if (cfg.literal_all) {
+      coop = true;
+    } else {
+      LaneCand* mine = sc.C + lane * LANE_RUN_CAP;
+      coop = !lane_lookup(ix2[lane / 3u], cv, p3, cfg, sc, read_len, lane % 3u,
+                          [&](uint32_t g, uint32_t mmc) {
+                            if (mmc > max_mismatches) return;          // paired.cpp:191-193
+                            LaneCand c; c.g = g; c.mm = mmc;
+                            mine[n_mine] = c;
+                            ++n_mine;
+                          },
+                          [&]() { n_mine = 0u; }, ctr);
+    }
+  }
+  const uint32_t coop_mask = w.ballot(coop);
+  const uint32_t hit_mask = w.ballot(n_mine != 0u);
+  w.sync();
   for (uint32_t s = 0; s < 2u; ++s) {
     const uint32_t strand = s ? '-' : '+';
     for (uint32_t seed_i = 0; seed_i < 3u; ++seed_i) {
       if (sink.stop_before_shift(seed_i)) break;
-      seed_lookup(w, ix2[s], cv, p3, cfg, sc, read_len, seed_i, strand, sink, ctr);
+      const uint32_t j = 3u * s + seed_i;
+      if ((coop_mask >> j) & 1u) {
+        seed_lookup(w, ix2[s], cv, p3, cfg, sc, read_len, seed_i, strand, sink, ctr);
+      } else if ((hit_mask >> j) & 1u) {
+        const uint32_t nj = w.shfl(n_mine, (int)j);
+        sink.push_list(w, sc.C + j * LANE_RUN_CAP, nj, strand);
+      }
     }
   }
   heap_size = sink.size;

@@ -265,6 +265,32 @@ struct SeArgs {
   unsigned long long* counters;  // optional
 };
 
+// The groups of a warp take consecutive reads with one queue ticket and walk the read loop
+// together, so the warp stays converged through the common phases (pack, keys, table and entry
+// loads, fold) and only splits where the data makes it (candidate windows, cooperative replays).
+template <uint32_t WD>
+__device__ __forceinline__ uint32_t next_read(uint32_t* queue) {
+  constexpr uint32_t GROUPS = 32u / WD;
+  uint32_t r = 0;
+  if ((threadIdx.x & 31u) == 0u) r = atomicAdd(queue, GROUPS);
+  r = __shfl_sync(0xFFFFFFFFu, r, 0);
+  return r + (threadIdx.x & 31u) / WD;
+}
+
+template <uint32_t WD>
+__device__ __forceinline__ void flush_counters(const HwGroup<WD>& w, const Counters& ctr, bool bad, uint32_t* flags,
+                                               unsigned long long* counters) {
+  const uint32_t a = w.reduce_add(ctr.lookups), b = w.reduce_add(ctr.candidates), c = w.reduce_add(ctr.literal);
+  if (w.lane() == 0) {
+    if (bad) atomicOr(flags, 1u);
+    if (counters) {
+      atomicAdd(counters + 0, (unsigned long long)a);
+      atomicAdd(counters + 1, (unsigned long long)b);
+      atomicAdd(counters + 2, (unsigned long long)c);
+    }
+  }
+}
+
 template <uint32_t WD>
 __global__ void __launch_bounds__(BLOCK_THREADS)
 se_map_kernel(const __grid_constant__ SeArgs a) {
@@ -277,30 +303,24 @@ se_map_kernel(const __grid_constant__ SeArgs a) {
   Counters ctr{0u, 0u, 0u};
   bool bad = false;
   for (;;) {
-    uint32_t r = 0;
-    if (lane == 0) r = atomicAdd(a.queue, 1u);
-    r = w.shfl(r, 0);
-    if (r >= a.n) break;
-    const uint64_t o0 = a.offs[r], o1 = a.offs[r + 1];
-    const uint32_t len = (uint32_t)(o1 - o0);
-    BestState st;
-    bool ok = map_read_se(w, a.ix, a.cv, a.p3, a.cfg, a.seqs + (o0 - a.seq_base), len, a.ag != 0u,
-                          a.max_mismatches, sc, cached_len, st, ctr);
-    bad |= !ok;
-    if (lane == 0) {
-      uint4 o;
-      o.x = st.pos; o.y = st.times; o.z = st.mm; o.w = st.strand & 0xFFu;
-      *reinterpret_cast<uint4*>(a.out + r) = o;
+    const uint32_t r = next_read<WD>(a.queue);
+    if (r - (threadIdx.x & 31u) / WD >= a.n) break;     // warp-uniform: the ticket is past the batch
+    if (r < a.n) {
+      const uint64_t o0 = a.offs[r], o1 = a.offs[r + 1];
+      const uint32_t len = (uint32_t)(o1 - o0);
+      BestState st;
+      bool ok = map_read_se(w, a.ix, a.cv, a.p3, a.cfg, a.seqs + (o0 - a.seq_base), len, a.ag != 0u,
+                            a.max_mismatches, sc, cached_len, st, ctr);
+      bad |= !ok;
+      if (lane == 0) {
+        uint4 o;
+        o.x = st.pos; o.y = st.times; o.z = st.mm; o.w = st.strand & 0xFFu;
+        *reinterpret_cast<uint4*>(a.out + r) = o;
+      }
     }
+    __syncwarp();
   }
-  if (lane == 0) {
-    if (bad) atomicOr(a.flags, 1u);
-    if (a.counters) {
-      atomicAdd(a.counters + 0, (unsigned long long)ctr.lookups);
-      atomicAdd(a.counters + 1, (unsigned long long)ctr.candidates);
-      atomicAdd(a.counters + 2, (unsigned long long)ctr.literal);
-    }
-  }
+  flush_counters(w, ctr, bad, a.flags, a.counters);
 }
 
 struct PeArgs {
@@ -339,43 +359,37 @@ pe_map_kernel(const __grid_constant__ PeArgs a) {
   Counters ctr{0u, 0u, 0u};
   bool bad = false;
   for (;;) {
-    uint32_t r = 0;
-    if (lane == 0) r = atomicAdd(a.queue, 1u);
-    r = w.shfl(r, 0);
-    if (r >= a.n) break;
-    const uint64_t o0 = a.offs[r], o1 = a.offs[r + 1];
-    const uint32_t len = (uint32_t)(o1 - o0);
-    uint32_t hsize = 0;
-    bool ok = map_read_pe(w, a.ix, a.cv, a.p3, a.cfg, a.seqs + (o0 - a.seq_base), len, a.ag != 0u,
-                          a.max_mismatches, a.top_k, sc, cached_len, heap, hsize, ctr);
-    bad |= !ok;
-    if (lane == 0) {
-      walt_cand* dst = a.ranked + (size_t)r * a.top_k;
-      uint32_t c = 0, sz = hsize;
-      while (sz) {
-        HeapEntry t = heap_pop(heap, sz);
-        walt_cand o;
-        o.genome_pos = t.pos; o.mismatch = he_mm(t); o.strand = (t.mm_strand & 0x10000u) ? '-' : '+';
-        o.pad[0] = o.pad[1] = o.pad[2] = 0;
-        dst[c++] = o;
+    const uint32_t r = next_read<WD>(a.queue);
+    if (r - (threadIdx.x & 31u) / WD >= a.n) break;
+    if (r < a.n) {
+      const uint64_t o0 = a.offs[r], o1 = a.offs[r + 1];
+      const uint32_t len = (uint32_t)(o1 - o0);
+      uint32_t hsize = 0;
+      bool ok = map_read_pe(w, a.ix, a.cv, a.p3, a.cfg, a.seqs + (o0 - a.seq_base), len, a.ag != 0u,
+                            a.max_mismatches, a.top_k, sc, cached_len, heap, hsize, ctr);
+      bad |= !ok;
+      if (lane == 0) {
+        walt_cand* dst = a.ranked + (size_t)r * a.top_k;
+        uint32_t c = 0, sz = hsize;
+        while (sz) {
+          HeapEntry t = heap_pop(heap, sz);
+          walt_cand o;
+          o.genome_pos = t.pos; o.mismatch = he_mm(t); o.strand = (t.mm_strand & 0x10000u) ? '-' : '+';
+          o.pad[0] = o.pad[1] = o.pad[2] = 0;
+          dst[c++] = o;
+        }
+        a.n_ranked[r] = c;
       }
-      a.n_ranked[r] = c;
+      w.sync();
+      {  // unused slots are defined (zero) so whole-array compares and copies are deterministic
+        const uint32_t used = w.shfl(hsize, 0);
+        uint32_t* z = reinterpret_cast<uint32_t*>(a.ranked + (size_t)r * a.top_k + used);
+        for (uint32_t i = lane; i < (a.top_k - used) * 3u; i += WD) z[i] = 0u;
+      }
     }
-    w.sync();
-    {  // unused slots are defined (zero) so whole-array compares and copies are deterministic
-      const uint32_t used = w.shfl(hsize, 0);
-      uint32_t* z = reinterpret_cast<uint32_t*>(a.ranked + (size_t)r * a.top_k + used);
-      for (uint32_t i = lane; i < (a.top_k - used) * 3u; i += WD) z[i] = 0u;
-    }
+    __syncwarp();
   }
-  if (lane == 0) {
-    if (bad) atomicOr(a.flags, 1u);
-    if (a.counters) {
-      atomicAdd(a.counters + 0, (unsigned long long)ctr.lookups);
-      atomicAdd(a.counters + 1, (unsigned long long)ctr.candidates);
-      atomicAdd(a.counters + 2, (unsigned long long)ctr.literal);
-    }
-  }
+  flush_counters(w, ctr, bad, a.flags, a.counters);
 }
 
 struct GetRanked {
