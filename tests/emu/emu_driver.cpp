@@ -173,14 +173,14 @@ struct EmuWarp {
 // ------------------------------------------------------------------------------------------
 struct EmuSubIndex {
   std::vector<uint64_t> genome;
-  std::vector<uint32_t> index, table, taint_bits, taint_key, taint_pos, taint_len;
+  std::vector<uint32_t> index, table, taint_bits, taint_rank, taint_start, taint_key, taint_pos, taint_len;
   std::vector<Entry> entries;
   uint32_t depth = 0, ag = 0;
   uint32_t unsorted = 0;
   SubIndexView view() const {
     SubIndexView v;
     v.genome = genome.data(); v.entries = entries.data(); v.table = table.data();
-    v.taint_bits = taint_bits.data(); v.taint_key = taint_key.data();
+    v.taint_bits = taint_bits.data(); v.taint_rank = taint_rank.data(); v.taint_start = taint_start.data();
     v.taint_pos = taint_pos.data(); v.taint_len = taint_len.data();
     v.n_taint = (uint32_t)taint_key.size(); v.index_size = (uint32_t)index.size();
     v.depth = depth; v.ag = ag;
@@ -275,12 +275,11 @@ int emu_engine_load_subindex(void* h, int which, const char* seq, const uint32_t
     }
   }
   std::sort(t.begin(), t.end());
-  s.taint_bits.assign((N_KEY12 + 31) / 32, 0);
   s.taint_key.clear(); s.taint_pos.clear(); s.taint_len.clear();
   for (auto& x : t) {
     s.taint_key.push_back(x.first); s.taint_pos.push_back(x.second.first); s.taint_len.push_back(x.second.second);
-    s.taint_bits[x.first >> 5] |= 1u << (x.first & 31);
   }
+  build_taint_directory(s.taint_key, s.taint_bits, s.taint_rank, s.taint_start);
   return s.unsorted ? 2 : 0;
 }
 

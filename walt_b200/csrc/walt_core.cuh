@@ -31,6 +31,8 @@
 
 #include <stdint.h>
 
+#include <vector>
+
 #if defined(__CUDACC__)
 #define WALT_HD __host__ __device__ __forceinline__
 #define WALT_HD_NOINLINE __host__ __device__ __noinline__
@@ -172,7 +174,8 @@ struct SubIndexView {
   const Entry* entries;        // index_size (+ readable pad)
   const uint32_t* table;       // 3^depth + 1 entries
   const uint32_t* taint_bits;  // N_KEY12 bits
-  const uint32_t* taint_key;   // sorted 12-mer keys (base 3) of tainted positions
+  const uint32_t* taint_rank;  // set bits in front of each 32-bit word of taint_bits
+  const uint32_t* taint_start; // per distinct tainted key (rank order): first slot in taint_pos/len, + end
   const uint32_t* taint_pos;   // their genome positions
   const uint32_t* taint_len;   // chromosome end - position
   uint32_t n_taint;
@@ -188,6 +191,24 @@ struct ChromView {
 };
 
 struct Pow3 { uint32_t v[MAX_DEPTH + 1]; };
+
+// Host helper (engine and test harness): filter bits, rank directory and per-key slot ranges of
+// the taint list from its sorted 12-mer keys.
+inline void build_taint_directory(const std::vector<uint32_t>& sorted_keys, std::vector<uint32_t>& bits,
+                                  std::vector<uint32_t>& rank, std::vector<uint32_t>& start) {
+  const uint32_t words = (N_KEY12 + 31u) / 32u;
+  bits.assign(words, 0u);
+  rank.assign(words, 0u);
+  start.clear();
+  for (uint32_t i = 0; i < sorted_keys.size(); ++i) {
+    const uint32_t k = sorted_keys[i];
+    if (i == 0 || k != sorted_keys[i - 1]) start.push_back(i);
+    bits[k >> 5] |= 1u << (k & 31u);
+  }
+  start.push_back((uint32_t)sorted_keys.size());
+  uint32_t acc = 0;
+  for (uint32_t w = 0; w < words; ++w) { rank[w] = acc; acc += popc32(bits[w]); }
+}
 
 // getChromID, reference.cpp:43-60
 WALT_HD uint32_t chrom_of(const uint32_t* __restrict__ starts, uint32_t n_chr, uint32_t pos) {
@@ -631,20 +652,25 @@ struct MapConfig {
   uint32_t literal_all;  // test hook: replay IndexRegion literally for every lookup
 };
 
+// Slots [t0, t1) of the taint list that hold positions whose 12-mer key is key12 (its filter bit
+// is known to be set).
+WALT_HD void taint_slots(const SubIndexView& ix, uint32_t key12, uint32_t& t0, uint32_t& t1) {
+  const uint32_t word = key12 >> 5, bit = key12 & 31u;
+  const uint32_t idx = ix.taint_rank[word] + popc32(ix.taint_bits[word] & ((1u << bit) - 1u));
+  t0 = ix.taint_start[idx]; t1 = ix.taint_start[idx + 1u];
+}
+
 // Is there a tainted entry in this 12-mer bucket whose in-chromosome seed characters all
 // match the read (so that the reference's search would look at its out-of-chromosome bytes)?
+// Group-cooperative version (the lanes split the characters).
 template <class W>
 WALT_HD bool lookup_is_affected(W& w, const SubIndexView& ix, const uint64_t* R, uint32_t seed_i,
                                 uint32_t seed_len, uint32_t key12) {
-  // first taint slot with key >= key12 (uniform binary search)
-  uint32_t lo = 0, hi = ix.n_taint;
-  while (lo < hi) {
-    uint32_t mid = (lo + hi) >> 1;
-    if (ix.taint_key[mid] < key12) lo = mid + 1u; else hi = mid;
-  }
+  uint32_t t0, t1;
+  taint_slots(ix, key12, t0, t1);
   const uint32_t lane = w.lane();
   bool affected = false;
-  for (uint32_t t = lo; t < ix.n_taint && ix.taint_key[t] == key12; ++t) {
+  for (uint32_t t = t0; t < t1; ++t) {
     uint32_t avail = ix.taint_len[t];
     uint32_t n_in = (avail + 1u) / 3u;  // seed characters with 3i+1 < avail
     if (n_in >= seed_len) continue;     // every probed character is inside the chromosome
@@ -657,6 +683,24 @@ WALT_HD bool lookup_is_affected(W& w, const SubIndexView& ix, const uint64_t* R,
     if (w.ballot(differ) == 0u) affected = true;
   }
   return affected;
+}
+// The same test by a single lane.
+WALT_HD bool lane_is_affected(const SubIndexView& ix, const uint64_t* R, uint32_t seed_i, uint32_t seed_len,
+                              uint32_t key12) {
+  uint32_t t0, t1;
+  taint_slots(ix, key12, t0, t1);
+  for (uint32_t t = t0; t < t1; ++t) {
+    const uint32_t n_in = (ix.taint_len[t] + 1u) / 3u;
+    if (n_in >= seed_len) continue;
+    const uint32_t e = ix.taint_pos[t];
+    bool differ = false;
+    for (uint32_t i = KEY_WEIGHT; i < n_in && !differ; ++i) {
+      const uint32_t off = 3u * i + 1u;
+      differ = packed_base(ix.genome, (uint64_t)e + PAD_BASES + off) != packed_base(R, seed_i + off);
+    }
+    if (!differ) return true;
+  }
+  return false;
 }
 
 // (WD+1)-ary narrowing of [l, h) to at most WD slots around the first slot whose value is not
@@ -813,6 +857,30 @@ WALT_HD void seed_lookup(W& w, const SubIndexView& ix, const ChromView& cv, cons
   }
 }
 
+// Out-of-line copy of seed_lookup for the read loops: the cooperative replay is the rare path
+// (tainted buckets, long repeat runs, the literal test mode), and keeping it out of the hot
+// loop keeps that loop inside the instruction cache.  Callers hand in copies of their state so
+// that nothing of the hot path has its address taken.
+template <class W, class Sink>
+WALT_HD_NOINLINE void seed_lookup_cold(W& w, const SubIndexView& ix, const ChromView& cv, const Pow3& p3,
+                                       const MapConfig& cfg, const ReadScratch& sc, uint32_t read_len,
+                                       uint32_t seed_i, uint32_t strand, Sink& sink, Counters& ctr) {
+  seed_lookup(w, ix, cv, p3, cfg, sc, read_len, seed_i, strand, sink, ctr);
+}
+template <class W, class Sink>
+WALT_HD void replay_lookup(W& w, const SubIndexView& ix, const ChromView& cv, const Pow3& p3,
+                           const MapConfig& cfg, const ReadScratch& sc, uint32_t read_len,
+                           uint32_t seed_i, uint32_t strand, Sink& sink, Counters& ctr) {
+  W wc = w;
+  Sink tmp = sink;
+  Counters c{0u, 0u, 0u};
+  ReadScratch sc2 = sc;
+  seed_lookup_cold(wc, ix, cv, p3, cfg, sc2, read_len, seed_i, strand, tmp, c);
+  w = wc;
+  sink = tmp;
+  ctr.lookups += c.lookups; ctr.candidates += c.candidates; ctr.literal += c.literal;
+}
+
 // ------------------------------------------------------------------------------------------
 // lane-per-lookup fast path
 // ------------------------------------------------------------------------------------------
@@ -845,7 +913,10 @@ WALT_HD bool lane_lookup(const SubIndexView& ix, const ChromView& cv, const Pow3
   const uint32_t fp_span = p3.v[FP_DIGITS - n_fp] - 1u;   // fingerprints in [fp_lo, fp_lo + fp_span] match
 
   const uint32_t lo = ix.table[lo_key], hi = ix.table[hi_key];
-  if ((ix.taint_bits[key12 >> 5] >> (key12 & 31u)) & 1u) return false;
+  // a tainted bucket needs the literal replay only if the read agrees with a tainted position
+  // on every seed character inside the chromosome (rare; the replay is the group's job)
+  if (((ix.taint_bits[key12 >> 5] >> (key12 & 31u)) & 1u) && lane_is_affected(ix, sc.R, seed_i, seed_len, key12))
+    return false;
   if (lo == hi) return true;
   ctr.lookups++;
   // first slot of [lo, hi) whose fingerprint is >= fp_lo: bisect down to a LANE_RUN_CAP window
@@ -871,8 +942,9 @@ WALT_HD bool lane_lookup(const SubIndexView& ix, const ChromView& cv, const Pow3
   const uint64_t* SM = sc.SM + seed_i * sc.nw;
   uint32_t n_region = 0u;   // the reference's narrowed region = seed-equal slots (-b applies to it)
   WALT_NO_UNROLL
-  for (uint32_t k = 0; k < LANE_RUN_CAP; ++k) {
-    if (!((match >> k) & 1u)) continue;
+  while (match) {   // lanes walk their own set bits, so the warp makes max-over-lanes passes
+    const uint32_t k = (uint32_t)ffs32(match) - 1u;
+    match &= match - 1u;
     uint32_t e = 0u;   // en[k].pos without dynamic register indexing
     WALT_UNROLL
     for (uint32_t q = 0; q < LANE_RUN_CAP; ++q) if (q == k) e = en[q].pos;
@@ -927,16 +999,20 @@ WALT_HD bool map_read_se(W& w, const SubIndexView* ix2, const ChromView& cv, con
   }
   const uint32_t coop_mask = w.ballot(coop);
   const uint32_t hit_mask = w.ballot(mn != NO_HIT);
-  for (uint32_t s = 0; s < 2u; ++s) {
+  // ordered fold over the lookups that can change the state.  Skipping a lookup where the
+  // reference would have left the shift loop (mapping.cpp:250-256) is the same as its break: the
+  // state is untouched by a skip, so the later shifts of that strand are skipped as well.
+  uint32_t todo = (coop_mask | hit_mask) & ((1u << LOOKUP_LANES) - 1u);
+  while (todo) {
+    const uint32_t j = (uint32_t)ffs32(todo) - 1u;
+    todo &= todo - 1u;
+    const uint32_t s = j >= 3u ? 1u : 0u, seed_i = j - 3u * s;
     const uint32_t strand = s ? '-' : '+';
-    for (uint32_t seed_i = 0; seed_i < 3u; ++seed_i) {
-      if (sink.stop_before_shift(seed_i)) break;
-      const uint32_t j = 3u * s + seed_i;
-      if ((coop_mask >> j) & 1u) {
-        seed_lookup(w, ix2[s], cv, p3, cfg, sc, read_len, seed_i, strand, sink, ctr);
-      } else if ((hit_mask >> j) & 1u) {
-        sink.apply(w.shfl(mn, (int)j), w.shfl(cnt, (int)j), w.shfl(g_first, (int)j), w.shfl(g_last, (int)j), strand);
-      }
+    if (sink.stop_before_shift(seed_i)) continue;
+    if ((coop_mask >> j) & 1u) {
+      replay_lookup(w, ix2[s], cv, p3, cfg, sc, read_len, seed_i, strand, sink, ctr);
+    } else {
+      sink.apply(w.shfl(mn, (int)j), w.shfl(cnt, (int)j), w.shfl(g_first, (int)j), w.shfl(g_last, (int)j), strand);
     }
   }
   out = sink.st;
@@ -981,17 +1057,18 @@ WALT_HD bool map_read_pe(W& w, const SubIndexView* ix2, const ChromView& cv, con
   const uint32_t coop_mask = w.ballot(coop);
   const uint32_t hit_mask = w.ballot(n_mine != 0u);
   w.sync();
-  for (uint32_t s = 0; s < 2u; ++s) {
+  uint32_t todo = (coop_mask | hit_mask) & ((1u << LOOKUP_LANES) - 1u);
+  while (todo) {   // see map_read_se: a skip is the reference's break (paired.cpp:127-137)
+    const uint32_t j = (uint32_t)ffs32(todo) - 1u;
+    todo &= todo - 1u;
+    const uint32_t s = j >= 3u ? 1u : 0u, seed_i = j - 3u * s;
     const uint32_t strand = s ? '-' : '+';
-    for (uint32_t seed_i = 0; seed_i < 3u; ++seed_i) {
-      if (sink.stop_before_shift(seed_i)) break;
-      const uint32_t j = 3u * s + seed_i;
-      if ((coop_mask >> j) & 1u) {
-        seed_lookup(w, ix2[s], cv, p3, cfg, sc, read_len, seed_i, strand, sink, ctr);
-      } else if ((hit_mask >> j) & 1u) {
-        const uint32_t nj = w.shfl(n_mine, (int)j);
-        sink.push_list(w, sc.C + j * LANE_RUN_CAP, nj, strand);
-      }
+    if (sink.stop_before_shift(seed_i)) continue;
+    if ((coop_mask >> j) & 1u) {
+      replay_lookup(w, ix2[s], cv, p3, cfg, sc, read_len, seed_i, strand, sink, ctr);
+    } else {
+      const uint32_t nj = w.shfl(n_mine, (int)j);
+      sink.push_list(w, sc.C + j * LANE_RUN_CAP, nj, strand);
     }
   }
   heap_size = sink.size;

@@ -55,13 +55,16 @@ struct HwGroup {
 SubIndexView DeviceSubIndex::view(int which) const {
   SubIndexView v;
   v.genome = genome; v.entries = entries; v.table = table; v.taint_bits = taint_bits;
-  v.taint_key = taint_key; v.taint_pos = taint_key + n_taint; v.taint_len = taint_key + 2 * (size_t)n_taint;
+  // one allocation: filter bits | rank per word | start per distinct key (+1) | pos | len
+  const size_t words = (N_KEY12 + 31u) / 32u;
+  v.taint_rank = taint_bits + words; v.taint_start = taint_bits + 2 * words;
+  v.taint_pos = v.taint_start + n_taint_keys + 1u; v.taint_len = v.taint_pos + n_taint;
   v.n_taint = n_taint; v.index_size = index_size; v.depth = depth; v.ag = which >= 2 ? 1u : 0u;
   return v;
 }
 
 void DeviceSubIndex::release() {
-  cudaFree(genome); cudaFree(index); cudaFree(entries); cudaFree(table); cudaFree(taint_bits); cudaFree(taint_key);
+  cudaFree(genome); cudaFree(index); cudaFree(entries); cudaFree(table); cudaFree(taint_bits);
   *this = DeviceSubIndex();
 }
 
@@ -209,17 +212,18 @@ int finalize_subindex(walt_engine* e, int which) {
     }
     std::sort(t.begin(), t.end());
     s.n_taint = (uint32_t)t.size();
-    std::vector<uint32_t> bits((N_KEY12 + 31u) / 32u, 0u), flat(3u * (size_t)s.n_taint + 1u, 0u);
-    for (uint32_t i = 0; i < s.n_taint; ++i) {
-      const uint32_t k = std::get<0>(t[i]);
-      bits[k >> 5] |= 1u << (k & 31u);
-      flat[i] = k; flat[s.n_taint + i] = std::get<1>(t[i]); flat[2u * (size_t)s.n_taint + i] = std::get<2>(t[i]);
-    }
-    WALT_CUDA_TRY(cudaMalloc(&s.taint_bits, bits.size() * 4u));
-    WALT_CUDA_TRY(cudaMemcpy(s.taint_bits, bits.data(), bits.size() * 4u, cudaMemcpyHostToDevice));
-    WALT_CUDA_TRY(cudaMalloc(&s.taint_key, flat.size() * 4u));
-    WALT_CUDA_TRY(cudaMemcpy(s.taint_key, flat.data(), flat.size() * 4u, cudaMemcpyHostToDevice));
-    s.bytes += bits.size() * 4u + flat.size() * 4u;
+    std::vector<uint32_t> keys12(s.n_taint), bits, rank, start;
+    for (uint32_t i = 0; i < s.n_taint; ++i) keys12[i] = std::get<0>(t[i]);
+    build_taint_directory(keys12, bits, rank, start);
+    s.n_taint_keys = (uint32_t)start.size() - 1u;
+    std::vector<uint32_t> flat(bits);
+    flat.insert(flat.end(), rank.begin(), rank.end());
+    flat.insert(flat.end(), start.begin(), start.end());
+    for (uint32_t i = 0; i < s.n_taint; ++i) flat.push_back(std::get<1>(t[i]));
+    for (uint32_t i = 0; i < s.n_taint; ++i) flat.push_back(std::get<2>(t[i]));
+    WALT_CUDA_TRY(cudaMalloc(&s.taint_bits, flat.size() * 4u));
+    WALT_CUDA_TRY(cudaMemcpy(s.taint_bits, flat.data(), flat.size() * 4u, cudaMemcpyHostToDevice));
+    s.bytes += flat.size() * 4u;
   }
   uint32_t* keys = nullptr;
   WALT_CUDA_TRY(cudaMalloc(&keys, ((size_t)s.index_size + 1u) * 4u));
@@ -246,6 +250,7 @@ int finalize_subindex(walt_engine* e, int which) {
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t WARPS_PER_BLOCK = 8;
 constexpr uint32_t BLOCK_THREADS = WARPS_PER_BLOCK * 32;
+constexpr uint32_t MIN_BLOCKS_PER_SM = 4;   // caps the kernels at 64 registers (the out-of-line replay may spill)
 
 struct SeArgs {
   SubIndexView ix[2];   // '+' then '-' sub-index
@@ -292,7 +297,7 @@ __device__ __forceinline__ void flush_counters(const HwGroup<WD>& w, const Count
 }
 
 template <uint32_t WD>
-__global__ void __launch_bounds__(BLOCK_THREADS)
+__global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS_PER_SM)
 se_map_kernel(const __grid_constant__ SeArgs a) {
   extern __shared__ uint64_t smem[];
   HwGroup<WD> w;
@@ -345,7 +350,7 @@ struct PeArgs {
 
 // PairEndMapping (paired.cpp:106-201) for one mate batch + the heap drain (paired.cpp:684-692)
 template <uint32_t WD>
-__global__ void __launch_bounds__(BLOCK_THREADS)
+__global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS_PER_SM)
 pe_map_kernel(const __grid_constant__ PeArgs a) {
   extern __shared__ uint64_t smem[];
   HwGroup<WD> w;

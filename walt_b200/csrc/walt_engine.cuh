@@ -32,9 +32,9 @@ struct DeviceSubIndex {
   uint32_t index_size = 0;
   uint32_t* table = nullptr;
   uint32_t depth = 0;
-  uint32_t* taint_bits = nullptr;
-  uint32_t* taint_key = nullptr;  // one allocation: key | pos | len
-  uint32_t n_taint = 0;
+  uint32_t* taint_bits = nullptr; // one allocation: filter bits | rank | start | pos | len
+  uint32_t n_taint = 0;           // tainted positions
+  uint32_t n_taint_keys = 0;      // distinct 12-mer keys among them
   uint64_t bytes = 0;
   waltcore::SubIndexView view(int which) const;
   void release();
