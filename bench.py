@@ -340,6 +340,11 @@ def run_ours(args):
     step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
     t_dev = evs[0].elapsed_time(evs[-1]) / 1e3
 
+    if args.no_e2e:   # kernel experiments only: not a bench line
+        if rank == 0:
+            print(json.dumps({"experiment": True, "kernel_ms": float(np.mean(step_ms)), "reads_per_s": n * 1e3 / float(np.mean(step_ms)),
+                              "env": {k: v for k, v in os.environ.items() if k.startswith("WALT_")}}))
+        return 0
     # ---- end-to-end timing through the C ABI with pinned host buffers (`e2e`) ----
     from walt_b200.engine import BEST_DT, PinnedArray
     h_reads = PinnedArray((n * rl,), np.uint8)
@@ -400,6 +405,7 @@ def main():
     ap.add_argument("--reads", type=int, default=10_000_000)
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--no-cpu", action="store_true", help="skip the oracle/reference side legs")
+    ap.add_argument("--no-e2e", action="store_true", help="kernel experiment: print the device timing only")
     ap.add_argument("--group-width", type=int, default=8, help="lanes that own one read (8, 16, 32)")
     ap.add_argument("--table-depth", type=int, default=0, help="prefix-table depth (0 = auto)")
     args = ap.parse_args()

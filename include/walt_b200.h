@@ -11,7 +11,7 @@
  * There is no CPU fallback: every mapping call runs on the CUDA device or fails.
  *
  * Conventions: caller owns all host buffers; calls are synchronous (internally the batch is
- * double-buffered over CUDA streams); one engine per GPU per process; an engine is
+ * pipelined over CUDA streams, three chunks in flight); one engine per GPU per process; an engine is
  * thread-compatible, not thread-safe.  Results are indexed by input read order.
  */
 #ifndef WALT_B200_H_
@@ -138,7 +138,7 @@ int walt_engine_last_stats(const walt_engine* e, walt_stats* out);
  * lookup (the in-repo device oracle; same results, slower). */
 int walt_engine_set_search_mode(walt_engine* e, int mode);
 /* Tuning/test hooks: prefix-table depth for sub-indexes loaded afterwards (0 = auto, else
- * 12..20) and the number of reads per double-buffered host chunk (default 2^20). */
+ * 12..20) and the number of reads per in-flight host chunk (default 2^18; three chunks in flight). */
 int walt_engine_set_table_depth(walt_engine* e, int depth);
 int walt_engine_set_chunk_reads(walt_engine* e, uint32_t n);
 /* Lanes of a warp that cooperate on one read: 8 (default; four reads per warp), 16 or 32. */

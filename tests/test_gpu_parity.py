@@ -90,7 +90,7 @@ def test_se_chunked_pipeline_matches_single_chunk(engine):
     try:
         out, _ = engine.map_se(buf, offs, m=6, b=5000)
     finally:
-        engine.set_chunk_reads(1 << 20)
+        engine.set_chunk_reads(1 << 18)
     _cmp_best(out, z["best_m6_b5000"])
 
 

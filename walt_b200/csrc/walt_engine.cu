@@ -13,6 +13,7 @@
 
 #include <errno.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
 
@@ -258,8 +259,9 @@ struct SeArgs {
   Pow3 p3;
   MapConfig cfg;
   const char* seqs;
-  const uint64_t* offs;   // n + 1, absolute; seqs[0] is byte `seq_base`
+  const uint64_t* offs;   // n + 1, absolute; seqs[0] is byte `seq_base` (unused if uniform_len)
   uint64_t seq_base;
+  uint32_t uniform_len;   // != 0: every read has this length, read r starts at seqs + r * uniform_len
   uint32_t n;
   uint32_t nw_max;        // scratch stride (words) for the longest read
   uint32_t ag;
@@ -296,8 +298,8 @@ __device__ __forceinline__ void flush_counters(const HwGroup<WD>& w, const Count
   }
 }
 
-template <uint32_t WD>
-__global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS_PER_SM)
+template <uint32_t WD, uint32_t MINB = MIN_BLOCKS_PER_SM>
+__global__ void __launch_bounds__(BLOCK_THREADS, MINB)
 se_map_kernel(const __grid_constant__ SeArgs a) {
   extern __shared__ uint64_t smem[];
   HwGroup<WD> w;
@@ -311,10 +313,16 @@ se_map_kernel(const __grid_constant__ SeArgs a) {
     const uint32_t r = next_read<WD>(a.queue);
     if (r - (threadIdx.x & 31u) / WD >= a.n) break;     // warp-uniform: the ticket is past the batch
     if (r < a.n) {
-      const uint64_t o0 = a.offs[r], o1 = a.offs[r + 1];
-      const uint32_t len = (uint32_t)(o1 - o0);
+      const char* seq;
+      uint32_t len;
+      if (a.uniform_len) {
+        len = a.uniform_len; seq = a.seqs + (size_t)r * len;
+      } else {
+        const uint64_t o0 = a.offs[r], o1 = a.offs[r + 1];
+        len = (uint32_t)(o1 - o0); seq = a.seqs + (o0 - a.seq_base);
+      }
       BestState st;
-      bool ok = map_read_se(w, a.ix, a.cv, a.p3, a.cfg, a.seqs + (o0 - a.seq_base), len, a.ag != 0u,
+      bool ok = map_read_se(w, a.ix, a.cv, a.p3, a.cfg, seq, len, a.ag != 0u,
                             a.max_mismatches, sc, cached_len, st, ctr);
       bad |= !ok;
       if (lane == 0) {
@@ -451,14 +459,14 @@ static int check_pair(walt_engine* e, int ag) {
 
 static int launch_se(walt_engine* e, const char* d_seqs, const uint64_t* d_offs, uint64_t seq_base, uint32_t n,
                      uint32_t max_read_len, int ag, uint32_t m, uint32_t b, walt_best* d_out, uint32_t* d_queue,
-                     cudaStream_t st) {
+                     cudaStream_t st, uint32_t uniform_len = 0) {
   if (max_read_len > MAX_READ_LEN) return fail(WALT_EINVAL, "read longer than 1024 bases");
   SeArgs a;
   const int base = ag ? WALT_GA10 : WALT_CT00;
   a.ix[0] = e->sub[base].view(base); a.ix[1] = e->sub[base + 1].view(base + 1);
   a.cv = chrom_view(e); a.p3 = e->pow3;
   a.cfg.b = b; a.cfg.literal_all = e->search_mode == 1 ? 1u : 0u;
-  a.seqs = d_seqs; a.offs = d_offs; a.seq_base = seq_base; a.n = n;
+  a.seqs = d_seqs; a.offs = d_offs; a.seq_base = seq_base; a.n = n; a.uniform_len = uniform_len;
   a.nw_max = std::max<uint32_t>(1u, (max_read_len + 31u) / 32u);
   a.ag = ag ? 1u : 0u; a.max_mismatches = m; a.out = d_out; a.flags = e->d_flags; a.queue = d_queue;
   a.counters = e->d_counters;
@@ -466,6 +474,9 @@ static int launch_se(walt_engine* e, const char* d_seqs, const uint64_t* d_offs,
   const size_t smem = se_smem_bytes(a.nw_max, wd);
   uint32_t grid = 0;
   auto kernel = wd == 8u ? se_map_kernel<8> : wd == 16u ? se_map_kernel<16> : se_map_kernel<32>;
+  if (wd == 8u && e->min_blocks == 5) kernel = se_map_kernel<8, 5>;
+  if (wd == 8u && e->min_blocks == 6) kernel = se_map_kernel<8, 6>;
+  if (wd == 8u && e->min_blocks == 8) kernel = se_map_kernel<8, 8>;
   int rc = grid_for(e, kernel, smem, n, wd, &grid);
   if (rc) return rc;
   WALT_CUDA_TRY(cudaMemsetAsync(d_queue, 0, 4, st));
@@ -528,16 +539,23 @@ static int fetch_status(walt_engine* e) {
   return WALT_OK;
 }
 
-static uint32_t max_len_of(const uint64_t* offs, uint32_t n, uint32_t* n_short) {
-  uint32_t mx = 0, sh = 0;
-  for (uint32_t i = 0; i < n; ++i) {
+// One pass over the offsets of reads [r0, r0 + cn): longest read, reads below the 38-base minimum,
+// and the common length if all reads share one (0 otherwise).  Run per chunk, while the copies of
+// the previous chunk are in flight.
+struct ChunkScan { uint32_t max_len, n_short, uniform_len; };
+static ChunkScan scan_chunk(const uint64_t* offs, uint32_t r0, uint32_t cn) {
+  ChunkScan c{0u, 0u, 0u};
+  bool uniform = cn > 0;
+  const uint64_t first = cn ? offs[r0 + 1] - offs[r0] : 0;
+  for (uint32_t i = r0; i < r0 + cn; ++i) {
     const uint64_t l = offs[i + 1] - offs[i];
-    if (l > 0xFFFFFFFFull) return 0xFFFFFFFFu;
-    mx = std::max<uint32_t>(mx, (uint32_t)l);
-    sh += l < MIN_READ_LEN ? 1u : 0u;
+    if (l > 0xFFFFFFFFull) { c.max_len = 0xFFFFFFFFu; return c; }
+    c.max_len = std::max<uint32_t>(c.max_len, (uint32_t)l);
+    c.n_short += l < MIN_READ_LEN ? 1u : 0u;
+    uniform &= l == first;
   }
-  if (n_short) *n_short = 2u * sh;   // once per strand pass (mapping.cpp:230-232, paired.cpp:112-115)
-  return mx;
+  if (uniform && first > 0) c.uniform_len = (uint32_t)first;
+  return c;
 }
 
 }  // namespace waltb200
@@ -566,10 +584,13 @@ int walt_engine_create(walt_engine** out, int device) {
   cudaDeviceProp prop;
   WALT_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   e->sm_count = prop.multiProcessorCount;
+  // undocumented tuning knobs for experiments (defaults are what bench.py measures)
+  if (const char* v = getenv("WALT_MIN_BLOCKS")) e->min_blocks = atoi(v);
+  if (const char* v = getenv("WALT_L2_FETCH")) WALT_CUDA_TRY(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(v)));
   uint32_t p = 1;
   for (uint32_t i = 0; i <= MAX_DEPTH; ++i) { e->pow3.v[i] = p; p *= 3u; }
-  WALT_CUDA_TRY(cudaMalloc(&e->d_flags, 8 * 4));
-  WALT_CUDA_TRY(cudaMemset(e->d_flags, 0, 8 * 4));
+  WALT_CUDA_TRY(cudaMalloc(&e->d_flags, 32 * 4));
+  WALT_CUDA_TRY(cudaMemset(e->d_flags, 0, 32 * 4));
   WALT_CUDA_TRY(cudaMalloc(&e->d_counters, 3 * 8));
   WALT_CUDA_TRY(cudaMemset(e->d_counters, 0, 3 * 8));
   for (auto& s : e->slot) {
@@ -829,27 +850,35 @@ int walt_engine_map_se(walt_engine* e, const char* seqs, const uint64_t* offs, u
   int rc = ensure_device(e);
   if (rc) return rc;
   if ((rc = check_pair(e, ag_wildcard))) return rc;
-  const uint32_t max_len = max_len_of(offs, n, n_short);
-  if (max_len > MAX_READ_LEN) return fail(WALT_EINVAL, "read longer than 1024 bases");
   e->stats = walt_stats{};
-  WALT_CUDA_TRY(cudaMemset(e->d_counters, 0, 3 * 8));
-  uint32_t k = 0;
+  WALT_CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, 3 * 8, e->slot[0].stream));
+  WALT_CUDA_TRY(cudaStreamSynchronize(e->slot[0].stream));
+  uint32_t k = 0, total_short = 0;
   for (uint32_t r0 = 0; r0 < n; r0 += e->chunk_reads, ++k) {
     const uint32_t cn = std::min<uint32_t>(e->chunk_reads, n - r0);
-    BatchSlot& s = e->slot[k & 1u];
+    const ChunkScan sc = scan_chunk(offs, r0, cn);   // overlaps the previous chunk's copies and kernel
+    if (sc.max_len > MAX_READ_LEN) {
+      for (auto& s : e->slot) cudaStreamSynchronize(s.stream);
+      return fail(WALT_EINVAL, "read longer than 1024 bases");
+    }
+    total_short += sc.n_short;
+    BatchSlot& s = e->slot[k % N_SLOTS];
     WALT_CUDA_TRY(cudaEventSynchronize(s.done));
     const uint64_t sb = offs[r0], se = offs[r0 + cn];
     if ((rc = reserve(&s.d_seqs, &s.seqs_cap, (size_t)(se - sb) + 16u))) return rc;
-    if ((rc = reserve(&s.d_offs, &s.offs_cap, (size_t)cn + 1u))) return rc;
     if ((rc = reserve_bytes(&s.d_out, &s.out_cap, (size_t)cn * sizeof(walt_best)))) return rc;
     if (se > sb) WALT_CUDA_TRY(cudaMemcpyAsync(s.d_seqs, seqs + sb, se - sb, cudaMemcpyHostToDevice, s.stream));
-    WALT_CUDA_TRY(cudaMemcpyAsync(s.d_offs, offs + r0, ((size_t)cn + 1u) * 8u, cudaMemcpyHostToDevice, s.stream));
-    if ((rc = launch_se(e, s.d_seqs, s.d_offs, sb, cn, max_len, ag_wildcard, max_mismatches, b, (walt_best*)s.d_out,
-                        e->d_flags + 4 + (k & 1u), s.stream)))
+    if (!sc.uniform_len) {   // equal-length reads are addressed by stride: no offsets cross PCIe
+      if ((rc = reserve(&s.d_offs, &s.offs_cap, (size_t)cn + 1u))) return rc;
+      WALT_CUDA_TRY(cudaMemcpyAsync(s.d_offs, offs + r0, ((size_t)cn + 1u) * 8u, cudaMemcpyHostToDevice, s.stream));
+    }
+    if ((rc = launch_se(e, s.d_seqs, s.d_offs, sb, cn, sc.max_len, ag_wildcard, max_mismatches, b, (walt_best*)s.d_out,
+                        e->d_flags + 4 + (k % N_SLOTS), s.stream, sc.uniform_len)))
       return rc;
     WALT_CUDA_TRY(cudaMemcpyAsync(out + r0, s.d_out, (size_t)cn * sizeof(walt_best), cudaMemcpyDeviceToHost, s.stream));
     WALT_CUDA_TRY(cudaEventRecord(s.done, s.stream));
   }
+  if (n_short) *n_short = 2u * total_short;   // once per strand pass (mapping.cpp:230-232)
   for (auto& s : e->slot) WALT_CUDA_TRY(cudaStreamSynchronize(s.stream));
   return fetch_status(e);
 }
@@ -874,7 +903,10 @@ int walt_engine_map_pe(walt_engine* e, const char* seqs1, const uint64_t* offs1,
     for (uint32_t i = 0; i < n; ++i) std::swap(pairs[i].best_i, pairs[i].best_j);
     return WALT_OK;
   }
-  const uint32_t max1 = max_len_of(offs1, n, n_short1), max2 = max_len_of(offs2, n, n_short2);
+  const ChunkScan sc1 = scan_chunk(offs1, 0, n), sc2 = scan_chunk(offs2, 0, n);
+  const uint32_t max1 = sc1.max_len, max2 = sc2.max_len;
+  if (n_short1) *n_short1 = 2u * sc1.n_short;   // once per strand pass (paired.cpp:112-115)
+  if (n_short2) *n_short2 = 2u * sc2.n_short;
   if (max1 > MAX_READ_LEN || max2 > MAX_READ_LEN) return fail(WALT_EINVAL, "read longer than 1024 bases");
   e->stats = walt_stats{};
   WALT_CUDA_TRY(cudaMemset(e->d_counters, 0, 3 * 8));
@@ -883,7 +915,7 @@ int walt_engine_map_pe(walt_engine* e, const char* seqs1, const uint64_t* offs1,
   uint32_t k = 0;
   for (uint32_t r0 = 0; r0 < n; r0 += chunk, ++k) {
     const uint32_t cn = std::min<uint32_t>(chunk, n - r0);
-    BatchSlot& s = e->slot[k & 1u];
+    BatchSlot& s = e->slot[k % N_SLOTS];
     WALT_CUDA_TRY(cudaEventSynchronize(s.done));
     const uint64_t sb1 = offs1[r0], se1 = offs1[r0 + cn], sb2 = offs2[r0], se2 = offs2[r0 + cn];
     if ((rc = reserve(&s.d_seqs, &s.seqs_cap, (size_t)(se1 - sb1) + 16u))) return rc;
@@ -903,7 +935,7 @@ int walt_engine_map_pe(walt_engine* e, const char* seqs1, const uint64_t* offs1,
     if (se2 > sb2) WALT_CUDA_TRY(cudaMemcpyAsync(s.d_seqs2, seqs2 + sb2, se2 - sb2, cudaMemcpyHostToDevice, s.stream));
     WALT_CUDA_TRY(cudaMemcpyAsync(s.d_offs, offs1 + r0, ((size_t)cn + 1u) * 8u, cudaMemcpyHostToDevice, s.stream));
     WALT_CUDA_TRY(cudaMemcpyAsync(s.d_offs2, offs2 + r0, ((size_t)cn + 1u) * 8u, cudaMemcpyHostToDevice, s.stream));
-    uint32_t* q = e->d_flags + 4 + 2u * (k & 1u);
+    uint32_t* q = e->d_flags + 4 + N_SLOTS + 2u * (k % N_SLOTS);
     // mate 1: C->T against _CT00/_CT01; mate 2: G->A against _GA10/_GA11 (paired.cpp:642-672)
     if ((rc = launch_pe_mate(e, s.d_seqs, s.d_offs, sb1, cn, max1, 0, max_mismatches, b, top_k, d_r1, d_n1, q, s.stream)))
       return rc;

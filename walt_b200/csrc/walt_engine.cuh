@@ -40,7 +40,9 @@ struct DeviceSubIndex {
   void release();
 };
 
-// one in-flight chunk of a host batch (double buffered)
+constexpr uint32_t N_SLOTS = 3;   // host chunks in flight (copy in / map / copy out)
+
+// one in-flight chunk of a host batch
 struct BatchSlot {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
@@ -68,10 +70,12 @@ struct walt_engine {
   waltcore::Pow3 pow3;
   int search_mode = 0;
   int force_depth = 0;
+  int min_blocks = 4;         // resident CTAs per SM the SE kernel is compiled for (register cap)
   uint32_t group_width = 8;   // lanes that own one read (8, 16 or 32)
-  uint32_t chunk_reads = 1u << 20;
-  waltb200::BatchSlot slot[2];
-  uint32_t* d_flags = nullptr;               // [0] non-ACGT flag, [1] work-queue head, [2..3] spare
+  uint32_t chunk_reads = 1u << 18;
+  waltb200::BatchSlot slot[waltb200::N_SLOTS];
+  uint32_t* d_flags = nullptr;               // [0] non-ACGT flag, [1] work-queue head, [2..3] spare,
+                                             // [4..4+N_SLOTS) SE chunk queues, then 2 per slot for PE
   unsigned long long* d_counters = nullptr;  // lookups, candidates, literal
   walt_stats stats{};
 };
