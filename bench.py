@@ -17,6 +17,10 @@ pinned host buffers, host<->device copies inside the timed region.  Multi-GPU: o
 GPU (torchrun), full index replica per GPU, reads sharded, no collective on the data path
 ("weak" scaling: 10 M reads per GPU); barrier + max over ranks.
 
+`--workload se_ag` (configs[2]: A-rich reads, -A, the _GA10/_GA11 pair) and `--workload pe`
+(configs[3]: 5 M pairs 2x150 bp, -k 50 -L 1000, all four sub-indexes) measure the other
+full-size configurations with the same contract; the default line is configs[1].
+
 `--impl reference` times the UNMODIFIED reference (oracle/_ref/libwaltref.so, the reference's
 own SingleEndMapping object code under OpenMP with every host core) on a bounded sample of the
 same workload; the index it maps against is exported from the device builder (set-up, not
@@ -40,9 +44,10 @@ sys.path.insert(0, ROOT)
 
 HG19_MB = [249.25, 243.20, 198.02, 191.15, 180.92, 171.12, 159.14, 146.36, 141.21, 135.53, 135.01, 133.85,
            115.17, 107.35, 102.53, 90.35, 81.20, 78.08, 59.13, 63.03, 48.13, 51.30, 155.27, 59.37]
-METRIC = "reads mapped/sec (SE 150bp, hg19-size synthetic)"
-UNIT = "reads/s"
-M, B = 6, 5000
+METRICS = {"se": ("reads mapped/sec (SE 150bp, hg19-size synthetic)", "reads/s"),
+           "se_ag": ("reads mapped/sec (SE 150bp -A, hg19-size synthetic)", "reads/s"),
+           "pe": ("read pairs mapped/sec (PE 2x150bp -k 50 -L 1000, hg19-size synthetic)", "pairs/s")}
+M, B, TOP_K, FRAG = 6, 5000, 50, 1000
 
 
 def chrom_lengths(total_bases):
@@ -57,53 +62,74 @@ def dist_env():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML every few milliseconds on a background
+    thread while the timed regions run (the nvidia-smi loop of B200_PROFILING.md cannot sample a
+    region that lasts tens of milliseconds)."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+    def __init__(self, gpu_index, period_s=0.004):
+        self.gpu, self.period = gpu_index, period_s
+        self.rows, self.stop_flag, self.thread, self.h = [], False, None, None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.rows.append((time.perf_counter(), float(sm), int(rs)))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def start(self):
-        try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
-                                      stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+        if self.h is None:
+            return
+        import threading
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
-    def stop(self):
+    def mark(self):
+        return time.perf_counter()
+
+    def stop(self, windows=None):
+        """windows: list of (t0, t1) perf_counter intervals that count as "timed region"."""
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
+        if self.h is None or self.thread is None:
             return out
-        time.sleep(0.15)
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-        self.f.flush()
-        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
-        os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            if len(r) < 8:
-                continue
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, r[4:8]):
-                if v.strip().lower().startswith("active"):
-                    reasons.add(nm)
-        if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                   "samples": len(sm)}
-        return out
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        rows = self.rows
+        if windows:
+            inside = [r for r in rows if any(a <= r[0] <= b for a, b in windows)]
+            rows = inside or rows
+        if not rows:
+            return out
+        reasons = sorted(nm for nm, bit in self.REASONS.items() if any(r[2] & bit for r in rows))
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": self.max_sm, "reasons": reasons,
+                "samples": len(rows), "how": "NVML, sampled every 4 ms inside the timed regions"}
+
+
+def committed_traffic(kernel, n_reads, genome_mb):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of
+    this same command (profiles/traffic.json); None when the workload differs from the captured one."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]
+        if t["reads_per_launch"] == n_reads and abs(t["genome_mb"] - genome_mb) < 1e-6:
+            return t["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
 
 
 def measured_peak_gbs():
@@ -113,13 +139,14 @@ def measured_peak_gbs():
         return 6650.0, "fallback"
 
 
-def algorithmic_bytes(ctr, n_reads, rl):
-    """bytes a step must touch, from the oracle's deterministic work counters."""
+def algorithmic_bytes(ctr, n_reads, rl, pe=False):
+    """bytes a step must touch, from the oracle's deterministic work counters.
+    n_reads counts reads (SE) or pairs (PE: two packed reads in, one 72-byte summary out)."""
     s = min(50, (rl - 2) // 3)
     per_probe = 4 + -(-3 * (s - 12) // 4)
     seed = 8 * ctr["n_lookups"] + 2 * ctr["sum_log2_bucket"] * per_probe
     verify = ctr["n_cand"] * (4 + -(-rl // 4))
-    io = n_reads * (-(-rl // 4) + 16)
+    io = n_reads * ((2 * -(-rl // 4) + 72) if pe else (-(-rl // 4) + 16))
     return {"seed": seed / n_reads, "verify": verify / n_reads, "io": io / n_reads,
             "total": (seed + verify + io) / n_reads}
 
@@ -133,6 +160,9 @@ class Workload:
         from walt_b200 import engine as eng
         self.torch, self.eng = torch, eng
         self.device = device
+        self.kind = getattr(args, "workload", "se")
+        self.ag = self.kind == "se_ag"
+        self.which = {"se": (0, 1), "se_ag": (2, 3), "pe": (0, 1, 2, 3)}[self.kind]
         self.n, self.rl = args.reads, args.read_len
         total = int(args.genome_mb * 1e6)
         self.lengths = chrom_lengths(total)
@@ -142,85 +172,168 @@ class Workload:
         self.e.set_group_width(args.group_width)
         self.e.set_table_depth(args.table_depth)
         self.e.set_chromosomes(self.lengths, self.names)
-        d_fwd = torch.empty(eng.packed_genome_bytes(total), dtype=torch.uint8, device=f"cuda:{device}")
+        dev = f"cuda:{device}"
+        d_fwd = torch.empty(eng.packed_genome_bytes(total), dtype=torch.uint8, device=dev)
         eng.synth_genome_device(device, total, 3, d_fwd.data_ptr())
-        self.e.build_from_device_genome(d_fwd.data_ptr(), which=(0, 1))
+        self.e.build_from_device_genome(d_fwd.data_ptr(), which=self.which)
         torch.cuda.synchronize()
         self.t_index = time.time() - t0
-        self.d_reads = torch.empty(self.n * self.rl, dtype=torch.uint8, device=f"cuda:{device}")
+        self.d_reads = torch.empty(self.n * self.rl, dtype=torch.uint8, device=dev)
+        self.d_reads2 = None
         # every rank maps its own shard: different read seed per rank
-        self.e.synth_reads_device(d_fwd.data_ptr(), self.n, self.rl, 4 + 1000 * rank, False, self.d_reads.data_ptr())
+        if self.kind == "pe":
+            self.d_reads2 = torch.empty(self.n * self.rl, dtype=torch.uint8, device=dev)
+            self.e.synth_pairs_device(d_fwd.data_ptr(), self.n, self.rl, 5 + 1000 * rank, self.d_reads.data_ptr(),
+                                      self.d_reads2.data_ptr())
+        else:
+            self.e.synth_reads_device(d_fwd.data_ptr(), self.n, self.rl, 4 + 1000 * rank, self.ag, self.d_reads.data_ptr())
         del d_fwd
         torch.cuda.empty_cache()
-        self.d_offs = torch.arange(self.n + 1, dtype=torch.int64, device=f"cuda:{device}") * self.rl
-        self.d_out = torch.zeros(self.n * 16, dtype=torch.uint8, device=f"cuda:{device}")
+        self.d_offs = torch.arange(self.n + 1, dtype=torch.int64, device=dev) * self.rl
+        out_bytes = eng.PE_RESULT_DT.itemsize if self.kind == "pe" else 16
+        self.out_dt = eng.PE_RESULT_DT if self.kind == "pe" else eng.BEST_DT
+        self.d_out = torch.zeros(self.n * out_bytes, dtype=torch.uint8, device=dev)
         torch.cuda.synchronize()
 
+    def device_step(self, stream):
+        if self.kind == "pe":
+            self.e.map_pe_device(self.d_reads.data_ptr(), self.d_offs.data_ptr(), self.d_reads2.data_ptr(),
+                                 self.d_offs.data_ptr(), self.n, self.rl, self.d_out.data_ptr(), m=M, b=B, top_k=TOP_K,
+                                 frag_range=FRAG, stream=stream)
+        else:
+            self.e.map_se_device(self.d_reads.data_ptr(), self.d_offs.data_ptr(), self.n, self.rl, self.d_out.data_ptr(),
+                                 ag=self.ag, m=M, b=B, stream=stream)
+
+    def launches_per_step(self):
+        if self.kind != "pe":
+            return 1
+        chunk = max(1024, min(self.n, (1 << 30) // (2 * TOP_K * 12)))
+        return 3 * -(-self.n // chunk)
+
     def host_index(self):
-        """Export both sub-indexes into reference-owned Genome/HashTable objects."""
+        """Export the resident sub-indexes into reference-owned Genome/HashTable objects."""
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import refio
         L = refio.ref_lib()
-        out = []
-        for which, strand in ((0, "+"), (1, "-")):
+        out = {}
+        for which in self.which:
             info = self.e.subindex_info(which)
             h = C.c_void_p(L.waltref_index_alloc(C.c_uint32(len(self.lengths)),
                                                  self.lengths.ctypes.data_as(C.c_void_p),
                                                  C.c_uint32(info["index_size"])))
-            L.waltref_index_set_strand(h, C.c_char(strand.encode()))
+            L.waltref_index_set_strand(h, C.c_char(b"-" if which & 1 else b"+"))
             got = C.c_uint32()
             self.e._check(self.e.L.walt_engine_export_subindex(
                 self.e.h, C.c_int(which), C.c_void_p(L.waltref_index_sequence(h)),
                 C.c_void_p(L.waltref_index_counter(h)), C.c_void_p(L.waltref_index_index(h)), C.byref(got)))
-            out.append(h)
+            out[which] = h
         return out
 
-    def sample_reads(self, n):
+    def sample_reads(self, n, mate=1):
         n = min(n, self.n)
-        buf = self.d_reads[: n * self.rl].cpu().numpy()
+        src = self.d_reads if mate == 1 else self.d_reads2
+        buf = src[: n * self.rl].cpu().numpy()
         offs = np.arange(n + 1, dtype=np.uint64) * np.uint64(self.rl)
         return buf, offs
 
 
-def reference_pass(hidx, buf, offs, threads):
-    """Both strand passes of the reference's OpenMP loop (mapping.cpp:486-500); -> (seconds, BestMatch[])."""
+def reference_pass(wl, hidx, n, threads):
+    """The reference's OpenMP loops over the first n reads (pairs) of the batch: both strand passes
+    of mapping.cpp:486-500, or the 2 mates x 2 strands of paired.cpp:642-672.
+    -> (seconds inside the loops, results: BestMatch[] | {mate: (ranked, sizes)})."""
     import refio
     L = refio.ref_lib()
-    n = len(offs) - 1
-    best = refio.init_best(n, M)
-    t = 0.0
-    for h, strand in zip(hidx, "+-"):
-        t += L.waltref_time_se(h, buf.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p), C.c_uint32(n),
-                               C.c_char(strand.encode()), C.c_int(0), C.c_uint32(B),
-                               best.ctypes.data_as(C.c_void_p), C.c_int(threads))
-    return t, best
+    if wl.kind != "pe":
+        buf, offs = wl.sample_reads(n)
+        best = refio.init_best(n, M)
+        t = 0.0
+        for which, strand in zip(wl.which, "+-"):
+            t += L.waltref_time_se(hidx[which], buf.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p),
+                                   C.c_uint32(n), C.c_char(strand.encode()), C.c_int(int(wl.ag)), C.c_uint32(B),
+                                   best.ctypes.data_as(C.c_void_p), C.c_int(threads))
+        return t, best
+    t, res = 0.0, {}
+    for mate, ag, pair in ((1, 0, (0, 1)), (2, 1, (2, 3))):
+        buf, offs = wl.sample_reads(n, mate)
+        hp = C.c_void_p(L.waltref_heaps_alloc(C.c_uint32(n), C.c_uint32(TOP_K)))
+        for which, strand in zip(pair, "+-"):
+            t += L.waltref_time_pe(hidx[which], hp, buf.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p),
+                                   C.c_uint32(n), C.c_char(strand.encode()), C.c_int(ag), C.c_uint32(M), C.c_uint32(B),
+                                   C.c_int(threads))
+        ranked = np.zeros((n, TOP_K), dtype=refio.CAND_DT)
+        sizes = np.zeros(n, dtype=np.uint32)
+        L.waltref_heaps_drain(hp, C.c_uint32(n), C.c_uint32(TOP_K), ranked.ctypes.data_as(C.c_void_p),
+                              sizes.ctypes.data_as(C.c_void_p))
+        L.waltref_heaps_free(hp)
+        res[mate] = (ranked, sizes)
+    return t, res
 
 
-def oracle_counters(wl, hidx, buf, offs):
-    """Work counters of the C oracle on a sample (feeds the algorithmic-bytes model)."""
+def oracle_counters(wl, hidx, n):
+    """Work counters of the C oracle on the first n reads (pairs): feeds the algorithmic-bytes model."""
     import refio
     L = refio.ref_lib()
     Lo = refio.oracle_lib()
     starts = np.concatenate([[0], np.cumsum(wl.lengths.astype(np.uint64))]).astype(np.uint32)
-    n = len(offs) - 1
-    best = refio.init_best(n, M)
     ctr = refio.WoCounters()
-    for h, strand in zip(hidx, "+-"):
-        ix = refio.WoIndex(L.waltref_index_sequence(h), int(L.waltref_index_genome_len(h)), len(wl.lengths),
-                           starts.ctypes.data, L.waltref_index_counter(h), L.waltref_index_index(h),
-                           int(L.waltref_index_index_size(h)))
-        Lo.wo_se_map_batch(C.byref(ix), buf.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p),
-                           C.c_uint32(n), C.c_char(strand.encode()), C.c_int(0), C.c_uint32(B),
-                           best.ctypes.data_as(C.c_void_p), C.byref(ctr))
-    return ctr.asdict(), best
+
+    def view(which):
+        h = hidx[which]
+        return refio.WoIndex(L.waltref_index_sequence(h), int(L.waltref_index_genome_len(h)), len(wl.lengths),
+                             starts.ctypes.data, L.waltref_index_counter(h), L.waltref_index_index(h),
+                             int(L.waltref_index_index_size(h)))
+    if wl.kind != "pe":
+        buf, offs = wl.sample_reads(n)
+        best = refio.init_best(n, M)
+        for which, strand in zip(wl.which, "+-"):
+            ix = view(which)
+            Lo.wo_se_map_batch(C.byref(ix), buf.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p),
+                               C.c_uint32(n), C.c_char(strand.encode()), C.c_int(int(wl.ag)), C.c_uint32(B),
+                               best.ctypes.data_as(C.c_void_p), C.byref(ctr))
+        return ctr.asdict(), best
+    for mate, ag, pair in ((1, 0, (0, 1)), (2, 1, (2, 3))):
+        buf, offs = wl.sample_reads(n, mate)
+        cands = np.zeros((n, TOP_K), dtype=refio.CAND_DT)
+        sizes = np.zeros(n, dtype=np.uint32)
+        for which, strand in zip(pair, "+-"):
+            ix = view(which)
+            Lo.wo_pe_map_batch(C.byref(ix), buf.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p),
+                               C.c_uint32(n), C.c_char(strand.encode()), C.c_int(ag), C.c_uint32(M), C.c_uint32(B),
+                               C.c_uint32(TOP_K), cands.ctypes.data_as(C.c_void_p), sizes.ctypes.data_as(C.c_void_p),
+                               C.byref(ctr))
+    return ctr.asdict(), None
+
+
+def parity_vs_reference(wl, n, ref_result):
+    """Fields of the engine's results that differ from the unmodified reference's on the first n
+    reads (pairs).  PE compares the drained heaps (through the full-list entry point)."""
+    import refio
+    if wl.kind != "pe":
+        got = wl.d_out[: n * 16].cpu().numpy().view(refio.BEST_DT)
+        return sum(int((got[f] != ref_result[f]).sum()) for f in ("genome_pos", "times", "mismatch", "strand"))
+    n = min(n, 200000)
+    b1, o1 = wl.sample_reads(n, 1)
+    b2, o2 = wl.sample_reads(n, 2)
+    r = wl.e.map_pe(b1, o1, b2, o2, m=M, b=B, top_k=TOP_K, frag_range=FRAG)
+    bad = 0
+    for mate in (1, 2):
+        ranked, sizes = ref_result[mate]
+        bad += int((r[f"n{mate}"] != sizes[:n]).sum())
+        for f in ("genome_pos", "mismatch", "strand"):
+            bad += int((r[f"ranked{mate}"][f] != ranked[:n][f]).sum())
+    return bad
 
 
 def config_dict(args, extra=None):
-    d = {"workload": f"configs[1]: {args.genome_mb:g} Mb synthetic genome (24 chr, hg19 profile), "
-                     f"{args.reads} SE {args.read_len} bp bisulfite reads per GPU, -m {M} -b {B}",
-         "genome_mb": args.genome_mb, "reads_per_gpu": args.reads, "read_len": args.read_len,
+    what = {"se": f"configs[1]: {args.genome_mb:g} Mb synthetic genome (24 chr, hg19 profile), {args.reads} SE "
+                  f"{args.read_len} bp bisulfite reads per GPU, -m {M} -b {B}",
+            "se_ag": f"configs[2]: {args.genome_mb:g} Mb synthetic genome (24 chr, hg19 profile), {args.reads} A-rich SE "
+                     f"{args.read_len} bp reads per GPU, -A -m {M} -b {B}",
+            "pe": f"configs[3]: {args.genome_mb:g} Mb synthetic genome (24 chr, hg19 profile), {args.reads} pairs "
+                  f"2x{args.read_len} bp per GPU, -m {M} -b {B} -k {TOP_K} -L {FRAG}"}[args.workload]
+    d = {"workload": what, "genome_mb": args.genome_mb, "reads_per_gpu": args.reads, "read_len": args.read_len,
          "max_mismatches": M, "bucket_limit": B, "parallelism": f"reads sharded x{args.gpus}, index replicated",
-         "l2": "inputs larger than L2 (index >= 13 GB randomly gathered, 1.5 GB of reads streamed per step)"}
+         "l2": "inputs larger than L2 (index >= 13 GB per strand randomly gathered, >= 1.5 GB of reads streamed per step)"}
     if extra:
         d.update(extra)
     return d
@@ -230,6 +343,7 @@ def run_reference(args):
     rank, local, world = dist_env()
     if rank != 0:
         return 0
+    metric, unit = METRICS[args.workload]
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import refio
     if not refio.have_reference():
@@ -239,25 +353,24 @@ def run_reference(args):
     hidx = wl.host_index()
     threads = os.cpu_count() or 1
     cal_n = min(50000, wl.n)
-    buf, offs = wl.sample_reads(cal_n)
-    t_cal, _ = reference_pass(hidx, buf, offs, threads)
+    t_cal, _ = reference_pass(wl, hidx, cal_n, threads)
     per_step_s = 8.0
     n = int(max(cal_n, min(wl.n, cal_n * per_step_s / max(t_cal, 1e-6))))
-    buf, offs = wl.sample_reads(n)
     for _ in range(args.warmup):
-        reference_pass(hidx, buf, offs, threads)
+        reference_pass(wl, hidx, n, threads)
     t = 0.0
     for _ in range(args.steps):
-        dt, _ = reference_pass(hidx, buf, offs, threads)
+        dt, _ = reference_pass(wl, hidx, n, threads)
         t += dt
     value = n * args.steps / t
-    sample = f"first {n} reads of rank 0's batch per step, both strand passes, OpenMP loop only"
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+    sample = (f"first {n} {'pairs' if wl.kind == 'pe' else 'reads'} of rank 0's batch per step, every strand pass, "
+              f"OpenMP loops only")
+    line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": config_dict(args, {"reference_sample_reads": n}),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "reference", "sample": sample},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
     return 0
@@ -266,6 +379,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     rank, local, world = dist_env()
+    metric, unit = METRICS[args.workload]
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
@@ -276,6 +390,7 @@ def run_ours(args):
     dev = torch.device(f"cuda:{local}")
     wl = Workload(args, local, rank)
     e, n, rl = wl.e, wl.n, wl.rl
+    pe = wl.kind == "pe"
     stream = torch.cuda.current_stream()
 
     def barrier():
@@ -285,8 +400,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def device_step():
-        e.map_se_device(wl.d_reads.data_ptr(), wl.d_offs.data_ptr(), n, rl, wl.d_out.data_ptr(), ag=False, m=M, b=B,
-                        stream=stream.cuda_stream)
+        wl.device_step(stream.cuda_stream)
 
     # ---- side legs on rank 0 (not timed): oracle counters, parity spot check, CPU baseline ----
     cpu_baseline, alg, parity = None, None, None
@@ -298,98 +412,124 @@ def run_ours(args):
         hidx = wl.host_index() if refio.have_reference() else None
         if hidx is not None:
             ns = min(20000, n)
-            buf, offs = wl.sample_reads(ns)
-            ctr, obest = oracle_counters(wl, hidx, buf, offs)
-            alg = algorithmic_bytes(ctr, ns, rl)
-            got = wl.d_out[: ns * 16].cpu().numpy().view(refio.BEST_DT)
-            bad = sum(int((got[f] != obest[f]).sum()) for f in ("genome_pos", "times", "mismatch", "strand"))
-            parity = {"sample_reads": ns, "fields_differing_vs_oracle": bad,
-                      "unique_frac": float((got["times"] == 1).mean())}
+            ctr, obest = oracle_counters(wl, hidx, ns)
+            alg = algorithmic_bytes(ctr, ns, rl, pe)
+            parity = {"sample_reads": ns}
+            if not pe:
+                got = wl.d_out[: ns * 16].cpu().numpy().view(refio.BEST_DT)
+                parity["fields_differing_vs_oracle"] = sum(int((got[f] != obest[f]).sum())
+                                                           for f in ("genome_pos", "times", "mismatch", "strand"))
+                parity["unique_frac"] = float((got["times"] == 1).mean())
+            else:
+                got = wl.d_out[: ns * wl.out_dt.itemsize].cpu().numpy().view(wl.out_dt)
+                parity["unique_pair_frac"] = float((got["pair"]["best_times"] == 1).mean())
             if world == 1:
                 threads = os.cpu_count() or 1
                 cal_n = min(50000, n)
-                buf, offs = wl.sample_reads(cal_n)
-                t_cal, _ = reference_pass(hidx, buf, offs, threads)
+                t_cal, _ = reference_pass(wl, hidx, cal_n, threads)
                 cn = int(max(cal_n, min(n, cal_n * 12.0 / max(t_cal, 1e-6))))
-                buf, offs = wl.sample_reads(cn)
-                t_ref, rbest = reference_pass(hidx, buf, offs, threads)
-                gotc = wl.d_out[: cn * 16].cpu().numpy().view(refio.BEST_DT)
-                badc = sum(int((gotc[f] != rbest[f]).sum()) for f in ("genome_pos", "times", "mismatch", "strand"))
-                parity["reference_sample_reads"] = cn
-                parity["fields_differing_vs_reference"] = badc
-                cpu_baseline = {"value": cn / t_ref, "unit": UNIT, "cores": threads, "kind": "reference",
-                                "sample": f"first {cn} reads of the batch, both strand passes, OpenMP loop of the "
-                                          f"unmodified reference (oracle/_ref/libwaltref.so), {t_ref:.1f} s"}
+                t_ref, rres = reference_pass(wl, hidx, cn, threads)
+                parity["reference_sample_reads"] = cn if not pe else min(cn, 200000)
+                parity["fields_differing_vs_reference"] = parity_vs_reference(wl, cn, rres)
+                cpu_baseline = {"value": cn / t_ref, "unit": unit, "cores": threads, "kind": "reference",
+                                "sample": f"first {cn} {'pairs' if pe else 'reads'} of the batch, every strand pass, "
+                                          f"OpenMP loops of the unmodified reference (oracle/_ref/libwaltref.so), "
+                                          f"{t_ref:.1f} s"}
             L = refio.ref_lib()
-            for h in hidx:
+            for h in hidx.values():
                 L.waltref_index_free(h)
 
     # ---- device-resident timing (`value`) ----
     for _ in range(args.warmup):
         device_step()
-    barrier()
     sampler = ClockSampler(local)
     sampler.start()
+    barrier()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    w0 = sampler.mark()
     evs[0].record(stream)
     for i in range(args.steps):
         device_step()
         evs[i + 1].record(stream)
     barrier()
-    clocks = sampler.stop()
+    windows = [(w0, sampler.mark())]
     step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
     t_dev = evs[0].elapsed_time(evs[-1]) / 1e3
 
     if args.no_e2e:   # kernel experiments only: not a bench line
+        sampler.stop(windows)
         if rank == 0:
-            print(json.dumps({"experiment": True, "kernel_ms": float(np.mean(step_ms)), "reads_per_s": n * 1e3 / float(np.mean(step_ms)),
+            print(json.dumps({"experiment": True, "workload": wl.kind, "kernel_ms": float(np.mean(step_ms)),
+                              "per_s": n * 1e3 / float(np.mean(step_ms)),
                               "env": {k: v for k, v in os.environ.items() if k.startswith("WALT_")}}))
         return 0
     # ---- end-to-end timing through the C ABI with pinned host buffers (`e2e`) ----
-    from walt_b200.engine import BEST_DT, PinnedArray
-    h_reads = PinnedArray((n * rl,), np.uint8)
+    from walt_b200.engine import PinnedArray
     h_offs = PinnedArray((n + 1,), np.uint64)
-    h_out = PinnedArray((n,), BEST_DT)
-    h_reads.array[:] = wl.d_reads.cpu().numpy()
     h_offs.array[:] = np.arange(n + 1, dtype=np.uint64) * np.uint64(rl)
+    h_out = PinnedArray((n,), wl.out_dt)
+    h_reads = PinnedArray((n * rl,), np.uint8)
+    h_reads.array[:] = wl.d_reads.cpu().numpy()
+    h_reads2 = None
+    if pe:
+        h_reads2 = PinnedArray((n * rl,), np.uint8)
+        h_reads2.array[:] = wl.d_reads2.cpu().numpy()
+
+    def e2e_step():
+        if pe:
+            e.map_pe_compact(h_reads.array, h_offs.array, h_reads2.array, h_offs.array, m=M, b=B, top_k=TOP_K,
+                             frag_range=FRAG, out=h_out.array)
+        else:
+            e.map_se(h_reads.array, h_offs.array, ag=wl.ag, m=M, b=B, out=h_out.array)
+
     for _ in range(max(1, args.warmup // 2)):
-        e.map_se(h_reads.array, h_offs.array, ag=False, m=M, b=B, out=h_out.array)
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        e.map_se(h_reads.array, h_offs.array, ag=False, m=M, b=B, out=h_out.array)
+        e2e_step()
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
+    windows.append((t0, t0 + t_e2e))
+    clocks = sampler.stop(windows)
     launches_e2e = e.stats()["n_kernel_launches"]
-    same = bool(np.array_equal(h_out.array[:1000].view(np.uint8), wl.d_out[:16000].cpu().numpy()))
+    nb = 1000 * wl.out_dt.itemsize
+    same = bool(np.array_equal(h_out.array[:1000].view(np.uint8), wl.d_out[:nb].cpu().numpy()))
     barrier()
 
     from walt_b200.sharding import max_over_ranks
     t_dev, t_e2e = max_over_ranks([t_dev, t_e2e], dist, dev)
     if rank == 0:
-        total_reads = n * world * args.steps
+        total = n * world * args.steps
         peak, peak_kind = measured_peak_gbs()
         kernel_s = float(np.mean(step_ms)) / 1e3
         roof = None
+        kname = "pe_map_kernel" if pe else "se_map_kernel"
         if alg is not None:
             achieved = alg["total"] * n / kernel_s / 1e9
             roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_kind": peak_kind, "kernel": "se_map_kernel",
-                    "algorithmic_bytes_per_read": alg, "kernel_ms": kernel_s * 1e3}
-        line = {"metric": METRIC, "value": total_reads / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                    "traffic": committed_traffic(kname if pe else "se_map_kernel" + ("_ag" if wl.ag else ""), n, args.genome_mb),
+                    "peak_kind": peak_kind, "kernel": kname,
+                    "algorithmic_bytes_per_read": alg, "kernel_ms": kernel_s * 1e3,
+                    "note": "algorithmic bytes follow SURVEY.md 8(d) (the reference's binary-search probes); "
+                            "achieved/frac are that figure over the step's device time"
+                            + (" (two pe_map_kernel launches + pair_kernel per chunk)" if pe else "")}
+        line = {"metric": metric, "value": total / t_dev, "unit": unit, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": config_dict(args, {"index_build_s": round(wl.t_index, 1), "hbm_index_bytes": e.hbm_bytes(),
-                                             "table_depth": e.subindex_info(0)["depth"],
+                                             "table_depth": [e.subindex_info(w)["depth"] for w in wl.which],
                                              "group_width": args.group_width}),
                 "clocks": clocks,
-                "e2e": {"value": total_reads / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(n * rl + 8 * (n + 1)),
-                        "d2h_bytes_per_step": int(16 * n), "ms_per_step": 1e3 * t_e2e / args.steps,
+                "e2e": {"value": total / t_e2e, "unit": unit, "h2d_bytes_per_step": int(n * rl * (2 if pe else 1)),
+                        "d2h_bytes_per_step": int(wl.out_dt.itemsize * n), "ms_per_step": 1e3 * t_e2e / args.steps,
                         "kernel_launches_per_step": launches_e2e, "matches_device_path": same},
-                "gpu_launches": args.steps,
+                "gpu_launches": args.steps * wl.launches_per_step(),
                 "roofline": roof, "cpu_baseline": cpu_baseline, "parity_check": parity}
         print(json.dumps(line))
-    h_reads.free(); h_offs.free(); h_out.free()
+    for h in (h_reads, h_reads2, h_offs, h_out):
+        if h is not None:
+            h.free()
     if dist is not None:
         dist.destroy_process_group()
     return 0
@@ -402,7 +542,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--genome-mb", type=float, default=3100.0)
-    ap.add_argument("--reads", type=int, default=10_000_000)
+    ap.add_argument("--workload", default="se", choices=["se", "se_ag", "pe"],
+                    help="se = configs[1] (the bench line), se_ag = configs[2], pe = configs[3]")
+    ap.add_argument("--reads", type=int, default=0, help="reads (pairs) per GPU; default 10 M reads / 5 M pairs")
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--no-cpu", action="store_true", help="skip the oracle/reference side legs")
     ap.add_argument("--no-e2e", action="store_true", help="kernel experiment: print the device timing only")
@@ -411,6 +553,8 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    if args.reads <= 0:
+        args.reads = 5_000_000 if args.workload == "pe" else 10_000_000
     sys.exit(run_reference(args) if args.impl == "reference" else run_ours(args))
 
 

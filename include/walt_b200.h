@@ -65,6 +65,16 @@ typedef struct {
   int32_t frag_len;        /* GetFragmentLength of the winning pair (valid if times>=1)  */
 } walt_pair;
 
+/* Everything the output stage needs for one pair, without the ranked lists: the pairing result,
+ * the two candidates of the winning pair (zero unless best_times >= 1) and each mate's own
+ * single-end resolution (GetBestMatch4Single, paired.cpp:296-318; what MergePairedEndResults
+ * reports for pairs that are not uniquely paired). */
+typedef struct {
+  walt_pair pair;
+  walt_cand c1, c2;
+  walt_best single1, single2;
+} walt_pe_result;
+
 /* Work counters of the last mapping call (device-side, for the roofline model). */
 typedef struct {
   uint64_t n_lookups;      /* table lookups with a non-empty 12-mer bucket               */
@@ -132,6 +142,18 @@ int walt_engine_map_pe(walt_engine* e, const char* seqs1, const uint64_t* offs1,
                        uint32_t* n_ranked1, walt_cand* ranked2, uint32_t* n_ranked2,
                        walt_pair* pairs, uint32_t* n_short1, uint32_t* n_short2);
 
+/* The same mapping with the per-pair summary only (72 bytes per pair cross PCIe instead of
+ * 2 * top_k * 12): pairing loop and GetBestMatch4Single run on the device. */
+int walt_engine_map_pe_compact(walt_engine* e, const char* seqs1, const uint64_t* offs1, const char* seqs2,
+                               const uint64_t* offs2, uint32_t n, uint32_t max_mismatches, uint32_t b,
+                               uint32_t top_k, int frag_range, int pbat, walt_pe_result* out,
+                               uint32_t* n_short1, uint32_t* n_short2);
+/* ... and with every buffer already resident in device memory (kernel-only timing). */
+int walt_engine_map_pe_device(walt_engine* e, const void* d_seqs1, const void* d_offs1, const void* d_seqs2,
+                              const void* d_offs2, uint32_t n, uint32_t max_read_len, uint32_t max_mismatches,
+                              uint32_t b, uint32_t top_k, int frag_range, int pbat, void* d_out /* walt_pe_result[n] */,
+                              void* cuda_stream);
+
 int walt_engine_last_stats(const walt_engine* e, walt_stats* out);
 
 /* Test hook: 0 = table-driven search (default), 1 = literal IndexRegion emulation for every
@@ -170,6 +192,10 @@ int walt_engine_export_subindex(walt_engine* e, int which, char* sequence, uint3
 int walt_synth_genome_device(int device, uint64_t n_bases, uint64_t seed, void* d_packed_out);
 int walt_synth_reads_device(walt_engine* e, const void* d_packed_genome, uint32_t n_reads, uint32_t read_len,
                             uint64_t seed, int a_rich, void* d_seqs_out /* n_reads*read_len ASCII */);
+/* Directional paired-end library: fragments N(300,50) clipped to [read_len, 1000]; mate 1 is the
+ * T-rich 5' end, mate 2 the reverse complement of the 3' end (A-rich). */
+int walt_synth_pairs_device(walt_engine* e, const void* d_packed_genome, uint32_t n_pairs, uint32_t read_len,
+                            uint64_t seed, void* d_seqs1_out, void* d_seqs2_out);
 
 #ifdef __cplusplus
 }

@@ -70,6 +70,9 @@ walt_pe_writer* walt_pe_writer_open(const char* output_path, const walt_chroms* 
 int walt_pe_writer_write(walt_pe_writer* w, const walt_batch* b1, const walt_batch* b2, const walt_cand* ranked1,
                          const uint32_t* n_ranked1, const walt_cand* ranked2, const uint32_t* n_ranked2,
                          const walt_pair* pairs, uint32_t n);
+/* Same output from the engine's compact per-pair summary (walt_engine_map_pe_compact). */
+int walt_pe_writer_write_compact(walt_pe_writer* w, const walt_batch* b1, const walt_batch* b2,
+                                 const walt_pe_result* results, uint32_t n);
 void walt_pe_writer_add_short(walt_pe_writer* w, uint32_t n_short1, uint32_t n_short2);
 int walt_pe_writer_close(walt_pe_writer* w);
 

@@ -192,6 +192,27 @@ uint32_t waltref_map_pe(void* h, void* hp, const char* seqs, const uint64_t* off
   return stat.num_of_short_reads;
 }
 
+/* Same pass, returning the wall time of the OpenMP loop alone (see waltref_time_se). */
+double waltref_time_pe(void* h, void* hp, const char* seqs, const uint64_t* offs, uint32_t n,
+                       char strand, int ag_wildcard, uint32_t max_mismatches, uint32_t b,
+                       int num_threads) {
+  RefIndex* r = static_cast<RefIndex*>(h);
+  std::vector<TopCandidates>& heaps = *static_cast<std::vector<TopCandidates>*>(hp);
+  std::vector<std::string> read_seqs(n);
+  for (uint32_t j = 0; j < n; ++j)
+    read_seqs[j].assign(seqs + offs[j], seqs + offs[j + 1]);
+  StatSingleReads stat(false, false, "", true);
+  const bool AG = ag_wildcard != 0;
+  omp_set_dynamic(0);
+  omp_set_num_threads(num_threads);
+  const double t0 = omp_get_wtime();
+#pragma omp parallel for
+  for (uint32_t j = 0; j < n; ++j)
+    PairEndMapping(read_seqs[j], r->genome, r->hash_table, strand, AG, max_mismatches, b,
+                   heaps[j], stat);
+  return omp_get_wtime() - t0;
+}
+
 /* Drain every heap like paired.cpp:684-692: out[j*top_k + 0] is the worst, the last one the
  * best; n_out[j] = number of entries. */
 void waltref_heaps_drain(void* hp, uint32_t n, uint32_t top_k, waltref_cand* out,

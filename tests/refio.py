@@ -245,6 +245,8 @@ def ref_lib():
         L.waltref_map_se.restype = C.c_uint32
         L.waltref_map_pe.restype = C.c_uint32
         L.waltref_time_se.restype = C.c_double
+        if hasattr(L, "waltref_time_pe"):
+            L.waltref_time_pe.restype = C.c_double
         L.waltref_heaps_alloc.restype = C.c_void_p
         _ref = L
     return _ref

@@ -221,3 +221,59 @@ def test_device_makedb_erases_large_buckets():
         assert np.array_equal(counter, subs[sfx].counter)
         assert np.array_equal(index, subs[sfx].index)
     e.close()
+
+
+def _single_best(ranked, n, m):
+    """GetBestMatch4Single, paired.cpp:296-318 (python restatement for the test)."""
+    pos, times, mm, strand = 0, 0, m, b"+"
+    for i in range(int(n) - 1, -1, -1):
+        c = ranked[i]
+        if c["mismatch"] < mm:
+            pos, times, mm, strand = int(c["genome_pos"]), 1, int(c["mismatch"]), c["strand"]
+        elif c["mismatch"] == mm:
+            if pos == int(c["genome_pos"]):
+                continue
+            pos, strand, times = int(c["genome_pos"]), c["strand"], times + 1
+        else:
+            break
+    return pos, times, mm, strand
+
+
+@pytest.mark.parametrize("pbat", [False, True])
+def test_pe_compact_and_device_paths_match_ranked(engine, pbat):
+    """walt_engine_map_pe_compact / _device return, per pair, exactly what the output stage derives
+    from the ranked lists of walt_engine_map_pe (pairing result, the winning candidates, each
+    mate's GetBestMatch4Single)."""
+    import torch
+    from walt_b200.engine import PE_RESULT_DT
+    z = goldenio.load("pe.npz")
+    b1, o1 = refio.pack_reads(z["m1"])
+    b2, o2 = refio.pack_reads(z["m2"])
+    for m, k, L in ((6, 50, 1000), (8, 3, 250)):
+        full = engine.map_pe(b1, o1, b2, o2, m=m, top_k=k, frag_range=L, pbat=pbat)
+        comp, s1, s2 = engine.map_pe_compact(b1, o1, b2, o2, m=m, top_k=k, frag_range=L, pbat=pbat)
+        assert (s1, s2) == (full["short1"], full["short2"])
+        assert np.array_equal(comp["pair"], full["pairs"])
+        for j in range(len(comp)):
+            pr = full["pairs"][j]
+            if pr["best_times"] >= 1:
+                assert comp["c1"][j] == full["ranked1"][j][pr["best_i"]], j
+                assert comp["c2"][j] == full["ranked2"][j][pr["best_j"]], j
+            else:
+                assert comp["c1"][j]["genome_pos"] == 0 and comp["c2"][j]["genome_pos"] == 0
+            for mate in (1, 2):
+                pos, times, mm, strand = _single_best(full[f"ranked{mate}"][j], full[f"n{mate}"][j], m)
+                got = comp[f"single{mate}"][j]
+                assert (int(got["genome_pos"]), int(got["times"]), int(got["mismatch"]), got["strand"]) == \
+                       (pos, times, mm, strand), (j, mate)
+        # device-resident path
+        dev = "cuda:0"
+        d1 = torch.from_numpy(b1).to(dev); d2 = torch.from_numpy(b2).to(dev)
+        do1 = torch.from_numpy(o1.astype(np.int64)).to(dev); do2 = torch.from_numpy(o2.astype(np.int64)).to(dev)
+        n = len(o1) - 1
+        d_out = torch.zeros(n * PE_RESULT_DT.itemsize, dtype=torch.uint8, device=dev)
+        engine.map_pe_device(d1.data_ptr(), do1.data_ptr(), d2.data_ptr(), do2.data_ptr(), n, 100, d_out.data_ptr(),
+                             m=m, top_k=k, frag_range=L, pbat=pbat, stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy().view(PE_RESULT_DT)
+        assert np.array_equal(got, comp)

@@ -192,6 +192,60 @@ __global__ void synth_reads_kernel(const uint64_t* __restrict__ fwd, ChromView c
   }
 }
 
+// Directional paired-end library: a fragment of length ~N(300,50) clipped
+// to [rl, 1000] is taken from either genome strand and bisulfite-converted (95 % of C -> T); mate 1
+// is its first rl bases, mate 2 the reverse complement of its last rl bases; each mate then gets
+// k substitutions, k uniform over {0,0,0,1,2,3,5,7}; 1 % of the pairs are random sequence.
+__global__ void synth_pairs_kernel(const uint64_t* __restrict__ fwd, ChromView cv, uint32_t n_pairs, uint32_t rl,
+                                   uint64_t seed, char* __restrict__ out1, char* __restrict__ out2) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_pairs) return;
+  uint64_t s = mix64(seed ^ (0x9E3779B97F4A7C15ull * (r + 1ull)));
+  auto next = [&]() { s = mix64(s); return s; };
+  char* d1 = out1 + (size_t)r * rl;
+  char* d2 = out2 + (size_t)r * rl;
+  if (next() % 100u == 0u) {
+    for (uint32_t i = 0; i < rl; ++i) { d1[i] = "ACGT"[next() & 3u]; d2[i] = "ACGT"[next() & 3u]; }
+    return;
+  }
+  // fragment length: sum of 12 uniforms ~ N(6, 1)
+  uint32_t acc = 0;
+  for (int i = 0; i < 12; ++i) acc += (uint32_t)(next() & 0xFFFFu);
+  const float z = (float)acc / 65536.0f - 6.0f;
+  int32_t fl = (int32_t)(300.0f + 50.0f * z);
+  fl = fl < (int32_t)rl ? (int32_t)rl : (fl > 1000 ? 1000 : fl);
+  uint32_t p;
+  for (;;) {
+    p = (uint32_t)(next() % cv.genome_len);
+    const uint32_t chr = chrom_of(cv.starts, cv.n_chr, p);
+    if ((uint64_t)p + (uint32_t)fl + 1u < cv.starts[chr + 1u]) break;
+  }
+  const bool minus = (next() & 1u) != 0u;
+  // base i of the fragment (5' -> 3' on its own strand), converted
+  auto frag_base = [&](uint32_t i) -> uint32_t {
+    uint32_t code = minus ? 3u - packed_base(fwd, (uint64_t)p + ((uint32_t)fl - 1u - i) + PAD_BASES)
+                          : packed_base(fwd, (uint64_t)p + i + PAD_BASES);
+    // conversion decided by a hash of (pair, fragment position) so that overlapping mates agree
+    if (code == 1u && (mix64(s ^ (0xA24BAED4963EE407ull * (i + 1ull))) % 100u) < 95u) code = 3u;
+    return code;
+  };
+  const uint32_t ks[8] = {0, 0, 0, 1, 2, 3, 5, 7};
+  uint8_t buf[MAX_READ_LEN];
+  for (int mate = 0; mate < 2; ++mate) {
+    for (uint32_t i = 0; i < rl; ++i)
+      buf[i] = (uint8_t)(mate == 0 ? frag_base(i) : 3u - frag_base((uint32_t)fl - 1u - i));
+    uint64_t t = mix64(s ^ (mate ? 0x1234567ull : 0x7654321ull));
+    auto tn = [&]() { t = mix64(t); return t; };
+    const uint32_t k = ks[tn() & 7u];
+    for (uint32_t q = 0; q < k; ++q) {
+      const uint32_t at = (uint32_t)(tn() % rl);
+      buf[at] = (uint8_t)((buf[at] + 1u + (uint32_t)(tn() % 3u)) & 3u);
+    }
+    char* d = mate ? d2 : d1;
+    for (uint32_t i = 0; i < rl; ++i) d[i] = "ACGT"[buf[i]];
+  }
+}
+
 static uint32_t blocks_for(uint64_t n, uint32_t t) { return (uint32_t)((n + t - 1) / t); }
 
 // Build sub-index `which` of `e` from the forward packed genome (device).
@@ -401,6 +455,21 @@ int walt_synth_reads_device(walt_engine* e, const void* d_packed_genome, uint32_
   if (n_reads)
     synth_reads_kernel<<<blocks_for(n_reads, 64), 64>>>((const uint64_t*)d_packed_genome, chrom_view(e), n_reads,
                                                         read_len, seed, a_rich ? 1u : 0u, (char*)d_seqs_out);
+  WALT_CUDA_TRY(cudaGetLastError());
+  WALT_CUDA_TRY(cudaDeviceSynchronize());
+  return WALT_OK;
+}
+
+int walt_synth_pairs_device(walt_engine* e, const void* d_packed_genome, uint32_t n_pairs, uint32_t read_len,
+                            uint64_t seed, void* d_seqs1_out, void* d_seqs2_out) {
+  if (!e || !d_packed_genome || !d_seqs1_out || !d_seqs2_out || read_len == 0 || read_len > MAX_READ_LEN)
+    return fail(WALT_EINVAL, "bad argument");
+  int rc = ensure_device(e);
+  if (rc) return rc;
+  if (!e->d_starts) return fail(WALT_EINVAL, "set the chromosome table first");
+  if (n_pairs)
+    synth_pairs_kernel<<<blocks_for(n_pairs, 64), 64>>>((const uint64_t*)d_packed_genome, chrom_view(e), n_pairs, read_len,
+                                                        seed, (char*)d_seqs1_out, (char*)d_seqs2_out);
   WALT_CUDA_TRY(cudaGetLastError());
   WALT_CUDA_TRY(cudaDeviceSynchronize());
   return WALT_OK;

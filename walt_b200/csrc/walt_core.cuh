@@ -1125,4 +1125,23 @@ WALT_HD PairResult pair_candidates(const ChromView& cv, GetCand get1, uint32_t n
   return r;
 }
 
+// GetBestMatch4Single (paired.cpp:296-318): the single-end style fold over one mate's ranked
+// list, best (last slot) to worst, stopping at the first worse candidate.
+template <class GetCand>
+WALT_HD BestState single_best(GetCand get, uint32_t n, uint32_t max_mismatches) {
+  BestState b; b.pos = 0u; b.times = 0u; b.mm = max_mismatches; b.strand = '+';
+  for (int32_t i = (int32_t)n - 1; i >= 0; --i) {
+    const RankedCand c = get((uint32_t)i);
+    if (c.mm < b.mm) {
+      b.pos = c.pos; b.times = 1u; b.strand = c.strand; b.mm = c.mm;
+    } else if (c.mm == b.mm) {
+      if (b.pos == c.pos) continue;
+      b.pos = c.pos; b.strand = c.strand; b.times++;
+    } else {
+      break;
+    }
+  }
+  return b;
+}
+
 }  // namespace waltcore

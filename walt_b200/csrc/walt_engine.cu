@@ -344,6 +344,7 @@ struct PeArgs {
   const char* seqs;
   const uint64_t* offs;
   uint64_t seq_base;
+  uint32_t uniform_len;   // see SeArgs
   uint32_t n;
   uint32_t nw_max;
   uint32_t ag;
@@ -375,10 +376,16 @@ pe_map_kernel(const __grid_constant__ PeArgs a) {
     const uint32_t r = next_read<WD>(a.queue);
     if (r - (threadIdx.x & 31u) / WD >= a.n) break;
     if (r < a.n) {
-      const uint64_t o0 = a.offs[r], o1 = a.offs[r + 1];
-      const uint32_t len = (uint32_t)(o1 - o0);
+      const char* seq;
+      uint32_t len;
+      if (a.uniform_len) {
+        len = a.uniform_len; seq = a.seqs + (size_t)r * len;
+      } else {
+        const uint64_t o0 = a.offs[r], o1 = a.offs[r + 1];
+        len = (uint32_t)(o1 - o0); seq = a.seqs + (o0 - a.seq_base);
+      }
       uint32_t hsize = 0;
-      bool ok = map_read_pe(w, a.ix, a.cv, a.p3, a.cfg, a.seqs + (o0 - a.seq_base), len, a.ag != 0u,
+      bool ok = map_read_pe(w, a.ix, a.cv, a.p3, a.cfg, seq, len, a.ag != 0u,
                             a.max_mismatches, a.top_k, sc, cached_len, heap, hsize, ctr);
       bad |= !ok;
       if (lane == 0) {
@@ -413,18 +420,50 @@ struct GetRanked {
   }
 };
 
-// pairing loop of MergePairedEndResults (paired.cpp:472-513): one thread per pair
-__global__ void pair_kernel(ChromView cv, const walt_cand* __restrict__ r1, const uint32_t* __restrict__ n1,
-                            const uint64_t* __restrict__ offs1, const walt_cand* __restrict__ r2,
-                            const uint32_t* __restrict__ n2, const uint64_t* __restrict__ offs2, uint32_t n,
-                            uint32_t top_k, uint32_t max_mismatches, int32_t frag_range, walt_pair* __restrict__ out) {
+// pairing loop of MergePairedEndResults (paired.cpp:472-513) and, for the compact result, the
+// per-mate GetBestMatch4Single (paired.cpp:296-318): one thread per pair.  `swap` hands every
+// per-mate field back to the other mate (PBAT runs the directional protocol on exchanged mates).
+struct PairArgs {
+  ChromView cv;
+  const walt_cand* r1; const uint32_t* n1; const uint64_t* offs1; uint32_t ulen1;
+  const walt_cand* r2; const uint32_t* n2; const uint64_t* offs2; uint32_t ulen2;
+  uint32_t n, top_k, max_mismatches;
+  int32_t frag_range;
+  uint32_t swap;
+  walt_pair* pairs;          // may be NULL
+  walt_pe_result* compact;   // may be NULL
+};
+
+__device__ __forceinline__ walt_best to_best(const BestState& b) {
+  walt_best o; o.genome_pos = b.pos; o.times = b.times; o.mismatch = b.mm; o.strand = (char)b.strand;
+  o.pad[0] = o.pad[1] = o.pad[2] = 0;
+  return o;
+}
+
+__global__ void pair_kernel(const __grid_constant__ PairArgs a) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  PairResult r = pair_candidates(cv, GetRanked{r1 + (size_t)p * top_k}, n1[p], (uint32_t)(offs1[p + 1] - offs1[p]),
-                                 GetRanked{r2 + (size_t)p * top_k}, n2[p], (uint32_t)(offs2[p + 1] - offs2[p]),
-                                 max_mismatches, frag_range);
-  walt_pair o; o.best_times = r.best_times; o.best_i = r.best_i; o.best_j = r.best_j; o.frag_len = r.frag;
-  out[p] = o;
+  if (p >= a.n) return;
+  const uint32_t len1 = a.ulen1 ? a.ulen1 : (uint32_t)(a.offs1[p + 1] - a.offs1[p]);
+  const uint32_t len2 = a.ulen2 ? a.ulen2 : (uint32_t)(a.offs2[p + 1] - a.offs2[p]);
+  const walt_cand* c1 = a.r1 + (size_t)p * a.top_k;
+  const walt_cand* c2 = a.r2 + (size_t)p * a.top_k;
+  const uint32_t k1 = a.n1[p], k2 = a.n2[p];
+  PairResult r = pair_candidates(a.cv, GetRanked{c1}, k1, len1, GetRanked{c2}, k2, len2, a.max_mismatches, a.frag_range);
+  walt_pair o; o.best_times = r.best_times; o.frag_len = r.frag;
+  o.best_i = a.swap ? r.best_j : r.best_i; o.best_j = a.swap ? r.best_i : r.best_j;
+  if (a.pairs) a.pairs[p] = o;
+  if (a.compact) {
+    walt_pe_result out;
+    out.pair = o;
+    walt_cand z; z.genome_pos = 0; z.mismatch = 0; z.strand = 0; z.pad[0] = z.pad[1] = z.pad[2] = 0;
+    walt_cand w1 = z, w2 = z;
+    if (r.best_times >= 1u) { w1 = c1[r.best_i]; w2 = c2[r.best_j]; }
+    const walt_best s1 = to_best(single_best(GetRanked{c1}, k1, a.max_mismatches));
+    const walt_best s2 = to_best(single_best(GetRanked{c2}, k2, a.max_mismatches));
+    out.c1 = a.swap ? w2 : w1; out.c2 = a.swap ? w1 : w2;
+    out.single1 = a.swap ? s2 : s1; out.single2 = a.swap ? s1 : s2;
+    a.compact[p] = out;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -488,14 +527,14 @@ static int launch_se(walt_engine* e, const char* d_seqs, const uint64_t* d_offs,
 
 static int launch_pe_mate(walt_engine* e, const char* d_seqs, const uint64_t* d_offs, uint64_t seq_base, uint32_t n,
                           uint32_t max_read_len, int ag, uint32_t m, uint32_t b, uint32_t top_k, walt_cand* d_ranked,
-                          uint32_t* d_nranked, uint32_t* d_queue, cudaStream_t st) {
+                          uint32_t* d_nranked, uint32_t* d_queue, cudaStream_t st, uint32_t uniform_len = 0) {
   if (max_read_len > MAX_READ_LEN) return fail(WALT_EINVAL, "read longer than 1024 bases");
   PeArgs a;
   const int base = ag ? WALT_GA10 : WALT_CT00;
   a.ix[0] = e->sub[base].view(base); a.ix[1] = e->sub[base + 1].view(base + 1);
   a.cv = chrom_view(e); a.p3 = e->pow3;
   a.cfg.b = b; a.cfg.literal_all = e->search_mode == 1 ? 1u : 0u;
-  a.seqs = d_seqs; a.offs = d_offs; a.seq_base = seq_base; a.n = n;
+  a.seqs = d_seqs; a.offs = d_offs; a.seq_base = seq_base; a.n = n; a.uniform_len = uniform_len;
   a.nw_max = std::max<uint32_t>(1u, (max_read_len + 31u) / 32u);
   a.ag = ag ? 1u : 0u; a.max_mismatches = m; a.top_k = top_k; a.ranked = d_ranked; a.n_ranked = d_nranked;
   a.flags = e->d_flags; a.queue = d_queue; a.counters = e->d_counters;
@@ -884,77 +923,173 @@ int walt_engine_map_se(walt_engine* e, const char* seqs, const uint64_t* offs, u
 }
 
 // ---- paired end ---------------------------------------------------------------------------
+// device layout of one chunk's paired-end scratch inside a slot's d_pe allocation
+struct PeScratch {
+  walt_pair* pairs; walt_pe_result* compact; walt_cand* r1; walt_cand* r2; uint32_t* n1; uint32_t* n2;
+};
+static size_t pe_scratch_bytes(uint32_t cn, uint32_t top_k) {
+  return (size_t)cn * sizeof(walt_pe_result) + (size_t)cn * sizeof(walt_pair) + 2u * (size_t)cn * top_k * sizeof(walt_cand) +
+         2u * (size_t)cn * 4u + 256u;
+}
+static PeScratch carve_pe(void* base, uint32_t cn, uint32_t top_k) {
+  PeScratch p;
+  char* c = (char*)base;
+  p.compact = (walt_pe_result*)c; c += (((size_t)cn * sizeof(walt_pe_result)) + 15u) & ~(size_t)15u;
+  p.pairs = (walt_pair*)c;        c += (size_t)cn * sizeof(walt_pair);
+  p.r1 = (walt_cand*)c;           c += (size_t)cn * top_k * sizeof(walt_cand);
+  p.r2 = (walt_cand*)c;           c += (size_t)cn * top_k * sizeof(walt_cand);
+  p.n1 = (uint32_t*)c;            c += (size_t)cn * 4u;
+  p.n2 = (uint32_t*)c;
+  return p;
+}
+
+// both mate kernels + the pairing kernel for one chunk resident on the device
+static int launch_pe_chunk(walt_engine* e, const char* d_seqs1, const uint64_t* d_offs1, uint64_t sb1, uint32_t ulen1,
+                           uint32_t max1, const char* d_seqs2, const uint64_t* d_offs2, uint64_t sb2, uint32_t ulen2,
+                           uint32_t max2, uint32_t cn, uint32_t m, uint32_t b, uint32_t top_k, int frag_range, int swap,
+                           const PeScratch& ps, bool want_pairs, walt_pe_result* d_compact, uint32_t* q, cudaStream_t st) {
+  int rc;
+  // mate 1: C->T against _CT00/_CT01; mate 2: G->A against _GA10/_GA11 (paired.cpp:642-672)
+  if ((rc = launch_pe_mate(e, d_seqs1, d_offs1, sb1, cn, max1, 0, m, b, top_k, ps.r1, ps.n1, q, st, ulen1))) return rc;
+  if ((rc = launch_pe_mate(e, d_seqs2, d_offs2, sb2, cn, max2, 1, m, b, top_k, ps.r2, ps.n2, q + 1, st, ulen2))) return rc;
+  PairArgs a;
+  a.cv = chrom_view(e);
+  a.r1 = ps.r1; a.n1 = ps.n1; a.offs1 = d_offs1; a.ulen1 = ulen1;
+  a.r2 = ps.r2; a.n2 = ps.n2; a.offs2 = d_offs2; a.ulen2 = ulen2;
+  a.n = cn; a.top_k = top_k; a.max_mismatches = m; a.frag_range = frag_range; a.swap = swap ? 1u : 0u;
+  a.pairs = want_pairs ? ps.pairs : nullptr; a.compact = d_compact;
+  pair_kernel<<<(cn + 127u) / 128u, 128, 0, st>>>(a);
+  WALT_CUDA_TRY(cudaGetLastError());
+  e->stats.n_kernel_launches++;
+  return WALT_OK;
+}
+
+// Host batch, chunked and pipelined.  Either the full ranked lists (ranked1 != NULL) or the
+// compact per-pair summary (compact != NULL) travel back.  Under PBAT the caller has already
+// exchanged the mates; `swap` makes the pairing kernel hand the per-mate fields back.
+static int map_pe_host(walt_engine* e, const char* seqs1, const uint64_t* offs1, const char* seqs2, const uint64_t* offs2,
+                       uint32_t n, uint32_t m, uint32_t b, uint32_t top_k, int frag_range, int swap, walt_cand* ranked1,
+                       uint32_t* n_ranked1, walt_cand* ranked2, uint32_t* n_ranked2, walt_pair* pairs,
+                       walt_pe_result* compact, uint32_t* n_short1, uint32_t* n_short2) {
+  int rc;
+  e->stats = walt_stats{};
+  WALT_CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, 3 * 8, e->slot[0].stream));
+  WALT_CUDA_TRY(cudaStreamSynchronize(e->slot[0].stream));
+  // chunk so that the ranked lists of a slot stay below ~1 GiB
+  const uint32_t chunk = std::max<uint32_t>(1024u, std::min<uint32_t>(e->chunk_reads, (1u << 30) / (2u * top_k * 12u)));
+  uint32_t k = 0, short1 = 0, short2 = 0;
+  for (uint32_t r0 = 0; r0 < n; r0 += chunk, ++k) {
+    const uint32_t cn = std::min<uint32_t>(chunk, n - r0);
+    const ChunkScan s1 = scan_chunk(offs1, r0, cn), s2 = scan_chunk(offs2, r0, cn);
+    if (s1.max_len > MAX_READ_LEN || s2.max_len > MAX_READ_LEN) {
+      for (auto& s : e->slot) cudaStreamSynchronize(s.stream);
+      return fail(WALT_EINVAL, "read longer than 1024 bases");
+    }
+    short1 += s1.n_short; short2 += s2.n_short;
+    BatchSlot& s = e->slot[k % N_SLOTS];
+    WALT_CUDA_TRY(cudaEventSynchronize(s.done));
+    const uint64_t sb1 = offs1[r0], se1 = offs1[r0 + cn], sb2 = offs2[r0], se2 = offs2[r0 + cn];
+    if ((rc = reserve(&s.d_seqs, &s.seqs_cap, (size_t)(se1 - sb1) + 16u))) return rc;
+    if ((rc = reserve(&s.d_seqs2, &s.seqs2_cap, (size_t)(se2 - sb2) + 16u))) return rc;
+    if ((rc = reserve_bytes(&s.d_pe, &s.pe_cap, pe_scratch_bytes(cn, top_k)))) return rc;
+    const PeScratch ps = carve_pe(s.d_pe, cn, top_k);
+    if (se1 > sb1) WALT_CUDA_TRY(cudaMemcpyAsync(s.d_seqs, seqs1 + sb1, se1 - sb1, cudaMemcpyHostToDevice, s.stream));
+    if (se2 > sb2) WALT_CUDA_TRY(cudaMemcpyAsync(s.d_seqs2, seqs2 + sb2, se2 - sb2, cudaMemcpyHostToDevice, s.stream));
+    if (!s1.uniform_len) {
+      if ((rc = reserve(&s.d_offs, &s.offs_cap, (size_t)cn + 1u))) return rc;
+      WALT_CUDA_TRY(cudaMemcpyAsync(s.d_offs, offs1 + r0, ((size_t)cn + 1u) * 8u, cudaMemcpyHostToDevice, s.stream));
+    }
+    if (!s2.uniform_len) {
+      if ((rc = reserve(&s.d_offs2, &s.offs2_cap, (size_t)cn + 1u))) return rc;
+      WALT_CUDA_TRY(cudaMemcpyAsync(s.d_offs2, offs2 + r0, ((size_t)cn + 1u) * 8u, cudaMemcpyHostToDevice, s.stream));
+    }
+    uint32_t* q = e->d_flags + 4 + N_SLOTS + 2u * (k % N_SLOTS);
+    if ((rc = launch_pe_chunk(e, s.d_seqs, s.d_offs, sb1, s1.uniform_len, s1.max_len, s.d_seqs2, s.d_offs2, sb2,
+                              s2.uniform_len, s2.max_len, cn, m, b, top_k, frag_range, swap, ps, pairs != nullptr,
+                              compact ? ps.compact : nullptr, q, s.stream)))
+      return rc;
+    if (ranked1) {
+      const size_t rk = (size_t)cn * top_k * sizeof(walt_cand);
+      WALT_CUDA_TRY(cudaMemcpyAsync(ranked1 + (size_t)r0 * top_k, ps.r1, rk, cudaMemcpyDeviceToHost, s.stream));
+      WALT_CUDA_TRY(cudaMemcpyAsync(ranked2 + (size_t)r0 * top_k, ps.r2, rk, cudaMemcpyDeviceToHost, s.stream));
+      WALT_CUDA_TRY(cudaMemcpyAsync(n_ranked1 + r0, ps.n1, (size_t)cn * 4u, cudaMemcpyDeviceToHost, s.stream));
+      WALT_CUDA_TRY(cudaMemcpyAsync(n_ranked2 + r0, ps.n2, (size_t)cn * 4u, cudaMemcpyDeviceToHost, s.stream));
+    }
+    if (pairs) WALT_CUDA_TRY(cudaMemcpyAsync(pairs + r0, ps.pairs, (size_t)cn * sizeof(walt_pair), cudaMemcpyDeviceToHost, s.stream));
+    if (compact)
+      WALT_CUDA_TRY(cudaMemcpyAsync(compact + r0, ps.compact, (size_t)cn * sizeof(walt_pe_result), cudaMemcpyDeviceToHost, s.stream));
+    WALT_CUDA_TRY(cudaEventRecord(s.done, s.stream));
+  }
+  if (n_short1) *n_short1 = 2u * short1;   // once per strand pass (paired.cpp:112-115)
+  if (n_short2) *n_short2 = 2u * short2;
+  for (auto& s : e->slot) WALT_CUDA_TRY(cudaStreamSynchronize(s.stream));
+  return fetch_status(e);
+}
+
+static int check_pe_args(walt_engine* e, uint32_t top_k) {
+  if (top_k < 2 || top_k > 300) return fail(WALT_EINVAL, "-k must be in [2, 300] (walt.cpp:245-249)");
+  int rc = ensure_device(e);
+  if (rc) return rc;
+  if ((rc = check_pair(e, 0)) || (rc = check_pair(e, 1))) return rc;
+  return WALT_OK;
+}
+
 int walt_engine_map_pe(walt_engine* e, const char* seqs1, const uint64_t* offs1, const char* seqs2,
                        const uint64_t* offs2, uint32_t n, uint32_t max_mismatches, uint32_t b, uint32_t top_k,
                        int frag_range, int pbat, walt_cand* ranked1, uint32_t* n_ranked1, walt_cand* ranked2,
                        uint32_t* n_ranked2, walt_pair* pairs, uint32_t* n_short1, uint32_t* n_short2) {
   if (!e || !offs1 || !offs2 || (n && (!seqs1 || !seqs2 || !ranked1 || !ranked2 || !n_ranked1 || !n_ranked2 || !pairs)))
     return fail(WALT_EINVAL, "bad argument");
-  if (top_k < 2 || top_k > 300) return fail(WALT_EINVAL, "-k must be in [2, 300] (walt.cpp:245-249)");
-  int rc = ensure_device(e);
+  int rc = check_pe_args(e, top_k);
   if (rc) return rc;
-  if ((rc = check_pair(e, 0)) || (rc = check_pair(e, 1))) return rc;
-  if (pbat) {
-    // PBAT swaps the bisulfite roles of the mates: run the directional protocol with the mates
-    // exchanged, then hand every per-mate result back to its owner.
-    rc = walt_engine_map_pe(e, seqs2, offs2, seqs1, offs1, n, max_mismatches, b, top_k, frag_range, 0, ranked2,
-                            n_ranked2, ranked1, n_ranked1, pairs, n_short2, n_short1);
-    if (rc) return rc;
-    for (uint32_t i = 0; i < n; ++i) std::swap(pairs[i].best_i, pairs[i].best_j);
-    return WALT_OK;
-  }
-  const ChunkScan sc1 = scan_chunk(offs1, 0, n), sc2 = scan_chunk(offs2, 0, n);
-  const uint32_t max1 = sc1.max_len, max2 = sc2.max_len;
-  if (n_short1) *n_short1 = 2u * sc1.n_short;   // once per strand pass (paired.cpp:112-115)
-  if (n_short2) *n_short2 = 2u * sc2.n_short;
-  if (max1 > MAX_READ_LEN || max2 > MAX_READ_LEN) return fail(WALT_EINVAL, "read longer than 1024 bases");
-  e->stats = walt_stats{};
-  WALT_CUDA_TRY(cudaMemset(e->d_counters, 0, 3 * 8));
-  // chunk so that the ranked lists of a slot stay below ~1 GiB
-  const uint32_t chunk = std::max<uint32_t>(1024u, std::min<uint32_t>(e->chunk_reads, (1u << 30) / (2u * top_k * 12u)));
-  uint32_t k = 0;
-  for (uint32_t r0 = 0; r0 < n; r0 += chunk, ++k) {
+  // PBAT swaps the bisulfite roles of the mates: run the directional protocol with the mates
+  // exchanged and hand every per-mate result back to its owner.
+  if (pbat)
+    return map_pe_host(e, seqs2, offs2, seqs1, offs1, n, max_mismatches, b, top_k, frag_range, 1, ranked2, n_ranked2,
+                       ranked1, n_ranked1, pairs, nullptr, n_short2, n_short1);
+  return map_pe_host(e, seqs1, offs1, seqs2, offs2, n, max_mismatches, b, top_k, frag_range, 0, ranked1, n_ranked1,
+                     ranked2, n_ranked2, pairs, nullptr, n_short1, n_short2);
+}
+
+int walt_engine_map_pe_compact(walt_engine* e, const char* seqs1, const uint64_t* offs1, const char* seqs2,
+                               const uint64_t* offs2, uint32_t n, uint32_t max_mismatches, uint32_t b, uint32_t top_k,
+                               int frag_range, int pbat, walt_pe_result* out, uint32_t* n_short1, uint32_t* n_short2) {
+  if (!e || !offs1 || !offs2 || (n && (!seqs1 || !seqs2 || !out))) return fail(WALT_EINVAL, "bad argument");
+  int rc = check_pe_args(e, top_k);
+  if (rc) return rc;
+  if (pbat)
+    return map_pe_host(e, seqs2, offs2, seqs1, offs1, n, max_mismatches, b, top_k, frag_range, 1, nullptr, nullptr,
+                       nullptr, nullptr, nullptr, out, n_short2, n_short1);
+  return map_pe_host(e, seqs1, offs1, seqs2, offs2, n, max_mismatches, b, top_k, frag_range, 0, nullptr, nullptr, nullptr,
+                     nullptr, nullptr, out, n_short1, n_short2);
+}
+
+int walt_engine_map_pe_device(walt_engine* e, const void* d_seqs1, const void* d_offs1, const void* d_seqs2,
+                              const void* d_offs2, uint32_t n, uint32_t max_read_len, uint32_t max_mismatches, uint32_t b,
+                              uint32_t top_k, int frag_range, int pbat, void* d_out, void* cuda_stream) {
+  if (!e || (n && (!d_seqs1 || !d_offs1 || !d_seqs2 || !d_offs2 || !d_out))) return fail(WALT_EINVAL, "bad argument");
+  int rc = check_pe_args(e, top_k);
+  if (rc) return rc;
+  if (max_read_len > MAX_READ_LEN) return fail(WALT_EINVAL, "read longer than 1024 bases");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const char* s1 = (const char*)(pbat ? d_seqs2 : d_seqs1);
+  const char* s2 = (const char*)(pbat ? d_seqs1 : d_seqs2);
+  const uint64_t* o1 = (const uint64_t*)(pbat ? d_offs2 : d_offs1);
+  const uint64_t* o2 = (const uint64_t*)(pbat ? d_offs1 : d_offs2);
+  // ranked lists live in engine scratch, one chunk at a time (stream-ordered reuse)
+  const uint32_t chunk = std::max<uint32_t>(1024u, (uint32_t)std::min<uint64_t>(n, (1ull << 30) / (2ull * top_k * 12ull)));
+  BatchSlot& s = e->slot[0];
+  WALT_CUDA_TRY(cudaStreamSynchronize(s.stream));
+  if ((rc = reserve_bytes(&s.d_pe, &s.pe_cap, pe_scratch_bytes(chunk, top_k)))) return rc;
+  for (uint32_t r0 = 0; r0 < n; r0 += chunk) {
     const uint32_t cn = std::min<uint32_t>(chunk, n - r0);
-    BatchSlot& s = e->slot[k % N_SLOTS];
-    WALT_CUDA_TRY(cudaEventSynchronize(s.done));
-    const uint64_t sb1 = offs1[r0], se1 = offs1[r0 + cn], sb2 = offs2[r0], se2 = offs2[r0 + cn];
-    if ((rc = reserve(&s.d_seqs, &s.seqs_cap, (size_t)(se1 - sb1) + 16u))) return rc;
-    if ((rc = reserve(&s.d_offs, &s.offs_cap, (size_t)cn + 1u))) return rc;
-    if ((rc = reserve(&s.d_seqs2, &s.seqs2_cap, (size_t)(se2 - sb2) + 16u))) return rc;
-    if ((rc = reserve(&s.d_offs2, &s.offs2_cap, (size_t)cn + 1u))) return rc;
-    const size_t rk = (size_t)cn * top_k * sizeof(walt_cand);
-    const size_t pe_bytes = 2u * rk + 2u * (size_t)cn * 4u + (size_t)cn * sizeof(walt_pair) + 64u;
-    if ((rc = reserve_bytes(&s.d_pe, &s.pe_cap, pe_bytes))) return rc;
-    char* base = (char*)s.d_pe;
-    walt_pair* d_pairs = (walt_pair*)base;
-    walt_cand* d_r1 = (walt_cand*)(base + (((size_t)cn * sizeof(walt_pair) + 15u) & ~(size_t)15u));
-    walt_cand* d_r2 = d_r1 + (size_t)cn * top_k;
-    uint32_t* d_n1 = (uint32_t*)(d_r2 + (size_t)cn * top_k);
-    uint32_t* d_n2 = d_n1 + cn;
-    if (se1 > sb1) WALT_CUDA_TRY(cudaMemcpyAsync(s.d_seqs, seqs1 + sb1, se1 - sb1, cudaMemcpyHostToDevice, s.stream));
-    if (se2 > sb2) WALT_CUDA_TRY(cudaMemcpyAsync(s.d_seqs2, seqs2 + sb2, se2 - sb2, cudaMemcpyHostToDevice, s.stream));
-    WALT_CUDA_TRY(cudaMemcpyAsync(s.d_offs, offs1 + r0, ((size_t)cn + 1u) * 8u, cudaMemcpyHostToDevice, s.stream));
-    WALT_CUDA_TRY(cudaMemcpyAsync(s.d_offs2, offs2 + r0, ((size_t)cn + 1u) * 8u, cudaMemcpyHostToDevice, s.stream));
-    uint32_t* q = e->d_flags + 4 + N_SLOTS + 2u * (k % N_SLOTS);
-    // mate 1: C->T against _CT00/_CT01; mate 2: G->A against _GA10/_GA11 (paired.cpp:642-672)
-    if ((rc = launch_pe_mate(e, s.d_seqs, s.d_offs, sb1, cn, max1, 0, max_mismatches, b, top_k, d_r1, d_n1, q, s.stream)))
+    const PeScratch ps = carve_pe(s.d_pe, cn, top_k);
+    // absolute offsets: read r of the chunk is global read r0 + r, addressed from the buffer start
+    if ((rc = launch_pe_chunk(e, s1, o1 + r0, 0, 0, max_read_len, s2, o2 + r0, 0, 0, max_read_len, cn, max_mismatches, b,
+                              top_k, frag_range, pbat, ps, false, (walt_pe_result*)d_out + r0, e->d_flags + 4 + N_SLOTS, st)))
       return rc;
-    if ((rc = launch_pe_mate(e, s.d_seqs2, s.d_offs2, sb2, cn, max2, 1, max_mismatches, b, top_k, d_r2, d_n2, q + 1,
-                             s.stream)))
-      return rc;
-    pair_kernel<<<(cn + 127u) / 128u, 128, 0, s.stream>>>(chrom_view(e), d_r1, d_n1, s.d_offs, d_r2, d_n2, s.d_offs2, cn,
-                                                         top_k, max_mismatches, frag_range, d_pairs);
-    WALT_CUDA_TRY(cudaGetLastError());
-    e->stats.n_kernel_launches++;
-    WALT_CUDA_TRY(cudaMemcpyAsync(ranked1 + (size_t)r0 * top_k, d_r1, rk, cudaMemcpyDeviceToHost, s.stream));
-    WALT_CUDA_TRY(cudaMemcpyAsync(ranked2 + (size_t)r0 * top_k, d_r2, rk, cudaMemcpyDeviceToHost, s.stream));
-    WALT_CUDA_TRY(cudaMemcpyAsync(n_ranked1 + r0, d_n1, (size_t)cn * 4u, cudaMemcpyDeviceToHost, s.stream));
-    WALT_CUDA_TRY(cudaMemcpyAsync(n_ranked2 + r0, d_n2, (size_t)cn * 4u, cudaMemcpyDeviceToHost, s.stream));
-    WALT_CUDA_TRY(cudaMemcpyAsync(pairs + r0, d_pairs, (size_t)cn * sizeof(walt_pair), cudaMemcpyDeviceToHost, s.stream));
-    WALT_CUDA_TRY(cudaEventRecord(s.done, s.stream));
   }
-  for (auto& s : e->slot) WALT_CUDA_TRY(cudaStreamSynchronize(s.stream));
-  return fetch_status(e);
+  return WALT_OK;
 }
 
 // ---- pinned host memory ------------------------------------------------------------------------

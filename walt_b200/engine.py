@@ -21,6 +21,8 @@ CAND_DT = np.dtype([("genome_pos", np.uint32), ("mismatch", np.uint32), ("strand
                     ("pad", "S3")])
 PAIR_DT = np.dtype([("best_times", np.uint32), ("best_i", np.int32), ("best_j", np.int32),
                     ("frag_len", np.int32)])
+PE_RESULT_DT = np.dtype([("pair", PAIR_DT), ("c1", CAND_DT), ("c2", CAND_DT), ("single1", BEST_DT),
+                         ("single2", BEST_DT)])
 STATS_FIELDS = ("n_lookups", "n_candidates", "n_literal", "n_kernel_launches")
 
 _ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -178,6 +180,11 @@ class Engine:
                                                    C.c_uint32(read_len), C.c_uint64(seed), C.c_int(int(a_rich)),
                                                    C.c_void_p(d_out)))
 
+    def synth_pairs_device(self, d_packed, n_pairs, read_len, seed, d_out1, d_out2):
+        self._check(self.L.walt_synth_pairs_device(self.h, C.c_void_p(d_packed), C.c_uint32(n_pairs),
+                                                   C.c_uint32(read_len), C.c_uint64(seed), C.c_void_p(d_out1),
+                                                   C.c_void_p(d_out2)))
+
     def subindex_info(self, which):
         a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
         self._check(self.L.walt_engine_subindex_info(self.h, C.c_int(which), C.byref(a), C.byref(b), C.byref(c)))
@@ -243,3 +250,30 @@ class Engine:
                                               _p(n2), _p(pairs), C.byref(s1), C.byref(s2)))
         return {"ranked1": r1, "n1": n1, "ranked2": r2, "n2": n2, "pairs": pairs, "short1": s1.value,
                 "short2": s2.value}
+
+    def map_pe_compact(self, buf1, offs1, buf2, offs2, m=6, b=5000, top_k=50, frag_range=1000, pbat=False, out=None):
+        """Same mapping, per-pair summary only (pairing + GetBestMatch4Single on the device)
+        -> (walt_pe_result[n], short1, short2)."""
+        buf1 = np.ascontiguousarray(buf1, dtype=np.uint8)
+        buf2 = np.ascontiguousarray(buf2, dtype=np.uint8)
+        offs1 = np.ascontiguousarray(offs1, dtype=np.uint64)
+        offs2 = np.ascontiguousarray(offs2, dtype=np.uint64)
+        n = offs1.size - 1
+        assert offs2.size - 1 == n
+        if out is None:
+            out = np.zeros(n, dtype=PE_RESULT_DT)
+        s1, s2 = C.c_uint32(), C.c_uint32()
+        self._check(self.L.walt_engine_map_pe_compact(self.h, _p(buf1), _p(offs1), _p(buf2), _p(offs2), C.c_uint32(n),
+                                                      C.c_uint32(m), C.c_uint32(b), C.c_uint32(top_k),
+                                                      C.c_int(frag_range), C.c_int(int(pbat)), _p(out),
+                                                      C.byref(s1), C.byref(s2)))
+        return out, s1.value, s2.value
+
+    def map_pe_device(self, d_seqs1, d_offs1, d_seqs2, d_offs2, n, max_read_len, d_out, m=6, b=5000, top_k=50,
+                      frag_range=1000, pbat=False, stream=0):
+        """Kernel-only paired-end path: device addresses in, walt_pe_result[n] on the device out."""
+        self._check(self.L.walt_engine_map_pe_device(self.h, C.c_void_p(d_seqs1), C.c_void_p(d_offs1),
+                                                     C.c_void_p(d_seqs2), C.c_void_p(d_offs2), C.c_uint32(n),
+                                                     C.c_uint32(max_read_len), C.c_uint32(m), C.c_uint32(b),
+                                                     C.c_uint32(top_k), C.c_int(frag_range), C.c_int(int(pbat)),
+                                                     C.c_void_p(d_out), C.c_void_p(stream)))

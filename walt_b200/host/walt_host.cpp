@@ -529,79 +529,96 @@ walt_pe_writer* walt_pe_writer_open(const char* output_path, const walt_chroms* 
 
 void walt_pe_writer_add_short(walt_pe_writer* w, uint32_t s1, uint32_t s2) { w->so1.st.n_short += s1; w->so2.st.n_short += s2; }
 
-int walt_pe_writer_write(walt_pe_writer* w, const walt_batch* b1, const walt_batch* b2, const walt_cand* ranked1,
-                         const uint32_t* n_ranked1, const walt_cand* ranked2, const uint32_t* n_ranked2,
-                         const walt_pair* pairs, uint32_t n) {
-  if (!w || !b1 || !b2 || n > b1->n || n > b2->n) return fail("bad argument");
+// One pair through MergePairedEndResults' output half (paired.cpp:515-569).  `r` holds the
+// per-file-mate fields (c1/single1 belong to the first file's read).
+static void write_pair(walt_pe_writer* w, const walt_batch* b1, const walt_batch* b2, uint32_t j, const walt_pe_result& r) {
   const walt_chroms& g = *w->g;
   // Under PBAT the mate that plays the reference's "mate 1" role (C->T, pairing-loop outer
   // index) is the second file's read; names and first/last flags stay with the files.
   const walt_batch* ba = w->pbat ? b2 : b1;   // role A: C->T mate
   const walt_batch* bb = w->pbat ? b1 : b2;   // role B: G->A mate
-  const walt_cand* ra = w->pbat ? ranked2 : ranked1;
-  const walt_cand* rb = w->pbat ? ranked1 : ranked2;
-  const uint32_t* na = w->pbat ? n_ranked2 : n_ranked1;
-  const uint32_t* nb = w->pbat ? n_ranked1 : n_ranked2;
+  const walt_cand& pa = w->pbat ? r.c2 : r.c1;
+  const walt_cand& pb = w->pbat ? r.c1 : r.c2;
+  const char* name = b1->name(j);            // QNAME of both lines = first file's read name
+  const uint32_t name_len = b1->name_len(j);
+  const uint32_t la = ba->seq_len(j), lb = bb->seq_len(j);
+  walt_best ma, mb;
+  ma.genome_pos = 0; ma.times = 0; ma.mismatch = w->m; ma.strand = '+';
+  mb = ma;
+  bool paired = false;
+  int len = 0;
+  if (r.pair.best_times == 1) {
+    w->unique_pairs++;
+    len = best_pair_out(w->out, g, pa, pb, w->frag_range, name, name_len, ba->seq(j), ba->qual(j), la,
+                        bb->seq(j), bb->qual(j), lb, w->sam);
+    if (len >= 0 && (size_t)len < w->frag_count.size()) w->frag_count[len]++;
+    if (w->sam) {
+      paired = true;
+      ma.genome_pos = pa.genome_pos; ma.times = 1; ma.strand = pa.strand; ma.mismatch = pa.mismatch;
+      mb.genome_pos = pb.genome_pos; mb.times = 1; mb.strand = pb.strand; mb.mismatch = pb.mismatch;
+    }
+  } else {
+    if (r.pair.best_times >= 2) w->ambiguous_pairs++; else w->unmapped_pairs++;
+    ma = w->pbat ? r.single2 : r.single1;
+    mb = w->pbat ? r.single1 : r.single2;
+    SingleOut& soa = w->pbat ? w->so2 : w->so1;
+    SingleOut& sob = w->pbat ? w->so1 : w->so2;
+    soa.st.update(ma.times);
+    sob.st.update(mb.times);
+    if (!w->sam) {
+      mr_single(w->out, soa, g, ma, name, name_len, ba->seq(j), ba->qual(j), la, ba->qual_len(j), false);
+      mr_single(w->out, sob, g, mb, name, name_len, bb->seq(j), bb->qual(j), lb, bb->qual_len(j), true);
+    }
+  }
+  if (w->sam) {
+    const uint32_t chra = g.chrom_of(ma.genome_pos), chrb = g.chrom_of(mb.genome_pos);
+    uint32_t sa, ea, sb, eb;
+    forward_pos(g, ma.genome_pos, ma.strand, chra, la, sa, ea);
+    forward_pos(g, mb.genome_pos, mb.strand, chrb, lb, sb, eb);
+    uint32_t mma = ma.mismatch, mmb = mb.mismatch;
+    if (ma.times == 0) { sa = 0; mma = 0; } else sa += 1;
+    if (mb.times == 0) { sb = 0; mmb = 0; } else sb += 1;
+    const int tla = ma.strand == '+' ? len : -len, tlb = mb.strand == '+' ? len : -len;
+    std::string rna = "=", rnb = "=";
+    if (!paired) {
+      rna = ma.times == 0 ? "*" : g.names[chra];
+      rnb = mb.times == 0 ? "*" : g.names[chrb];
+    }
+    const bool a_first = !w->pbat;
+    const int fa = sam_flag(paired, ma.times == 0, mb.times == 0, ma.strand == '-', mb.strand == '-', a_first, ma.times >= 2);
+    const int fb = sam_flag(paired, mb.times == 0, ma.times == 0, mb.strand == '-', ma.strand == '-', !a_first, mb.times >= 2);
+    const SingleOut& soa = w->pbat ? w->so2 : w->so1;
+    const SingleOut& sob = w->pbat ? w->so1 : w->so2;
+    auto line_a = [&]() { sam_mate_line(w->out, soa, g, ma, chra, name, name_len, fa, sa, rnb, sb, tla, ba->seq(j), ba->qual(j), la, ba->qual_len(j), mma); };
+    auto line_b = [&]() { sam_mate_line(w->out, sob, g, mb, chrb, name, name_len, fb, sb, rna, sa, tlb, bb->seq(j), bb->qual(j), lb, bb->qual_len(j), mmb); };
+    if (a_first) { line_a(); line_b(); } else { line_b(); line_a(); }
+  }
+}
+
+int walt_pe_writer_write_compact(walt_pe_writer* w, const walt_batch* b1, const walt_batch* b2, const walt_pe_result* res,
+                                 uint32_t n) {
+  if (!w || !b1 || !b2 || !res || n > b1->n || n > b2->n) return fail("bad argument");
+  w->total_pairs += n;
+  for (uint32_t j = 0; j < n; ++j) write_pair(w, b1, b2, j, res[j]);
+  return 0;
+}
+
+int walt_pe_writer_write(walt_pe_writer* w, const walt_batch* b1, const walt_batch* b2, const walt_cand* ranked1,
+                         const uint32_t* n_ranked1, const walt_cand* ranked2, const uint32_t* n_ranked2,
+                         const walt_pair* pairs, uint32_t n) {
+  if (!w || !b1 || !b2 || n > b1->n || n > b2->n) return fail("bad argument");
   w->total_pairs += n;
   for (uint32_t j = 0; j < n; ++j) {
-    const char* name = b1->name(j);            // QNAME of both lines = first file's read name
-    const uint32_t name_len = b1->name_len(j);
-    const walt_cand* ca = ra + (size_t)j * w->top_k;
-    const walt_cand* cb = rb + (size_t)j * w->top_k;
-    const int bi = w->pbat ? pairs[j].best_j : pairs[j].best_i;
-    const int bj = w->pbat ? pairs[j].best_i : pairs[j].best_j;
-    const uint32_t la = ba->seq_len(j), lb = bb->seq_len(j);
-    walt_best ma, mb;
-    ma.genome_pos = 0; ma.times = 0; ma.mismatch = w->m; ma.strand = '+';
-    mb = ma;
-    bool paired = false;
-    int len = 0;
-    if (pairs[j].best_times == 1) {
-      w->unique_pairs++;
-      len = best_pair_out(w->out, g, ca[bi], cb[bj], w->frag_range, name, name_len, ba->seq(j), ba->qual(j), la,
-                          bb->seq(j), bb->qual(j), lb, w->sam);
-      if (len >= 0 && (size_t)len < w->frag_count.size()) w->frag_count[len]++;
-      if (w->sam) {
-        paired = true;
-        ma.genome_pos = ca[bi].genome_pos; ma.times = 1; ma.strand = ca[bi].strand; ma.mismatch = ca[bi].mismatch;
-        mb.genome_pos = cb[bj].genome_pos; mb.times = 1; mb.strand = cb[bj].strand; mb.mismatch = cb[bj].mismatch;
-      }
-    } else {
-      if (pairs[j].best_times >= 2) w->ambiguous_pairs++; else w->unmapped_pairs++;
-      ma = best_for_single(ca, na[j], w->m);
-      mb = best_for_single(cb, nb[j], w->m);
-      SingleOut& soa = w->pbat ? w->so2 : w->so1;
-      SingleOut& sob = w->pbat ? w->so1 : w->so2;
-      soa.st.update(ma.times);
-      sob.st.update(mb.times);
-      if (!w->sam) {
-        mr_single(w->out, soa, g, ma, name, name_len, ba->seq(j), ba->qual(j), la, ba->qual_len(j), false);
-        mr_single(w->out, sob, g, mb, name, name_len, bb->seq(j), bb->qual(j), lb, bb->qual_len(j), true);
-      }
-    }
-    if (w->sam) {
-      const uint32_t chra = g.chrom_of(ma.genome_pos), chrb = g.chrom_of(mb.genome_pos);
-      uint32_t sa, ea, sb, eb;
-      forward_pos(g, ma.genome_pos, ma.strand, chra, la, sa, ea);
-      forward_pos(g, mb.genome_pos, mb.strand, chrb, lb, sb, eb);
-      uint32_t mma = ma.mismatch, mmb = mb.mismatch;
-      if (ma.times == 0) { sa = 0; mma = 0; } else sa += 1;
-      if (mb.times == 0) { sb = 0; mmb = 0; } else sb += 1;
-      const int tla = ma.strand == '+' ? len : -len, tlb = mb.strand == '+' ? len : -len;
-      std::string rna = "=", rnb = "=";
-      if (!paired) {
-        rna = ma.times == 0 ? "*" : g.names[chra];
-        rnb = mb.times == 0 ? "*" : g.names[chrb];
-      }
-      const bool a_first = !w->pbat;
-      const int fa = sam_flag(paired, ma.times == 0, mb.times == 0, ma.strand == '-', mb.strand == '-', a_first, ma.times >= 2);
-      const int fb = sam_flag(paired, mb.times == 0, ma.times == 0, mb.strand == '-', ma.strand == '-', !a_first, mb.times >= 2);
-      const SingleOut& soa = w->pbat ? w->so2 : w->so1;
-      const SingleOut& sob = w->pbat ? w->so1 : w->so2;
-      auto line_a = [&]() { sam_mate_line(w->out, soa, g, ma, chra, name, name_len, fa, sa, rnb, sb, tla, ba->seq(j), ba->qual(j), la, ba->qual_len(j), mma); };
-      auto line_b = [&]() { sam_mate_line(w->out, sob, g, mb, chrb, name, name_len, fb, sb, rna, sa, tlb, bb->seq(j), bb->qual(j), lb, bb->qual_len(j), mmb); };
-      if (a_first) { line_a(); line_b(); } else { line_b(); line_a(); }
-    }
+    // the summary the device computes in the compact path, derived here from the ranked lists
+    const walt_cand* c1 = ranked1 + (size_t)j * w->top_k;
+    const walt_cand* c2 = ranked2 + (size_t)j * w->top_k;
+    walt_pe_result r;
+    memset(&r, 0, sizeof(r));
+    r.pair = pairs[j];
+    if (pairs[j].best_times >= 1) { r.c1 = c1[pairs[j].best_i]; r.c2 = c2[pairs[j].best_j]; }
+    r.single1 = best_for_single(c1, n_ranked1[j], w->m);
+    r.single2 = best_for_single(c2, n_ranked2[j], w->m);
+    write_pair(w, b1, b2, j, r);
   }
   return 0;
 }

@@ -199,9 +199,7 @@ void process_paired_end(Engines& eng, const walt_chroms* chroms, const Settings&
   fprintf(stderr, "[OUTPUT MAPPING RESULTS TO %s]\n", output.c_str());
   walt_batch* b1 = walt_batch_create();
   walt_batch* b2 = walt_batch_create();
-  std::vector<walt_cand> r1, r2;
-  std::vector<uint32_t> n1, n2;
-  std::vector<walt_pair> pairs;
+  std::vector<walt_pe_result> res;
   bool unequal = false;
   try {
     for (;;) {
@@ -217,8 +215,7 @@ void process_paired_end(Engines& eng, const walt_chroms* chroms, const Settings&
       if (c1 != c2) { unequal = true; break; }
       if (c1 == 0) break;
       const uint32_t n = (uint32_t)c1, g = (uint32_t)eng.e.size();
-      r1.resize((size_t)n * s.top_k); r2.resize((size_t)n * s.top_k);
-      n1.resize(n); n2.resize(n); pairs.resize(n);
+      res.resize(n);
       std::vector<int> rc(g, 0);
       std::vector<uint32_t> s1(g, 0), s2(g, 0);
       std::vector<std::string> err(g);
@@ -227,10 +224,9 @@ void process_paired_end(Engines& eng, const walt_chroms* chroms, const Settings&
         th.emplace_back([&, i]() {
           const uint32_t lo = cut(n, g, i), hi = cut(n, g, i + 1);
           if (hi == lo) return;
-          rc[i] = walt_engine_map_pe(eng.e[i], walt_batch_seqs(b1), walt_batch_offsets(b1) + lo, walt_batch_seqs(b2),
-                                     walt_batch_offsets(b2) + lo, hi - lo, s.m, s.b, s.top_k, s.frag, s.pbat ? 1 : 0,
-                                     r1.data() + (size_t)lo * s.top_k, n1.data() + lo, r2.data() + (size_t)lo * s.top_k,
-                                     n2.data() + lo, pairs.data() + lo, &s1[i], &s2[i]);
+          rc[i] = walt_engine_map_pe_compact(eng.e[i], walt_batch_seqs(b1), walt_batch_offsets(b1) + lo,
+                                             walt_batch_seqs(b2), walt_batch_offsets(b2) + lo, hi - lo, s.m, s.b, s.top_k,
+                                             s.frag, s.pbat ? 1 : 0, res.data() + lo, &s1[i], &s2[i]);
           if (rc[i]) err[i] = walt_last_error();
         });
       }
@@ -239,7 +235,7 @@ void process_paired_end(Engines& eng, const walt_chroms* chroms, const Settings&
         if (rc[i]) throw std::runtime_error("walt engine: " + err[i]);
         walt_pe_writer_add_short(w, s1[i], s2[i]);
       }
-      if (walt_pe_writer_write(w, b1, b2, r1.data(), n1.data(), r2.data(), n2.data(), pairs.data(), n))
+      if (walt_pe_writer_write_compact(w, b1, b2, res.data(), n))
         throw std::runtime_error(walt_host_last_error());
       if (n < s.batch) break;
     }
