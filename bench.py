@@ -46,7 +46,10 @@ HG19_MB = [249.25, 243.20, 198.02, 191.15, 180.92, 171.12, 159.14, 146.36, 141.2
            115.17, 107.35, 102.53, 90.35, 81.20, 78.08, 59.13, 63.03, 48.13, 51.30, 155.27, 59.37]
 METRICS = {"se": ("reads mapped/sec (SE 150bp, hg19-size synthetic)", "reads/s"),
            "se_ag": ("reads mapped/sec (SE 150bp -A, hg19-size synthetic)", "reads/s"),
-           "pe": ("read pairs mapped/sec (PE 2x150bp -k 50 -L 1000, hg19-size synthetic)", "pairs/s")}
+           "pe": ("read pairs mapped/sec (PE 2x150bp -k 50 -L 1000, hg19-size synthetic)", "pairs/s"),
+           "pe_stress": ("read pairs mapped/sec (PBAT PE 2x150bp -P -m 8 -b 5000, repeat-heavy synthetic genome, "
+                         "30% adaptor read-through)", "pairs/s")}
+MISMATCHES = {"se": 6, "se_ag": 6, "pe": 6, "pe_stress": 8}
 M, B, TOP_K, FRAG = 6, 5000, 50, 1000
 
 
@@ -162,7 +165,10 @@ class Workload:
         self.device = device
         self.kind = getattr(args, "workload", "se")
         self.ag = self.kind == "se_ag"
-        self.which = {"se": (0, 1), "se_ag": (2, 3), "pe": (0, 1, 2, 3)}[self.kind]
+        self.is_pe = self.kind in ("pe", "pe_stress")
+        self.pbat = self.kind == "pe_stress"
+        self.m = MISMATCHES[self.kind]
+        self.which = {"se": (0, 1), "se_ag": (2, 3), "pe": (0, 1, 2, 3), "pe_stress": (0, 1, 2, 3)}[self.kind]
         self.n, self.rl = args.reads, args.read_len
         total = int(args.genome_mb * 1e6)
         self.lengths = chrom_lengths(total)
@@ -174,38 +180,41 @@ class Workload:
         self.e.set_chromosomes(self.lengths, self.names)
         dev = f"cuda:{device}"
         d_fwd = torch.empty(eng.packed_genome_bytes(total), dtype=torch.uint8, device=dev)
-        eng.synth_genome_device(device, total, 3, d_fwd.data_ptr())
+        eng.synth_genome_device(device, total, 3, d_fwd.data_ptr(), repeats=self.kind == "pe_stress")
         self.e.build_from_device_genome(d_fwd.data_ptr(), which=self.which)
         torch.cuda.synchronize()
         self.t_index = time.time() - t0
         self.d_reads = torch.empty(self.n * self.rl, dtype=torch.uint8, device=dev)
         self.d_reads2 = None
         # every rank maps its own shard: different read seed per rank
-        if self.kind == "pe":
+        if self.is_pe:
             self.d_reads2 = torch.empty(self.n * self.rl, dtype=torch.uint8, device=dev)
-            self.e.synth_pairs_device(d_fwd.data_ptr(), self.n, self.rl, 5 + 1000 * rank, self.d_reads.data_ptr(),
-                                      self.d_reads2.data_ptr())
+            # d_reads / d_reads2 are the first / second read FILE; under PBAT the first file holds the
+            # A-rich mate, i.e. the directional library with its mates exchanged
+            t_rich, a_rich = (self.d_reads2, self.d_reads) if self.pbat else (self.d_reads, self.d_reads2)
+            self.e.synth_pairs_device(d_fwd.data_ptr(), self.n, self.rl, 5 + 1000 * rank, t_rich.data_ptr(),
+                                      a_rich.data_ptr(), readthrough_pct=30 if self.kind == "pe_stress" else 0)
         else:
             self.e.synth_reads_device(d_fwd.data_ptr(), self.n, self.rl, 4 + 1000 * rank, self.ag, self.d_reads.data_ptr())
         del d_fwd
         torch.cuda.empty_cache()
         self.d_offs = torch.arange(self.n + 1, dtype=torch.int64, device=dev) * self.rl
-        out_bytes = eng.PE_RESULT_DT.itemsize if self.kind == "pe" else 16
-        self.out_dt = eng.PE_RESULT_DT if self.kind == "pe" else eng.BEST_DT
+        out_bytes = eng.PE_RESULT_DT.itemsize if self.is_pe else 16
+        self.out_dt = eng.PE_RESULT_DT if self.is_pe else eng.BEST_DT
         self.d_out = torch.zeros(self.n * out_bytes, dtype=torch.uint8, device=dev)
         torch.cuda.synchronize()
 
     def device_step(self, stream):
-        if self.kind == "pe":
+        if self.is_pe:
             self.e.map_pe_device(self.d_reads.data_ptr(), self.d_offs.data_ptr(), self.d_reads2.data_ptr(),
-                                 self.d_offs.data_ptr(), self.n, self.rl, self.d_out.data_ptr(), m=M, b=B, top_k=TOP_K,
-                                 frag_range=FRAG, stream=stream)
+                                 self.d_offs.data_ptr(), self.n, self.rl, self.d_out.data_ptr(), m=self.m, b=B, top_k=TOP_K,
+                                 frag_range=FRAG, pbat=self.pbat, stream=stream)
         else:
             self.e.map_se_device(self.d_reads.data_ptr(), self.d_offs.data_ptr(), self.n, self.rl, self.d_out.data_ptr(),
-                                 ag=self.ag, m=M, b=B, stream=stream)
+                                 ag=self.ag, m=self.m, b=B, stream=stream)
 
     def launches_per_step(self):
-        if self.kind != "pe":
+        if not self.is_pe:
             return 1
         chunk = max(1024, min(self.n, (1 << 30) // (2 * TOP_K * 12)))
         return 3 * -(-self.n // chunk)
@@ -230,7 +239,10 @@ class Workload:
         return out
 
     def sample_reads(self, n, mate=1):
+        """first n reads; for pairs `mate` is the bisulfite ROLE (1 = C->T mate, 2 = G->A mate)"""
         n = min(n, self.n)
+        if self.is_pe and self.pbat:
+            mate = 3 - mate
         src = self.d_reads if mate == 1 else self.d_reads2
         buf = src[: n * self.rl].cpu().numpy()
         offs = np.arange(n + 1, dtype=np.uint64) * np.uint64(self.rl)
@@ -243,9 +255,9 @@ def reference_pass(wl, hidx, n, threads):
     -> (seconds inside the loops, results: BestMatch[] | {mate: (ranked, sizes)})."""
     import refio
     L = refio.ref_lib()
-    if wl.kind != "pe":
+    if not wl.is_pe:
         buf, offs = wl.sample_reads(n)
-        best = refio.init_best(n, M)
+        best = refio.init_best(n, wl.m)
         t = 0.0
         for which, strand in zip(wl.which, "+-"):
             t += L.waltref_time_se(hidx[which], buf.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p),
@@ -258,7 +270,7 @@ def reference_pass(wl, hidx, n, threads):
         hp = C.c_void_p(L.waltref_heaps_alloc(C.c_uint32(n), C.c_uint32(TOP_K)))
         for which, strand in zip(pair, "+-"):
             t += L.waltref_time_pe(hidx[which], hp, buf.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p),
-                                   C.c_uint32(n), C.c_char(strand.encode()), C.c_int(ag), C.c_uint32(M), C.c_uint32(B),
+                                   C.c_uint32(n), C.c_char(strand.encode()), C.c_int(ag), C.c_uint32(wl.m), C.c_uint32(B),
                                    C.c_int(threads))
         ranked = np.zeros((n, TOP_K), dtype=refio.CAND_DT)
         sizes = np.zeros(n, dtype=np.uint32)
@@ -282,9 +294,9 @@ def oracle_counters(wl, hidx, n):
         return refio.WoIndex(L.waltref_index_sequence(h), int(L.waltref_index_genome_len(h)), len(wl.lengths),
                              starts.ctypes.data, L.waltref_index_counter(h), L.waltref_index_index(h),
                              int(L.waltref_index_index_size(h)))
-    if wl.kind != "pe":
+    if not wl.is_pe:
         buf, offs = wl.sample_reads(n)
-        best = refio.init_best(n, M)
+        best = refio.init_best(n, wl.m)
         for which, strand in zip(wl.which, "+-"):
             ix = view(which)
             Lo.wo_se_map_batch(C.byref(ix), buf.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p),
@@ -298,7 +310,7 @@ def oracle_counters(wl, hidx, n):
         for which, strand in zip(pair, "+-"):
             ix = view(which)
             Lo.wo_pe_map_batch(C.byref(ix), buf.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p),
-                               C.c_uint32(n), C.c_char(strand.encode()), C.c_int(ag), C.c_uint32(M), C.c_uint32(B),
+                               C.c_uint32(n), C.c_char(strand.encode()), C.c_int(ag), C.c_uint32(wl.m), C.c_uint32(B),
                                C.c_uint32(TOP_K), cands.ctypes.data_as(C.c_void_p), sizes.ctypes.data_as(C.c_void_p),
                                C.byref(ctr))
     return ctr.asdict(), None
@@ -308,13 +320,13 @@ def parity_vs_reference(wl, n, ref_result):
     """Fields of the engine's results that differ from the unmodified reference's on the first n
     reads (pairs).  PE compares the drained heaps (through the full-list entry point)."""
     import refio
-    if wl.kind != "pe":
+    if not wl.is_pe:
         got = wl.d_out[: n * 16].cpu().numpy().view(refio.BEST_DT)
         return sum(int((got[f] != ref_result[f]).sum()) for f in ("genome_pos", "times", "mismatch", "strand"))
     n = min(n, 200000)
     b1, o1 = wl.sample_reads(n, 1)
     b2, o2 = wl.sample_reads(n, 2)
-    r = wl.e.map_pe(b1, o1, b2, o2, m=M, b=B, top_k=TOP_K, frag_range=FRAG)
+    r = wl.e.map_pe(b1, o1, b2, o2, m=wl.m, b=B, top_k=TOP_K, frag_range=FRAG)
     bad = 0
     for mate in (1, 2):
         ranked, sizes = ref_result[mate]
@@ -330,9 +342,12 @@ def config_dict(args, extra=None):
             "se_ag": f"configs[2]: {args.genome_mb:g} Mb synthetic genome (24 chr, hg19 profile), {args.reads} A-rich SE "
                      f"{args.read_len} bp reads per GPU, -A -m {M} -b {B}",
             "pe": f"configs[3]: {args.genome_mb:g} Mb synthetic genome (24 chr, hg19 profile), {args.reads} pairs "
-                  f"2x{args.read_len} bp per GPU, -m {M} -b {B} -k {TOP_K} -L {FRAG}"}[args.workload]
+                  f"2x{args.read_len} bp per GPU, -m {M} -b {B} -k {TOP_K} -L {FRAG}",
+            "pe_stress": f"configs[4]: {args.genome_mb:g} Mb repeat-heavy synthetic genome (2000 repeat families, ~40 % of "
+                         f"the bases), {args.reads} PBAT pairs 2x{args.read_len} bp per GPU, 30 % adaptor read-through "
+                         f"(as clipped by -C), -P -m 8 -b {B} -k {TOP_K} -L {FRAG}"}[args.workload]
     d = {"workload": what, "genome_mb": args.genome_mb, "reads_per_gpu": args.reads, "read_len": args.read_len,
-         "max_mismatches": M, "bucket_limit": B, "parallelism": f"reads sharded x{args.gpus}, index replicated",
+         "max_mismatches": MISMATCHES[args.workload], "bucket_limit": B, "parallelism": f"reads sharded x{args.gpus}, index replicated",
          "l2": "inputs larger than L2 (index >= 13 GB per strand randomly gathered, >= 1.5 GB of reads streamed per step)"}
     if extra:
         d.update(extra)
@@ -363,7 +378,7 @@ def run_reference(args):
         dt, _ = reference_pass(wl, hidx, n, threads)
         t += dt
     value = n * args.steps / t
-    sample = (f"first {n} {'pairs' if wl.kind == 'pe' else 'reads'} of rank 0's batch per step, every strand pass, "
+    sample = (f"first {n} {'pairs' if wl.is_pe else 'reads'} of rank 0's batch per step, every strand pass, "
               f"OpenMP loops only")
     line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
@@ -381,6 +396,8 @@ def run_ours(args):
     rank, local, world = dist_env()
     metric, unit = METRICS[args.workload]
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"     # keep stdout to the one JSON line
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
@@ -390,7 +407,7 @@ def run_ours(args):
     dev = torch.device(f"cuda:{local}")
     wl = Workload(args, local, rank)
     e, n, rl = wl.e, wl.n, wl.rl
-    pe = wl.kind == "pe"
+    pe = wl.is_pe
     stream = torch.cuda.current_stream()
 
     def barrier():
@@ -477,10 +494,10 @@ def run_ours(args):
 
     def e2e_step():
         if pe:
-            e.map_pe_compact(h_reads.array, h_offs.array, h_reads2.array, h_offs.array, m=M, b=B, top_k=TOP_K,
-                             frag_range=FRAG, out=h_out.array)
+            e.map_pe_compact(h_reads.array, h_offs.array, h_reads2.array, h_offs.array, m=wl.m, b=B, top_k=TOP_K,
+                             frag_range=FRAG, pbat=wl.pbat, out=h_out.array)
         else:
-            e.map_se(h_reads.array, h_offs.array, ag=wl.ag, m=M, b=B, out=h_out.array)
+            e.map_se(h_reads.array, h_offs.array, ag=wl.ag, m=wl.m, b=B, out=h_out.array)
 
     for _ in range(max(1, args.warmup // 2)):
         e2e_step()
@@ -542,8 +559,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--genome-mb", type=float, default=3100.0)
-    ap.add_argument("--workload", default="se", choices=["se", "se_ag", "pe"],
-                    help="se = configs[1] (the bench line), se_ag = configs[2], pe = configs[3]")
+    ap.add_argument("--workload", default="se", choices=["se", "se_ag", "pe", "pe_stress"],
+                    help="se = configs[1] (the bench line), se_ag = configs[2], pe = configs[3], pe_stress = configs[4]")
     ap.add_argument("--reads", type=int, default=0, help="reads (pairs) per GPU; default 10 M reads / 5 M pairs")
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--no-cpu", action="store_true", help="skip the oracle/reference side legs")
@@ -554,7 +571,7 @@ def main():
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.reads <= 0:
-        args.reads = 5_000_000 if args.workload == "pe" else 10_000_000
+        args.reads = 5_000_000 if args.workload.startswith("pe") else 10_000_000
     sys.exit(run_reference(args) if args.impl == "reference" else run_ours(args))
 
 

@@ -81,9 +81,10 @@ def packed_genome_bytes(n_bases):
     return int(load_library().walt_packed_genome_bytes(C.c_uint64(n_bases)))
 
 
-def synth_genome_device(device, n_bases, seed, d_out):
+def synth_genome_device(device, n_bases, seed, d_out, repeats=False):
     L = load_library()
-    rc = L.walt_synth_genome_device(C.c_int(device), C.c_uint64(n_bases), C.c_uint64(seed), C.c_void_p(d_out))
+    fn = L.walt_synth_repeat_genome_device if repeats else L.walt_synth_genome_device
+    rc = fn(C.c_int(device), C.c_uint64(n_bases), C.c_uint64(seed), C.c_void_p(d_out))
     if rc:
         raise WaltError(rc, L.walt_last_error().decode())
 
@@ -180,9 +181,10 @@ class Engine:
                                                    C.c_uint32(read_len), C.c_uint64(seed), C.c_int(int(a_rich)),
                                                    C.c_void_p(d_out)))
 
-    def synth_pairs_device(self, d_packed, n_pairs, read_len, seed, d_out1, d_out2):
+    def synth_pairs_device(self, d_packed, n_pairs, read_len, seed, d_out1, d_out2, readthrough_pct=0):
         self._check(self.L.walt_synth_pairs_device(self.h, C.c_void_p(d_packed), C.c_uint32(n_pairs),
-                                                   C.c_uint32(read_len), C.c_uint64(seed), C.c_void_p(d_out1),
+                                                   C.c_uint32(read_len), C.c_uint64(seed),
+                                                   C.c_uint32(readthrough_pct), C.c_void_p(d_out1),
                                                    C.c_void_p(d_out2)))
 
     def subindex_info(self, which):
