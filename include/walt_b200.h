@@ -124,6 +124,13 @@ int walt_engine_map_se(walt_engine* e, const char* seqs, const uint64_t* offs, u
                        int ag_wildcard, uint32_t max_mismatches, uint32_t b, walt_best* out,
                        uint32_t* n_short);
 
+/* The same call on a 2-bit packed batch (layout: walt_pack_reads, include/walt_host.h; `offs`
+ * are still base offsets).  A quarter of the read bytes cross PCIe; the C->T / G->A conversion
+ * still happens on the device. */
+int walt_engine_map_se_packed(walt_engine* e, const uint8_t* packed, const uint64_t* offs, uint32_t n,
+                              int ag_wildcard, uint32_t max_mismatches, uint32_t b, walt_best* out,
+                              uint32_t* n_short);
+
 /* Same computation with every buffer already resident in device memory (kernel-only
  * timing; no host<->device copies). */
 int walt_engine_map_se_device(walt_engine* e, const void* d_seqs, const void* d_offs, uint32_t n,
@@ -148,6 +155,11 @@ int walt_engine_map_pe_compact(walt_engine* e, const char* seqs1, const uint64_t
                                const uint64_t* offs2, uint32_t n, uint32_t max_mismatches, uint32_t b,
                                uint32_t top_k, int frag_range, int pbat, walt_pe_result* out,
                                uint32_t* n_short1, uint32_t* n_short2);
+/* ... on 2-bit packed mates (walt_pack_reads layout) ... */
+int walt_engine_map_pe_compact_packed(walt_engine* e, const uint8_t* packed1, const uint64_t* offs1,
+                                      const uint8_t* packed2, const uint64_t* offs2, uint32_t n,
+                                      uint32_t max_mismatches, uint32_t b, uint32_t top_k, int frag_range, int pbat,
+                                      walt_pe_result* out, uint32_t* n_short1, uint32_t* n_short2);
 /* ... and with every buffer already resident in device memory (kernel-only timing). */
 int walt_engine_map_pe_device(walt_engine* e, const void* d_seqs1, const void* d_offs1, const void* d_seqs2,
                               const void* d_offs2, uint32_t n, uint32_t max_read_len, uint32_t max_mismatches,

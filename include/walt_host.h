@@ -47,6 +47,17 @@ const uint64_t* walt_batch_offsets(const walt_batch* b);
 const char* walt_batch_name(const walt_batch* b, uint32_t i);
 const char* walt_batch_qual(const walt_batch* b, uint32_t i);
 
+/* 2-bit form of a batch for walt_engine_map_se_packed / walt_engine_map_pe_compact_packed (a
+ * quarter of the bytes cross PCIe).  Codes A0 C1 G2 T3 (util.hpp:107-121), unconverted, four
+ * bases per byte with the first base in the top bits; read j occupies ceil(len_j / 4) bytes
+ * starting at byte (offs[j] >> 2) + j, so the same offsets array addresses both forms.  `out`
+ * holds walt_packed_reads_bytes(offs, n) bytes.  Returns -1 if a byte is not A/C/G/T (the
+ * loader never leaves one behind, mapping.cpp:101-104). */
+uint64_t walt_packed_reads_bytes(const uint64_t* offs, uint32_t n);
+int walt_pack_reads(const char* seqs, const uint64_t* offs, uint32_t n, uint8_t* out);
+/* The loader's own packed copy of the batch (built on first use, owned by the batch). */
+const uint8_t* walt_batch_packed(walt_batch* b);
+
 /* clip_adaptor_from_read (util.hpp:189-217); returns the number of clipped characters */
 size_t walt_clip_adaptor(const char* adaptor, char* s, size_t len);
 

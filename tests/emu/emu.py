@@ -44,13 +44,13 @@ class EmuEngine:
     def depth(self, which):
         return int(self.L.emu_engine_depth(self.h, C.c_int(which)))
 
-    def map_se(self, buf, offs, best_dtype, ag=False, m=6, b=5000, literal=False, threads=8, width=32):
+    def map_se(self, buf, offs, best_dtype, ag=False, m=6, b=5000, literal=False, threads=8, width=32, packed=False):
         n = len(offs) - 1
         out = np.zeros(n, dtype=best_dtype)
         ctr = np.zeros(3, dtype=np.uint64)
         rc = self.L.emu_map_se(self.h, _p(buf), _p(offs), C.c_uint32(n), C.c_int(int(ag)), C.c_uint32(m),
                                C.c_uint32(b), C.c_int(int(literal)), _p(out), C.c_int(threads), _p(ctr),
-                               C.c_uint32(width))
+                               C.c_uint32(width), C.c_int(int(packed)))
         return rc, out, ctr
 
     def map_pe_mate(self, buf, offs, cand_dtype, ag, m=6, b=5000, top_k=50, literal=False, threads=8, width=32):

@@ -297,6 +297,7 @@ struct SeJob {
   const EmuEngine* e; const char* seqs; const uint64_t* offs; uint32_t lo, hi;
   int ag; uint32_t m, b; int literal; emu_best* out; uint32_t max_len;
   uint64_t* scratch; uint32_t* cached_len; Counters* ctr; int* bad;
+  int packed;   // seqs is the 2-bit form of walt_pack_reads (include/walt_host.h)
 };
 
 template <uint32_t WD>
@@ -313,8 +314,11 @@ void se_lane(WarpEmu* w, uint32_t lane, void* arg) {
   for (uint32_t r = j->lo; r < j->hi; ++r) {
     BestState st;
     uint32_t len = (uint32_t)(j->offs[r + 1] - j->offs[r]);
-    bool ok = map_read_se(W, ix2, cv, j->e->p3, cfg, j->seqs + j->offs[r], len, j->ag != 0, j->m, sc,
-                          cached, st, ctr);
+    bool ok = j->packed
+                  ? map_read_se<EmuWarp<WD>, true>(W, ix2, cv, j->e->p3, cfg, j->seqs + (j->offs[r] >> 2) + r, len,
+                                                   j->ag != 0, j->m, sc, cached, st, ctr)
+                  : map_read_se<EmuWarp<WD>, false>(W, ix2, cv, j->e->p3, cfg, j->seqs + j->offs[r], len, j->ag != 0,
+                                                    j->m, sc, cached, st, ctr);
     if (lane == 0) {
       if (!ok) *j->bad = 1;
       j->out[r].genome_pos = st.pos; j->out[r].times = st.times; j->out[r].mismatch = st.mm;
@@ -392,7 +396,7 @@ extern "C" {
 
 // returns 0 ok; 1 = warp primitives diverged (bug); 5 = non-ACGT read
 int emu_map_se(void* h, const char* seqs, const uint64_t* offs, uint32_t n, int ag, uint32_t m,
-               uint32_t b, int literal, emu_best* out, int threads, uint64_t* counters3, uint32_t width) {
+               uint32_t b, int literal, emu_best* out, int threads, uint64_t* counters3, uint32_t width, int packed) {
   if (width != 8 && width != 16 && width != 32) return 1;
   EmuEngine* e = (EmuEngine*)h;
   uint32_t max_len = 1;
@@ -403,7 +407,7 @@ int emu_map_se(void* h, const char* seqs, const uint64_t* offs, uint32_t n, int 
   int div = run_parallel<SeJob>(n, threads, width, [&](WarpEmu* w, uint32_t lo, uint32_t hi) {
     std::vector<uint64_t> scratch(scratch_words((max_len + 31) / 32) + 8);
     uint32_t cached = 0; Counters ctr{0, 0, 0}; int b_ = 0;
-    SeJob j{e, seqs, offs, lo, hi, ag, m, b, literal, out, max_len, scratch.data(), &cached, &ctr, &b_};
+    SeJob j{e, seqs, offs, lo, hi, ag, m, b, literal, out, max_len, scratch.data(), &cached, &ctr, &b_, packed};
     w->run(width == 8 ? se_lane<8> : width == 16 ? se_lane<16> : se_lane<32>, &j);
     if (b_) bad = 1;
     c0 += ctr.lookups; c1 += ctr.candidates; c2 += ctr.literal;

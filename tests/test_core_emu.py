@@ -39,6 +39,53 @@ def test_se_emu_matches_reference(engine, literal, width):
             _cmp_best(out, z[key])
 
 
+def _pack_numpy(buf, offs):
+    """independent statement of the walt_pack_reads layout (include/walt_host.h)"""
+    code = np.zeros(256, np.uint8)
+    for i, c in enumerate(b"ACGT"):
+        code[c] = i
+    n = len(offs) - 1
+    out = np.zeros((int(offs[n]) >> 2) + n + 16, np.uint8)
+    for j in range(n):
+        o0, o1 = int(offs[j]), int(offs[j + 1])
+        c = code[buf[o0:o1]]
+        c = np.concatenate([c, np.zeros((-len(c)) % 4, np.uint8)]).reshape(-1, 4)
+        b = (c[:, 0] << 6) | (c[:, 1] << 4) | (c[:, 2] << 2) | c[:, 3]
+        out[(o0 >> 2) + j:(o0 >> 2) + j + len(b)] |= b.astype(np.uint8)   # |= : overlap would corrupt
+    return out
+
+
+def test_pack_reads_layout():
+    from walt_b200 import host
+    z = goldenio.load("se_edge.npz")          # ragged lengths
+    got = host.pack_reads_2bit(z["buf"], z["offs"])
+    assert np.array_equal(got, _pack_numpy(z["buf"], z["offs"]))
+    buf, offs = refio.pack_reads([b"ACGTN" * 20])
+    with pytest.raises(host.HostError):
+        host.pack_reads_2bit(buf, offs)
+    assert host.pack_reads_2bit(np.zeros(1, np.uint8), np.zeros(1, np.uint64)).sum() == 0
+
+
+@pytest.mark.parametrize("width", [8, 16, 32])
+def test_se_emu_packed_input(engine, width):
+    """the kernels' PACKED read loader (2-bit reads over PCIe) gives the ASCII loader's results"""
+    from walt_b200 import host
+    for name, ag in (("se_ct.npz", False), ("se_ga.npz", True)):
+        z = goldenio.load(name)
+        buf, offs = refio.pack_reads(z["reads"])
+        rc, out, _ = engine.map_se(host.pack_reads_2bit(buf, offs), offs, refio.BEST_DT, ag=ag, m=6, b=5000,
+                                   width=width, packed=True)
+        assert rc == 0
+        _cmp_best(out, z["best_m6_b5000"])
+    z = goldenio.load("se_edge.npz")
+    key = [k for k in z.files if k.startswith("ct_best_")][0]
+    m, b = (int(x[1:]) for x in key[len("ct_best_"):].split("_"))
+    rc, out, _ = engine.map_se(host.pack_reads_2bit(z["buf"], z["offs"]), z["offs"], refio.BEST_DT, m=m, b=b,
+                               width=width, packed=True)
+    assert rc == 0
+    _cmp_best(out, z[key])
+
+
 @pytest.mark.parametrize("depth,width", [(0, 32), (12, 32), (13, 8), (16, 8), (0, 8), (12, 16)])
 def test_se_edge_emu(depth, width):
     hdr, subs = goldenio.genome()

@@ -94,6 +94,41 @@ def test_se_chunked_pipeline_matches_single_chunk(engine):
     _cmp_best(out, z["best_m6_b5000"])
 
 
+@pytest.mark.parametrize("width", [8, 16, 32])
+def test_se_packed_input_golden(engine, width):
+    """walt_engine_map_se_packed (2-bit reads over PCIe) == the reference, equal-length and ragged
+    batches, one chunk and many"""
+    from walt_b200 import host
+    engine.set_group_width(width)
+    try:
+        for name, ag in (("se_ct.npz", False), ("se_ga.npz", True)):
+            z = goldenio.load(name)
+            buf, offs = refio.pack_reads(z["reads"])
+            packed = host.pack_reads_2bit(buf, offs)
+            for key in [k for k in z.files if k.startswith("best_")]:
+                m, b = (int(x[1:]) for x in key[5:].split("_"))
+                out, short = engine.map_se_packed(packed, offs, ag=ag, m=m, b=b)
+                _cmp_best(out, z[key], (name, key))
+                assert short == int(z[key.replace("best", "short")])
+            engine.set_chunk_reads(257)
+            out, _ = engine.map_se_packed(packed, offs, ag=ag, m=6, b=5000)
+            engine.set_chunk_reads(1 << 18)
+            _cmp_best(out, z["best_m6_b5000"], "chunked")
+        z = goldenio.load("se_edge.npz")
+        packed = host.pack_reads_2bit(z["buf"], z["offs"])
+        for chunk in (1 << 18, 7):
+            engine.set_chunk_reads(chunk)
+            for ag, pre in ((False, "ct_best_"), (True, "ga_best_")):
+                for key in [k for k in z.files if k.startswith(pre)]:
+                    m, b = (int(x[1:]) for x in key[len(pre):].split("_"))
+                    out, short = engine.map_se_packed(packed, z["offs"], ag=ag, m=m, b=b)
+                    _cmp_best(out, z[key], (chunk, key))
+                    assert short == int(z[key.replace("best", "short")])
+    finally:
+        engine.set_group_width(8)
+        engine.set_chunk_reads(1 << 18)
+
+
 def test_se_empty_and_errors(engine):
     import walt_b200
     out, short = engine.map_se(np.zeros(1, np.uint8), np.zeros(1, np.uint64))
@@ -266,6 +301,16 @@ def test_pe_compact_and_device_paths_match_ranked(engine, pbat):
                 got = comp[f"single{mate}"][j]
                 assert (int(got["genome_pos"]), int(got["times"]), int(got["mismatch"]), got["strand"]) == \
                        (pos, times, mm, strand), (j, mate)
+        # 2-bit packed mates over PCIe
+        from walt_b200 import host
+        for chunk in (1 << 18, 61):
+            engine.set_chunk_reads(chunk)
+            try:
+                pk, p1, p2 = engine.map_pe_compact_packed(host.pack_reads_2bit(b1, o1), o1, host.pack_reads_2bit(b2, o2),
+                                                          o2, m=m, top_k=k, frag_range=L, pbat=pbat)
+            finally:
+                engine.set_chunk_reads(1 << 18)
+            assert (p1, p2) == (s1, s2) and np.array_equal(pk, comp), chunk
         # device-resident path
         dev = "cuda:0"
         d1 = torch.from_numpy(b1).to(dev); d2 = torch.from_numpy(b2).to(dev)

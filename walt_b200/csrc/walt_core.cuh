@@ -44,6 +44,12 @@
 #define WALT_UNROLL
 #define WALT_NO_UNROLL
 #endif
+// pull the line that holds *p towards the SM ahead of a dependent load (no-op on the CPU harness)
+#if defined(__CUDA_ARCH__)
+#define WALT_PREFETCH(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
+#else
+#define WALT_PREFETCH(p) ((void)(p))
+#endif
 
 namespace waltcore {
 
@@ -304,11 +310,19 @@ WALT_HD uint32_t load4_ascii(const char* __restrict__ seq, uint32_t p, uint32_t 
   return v;
 }
 
+// read conversion (mapping.cpp:142-164) on four codes, one per byte: C->T sets bit 1 where bit 0
+// is set; G->A clears bit 1 where bit 0 is clear
+WALT_HD uint32_t convert4(uint32_t code4, bool ag) {
+  const uint32_t b0 = code4 & 0x01010101u;
+  return ag ? (code4 & ((b0 << 1) | 0x01010101u)) : (code4 | (b0 << 1));
+}
+WALT_HD uint32_t keep4(uint32_t n_valid) { return n_valid >= 4u ? 0xFFFFFFFFu : ((1u << (8u * n_valid)) - 1u); }
+
 // The same four characters as 2-bit codes (one per byte), SIMD inside the register.
 // *bad is set if a byte in front of read_len is not A/C/G/T.
 WALT_HD uint32_t codes4(uint32_t ascii4, uint32_t n_valid, bool ag, bool& bad) {
   const uint32_t x = (ascii4 >> 1) & 0x03030303u;
-  uint32_t code = x ^ ((x >> 1) & 0x01010101u);                       // A0 C1 G2 T3 (util.hpp:107-121)
+  const uint32_t code = x ^ ((x >> 1) & 0x01010101u);                 // A0 C1 G2 T3 (util.hpp:107-121)
   // rebuild the letters from the codes; any difference is a non-ACGT byte
   uint32_t letters = 0u;
 #if defined(__CUDA_ARCH__)
@@ -317,13 +331,15 @@ WALT_HD uint32_t codes4(uint32_t ascii4, uint32_t n_valid, bool ag, bool& bad) {
 #else
   for (uint32_t j = 0; j < 4u; ++j) letters |= (uint32_t)(uint8_t)"ACGT"[(code >> (8u * j)) & 3u] << (8u * j);
 #endif
-  const uint32_t keep = n_valid >= 4u ? 0xFFFFFFFFu : ((1u << (8u * n_valid)) - 1u);
+  const uint32_t keep = keep4(n_valid);
   bad |= ((letters ^ ascii4) & keep) != 0u;
-  // read conversion (mapping.cpp:142-164): C->T sets bit 1 where bit 0 is set; G->A clears bit 1
-  // where bit 0 is clear
-  const uint32_t b0 = code & 0x01010101u;
-  code = ag ? (code & ((b0 << 1) | 0x01010101u)) : (code | (b0 << 1));
-  return code & keep;
+  return convert4(code, ag) & keep;
+}
+// One byte of a 2-bit packed read (first base in the top bits, see walt_pack_reads in
+// include/walt_host.h) -> the same register layout: four codes, first base in the low byte.
+WALT_HD uint32_t packed_codes4(uint32_t byte, uint32_t n_valid, bool ag) {
+  const uint32_t code = ((byte >> 6) & 3u) | (((byte >> 4) & 3u) << 8) | (((byte >> 2) & 3u) << 16) | ((byte & 3u) << 24);
+  return convert4(code, ag) & keep4(n_valid);
 }
 // rank of each converted code inside its 3-letter alphabet (== ternary_digit, four at a time)
 WALT_HD uint32_t digits4(uint32_t code4, bool ag) {
@@ -331,11 +347,13 @@ WALT_HD uint32_t digits4(uint32_t code4, bool ag) {
             : (((code4 >> 1) & 0x01010101u) + (code4 & 0x01010101u));
 }
 
-// Pack + convert one ASCII read into sc.R and its base-3 digits into sc.D (group-cooperative).
-// Returns false (uniformly) if a byte is not A/C/G/T.  A group of W::WIDTH lanes owns the read:
-// with 8 lanes every lane turns 4 consecutive characters into one byte of the packed word (no
-// cross-lane traffic); other widths assemble the word from ballots.
-template <class W>
+// Pack + convert one read into sc.R and its base-3 digits into sc.D (group-cooperative).  The
+// read arrives as ASCII (PACKED = false; returns false, uniformly, if a byte is not A/C/G/T) or
+// already 2 bits per base, unconverted (PACKED = true: ceil(read_len / 4) bytes, first base in the
+// top bits of each byte).  A group of W::WIDTH lanes owns the read: with 8 lanes every lane turns
+// 4 consecutive characters into one byte of the packed word (no cross-lane traffic); other widths
+// assemble the word from ballots.
+template <class W, bool PACKED>
 WALT_HD bool load_read(W& w, const char* __restrict__ seq, uint32_t read_len, bool ag, ReadScratch& sc) {
   const uint32_t lane = w.lane();
   const uint32_t nw = (read_len + 31u) >> 5;
@@ -345,8 +363,10 @@ WALT_HD bool load_read(W& w, const char* __restrict__ seq, uint32_t read_len, bo
     uint32_t* dw = reinterpret_cast<uint32_t*>(sc.D);
     for (uint32_t k = 0; k < nw; ++k) {
       const uint32_t p = 32u * k + 4u * lane;
-      const uint32_t a4 = load4_ascii(seq, p, read_len);
-      const uint32_t c4 = codes4(a4, p < read_len ? read_len - p : 0u, ag, bad);
+      const uint32_t nv = p < read_len ? read_len - p : 0u;
+      uint32_t c4;
+      if (PACKED) c4 = nv ? packed_codes4((uint8_t)seq[p >> 2], nv, ag) : 0u;
+      else c4 = codes4(load4_ascii(seq, p, read_len), nv, ag, bad);
       // bytes c0..c3 (first character lowest) -> c0<<6 | c1<<4 | c2<<2 | c3
       rb[8u * k + (7u - lane)] = (uint8_t)((c4 * 0x40100401u) >> 24);   // little-endian u64: first base on top
       dw[8u * k + lane] = digits4(c4, ag);
@@ -358,9 +378,13 @@ WALT_HD bool load_read(W& w, const char* __restrict__ seq, uint32_t read_len, bo
         const uint32_t p = 32u * k + j * W::WIDTH + lane;
         uint32_t code = 0;
         if (p < read_len) {
-          const uint32_t c = (uint8_t)seq[p];
-          bad |= !ascii_is_acgt(c);
-          code = convert_code(ascii_code(c), ag);
+          if (PACKED) {
+            code = convert_code(((uint32_t)(uint8_t)seq[p >> 2] >> (6u - 2u * (p & 3u))) & 3u, ag);
+          } else {
+            const uint32_t c = (uint8_t)seq[p];
+            bad |= !ascii_is_acgt(c);
+            code = convert_code(ascii_code(c), ag);
+          }
         }
         sc.D[p] = (uint8_t)ternary_digit(code, ag);
         const uint32_t sh = 32u - W::WIDTH;        // ballot bit l -> base j*WIDTH + l of the word
@@ -372,7 +396,7 @@ WALT_HD bool load_read(W& w, const char* __restrict__ seq, uint32_t read_len, bo
       if (lane == 0) sc.R[k] = word;
     }
   }
-  bool any_bad = w.ballot(bad) != 0u;
+  bool any_bad = PACKED ? false : w.ballot(bad) != 0u;
   w.sync();
   return !any_bad;
 }
@@ -512,6 +536,8 @@ struct BestSink {
   WALT_HD bool stop_before_shift(uint32_t seed_i) const {  // mapping.cpp:250-256
     return (st.mm == 0u && seed_i >= 1u) || (st.mm == 1u && seed_i >= 2u);
   }
+  // can a candidate with this many mismatches still change the state?
+  WALT_HD bool may_take(uint32_t mm) const { return mm <= st.mm; }
   // candidates of lanes (ascending) with valid set, in index order; g are distinct per lookup
   WALT_HD void consume(W& w, bool valid, uint32_t mm, uint32_t g, uint32_t strand) {
     uint32_t below = w.ballot(valid && mm < st.mm);
@@ -608,8 +634,12 @@ struct HeapSink {
     bool full = size > 0u && size >= cap;
     return full && ((top_mm == 0u && seed_i >= 1u) || (top_mm == 1u && seed_i >= 2u));
   }
+  // Can a candidate with this many mismatches still enter the heap?  Once the heap is full a push
+  // needs mm < heap[0].mm (paired.hpp:60-67), and heap[0].mm only falls, so a candidate turned
+  // away by the (warp-uniform, possibly stale) top_mm would be turned away by the heap as well.
+  WALT_HD bool may_take(uint32_t mm) const { return mm <= max_mm && (size < cap || mm < top_mm); }
   WALT_HD void consume(W& w, bool valid, uint32_t mm, uint32_t g, uint32_t strand) {
-    uint32_t take = w.ballot(valid && mm <= max_mm);
+    uint32_t take = w.ballot(valid && may_take(mm));
     if (!take) return;
     // pushes must happen one by one in lane order; lane 0 owns the heap
     while (take) {
@@ -838,22 +868,45 @@ WALT_HD void seed_lookup(W& w, const SubIndexView& ix, const ChromView& cv, cons
     if (last_excl - first > cfg.b) return;
   }
 
-  // exact region [first, last_excl): every slot is a candidate
-  for (uint32_t base = first; base < last_excl; base += WD) {
-    const uint32_t slot = base + lane;
-    bool valid = slot < last_excl;
-    uint32_t g = 0, mm = 0;
-    if (valid) {
-      const uint32_t e = ix.entries[slot].pos;
-      WindowResult r = compare_window(ix.genome, (uint64_t)e + PAD_BASES - seed_i, R, VM, SM, nw);
-      mm = r.mismatches;
-      // bounds, mapping.cpp:281-286 (all uint32 arithmetic, as the reference)
-      const uint32_t chr = chrom_of(cv.starts, cv.n_chr, e);
-      g = e - seed_i;
-      valid = (e - cv.starts[chr] >= seed_i) && !(g + read_len >= cv.starts[chr + 1u]);
+  // Exact region [first, last_excl): every slot is a candidate.  Long regions (repeats) are a
+  // chain of dependent gathers -- entry, then genome window -- so every lane keeps SLOTS_AHEAD
+  // of them in flight: the entries of a block are loaded together and their windows prefetched
+  // before the first is compared.  Candidates reach the sink in slot order, WD at a time.
+  constexpr uint32_t SLOTS_AHEAD = 4;
+  for (uint32_t base = first; base < last_excl; base += WD * SLOTS_AHEAD) {
+    uint32_t e[SLOTS_AHEAD];
+    WALT_UNROLL
+    for (uint32_t u = 0; u < SLOTS_AHEAD; ++u) {
+      const uint32_t slot = base + u * WD + lane;
+      e[u] = slot < last_excl ? ix.entries[slot].pos : 0u;   // 64 readable pad entries behind index[]
     }
-    if (valid) ctr.candidates++;
-    sink.consume(w, valid, mm, g, strand);
+    WALT_UNROLL
+    for (uint32_t u = 0; u < SLOTS_AHEAD; ++u) {
+      if (base + u * WD + lane < last_excl) {
+        const uint64_t* g0 = ix.genome + (((uint64_t)e[u] + PAD_BASES - seed_i) >> 5);
+        WALT_PREFETCH(g0);
+        WALT_PREFETCH(g0 + nw);
+      }
+    }
+    WALT_UNROLL
+    for (uint32_t u = 0; u < SLOTS_AHEAD; ++u) {
+      if (base + u * WD >= last_excl) break;                 // uniform
+      bool valid = base + u * WD + lane < last_excl;
+      uint32_t g = 0, mm = 0;
+      if (valid) {
+        WindowResult r = compare_window(ix.genome, (uint64_t)e[u] + PAD_BASES - seed_i, R, VM, SM, nw);
+        mm = r.mismatches;
+        ctr.candidates++;
+        valid = sink.may_take(mm);
+      }
+      if (valid) {
+        // bounds, mapping.cpp:281-286 (all uint32 arithmetic, as the reference)
+        const uint32_t chr = chrom_of(cv.starts, cv.n_chr, e[u]);
+        g = e[u] - seed_i;
+        valid = (e[u] - cv.starts[chr] >= seed_i) && !(g + read_len >= cv.starts[chr + 1u]);
+      }
+      sink.consume(w, valid, mm, g, strand);
+    }
   }
 }
 
@@ -968,7 +1021,7 @@ WALT_HD bool lane_lookup(const SubIndexView& ix, const ChromView& cv, const Pow3
 // SingleEndMapping for both strand passes of one read (mapping.cpp:486-500 order: all shifts
 // on the '+' sub-index, then all shifts on the '-' sub-index, state carried across).
 // Returns false if the read holds a non-ACGT byte.
-template <class W>
+template <class W, bool PACKED = false>
 WALT_HD bool map_read_se(W& w, const SubIndexView* ix2, const ChromView& cv, const Pow3& p3,
                          const MapConfig& cfg, const char* seq, uint32_t read_len, bool ag,
                          uint32_t max_mismatches, ReadScratch& sc, uint32_t& cached_len,
@@ -978,7 +1031,7 @@ WALT_HD bool map_read_se(W& w, const SubIndexView* ix2, const ChromView& cv, con
   sink.st.pos = 0u; sink.st.times = 0u; sink.st.mm = max_mismatches; sink.st.strand = '+';
   out = sink.st;
   if (read_len < MIN_READ_LEN) return true;
-  if (!load_read(w, seq, read_len, ag, sc)) return false;
+  if (!load_read<W, PACKED>(w, seq, read_len, ag, sc)) return false;
   if (cached_len != read_len) { build_masks(w, read_len, sc); cached_len = read_len; }
   // every lookup lane runs its own lookup and summarises it: minimum, how many candidates
   // share it, the first and the last of them (all the ordered fold needs, see BestSink::apply)
@@ -1022,7 +1075,7 @@ WALT_HD bool map_read_se(W& w, const SubIndexView* ix2, const ChromView& cv, con
 
 // PairEndMapping for both strand passes of one mate (paired.cpp:650-671); the heap persists
 // across the two passes.  On return heap[0..size) is the libstdc++ heap array.
-template <class W>
+template <class W, bool PACKED = false>
 WALT_HD bool map_read_pe(W& w, const SubIndexView* ix2, const ChromView& cv, const Pow3& p3,
                          const MapConfig& cfg, const char* seq, uint32_t read_len, bool ag,
                          uint32_t max_mismatches, uint32_t top_k, ReadScratch& sc,
@@ -1032,7 +1085,7 @@ WALT_HD bool map_read_pe(W& w, const SubIndexView* ix2, const ChromView& cv, con
   sink.heap = heap; sink.size = 0u; sink.cap = top_k; sink.top_mm = 0u; sink.max_mm = max_mismatches;
   heap_size = 0u;
   if (read_len < MIN_READ_LEN) return true;
-  if (!load_read(w, seq, read_len, ag, sc)) return false;
+  if (!load_read<W, PACKED>(w, seq, read_len, ag, sc)) return false;
   if (cached_len != read_len) { build_masks(w, read_len, sc); cached_len = read_len; }
   // lookup lanes leave their candidates (index order) in the group's scratch; lane 0 pushes
   // them in reference order

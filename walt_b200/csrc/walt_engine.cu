@@ -261,7 +261,8 @@ struct SeArgs {
   const char* seqs;
   const uint64_t* offs;   // n + 1, absolute; seqs[0] is byte `seq_base` (unused if uniform_len)
   uint64_t seq_base;
-  uint32_t uniform_len;   // != 0: every read has this length, read r starts at seqs + r * uniform_len
+  uint32_t uniform_len;   // != 0: every read has this length, read r starts at offset seq_base + r * uniform_len
+  uint32_t read_base;     // packed input: read r of this launch is read `read_base + r` of the buffer
   uint32_t n;
   uint32_t nw_max;        // scratch stride (words) for the longest read
   uint32_t ag;
@@ -284,6 +285,21 @@ __device__ __forceinline__ uint32_t next_read(uint32_t* queue) {
   return r + (threadIdx.x & 31u) / WD;
 }
 
+// Where read r of a launch starts and how long it is.  ASCII: byte offs[r] - seq_base of `seqs`.
+// 2-bit packed (walt_pack_reads, include/walt_host.h): read j of a batch occupies ceil(len / 4)
+// bytes from byte (offs[j] >> 2) + j, so one offsets array addresses both forms.
+template <bool PACKED, class Args>
+__device__ __forceinline__ const char* read_at(const Args& a, uint32_t r, uint32_t& len) {
+  uint64_t o0;
+  if (a.uniform_len) {
+    len = a.uniform_len; o0 = a.seq_base + (uint64_t)r * len;
+  } else {
+    o0 = a.offs[r]; len = (uint32_t)(a.offs[r + 1] - o0);
+  }
+  if (PACKED) return a.seqs + ((o0 >> 2) - (a.seq_base >> 2) + r + a.read_base);
+  return a.seqs + (o0 - a.seq_base);
+}
+
 template <uint32_t WD>
 __device__ __forceinline__ void flush_counters(const HwGroup<WD>& w, const Counters& ctr, bool bad, uint32_t* flags,
                                                unsigned long long* counters) {
@@ -298,8 +314,8 @@ __device__ __forceinline__ void flush_counters(const HwGroup<WD>& w, const Count
   }
 }
 
-template <uint32_t WD, uint32_t MINB = MIN_BLOCKS_PER_SM>
-__global__ void __launch_bounds__(BLOCK_THREADS, MINB)
+template <uint32_t WD, bool PACKED>
+__global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS_PER_SM)
 se_map_kernel(const __grid_constant__ SeArgs a) {
   extern __shared__ uint64_t smem[];
   HwGroup<WD> w;
@@ -313,16 +329,10 @@ se_map_kernel(const __grid_constant__ SeArgs a) {
     const uint32_t r = next_read<WD>(a.queue);
     if (r - (threadIdx.x & 31u) / WD >= a.n) break;     // warp-uniform: the ticket is past the batch
     if (r < a.n) {
-      const char* seq;
       uint32_t len;
-      if (a.uniform_len) {
-        len = a.uniform_len; seq = a.seqs + (size_t)r * len;
-      } else {
-        const uint64_t o0 = a.offs[r], o1 = a.offs[r + 1];
-        len = (uint32_t)(o1 - o0); seq = a.seqs + (o0 - a.seq_base);
-      }
+      const char* seq = read_at<PACKED>(a, r, len);
       BestState st;
-      bool ok = map_read_se(w, a.ix, a.cv, a.p3, a.cfg, seq, len, a.ag != 0u,
+      bool ok = map_read_se<HwGroup<WD>, PACKED>(w, a.ix, a.cv, a.p3, a.cfg, seq, len, a.ag != 0u,
                             a.max_mismatches, sc, cached_len, st, ctr);
       bad |= !ok;
       if (lane == 0) {
@@ -345,6 +355,7 @@ struct PeArgs {
   const uint64_t* offs;
   uint64_t seq_base;
   uint32_t uniform_len;   // see SeArgs
+  uint32_t read_base;
   uint32_t n;
   uint32_t nw_max;
   uint32_t ag;
@@ -358,7 +369,7 @@ struct PeArgs {
 };
 
 // PairEndMapping (paired.cpp:106-201) for one mate batch + the heap drain (paired.cpp:684-692)
-template <uint32_t WD>
+template <uint32_t WD, bool PACKED>
 __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS_PER_SM)
 pe_map_kernel(const __grid_constant__ PeArgs a) {
   extern __shared__ uint64_t smem[];
@@ -376,16 +387,10 @@ pe_map_kernel(const __grid_constant__ PeArgs a) {
     const uint32_t r = next_read<WD>(a.queue);
     if (r - (threadIdx.x & 31u) / WD >= a.n) break;
     if (r < a.n) {
-      const char* seq;
       uint32_t len;
-      if (a.uniform_len) {
-        len = a.uniform_len; seq = a.seqs + (size_t)r * len;
-      } else {
-        const uint64_t o0 = a.offs[r], o1 = a.offs[r + 1];
-        len = (uint32_t)(o1 - o0); seq = a.seqs + (o0 - a.seq_base);
-      }
+      const char* seq = read_at<PACKED>(a, r, len);
       uint32_t hsize = 0;
-      bool ok = map_read_pe(w, a.ix, a.cv, a.p3, a.cfg, seq, len, a.ag != 0u,
+      bool ok = map_read_pe<HwGroup<WD>, PACKED>(w, a.ix, a.cv, a.p3, a.cfg, seq, len, a.ag != 0u,
                             a.max_mismatches, a.top_k, sc, cached_len, heap, hsize, ctr);
       bad |= !ok;
       if (lane == 0) {
@@ -496,26 +501,42 @@ static int check_pair(walt_engine* e, int ag) {
   return WALT_OK;
 }
 
-static int launch_se(walt_engine* e, const char* d_seqs, const uint64_t* d_offs, uint64_t seq_base, uint32_t n,
-                     uint32_t max_read_len, int ag, uint32_t m, uint32_t b, walt_best* d_out, uint32_t* d_queue,
-                     cudaStream_t st, uint32_t uniform_len = 0) {
-  if (max_read_len > MAX_READ_LEN) return fail(WALT_EINVAL, "read longer than 1024 bases");
-  SeArgs a;
+// one batch (or chunk) of reads resident on the device
+struct ReadSrc {
+  const char* d_seqs;       // ASCII, or 2-bit packed (walt_pack_reads layout)
+  const uint64_t* d_offs;   // n + 1 base offsets; may be NULL if uniform_len
+  uint64_t seq_base;        // offs value of the first read of d_seqs
+  uint32_t uniform_len;     // != 0: all reads have this length (stride addressing)
+  uint32_t read_base;       // packed: index inside the packed buffer of the launch's first read
+  uint32_t max_len;
+  bool packed;
+};
+
+template <class Args>
+static void fill_common(walt_engine* e, Args& a, const ReadSrc& src, uint32_t n, int ag, uint32_t m, uint32_t b,
+                        uint32_t* d_queue) {
   const int base = ag ? WALT_GA10 : WALT_CT00;
   a.ix[0] = e->sub[base].view(base); a.ix[1] = e->sub[base + 1].view(base + 1);
   a.cv = chrom_view(e); a.p3 = e->pow3;
   a.cfg.b = b; a.cfg.literal_all = e->search_mode == 1 ? 1u : 0u;
-  a.seqs = d_seqs; a.offs = d_offs; a.seq_base = seq_base; a.n = n; a.uniform_len = uniform_len;
-  a.nw_max = std::max<uint32_t>(1u, (max_read_len + 31u) / 32u);
-  a.ag = ag ? 1u : 0u; a.max_mismatches = m; a.out = d_out; a.flags = e->d_flags; a.queue = d_queue;
+  a.seqs = src.d_seqs; a.offs = src.d_offs; a.seq_base = src.seq_base; a.n = n; a.uniform_len = src.uniform_len;
+  a.read_base = src.read_base;
+  a.nw_max = std::max<uint32_t>(1u, (src.max_len + 31u) / 32u);
+  a.ag = ag ? 1u : 0u; a.max_mismatches = m; a.flags = e->d_flags; a.queue = d_queue;
   a.counters = e->d_counters;
+}
+
+static int launch_se(walt_engine* e, const ReadSrc& src, uint32_t n, int ag, uint32_t m, uint32_t b, walt_best* d_out,
+                     uint32_t* d_queue, cudaStream_t st) {
+  if (src.max_len > MAX_READ_LEN) return fail(WALT_EINVAL, "read longer than 1024 bases");
+  SeArgs a;
+  fill_common(e, a, src, n, ag, m, b, d_queue);
+  a.out = d_out;
   const uint32_t wd = e->group_width;
   const size_t smem = se_smem_bytes(a.nw_max, wd);
   uint32_t grid = 0;
-  auto kernel = wd == 8u ? se_map_kernel<8> : wd == 16u ? se_map_kernel<16> : se_map_kernel<32>;
-  if (wd == 8u && e->min_blocks == 5) kernel = se_map_kernel<8, 5>;
-  if (wd == 8u && e->min_blocks == 6) kernel = se_map_kernel<8, 6>;
-  if (wd == 8u && e->min_blocks == 8) kernel = se_map_kernel<8, 8>;
+  auto kernel = src.packed ? (wd == 8u ? se_map_kernel<8, true> : wd == 16u ? se_map_kernel<16, true> : se_map_kernel<32, true>)
+                           : (wd == 8u ? se_map_kernel<8, false> : wd == 16u ? se_map_kernel<16, false> : se_map_kernel<32, false>);
   int rc = grid_for(e, kernel, smem, n, wd, &grid);
   if (rc) return rc;
   WALT_CUDA_TRY(cudaMemsetAsync(d_queue, 0, 4, st));
@@ -525,23 +546,17 @@ static int launch_se(walt_engine* e, const char* d_seqs, const uint64_t* d_offs,
   return WALT_OK;
 }
 
-static int launch_pe_mate(walt_engine* e, const char* d_seqs, const uint64_t* d_offs, uint64_t seq_base, uint32_t n,
-                          uint32_t max_read_len, int ag, uint32_t m, uint32_t b, uint32_t top_k, walt_cand* d_ranked,
-                          uint32_t* d_nranked, uint32_t* d_queue, cudaStream_t st, uint32_t uniform_len = 0) {
-  if (max_read_len > MAX_READ_LEN) return fail(WALT_EINVAL, "read longer than 1024 bases");
+static int launch_pe_mate(walt_engine* e, const ReadSrc& src, uint32_t n, int ag, uint32_t m, uint32_t b, uint32_t top_k,
+                          walt_cand* d_ranked, uint32_t* d_nranked, uint32_t* d_queue, cudaStream_t st) {
+  if (src.max_len > MAX_READ_LEN) return fail(WALT_EINVAL, "read longer than 1024 bases");
   PeArgs a;
-  const int base = ag ? WALT_GA10 : WALT_CT00;
-  a.ix[0] = e->sub[base].view(base); a.ix[1] = e->sub[base + 1].view(base + 1);
-  a.cv = chrom_view(e); a.p3 = e->pow3;
-  a.cfg.b = b; a.cfg.literal_all = e->search_mode == 1 ? 1u : 0u;
-  a.seqs = d_seqs; a.offs = d_offs; a.seq_base = seq_base; a.n = n; a.uniform_len = uniform_len;
-  a.nw_max = std::max<uint32_t>(1u, (max_read_len + 31u) / 32u);
-  a.ag = ag ? 1u : 0u; a.max_mismatches = m; a.top_k = top_k; a.ranked = d_ranked; a.n_ranked = d_nranked;
-  a.flags = e->d_flags; a.queue = d_queue; a.counters = e->d_counters;
+  fill_common(e, a, src, n, ag, m, b, d_queue);
+  a.top_k = top_k; a.ranked = d_ranked; a.n_ranked = d_nranked;
   const uint32_t wd = e->group_width;
   const size_t smem = pe_smem_bytes(a.nw_max, top_k, wd);
   uint32_t grid = 0;
-  auto kernel = wd == 8u ? pe_map_kernel<8> : wd == 16u ? pe_map_kernel<16> : pe_map_kernel<32>;
+  auto kernel = src.packed ? (wd == 8u ? pe_map_kernel<8, true> : wd == 16u ? pe_map_kernel<16, true> : pe_map_kernel<32, true>)
+                           : (wd == 8u ? pe_map_kernel<8, false> : wd == 16u ? pe_map_kernel<16, false> : pe_map_kernel<32, false>);
   int rc = grid_for(e, kernel, smem, n, wd, &grid);
   if (rc) return rc;
   WALT_CUDA_TRY(cudaMemsetAsync(d_queue, 0, 4, st));
@@ -625,6 +640,7 @@ int walt_engine_create(walt_engine** out, int device) {
   e->sm_count = prop.multiProcessorCount;
   // undocumented tuning knobs for experiments (defaults are what bench.py measures)
   if (const char* v = getenv("WALT_MIN_BLOCKS")) e->min_blocks = atoi(v);
+  if (const char* v = getenv("WALT_PE_SIDE")) e->pe_side = atoi(v);
   if (const char* v = getenv("WALT_L2_FETCH")) WALT_CUDA_TRY(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(v)));
   uint32_t p = 1;
   for (uint32_t i = 0; i <= MAX_DEPTH; ++i) { e->pow3.v[i] = p; p *= 3u; }
@@ -636,6 +652,9 @@ int walt_engine_create(walt_engine** out, int device) {
     WALT_CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     WALT_CUDA_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
   }
+  WALT_CUDA_TRY(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
+  WALT_CUDA_TRY(cudaEventCreateWithFlags(&e->fork, cudaEventDisableTiming));
+  WALT_CUDA_TRY(cudaEventCreateWithFlags(&e->join, cudaEventDisableTiming));
   *out = e.release();
   return WALT_OK;
 }
@@ -651,6 +670,9 @@ void walt_engine_destroy(walt_engine* e) {
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.done) cudaEventDestroy(s.done);
   }
+  if (e->side_stream) cudaStreamDestroy(e->side_stream);
+  if (e->fork) cudaEventDestroy(e->fork);
+  if (e->join) cudaEventDestroy(e->join);
   cudaFree(e->d_starts); cudaFree(e->d_flags); cudaFree(e->d_counters);
   delete e;
 }
@@ -879,11 +901,19 @@ int walt_engine_map_se_device(walt_engine* e, const void* d_seqs, const void* d_
   if (rc) return rc;
   if ((rc = check_pair(e, ag_wildcard))) return rc;
   if (n == 0) return WALT_OK;
-  return launch_se(e, (const char*)d_seqs, (const uint64_t*)d_offs, 0, n, max_read_len, ag_wildcard, max_mismatches,
-                   b, (walt_best*)d_out, e->d_flags + 1, (cudaStream_t)cuda_stream);
+  e->stats.n_kernel_launches = 0;
+  const ReadSrc src{(const char*)d_seqs, (const uint64_t*)d_offs, 0, 0, 0, max_read_len, false};
+  return launch_se(e, src, n, ag_wildcard, max_mismatches, b, (walt_best*)d_out, e->d_flags + 1, (cudaStream_t)cuda_stream);
 }
 
-int walt_engine_map_se(walt_engine* e, const char* seqs, const uint64_t* offs, uint32_t n, int ag_wildcard,
+// Bytes [*b0, *b1) of a batch buffer that hold reads [r0, r0 + cn): ASCII, or the 2-bit packed
+// form where read j starts at byte (offs[j] >> 2) + j.
+static void chunk_bytes(const uint64_t* offs, uint32_t r0, uint32_t cn, bool packed, uint64_t* b0, uint64_t* b1) {
+  if (packed) { *b0 = (offs[r0] >> 2) + r0; *b1 = (offs[r0 + cn] >> 2) + r0 + cn; }
+  else { *b0 = offs[r0]; *b1 = offs[r0 + cn]; }
+}
+
+static int map_se_host(walt_engine* e, const char* seqs, const uint64_t* offs, uint32_t n, bool packed, int ag_wildcard,
                        uint32_t max_mismatches, uint32_t b, walt_best* out, uint32_t* n_short) {
   if (!e || !offs || (n && (!seqs || !out))) return fail(WALT_EINVAL, "bad argument");
   int rc = ensure_device(e);
@@ -903,7 +933,8 @@ int walt_engine_map_se(walt_engine* e, const char* seqs, const uint64_t* offs, u
     total_short += sc.n_short;
     BatchSlot& s = e->slot[k % N_SLOTS];
     WALT_CUDA_TRY(cudaEventSynchronize(s.done));
-    const uint64_t sb = offs[r0], se = offs[r0 + cn];
+    uint64_t sb, se;
+    chunk_bytes(offs, r0, cn, packed, &sb, &se);
     if ((rc = reserve(&s.d_seqs, &s.seqs_cap, (size_t)(se - sb) + 16u))) return rc;
     if ((rc = reserve_bytes(&s.d_out, &s.out_cap, (size_t)cn * sizeof(walt_best)))) return rc;
     if (se > sb) WALT_CUDA_TRY(cudaMemcpyAsync(s.d_seqs, seqs + sb, se - sb, cudaMemcpyHostToDevice, s.stream));
@@ -911,8 +942,9 @@ int walt_engine_map_se(walt_engine* e, const char* seqs, const uint64_t* offs, u
       if ((rc = reserve(&s.d_offs, &s.offs_cap, (size_t)cn + 1u))) return rc;
       WALT_CUDA_TRY(cudaMemcpyAsync(s.d_offs, offs + r0, ((size_t)cn + 1u) * 8u, cudaMemcpyHostToDevice, s.stream));
     }
-    if ((rc = launch_se(e, s.d_seqs, s.d_offs, sb, cn, sc.max_len, ag_wildcard, max_mismatches, b, (walt_best*)s.d_out,
-                        e->d_flags + 4 + (k % N_SLOTS), s.stream, sc.uniform_len)))
+    const ReadSrc src{s.d_seqs, s.d_offs, offs[r0], sc.uniform_len, 0, sc.max_len, packed};
+    if ((rc = launch_se(e, src, cn, ag_wildcard, max_mismatches, b, (walt_best*)s.d_out, e->d_flags + 4 + (k % N_SLOTS),
+                        s.stream)))
       return rc;
     WALT_CUDA_TRY(cudaMemcpyAsync(out + r0, s.d_out, (size_t)cn * sizeof(walt_best), cudaMemcpyDeviceToHost, s.stream));
     WALT_CUDA_TRY(cudaEventRecord(s.done, s.stream));
@@ -920,6 +952,16 @@ int walt_engine_map_se(walt_engine* e, const char* seqs, const uint64_t* offs, u
   if (n_short) *n_short = 2u * total_short;   // once per strand pass (mapping.cpp:230-232)
   for (auto& s : e->slot) WALT_CUDA_TRY(cudaStreamSynchronize(s.stream));
   return fetch_status(e);
+}
+
+int walt_engine_map_se(walt_engine* e, const char* seqs, const uint64_t* offs, uint32_t n, int ag_wildcard,
+                       uint32_t max_mismatches, uint32_t b, walt_best* out, uint32_t* n_short) {
+  return map_se_host(e, seqs, offs, n, false, ag_wildcard, max_mismatches, b, out, n_short);
+}
+
+int walt_engine_map_se_packed(walt_engine* e, const uint8_t* packed, const uint64_t* offs, uint32_t n, int ag_wildcard,
+                              uint32_t max_mismatches, uint32_t b, walt_best* out, uint32_t* n_short) {
+  return map_se_host(e, (const char*)packed, offs, n, true, ag_wildcard, max_mismatches, b, out, n_short);
 }
 
 // ---- paired end ---------------------------------------------------------------------------
@@ -944,14 +986,26 @@ static PeScratch carve_pe(void* base, uint32_t cn, uint32_t top_k) {
 }
 
 // both mate kernels + the pairing kernel for one chunk resident on the device
-static int launch_pe_chunk(walt_engine* e, const char* d_seqs1, const uint64_t* d_offs1, uint64_t sb1, uint32_t ulen1,
-                           uint32_t max1, const char* d_seqs2, const uint64_t* d_offs2, uint64_t sb2, uint32_t ulen2,
-                           uint32_t max2, uint32_t cn, uint32_t m, uint32_t b, uint32_t top_k, int frag_range, int swap,
-                           const PeScratch& ps, bool want_pairs, walt_pe_result* d_compact, uint32_t* q, cudaStream_t st) {
+static int launch_pe_chunk(walt_engine* e, const ReadSrc& m1, const ReadSrc& m2, uint32_t cn, uint32_t m, uint32_t b,
+                           uint32_t top_k, int frag_range, int swap, const PeScratch& ps, bool want_pairs,
+                           walt_pe_result* d_compact, uint32_t* q, cudaStream_t st) {
   int rc;
-  // mate 1: C->T against _CT00/_CT01; mate 2: G->A against _GA10/_GA11 (paired.cpp:642-672)
-  if ((rc = launch_pe_mate(e, d_seqs1, d_offs1, sb1, cn, max1, 0, m, b, top_k, ps.r1, ps.n1, q, st, ulen1))) return rc;
-  if ((rc = launch_pe_mate(e, d_seqs2, d_offs2, sb2, cn, max2, 1, m, b, top_k, ps.r2, ps.n2, q + 1, st, ulen2))) return rc;
+  // mate 1: C->T against _CT00/_CT01; mate 2: G->A against _GA10/_GA11 (paired.cpp:642-672).  The
+  // two mate kernels are independent: the second runs on a side stream so that its blocks fill
+  // the SMs the first one's tail (a few repeat-heavy reads) leaves idle.
+  cudaStream_t st2 = e->pe_side ? e->side_stream : st;
+  if (e->pe_side) {
+    WALT_CUDA_TRY(cudaEventRecord(e->fork, st));
+    WALT_CUDA_TRY(cudaStreamWaitEvent(st2, e->fork, 0));
+  }
+  if ((rc = launch_pe_mate(e, m1, cn, 0, m, b, top_k, ps.r1, ps.n1, q, st))) return rc;
+  if ((rc = launch_pe_mate(e, m2, cn, 1, m, b, top_k, ps.r2, ps.n2, q + 1, st2))) return rc;
+  if (e->pe_side) {
+    WALT_CUDA_TRY(cudaEventRecord(e->join, st2));
+    WALT_CUDA_TRY(cudaStreamWaitEvent(st, e->join, 0));
+  }
+  const uint64_t* d_offs1 = m1.d_offs; const uint64_t* d_offs2 = m2.d_offs;
+  const uint32_t ulen1 = m1.uniform_len, ulen2 = m2.uniform_len;
   PairArgs a;
   a.cv = chrom_view(e);
   a.r1 = ps.r1; a.n1 = ps.n1; a.offs1 = d_offs1; a.ulen1 = ulen1;
@@ -968,8 +1022,8 @@ static int launch_pe_chunk(walt_engine* e, const char* d_seqs1, const uint64_t* 
 // compact per-pair summary (compact != NULL) travel back.  Under PBAT the caller has already
 // exchanged the mates; `swap` makes the pairing kernel hand the per-mate fields back.
 static int map_pe_host(walt_engine* e, const char* seqs1, const uint64_t* offs1, const char* seqs2, const uint64_t* offs2,
-                       uint32_t n, uint32_t m, uint32_t b, uint32_t top_k, int frag_range, int swap, walt_cand* ranked1,
-                       uint32_t* n_ranked1, walt_cand* ranked2, uint32_t* n_ranked2, walt_pair* pairs,
+                       uint32_t n, bool packed, uint32_t m, uint32_t b, uint32_t top_k, int frag_range, int swap,
+                       walt_cand* ranked1, uint32_t* n_ranked1, walt_cand* ranked2, uint32_t* n_ranked2, walt_pair* pairs,
                        walt_pe_result* compact, uint32_t* n_short1, uint32_t* n_short2) {
   int rc;
   e->stats = walt_stats{};
@@ -988,7 +1042,9 @@ static int map_pe_host(walt_engine* e, const char* seqs1, const uint64_t* offs1,
     short1 += s1.n_short; short2 += s2.n_short;
     BatchSlot& s = e->slot[k % N_SLOTS];
     WALT_CUDA_TRY(cudaEventSynchronize(s.done));
-    const uint64_t sb1 = offs1[r0], se1 = offs1[r0 + cn], sb2 = offs2[r0], se2 = offs2[r0 + cn];
+    uint64_t sb1, se1, sb2, se2;
+    chunk_bytes(offs1, r0, cn, packed, &sb1, &se1);
+    chunk_bytes(offs2, r0, cn, packed, &sb2, &se2);
     if ((rc = reserve(&s.d_seqs, &s.seqs_cap, (size_t)(se1 - sb1) + 16u))) return rc;
     if ((rc = reserve(&s.d_seqs2, &s.seqs2_cap, (size_t)(se2 - sb2) + 16u))) return rc;
     if ((rc = reserve_bytes(&s.d_pe, &s.pe_cap, pe_scratch_bytes(cn, top_k)))) return rc;
@@ -1004,8 +1060,9 @@ static int map_pe_host(walt_engine* e, const char* seqs1, const uint64_t* offs1,
       WALT_CUDA_TRY(cudaMemcpyAsync(s.d_offs2, offs2 + r0, ((size_t)cn + 1u) * 8u, cudaMemcpyHostToDevice, s.stream));
     }
     uint32_t* q = e->d_flags + 4 + N_SLOTS + 2u * (k % N_SLOTS);
-    if ((rc = launch_pe_chunk(e, s.d_seqs, s.d_offs, sb1, s1.uniform_len, s1.max_len, s.d_seqs2, s.d_offs2, sb2,
-                              s2.uniform_len, s2.max_len, cn, m, b, top_k, frag_range, swap, ps, pairs != nullptr,
+    const ReadSrc m1{s.d_seqs, s.d_offs, offs1[r0], s1.uniform_len, 0, s1.max_len, packed};
+    const ReadSrc m2{s.d_seqs2, s.d_offs2, offs2[r0], s2.uniform_len, 0, s2.max_len, packed};
+    if ((rc = launch_pe_chunk(e, m1, m2, cn, m, b, top_k, frag_range, swap, ps, pairs != nullptr,
                               compact ? ps.compact : nullptr, q, s.stream)))
       return rc;
     if (ranked1) {
@@ -1045,23 +1102,38 @@ int walt_engine_map_pe(walt_engine* e, const char* seqs1, const uint64_t* offs1,
   // PBAT swaps the bisulfite roles of the mates: run the directional protocol with the mates
   // exchanged and hand every per-mate result back to its owner.
   if (pbat)
-    return map_pe_host(e, seqs2, offs2, seqs1, offs1, n, max_mismatches, b, top_k, frag_range, 1, ranked2, n_ranked2,
+    return map_pe_host(e, seqs2, offs2, seqs1, offs1, n, false, max_mismatches, b, top_k, frag_range, 1, ranked2, n_ranked2,
                        ranked1, n_ranked1, pairs, nullptr, n_short2, n_short1);
-  return map_pe_host(e, seqs1, offs1, seqs2, offs2, n, max_mismatches, b, top_k, frag_range, 0, ranked1, n_ranked1,
+  return map_pe_host(e, seqs1, offs1, seqs2, offs2, n, false, max_mismatches, b, top_k, frag_range, 0, ranked1, n_ranked1,
                      ranked2, n_ranked2, pairs, nullptr, n_short1, n_short2);
+}
+
+static int map_pe_compact(walt_engine* e, const char* seqs1, const uint64_t* offs1, const char* seqs2, const uint64_t* offs2,
+                          uint32_t n, bool packed, uint32_t max_mismatches, uint32_t b, uint32_t top_k, int frag_range,
+                          int pbat, walt_pe_result* out, uint32_t* n_short1, uint32_t* n_short2) {
+  if (!e || !offs1 || !offs2 || (n && (!seqs1 || !seqs2 || !out))) return fail(WALT_EINVAL, "bad argument");
+  int rc = check_pe_args(e, top_k);
+  if (rc) return rc;
+  if (pbat)
+    return map_pe_host(e, seqs2, offs2, seqs1, offs1, n, packed, max_mismatches, b, top_k, frag_range, 1, nullptr, nullptr,
+                       nullptr, nullptr, nullptr, out, n_short2, n_short1);
+  return map_pe_host(e, seqs1, offs1, seqs2, offs2, n, packed, max_mismatches, b, top_k, frag_range, 0, nullptr, nullptr,
+                     nullptr, nullptr, nullptr, out, n_short1, n_short2);
 }
 
 int walt_engine_map_pe_compact(walt_engine* e, const char* seqs1, const uint64_t* offs1, const char* seqs2,
                                const uint64_t* offs2, uint32_t n, uint32_t max_mismatches, uint32_t b, uint32_t top_k,
                                int frag_range, int pbat, walt_pe_result* out, uint32_t* n_short1, uint32_t* n_short2) {
-  if (!e || !offs1 || !offs2 || (n && (!seqs1 || !seqs2 || !out))) return fail(WALT_EINVAL, "bad argument");
-  int rc = check_pe_args(e, top_k);
-  if (rc) return rc;
-  if (pbat)
-    return map_pe_host(e, seqs2, offs2, seqs1, offs1, n, max_mismatches, b, top_k, frag_range, 1, nullptr, nullptr,
-                       nullptr, nullptr, nullptr, out, n_short2, n_short1);
-  return map_pe_host(e, seqs1, offs1, seqs2, offs2, n, max_mismatches, b, top_k, frag_range, 0, nullptr, nullptr, nullptr,
-                     nullptr, nullptr, out, n_short1, n_short2);
+  return map_pe_compact(e, seqs1, offs1, seqs2, offs2, n, false, max_mismatches, b, top_k, frag_range, pbat, out, n_short1,
+                        n_short2);
+}
+
+int walt_engine_map_pe_compact_packed(walt_engine* e, const uint8_t* packed1, const uint64_t* offs1, const uint8_t* packed2,
+                                      const uint64_t* offs2, uint32_t n, uint32_t max_mismatches, uint32_t b,
+                                      uint32_t top_k, int frag_range, int pbat, walt_pe_result* out, uint32_t* n_short1,
+                                      uint32_t* n_short2) {
+  return map_pe_compact(e, (const char*)packed1, offs1, (const char*)packed2, offs2, n, true, max_mismatches, b, top_k,
+                        frag_range, pbat, out, n_short1, n_short2);
 }
 
 int walt_engine_map_pe_device(walt_engine* e, const void* d_seqs1, const void* d_offs1, const void* d_seqs2,
@@ -1072,21 +1144,28 @@ int walt_engine_map_pe_device(walt_engine* e, const void* d_seqs1, const void* d
   if (rc) return rc;
   if (max_read_len > MAX_READ_LEN) return fail(WALT_EINVAL, "read longer than 1024 bases");
   cudaStream_t st = (cudaStream_t)cuda_stream;
+  e->stats.n_kernel_launches = 0;
   const char* s1 = (const char*)(pbat ? d_seqs2 : d_seqs1);
   const char* s2 = (const char*)(pbat ? d_seqs1 : d_seqs2);
   const uint64_t* o1 = (const uint64_t*)(pbat ? d_offs2 : d_offs1);
   const uint64_t* o2 = (const uint64_t*)(pbat ? d_offs1 : d_offs2);
-  // ranked lists live in engine scratch, one chunk at a time (stream-ordered reuse)
-  const uint32_t chunk = std::max<uint32_t>(1024u, (uint32_t)std::min<uint64_t>(n, (1ull << 30) / (2ull * top_k * 12ull)));
+  // ranked lists live in engine scratch, one chunk at a time (stream-ordered reuse); the chunk is
+  // as large as a quarter of the free HBM allows (1..8 GiB): every launch ends in a tail of a few
+  // repeat-heavy reads, so fewer, larger launches are faster
   BatchSlot& s = e->slot[0];
   WALT_CUDA_TRY(cudaStreamSynchronize(s.stream));
+  size_t free_b = 0, total_b = 0;
+  WALT_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+  const uint64_t budget = std::max<uint64_t>(s.pe_cap, std::min<uint64_t>(8ull << 30, std::max<uint64_t>(1ull << 30, free_b / 4)));
+  const uint32_t chunk = std::max<uint32_t>(1024u, (uint32_t)std::min<uint64_t>(n, budget / (2ull * top_k * 12ull + 128ull)));
   if ((rc = reserve_bytes(&s.d_pe, &s.pe_cap, pe_scratch_bytes(chunk, top_k)))) return rc;
   for (uint32_t r0 = 0; r0 < n; r0 += chunk) {
     const uint32_t cn = std::min<uint32_t>(chunk, n - r0);
     const PeScratch ps = carve_pe(s.d_pe, cn, top_k);
     // absolute offsets: read r of the chunk is global read r0 + r, addressed from the buffer start
-    if ((rc = launch_pe_chunk(e, s1, o1 + r0, 0, 0, max_read_len, s2, o2 + r0, 0, 0, max_read_len, cn, max_mismatches, b,
-                              top_k, frag_range, pbat, ps, false, (walt_pe_result*)d_out + r0, e->d_flags + 4 + N_SLOTS, st)))
+    const ReadSrc m1{s1, o1 + r0, 0, 0, r0, max_read_len, false}, m2{s2, o2 + r0, 0, 0, r0, max_read_len, false};
+    if ((rc = launch_pe_chunk(e, m1, m2, cn, max_mismatches, b, top_k, frag_range, pbat, ps, false,
+                              (walt_pe_result*)d_out + r0, e->d_flags + 4 + N_SLOTS, st)))
       return rc;
   }
   return WALT_OK;

@@ -74,6 +74,9 @@ struct walt_engine {
   uint32_t group_width = 8;   // lanes that own one read (8, 16 or 32)
   uint32_t chunk_reads = 1u << 18;
   waltb200::BatchSlot slot[waltb200::N_SLOTS];
+  cudaStream_t side_stream = nullptr;        // second mate kernel of a paired-end chunk
+  cudaEvent_t fork = nullptr, join = nullptr;
+  int pe_side = 1;                           // 0: both mate kernels on the caller's stream
   uint32_t* d_flags = nullptr;               // [0] non-ACGT flag, [1] work-queue head, [2..3] spare,
                                              // [4..4+N_SLOTS) SE chunk queues, then 2 per slot for PE
   unsigned long long* d_counters = nullptr;  // lookups, candidates, literal

@@ -225,6 +225,18 @@ class Engine:
                                               C.c_uint32(m), C.c_uint32(b), _p(out), C.byref(short)))
         return out, short.value
 
+    def map_se_packed(self, packed, offs, ag=False, m=6, b=5000, out=None):
+        """map_se on a 2-bit packed batch (walt_b200.host.pack_reads_2bit); offs are base offsets."""
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        n = offs.size - 1
+        if out is None:
+            out = np.zeros(n, dtype=BEST_DT)
+        short = C.c_uint32()
+        self._check(self.L.walt_engine_map_se_packed(self.h, _p(packed), _p(offs), C.c_uint32(n), C.c_int(int(ag)),
+                                                     C.c_uint32(m), C.c_uint32(b), _p(out), C.byref(short)))
+        return out, short.value
+
     def map_se_device(self, d_seqs, d_offs, n, max_read_len, d_out, ag=False, m=6, b=5000, stream=0):
         """Kernel-only path: all pointers are device addresses (ints)."""
         self._check(self.L.walt_engine_map_se_device(self.h, C.c_void_p(d_seqs), C.c_void_p(d_offs),
@@ -269,6 +281,24 @@ class Engine:
                                                       C.c_uint32(m), C.c_uint32(b), C.c_uint32(top_k),
                                                       C.c_int(frag_range), C.c_int(int(pbat)), _p(out),
                                                       C.byref(s1), C.byref(s2)))
+        return out, s1.value, s2.value
+
+    def map_pe_compact_packed(self, packed1, offs1, packed2, offs2, m=6, b=5000, top_k=50, frag_range=1000, pbat=False,
+                              out=None):
+        """map_pe_compact on 2-bit packed mates (walt_b200.host.pack_reads_2bit)."""
+        packed1 = np.ascontiguousarray(packed1, dtype=np.uint8)
+        packed2 = np.ascontiguousarray(packed2, dtype=np.uint8)
+        offs1 = np.ascontiguousarray(offs1, dtype=np.uint64)
+        offs2 = np.ascontiguousarray(offs2, dtype=np.uint64)
+        n = offs1.size - 1
+        assert offs2.size - 1 == n
+        if out is None:
+            out = np.zeros(n, dtype=PE_RESULT_DT)
+        s1, s2 = C.c_uint32(), C.c_uint32()
+        self._check(self.L.walt_engine_map_pe_compact_packed(self.h, _p(packed1), _p(offs1), _p(packed2), _p(offs2),
+                                                             C.c_uint32(n), C.c_uint32(m), C.c_uint32(b),
+                                                             C.c_uint32(top_k), C.c_int(frag_range), C.c_int(int(pbat)),
+                                                             _p(out), C.byref(s1), C.byref(s2)))
         return out, s1.value, s2.value
 
     def map_pe_device(self, d_seqs1, d_offs1, d_seqs2, d_offs2, n, max_read_len, d_out, m=6, b=5000, top_k=50,

@@ -34,6 +34,8 @@ def load_library():
         L.walt_batch_size.restype = C.c_uint32
         L.walt_chroms_count.restype = C.c_uint32
         L.walt_clip_adaptor.restype = C.c_size_t
+        L.walt_packed_reads_bytes.restype = C.c_uint64
+        L.walt_batch_packed.restype = C.c_void_p
         _lib = L
     return _lib
 
@@ -44,6 +46,21 @@ def _err():
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def pack_reads_2bit(buf, offs, out=None):
+    """walt_pack_reads: ASCII batch (buffer + base offsets[n+1]) -> its 2-bit packed form (uint8 array)."""
+    L = load_library()
+    buf = np.ascontiguousarray(buf, np.uint8)
+    offs = np.ascontiguousarray(offs, np.uint64)
+    n = offs.size - 1
+    nbytes = int(L.walt_packed_reads_bytes(_p(offs), C.c_uint32(n)))
+    if out is None:
+        out = np.zeros(nbytes, np.uint8)
+    assert out.size >= nbytes
+    if L.walt_pack_reads(_p(buf), _p(offs), C.c_uint32(n), _p(out)) != 0:
+        raise _err()
+    return out
 
 
 class Chroms:

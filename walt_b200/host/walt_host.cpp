@@ -84,8 +84,9 @@ struct walt_fastq { FILE* f = nullptr; };
 struct walt_batch {
   std::string seqs, quals, names;
   std::vector<uint64_t> seq_off, qual_off, name_off;   // n + 1 each; names/quals NUL-terminated copies
+  std::vector<uint8_t> packed;                         // 2-bit form of seqs (walt_batch_packed), built on demand
   uint32_t n = 0;
-  void clear() { seqs.clear(); quals.clear(); names.clear(); seq_off.assign(1, 0); qual_off.assign(1, 0); name_off.assign(1, 0); n = 0; }
+  void clear() { seqs.clear(); quals.clear(); names.clear(); packed.clear(); seq_off.assign(1, 0); qual_off.assign(1, 0); name_off.assign(1, 0); n = 0; }
   const char* seq(uint32_t i) const { return seqs.data() + seq_off[i]; }
   uint32_t seq_len(uint32_t i) const { return (uint32_t)(seq_off[i + 1] - seq_off[i]); }
   const char* qual(uint32_t i) const { return quals.data() + qual_off[i]; }
@@ -459,6 +460,48 @@ int64_t walt_fastq_next_batch(walt_fastq* fq, walt_batch* b, uint32_t max_reads,
   // a trailing partial record leaves bases behind the last committed read: drop them
   b->seqs.resize(b->seq_off.back());
   return b->n;
+}
+
+uint64_t walt_packed_reads_bytes(const uint64_t* offs, uint32_t n) { return (offs[n] >> 2) + n + 16u; }
+
+int walt_pack_reads(const char* seqs, const uint64_t* offs, uint32_t n, uint8_t* out) {
+  if (!offs || !out || (n && !seqs)) return fail("bad argument");
+  // A0 C1 G2 T3 (util.hpp:107-121): bits 1..2 of the ASCII letter, with the upper bit folded in
+  unsigned bad = 0;
+  for (uint32_t j = 0; j < n; ++j) {
+    const char* s = seqs + offs[j];
+    const uint64_t len = offs[j + 1] - offs[j];
+    uint8_t* o = out + (offs[j] >> 2) + j;
+    uint64_t i = 0;
+    for (; i + 4 <= len; i += 4) {
+      unsigned v = 0;
+      for (unsigned t = 0; t < 4; ++t) {
+        const unsigned c = (unsigned char)s[i + t], x = (c >> 1) & 3u, code = x ^ (x >> 1);
+        bad |= (unsigned)("ACGT"[code] != (char)c);
+        v = (v << 2) | code;
+      }
+      *o++ = (uint8_t)v;
+    }
+    if (i < len) {
+      unsigned v = 0, t = 0;
+      for (; i + t < len; ++t) {
+        const unsigned c = (unsigned char)s[i + t], x = (c >> 1) & 3u, code = x ^ (x >> 1);
+        bad |= (unsigned)("ACGT"[code] != (char)c);
+        v |= code << (6u - 2u * t);
+      }
+      *o = (uint8_t)v;
+    }
+  }
+  return bad ? fail("walt_pack_reads: a read holds a byte that is not A/C/G/T") : 0;
+}
+
+const uint8_t* walt_batch_packed(walt_batch* b) {
+  if (!b) return nullptr;
+  if (b->packed.empty()) {
+    b->packed.assign(walt_packed_reads_bytes(b->seq_off.data(), b->n), 0);
+    if (walt_pack_reads(b->seqs.data(), b->seq_off.data(), b->n, b->packed.data()) != 0) { b->packed.clear(); return nullptr; }
+  }
+  return b->packed.data();
 }
 
 uint32_t walt_batch_size(const walt_batch* b) { return b->n; }
