@@ -184,6 +184,7 @@ class Workload:
         self.e.build_from_device_genome(d_fwd.data_ptr(), which=self.which)
         torch.cuda.synchronize()
         self.t_index = time.time() - t0
+        self.build_info = self.e.last_build_info()   # of the last sub-index built
         self.d_reads = torch.empty(self.n * self.rl, dtype=torch.uint8, device=dev)
         self.d_reads2 = None
         # every rank maps its own shard: different read seed per rank
@@ -565,7 +566,9 @@ def run_ours(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": config_dict(args, {"index_build_s": round(wl.t_index, 1), "hbm_index_bytes": e.hbm_bytes(),
                                              "table_depth": [e.subindex_info(w)["depth"] for w in wl.which],
-                                             "group_width": args.group_width}),
+                                             "group_width": args.group_width,
+                                             "index_tie_order": {"rule": "std::sort replay (byte-identical to reference makedb)",
+                                                                 **wl.build_info}}),
                 "clocks": clocks,
                 "e2e": {"value": total / t_e2e, "unit": unit, "h2d_bytes_per_step": int(n * rl * (2 if pe else 1)),
                         "d2h_bytes_per_step": int(wl.out_dt.itemsize * n), "ms_per_step": 1e3 * t_e2e / args.steps,

@@ -194,6 +194,14 @@ int walt_pack_genome_device(int device, const char* sequence /* upper-case ACGT 
 int walt_engine_build_from_device_genome(walt_engine* e, const void* d_packed_genome, uint32_t which_mask);
 int walt_engine_build_from_sequence(walt_engine* e, const char* sequence, uint32_t which_mask);
 
+/* Order of suffixes that compare equal under SortHashTableBucketCMP (reference.cpp:258-288)
+ * in indexes built afterwards: 0 (default) = the order the reference's std::sort leaves them in
+ * (reference.cpp:296-298; libstdc++ introsort replayed per bucket, so the .dbindex files are
+ * byte-identical to the reference makedb's), 1 = ascending position (skips the replay). */
+int walt_engine_set_tie_order(walt_engine* e, int mode);
+/* Of the last sub-index built: slots that tie with their predecessor, buckets replayed. */
+int walt_engine_last_build_info(const walt_engine* e, uint64_t* n_tied_slots, uint64_t* n_buckets_replayed);
+
 /* Export a resident sub-index to host arrays in the reference's in-memory form (what ReadIndex
  * fills, reference.cpp:324-351): converted ASCII genome, counter[4^12+1], index[index_size].
  * Any pointer may be NULL. */

@@ -20,6 +20,15 @@ extern "C" {
 
 const char* walt_host_last_error(void);
 
+/* Host threads used by the loader and the writers (the reference's -t sets its OpenMP mapping
+ * threads, walt.cpp:150; here the mapping is on the GPU and -t sizes the text path instead).
+ * 0 = one per hardware thread (default).  Output bytes do not depend on it. */
+void walt_host_set_threads(unsigned n);
+unsigned walt_host_threads(void);
+/* Tuning/test hook: the smallest piece of a file one loader task scans (default 64 KiB) and the
+ * number of reads one writer task formats (default 8192); 0 restores a default. */
+void walt_host_set_grain(uint32_t chunk_bytes, uint32_t block_reads);
+
 /* ---- chromosome table: ReadIndexHeadInfo (reference.cpp:381-417) -------------------------- */
 typedef struct walt_chroms walt_chroms;
 walt_chroms* walt_chroms_read(const char* dbindex_path);

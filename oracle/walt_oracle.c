@@ -417,14 +417,109 @@ int wo_bucket_cmp(const char* seq, uint32_t n_chr, const uint32_t* start_index, 
   return 0;
 }
 
-static const char* g_sort_seq;
-static const uint32_t* g_sort_starts;
-static uint32_t g_sort_nchr;
-static int sort_cmp(const void* x, const void* y) {
-  uint32_t p1 = *(const uint32_t*)x, p2 = *(const uint32_t*)y;
-  int c = wo_bucket_cmp(g_sort_seq, g_sort_nchr, g_sort_starts, p1, p2);
-  if (c) return c;
-  return p1 < p2 ? -1 : (p1 > p2 ? 1 : 0);
+/* std::sort as GCC 13's libstdc++ implements it (bits/stl_algo.h:1941-1952 __sort ->
+ * __introsort_loop 1918-1936 with median-of-three __unguarded_partition_pivot 1871-1900,
+ * heap-sort fallback 1905-1913 + bits/stl_heap.h:135-147,224-267,340-362,419-427, then
+ * __final_insertion_sort 1792-1866 with threshold 16).  The reference sorts each bucket with it
+ * (reference.cpp:296-298); the sort is unstable, so the order of suffixes that compare equal
+ * in the .dbindex file is a product of this exact sequence of compares and swaps applied to the
+ * bucket's initial ascending-position arrangement.  Restated here so that the oracle's index
+ * is the reference's index byte for byte (third-party algorithm). */
+typedef struct { const char* seq; const uint32_t* starts; uint32_t n_chr; } sort_ctx;
+static int sl(const sort_ctx* c, uint32_t a, uint32_t b) {   /* SortHashTableBucketCMP(a, b) */
+  return wo_bucket_cmp(c->seq, c->n_chr, c->starts, a, b) < 0;
+}
+static void ss_swap(uint32_t* v, long a, long b) { uint32_t t = v[a]; v[a] = v[b]; v[b] = t; }
+
+static void ss_push_heap(const sort_ctx* c, uint32_t* v, long hole, long top, uint32_t value) {
+  long parent = (hole - 1) / 2;
+  while (hole > top && sl(c, v[parent], value)) { v[hole] = v[parent]; hole = parent; parent = (hole - 1) / 2; }
+  v[hole] = value;
+}
+static void ss_adjust_heap(const sort_ctx* c, uint32_t* v, long hole, long len, uint32_t value) {
+  const long top = hole;
+  long child = hole;
+  while (child < (len - 1) / 2) {
+    child = 2 * (child + 1);
+    if (sl(c, v[child], v[child - 1])) child--;
+    v[hole] = v[child]; hole = child;
+  }
+  if ((len & 1) == 0 && child == (len - 2) / 2) {
+    child = 2 * (child + 1);
+    v[hole] = v[child - 1]; hole = child - 1;
+  }
+  ss_push_heap(c, v, hole, top, value);
+}
+static void ss_heap_sort(const sort_ctx* c, uint32_t* v, long len) {   /* __partial_sort(f, l, l) */
+  if (len >= 2)
+    for (long parent = (len - 2) / 2;; --parent) {
+      ss_adjust_heap(c, v, parent, len, v[parent]);
+      if (parent == 0) break;
+    }
+  for (long last = len; last > 1;) {   /* __sort_heap: __pop_heap(first, last, last) */
+    --last;
+    uint32_t value = v[last];
+    v[last] = v[0];
+    ss_adjust_heap(c, v, 0, last, value);
+  }
+}
+static void ss_linear_insert(const sort_ctx* c, uint32_t* v, long last) {   /* unguarded */
+  uint32_t val = v[last];
+  long next = last - 1;
+  while (sl(c, val, v[next])) { v[last] = v[next]; last = next; --next; }
+  v[last] = val;
+}
+static void ss_insertion_sort(const sort_ctx* c, uint32_t* v, long first, long last) {
+  if (first == last) return;
+  for (long i = first + 1; i != last; ++i) {
+    if (sl(c, v[i], v[first])) {
+      uint32_t val = v[i];
+      memmove(v + first + 1, v + first, sizeof(uint32_t) * (size_t)(i - first));
+      v[first] = val;
+    } else {
+      ss_linear_insert(c, v, i);
+    }
+  }
+}
+static void ss_introsort_loop(const sort_ctx* c, uint32_t* v, long first, long last, long depth_limit) {
+  while (last - first > 16) {
+    if (depth_limit == 0) { ss_heap_sort(c, v + first, last - first); return; }
+    --depth_limit;
+    /* __move_median_to_first(first, first + 1, mid, last - 1) */
+    long a = first + 1, b = first + (last - first) / 2, d = last - 1;
+    if (sl(c, v[a], v[b])) {
+      if (sl(c, v[b], v[d])) ss_swap(v, first, b);
+      else if (sl(c, v[a], v[d])) ss_swap(v, first, d);
+      else ss_swap(v, first, a);
+    } else if (sl(c, v[a], v[d])) ss_swap(v, first, a);
+    else if (sl(c, v[b], v[d])) ss_swap(v, first, d);
+    else ss_swap(v, first, b);
+    /* __unguarded_partition(first + 1, last, pivot = first) */
+    long lo = first + 1, hi = last;
+    for (;;) {
+      while (sl(c, v[lo], v[first])) ++lo;
+      --hi;
+      while (sl(c, v[first], v[hi])) --hi;
+      if (!(lo < hi)) break;
+      ss_swap(v, lo, hi);
+      ++lo;
+    }
+    ss_introsort_loop(c, v, lo, last, depth_limit);
+    last = lo;
+  }
+}
+void wo_std_sort_bucket(const char* seq, uint32_t n_chr, const uint32_t* start_index, uint32_t* v, uint32_t n) {
+  if (n == 0) return;
+  sort_ctx c = {seq, start_index, n_chr};
+  long lg = 0;
+  for (uint32_t x = n; x > 1; x >>= 1) ++lg;
+  ss_introsort_loop(&c, v, 0, (long)n, 2 * lg);
+  if (n > 16) {
+    ss_insertion_sort(&c, v, 0, 16);
+    for (long i = 16; i != (long)n; ++i) ss_linear_insert(&c, v, i);
+  } else {
+    ss_insertion_sort(&c, v, 0, (long)n);
+  }
 }
 
 uint32_t wo_build_index(const char* seq, uint64_t genome_len, uint32_t n_chr,
@@ -460,10 +555,9 @@ uint32_t wo_build_index(const char* seq, uint64_t genome_len, uint32_t n_chr,
   }
   free(cursor); free(erased);
   /* SortHashTableBucket, reference.cpp:290-300 */
-  g_sort_seq = seq; g_sort_starts = start_index; g_sort_nchr = n_chr;
   for (uint32_t k = 0; k < n_keys; ++k) {
     uint32_t n = counter[k + 1] - counter[k];
-    if (n > 1) qsort(index + counter[k], n, sizeof(uint32_t), sort_cmp);
+    if (n > 1) wo_std_sort_bucket(seq, n_chr, start_index, index + counter[k], n);
   }
   return index_size;
 }

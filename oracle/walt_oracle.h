@@ -128,10 +128,13 @@ int wo_fragment_length(const wo_chroms* g, const wo_cand* r1, uint32_t len1, con
 
 /* ---- index builder (makedb), reference.cpp:192-300 ---- */
 /* Build counter/index for an already converted ASCII genome. counter must hold 4^12+1
- * entries; index must hold genome_len entries; returns index_size.  Ties inside a bucket are
- * ordered by ascending position (the reference's std::sort leaves tie order unspecified). */
+ * entries; index must hold genome_len entries; returns index_size.  Every bucket is sorted by
+ * a restatement of libstdc++'s std::sort (wo_std_sort_bucket), so suffixes that compare equal
+ * come out in the order the reference's makedb writes them. */
 uint32_t wo_build_index(const char* seq, uint64_t genome_len, uint32_t n_chr,
                         const uint32_t* start_index, uint32_t* counter, uint32_t* index);
+/* std::sort(v, v + n, SortHashTableBucketCMP(genome)) as GCC 13 libstdc++ executes it */
+void wo_std_sort_bucket(const char* seq, uint32_t n_chr, const uint32_t* start_index, uint32_t* v, uint32_t n);
 /* comparator of SortHashTableBucketCMP (reference.cpp:258-288): <0, 0, >0 */
 int wo_bucket_cmp(const char* seq, uint32_t n_chr, const uint32_t* start_index, uint32_t p1,
                   uint32_t p2);

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../walt_b200/csrc/walt_core.cuh"
+#include "../../walt_b200/csrc/walt_stdsort.cuh"
 
 using namespace waltcore;
 
@@ -456,6 +457,53 @@ void emu_pair(void* h, const emu_cand* r1, const uint32_t* n1, const uint64_t* o
                                    (uint32_t)(offs2[p + 1] - offs2[p]), m, frag_range);
     out[p].best_times = r.best_times; out[p].best_i = r.best_i; out[p].best_j = r.best_j; out[p].frag_len = r.frag;
   }
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// std::sort replay (walt_stdsort.cuh) against the real libstdc++ std::sort
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+// cls[i] is the class rank of the element that starts in slot i (its "position" is i).  Writes
+// the final arrangement of positions under our transcription and under std::sort with the same
+// comparator; returns the number of heap-sort fallbacks our replay took.
+int emu_stdsort_both(const uint32_t* cls, uint32_t n, uint32_t* out_ours, uint32_t* out_std) {
+  std::vector<uint32_t> c(cls, cls + n), p(n);
+  for (uint32_t i = 0; i < n; ++i) p[i] = i;
+  const int fb = waltsort::std_sort(waltsort::PairSeq{p.data(), c.data()}, 0, (int64_t)n, waltsort::ByClass());
+  memcpy(out_ours, p.data(), (size_t)n * 4u);
+  std::vector<waltsort::Elem> v(n);
+  for (uint32_t i = 0; i < n; ++i) v[i] = waltsort::Elem{i, cls[i]};
+  std::sort(v.begin(), v.end(), [](const waltsort::Elem& a, const waltsort::Elem& b) { return a.cls < b.cls; });
+  for (uint32_t i = 0; i < n; ++i) out_std[i] = v[i].pos;
+  return fb;
+}
+
+// the builder's "back to ascending position" step: heap sort by position of (pos, cls) pairs
+void emu_heapsort_by_pos(uint32_t* pos, uint32_t* cls, uint32_t n) {
+  waltsort::heap_sort_(waltsort::PairSeq{pos, cls}, 0, (int64_t)n, waltsort::ByPos());
+}
+
+// McIlroy's adversary ("A killer adversary for quicksort", 1999) run against the real std::sort:
+// produces a permutation of 0..n-1 on which median-of-three introsort degenerates, so that the
+// depth limit is hit and the heap-sort fallback of the replay gets exercised.
+void emu_antiqsort(uint32_t n, uint32_t* out_vals) {
+  std::vector<int> val(n, (int)n);   // n == "gas"
+  std::vector<uint32_t> ptr(n);
+  for (uint32_t i = 0; i < n; ++i) ptr[i] = i;
+  int nsolid = 0, candidate = 0;
+  const int gas = (int)n;
+  std::sort(ptr.begin(), ptr.end(), [&](uint32_t x, uint32_t y) {
+    if (val[x] == gas && val[y] == gas) {
+      if ((int)x == candidate) val[x] = nsolid++; else val[y] = nsolid++;
+    }
+    if (val[x] == gas) candidate = (int)x;
+    else if (val[y] == gas) candidate = (int)y;
+    return val[x] < val[y];
+  });
+  for (uint32_t i = 0; i < n; ++i) out_vals[i] = (uint32_t)(val[i] == gas ? nsolid++ : val[i]);
 }
 
 }  // extern "C"

@@ -131,11 +131,21 @@ def test_cli_errors(dbindex, tmp_path):
 
 
 @pytest.mark.reference
-def test_makedb_matches_reference_makedb(tmp_path):
+@pytest.mark.parametrize("divergence", [0.02, 0.0])
+def test_makedb_matches_reference_makedb(tmp_path, divergence):
+    """All five files of the index byte-identical to the reference makedb's, including the order
+    of tied suffixes inside a bucket (exact repeats when divergence is 0, chromosome ends that
+    look alike): the device builder replays libstdc++'s std::sort (walt_stdsort.cuh)."""
     if not refio.have_reference():
         pytest.skip("oracle/_ref not built")
     chroms = synth.make_repeat_genome([120000, 70000, 500, 30], seed=41, n_families=5, fam_len=(200, 900),
-                                      copies=(3, 20), divergence=0.02, repeat_frac=0.2)
+                                      copies=(3, 20), divergence=divergence, repeat_frac=0.2)
+    chroms[1][1][-300:] = chroms[0][1][-300:]      # suffixes cut by a chromosome end tie as well
+    chroms[2][1][:] = chroms[0][1][-500:]
+    if divergence == 0.0:                          # one large class: 400 copies of a 250-mer
+        unit = chroms[0][1][5000:5250].copy()
+        for k in range(400):
+            chroms[0][1][10000 + 260 * k: 10000 + 260 * k + 250] = unit
     fa = str(tmp_path / "g.fa")
     synth.write_fasta(fa, chroms)
     ours, ref = str(tmp_path / "ours.dbindex"), str(tmp_path / "ref.dbindex")
@@ -147,29 +157,12 @@ def test_makedb_matches_reference_makedb(tmp_path):
     L = refio.oracle_lib()
     import ctypes as C
     starts = np.ascontiguousarray(hdr.start_index, np.uint32)
+    n_ties = 0
     for sfx in refio.SUFFIXES:
-        a = refio.read_subindex(ours + sfx, hdr.genome_len)
         b = refio.read_subindex(ref + sfx, hdr.genome_len)
-        assert a.strand == b.strand and np.array_equal(a.seq, b.seq) and np.array_equal(a.counter, b.counter)
-        assert a.index.size == b.index.size
-        diff = np.nonzero(a.index != b.index)[0]
-        for i in diff:   # only ties of the bucket order may differ (unstable std::sort in the reference)
-            assert L.wo_bucket_cmp(b.seq.ctypes.data_as(C.c_void_p), C.c_uint32(len(hdr.lengths)),
-                                   starts.ctypes.data_as(C.c_void_p), C.c_uint32(int(a.index[i])),
-                                   C.c_uint32(int(b.index[i]))) == 0
-        assert np.array_equal(np.sort(a.index), np.sort(b.index))
-    # and the reference maps identically on either index
-    reads = synth.simulate_se_reads(chroms[:2], 400, 100, seed=5, n_frac=0.0)
-    fq = str(tmp_path / "r.fastq")
-    synth.write_fastq(fq, reads)
-    o1, o2 = str(tmp_path / "o1.sam"), str(tmp_path / "o2.sam")
-    refio.ref_walt(["-i", ours, "-r", fq, "-o", o1, "-sam", "-u", "-a"])
-    refio.ref_walt(["-i", ref, "-r", fq, "-o", o2, "-sam", "-u", "-a"])
-    # ... except for WHICH of several equal-best positions an ambiguous read reports: that follows
-    # the order of tied suffixes, which the reference's unstable std::sort leaves unspecified
-    def unambiguous(path):
-        return [l for l in open(path, "rb").read().split(b"\n")
-                if l and (l.startswith(b"@") or not int(l.split(b"\t")[1]) & 0x100)]
-    a1, a2 = unambiguous(o1), unambiguous(o2)
-    assert a1 == a2 and len(a1) > 300
-    assert open(o1 + ".mapstats", "rb").read() == open(o2 + ".mapstats", "rb").read()
+        for i in range(0, b.index.size - 1, 5):
+            n_ties += L.wo_bucket_cmp(b.seq.ctypes.data_as(C.c_void_p), C.c_uint32(len(hdr.lengths)),
+                                      starts.ctypes.data_as(C.c_void_p), C.c_uint32(int(b.index[i])),
+                                      C.c_uint32(int(b.index[i + 1]))) == 0
+        assert open(ours + sfx, "rb").read() == open(ref + sfx, "rb").read(), sfx
+    assert n_ties > 0, "no tied suffixes in this genome: the tie order is untested"

@@ -214,7 +214,9 @@ def test_se_fresh_genome_vs_oracle():
 def test_device_makedb_matches_oracle_builder():
     """walt_engine_build_from_sequence (makedb on the GPU) against the oracle's restatement of
     CountBucketSize/HashToBucket/SortHashTableBucket: same converted genomes, same counter[],
-    same index[] (ties by ascending position in both), then mapping parity on top of it."""
+    same index[] -- tied suffixes (the genome has exact repeats) in std::sort's order in both: the
+    oracle runs its C restatement of libstdc++'s introsort with the genome comparator, the device
+    radix-sorts and replays the introsort on class ranks -- then mapping parity on top of it."""
     import walt_b200
     lengths = [300000, 180000, 36, 37, 120, 35, 60000]
     chroms = synth.make_repeat_genome(lengths, seed=303, n_families=8, fam_len=(200, 1200),
@@ -223,12 +225,29 @@ def test_device_makedb_matches_oracle_builder():
     e = walt_b200.Engine(0)
     e.set_chromosomes(hdr.lengths, hdr.names)
     e.build_from_sequence(np.concatenate([s for _, s in chroms]))
+    info = e.last_build_info()
+    assert info["tied_slots"] > 0 and info["buckets_replayed"] > 0, info
+    by_std_sort = {}
     for w, sfx in enumerate(refio.SUFFIXES):
         seq, counter, index = e.export_subindex(w, hdr.genome_len)
         assert np.array_equal(seq, subs[sfx].seq), sfx
         assert np.array_equal(counter, subs[sfx].counter), sfx
         assert index.size == subs[sfx].index.size
         assert np.array_equal(index, subs[sfx].index), sfx
+        by_std_sort[sfx] = (counter, index)
+    # tie order 1 = ascending position: same buckets, same classes, ties ascending
+    e2 = walt_b200.Engine(0)
+    e2.set_chromosomes(hdr.lengths, hdr.names)
+    e2.set_tie_order(True)
+    e2.build_from_sequence(np.concatenate([s for _, s in chroms]), which=(0,))
+    assert e2.last_build_info()["buckets_replayed"] == 0
+    _, counter, index = e2.export_subindex(0, hdr.genome_len, want_seq=False)
+    ref_counter, ref_index = by_std_sort["_CT00"]
+    assert np.array_equal(counter, ref_counter) and not np.array_equal(index, ref_index)
+    for k in np.nonzero(np.diff(counter.astype(np.int64)) > 1)[0][:20000]:
+        lo, hi = int(counter[k]), int(counter[k + 1])
+        assert np.array_equal(np.sort(index[lo:hi]), np.sort(ref_index[lo:hi]))
+    e2.close()
     reads = synth.simulate_se_reads([chroms[0], chroms[1], chroms[6]], 5000, 100, seed=9, n_frac=0.0)
     want = refio.oracle_se_map(hdr, (subs["_CT00"], subs["_CT01"]), reads)
     buf, offs = refio.pack_reads(reads)

@@ -61,7 +61,8 @@ def test_pe_oracle_matches_reference():
 
 def test_counter_rederivation_matches_oracle_builder():
     """counter[] rebuilt from index[] must equal what the oracle's makedb restatement
-    produces from the converted sequence (and the index must be the same set)."""
+    produces from the converted sequence, and the oracle's index[] must be the reference
+    makedb's byte for byte."""
     hdr, subs = goldenio.genome()
     L = refio.oracle_lib()
     starts = np.ascontiguousarray(hdr.start_index, np.uint32)
@@ -73,11 +74,14 @@ def test_counter_rederivation_matches_oracle_builder():
                              counter.ctypes.data_as(C.c_void_p), index.ctypes.data_as(C.c_void_p))
         assert n == sub.index.size
         assert np.array_equal(counter, sub.counter)
-        # same buckets; inside a bucket the reference's unstable sort may order ties differently
-        assert np.array_equal(np.sort(index[:n]), np.sort(sub.index))
+        # identical, ties included: the oracle replays libstdc++'s std::sort (the golden index came
+        # from the reference makedb and has tied suffixes: exact repeats, look-alike chromosome ends)
+        assert np.array_equal(index[:n], sub.index)
         cmp = L.wo_bucket_cmp
-        mism = np.nonzero(index[:n] != sub.index)[0]
-        for i in mism[:200]:
-            assert cmp(sub.seq.ctypes.data_as(C.c_void_p), C.c_uint32(len(hdr.lengths)),
-                       starts.ctypes.data_as(C.c_void_p), C.c_uint32(int(index[i])),
-                       C.c_uint32(int(sub.index[i]))) == 0
+        a = sub.index[:-1].astype(np.uint32)
+        b = sub.index[1:].astype(np.uint32)
+        ties = 0
+        for i in range(0, a.size, 7):   # a sample of adjacent slots: how many are ties?
+            ties += cmp(sub.seq.ctypes.data_as(C.c_void_p), C.c_uint32(len(hdr.lengths)),
+                        starts.ctypes.data_as(C.c_void_p), C.c_uint32(int(a[i])), C.c_uint32(int(b[i]))) == 0
+        assert ties > 0, "the golden genome no longer has tied suffixes: tie order is untested"

@@ -10,9 +10,12 @@
 // positions ordered by their 60 spaced characters (offsets 1,4,..,178), a character at or
 // beyond the chromosome end comparing lowest.  Here that is four stable LSD radix-sort passes
 // (cub::DeviceRadixSort) over 15-digit base-4 keys recomputed from the packed genome.  Ties
-// (fully equal 60-character keys) come out by ascending position; the reference's unstable
-// std::sort leaves their order unspecified.
+// (fully equal 60-character keys) come out of that by ascending position, which is not what the
+// reference's unstable std::sort leaves behind; buckets that contain ties are therefore
+// finished by replaying libstdc++'s std::sort on the class ranks the radix sort established
+// (walt_stdsort.cuh), one thread per bucket, so the index is the reference's byte for byte.
 #include "walt_engine.cuh"
+#include "walt_stdsort.cuh"
 
 #include <cub/cub.cuh>
 
@@ -116,6 +119,63 @@ __global__ void sort_keys_kernel(const uint64_t* __restrict__ genome, ChromView 
     key = (key << 2) | digit;
   }
   keys[i] = key;
+}
+
+// ---- tie order (walt_stdsort.cuh) ------------------------------------------------------------
+// head[i] = 1 when sorted slot i starts a new equivalence class of SortHashTableBucketCMP
+// (reference.cpp:258-288): its 60 sort digits differ from slot i-1's.  An inclusive scan of head
+// is the class rank.  n_ties counts the slots that continue a class.
+__global__ void tie_head_kernel(const uint64_t* __restrict__ genome, ChromView cv, uint32_t ag,
+                                const uint32_t* __restrict__ pos, uint64_t n, uint32_t* __restrict__ head,
+                                unsigned long long* __restrict__ n_ties) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t differs = 1u;
+  if (i > 0) {
+    const uint32_t a = pos[i - 1u], b = pos[i];
+    const uint32_t avail_a = cv.starts[chrom_of(cv.starts, cv.n_chr, a) + 1u] - a;
+    const uint32_t avail_b = cv.starts[chrom_of(cv.starts, cv.n_chr, b) + 1u] - b;
+    differs = 0u;
+    for (uint32_t d = 0; d < N_SORT_CHARS && !differs; ++d) {
+      const uint32_t off = 3u * d + 1u;
+      const uint32_t da = off < avail_a ? 1u + ternary_digit(packed_base(genome, (uint64_t)a + PAD_BASES + off), ag != 0u) : 0u;
+      const uint32_t db = off < avail_b ? 1u + ternary_digit(packed_base(genome, (uint64_t)b + PAD_BASES + off), ag != 0u) : 0u;
+      differs = da != db ? 1u : 0u;
+    }
+    if (!differs) atomicAdd(n_ties, 1ull);
+  }
+  head[i] = differs;
+}
+
+// counts[k] = size of bucket k (0 if erased) -> an exclusive scan gives the bucket's first slot
+__global__ void kept_counts_kernel(const uint32_t* __restrict__ raw_hist, uint32_t* __restrict__ counts) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > N_KEY12) return;
+  const uint32_t c = k < N_KEY12 ? raw_hist[k] : 0u;
+  counts[k] = c >= BUCKET_ERASE ? 0u : c;
+}
+
+// One thread per 12-mer bucket.  A bucket whose class ranks are all distinct has a unique sorted
+// order and is left alone; otherwise: back to the arrangement HashToBucket produced (ascending
+// position, reference.cpp:231-256), then std::sort's exact sequence of swaps with "class rank
+// less" standing in for the genome comparator.
+__global__ void tie_replay_kernel(const uint32_t* __restrict__ starts, uint32_t* __restrict__ index,
+                                  uint32_t* __restrict__ scratch_pos, uint32_t* __restrict__ cls,
+                                  unsigned long long* __restrict__ n_replayed) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= N_KEY12) return;
+  const uint64_t s = starts[k], e = starts[k + 1u];
+  if (e - s < 2u) return;
+  if ((uint64_t)(cls[e - 1u] - cls[s]) + 1u == e - s) return;
+  uint32_t* p = scratch_pos + s;
+  uint32_t* c = cls + s;
+  const int64_t n = (int64_t)(e - s);
+  for (int64_t i = 0; i < n; ++i) p[i] = index[s + i];
+  const waltsort::PairSeq seq{p, c};
+  waltsort::std_sort(seq, 0, n, waltsort::ByPos());   // positions are distinct: any sort gives this order
+  waltsort::std_sort(seq, 0, n, waltsort::ByClass());
+  for (int64_t i = 0; i < n; ++i) index[s + i] = p[i];
+  atomicAdd(n_replayed, 1ull);
 }
 
 // ---- export helpers --------------------------------------------------------------------------
@@ -314,6 +374,9 @@ static int build_subindex_device(walt_engine* e, int which, const uint64_t* d_fw
   WALT_CUDA_TRY(cudaMalloc(&d_hist, (N_KEY12 + 2u) * 4u));
   WALT_CUDA_TRY(cudaMemset(d_hist, 0, (N_KEY12 + 2u) * 4u));
   key12_hist_kernel<<<blocks_for(e->genome_len, T), T>>>(s.genome, cv, e->pow3, ag, d_hist);
+  uint32_t* d_starts = nullptr;   // bucket sizes now, first slots later (tie replay)
+  WALT_CUDA_TRY(cudaMalloc(&d_starts, (N_KEY12 + 1u) * 4u));
+  kept_counts_kernel<<<blocks_for(N_KEY12 + 1u, T), T>>>(d_hist, d_starts);
   erase_large_kernel<<<blocks_for(N_KEY12, T), T>>>(d_hist, d_hist + N_KEY12 + 1u);
   WALT_CUDA_TRY(cudaGetLastError());
 
@@ -325,7 +388,7 @@ static int build_subindex_device(walt_engine* e, int which, const uint64_t* d_fw
   unsigned long long* d_count = nullptr;
   void* d_temp = nullptr;
   auto cleanup = [&]() {
-    cudaFree(d_hist); cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(d_count); cudaFree(d_temp);
+    cudaFree(d_hist); cudaFree(d_starts); cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(d_count); cudaFree(d_temp);
   };
   for (int i = 0; i < 2; ++i) {
     if (cudaMalloc(&vals[i], (cap + 64u) * 4u) != cudaSuccess || cudaMalloc(&keys[i], (cap + 64u) * 4u) != cudaSuccess) {
@@ -364,6 +427,43 @@ static int build_subindex_device(walt_engine* e, int which, const uint64_t* d_fw
       sort_keys_kernel<<<blocks_for(n, T), T>>>(s.genome, cv, ag, dv.Current(), n, (uint32_t)pass * DIGITS_PER_PASS, dk.Current());
       cudaError_t ce = cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, dk, dv, (uint64_t)n, 0, 2 * DIGITS_PER_PASS);
       if (ce != cudaSuccess) { cleanup(); cudaFree(vals[0]); cudaFree(vals[1]); return fail(WALT_ECUDA, std::string("radix sort: ") + cudaGetErrorString(ce)); }
+    }
+    // tie order: class ranks from the sorted order, then std::sort replayed per bucket with ties
+    e->last_build_ties = 0; e->last_build_replayed = 0;
+    if (n > 1 && e->tie_order == 0) {
+      auto bail = [&](const char* what, cudaError_t ce) {
+        cleanup(); cudaFree(vals[0]); cudaFree(vals[1]);
+        return fail(WALT_ECUDA, std::string(what) + ": " + cudaGetErrorString(ce));
+      };
+      uint32_t* head = dk.Current();
+      unsigned long long* d_ctr = nullptr;
+      if (cudaMalloc(&d_ctr, 16) != cudaSuccess) return bail("cudaMalloc", cudaGetLastError());
+      cudaMemset(d_ctr, 0, 16);
+      tie_head_kernel<<<blocks_for(n, T), T>>>(s.genome, cv, ag, dv.Current(), n, head, d_ctr);
+      unsigned long long ctr[2] = {0, 0};
+      cudaError_t ce = cudaMemcpy(ctr, d_ctr, 16, cudaMemcpyDeviceToHost);
+      if (ce != cudaSuccess) { cudaFree(d_ctr); return bail("tie detection", ce); }
+      if (ctr[0] > 0) {
+        // the sort's temp storage is far larger than a scan's; check anyway
+        size_t need = 0;
+        cub::DeviceScan::InclusiveSum(nullptr, need, head, head, (::cuda::std::int64_t)n);
+        size_t need2 = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, need2, d_starts, d_starts, (int)(N_KEY12 + 1u));
+        need = std::max(need, need2);
+        if (need > temp_bytes) {
+          cudaFree(d_temp); d_temp = nullptr; temp_bytes = need;
+          if (cudaMalloc(&d_temp, temp_bytes) != cudaSuccess) { cudaFree(d_ctr); return bail("cudaMalloc(scan temp)", cudaGetLastError()); }
+        }
+        size_t tb = temp_bytes;
+        cub::DeviceScan::InclusiveSum(d_temp, tb, head, head, (::cuda::std::int64_t)n);
+        tb = temp_bytes;
+        cub::DeviceScan::ExclusiveSum(d_temp, tb, d_starts, d_starts, (int)(N_KEY12 + 1u));
+        tie_replay_kernel<<<blocks_for(N_KEY12, 32), 32>>>(d_starts, dv.Current(), dk.Alternate(), head, d_ctr + 1);
+        ce = cudaMemcpy(ctr, d_ctr, 16, cudaMemcpyDeviceToHost);
+        if (ce != cudaSuccess) { cudaFree(d_ctr); return bail("tie replay", ce); }
+      }
+      cudaFree(d_ctr);
+      e->last_build_ties = ctr[0]; e->last_build_replayed = ctr[1];
     }
     cudaError_t ce = cudaDeviceSynchronize();
     if (ce != cudaSuccess) { cleanup(); cudaFree(vals[0]); cudaFree(vals[1]); return fail(WALT_ECUDA, std::string("index build: ") + cudaGetErrorString(ce)); }

@@ -874,6 +874,19 @@ int walt_engine_set_table_depth(walt_engine* e, int depth) {
   return WALT_OK;
 }
 
+int walt_engine_set_tie_order(walt_engine* e, int mode) {
+  if (!e || (mode != 0 && mode != 1)) return fail(WALT_EINVAL, "tie order must be 0 (std::sort) or 1 (ascending position)");
+  e->tie_order = mode;
+  return WALT_OK;
+}
+
+int walt_engine_last_build_info(const walt_engine* e, uint64_t* n_tied_slots, uint64_t* n_buckets_replayed) {
+  if (!e) return fail(WALT_EINVAL, "bad argument");
+  if (n_tied_slots) *n_tied_slots = e->last_build_ties;
+  if (n_buckets_replayed) *n_buckets_replayed = e->last_build_replayed;
+  return WALT_OK;
+}
+
 int walt_engine_set_group_width(walt_engine* e, uint32_t lanes) {
   if (!e || (lanes != 8u && lanes != 16u && lanes != 32u)) return fail(WALT_EINVAL, "group width must be 8, 16 or 32");
   e->group_width = lanes;

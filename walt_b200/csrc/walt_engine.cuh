@@ -69,6 +69,8 @@ struct walt_engine {
   waltb200::DeviceSubIndex sub[4];
   waltcore::Pow3 pow3;
   int search_mode = 0;
+  int tie_order = 0;          // 0: std::sort's order among equal suffixes, 1: ascending position
+  unsigned long long last_build_ties = 0, last_build_replayed = 0;
   int force_depth = 0;
   int min_blocks = 4;         // resident CTAs per SM the SE kernel is compiled for (register cap)
   uint32_t group_width = 8;   // lanes that own one read (8, 16 or 32)

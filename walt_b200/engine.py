@@ -201,6 +201,15 @@ class Engine:
     def set_table_depth(self, depth):
         self._check(self.L.walt_engine_set_table_depth(self.h, C.c_int(depth)))
 
+    def set_tie_order(self, ascending_position):
+        """False (default): equal suffixes in std::sort's order (byte-identical to reference makedb)."""
+        self._check(self.L.walt_engine_set_tie_order(self.h, C.c_int(1 if ascending_position else 0)))
+
+    def last_build_info(self):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._check(self.L.walt_engine_last_build_info(self.h, C.byref(a), C.byref(b)))
+        return {"tied_slots": int(a.value), "buckets_replayed": int(b.value)}
+
     def set_group_width(self, lanes):
         self._check(self.L.walt_engine_set_group_width(self.h, C.c_uint32(lanes)))
 

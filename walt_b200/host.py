@@ -173,3 +173,13 @@ class PeWriter:
         if self.h and self.L.walt_pe_writer_close(self.h):
             raise _err()
         self.h = None
+
+
+def set_threads(n):
+    """Host threads of the loader / writers (0 = one per hardware thread)."""
+    load_library().walt_host_set_threads(C.c_uint(n))
+
+
+def set_grain(chunk_bytes=0, block_reads=0):
+    """Tuning/test hook: loader task size in bytes and writer task size in reads (0 = default)."""
+    load_library().walt_host_set_grain(C.c_uint32(chunk_bytes), C.c_uint32(block_reads))

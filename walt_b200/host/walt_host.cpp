@@ -9,26 +9,65 @@
 //   GetBestMatch4Single, GetSAMFLAG, OutputPairedSAM, StatPairedReads::tostring
 //                               src/walt/paired.cpp:52-95,210-435,515-569
 // The pairing loop itself and all mapping run on the GPU (walt_engine.cu); nothing here
-// computes alignments.  glibc rand()/srand() are called exactly like the reference does, so
-// the N-replacement stream is identical.
+// computes alignments.  The N-replacement stream is glibc's: random_r on a private state set
+// up by initstate_r(0, ..) yields exactly the srand(0); rand() sequence of mapping.cpp:73 and
+// util.hpp:156-163 (rand() is random_r on glibc's global state), without sharing that global
+// state between the loader threads of the two mate files.
+//
+// At GPU mapping rates the text path is the whole wall clock, so both
+// directions are multi-threaded with an ordered commit: the loader splits the mapped file at
+// line boundaries, the writers format blocks of reads on worker threads while the calling
+// thread appends finished blocks to the output files in input order.
 #include "../../include/walt_host.h"
 
 #include <errno.h>
+#include <fcntl.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <fstream>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <numeric>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
 
 thread_local std::string g_err;
 int fail(const std::string& m) { g_err = m; return -1; }
+
+std::atomic<unsigned> g_threads{0};
+std::atomic<uint32_t> g_chunk_bytes{1u << 16};   // smallest piece of a file one loader task scans
+std::atomic<uint32_t> g_block_reads{8192};       // reads one writer task formats
+unsigned host_threads() {
+  unsigned t = g_threads.load();
+  if (!t) { t = std::thread::hardware_concurrency(); if (!t) t = 1; }
+  return t;
+}
+
+// fn(i) for i in [0, n), handed out dynamically to up to host_threads() threads (the caller's included)
+template <class F>
+void parallel_tasks(size_t n, F&& fn) {
+  const size_t T = std::min<size_t>(host_threads(), n);
+  if (T <= 1) { for (size_t i = 0; i < n; ++i) fn(i); return; }
+  std::atomic<size_t> next{0};
+  auto body = [&]() { for (;;) { const size_t i = next.fetch_add(1); if (i >= n) break; fn(i); } };
+  std::vector<std::thread> th;
+  for (size_t t = 1; t < T; ++t) th.emplace_back(body);
+  body();
+  for (auto& t : th) t.join();
+}
 
 constexpr size_t LINE_CAP = 1000;      // MAX_LINE_LENGTH, util.hpp:43
 constexpr uint32_t MIN_READ_LEN = 38;  // MINIMALREADLEN
@@ -38,26 +77,88 @@ inline char comp(char c) {
   return c;
 }
 
-// buffered text sink
+// complement table (anything but ACGT maps to itself, like complimentBase never sees here)
+struct CompTable {
+  char t[256];
+  CompTable() { for (int i = 0; i < 256; ++i) t[i] = (char)i; t['A'] = 'T'; t['C'] = 'G'; t['G'] = 'C'; t['T'] = 'A'; }
+};
+const CompTable g_comp;
+
+// Text sink: a raw growable buffer in front of a file (or alone: an in-memory block that a
+// worker thread fills and the committing thread appends to the file).  The file offset is kept
+// here and every write is a pwrite at a known offset.
 struct Sink {
-  FILE* f = nullptr;
-  std::string buf;
+  int fd = -1;
+  uint64_t file_off = 0;
+  char* buf = nullptr;
+  size_t n = 0, cap = 0;
+  bool write_failed = false;
+  Sink() = default;
+  Sink(const Sink&) = delete;
+  Sink& operator=(const Sink&) = delete;
+  ~Sink() { if (fd >= 0) ::close(fd); free(buf); }
+  bool is_file() const { return fd >= 0; }
+  // mode "a": behind whatever the file holds (the outputs are created empty by main, walt.cpp:230-233,
+  // and the SAM header / earlier batches are already in them); "w": truncate
   bool open(const std::string& path, const char* mode) {
-    f = fopen(path.c_str(), mode);
-    buf.reserve(1u << 20);
-    return f != nullptr;
+    const bool append = mode[0] == 'a';
+    fd = ::open(path.c_str(), O_WRONLY | O_CREAT | (append ? 0 : O_TRUNC), 0666);
+    if (fd < 0) return false;
+    const off_t end = append ? lseek(fd, 0, SEEK_END) : 0;
+    file_off = end > 0 ? (uint64_t)end : 0;
+    return true;
   }
-  void flush() { if (f && !buf.empty()) { fwrite(buf.data(), 1, buf.size(), f); buf.clear(); } }
-  void maybe_flush() { if (buf.size() > (1u << 20) - 4096) flush(); }
-  void close() { flush(); if (f) fclose(f); f = nullptr; }
-  void str(const char* s, size_t n) { buf.append(s, n); }
-  template <size_t N> void lit(const char (&s)[N]) { buf.append(s, N - 1); }
-  void str(const std::string& s) { buf.append(s); }
-  void ch(char c) { buf.push_back(c); }
-  void u32(uint32_t v) { char t[12]; int n = 0; do { t[n++] = (char)('0' + v % 10); v /= 10; } while (v); while (n) buf.push_back(t[--n]); }
-  void i32(int32_t v) { if (v < 0) { buf.push_back('-'); u32((uint32_t)(-(int64_t)v)); } else u32((uint32_t)v); }
-  void revcomp(const char* s, size_t n) { for (size_t i = n; i-- > 0;) buf.push_back(comp(s[i])); }
-  void rev(const char* s, size_t n) { for (size_t i = n; i-- > 0;) buf.push_back(s[i]); }
+  char* room(size_t k) {   // space for k more bytes
+    if (n + k > cap) {
+      size_t c = cap ? cap * 2 : (1u << 16);
+      while (c < n + k) c *= 2;
+      buf = (char*)realloc(buf, c);
+      cap = c;
+    }
+    return buf + n;
+  }
+  static bool write_all(int fd, const char* p, size_t k, uint64_t off) {
+    while (k) {
+      const ssize_t w = pwrite(fd, p, k, (off_t)off);
+      if (w < 0) { if (errno == EINTR) continue; return false; }
+      p += w; k -= (size_t)w; off += (uint64_t)w;
+    }
+    return true;
+  }
+  void flush() {
+    if (fd >= 0 && n) { if (!write_all(fd, buf, n, file_off)) write_failed = true; file_off += n; n = 0; }
+  }
+  void maybe_flush() { if (fd >= 0 && n > (1u << 20) - 4096) flush(); }   // no file: an in-memory block
+  // a block formatted elsewhere goes behind everything written so far.  (Writes to one file
+  // serialise on the inode lock, so handing them to more threads gains nothing: the committing
+  // thread writes while the worker threads format the following blocks.)
+  void append_block(Sink& block) {
+    if (!block.n) return;
+    if (fd < 0) { memcpy(room(block.n), block.buf, block.n); n += block.n; return; }
+    flush();
+    if (!write_all(fd, block.buf, block.n, file_off)) write_failed = true;
+    file_off += block.n;
+  }
+  bool close() {
+    flush();
+    if (fd >= 0 && ::close(fd) != 0) write_failed = true;
+    fd = -1;
+    return !write_failed;
+  }
+  void str(const char* s, size_t k) { memcpy(room(k), s, k); n += k; }
+  template <size_t N> void lit(const char (&s)[N]) { memcpy(room(N - 1), s, N - 1); n += N - 1; }
+  void str(const std::string& s) { str(s.data(), s.size()); }
+  void ch(char c) { *room(1) = c; ++n; }
+  void u32(uint32_t v) {
+    char t[12]; int k = 0;
+    do { t[k++] = (char)('0' + v % 10); v /= 10; } while (v);
+    char* o = room((size_t)k);
+    for (int i = 0; i < k; ++i) o[i] = t[k - 1 - i];
+    n += (size_t)k;
+  }
+  void i32(int32_t v) { if (v < 0) { ch('-'); u32((uint32_t)(-(int64_t)v)); } else u32((uint32_t)v); }
+  void revcomp(const char* s, size_t k) { char* o = room(k); for (size_t i = 0; i < k; ++i) o[i] = g_comp.t[(unsigned char)s[k - 1 - i]]; n += k; }
+  void rev(const char* s, size_t k) { char* o = room(k); for (size_t i = 0; i < k; ++i) o[i] = s[k - 1 - i]; n += k; }
 };
 
 }  // namespace
@@ -79,19 +180,46 @@ struct walt_chroms {
   }
 };
 
-struct walt_fastq { FILE* f = nullptr; };
+struct walt_fastq {
+  int fd = -1;
+  const char* data = nullptr;   // the whole file: mmap for regular files, a heap copy otherwise
+  size_t size = 0, pos = 0;
+  bool mapped = false;
+  std::vector<char> heap;
+  double bytes_per_line = 90.0; // running estimate, sizes the window scanned for one batch
+};
+
+// uninitialised growable byte buffer (std::string would zero-fill gigabytes on resize)
+struct RawBuf {
+  char* p = nullptr;
+  size_t n = 0, cap = 0;
+  RawBuf() = default;
+  RawBuf(const RawBuf&) = delete;
+  RawBuf& operator=(const RawBuf&) = delete;
+  ~RawBuf() { free(p); }
+  bool size_to(size_t need) {
+    if (need > cap) {
+      free(p);
+      p = (char*)malloc(need + 64);
+      cap = p ? need : 0;
+      if (!p) { n = 0; return false; }
+    }
+    n = need;
+    return true;
+  }
+};
 
 struct walt_batch {
-  std::string seqs, quals, names;
-  std::vector<uint64_t> seq_off, qual_off, name_off;   // n + 1 each; names/quals NUL-terminated copies
-  std::vector<uint8_t> packed;                         // 2-bit form of seqs (walt_batch_packed), built on demand
+  RawBuf seqs, quals, names, packed;                   // names/quals hold NUL-terminated copies
+  std::vector<uint64_t> seq_off, qual_off, name_off;   // n + 1 each
+  bool have_packed = false;                            // 2-bit form of seqs (walt_batch_packed), built on demand
   uint32_t n = 0;
-  void clear() { seqs.clear(); quals.clear(); names.clear(); packed.clear(); seq_off.assign(1, 0); qual_off.assign(1, 0); name_off.assign(1, 0); n = 0; }
-  const char* seq(uint32_t i) const { return seqs.data() + seq_off[i]; }
+  void clear() { seqs.n = quals.n = names.n = packed.n = 0; have_packed = false; seq_off.assign(1, 0); qual_off.assign(1, 0); name_off.assign(1, 0); n = 0; }
+  const char* seq(uint32_t i) const { return seqs.p + seq_off[i]; }
   uint32_t seq_len(uint32_t i) const { return (uint32_t)(seq_off[i + 1] - seq_off[i]); }
-  const char* qual(uint32_t i) const { return quals.data() + qual_off[i]; }
+  const char* qual(uint32_t i) const { return quals.p + qual_off[i]; }
   uint32_t qual_len(uint32_t i) const { return (uint32_t)(qual_off[i + 1] - qual_off[i] - 1); }
-  const char* name(uint32_t i) const { return names.data() + name_off[i]; }
+  const char* name(uint32_t i) const { return names.p + name_off[i]; }
   uint32_t name_len(uint32_t i) const { return (uint32_t)(name_off[i + 1] - name_off[i] - 1); }
 };
 
@@ -135,7 +263,7 @@ struct SingleOut {
     if (unmapped && !sam && !funm.open(prefix + "_unmapped", "w")) return false;
     return true;
   }
-  void close() { famb.close(); funm.close(); }
+  bool close() { const bool a = famb.close(), b = funm.close(); return a && b; }
 };
 
 // OutputUniquelyAndAmbiguousMapped, mapping.cpp:329-349 (seq/qual already oriented)
@@ -213,6 +341,91 @@ void sam_header(Sink& o, const walt_chroms& g) {
 
 }  // namespace
 
+namespace {
+
+// Formats reads [0, n) in blocks on worker threads and commits the blocks in input order on
+// the calling thread, which therefore overlaps the file writes with the formatting.
+//   make()            -> a fresh block-local output (in-memory sinks, zeroed counters)
+//   fmt(block, lo, hi)   formats reads [lo, hi) into it        (worker threads)
+//   commit(block)        appends it to the files / totals      (calling thread, ascending order)
+template <class Block, class Make, class Fmt, class Commit>
+void ordered_blocks(uint32_t n, Make make, Fmt fmt, Commit commit) {
+  const uint32_t BLOCK = g_block_reads.load();
+  const size_t nb = ((size_t)n + BLOCK - 1) / BLOCK;
+  const size_t T = std::min<size_t>(host_threads(), nb);
+  if (T <= 1) {
+    for (size_t k = 0; k < nb; ++k) {
+      std::unique_ptr<Block> bl(make());
+      fmt(*bl, (uint32_t)(k * BLOCK), (uint32_t)std::min<size_t>(n, (k + 1) * BLOCK));
+      commit(*bl);
+    }
+    return;
+  }
+  std::mutex mu;
+  std::condition_variable cv_ready, cv_room;
+  std::map<size_t, std::unique_ptr<Block>> ready;
+  size_t next_commit = 0;
+  std::atomic<size_t> next_task{0};
+  const size_t window = 4 * T;   // blocks formatted ahead of the commit point (bounds memory)
+  std::vector<std::thread> th;
+  for (size_t t = 0; t < T; ++t)
+    th.emplace_back([&]() {
+      for (;;) {
+        const size_t k = next_task.fetch_add(1);
+        if (k >= nb) return;
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          cv_room.wait(lk, [&]() { return k < next_commit + window; });
+        }
+        std::unique_ptr<Block> bl(make());
+        fmt(*bl, (uint32_t)(k * BLOCK), (uint32_t)std::min<size_t>(n, (k + 1) * BLOCK));
+        {
+          std::lock_guard<std::mutex> lk(mu);
+          ready[k] = std::move(bl);
+        }
+        cv_ready.notify_one();
+      }
+    });
+  for (size_t k = 0; k < nb; ++k) {
+    std::unique_ptr<Block> bl;
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv_ready.wait(lk, [&]() { return ready.count(k) != 0; });
+      bl = std::move(ready[k]);
+      ready.erase(k);
+    }
+    commit(*bl);
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      next_commit = k + 1;
+    }
+    cv_room.notify_all();
+  }
+  for (auto& t : th) t.join();
+}
+
+void add_stats(SingleStats& a, const SingleStats& b) {
+  a.total += b.total; a.unique += b.unique; a.ambiguous += b.ambiguous; a.unmapped += b.unmapped; a.n_short += b.n_short;
+}
+// block-local twin of a SingleOut: same flags, in-memory side files, zero counters
+void local_twin(SingleOut& l, const SingleOut& of) { l.ambiguous = of.ambiguous; l.unmapped = of.unmapped; l.sam = of.sam; }
+void commit_twin(SingleOut& to, SingleOut& l) {
+  to.famb.append_block(l.famb); to.funm.append_block(l.funm);
+  add_stats(to.st, l.st);
+}
+
+struct SeBlock { Sink out; SingleOut so; };
+
+// what write_pair touches: the main output, the two mates' side files / counters, pair totals
+struct PeOut {
+  Sink out;
+  SingleOut so1, so2;
+  uint32_t unique_pairs = 0, ambiguous_pairs = 0, unmapped_pairs = 0;
+  std::vector<uint32_t> frag_count;
+};
+
+}  // namespace
+
 struct walt_se_writer {
   const walt_chroms* g = nullptr;
   std::string path;
@@ -227,10 +440,8 @@ struct walt_pe_writer {
   uint32_t m = 6, top_k = 50;
   int frag_range = 1000;
   bool sam = false, pbat = false;
-  Sink out;
-  SingleOut so1, so2;
-  uint32_t total_pairs = 0, unique_pairs = 0, ambiguous_pairs = 0, unmapped_pairs = 0;
-  std::vector<uint32_t> frag_count;
+  PeOut o;                   // the files and the running totals
+  uint32_t total_pairs = 0;
 };
 
 namespace {
@@ -381,22 +592,58 @@ const uint32_t* walt_chroms_lengths(const walt_chroms* c) { return c->lengths.da
 const char* walt_chroms_name(const walt_chroms* c, uint32_t i) { return c->names[i].c_str(); }
 
 // ---- FASTQ ---------------------------------------------------------------------------------
+void walt_host_set_threads(unsigned n) { g_threads.store(n); }
+unsigned walt_host_threads(void) { return host_threads(); }
+void walt_host_set_grain(uint32_t chunk_bytes, uint32_t block_reads) {
+  g_chunk_bytes.store(chunk_bytes ? chunk_bytes : (1u << 16));
+  g_block_reads.store(block_reads ? block_reads : 8192u);
+}
+
 walt_fastq* walt_fastq_open(const char* path) {
-  FILE* f = fopen(path, "r");
-  if (!f) { fail(std::string("cannot open input file ") + path); return nullptr; }
-  static const size_t BUF = 4u << 20;
-  setvbuf(f, nullptr, _IOFBF, BUF);
-  walt_fastq* q = new walt_fastq; q->f = f;
+  const int fd = open(path, O_RDONLY);
+  struct stat st;
+  if (fd < 0 || fstat(fd, &st) != 0 || S_ISDIR(st.st_mode)) {
+    if (fd >= 0) close(fd);
+    fail(std::string("cannot open input file ") + path);
+    return nullptr;
+  }
+  walt_fastq* q = new walt_fastq;
+  q->fd = fd;
+  if (S_ISREG(st.st_mode) && st.st_size > 0) {
+    void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (m != MAP_FAILED) {
+      madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+      q->data = (const char*)m; q->size = (size_t)st.st_size; q->mapped = true;
+    }
+  }
+  if (!q->mapped) {   // pipes, empty files, mmap refused: read it all
+    char tmp[1 << 16];
+    for (;;) {
+      const ssize_t r = read(fd, tmp, sizeof tmp);
+      if (r < 0 && errno == EINTR) continue;
+      if (r <= 0) break;
+      q->heap.insert(q->heap.end(), tmp, tmp + r);
+    }
+    q->data = q->heap.data(); q->size = q->heap.size();
+  }
   return q;
 }
-void walt_fastq_close(walt_fastq* f) { if (f) { if (f->f) fclose(f->f); delete f; } }
+void walt_fastq_close(walt_fastq* f) {
+  if (!f) return;
+  if (f->mapped) munmap((void*)f->data, f->size);
+  if (f->fd >= 0) close(f->fd);
+  delete f;
+}
 walt_batch* walt_batch_create(void) { walt_batch* b = new walt_batch; b->clear(); return b; }
 void walt_batch_free(walt_batch* b) { delete b; }
 
 size_t walt_clip_adaptor(const char* adaptor, char* s, size_t len) {
-  // util.hpp:200-217, including its size_t arithmetic
+  // util.hpp:200-217.  For reads shorter than 13 (5) bases the reference's size_t arithmetic
+  // wraps and its loops run off the end of the string (undefined behaviour, in practice a
+  // crash); here those loops are simply empty.
   const size_t ad_len = strlen(adaptor);
-  const size_t lim1 = len - 14 + 1;
+  if (len < 5) return 0;
+  const size_t lim1 = len >= 13 ? len - 14 + 1 : 0;
   for (size_t i = 0; i < lim1; ++i)
     if (similarity(s, len, i, adaptor, ad_len) >= 11) { memset(s + i, 'N', len - i); return len - i; }
   const size_t lim2 = len - 5 + 1;
@@ -405,82 +652,224 @@ size_t walt_clip_adaptor(const char* adaptor, char* s, size_t len) {
   return 0;
 }
 
+}  // extern "C"
+
+namespace {
+
+// One `fgets(cline, MAX_LINE_LENGTH, fin); cline[strlen(cline) - 1] = 0;` step of the reference
+// loader (mapping.cpp:79-80) over memory: at most 999 bytes, ending behind a newline if one
+// comes first; strlen stops at an embedded NUL; the last character goes, whatever it is.
+struct Piece { const char* s = nullptr; uint32_t len = 0; const char* next = nullptr; };
+inline bool next_piece(const char* p, const char* end, Piece& out) {
+  if (p >= end) return false;
+  const size_t room = std::min<size_t>((size_t)(end - p), LINE_CAP - 1);
+  const char* nl = (const char*)memchr(p, '\n', room);
+  const char* q = nl ? nl + 1 : p + room;
+  size_t slen = (size_t)(q - p);
+  const char* z = (const char*)memchr(p, 0, slen);
+  if (z) slen = (size_t)(z - p);
+  if (slen) --slen;
+  out.s = p; out.len = (uint32_t)slen; out.next = q;
+  return true;
+}
+// next piece that survives `if (line.size() == 0) continue;` (mapping.cpp:82-83)
+inline bool next_line(const char*& p, const char* end, Piece& out) {
+  while (next_piece(p, end, out)) {
+    p = out.next;
+    if (out.len) return true;
+  }
+  return false;
+}
+
+struct RecRef {            // the four lines of one record inside the file
+  uint64_t name;           // offset of the name's first character
+  uint32_t seq_delta, qual_delta;   // from `name`
+  uint16_t name_len, seq_len, qual_len;
+};
+
+}  // namespace
+
+extern "C" {
+
 int64_t walt_fastq_next_batch(walt_fastq* fq, walt_batch* b, uint32_t max_reads, const char* adaptor) {
   if (!fq || !b) return fail("bad argument");
   b->clear();
-  srand(0);                                   // mapping.cpp:73
-  char line[LINE_CAP];
-  int code = 0;
-  uint64_t line_count = 0;
-  const uint64_t lim = (uint64_t)max_reads * 4u;
+  const uint64_t lim = (uint64_t)max_reads * 4u;   // lines, mapping.cpp:78
   const bool clip = adaptor && adaptor[0];
-  std::string pend_name;
-  bool have_name = false, have_seq = false;
-  size_t pend_seq_off = 0;
-  while (line_count < lim && fgets(line, (int)LINE_CAP, fq->f)) {
-    size_t len = strlen(line);
-    if (len) line[--len] = 0;                 // the last character goes, whatever it is
-    if (len == 0) continue;                   // empty lines do not advance the record state
-    switch (code) {
-      case 0: {
-        const char* sp = (const char*)memchr(line, ' ', len);
-        const size_t end = sp ? (size_t)(sp - line) : len;
-        pend_name.assign(line + 1, end > 0 ? end - 1 : 0);
-        have_name = true;
-        break;
+  if (lim == 0 || fq->pos >= fq->size) return 0;
+  const char* const base = fq->data;
+  const char* const file_end = base + fq->size;
+
+  // ---- 1. a window [lo, hi) that holds the batch's lines, split at physical line starts ----
+  const char* lo = base + fq->pos;
+  const char* hi = lo;
+  std::vector<const char*> cut;       // chunk boundaries, cut.front() == lo, cut.back() == hi
+  std::vector<uint64_t> first_line;   // index of the first surviving line of each chunk (+ total)
+  uint64_t total = 0;
+  double want = (double)lim * fq->bytes_per_line * 1.1 + 65536.0;
+  for (;;) {
+    const char* h = (double)(file_end - lo) <= want ? file_end : lo + (size_t)want;
+    if (h < file_end) {
+      const char* nl = (const char*)memchr(h, '\n', (size_t)(file_end - h));
+      h = nl ? nl + 1 : file_end;
+    }
+    hi = h;
+    const size_t K = std::max<size_t>(1, std::min<size_t>((size_t)host_threads() * 4u, (size_t)(hi - lo) / g_chunk_bytes.load()));
+    cut.assign(K + 1, hi);
+    cut[0] = lo;
+    for (size_t i = 1; i < K; ++i) {
+      const char* c = lo + (size_t)(hi - lo) / K * i;
+      c = std::max(c, cut[i - 1]);
+      if (c > lo && c[-1] != '\n') {
+        const char* nl = (const char*)memchr(c, '\n', (size_t)(hi - c));
+        c = nl ? nl + 1 : hi;
       }
-      case 1: {
-        if (clip) walt_clip_adaptor(adaptor, line, len);
-        pend_seq_off = b->seqs.size();
-        for (size_t i = 0; i < len; ++i) {
-          char c = line[i];
-          if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T')) c = "ACGT"[rand() % 4];   // util.hpp:156-163
-          b->seqs.push_back(c);
-        }
-        have_seq = true;
-        break;
-      }
-      case 2: break;
-      case 3: {
-        // a record is committed when its quality line arrives (mapping.cpp:104-108)
-        if (!have_seq) pend_seq_off = b->seqs.size();
-        if (!have_name) pend_name.clear();
-        b->seq_off.back() = pend_seq_off;
-        b->seq_off.push_back(b->seqs.size());
-        b->names.append(pend_name); b->names.push_back('\0'); b->name_off.push_back(b->names.size());
-        b->quals.append(line, len); b->quals.push_back('\0'); b->qual_off.push_back(b->quals.size());
-        b->n++;
-        have_name = have_seq = false;
-        break;
+      cut[i] = c;
+    }
+    std::vector<uint64_t> cnt(K, 0);
+    parallel_tasks(K, [&](size_t i) {
+      const char* p = cut[i];
+      Piece pc;
+      uint64_t c = 0;
+      while (next_line(p, cut[i + 1], pc)) ++c;
+      cnt[i] = c;
+    });
+    first_line.assign(K + 1, 0);
+    for (size_t i = 0; i < K; ++i) first_line[i + 1] = first_line[i] + cnt[i];
+    total = first_line[K];
+    if (total >= lim || hi == file_end) break;
+    want *= 2.0;
+  }
+  const size_t K = cut.size() - 1;
+  const uint64_t take = std::min(total, lim);
+  const uint64_t n_rec = take / 4u;   // a trailing partial record is never committed (mapping.cpp:104-108)
+  if (total) fq->bytes_per_line = std::max(16.0, (double)(hi - lo) / (double)total);
+
+  // where the next batch starts: behind line take-1 (behind the window if it was used up)
+  if (take == total) {
+    fq->pos = (size_t)(hi - base);
+  } else {
+    size_t j = 0;
+    while (first_line[j + 1] <= take - 1) ++j;
+    const char* p = cut[j];
+    Piece pc;
+    for (uint64_t k = first_line[j]; k <= take - 1; ++k) next_line(p, cut[j + 1], pc);
+    fq->pos = (size_t)(pc.next - base);
+  }
+  if (n_rec == 0) return 0;
+
+  // ---- 2. record table: every chunk emits the records that START in it ----
+  std::vector<std::vector<RecRef>> recs(K);
+  parallel_tasks(K, [&](size_t i) {
+    const uint64_t g0 = first_line[i], g1 = std::min<uint64_t>(first_line[i + 1], n_rec * 4u);
+    uint64_t g = g0 + (4u - g0 % 4u) % 4u;   // first record boundary at or behind the chunk start
+    if (g >= g1) return;
+    const char* p = cut[i];
+    Piece pc;
+    for (uint64_t k = g0; k < g; ++k) next_line(p, hi, pc);
+    std::vector<RecRef>& out = recs[i];
+    out.reserve((size_t)((g1 - g + 3u) / 4u));
+    for (; g < g1; g += 4u) {
+      Piece l0, l1, l2, l3;
+      next_line(p, hi, l0); next_line(p, hi, l1); next_line(p, hi, l2); next_line(p, hi, l3);
+      // mapping.cpp:86-92: substr(1) or substr(1, space_pos - 1); a leading space makes the count npos
+      const char* sp = (const char*)memchr(l0.s, ' ', l0.len);
+      const uint32_t name_end = (sp && sp != l0.s) ? (uint32_t)(sp - l0.s) : l0.len;
+      RecRef r;
+      r.name = (uint64_t)(l0.s + 1 - base);
+      r.name_len = (uint16_t)(name_end - 1u);
+      r.seq_delta = (uint32_t)(l1.s - (l0.s + 1)); r.seq_len = (uint16_t)l1.len;
+      r.qual_delta = (uint32_t)(l3.s - (l0.s + 1)); r.qual_len = (uint16_t)l3.len;
+      out.push_back(r);
+    }
+  });
+
+  // ---- 3. output offsets (serial prefix sums), then the copies in parallel ----
+  b->n = (uint32_t)n_rec;
+  b->seq_off.resize(n_rec + 1); b->qual_off.resize(n_rec + 1); b->name_off.resize(n_rec + 1);
+  std::vector<size_t> rec_base(K + 1, 0);
+  {
+    uint64_t so = 0, qo = 0, no = 0;
+    size_t j = 0;
+    for (size_t i = 0; i < K; ++i) {
+      rec_base[i] = j;
+      for (const RecRef& r : recs[i]) {
+        b->seq_off[j] = so; b->qual_off[j] = qo; b->name_off[j] = no;
+        so += r.seq_len; qo += (uint64_t)r.qual_len + 1u; no += (uint64_t)r.name_len + 1u;
+        ++j;
       }
     }
-    ++line_count;
-    if (++code == 4) code = 0;
+    rec_base[K] = j;
+    b->seq_off[j] = so; b->qual_off[j] = qo; b->name_off[j] = no;
+    if (j != n_rec) return fail("internal error: FASTQ record table out of step");
+    if (!b->seqs.size_to(so) || !b->quals.size_to(qo) || !b->names.size_to(no)) return fail("ERROR: could not allocate memory");
   }
-  // a trailing partial record leaves bases behind the last committed read: drop them
-  b->seqs.resize(b->seq_off.back());
+  std::vector<std::vector<uint64_t>> marks(K);   // offsets in b->seqs of the characters toACGT replaces
+  parallel_tasks(K, [&](size_t i) {
+    size_t j = rec_base[i];
+    std::vector<uint64_t>& mk = marks[i];
+    for (const RecRef& r : recs[i]) {
+      const char* nm = base + r.name;
+      char* dn = b->names.p + b->name_off[j];
+      memcpy(dn, nm, r.name_len); dn[r.name_len] = 0;
+      char* dq = b->quals.p + b->qual_off[j];
+      memcpy(dq, nm + r.qual_delta, r.qual_len); dq[r.qual_len] = 0;
+      char* ds = b->seqs.p + b->seq_off[j];
+      memcpy(ds, nm + r.seq_delta, r.seq_len);
+      if (clip) walt_clip_adaptor(adaptor, ds, r.seq_len);
+      for (uint32_t t = 0; t < r.seq_len; ++t) {
+        const char c = ds[t];
+        if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T')) mk.push_back(b->seq_off[j] + t);
+      }
+      ++j;
+    }
+  });
+
+  // ---- 4. toACGT (util.hpp:156-163) in file order on the srand(0) stream (mapping.cpp:73) ----
+  {
+    struct random_data rd;
+    char state[128];
+    memset(&rd, 0, sizeof rd);
+    initstate_r(0, state, sizeof state, &rd);
+    for (size_t i = 0; i < K; ++i)
+      for (const uint64_t at : marks[i]) {
+        int32_t r = 0;
+        random_r(&rd, &r);
+        b->seqs.p[at] = "ACGT"[r % 4];
+      }
+  }
   return b->n;
 }
 
 uint64_t walt_packed_reads_bytes(const uint64_t* offs, uint32_t n) { return (offs[n] >> 2) + n + 16u; }
 
+// Codes A0 C1 G2 T3 (util.hpp:107-121) are bits 1..2 of the ASCII letter with the upper bit folded
+// into the lower: x = (c >> 1) & 3, code = x ^ (x >> 1).  Four letters at a time: the four codes sit
+// in the low bits of the four bytes of a word; one multiply gathers them into a byte, first letter
+// in the top bits.  Validation is the same arithmetic run backwards ("ACGT"[code] == letter).
+static inline uint32_t codes_of4(uint32_t w) {
+  const uint32_t x = (w >> 1) & 0x03030303u;
+  return x ^ ((x >> 1) & 0x01010101u);
+}
+static inline uint32_t letters_of4(uint32_t code) {   // "ACGT"[code] per byte: 0x41 + {0, 2, 6, 0x13}
+  const uint32_t lo = code & 0x01010101u, hi = (code >> 1) & 0x01010101u;
+  return 0x41414141u + lo * 2u + hi * 6u + (lo & hi) * 0x0Bu;
+}
+
 int walt_pack_reads(const char* seqs, const uint64_t* offs, uint32_t n, uint8_t* out) {
   if (!offs || !out || (n && !seqs)) return fail("bad argument");
-  // A0 C1 G2 T3 (util.hpp:107-121): bits 1..2 of the ASCII letter, with the upper bit folded in
-  unsigned bad = 0;
+  uint32_t bad = 0;
   for (uint32_t j = 0; j < n; ++j) {
     const char* s = seqs + offs[j];
     const uint64_t len = offs[j + 1] - offs[j];
     uint8_t* o = out + (offs[j] >> 2) + j;
     uint64_t i = 0;
     for (; i + 4 <= len; i += 4) {
-      unsigned v = 0;
-      for (unsigned t = 0; t < 4; ++t) {
-        const unsigned c = (unsigned char)s[i + t], x = (c >> 1) & 3u, code = x ^ (x >> 1);
-        bad |= (unsigned)("ACGT"[code] != (char)c);
-        v = (v << 2) | code;
-      }
-      *o++ = (uint8_t)v;
+      uint32_t w;
+      memcpy(&w, s + i, 4);
+      const uint32_t code = codes_of4(w);
+      bad |= letters_of4(code) ^ w;
+      *o++ = (uint8_t)((code * 0x40100401u) >> 24);
     }
     if (i < len) {
       unsigned v = 0, t = 0;
@@ -497,15 +886,29 @@ int walt_pack_reads(const char* seqs, const uint64_t* offs, uint32_t n, uint8_t*
 
 const uint8_t* walt_batch_packed(walt_batch* b) {
   if (!b) return nullptr;
-  if (b->packed.empty()) {
-    b->packed.assign(walt_packed_reads_bytes(b->seq_off.data(), b->n), 0);
-    if (walt_pack_reads(b->seqs.data(), b->seq_off.data(), b->n, b->packed.data()) != 0) { b->packed.clear(); return nullptr; }
+  if (!b->have_packed) {
+    const uint64_t* offs = b->seq_off.data();
+    if (!b->packed.size_to(walt_packed_reads_bytes(offs, b->n))) { fail("ERROR: could not allocate memory"); return nullptr; }
+    const uint32_t BLOCK = 1u << 16;
+    const size_t nb = ((size_t)b->n + BLOCK - 1) / BLOCK;
+    std::atomic<int> bad{0};
+    // read j lives at byte (offs[j] >> 2) + j whatever range it is packed with: shift the output
+    // pointer by the block's first read so that a sub-range call writes the same bytes
+    parallel_tasks(nb, [&](size_t k) {
+      const uint32_t lo = (uint32_t)k * BLOCK, cnt = std::min<uint32_t>(BLOCK, b->n - lo);
+      const uint64_t b0 = (offs[lo] >> 2) + lo, b1 = (offs[lo + cnt] >> 2) + lo + cnt;
+      memset(b->packed.p + b0, 0, (size_t)(b1 - b0));   // bytes between two reads stay zero
+      if (walt_pack_reads(b->seqs.p, offs + lo, cnt, (uint8_t*)b->packed.p + lo) != 0) bad = 1;
+    });
+    memset(b->packed.p + b->packed.n - 16, 0, 16);
+    if (bad) { fail("walt_pack_reads: a read holds a byte that is not A/C/G/T"); return nullptr; }
+    b->have_packed = true;
   }
-  return b->packed.data();
+  return (const uint8_t*)b->packed.p;
 }
 
 uint32_t walt_batch_size(const walt_batch* b) { return b->n; }
-const char* walt_batch_seqs(const walt_batch* b) { return b->seqs.data(); }
+const char* walt_batch_seqs(const walt_batch* b) { return b->seqs.p; }
 const uint64_t* walt_batch_offsets(const walt_batch* b) { return b->seq_off.data(); }
 const char* walt_batch_name(const walt_batch* b, uint32_t i) { return b->name(i); }
 const char* walt_batch_qual(const walt_batch* b, uint32_t i) { return b->qual(i); }
@@ -533,11 +936,17 @@ walt_se_writer* walt_se_writer_open(const char* output_path, const walt_chroms* 
 
 int walt_se_writer_write(walt_se_writer* w, const walt_batch* b, const walt_best* res, uint32_t n) {
   if (!w || !b || n > b->n) return fail("bad argument");
-  for (uint32_t j = 0; j < n; ++j) {
-    w->so.st.update(res[j].times);
-    if (w->sam) sam_single(w->out, w->so, *w->g, res[j], b->name(j), b->name_len(j), b->seq(j), b->qual(j), b->seq_len(j), b->qual_len(j));
-    else mr_single(w->out, w->so, *w->g, res[j], b->name(j), b->name_len(j), b->seq(j), b->qual(j), b->seq_len(j), b->qual_len(j), w->ag);
-  }
+  ordered_blocks<SeBlock>(
+      n,
+      [&]() { SeBlock* bl = new SeBlock; local_twin(bl->so, w->so); return bl; },
+      [&](SeBlock& bl, uint32_t lo, uint32_t hi) {
+        for (uint32_t j = lo; j < hi; ++j) {
+          bl.so.st.update(res[j].times);
+          if (w->sam) sam_single(bl.out, bl.so, *w->g, res[j], b->name(j), b->name_len(j), b->seq(j), b->qual(j), b->seq_len(j), b->qual_len(j));
+          else mr_single(bl.out, bl.so, *w->g, res[j], b->name(j), b->name_len(j), b->seq(j), b->qual(j), b->seq_len(j), b->qual_len(j), w->ag);
+        }
+      },
+      [&](SeBlock& bl) { w->out.append_block(bl.out); commit_twin(w->so, bl.so); });
   return 0;
 }
 
@@ -545,13 +954,13 @@ void walt_se_writer_add_short(walt_se_writer* w, uint32_t n_short) { w->so.st.n_
 
 int walt_se_writer_close(walt_se_writer* w) {
   if (!w) return 0;
-  w->out.close();
-  w->so.close();
+  bool ok = w->out.close();
+  ok = w->so.close() && ok;
   std::ofstream ms(w->path + ".mapstats", std::ios::app);
   ms << w->so.st.text(0) << std::endl;
-  const bool ok = (bool)ms;
+  ok = ok && (bool)ms;
   delete w;
-  return ok ? 0 : fail("cannot write mapstats");
+  return ok ? 0 : fail("cannot write the outputs / mapstats");
 }
 
 // ---- paired end --------------------------------------------------------------------------------
@@ -560,21 +969,21 @@ walt_pe_writer* walt_pe_writer_open(const char* output_path, const walt_chroms* 
   walt_pe_writer* w = new walt_pe_writer;
   w->g = chroms; w->path = output_path; w->m = max_mismatches; w->top_k = top_k; w->frag_range = frag_range;
   w->sam = sam != 0; w->pbat = pbat != 0;
-  w->frag_count.assign((size_t)frag_range + 1, 0);
-  if (!w->out.open(w->path, "a")) { fail("cannot open input file " + w->path); delete w; return nullptr; }
-  if (!w->so1.open(w->path + "_1", ambiguous != 0, unmapped != 0, w->sam) ||
-      !w->so2.open(w->path + "_2", ambiguous != 0, unmapped != 0, w->sam)) {
-    fail("cannot open the _1/_2 side files of " + w->path); w->out.close(); delete w; return nullptr;
+  w->o.frag_count.assign((size_t)frag_range + 1, 0);
+  if (!w->o.out.open(w->path, "a")) { fail("cannot open input file " + w->path); delete w; return nullptr; }
+  if (!w->o.so1.open(w->path + "_1", ambiguous != 0, unmapped != 0, w->sam) ||
+      !w->o.so2.open(w->path + "_2", ambiguous != 0, unmapped != 0, w->sam)) {
+    fail("cannot open the _1/_2 side files of " + w->path); w->o.out.close(); delete w; return nullptr;
   }
-  if (w->sam) sam_header(w->out, *chroms);
+  if (w->sam) sam_header(w->o.out, *chroms);
   return w;
 }
 
-void walt_pe_writer_add_short(walt_pe_writer* w, uint32_t s1, uint32_t s2) { w->so1.st.n_short += s1; w->so2.st.n_short += s2; }
+void walt_pe_writer_add_short(walt_pe_writer* w, uint32_t s1, uint32_t s2) { w->o.so1.st.n_short += s1; w->o.so2.st.n_short += s2; }
 
 // One pair through MergePairedEndResults' output half (paired.cpp:515-569).  `r` holds the
 // per-file-mate fields (c1/single1 belong to the first file's read).
-static void write_pair(walt_pe_writer* w, const walt_batch* b1, const walt_batch* b2, uint32_t j, const walt_pe_result& r) {
+static void write_pair(const walt_pe_writer* w, PeOut& o, const walt_batch* b1, const walt_batch* b2, uint32_t j, const walt_pe_result& r) {
   const walt_chroms& g = *w->g;
   // Under PBAT the mate that plays the reference's "mate 1" role (C->T, pairing-loop outer
   // index) is the second file's read; names and first/last flags stay with the files.
@@ -591,26 +1000,26 @@ static void write_pair(walt_pe_writer* w, const walt_batch* b1, const walt_batch
   bool paired = false;
   int len = 0;
   if (r.pair.best_times == 1) {
-    w->unique_pairs++;
-    len = best_pair_out(w->out, g, pa, pb, w->frag_range, name, name_len, ba->seq(j), ba->qual(j), la,
+    o.unique_pairs++;
+    len = best_pair_out(o.out, g, pa, pb, w->frag_range, name, name_len, ba->seq(j), ba->qual(j), la,
                         bb->seq(j), bb->qual(j), lb, w->sam);
-    if (len >= 0 && (size_t)len < w->frag_count.size()) w->frag_count[len]++;
+    if (len >= 0 && (size_t)len < o.frag_count.size()) o.frag_count[len]++;
     if (w->sam) {
       paired = true;
       ma.genome_pos = pa.genome_pos; ma.times = 1; ma.strand = pa.strand; ma.mismatch = pa.mismatch;
       mb.genome_pos = pb.genome_pos; mb.times = 1; mb.strand = pb.strand; mb.mismatch = pb.mismatch;
     }
   } else {
-    if (r.pair.best_times >= 2) w->ambiguous_pairs++; else w->unmapped_pairs++;
+    if (r.pair.best_times >= 2) o.ambiguous_pairs++; else o.unmapped_pairs++;
     ma = w->pbat ? r.single2 : r.single1;
     mb = w->pbat ? r.single1 : r.single2;
-    SingleOut& soa = w->pbat ? w->so2 : w->so1;
-    SingleOut& sob = w->pbat ? w->so1 : w->so2;
+    SingleOut& soa = w->pbat ? o.so2 : o.so1;
+    SingleOut& sob = w->pbat ? o.so1 : o.so2;
     soa.st.update(ma.times);
     sob.st.update(mb.times);
     if (!w->sam) {
-      mr_single(w->out, soa, g, ma, name, name_len, ba->seq(j), ba->qual(j), la, ba->qual_len(j), false);
-      mr_single(w->out, sob, g, mb, name, name_len, bb->seq(j), bb->qual(j), lb, bb->qual_len(j), true);
+      mr_single(o.out, soa, g, ma, name, name_len, ba->seq(j), ba->qual(j), la, ba->qual_len(j), false);
+      mr_single(o.out, sob, g, mb, name, name_len, bb->seq(j), bb->qual(j), lb, bb->qual_len(j), true);
     }
   }
   if (w->sam) {
@@ -630,19 +1039,36 @@ static void write_pair(walt_pe_writer* w, const walt_batch* b1, const walt_batch
     const bool a_first = !w->pbat;
     const int fa = sam_flag(paired, ma.times == 0, mb.times == 0, ma.strand == '-', mb.strand == '-', a_first, ma.times >= 2);
     const int fb = sam_flag(paired, mb.times == 0, ma.times == 0, mb.strand == '-', ma.strand == '-', !a_first, mb.times >= 2);
-    const SingleOut& soa = w->pbat ? w->so2 : w->so1;
-    const SingleOut& sob = w->pbat ? w->so1 : w->so2;
-    auto line_a = [&]() { sam_mate_line(w->out, soa, g, ma, chra, name, name_len, fa, sa, rnb, sb, tla, ba->seq(j), ba->qual(j), la, ba->qual_len(j), mma); };
-    auto line_b = [&]() { sam_mate_line(w->out, sob, g, mb, chrb, name, name_len, fb, sb, rna, sa, tlb, bb->seq(j), bb->qual(j), lb, bb->qual_len(j), mmb); };
+    const SingleOut& soa = w->pbat ? o.so2 : o.so1;
+    const SingleOut& sob = w->pbat ? o.so1 : o.so2;
+    auto line_a = [&]() { sam_mate_line(o.out, soa, g, ma, chra, name, name_len, fa, sa, rnb, sb, tla, ba->seq(j), ba->qual(j), la, ba->qual_len(j), mma); };
+    auto line_b = [&]() { sam_mate_line(o.out, sob, g, mb, chrb, name, name_len, fb, sb, rna, sa, tlb, bb->seq(j), bb->qual(j), lb, bb->qual_len(j), mmb); };
     if (a_first) { line_a(); line_b(); } else { line_b(); line_a(); }
   }
+}
+
+// block-local PeOut and its commit into the writer's files and totals
+static PeOut* pe_block(const walt_pe_writer* w) {
+  PeOut* bl = new PeOut;
+  local_twin(bl->so1, w->o.so1); local_twin(bl->so2, w->o.so2);
+  bl->frag_count.assign(w->o.frag_count.size(), 0);
+  return bl;
+}
+static void pe_commit(walt_pe_writer* w, PeOut& bl) {
+  w->o.out.append_block(bl.out);
+  commit_twin(w->o.so1, bl.so1); commit_twin(w->o.so2, bl.so2);
+  w->o.unique_pairs += bl.unique_pairs; w->o.ambiguous_pairs += bl.ambiguous_pairs; w->o.unmapped_pairs += bl.unmapped_pairs;
+  for (size_t i = 0; i < bl.frag_count.size(); ++i) w->o.frag_count[i] += bl.frag_count[i];
 }
 
 int walt_pe_writer_write_compact(walt_pe_writer* w, const walt_batch* b1, const walt_batch* b2, const walt_pe_result* res,
                                  uint32_t n) {
   if (!w || !b1 || !b2 || !res || n > b1->n || n > b2->n) return fail("bad argument");
   w->total_pairs += n;
-  for (uint32_t j = 0; j < n; ++j) write_pair(w, b1, b2, j, res[j]);
+  ordered_blocks<PeOut>(
+      n, [&]() { return pe_block(w); },
+      [&](PeOut& bl, uint32_t lo, uint32_t hi) { for (uint32_t j = lo; j < hi; ++j) write_pair(w, bl, b1, b2, j, res[j]); },
+      [&](PeOut& bl) { pe_commit(w, bl); });
   return 0;
 }
 
@@ -651,48 +1077,54 @@ int walt_pe_writer_write(walt_pe_writer* w, const walt_batch* b1, const walt_bat
                          const walt_pair* pairs, uint32_t n) {
   if (!w || !b1 || !b2 || n > b1->n || n > b2->n) return fail("bad argument");
   w->total_pairs += n;
-  for (uint32_t j = 0; j < n; ++j) {
-    // the summary the device computes in the compact path, derived here from the ranked lists
-    const walt_cand* c1 = ranked1 + (size_t)j * w->top_k;
-    const walt_cand* c2 = ranked2 + (size_t)j * w->top_k;
-    walt_pe_result r;
-    memset(&r, 0, sizeof(r));
-    r.pair = pairs[j];
-    if (pairs[j].best_times >= 1) { r.c1 = c1[pairs[j].best_i]; r.c2 = c2[pairs[j].best_j]; }
-    r.single1 = best_for_single(c1, n_ranked1[j], w->m);
-    r.single2 = best_for_single(c2, n_ranked2[j], w->m);
-    write_pair(w, b1, b2, j, r);
-  }
+  ordered_blocks<PeOut>(
+      n, [&]() { return pe_block(w); },
+      [&](PeOut& bl, uint32_t lo, uint32_t hi) {
+        for (uint32_t j = lo; j < hi; ++j) {
+          // the summary the device computes in the compact path, derived here from the ranked lists
+          const walt_cand* c1 = ranked1 + (size_t)j * w->top_k;
+          const walt_cand* c2 = ranked2 + (size_t)j * w->top_k;
+          walt_pe_result r;
+          memset(&r, 0, sizeof(r));
+          r.pair = pairs[j];
+          if (pairs[j].best_times >= 1) { r.c1 = c1[pairs[j].best_i]; r.c2 = c2[pairs[j].best_j]; }
+          r.single1 = best_for_single(c1, n_ranked1[j], w->m);
+          r.single2 = best_for_single(c2, n_ranked2[j], w->m);
+          write_pair(w, bl, b1, b2, j, r);
+        }
+      },
+      [&](PeOut& bl) { pe_commit(w, bl); });
   return 0;
 }
 
 int walt_pe_writer_close(walt_pe_writer* w) {
   if (!w) return 0;
-  w->out.close();
-  w->so1.close(); w->so2.close();
+  bool files_ok = w->o.out.close();
+  files_ok = w->o.so1.close() && files_ok;
+  files_ok = w->o.so2.close() && files_ok;
   // StatPairedReads::tostring, paired.cpp:52-77
   std::ostringstream o;
   o << "pairs:" << std::endl
     << "    total_read_pairs: " << w->total_pairs << std::endl
     << "    mapped:" << std::endl
-    << "        unique: " << w->unique_pairs << std::endl
-    << "        percent_unique: " << (100.0 * (double)w->unique_pairs) / (double)w->total_pairs << std::endl
-    << "        ambiguous: " << w->ambiguous_pairs << std::endl
-    << "    unmapped: " << w->unmapped_pairs << std::endl
-    << "mate1:" << std::endl << w->so1.st.text(1) << std::endl
-    << "mate2:" << std::endl << w->so2.st.text(1) << std::endl;
+    << "        unique: " << w->o.unique_pairs << std::endl
+    << "        percent_unique: " << (100.0 * (double)w->o.unique_pairs) / (double)w->total_pairs << std::endl
+    << "        ambiguous: " << w->o.ambiguous_pairs << std::endl
+    << "    unmapped: " << w->o.unmapped_pairs << std::endl
+    << "mate1:" << std::endl << w->o.so1.st.text(1) << std::endl
+    << "mate2:" << std::endl << w->o.so2.st.text(1) << std::endl;
   o << "frag_len_distribution:" << std::endl;
   double total = 0.0;
-  for (size_t i = 0; i < w->frag_count.size(); ++i) {
-    o << "    " << i << ": " << w->frag_count[i] << std::endl;
-    total += (double)(i * w->frag_count[i]);
+  for (size_t i = 0; i < w->o.frag_count.size(); ++i) {
+    o << "    " << i << ": " << w->o.frag_count[i] << std::endl;
+    total += (double)(i * w->o.frag_count[i]);
   }
-  o << "frag_len_mean: " << total / std::accumulate(w->frag_count.begin(), w->frag_count.end(), 0.0);
+  o << "frag_len_mean: " << total / std::accumulate(w->o.frag_count.begin(), w->o.frag_count.end(), 0.0);
   std::ofstream ms(w->path + ".mapstats", std::ios::app);
   ms << o.str() << std::endl;
-  const bool ok = (bool)ms;
+  const bool ok = files_ok && (bool)ms;
   delete w;
-  return ok ? 0 : fail("cannot write mapstats");
+  return ok ? 0 : fail("cannot write the outputs / mapstats");
 }
 
 // ---- makedb output -----------------------------------------------------------------------------

@@ -18,6 +18,8 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <chrono>
+#include <future>
 #include <thread>
 #include <vector>
 
@@ -111,7 +113,7 @@ struct Settings {
   std::string index, se_csv, pe1_csv, pe2_csv, out_csv, adaptor;
   bool sam = false, ambiguous = false, unmapped = false, ag = false, verbose = false, pbat = false;
   uint32_t m = 6, batch = 10000000, b = 5000, top_k = 50, gpus = 1;
-  int frag = 1000, threads = 1;
+  int frag = 1000, threads = 0;   // 0: -t not given, one host thread per hardware thread
 };
 
 void engine_check(int rc) {
@@ -126,11 +128,37 @@ struct Engines {
 // contiguous split of [0, n) over g workers
 inline uint32_t cut(uint32_t n, uint32_t g, uint32_t i) { return (uint32_t)((uint64_t)n * i / g); }
 
-void map_se_batch(Engines& eng, const walt_batch* b, const Settings& s, bool ag, std::vector<walt_best>& res,
-                  uint32_t& n_short) {
+// stage timings on stderr when WALT_TIMING is set (never part of the outputs)
+struct StageClock {
+  bool on = getenv("WALT_TIMING") != nullptr;
+  double load = 0, map = 0, write = 0;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  static double since(std::chrono::steady_clock::time_point a) {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count();
+  }
+  void report(const char* what, uint64_t n) const {
+    if (on) fprintf(stderr, "[walt timing] %s: %llu reads, load %.3f s (overlapped with map+write after the first batch), map %.3f s, "
+                            "write %.3f s, total %.3f s, %u host threads\n", what, (unsigned long long)n, load, map, write,
+                    since(t0), walt_host_threads());
+  }
+};
+
+// one loaded batch: the ASCII reads (for the writers) and their 2-bit form (what crosses PCIe)
+struct Loaded { int64_t n = 0; const uint8_t* packed = nullptr; std::string err; double seconds = 0; };
+Loaded load_batch(walt_fastq* fq, walt_batch* b, uint32_t max_reads, const std::string& adaptor) {
+  Loaded l;
+  const auto t = std::chrono::steady_clock::now();
+  l.n = walt_fastq_next_batch(fq, b, max_reads, adaptor.c_str());
+  if (l.n < 0) l.err = walt_host_last_error();
+  if (l.n > 0 && !(l.packed = walt_batch_packed(b))) { l.n = -1; l.err = walt_host_last_error(); }
+  l.seconds = StageClock::since(t);
+  return l;
+}
+
+void map_se_batch(Engines& eng, const walt_batch* b, const uint8_t* packed, const Settings& s, bool ag,
+                  std::vector<walt_best>& res, uint32_t& n_short) {
   const uint32_t n = walt_batch_size(b), g = (uint32_t)eng.e.size();
   res.resize(n);
-  const char* seqs = walt_batch_seqs(b);
   const uint64_t* offs = walt_batch_offsets(b);
   std::vector<int> rc(g, 0);
   std::vector<uint32_t> sh(g, 0);
@@ -140,7 +168,9 @@ void map_se_batch(Engines& eng, const walt_batch* b, const Settings& s, bool ag,
     th.emplace_back([&, i]() {
       const uint32_t lo = cut(n, g, i), hi = cut(n, g, i + 1);
       if (hi == lo) return;
-      rc[i] = walt_engine_map_se(eng.e[i], seqs, offs + lo, hi - lo, ag ? 1 : 0, s.m, s.b, res.data() + lo, &sh[i]);
+      // read j of the batch lives at byte (offs[j] >> 2) + j of `packed`: a shard that starts at
+      // read lo passes the buffer shifted by lo so that its own j = 0 lands on the same byte
+      rc[i] = walt_engine_map_se_packed(eng.e[i], packed + lo, offs + lo, hi - lo, ag ? 1 : 0, s.m, s.b, res.data() + lo, &sh[i]);
       if (rc[i]) err[i] = walt_last_error();
     });
   }
@@ -160,26 +190,44 @@ void process_single_end(Engines& eng, const walt_chroms* chroms, const Settings&
   walt_se_writer* w = walt_se_writer_open(output.c_str(), chroms, ag, s.ambiguous, s.unmapped, s.sam);
   if (!w) { walt_fastq_close(fq); throw std::runtime_error(walt_host_last_error()); }
   if (s.verbose) std::cerr << "input_file: " << reads << std::endl << "output_file: " << output << std::endl;
-  walt_batch* b = walt_batch_create();
+  // two batches: the next one is loaded (and packed) while the current one is mapped and written
+  walt_batch* bb[2] = {walt_batch_create(), walt_batch_create()};
   std::vector<walt_best> res;
+  StageClock clk;
+  uint64_t total = 0;
+  std::future<Loaded> next;
   try {
+    int k = 0;
+    Loaded cur = load_batch(fq, bb[0], s.batch, s.adaptor);
+    clk.load += cur.seconds;
     for (;;) {
-      const int64_t n = walt_fastq_next_batch(fq, b, s.batch, s.adaptor.c_str());
-      if (n < 0) throw std::runtime_error(walt_host_last_error());
-      if (n == 0) break;
+      if (cur.n < 0) throw std::runtime_error(cur.err);
+      if (cur.n == 0) break;
+      const bool last = (uint32_t)cur.n < s.batch;
+      if (!last) next = std::async(std::launch::async, load_batch, fq, bb[1 - k], s.batch, s.adaptor);
       uint32_t n_short = 0;
-      map_se_batch(eng, b, s, ag, res, n_short);
+      auto t = std::chrono::steady_clock::now();
+      map_se_batch(eng, bb[k], cur.packed, s, ag, res, n_short);
+      clk.map += StageClock::since(t);
+      t = std::chrono::steady_clock::now();
       walt_se_writer_add_short(w, n_short);
-      if (walt_se_writer_write(w, b, res.data(), (uint32_t)n)) throw std::runtime_error(walt_host_last_error());
-      if ((uint32_t)n < s.batch) break;
+      if (walt_se_writer_write(w, bb[k], res.data(), (uint32_t)cur.n)) throw std::runtime_error(walt_host_last_error());
+      clk.write += StageClock::since(t);
+      total += (uint64_t)cur.n;
+      if (last) break;
+      cur = next.get();
+      clk.load += cur.seconds;
+      k = 1 - k;
     }
   } catch (...) {
-    walt_batch_free(b); walt_fastq_close(fq); walt_se_writer_close(w);
+    if (next.valid()) next.wait();
+    walt_batch_free(bb[0]); walt_batch_free(bb[1]); walt_fastq_close(fq); walt_se_writer_close(w);
     throw;
   }
-  walt_batch_free(b);
+  walt_batch_free(bb[0]); walt_batch_free(bb[1]);
   walt_fastq_close(fq);
   if (walt_se_writer_close(w)) throw std::runtime_error(walt_host_last_error());
+  clk.report("single-end", total);
 }
 
 void process_paired_end(Engines& eng, const walt_chroms* chroms, const Settings& s, const std::string& reads1,
@@ -197,59 +245,84 @@ void process_paired_end(Engines& eng, const walt_chroms* chroms, const Settings&
   if (!w) { walt_fastq_close(f1); walt_fastq_close(f2); throw std::runtime_error(walt_host_last_error()); }
   fprintf(stderr, "[MAPPING PAIRED-END READS FROM THE FOLLOWING TWO FILES]\n   %s (AND)\n   %s\n", reads1.c_str(), reads2.c_str());
   fprintf(stderr, "[OUTPUT MAPPING RESULTS TO %s]\n", output.c_str());
-  walt_batch* b1 = walt_batch_create();
-  walt_batch* b2 = walt_batch_create();
+  // two pairs of batches: both mate files of the next batch are loaded concurrently while the
+  // current batch is mapped and written
+  walt_batch* b1[2] = {walt_batch_create(), walt_batch_create()};
+  walt_batch* b2[2] = {walt_batch_create(), walt_batch_create()};
   std::vector<walt_pe_result> res;
   bool unequal = false;
+  StageClock clk;
+  uint64_t total = 0;
+  std::future<Loaded> next1, next2;
+  auto free_all = [&]() {
+    for (int i = 0; i < 2; ++i) { walt_batch_free(b1[i]); walt_batch_free(b2[i]); }
+    walt_fastq_close(f1); walt_fastq_close(f2);
+  };
   try {
+    int k = 0;
+    // (the order in which the two files are read only matters for the rand() stream, which every
+    // load restarts from srand(0), mapping.cpp:73)
+    next1 = std::async(std::launch::async, load_batch, f1, b1[0], s.batch, ad1);
+    Loaded c2 = load_batch(f2, b2[0], s.batch, ad2);
+    Loaded c1 = next1.get();
+    clk.load += std::max(c1.seconds, c2.seconds);
     for (;;) {
-      // under PBAT the reference-equivalent run reads the C->T mate (file 2) first; the order only
-      // matters for the rand() stream, which is reseeded per file anyway (mapping.cpp:73)
-      const int64_t c1 = walt_fastq_next_batch(f1, b1, s.batch, ad1.c_str());
-      if (c1 < 0) throw std::runtime_error(walt_host_last_error());
-      int64_t c2 = 0;
-      if (c1 > 0) {
-        c2 = walt_fastq_next_batch(f2, b2, s.batch, ad2.c_str());
-        if (c2 < 0) throw std::runtime_error(walt_host_last_error());
+      if (c1.n < 0) throw std::runtime_error(c1.err);
+      if (c2.n < 0) throw std::runtime_error(c2.err);
+      if (c1.n != c2.n) { unequal = true; break; }
+      if (c1.n == 0) break;
+      const uint32_t n = (uint32_t)c1.n, g = (uint32_t)eng.e.size();
+      const bool last = n < s.batch;
+      if (!last) {
+        next1 = std::async(std::launch::async, load_batch, f1, b1[1 - k], s.batch, ad1);
+        next2 = std::async(std::launch::async, load_batch, f2, b2[1 - k], s.batch, ad2);
       }
-      if (c1 != c2) { unequal = true; break; }
-      if (c1 == 0) break;
-      const uint32_t n = (uint32_t)c1, g = (uint32_t)eng.e.size();
+      auto t = std::chrono::steady_clock::now();
       res.resize(n);
       std::vector<int> rc(g, 0);
       std::vector<uint32_t> s1(g, 0), s2(g, 0);
       std::vector<std::string> err(g);
       std::vector<std::thread> th;
+      const uint64_t* o1 = walt_batch_offsets(b1[k]);
+      const uint64_t* o2 = walt_batch_offsets(b2[k]);
       for (uint32_t i = 0; i < g; ++i) {
         th.emplace_back([&, i]() {
           const uint32_t lo = cut(n, g, i), hi = cut(n, g, i + 1);
           if (hi == lo) return;
-          rc[i] = walt_engine_map_pe_compact(eng.e[i], walt_batch_seqs(b1), walt_batch_offsets(b1) + lo,
-                                             walt_batch_seqs(b2), walt_batch_offsets(b2) + lo, hi - lo, s.m, s.b, s.top_k,
-                                             s.frag, s.pbat ? 1 : 0, res.data() + lo, &s1[i], &s2[i]);
+          rc[i] = walt_engine_map_pe_compact_packed(eng.e[i], c1.packed + lo, o1 + lo, c2.packed + lo, o2 + lo, hi - lo, s.m,
+                                                    s.b, s.top_k, s.frag, s.pbat ? 1 : 0, res.data() + lo, &s1[i], &s2[i]);
           if (rc[i]) err[i] = walt_last_error();
         });
       }
-      for (auto& t : th) t.join();
+      for (auto& t2 : th) t2.join();
       for (uint32_t i = 0; i < g; ++i) {
         if (rc[i]) throw std::runtime_error("walt engine: " + err[i]);
         walt_pe_writer_add_short(w, s1[i], s2[i]);
       }
-      if (walt_pe_writer_write_compact(w, b1, b2, res.data(), n))
+      clk.map += StageClock::since(t);
+      t = std::chrono::steady_clock::now();
+      if (walt_pe_writer_write_compact(w, b1[k], b2[k], res.data(), n))
         throw std::runtime_error(walt_host_last_error());
-      if (n < s.batch) break;
+      clk.write += StageClock::since(t);
+      total += n;
+      if (last) break;
+      c1 = next1.get(); c2 = next2.get();
+      clk.load += std::max(c1.seconds, c2.seconds);
+      k = 1 - k;
     }
   } catch (...) {
-    walt_batch_free(b1); walt_batch_free(b2); walt_fastq_close(f1); walt_fastq_close(f2); walt_pe_writer_close(w);
+    if (next1.valid()) next1.wait();
+    if (next2.valid()) next2.wait();
+    free_all(); walt_pe_writer_close(w);
     throw;
   }
-  walt_batch_free(b1); walt_batch_free(b2);
-  walt_fastq_close(f1); walt_fastq_close(f2);
+  free_all();
   if (unequal) {   // paired.cpp:673-677: exits without writing mapstats
     fprintf(stderr, "The number of reads in paired-end files should be the same.\n");
     exit(EXIT_FAILURE);
   }
   if (walt_pe_writer_close(w)) throw std::runtime_error(walt_host_last_error());
+  clk.report("paired-end", total);
 }
 
 }  // namespace
@@ -306,10 +379,11 @@ int main(int argc, const char** argv) {
     if (outs.size() == 1) outs.assign(se.size() + pe1.size(), outs[0]);
     for (auto& o : outs) { std::ofstream a(o); std::ofstream b(o + ".mapstats"); }   // walt.cpp:230-233
 
-    if (s.verbose) std::cerr << "max_mismatches: " << s.m << std::endl << "threads: " << s.threads << std::endl;
+    if (s.verbose) std::cerr << "max_mismatches: " << s.m << std::endl << "threads: " << (s.threads > 0 ? (unsigned)s.threads : walt_host_threads()) << std::endl;
     if (s.batch > 100000000u) throw std::runtime_error("batch size may not exceed" + std::to_string(100000000u));
     if (s.top_k < 2 || s.top_k > 300) throw std::runtime_error("paired-end candidates must be in [2, 300]");
     if (s.gpus < 1) s.gpus = 1;
+    walt_host_set_threads(s.threads > 0 ? (unsigned)s.threads : 0u);
 
     walt_chroms* chroms = walt_chroms_read(s.index.c_str());
     if (!chroms) throw std::runtime_error(walt_host_last_error());
