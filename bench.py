@@ -354,6 +354,136 @@ def config_dict(args, extra=None):
     return d
 
 
+# ---------------------------------------------------------------------------------------------
+# files in -> files out: the `walt` program against the reference `walt` on the same inputs
+# ---------------------------------------------------------------------------------------------
+def write_fastq_fixed(path, seqs, n, rl):
+    """FASTQ with fixed-width records (vectorised): @r%09d / seq / + / qualities."""
+    rec = 11 + 1 + rl + 3 + rl + 1
+    step = 250_000
+    digits = 10 ** np.arange(8, -1, -1, dtype=np.int64)
+    with open(path, "wb") as f:
+        for i0 in range(0, n, step):
+            m = min(step, n - i0)
+            a = np.empty((m, rec), np.uint8)
+            a[:, 0] = ord("@"); a[:, 1] = ord("r")
+            idx = np.arange(i0, i0 + m, dtype=np.int64)
+            a[:, 2:11] = (idx[:, None] // digits[None, :] % 10 + 48).astype(np.uint8)
+            a[:, 11] = 10
+            a[:, 12:12 + rl] = seqs[i0 * rl:(i0 + m) * rl].reshape(m, rl)
+            a[:, 12 + rl] = 10; a[:, 13 + rl] = ord("+"); a[:, 14 + rl] = 10
+            a[:, 15 + rl:15 + 2 * rl] = (35 + (idx[:, None] * 7 + np.arange(rl)[None, :] * 13) % 38).astype(np.uint8)
+            a[:, 15 + 2 * rl] = 10
+            f.write(a.tobytes())
+
+
+def cli_leg(device, genome_mb, n_reads, rl, workdir=None, keep=False):
+    """makedb-equivalent on the device -> .dbindex files; synthetic FASTQ; then `walt_b200/bin/walt`
+    and the unmodified reference `oracle/_ref/walt -t <cores>` on the same files, wall clock of each
+    whole process (index load, FASTQ parse, mapping, SAM formatting), outputs compared byte for byte."""
+    import hashlib
+    import shutil
+    import subprocess
+    import tempfile
+    import torch
+    import walt_b200
+    from walt_b200 import engine as eng
+    from walt_b200 import host as wh
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import refio
+    total = int(genome_mb * 1e6)
+    lengths = chrom_lengths(total)
+    names = [f"chr{i + 1}" for i in range(22)] + ["chrX", "chrY"]
+    work = tempfile.mkdtemp(prefix="walt_cli_", dir=workdir or os.environ.get("WALT_BENCH_TMP") or None)
+    out = {"genome_mb": genome_mb, "reads": n_reads, "read_len": rl}
+    try:
+        t0 = time.time()
+        e = walt_b200.Engine(device)
+        e.set_chromosomes(lengths, names)
+        dev = f"cuda:{device}"
+        d_fwd = torch.empty(eng.packed_genome_bytes(total), dtype=torch.uint8, device=dev)
+        eng.synth_genome_device(device, total, 7, d_fwd.data_ptr())
+        idx = os.path.join(work, "g.dbindex")
+        chroms = wh.Chroms(names=names, lengths=lengths)
+        size_of_index = 0
+        for which, sfx in enumerate(("_CT00", "_CT01", "_GA10", "_GA11")):
+            e.build_from_device_genome(d_fwd.data_ptr(), which=(which,))
+            seq, counter, index = e.export_subindex(which, total)
+            wh.write_subindex(idx + sfx, "-" if which & 1 else "+", seq, counter, index)
+            size_of_index = max(size_of_index, int(index.size))
+        wh.write_dbindex_header(idx, chroms, size_of_index)
+        d_reads = torch.empty(n_reads * rl, dtype=torch.uint8, device=dev)
+        e.synth_reads_device(d_fwd.data_ptr(), n_reads, rl, 11, False, d_reads.data_ptr())
+        fq = os.path.join(work, "reads.fastq")
+        write_fastq_fixed(fq, d_reads.cpu().numpy(), n_reads, rl)
+        del d_fwd, d_reads
+        e.close()
+        torch.cuda.empty_cache()
+        out["setup_s"] = round(time.time() - t0, 1)
+        out["fastq_bytes"] = os.path.getsize(fq)
+        out["index_bytes"] = sum(os.path.getsize(idx + s) for s in ("", "_CT00", "_CT01", "_GA10", "_GA11"))
+        cores = os.cpu_count() or 1
+        opts = ["-i", idx, "-r", fq, "-sam", "-u", "-a", "-m", str(M), "-b", str(B)]
+
+        def timed(cmd, env=None):
+            t = time.perf_counter()
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+            dt = time.perf_counter() - t
+            if r.returncode != 0:
+                raise RuntimeError(f"{cmd[0]} failed: {r.stderr.decode()[-500:]}")
+            return dt, r.stderr.decode()
+
+        def digest(path):
+            h = hashlib.sha256()
+            with open(path, "rb") as f:
+                for blk in iter(lambda: f.read(1 << 24), b""):
+                    h.update(blk)
+            return h.hexdigest(), os.path.getsize(path)
+
+        ours_bin = os.path.join(ROOT, "walt_b200", "bin", "walt")
+        env = dict(os.environ, WALT_TIMING="1", CUDA_VISIBLE_DEVICES=str(device))
+        o_out = os.path.join(work, "ours.sam")
+        runs = []
+        for _ in range(2):   # the second run has every input in the page cache (as has the reference's)
+            dt, err = timed([ours_bin] + opts + ["-o", o_out], env)
+            runs.append(dt)
+            stages = [l for l in err.splitlines() if l.startswith("[walt timing]")]
+        out["ours_s"] = min(runs)
+        out["ours_runs_s"] = [round(x, 3) for x in runs]
+        out["ours_stages"] = stages[-1] if stages else None
+        out["ours_reads_per_s"] = n_reads / min(runs)
+        d_ours = digest(o_out)
+        ms_ours = open(o_out + ".mapstats", "rb").read()
+        out["sam_bytes"] = d_ours[1]
+        if refio.have_reference():
+            r_out = os.path.join(work, "ref.sam")
+            ref_bin = os.path.join(ROOT, "oracle", "_ref", "walt")
+            dt, _ = timed([ref_bin] + opts + ["-o", r_out, "-t", str(cores)])
+            out["reference_s"] = dt
+            out["reference_reads_per_s"] = n_reads / dt
+            out["reference_threads"] = cores
+            out["outputs_identical"] = bool(digest(r_out) == d_ours and open(r_out + ".mapstats", "rb").read() == ms_ours)
+            out["speedup"] = dt / min(runs)
+        return out
+    finally:
+        if not keep:
+            shutil.rmtree(work, ignore_errors=True)
+
+
+def run_cli(args):
+    rank, local, world = dist_env()
+    if rank != 0:
+        return 0
+    r = cli_leg(local, args.cli_genome_mb, args.cli_reads, args.read_len)
+    line = {"metric": "reads mapped/sec, walt program: .dbindex + FASTQ files in, SAM file out (process wall clock)",
+            "value": r["ours_reads_per_s"], "unit": "reads/s", "n_gpus": 1, "higher_is_better": True, "data": "synthetic",
+            "config": {"workload": f"walt -i <{r['genome_mb']:g} Mb index> -r <{r['reads']} SE {r['read_len']} bp reads> -sam -u -a "
+                                   f"-m {M} -b {B}; reference: the unmodified walt -t <cores> on the same files"},
+            "cli": r}
+    print(json.dumps(line))
+    return 0
+
+
 def run_reference(args):
     rank, local, world = dist_env()
     if rank != 0:
@@ -581,6 +711,12 @@ def run_ours(args):
                                "input": "2-bit packed reads (walt_pack_reads, packed by the loader outside the timed region)"},
                 "gpu_launches": args.steps * wl.launches_per_step(),
                 "roofline": roof, "cpu_baseline": cpu_baseline, "parity_check": parity}
+        if world == 1 and not pe and not args.no_cpu and not args.no_cli:
+            # files in -> files out through the walt program, next to the reference program (not a timed step)
+            try:
+                line["cli"] = cli_leg(local, args.cli_genome_mb, args.cli_reads, rl)
+            except Exception as ex:   # the bench line stands without it
+                line["cli"] = {"error": str(ex)[-300:]}
         print(json.dumps(line))
     for h in (h_reads, h_reads2, h_offs, h_out, h_pk, h_pk2):
         if h is not None:
@@ -597,8 +733,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--genome-mb", type=float, default=3100.0)
-    ap.add_argument("--workload", default="se", choices=["se", "se_ag", "pe", "pe_stress"],
-                    help="se = configs[1] (the bench line), se_ag = configs[2], pe = configs[3], pe_stress = configs[4]")
+    ap.add_argument("--workload", default="se", choices=["se", "se_ag", "pe", "pe_stress", "cli"],
+                    help="se = configs[1] (the bench line), se_ag = configs[2], pe = configs[3], pe_stress = configs[4], "
+                         "cli = the walt program on files against the reference program")
+    ap.add_argument("--cli-genome-mb", type=float, default=300.0)
+    ap.add_argument("--cli-reads", type=int, default=5_000_000)
+    ap.add_argument("--no-cli", action="store_true", help="skip the files-in/files-out leg of the default run")
     ap.add_argument("--reads", type=int, default=0, help="reads (pairs) per GPU; default 10 M reads / 5 M pairs")
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--no-cpu", action="store_true", help="skip the oracle/reference side legs")
@@ -610,6 +750,8 @@ def main():
         args.warmup = 3
     if args.reads <= 0:
         args.reads = 5_000_000 if args.workload.startswith("pe") else 10_000_000
+    if args.workload == "cli":
+        sys.exit(run_cli(args))
     sys.exit(run_reference(args) if args.impl == "reference" else run_ours(args))
 
 

@@ -15,10 +15,16 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <fcntl.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
+#include <thread>
 #include <tuple>
 
 using namespace waltcore;
@@ -748,6 +754,81 @@ static int read_exact(FILE* f, void* dst, size_t n, const char* what) {
   return WALT_OK;
 }
 
+extern "C++" {
+// Pinned staging ring for the one-time index upload.  A few reader threads pread pieces of a
+// sub-index file into the ring in parallel (a single thread copies out of the page cache at a few
+// GB/s; the PCIe link takes ten times that), the calling thread consumes the pieces in file order.
+struct StageRing {
+  static constexpr size_t PIECE = 32u << 20;
+  static constexpr int SLOTS = 8, READERS = 6;
+  char* slot[SLOTS] = {};
+  ~StageRing() { for (char* p : slot) if (p) cudaFreeHost(p); }
+  int init() {
+    for (int i = 0; i < SLOTS; ++i) WALT_CUDA_TRY(cudaMallocHost(&slot[i], PIECE));
+    return WALT_OK;
+  }
+  // consume(host, offset_in_range, n) is called for consecutive pieces of [off, off + len) of fd;
+  // it must be done with `host` when it returns.
+  template <class F>
+  int stream(int fd, uint64_t off, uint64_t len, const char* what, F consume) {
+    const uint64_t np = (len + PIECE - 1) / PIECE;
+    if (np == 0) return WALT_OK;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<int> state(np, 0);          // 0 not read, 1 ready, 2 consumed, -1 read error
+    uint64_t consumed = 0;                  // pieces [0, consumed) are done with their slots
+    bool abort = false;
+    std::atomic<uint64_t> next{0};
+    auto reader = [&]() {
+      for (;;) {
+        const uint64_t k = next.fetch_add(1);
+        if (k >= np) return;
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [&]() { return abort || k < consumed + SLOTS; });
+          if (abort) return;
+        }
+        const uint64_t p0 = k * PIECE, n = std::min<uint64_t>(PIECE, len - p0);
+        char* dst = slot[k % SLOTS];
+        uint64_t got = 0;
+        bool ok = true;
+        while (got < n) {
+          const ssize_t r = pread(fd, dst + got, n - got, (off_t)(off + p0 + got));
+          if (r < 0 && errno == EINTR) continue;
+          if (r <= 0) { ok = false; break; }
+          got += (uint64_t)r;
+        }
+        {
+          std::lock_guard<std::mutex> lk(mu);
+          state[k] = ok ? 1 : -1;
+        }
+        cv.notify_all();
+      }
+    };
+    std::vector<std::thread> th;
+    const int nr = (int)std::min<uint64_t>(READERS, np);
+    for (int i = 0; i < nr; ++i) th.emplace_back(reader);
+    int rc = WALT_OK;
+    for (uint64_t k = 0; k < np && !rc; ++k) {
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&]() { return state[k] != 0; });
+        if (state[k] < 0) rc = fail(WALT_EIO, std::string("short read: ") + what);
+      }
+      if (!rc) rc = consume(slot[k % SLOTS], k * PIECE, std::min<uint64_t>(PIECE, len - k * PIECE));
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        consumed = k + 1;
+        if (rc) abort = true;
+      }
+      cv.notify_all();
+    }
+    for (auto& t : th) t.join();
+    return rc;
+  }
+};
+}  // extern "C++"
+
 // ReadIndexHeadInfo (reference.cpp:381-417) + ReadIndex (reference.cpp:324-351), once.
 int walt_engine_load_dbindex(walt_engine* e, const char* path, uint32_t which_mask) {
   if (!e || !path) return fail(WALT_EINVAL, "bad argument");
@@ -782,47 +863,58 @@ int walt_engine_load_dbindex(walt_engine* e, const char* path, uint32_t which_ma
 
   static const char* SFX[4] = {"_CT00", "_CT01", "_GA10", "_GA11"};
   uint8_t* d_stage = nullptr;
-  char* h_stage = nullptr;
-  WALT_CUDA_TRY(cudaMalloc(&d_stage, STAGE_BYTES));
-  WALT_CUDA_TRY(cudaMallocHost(&h_stage, STAGE_BYTES));
+  StageRing ring;
+  if ((rc = ring.init())) return rc;
+  WALT_CUDA_TRY(cudaMalloc(&d_stage, StageRing::PIECE));
   for (int which = 0; which < 4 && !rc; ++which) {
     if (!((which_mask >> which) & 1u)) continue;
     const std::string sp = std::string(path) + SFX[which];
-    FILE* g = fopen(sp.c_str(), "rb");
-    if (!g) { rc = fail(WALT_EIO, "cannot open " + sp + ": " + strerror(errno)); break; }
+    const int fd = open(sp.c_str(), O_RDONLY);
+    if (fd < 0) { rc = fail(WALT_EIO, "cannot open " + sp + ": " + strerror(errno)); break; }
+    auto pread_exact = [&](void* dst, size_t n, uint64_t at, const char* what) {
+      size_t got = 0;
+      while (got < n) {
+        const ssize_t r = pread(fd, (char*)dst + got, n - got, (off_t)(at + got));
+        if (r < 0 && errno == EINTR) continue;
+        if (r <= 0) return fail(WALT_EIO, std::string("short read: ") + what);
+        got += (size_t)r;
+      }
+      return (int)WALT_OK;
+    };
+    // file layout (reference.cpp:302-322): strand byte, genome, counter_size, index_size, counter[], index[]
     DeviceSubIndex& s = e->sub[which];
     s.release();
     char strand = 0;
-    rc = read_exact(g, &strand, 1, "strand byte");
+    rc = pread_exact(&strand, 1, 0, "strand byte");
     if (!rc && strand != ((which & 1) ? '-' : '+')) rc = fail(WALT_EFORMAT, sp + ": wrong strand byte");
     if (!rc) rc = alloc_packed_genome(e, s);
     if (!rc && cudaMemset(e->d_flags + 3, 0, 4) != cudaSuccess) rc = fail(WALT_ECUDA, "memset");
-    for (uint64_t off = 0; !rc && off < genome_len; off += STAGE_BYTES) {
-      const uint64_t n = std::min<uint64_t>(STAGE_BYTES, genome_len - off);
-      rc = read_exact(g, h_stage, n, "genome sequence");
-      if (!rc) rc = upload_genome_chunk(e, s, which, h_stage, off, n, d_stage);
-    }
+    if (!rc)
+      rc = ring.stream(fd, 1, genome_len, "genome sequence", [&](const char* host, uint64_t off, uint64_t n) {
+        return upload_genome_chunk(e, s, which, host, off, n, d_stage);
+      });
     uint32_t hdr[2] = {0, 0};
-    if (!rc) rc = read_exact(g, hdr, 8, "counter/index sizes");
+    const uint64_t at_hdr = 1u + (uint64_t)genome_len;
+    if (!rc) rc = pread_exact(hdr, 8, at_hdr, "counter/index sizes");
     if (!rc && hdr[0] != (1u << 24)) rc = fail(WALT_EFORMAT, sp + ": counter_size != 4^12");
     if (!rc && hdr[1] > size_of_index) rc = fail(WALT_EFORMAT, sp + ": index_size exceeds the header's size_of_index");
     // counter[] is superseded by the base-3 prefix table; only its last entry is checked
-    if (!rc && fseeko(g, (off_t)4 * (1u << 24), SEEK_CUR) != 0) rc = fail(WALT_EIO, "seek over counter[]");
     uint32_t last = 0;
-    if (!rc) rc = read_exact(g, &last, 4, "counter[4^12]");
+    if (!rc) rc = pread_exact(&last, 4, at_hdr + 8u + (uint64_t)4 * (1u << 24), "counter[4^12]");
     if (!rc && last != hdr[1]) rc = fail(WALT_EFORMAT, sp + ": counter[4^12] != index_size");
     if (!rc) {
       s.index_size = hdr[1];
       if (cudaMalloc(&s.index, ((size_t)s.index_size + 64u) * 4u) != cudaSuccess) rc = fail(WALT_ECUDA, "cudaMalloc(index)");
       else cudaMemset(s.index + s.index_size, 0, 64u * 4u);
     }
-    for (uint64_t off = 0; !rc && off < (uint64_t)s.index_size * 4u; off += STAGE_BYTES) {
-      const uint64_t n = std::min<uint64_t>(STAGE_BYTES, (uint64_t)s.index_size * 4u - off);
-      rc = read_exact(g, h_stage, n, "index[]");
-      if (!rc && cudaMemcpy((char*)s.index + off, h_stage, n, cudaMemcpyHostToDevice) != cudaSuccess)
-        rc = fail(WALT_ECUDA, "index upload");
-    }
-    fclose(g);
+    if (!rc)
+      rc = ring.stream(fd, at_hdr + 8u + (uint64_t)4 * ((1u << 24) + 1u), (uint64_t)s.index_size * 4u, "index[]",
+                       [&](const char* host, uint64_t off, uint64_t n) {
+                         if (cudaMemcpy((char*)s.index + off, host, n, cudaMemcpyHostToDevice) != cudaSuccess)
+                           return fail(WALT_ECUDA, "index upload");
+                         return (int)WALT_OK;
+                       });
+    close(fd);
     if (!rc) {
       uint32_t bad = 0;
       cudaMemcpy(&bad, e->d_flags + 3, 4, cudaMemcpyDeviceToHost);
@@ -831,7 +923,6 @@ int walt_engine_load_dbindex(walt_engine* e, const char* path, uint32_t which_ma
     if (!rc) rc = finalize_subindex(e, which);
   }
   cudaFree(d_stage);
-  cudaFreeHost(h_stage);
   return rc;
 }
 

@@ -183,3 +183,20 @@ def set_threads(n):
 def set_grain(chunk_bytes=0, block_reads=0):
     """Tuning/test hook: loader task size in bytes and writer task size in reads (0 = default)."""
     load_library().walt_host_set_grain(C.c_uint32(chunk_bytes), C.c_uint32(block_reads))
+
+
+def write_subindex(path, strand, seq, counter, index):
+    """WriteIndex (reference.cpp:302-322): one _CT00/_CT01/_GA10/_GA11 file."""
+    L = load_library()
+    seq = np.ascontiguousarray(seq, np.uint8)
+    counter = np.ascontiguousarray(counter, np.uint32)
+    index = np.ascontiguousarray(index, np.uint32)
+    if L.walt_write_subindex(path.encode(), C.c_char(strand.encode()), _p(seq), C.c_uint64(seq.size), _p(counter),
+                             _p(index), C.c_uint32(index.size)):
+        raise _err()
+
+
+def write_dbindex_header(path, chroms, size_of_index):
+    """WriteIndexHeadInfo (reference.cpp:353-379)."""
+    if load_library().walt_write_dbindex_header(path.encode(), chroms.h, C.c_uint32(size_of_index)):
+        raise _err()
