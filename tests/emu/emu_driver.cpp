@@ -481,6 +481,29 @@ int emu_stdsort_both(const uint32_t* cls, uint32_t n, uint32_t* out_ours, uint32
   return fb;
 }
 
+// the same sort run the way the device builder runs it: level by level, one task at a time
+void emu_stdsort_levels(const uint32_t* cls, uint32_t n, uint32_t* out_pos, uint32_t* n_levels) {
+  std::vector<uint32_t> c(cls, cls + n), p(n);
+  for (uint32_t i = 0; i < n; ++i) p[i] = i;
+  const waltsort::PairSeq seq{p.data(), c.data()};
+  std::vector<waltsort::SortTask> cur, nxt;
+  if (n) cur.push_back(waltsort::SortTask{0u, n, waltsort::depth_limit_for(n)});
+  uint32_t levels = 0;
+  while (!cur.empty()) {
+    nxt.clear();
+    // any order inside a level is as good as any other: go backwards to make that point
+    for (size_t i = cur.size(); i-- > 0;) {
+      waltsort::SortTask kids[2];
+      const int k = waltsort::sort_task_step(seq, cur[i], waltsort::ByClass(), kids);
+      for (int j = 0; j < k; ++j) nxt.push_back(kids[j]);
+    }
+    cur.swap(nxt);
+    ++levels;
+  }
+  memcpy(out_pos, p.data(), (size_t)n * 4u);
+  if (n_levels) *n_levels = levels;
+}
+
 // the builder's "back to ascending position" step: heap sort by position of (pos, cls) pairs
 void emu_heapsort_by_pos(uint32_t* pos, uint32_t* cls, uint32_t n) {
   waltsort::heap_sort_(waltsort::PairSeq{pos, cls}, 0, (int64_t)n, waltsort::ByPos());

@@ -19,6 +19,15 @@ def _both(cls):
     return ours, std, fb
 
 
+def _levels(cls):
+    L = emu.lib()
+    cls = np.ascontiguousarray(cls, dtype=np.uint32)
+    out = np.zeros(cls.size, np.uint32)
+    lv = C.c_uint32(0)
+    L.emu_stdsort_levels(cls.ctypes.data_as(C.c_void_p), C.c_uint32(cls.size), out.ctypes.data_as(C.c_void_p), C.byref(lv))
+    return out, int(lv.value)
+
+
 def _killer(n):
     out = np.zeros(n, np.uint32)
     emu.lib().emu_antiqsort(C.c_uint32(n), out.ctypes.data_as(C.c_void_p))
@@ -34,6 +43,7 @@ def test_random_with_ties(n, n_classes):
         ours, std, _ = _both(cls)
         assert np.array_equal(ours, std)
         assert np.all(np.diff(cls[ours].astype(np.int64)) >= 0)
+        assert np.array_equal(_levels(cls)[0], std)     # the task-tree form the device runs
 
 
 @pytest.mark.parametrize("n", [17, 64, 1000, 30000])
@@ -44,6 +54,7 @@ def test_structured_inputs(n):
     for cls in cases:
         ours, std, _ = _both(cls)
         assert np.array_equal(ours, std)
+        assert np.array_equal(_levels(cls)[0], std)
 
 
 @pytest.mark.parametrize("n", [200, 3000, 40000])
@@ -54,6 +65,10 @@ def test_depth_limit_fallback(n, div):
     cls = _killer(n) // div
     ours, std, fb = _both(cls)
     assert np.array_equal(ours, std)
+    by_levels, n_levels = _levels(cls)
+    assert np.array_equal(by_levels, std)
+    if div == 1:
+        assert n_levels > 2 * int(np.log2(n)), "the depth limit was not reached in the task-tree form"
     if div == 1:
         assert fb > 0, "the adversary did not reach the depth limit: the fallback path is untested"
 

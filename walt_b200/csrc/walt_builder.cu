@@ -155,27 +155,39 @@ __global__ void kept_counts_kernel(const uint32_t* __restrict__ raw_hist, uint32
   counts[k] = c >= BUCKET_ERASE ? 0u : c;
 }
 
-// One thread per 12-mer bucket.  A bucket whose class ranks are all distinct has a unique sorted
-// order and is left alone; otherwise: back to the arrangement HashToBucket produced (ascending
-// position, reference.cpp:231-256), then std::sort's exact sequence of swaps with "class rank
-// less" standing in for the genome comparator.
-__global__ void tie_replay_kernel(const uint32_t* __restrict__ starts, uint32_t* __restrict__ index,
-                                  uint32_t* __restrict__ scratch_pos, uint32_t* __restrict__ cls,
-                                  unsigned long long* __restrict__ n_replayed) {
+// One thread per 12-mer bucket: a bucket whose class ranks are not all distinct becomes the root
+// task of a std::sort replay.  (A bucket with distinct ranks has one sorted order: left alone.)
+__global__ void tie_seed_kernel(const uint32_t* __restrict__ starts, const uint32_t* __restrict__ cls,
+                                waltsort::SortTask* __restrict__ seeds, unsigned long long* __restrict__ n_seeds) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= N_KEY12) return;
   const uint64_t s = starts[k], e = starts[k + 1u];
   if (e - s < 2u) return;
   if ((uint64_t)(cls[e - 1u] - cls[s]) + 1u == e - s) return;
-  uint32_t* p = scratch_pos + s;
-  uint32_t* c = cls + s;
-  const int64_t n = (int64_t)(e - s);
-  for (int64_t i = 0; i < n; ++i) p[i] = index[s + i];
-  const waltsort::PairSeq seq{p, c};
-  waltsort::std_sort(seq, 0, n, waltsort::ByPos());   // positions are distinct: any sort gives this order
-  waltsort::std_sort(seq, 0, n, waltsort::ByClass());
-  for (int64_t i = 0; i < n; ++i) index[s + i] = p[i];
-  atomicAdd(n_replayed, 1ull);
+  const unsigned long long at = atomicAdd(n_seeds, 1ull);
+  seeds[at] = waltsort::SortTask{(uint32_t)s, (uint32_t)e, waltsort::depth_limit_for(e - s)};
+}
+
+// One level of the task tree (walt_stdsort.cuh): one thread per task, children appended to the
+// next level's list.  BY_POS = true first brings every tie bucket back to the arrangement
+// HashToBucket produced (ascending position, reference.cpp:231-256; positions are distinct, so
+// any sort gives it), BY_POS = false is std::sort's exact sequence of swaps with "class rank less"
+// standing in for the genome comparator.
+template <bool BY_POS>
+__global__ void sort_level_kernel(const waltsort::SortTask* __restrict__ in, unsigned long long n_in,
+                                  uint32_t* __restrict__ pos, uint32_t* __restrict__ cls,
+                                  waltsort::SortTask* __restrict__ out, unsigned long long* __restrict__ n_out) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_in) return;
+  const waltsort::PairSeq seq{pos, cls};
+  waltsort::SortTask kids[2];
+  int k;
+  if (BY_POS) k = waltsort::sort_task_step(seq, in[i], waltsort::ByPos(), kids);
+  else k = waltsort::sort_task_step(seq, in[i], waltsort::ByClass(), kids);
+  if (k) {
+    const unsigned long long at = atomicAdd(n_out, (unsigned long long)k);
+    for (int j = 0; j < k; ++j) out[at + j] = kids[j];
+  }
 }
 
 // ---- export helpers --------------------------------------------------------------------------
@@ -428,26 +440,26 @@ static int build_subindex_device(walt_engine* e, int which, const uint64_t* d_fw
       cudaError_t ce = cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, dk, dv, (uint64_t)n, 0, 2 * DIGITS_PER_PASS);
       if (ce != cudaSuccess) { cleanup(); cudaFree(vals[0]); cudaFree(vals[1]); return fail(WALT_ECUDA, std::string("radix sort: ") + cudaGetErrorString(ce)); }
     }
-    // tie order: class ranks from the sorted order, then std::sort replayed per bucket with ties
+    // tie order: class ranks from the sorted order, then std::sort replayed on the tie buckets
     e->last_build_ties = 0; e->last_build_replayed = 0;
+    uint32_t* final_index = dv.Current();
     if (n > 1 && e->tie_order == 0) {
       auto bail = [&](const char* what, cudaError_t ce) {
         cleanup(); cudaFree(vals[0]); cudaFree(vals[1]);
         return fail(WALT_ECUDA, std::string(what) + ": " + cudaGetErrorString(ce));
       };
-      uint32_t* head = dk.Current();
-      unsigned long long* d_ctr = nullptr;
-      if (cudaMalloc(&d_ctr, 16) != cudaSuccess) return bail("cudaMalloc", cudaGetLastError());
-      cudaMemset(d_ctr, 0, 16);
-      tie_head_kernel<<<blocks_for(n, T), T>>>(s.genome, cv, ag, dv.Current(), n, head, d_ctr);
-      unsigned long long ctr[2] = {0, 0};
-      cudaError_t ce = cudaMemcpy(ctr, d_ctr, 16, cudaMemcpyDeviceToHost);
+      uint32_t* cls = dk.Current();          // head flags, then class ranks, in sorted order
+      uint32_t* work_pos = dk.Alternate();   // the array the replay permutes
+      unsigned long long* d_ctr = nullptr;   // [0] tied slots, [1] seeds, [2] next level's tasks
+      if (cudaMalloc(&d_ctr, 32) != cudaSuccess) return bail("cudaMalloc", cudaGetLastError());
+      cudaMemset(d_ctr, 0, 32);
+      tie_head_kernel<<<blocks_for(n, T), T>>>(s.genome, cv, ag, dv.Current(), n, cls, d_ctr);
+      unsigned long long ctr[3] = {0, 0, 0};
+      cudaError_t ce = cudaMemcpy(ctr, d_ctr, 24, cudaMemcpyDeviceToHost);
       if (ce != cudaSuccess) { cudaFree(d_ctr); return bail("tie detection", ce); }
       if (ctr[0] > 0) {
-        // the sort's temp storage is far larger than a scan's; check anyway
-        size_t need = 0;
-        cub::DeviceScan::InclusiveSum(nullptr, need, head, head, (::cuda::std::int64_t)n);
-        size_t need2 = 0;
+        size_t need = 0, need2 = 0;
+        cub::DeviceScan::InclusiveSum(nullptr, need, cls, cls, (::cuda::std::int64_t)n);
         cub::DeviceScan::ExclusiveSum(nullptr, need2, d_starts, d_starts, (int)(N_KEY12 + 1u));
         need = std::max(need, need2);
         if (need > temp_bytes) {
@@ -455,20 +467,52 @@ static int build_subindex_device(walt_engine* e, int which, const uint64_t* d_fw
           if (cudaMalloc(&d_temp, temp_bytes) != cudaSuccess) { cudaFree(d_ctr); return bail("cudaMalloc(scan temp)", cudaGetLastError()); }
         }
         size_t tb = temp_bytes;
-        cub::DeviceScan::InclusiveSum(d_temp, tb, head, head, (::cuda::std::int64_t)n);
+        cub::DeviceScan::InclusiveSum(d_temp, tb, cls, cls, (::cuda::std::int64_t)n);
         tb = temp_bytes;
         cub::DeviceScan::ExclusiveSum(d_temp, tb, d_starts, d_starts, (int)(N_KEY12 + 1u));
-        tie_replay_kernel<<<blocks_for(N_KEY12, 32), 32>>>(d_starts, dv.Current(), dk.Alternate(), head, d_ctr + 1);
-        ce = cudaMemcpy(ctr, d_ctr, 16, cudaMemcpyDeviceToHost);
+        waltsort::SortTask* seeds = nullptr;
+        if (cudaMalloc(&seeds, (size_t)N_KEY12 * sizeof(waltsort::SortTask)) != cudaSuccess) { cudaFree(d_ctr); return bail("cudaMalloc(seeds)", cudaGetLastError()); }
+        tie_seed_kernel<<<blocks_for(N_KEY12, T), T>>>(d_starts, cls, seeds, d_ctr + 1);
+        cudaMemcpy(ctr, d_ctr, 24, cudaMemcpyDeviceToHost);
+        // the replay permutes a copy; buckets without ties keep what the radix sort left
+        cudaMemcpyAsync(work_pos, dv.Current(), (size_t)n * 4u, cudaMemcpyDeviceToDevice);
+        // two task lists inside the free value buffer: a level holds at most n / 17 tasks
+        waltsort::SortTask* lists[2];
+        lists[0] = (waltsort::SortTask*)dv.Alternate();
+        lists[1] = lists[0] + ((size_t)n / 17u + 2u);
+        auto run = [&](bool by_pos) -> cudaError_t {
+          const waltsort::SortTask* in = seeds;
+          unsigned long long n_in = ctr[1];
+          int flip = 0;
+          while (n_in > 0) {
+            cudaMemsetAsync(d_ctr + 2, 0, 8);
+            const uint32_t TB = 64;
+            if (by_pos) sort_level_kernel<true><<<blocks_for(n_in, TB), TB>>>(in, n_in, work_pos, cls, lists[flip], d_ctr + 2);
+            else sort_level_kernel<false><<<blocks_for(n_in, TB), TB>>>(in, n_in, work_pos, cls, lists[flip], d_ctr + 2);
+            unsigned long long n_out = 0;
+            const cudaError_t rc2 = cudaMemcpy(&n_out, d_ctr + 2, 8, cudaMemcpyDeviceToHost);
+            if (rc2 != cudaSuccess) return rc2;
+            in = lists[flip]; n_in = n_out; flip ^= 1;
+          }
+          return cudaSuccess;
+        };
+        ce = run(true);
+        if (ce == cudaSuccess) ce = run(false);
+        cudaFree(seeds);
         if (ce != cudaSuccess) { cudaFree(d_ctr); return bail("tie replay", ce); }
+        final_index = work_pos;
       }
       cudaFree(d_ctr);
       e->last_build_ties = ctr[0]; e->last_build_replayed = ctr[1];
     }
     cudaError_t ce = cudaDeviceSynchronize();
     if (ce != cudaSuccess) { cleanup(); cudaFree(vals[0]); cudaFree(vals[1]); return fail(WALT_ECUDA, std::string("index build: ") + cudaGetErrorString(ce)); }
-    s.index = dv.Current();
-    cudaFree(dv.Alternate());
+    // keep the buffer that holds the finished index, free the other three
+    s.index = final_index;
+    for (int i = 0; i < 2; ++i) {
+      if (vals[i] != final_index) cudaFree(vals[i]);
+      if (keys[i] == final_index) keys[i] = nullptr;
+    }
   }
   cleanup();
   s.index_size = (uint32_t)n;

@@ -221,4 +221,41 @@ WALT_SORT_HD int std_sort(const PairSeq& s, int64_t first, int64_t last, Cmp com
   return fallbacks;
 }
 
+// ---- the same sort as a tree of independent tasks ----------------------------------------------
+// After a partition the two sides never interact again: __introsort_loop sorts [cut, last) by
+// recursion and [first, cut) by iteration, and the closing __final_insertion_sort never moves an
+// element across a partition boundary (everything left of a cut is <= everything right of it,
+// and the insertion loops stop at the first element that is not greater).  Inside one leaf
+// (a range of <= 16 elements, or a heap-sorted range) the final pass is a plain stable insertion
+// sort.  So std::sort == process(first, last, 2 * lg(n)) with
+//     process(f, l, d):  l - f <= 16 -> stable insertion sort
+//                        d == 0      -> heap sort
+//                        else        -> cut = partition(f, l); process(f, cut, d-1); process(cut, l, d-1)
+// and the two recursive calls may run concurrently.  The device builder runs this level by level
+// (one thread per task, children appended to the next level's list), which turns the n log n
+// serial steps of a 500 000-entry bucket into ~2n.
+struct SortTask { uint32_t first, last, depth; };   // slots [first, last) of the whole index
+
+WALT_SORT_HD uint32_t depth_limit_for(uint64_t n) {
+  uint32_t lg = 0;
+  for (; n > 1; n >>= 1) ++lg;
+  return 2u * lg;
+}
+
+// One task.  Children that still need partitioning are written to out[0..return value).
+template <class Cmp>
+WALT_SORT_HD int sort_task_step(const PairSeq& s, SortTask t, Cmp comp, SortTask out[2]) {
+  constexpr int64_t THRESHOLD = 16;
+  const int64_t first = t.first, last = t.last;
+  if (last - first <= THRESHOLD) { insertion_sort_(s, first, last, comp); return 0; }
+  if (t.depth == 0) { heap_sort_(s, first, last, comp); return 0; }
+  const int64_t cut = unguarded_partition_pivot_(s, first, last, comp);
+  int k = 0;
+  if (cut - first <= THRESHOLD) insertion_sort_(s, first, cut, comp);
+  else out[k++] = SortTask{(uint32_t)first, (uint32_t)cut, t.depth - 1u};
+  if (last - cut <= THRESHOLD) insertion_sort_(s, cut, last, comp);
+  else out[k++] = SortTask{(uint32_t)cut, (uint32_t)last, t.depth - 1u};
+  return k;
+}
+
 }  // namespace waltsort
