@@ -172,7 +172,8 @@ int walt_engine_last_stats(const walt_engine* e, walt_stats* out);
  * lookup (the in-repo device oracle; same results, slower). */
 int walt_engine_set_search_mode(walt_engine* e, int mode);
 /* Tuning/test hooks: prefix-table depth for sub-indexes loaded afterwards (0 = auto, else
- * 12..20) and the number of reads per in-flight host chunk (default 2^18; three chunks in flight). */
+ * 12..20) and the number of reads per in-flight host chunk (0 = automatic: 2^18 for ASCII batches,
+ * 2^19 for packed ones; three chunks in flight). */
 int walt_engine_set_table_depth(walt_engine* e, int depth);
 int walt_engine_set_chunk_reads(walt_engine* e, uint32_t n);
 /* Lanes of a warp that cooperate on one read: 8 (default; four reads per warp), 16 or 32. */

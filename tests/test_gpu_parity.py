@@ -90,7 +90,7 @@ def test_se_chunked_pipeline_matches_single_chunk(engine):
     try:
         out, _ = engine.map_se(buf, offs, m=6, b=5000)
     finally:
-        engine.set_chunk_reads(1 << 18)
+        engine.set_chunk_reads(0)
     _cmp_best(out, z["best_m6_b5000"])
 
 
@@ -112,7 +112,7 @@ def test_se_packed_input_golden(engine, width):
                 assert short == int(z[key.replace("best", "short")])
             engine.set_chunk_reads(257)
             out, _ = engine.map_se_packed(packed, offs, ag=ag, m=6, b=5000)
-            engine.set_chunk_reads(1 << 18)
+            engine.set_chunk_reads(0)
             _cmp_best(out, z["best_m6_b5000"], "chunked")
         z = goldenio.load("se_edge.npz")
         packed = host.pack_reads_2bit(z["buf"], z["offs"])
@@ -126,7 +126,7 @@ def test_se_packed_input_golden(engine, width):
                     assert short == int(z[key.replace("best", "short")])
     finally:
         engine.set_group_width(8)
-        engine.set_chunk_reads(1 << 18)
+        engine.set_chunk_reads(0)
 
 
 def test_se_empty_and_errors(engine):
@@ -328,7 +328,7 @@ def test_pe_compact_and_device_paths_match_ranked(engine, pbat):
                 pk, p1, p2 = engine.map_pe_compact_packed(host.pack_reads_2bit(b1, o1), o1, host.pack_reads_2bit(b2, o2),
                                                           o2, m=m, top_k=k, frag_range=L, pbat=pbat)
             finally:
-                engine.set_chunk_reads(1 << 18)
+                engine.set_chunk_reads(0)
             assert (p1, p2) == (s1, s2) and np.array_equal(pk, comp), chunk
         # device-resident path
         dev = "cuda:0"

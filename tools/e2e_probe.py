@@ -47,6 +47,24 @@ def main():
         torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 3
         print(json.dumps({"probe": "e2e", "chunk_reads": chunk, "ms": dt * 1e3, "reads_per_s": n / dt,
                           "env": {k: v for k, v in os.environ.items() if k.startswith("WALT_")}}), flush=True)
+    packed_sweep(wl, h_reads, h_offs, h_out, n)
+
+
+def packed_sweep(wl, h_reads, h_offs, h_out, n):
+    """the same sweep for walt_engine_map_se_packed (the call the walt program makes)"""
+    from walt_b200 import host as wh
+    from walt_b200.engine import PinnedArray
+    h_pk = PinnedArray(((n * wl.rl >> 2) + n + 16,), np.uint8)
+    wh.pack_reads_2bit(h_reads.array, h_offs.array, out=h_pk.array)
+    for chunk in [int(x) for x in os.environ.get("CHUNKS", "131072,262144,524288,1048576,2097152").split(",")]:
+        wl.e.set_chunk_reads(chunk)
+        for _ in range(2):
+            wl.e.map_se_packed(h_pk.array, h_offs.array, ag=False, m=6, b=5000, out=h_out.array)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(3):
+            wl.e.map_se_packed(h_pk.array, h_offs.array, ag=False, m=6, b=5000, out=h_out.array)
+        torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 3
+        print(json.dumps({"probe": "e2e_packed", "chunk_reads": chunk, "ms": dt * 1e3, "reads_per_s": n / dt}), flush=True)
 
 
 if __name__ == "__main__":

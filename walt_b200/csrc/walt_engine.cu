@@ -10,6 +10,7 @@
 // the kernels' warp policy and launch geometry, and the double-buffered host<->device batch
 // pipeline.  There is no CPU fallback: without a CUDA device every entry point fails.
 #include "walt_engine.cuh"
+#include "walt_hostscan.h"
 
 #include <errno.h>
 #include <stdio.h>
@@ -22,6 +23,7 @@
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -306,16 +308,34 @@ __device__ __forceinline__ const char* read_at(const Args& a, uint32_t r, uint32
   return a.seqs + (o0 - a.seq_base);
 }
 
+// Work counters and the non-ACGT flag leave the kernel through ONE set of global atomics per
+// CTA: every group adds into shared memory, thread 0 publishes after the barrier.  (One set per
+// group would be ~57 000 same-address atomics arriving together in the tail of every launch --
+// a fixed ~0.2 ms that dominated 262 144-read chunk launches.)
+struct BlockTally { unsigned long long c[3]; unsigned int bad; };
+
+__device__ __forceinline__ void tally_init(BlockTally& t) {
+  if (threadIdx.x == 0) { t.c[0] = t.c[1] = t.c[2] = 0ull; t.bad = 0u; }
+  __syncthreads();
+}
+
 template <uint32_t WD>
-__device__ __forceinline__ void flush_counters(const HwGroup<WD>& w, const Counters& ctr, bool bad, uint32_t* flags,
-                                               unsigned long long* counters) {
+__device__ __forceinline__ void flush_counters(const HwGroup<WD>& w, const Counters& ctr, bool bad, BlockTally& t,
+                                               uint32_t* flags, unsigned long long* counters) {
   const uint32_t a = w.reduce_add(ctr.lookups), b = w.reduce_add(ctr.candidates), c = w.reduce_add(ctr.literal);
   if (w.lane() == 0) {
-    if (bad) atomicOr(flags, 1u);
+    if (bad) atomicOr(&t.bad, 1u);
+    if (a) atomicAdd(&t.c[0], (unsigned long long)a);
+    if (b) atomicAdd(&t.c[1], (unsigned long long)b);
+    if (c) atomicAdd(&t.c[2], (unsigned long long)c);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (t.bad) atomicOr(flags, 1u);
     if (counters) {
-      atomicAdd(counters + 0, (unsigned long long)a);
-      atomicAdd(counters + 1, (unsigned long long)b);
-      atomicAdd(counters + 2, (unsigned long long)c);
+      if (t.c[0]) atomicAdd(counters + 0, t.c[0]);
+      if (t.c[1]) atomicAdd(counters + 1, t.c[1]);
+      if (t.c[2]) atomicAdd(counters + 2, t.c[2]);
     }
   }
 }
@@ -324,6 +344,8 @@ template <uint32_t WD, bool PACKED>
 __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS_PER_SM)
 se_map_kernel(const __grid_constant__ SeArgs a) {
   extern __shared__ uint64_t smem[];
+  __shared__ BlockTally tally;
+  tally_init(tally);
   HwGroup<WD> w;
   const uint32_t lane = w.lane();
   const uint32_t group_in_block = threadIdx.x / WD;
@@ -349,7 +371,7 @@ se_map_kernel(const __grid_constant__ SeArgs a) {
     }
     __syncwarp();
   }
-  flush_counters(w, ctr, bad, a.flags, a.counters);
+  flush_counters(w, ctr, bad, tally, a.flags, a.counters);
 }
 
 struct PeArgs {
@@ -379,6 +401,8 @@ template <uint32_t WD, bool PACKED>
 __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS_PER_SM)
 pe_map_kernel(const __grid_constant__ PeArgs a) {
   extern __shared__ uint64_t smem[];
+  __shared__ BlockTally tally;
+  tally_init(tally);
   HwGroup<WD> w;
   const uint32_t lane = w.lane();
   const uint32_t group_in_block = threadIdx.x / WD;
@@ -420,7 +444,7 @@ pe_map_kernel(const __grid_constant__ PeArgs a) {
     }
     __syncwarp();
   }
-  flush_counters(w, ctr, bad, a.flags, a.counters);
+  flush_counters(w, ctr, bad, tally, a.flags, a.counters);
 }
 
 struct GetRanked {
@@ -486,12 +510,16 @@ static size_t pe_smem_bytes(uint32_t nw_max, uint32_t top_k, uint32_t wd) {
 }
 
 template <class K>
-static int grid_for(walt_engine* e, K kernel, size_t smem, uint32_t n, uint32_t wd, uint32_t* grid) {
+static int grid_for(walt_engine* e, K kernel, size_t smem, uint32_t n, uint32_t wd, uint32_t* grid, uint32_t share = 1) {
   int per_sm = 0;
   WALT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   WALT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)BLOCK_THREADS, smem));
   if (per_sm < 1) return fail(WALT_ECUDA, "mapping kernel does not fit on an SM");
-  uint64_t g = (uint64_t)per_sm * (uint64_t)e->sm_count;   // persistent: a multiple of the SM count
+  // persistent: a multiple of the SM count.  share > 1: this launch is one of several chunk kernels in
+  // flight (host batches) and takes per_sm / share CTA slots per SM, so that the next chunk's kernel
+  // runs beside it and each launch's ramp-up and tail overlap the other's steady state.
+  per_sm = std::max<int>(1, per_sm / (int)std::max<uint32_t>(1u, share));
+  uint64_t g = (uint64_t)per_sm * (uint64_t)e->sm_count;
   const uint32_t per_block = BLOCK_THREADS / wd;
   const uint64_t need = ((uint64_t)n + per_block - 1) / per_block;
   if (need < g) g = need ? need : 1;
@@ -533,7 +561,7 @@ static void fill_common(walt_engine* e, Args& a, const ReadSrc& src, uint32_t n,
 }
 
 static int launch_se(walt_engine* e, const ReadSrc& src, uint32_t n, int ag, uint32_t m, uint32_t b, walt_best* d_out,
-                     uint32_t* d_queue, cudaStream_t st) {
+                     uint32_t* d_queue, cudaStream_t st, uint32_t share = 1) {
   if (src.max_len > MAX_READ_LEN) return fail(WALT_EINVAL, "read longer than 1024 bases");
   SeArgs a;
   fill_common(e, a, src, n, ag, m, b, d_queue);
@@ -543,7 +571,7 @@ static int launch_se(walt_engine* e, const ReadSrc& src, uint32_t n, int ag, uin
   uint32_t grid = 0;
   auto kernel = src.packed ? (wd == 8u ? se_map_kernel<8, true> : wd == 16u ? se_map_kernel<16, true> : se_map_kernel<32, true>)
                            : (wd == 8u ? se_map_kernel<8, false> : wd == 16u ? se_map_kernel<16, false> : se_map_kernel<32, false>);
-  int rc = grid_for(e, kernel, smem, n, wd, &grid);
+  int rc = grid_for(e, kernel, smem, n, wd, &grid, share);
   if (rc) return rc;
   WALT_CUDA_TRY(cudaMemsetAsync(d_queue, 0, 4, st));
   kernel<<<grid, BLOCK_THREADS, smem, st>>>(a);
@@ -599,24 +627,40 @@ static int fetch_status(walt_engine* e) {
   return WALT_OK;
 }
 
-// One pass over the offsets of reads [r0, r0 + cn): longest read, reads below the 38-base minimum,
-// and the common length if all reads share one (0 otherwise).  Run per chunk, while the copies of
-// the previous chunk are in flight.
-struct ChunkScan { uint32_t max_len, n_short, uniform_len; };
-static ChunkScan scan_chunk(const uint64_t* offs, uint32_t r0, uint32_t cn) {
-  ChunkScan c{0u, 0u, 0u};
-  bool uniform = cn > 0;
-  const uint64_t first = cn ? offs[r0 + 1] - offs[r0] : 0;
-  for (uint32_t i = r0; i < r0 + cn; ++i) {
-    const uint64_t l = offs[i + 1] - offs[i];
-    if (l > 0xFFFFFFFFull) { c.max_len = 0xFFFFFFFFu; return c; }
-    c.max_len = std::max<uint32_t>(c.max_len, (uint32_t)l);
-    c.n_short += l < MIN_READ_LEN ? 1u : 0u;
-    uniform &= l == first;
+// scan_chunk (one pass over a chunk's read offsets) lives in walt_hostscan.cpp.
+//
+// One core streams the offsets at ~5 GB/s: 80 MB for ten million reads is 15 ms, longer than the GPU
+// needs to map them.  AheadScans runs the per-chunk scans of a batch on a few helper threads, ahead
+// of the loop that queues the chunks; get(k) waits for chunk k's result.
+struct AheadScans {
+  std::vector<ChunkScan> res[2];
+  std::unique_ptr<std::atomic<int>[]> ready;
+  std::vector<std::thread> th;
+  AheadScans(const uint64_t* offs1, const uint64_t* offs2, uint32_t n, uint32_t chunk) {
+    const uint32_t nk = (n + chunk - 1) / chunk;
+    res[0].resize(nk); res[1].resize(nk);
+    ready.reset(new std::atomic<int>[nk ? nk : 1]);
+    for (uint32_t k = 0; k < nk; ++k) ready[k].store(0, std::memory_order_relaxed);
+    auto one = [=](uint32_t k) {
+      const uint32_t r0 = k * chunk, cn = std::min<uint32_t>(chunk, n - r0);
+      res[0][k] = scan_chunk(offs1, r0, cn);
+      if (offs2) res[1][k] = scan_chunk(offs2, r0, cn);
+      ready[k].store(1, std::memory_order_release);
+    };
+    const uint32_t T = nk >= 8 ? 4u : 0u;   // small batches: scanned inline by get()
+    for (uint32_t t = 0; t < T; ++t)
+      th.emplace_back([=]() { for (uint32_t k = t; k < nk; k += T) one(k); });
+    if (!T) inline_one = one;
   }
-  if (uniform && first > 0) c.uniform_len = (uint32_t)first;
-  return c;
-}
+  std::function<void(uint32_t)> inline_one;
+  void get(uint32_t k, ChunkScan* a, ChunkScan* b) {
+    if (inline_one) inline_one(k);
+    while (!ready[k].load(std::memory_order_acquire)) std::this_thread::yield();
+    *a = res[0][k];
+    if (b) *b = res[1][k];
+  }
+  ~AheadScans() { for (auto& t : th) t.join(); }
+};
 
 }  // namespace waltb200
 
@@ -647,6 +691,7 @@ int walt_engine_create(walt_engine** out, int device) {
   // undocumented tuning knobs for experiments (defaults are what bench.py measures)
   if (const char* v = getenv("WALT_MIN_BLOCKS")) e->min_blocks = atoi(v);
   if (const char* v = getenv("WALT_PE_SIDE")) e->pe_side = atoi(v);
+  if (const char* v = getenv("WALT_CHUNK_SHARE")) e->chunk_share = (uint32_t)std::max(1, atoi(v));
   if (const char* v = getenv("WALT_L2_FETCH")) WALT_CUDA_TRY(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(v)));
   uint32_t p = 1;
   for (uint32_t i = 0; i <= MAX_DEPTH; ++i) { e->pow3.v[i] = p; p *= 3u; }
@@ -985,8 +1030,8 @@ int walt_engine_set_group_width(walt_engine* e, uint32_t lanes) {
 }
 
 int walt_engine_set_chunk_reads(walt_engine* e, uint32_t n) {
-  if (!e || n == 0) return fail(WALT_EINVAL, "chunk size must be positive");
-  e->chunk_reads = n;
+  if (!e) return fail(WALT_EINVAL, "bad argument");
+  e->chunk_reads = n;   // 0 = automatic
   return WALT_OK;
 }
 
@@ -1027,9 +1072,14 @@ static int map_se_host(walt_engine* e, const char* seqs, const uint64_t* offs, u
   WALT_CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, 3 * 8, e->slot[0].stream));
   WALT_CUDA_TRY(cudaStreamSynchronize(e->slot[0].stream));
   uint32_t k = 0, total_short = 0;
-  for (uint32_t r0 = 0; r0 < n; r0 += e->chunk_reads, ++k) {
-    const uint32_t cn = std::min<uint32_t>(e->chunk_reads, n - r0);
-    const ChunkScan sc = scan_chunk(offs, r0, cn);   // overlaps the previous chunk's copies and kernel
+  // chunk size: ASCII batches are PCIe-bound and like a short pipeline fill; packed batches are
+  // kernel-bound and like fewer launches (measured: 2^18 resp. 2^19 reads)
+  const uint32_t chunk = e->chunk_reads ? e->chunk_reads : (packed ? 1u << 19 : 1u << 18);
+  AheadScans scans(offs, nullptr, n, chunk);
+  for (uint32_t r0 = 0; r0 < n; r0 += chunk, ++k) {
+    const uint32_t cn = std::min<uint32_t>(chunk, n - r0);
+    ChunkScan sc;
+    scans.get(k, &sc, nullptr);
     if (sc.max_len > MAX_READ_LEN) {
       for (auto& s : e->slot) cudaStreamSynchronize(s.stream);
       return fail(WALT_EINVAL, "read longer than 1024 bases");
@@ -1048,7 +1098,7 @@ static int map_se_host(walt_engine* e, const char* seqs, const uint64_t* offs, u
     }
     const ReadSrc src{s.d_seqs, s.d_offs, offs[r0], sc.uniform_len, 0, sc.max_len, packed};
     if ((rc = launch_se(e, src, cn, ag_wildcard, max_mismatches, b, (walt_best*)s.d_out, e->d_flags + 4 + (k % N_SLOTS),
-                        s.stream)))
+                        s.stream, e->chunk_share)))
       return rc;
     WALT_CUDA_TRY(cudaMemcpyAsync(out + r0, s.d_out, (size_t)cn * sizeof(walt_best), cudaMemcpyDeviceToHost, s.stream));
     WALT_CUDA_TRY(cudaEventRecord(s.done, s.stream));
@@ -1134,11 +1184,13 @@ static int map_pe_host(walt_engine* e, const char* seqs1, const uint64_t* offs1,
   WALT_CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, 3 * 8, e->slot[0].stream));
   WALT_CUDA_TRY(cudaStreamSynchronize(e->slot[0].stream));
   // chunk so that the ranked lists of a slot stay below ~1 GiB
-  const uint32_t chunk = std::max<uint32_t>(1024u, std::min<uint32_t>(e->chunk_reads, (1u << 30) / (2u * top_k * 12u)));
+  const uint32_t chunk = std::max<uint32_t>(1024u, std::min<uint32_t>(e->chunk_reads ? e->chunk_reads : (1u << 18), (1u << 30) / (2u * top_k * 12u)));
   uint32_t k = 0, short1 = 0, short2 = 0;
+  AheadScans scans(offs1, offs2, n, chunk);
   for (uint32_t r0 = 0; r0 < n; r0 += chunk, ++k) {
     const uint32_t cn = std::min<uint32_t>(chunk, n - r0);
-    const ChunkScan s1 = scan_chunk(offs1, r0, cn), s2 = scan_chunk(offs2, r0, cn);
+    ChunkScan s1, s2;
+    scans.get(k, &s1, &s2);
     if (s1.max_len > MAX_READ_LEN || s2.max_len > MAX_READ_LEN) {
       for (auto& s : e->slot) cudaStreamSynchronize(s.stream);
       return fail(WALT_EINVAL, "read longer than 1024 bases");

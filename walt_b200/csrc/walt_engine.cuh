@@ -74,10 +74,11 @@ struct walt_engine {
   int force_depth = 0;
   int min_blocks = 4;         // resident CTAs per SM the SE kernel is compiled for (register cap)
   uint32_t group_width = 8;   // lanes that own one read (8, 16 or 32)
-  uint32_t chunk_reads = 1u << 18;
+  uint32_t chunk_reads = 0;   // reads per in-flight host chunk; 0 = automatic
   waltb200::BatchSlot slot[waltb200::N_SLOTS];
   cudaStream_t side_stream = nullptr;        // second mate kernel of a paired-end chunk
   cudaEvent_t fork = nullptr, join = nullptr;
+  uint32_t chunk_share = 1;                  // chunk kernels of a host batch that share the SMs (see grid_for)
   int pe_side = 1;                           // 0: both mate kernels on the caller's stream
   uint32_t* d_flags = nullptr;               // [0] non-ACGT flag, [1] work-queue head, [2..3] spare,
                                              // [4..4+N_SLOTS) SE chunk queues, then 2 per slot for PE
