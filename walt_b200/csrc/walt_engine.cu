@@ -284,13 +284,20 @@ struct SeArgs {
 // The groups of a warp take consecutive reads with one queue ticket and walk the read loop
 // together, so the warp stays converged through the common phases (pack, keys, table and entry
 // loads, fold) and only splits where the data makes it (candidate windows, cooperative replays).
+#ifndef WALT_TICKET_ROUNDS
+#define WALT_TICKET_ROUNDS 1
+#endif
+// One queue ticket covers TICKET_ROUNDS rounds of the warp's groups.  Measured on configs[1]: 4 rounds
+// per ticket (a quarter of the same-address atomics) is 3 % SLOWER than 1 (8.94 vs 8.67 ms per 10 M
+// reads): the queue is not a bottleneck and the extra loop state costs registers.
+constexpr uint32_t TICKET_ROUNDS = WALT_TICKET_ROUNDS;
+
 template <uint32_t WD>
-__device__ __forceinline__ uint32_t next_read(uint32_t* queue) {
+__device__ __forceinline__ uint32_t next_ticket(uint32_t* queue) {
   constexpr uint32_t GROUPS = 32u / WD;
   uint32_t r = 0;
-  if ((threadIdx.x & 31u) == 0u) r = atomicAdd(queue, GROUPS);
-  r = __shfl_sync(0xFFFFFFFFu, r, 0);
-  return r + (threadIdx.x & 31u) / WD;
+  if ((threadIdx.x & 31u) == 0u) r = atomicAdd(queue, GROUPS * TICKET_ROUNDS);
+  return __shfl_sync(0xFFFFFFFFu, r, 0);
 }
 
 // Where read r of a launch starts and how long it is.  ASCII: byte offs[r] - seq_base of `seqs`.
@@ -353,9 +360,11 @@ se_map_kernel(const __grid_constant__ SeArgs a) {
   uint32_t cached_len = 0;
   Counters ctr{0u, 0u, 0u};
   bool bad = false;
-  for (;;) {
-    const uint32_t r = next_read<WD>(a.queue);
-    if (r - (threadIdx.x & 31u) / WD >= a.n) break;     // warp-uniform: the ticket is past the batch
+  for (uint32_t round = TICKET_ROUNDS, base = 0;; ++round) {
+    if (round == TICKET_ROUNDS) { base = next_ticket<WD>(a.queue); round = 0; }
+    const uint32_t first = base + round * (32u / WD);
+    if (first >= a.n) break;                            // warp-uniform: past the batch
+    const uint32_t r = first + (threadIdx.x & 31u) / WD;
     if (r < a.n) {
       uint32_t len;
       const char* seq = read_at<PACKED>(a, r, len);
@@ -413,9 +422,11 @@ pe_map_kernel(const __grid_constant__ PeArgs a) {
   uint32_t cached_len = 0;
   Counters ctr{0u, 0u, 0u};
   bool bad = false;
-  for (;;) {
-    const uint32_t r = next_read<WD>(a.queue);
-    if (r - (threadIdx.x & 31u) / WD >= a.n) break;
+  for (uint32_t round = TICKET_ROUNDS, base = 0;; ++round) {
+    if (round == TICKET_ROUNDS) { base = next_ticket<WD>(a.queue); round = 0; }
+    const uint32_t first = base + round * (32u / WD);
+    if (first >= a.n) break;
+    const uint32_t r = first + (threadIdx.x & 31u) / WD;
     if (r < a.n) {
       uint32_t len;
       const char* seq = read_at<PACKED>(a, r, len);
