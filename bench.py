@@ -549,6 +549,24 @@ def run_ours(args):
     def device_step():
         wl.device_step(stream.cuda_stream)
 
+    # ---- device-resident timing (`value`) ----
+    for _ in range(args.warmup):
+        device_step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    w0 = sampler.mark()
+    evs[0].record(stream)
+    for i in range(args.steps):
+        device_step()
+        evs[i + 1].record(stream)
+    barrier()
+    windows = [(w0, sampler.mark())]
+    step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    t_dev = evs[0].elapsed_time(evs[-1]) / 1e3
+    launches_dev = args.steps * wl.launches_per_step()   # kernels of the timed device-resident steps
+
     # ---- side legs on rank 0 (not timed): oracle counters, parity spot check, CPU baseline ----
     cpu_baseline, alg, parity = None, None, None
     if rank == 0 and not args.no_cpu:
@@ -585,23 +603,6 @@ def run_ours(args):
             L = refio.ref_lib()
             for h in hidx.values():
                 L.waltref_index_free(h)
-
-    # ---- device-resident timing (`value`) ----
-    for _ in range(args.warmup):
-        device_step()
-    sampler = ClockSampler(local)
-    sampler.start()
-    barrier()
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    w0 = sampler.mark()
-    evs[0].record(stream)
-    for i in range(args.steps):
-        device_step()
-        evs[i + 1].record(stream)
-    barrier()
-    windows = [(w0, sampler.mark())]
-    step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
-    t_dev = evs[0].elapsed_time(evs[-1]) / 1e3
 
     if args.no_e2e:   # kernel experiments only: not a bench line
         sampler.stop(windows)
@@ -709,7 +710,7 @@ def run_ours(args):
                                "d2h_bytes_per_step": int(wl.out_dt.itemsize * n), "ms_per_step": 1e3 * t_pk / args.steps,
                                "identical_to_e2e_result": same_pk,
                                "input": "2-bit packed reads (walt_pack_reads, packed by the loader outside the timed region)"},
-                "gpu_launches": args.steps * wl.launches_per_step(),
+                "gpu_launches": launches_dev,
                 "roofline": roof, "cpu_baseline": cpu_baseline, "parity_check": parity}
         if world == 1 and not pe and not args.no_cpu and not args.no_cli:
             # files in -> files out through the walt program, next to the reference program (not a timed step)

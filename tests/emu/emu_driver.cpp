@@ -336,6 +336,7 @@ struct PeJob {
   const EmuEngine* e; const char* seqs; const uint64_t* offs; uint32_t lo, hi;
   int ag; uint32_t m, b, top_k; int literal; emu_cand* ranked; uint32_t* n_ranked; uint32_t max_len;
   uint64_t* scratch; HeapEntry* heap; int* bad;
+  int logged; HeapEntry* log; uint32_t* hist;   // two-phase form: LogSink + replay_heap_log
 };
 
 template <uint32_t WD>
@@ -352,8 +353,17 @@ void pe_lane(WarpEmu* w, uint32_t lane, void* arg) {
   for (uint32_t r = j->lo; r < j->hi; ++r) {
     uint32_t len = (uint32_t)(j->offs[r + 1] - j->offs[r]);
     uint32_t hsize = 0;
-    bool ok = map_read_pe(W, ix2, cv, j->e->p3, cfg, j->seqs + j->offs[r], len, j->ag != 0, j->m,
-                          j->top_k, sc, cached, j->heap, hsize, ctr);
+    bool ok;
+    if (j->logged) {
+      uint32_t n_log = 0;
+      ok = map_read_pe_logged(W, ix2, cv, j->e->p3, cfg, j->seqs + j->offs[r], len, j->ag != 0, j->m,
+                              j->top_k, sc, cached, j->log, j->hist, n_log, ctr);
+      W.sync();
+      if (lane == 0) replay_heap_log(j->log, n_log, j->top_k, j->heap, hsize);   // second kernel: one thread per read
+    } else {
+      ok = map_read_pe(W, ix2, cv, j->e->p3, cfg, j->seqs + j->offs[r], len, j->ag != 0, j->m,
+                       j->top_k, sc, cached, j->heap, hsize, ctr);
+    }
     if (lane == 0) {
       if (!ok) *j->bad = 1;
       // drain, paired.cpp:684-692
@@ -420,8 +430,9 @@ int emu_map_se(void* h, const char* seqs, const uint64_t* offs, uint32_t n, int 
 
 int emu_map_pe_mate(void* h, const char* seqs, const uint64_t* offs, uint32_t n, int ag, uint32_t m,
                     uint32_t b, uint32_t top_k, int literal, emu_cand* ranked, uint32_t* n_ranked,
-                    int threads, uint32_t width) {
+                    int threads, uint32_t width, int logged) {
   if (width != 8 && width != 16 && width != 32) return 1;
+  if (logged && m > LOG_MAX_MM) return 1;
   EmuEngine* e = (EmuEngine*)h;
   uint32_t max_len = 1;
   for (uint32_t r = 0; r < n; ++r) max_len = std::max<uint32_t>(max_len, (uint32_t)(offs[r + 1] - offs[r]));
@@ -429,9 +440,11 @@ int emu_map_pe_mate(void* h, const char* seqs, const uint64_t* offs, uint32_t n,
   std::atomic<int> bad{0};
   int div = run_parallel<PeJob>(n, threads, width, [&](WarpEmu* w, uint32_t lo, uint32_t hi) {
     std::vector<uint64_t> scratch(scratch_words((max_len + 31) / 32) + 8);
-    std::vector<HeapEntry> heap(top_k + 1);
+    std::vector<HeapEntry> heap(top_k + 1), log(pe_log_slots(top_k, m) + 1);
+    std::vector<uint32_t> hist(m + 2);
     int b_ = 0;
-    PeJob j{e, seqs, offs, lo, hi, ag, m, b, top_k, literal, ranked, n_ranked, max_len, scratch.data(), heap.data(), &b_};
+    PeJob j{e, seqs, offs, lo, hi, ag, m, b, top_k, literal, ranked, n_ranked, max_len, scratch.data(), heap.data(), &b_,
+            logged, log.data(), hist.data()};
     w->run(width == 8 ? pe_lane<8> : width == 16 ? pe_lane<16> : pe_lane<32>, &j);
     if (b_) bad = 1;
   });

@@ -102,8 +102,9 @@ def test_se_edge_emu(depth, width):
     e.close()
 
 
+@pytest.mark.parametrize("logged", [False, True], ids=["heap-in-kernel", "logged+replay"])
 @pytest.mark.parametrize("width", [32, 8])
-def test_pe_emu_matches_reference(engine, width):
+def test_pe_emu_matches_reference(engine, width, logged):
     hdr, _ = goldenio.genome()
     z = goldenio.load("pe.npz")
     L = refio.oracle_lib()
@@ -114,7 +115,7 @@ def test_pe_emu_matches_reference(engine, width):
         got = {}
         for mate, ag in ((1, False), (2, True)):
             buf, offs = refio.pack_reads(z[f"m{mate}"])
-            rc, ranked, sizes = engine.map_pe_mate(buf, offs, refio.CAND_DT, ag, m=m, top_k=k, width=width)
+            rc, ranked, sizes = engine.map_pe_mate(buf, offs, refio.CAND_DT, ag, m=m, top_k=k, width=width, logged=logged)
             assert rc == 0
             assert np.array_equal(sizes, z[f"sizes{mate}_m{m}_k{k}"])
             want = z[f"ranked{mate}_m{m}_k{k}"]

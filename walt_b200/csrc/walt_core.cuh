@@ -674,6 +674,83 @@ struct HeapSink {
   }
 };
 
+// PE, two-phase form.  Heap maintenance is serial per read (one lane works, the rest of the warp
+// idles) and on repeat-heavy input it was ~40 % of all issued instructions at ~1.2 active threads.
+// The mapping kernel therefore only LOGS the candidates that change the heap, in order, and a
+// second kernel replays every read's log through the libstdc++ heap with one THREAD per read.
+// What the mapping pass needs from the heap -- is it full, what is its worst mismatch count
+// (paired.hpp:60-67 for the push rule, paired.cpp:127-137 for the shift exits) -- depends only on
+// the multiset of kept mismatch counts, which evolves without the heap's shape: while not full
+// every candidate is kept; once full a candidate with mm < max(kept) replaces one entry with
+// mm == max(kept).  `hist` (max_mm + 1 counters in memory owned by the group) is that multiset,
+// so the log holds exactly the pushes that std::priority_queue would have executed.
+constexpr uint32_t LOG_MAX_MM = 15;    // the logged form needs (max_mm + 1) * top_k log slots per read
+WALT_HD uint32_t pe_log_slots(uint32_t top_k, uint32_t max_mm) { return top_k * (max_mm + 1u); }
+
+template <class W>
+struct LogSink {
+  HeapEntry* log;      // this read's event list (global memory), pe_log_slots entries
+  uint32_t* hist;      // kept entries per mismatch count, [0, max_mm]; lane 0 writes, all read
+  uint32_t n_log;      // group-uniform
+  uint32_t size;       // group-uniform, exact
+  uint32_t cap;
+  uint32_t top_mm;     // group-uniform, exact: the heap's heap[0].mm (valid if size > 0)
+  uint32_t max_mm;
+  WALT_HD void reset(W& w) {
+    for (uint32_t i = w.lane(); i <= max_mm; i += W::WIDTH) hist[i] = 0u;
+    n_log = 0u; size = 0u; top_mm = 0u;
+    w.sync();
+  }
+  WALT_HD bool stop_before_shift(uint32_t seed_i) const {  // paired.cpp:127-137
+    bool full = size > 0u && size >= cap;
+    return full && ((top_mm == 0u && seed_i >= 1u) || (top_mm == 1u && seed_i >= 2u));
+  }
+  WALT_HD bool may_take(uint32_t mm) const { return mm <= max_mm && (size < cap || mm < top_mm); }
+  // one candidate that passed may_take against the CURRENT state; arguments are group-uniform
+  WALT_HD void take_one(W& w, uint32_t g, uint32_t mm, uint32_t strand) {
+    if (size < cap) {
+      if (w.lane() == 0u) hist[mm]++;
+      top_mm = (size == 0u || mm > top_mm) ? mm : top_mm;
+      ++size;
+    } else {
+      if (w.lane() == 0u) { hist[top_mm]--; hist[mm]++; }
+      w.sync();
+      uint32_t t = top_mm;
+      while (t > 0u && hist[t] == 0u) --t;   // mm < top_mm went in, so some counter at or below is set
+      top_mm = t;
+      w.sync();                              // the next event's writer must not run ahead of these reads
+    }
+    if (w.lane() == 0u) {
+      HeapEntry v; v.pos = g; v.mm_strand = mm | (strand == '-' ? 0x10000u : 0u);
+      log[n_log] = v;
+    }
+    ++n_log;
+  }
+  WALT_HD void consume(W& w, bool valid, uint32_t mm, uint32_t g, uint32_t strand) {
+    uint32_t take = w.ballot(valid && may_take(mm));   // a superset: the state only gets stricter
+    while (take) {
+      int src = ffs32(take) - 1;
+      take &= take - 1u;
+      const uint32_t cg = w.shfl(g, src);
+      const uint32_t cm = w.shfl(mm, src);
+      if (may_take(cm)) take_one(w, cg, cm, strand);
+    }
+  }
+  WALT_HD void push_list(W& w, const LaneCand* c, uint32_t n, uint32_t strand) {
+    for (uint32_t k = 0; k < n; ++k) {
+      const LaneCand v = c[k];
+      if (may_take(v.mm)) take_one(w, v.g, v.mm, strand);
+    }
+  }
+};
+
+// Second phase: one read's log through TopCandidates (paired.hpp:51-74).  Every logged event is a
+// push the reference executes; heap_push_bounded re-derives the same decision.
+WALT_HD void replay_heap_log(const HeapEntry* log, uint32_t n_log, uint32_t cap, HeapEntry* heap, uint32_t& size) {
+  size = 0u;
+  for (uint32_t i = 0; i < n_log; ++i) heap_push_bounded(heap, size, cap, log[i]);
+}
+
 // ------------------------------------------------------------------------------------------
 // one seed lookup: table -> region -> candidates, fed to the sink in reference order
 // ------------------------------------------------------------------------------------------
@@ -1073,22 +1150,19 @@ WALT_HD bool map_read_se(W& w, const SubIndexView* ix2, const ChromView& cv, con
   return true;
 }
 
-// PairEndMapping for both strand passes of one mate (paired.cpp:650-671); the heap persists
-// across the two passes.  On return heap[0..size) is the libstdc++ heap array.
-template <class W, bool PACKED = false>
-WALT_HD bool map_read_pe(W& w, const SubIndexView* ix2, const ChromView& cv, const Pow3& p3,
-                         const MapConfig& cfg, const char* seq, uint32_t read_len, bool ag,
-                         uint32_t max_mismatches, uint32_t top_k, ReadScratch& sc,
-                         uint32_t& cached_len, HeapEntry* heap, uint32_t& heap_size, Counters& ctr) {
+// PairEndMapping for both strand passes of one mate (paired.cpp:650-671) into `sink` (reset by the
+// caller; its state persists across the two passes).
+template <class W, bool PACKED, class SinkT>
+WALT_HD bool map_read_pe_into(W& w, const SubIndexView* ix2, const ChromView& cv, const Pow3& p3,
+                              const MapConfig& cfg, const char* seq, uint32_t read_len, bool ag,
+                              uint32_t max_mismatches, ReadScratch& sc, uint32_t& cached_len, SinkT& sink,
+                              Counters& ctr) {
   static_assert(W::WIDTH >= LOOKUP_LANES, "a group needs one lane per lookup");
-  HeapSink<W> sink;
-  sink.heap = heap; sink.size = 0u; sink.cap = top_k; sink.top_mm = 0u; sink.max_mm = max_mismatches;
-  heap_size = 0u;
   if (read_len < MIN_READ_LEN) return true;
   if (!load_read<W, PACKED>(w, seq, read_len, ag, sc)) return false;
   if (cached_len != read_len) { build_masks(w, read_len, sc); cached_len = read_len; }
-  // lookup lanes leave their candidates (index order) in the group's scratch; lane 0 pushes
-  // them in reference order
+  // lookup lanes leave their candidates (index order) in the group's scratch; they reach the
+  // sink in reference order
   const uint32_t lane = w.lane();
   bool coop = false;
   uint32_t n_mine = 0u;
@@ -1124,9 +1198,37 @@ WALT_HD bool map_read_pe(W& w, const SubIndexView* ix2, const ChromView& cv, con
       sink.push_list(w, sc.C + j * LANE_RUN_CAP, nj, strand);
     }
   }
-  heap_size = sink.size;
   w.sync();
   return true;
+}
+
+// ... with the heap maintained in place by lane 0.  On return heap[0..size) is the libstdc++ heap array.
+template <class W, bool PACKED = false>
+WALT_HD bool map_read_pe(W& w, const SubIndexView* ix2, const ChromView& cv, const Pow3& p3,
+                         const MapConfig& cfg, const char* seq, uint32_t read_len, bool ag,
+                         uint32_t max_mismatches, uint32_t top_k, ReadScratch& sc,
+                         uint32_t& cached_len, HeapEntry* heap, uint32_t& heap_size, Counters& ctr) {
+  HeapSink<W> sink;
+  sink.heap = heap; sink.size = 0u; sink.cap = top_k; sink.top_mm = 0u; sink.max_mm = max_mismatches;
+  heap_size = 0u;
+  const bool ok = map_read_pe_into<W, PACKED>(w, ix2, cv, p3, cfg, seq, read_len, ag, max_mismatches, sc, cached_len, sink, ctr);
+  heap_size = sink.size;
+  return ok;
+}
+
+// ... logging the heap-changing candidates for replay_heap_log (max_mismatches <= LOG_MAX_MM; `log`
+// holds pe_log_slots(top_k, max_mismatches) entries, `hist` max_mismatches + 1 counters).
+template <class W, bool PACKED = false>
+WALT_HD bool map_read_pe_logged(W& w, const SubIndexView* ix2, const ChromView& cv, const Pow3& p3,
+                                const MapConfig& cfg, const char* seq, uint32_t read_len, bool ag,
+                                uint32_t max_mismatches, uint32_t top_k, ReadScratch& sc,
+                                uint32_t& cached_len, HeapEntry* log, uint32_t* hist, uint32_t& n_log, Counters& ctr) {
+  LogSink<W> sink;
+  sink.log = log; sink.hist = hist; sink.cap = top_k; sink.max_mm = max_mismatches;
+  sink.reset(w);
+  const bool ok = map_read_pe_into<W, PACKED>(w, ix2, cv, p3, cfg, seq, read_len, ag, max_mismatches, sc, cached_len, sink, ctr);
+  n_log = sink.n_log;
+  return ok;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -400,12 +400,94 @@ struct PeArgs {
   uint32_t top_k;
   walt_cand* ranked;      // n * top_k, worst first
   uint32_t* n_ranked;
+  HeapEntry* log;         // two-phase form: log_slots heap-changing candidates per read, in order
+  uint32_t* n_log;
+  uint32_t log_slots;
+  uint32_t zero_fill;     // the ranked lists travel to the host: define (zero) their unused slots
   uint32_t* flags;
   uint32_t* queue;
   unsigned long long* counters;
 };
 
-// PairEndMapping (paired.cpp:106-201) for one mate batch + the heap drain (paired.cpp:684-692)
+// Two-phase form, first phase: PairEndMapping (paired.cpp:106-201) for one mate batch with the
+// heap-changing candidates logged (LogSink, walt_core.cuh); pe_heap_kernel finishes the job.
+template <uint32_t WD, bool PACKED>
+__global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS_PER_SM)
+pe_log_kernel(const __grid_constant__ PeArgs a) {
+  extern __shared__ uint64_t smem[];
+  __shared__ BlockTally tally;
+  tally_init(tally);
+  HwGroup<WD> w;
+  const uint32_t lane = w.lane();
+  const uint32_t group_in_block = threadIdx.x / WD;
+  const uint32_t per_group = scratch_words(a.nw_max) + (LOG_MAX_MM + 2u) / 2u;   // + the mismatch histogram
+  uint64_t* mine = smem + (size_t)group_in_block * per_group;
+  ReadScratch sc = carve_scratch(mine, a.nw_max);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(mine + scratch_words(a.nw_max));
+  uint32_t cached_len = 0;
+  Counters ctr{0u, 0u, 0u};
+  bool bad = false;
+  for (uint32_t round = TICKET_ROUNDS, base = 0;; ++round) {
+    if (round == TICKET_ROUNDS) { base = next_ticket<WD>(a.queue); round = 0; }
+    const uint32_t first = base + round * (32u / WD);
+    if (first >= a.n) break;
+    const uint32_t r = first + (threadIdx.x & 31u) / WD;
+    if (r < a.n) {
+      uint32_t len;
+      const char* seq = read_at<PACKED>(a, r, len);
+      uint32_t n_log = 0;
+      bool ok = map_read_pe_logged<HwGroup<WD>, PACKED>(w, a.ix, a.cv, a.p3, a.cfg, seq, len, a.ag != 0u,
+                            a.max_mismatches, a.top_k, sc, cached_len, a.log + (size_t)r * a.log_slots, hist, n_log, ctr);
+      bad |= !ok;
+      if (lane == 0) a.n_log[r] = n_log;
+    }
+    __syncwarp();
+  }
+  flush_counters(w, ctr, bad, tally, a.flags, a.counters);
+}
+
+// Second phase: one THREAD per read replays its log through TopCandidates' heap (paired.hpp:51-74,
+// libstdc++ mechanics) and drains it (paired.cpp:684-692).  Thread t < n serves mate 1's read t,
+// thread n + t mate 2's.  LOCAL_CAP > 0: the heap is a local array (top_k <= LOCAL_CAP), else it
+// lives in `heaps` (top_k entries per thread).
+struct HeapArgs {
+  const HeapEntry* log[2];
+  const uint32_t* n_log[2];
+  walt_cand* ranked[2];
+  uint32_t* n_ranked[2];
+  HeapEntry* heaps;
+  uint32_t n, top_k, log_slots;
+  uint32_t zero_fill;     // see PeArgs
+};
+
+template <uint32_t LOCAL_CAP>
+__global__ void __launch_bounds__(128)
+pe_heap_kernel(const __grid_constant__ HeapArgs a) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2u * a.n) return;
+  const uint32_t mate = t >= a.n ? 1u : 0u, r = t - mate * a.n;
+  HeapEntry local[LOCAL_CAP ? LOCAL_CAP : 1u];
+  HeapEntry* heap = LOCAL_CAP ? local : a.heaps + (size_t)t * a.top_k;
+  uint32_t size = 0;
+  replay_heap_log(a.log[mate] + (size_t)r * a.log_slots, a.n_log[mate][r], a.top_k, heap, size);
+  walt_cand* dst = a.ranked[mate] + (size_t)r * a.top_k;
+  uint32_t c = 0;
+  while (size) {
+    const HeapEntry e = heap_pop(heap, size);
+    walt_cand o;
+    o.genome_pos = e.pos; o.mismatch = he_mm(e); o.strand = (e.mm_strand & 0x10000u) ? '-' : '+';
+    o.pad[0] = o.pad[1] = o.pad[2] = 0;
+    dst[c++] = o;
+  }
+  a.n_ranked[mate][r] = c;
+  if (a.zero_fill) {   // whole-array compares and copies on the host side are deterministic
+    uint32_t* z = reinterpret_cast<uint32_t*>(dst + c);
+    for (uint32_t i = 0; i < (a.top_k - c) * 3u; ++i) z[i] = 0u;
+  }
+}
+
+// Single-kernel form (max_mismatches > LOG_MAX_MM, or WALT_PE_LOGGED=0): PairEndMapping
+// (paired.cpp:106-201) for one mate batch + the heap drain (paired.cpp:684-692), heap kept by lane 0
 template <uint32_t WD, bool PACKED>
 __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS_PER_SM)
 pe_map_kernel(const __grid_constant__ PeArgs a) {
@@ -447,7 +529,7 @@ pe_map_kernel(const __grid_constant__ PeArgs a) {
         a.n_ranked[r] = c;
       }
       w.sync();
-      {  // unused slots are defined (zero) so whole-array compares and copies are deterministic
+      if (a.zero_fill) {  // unused slots are defined (zero) so whole-array compares and copies are deterministic
         const uint32_t used = w.shfl(hsize, 0);
         uint32_t* z = reinterpret_cast<uint32_t*>(a.ranked + (size_t)r * a.top_k + used);
         for (uint32_t i = lane; i < (a.top_k - used) * 3u; i += WD) z[i] = 0u;
@@ -518,6 +600,10 @@ __global__ void pair_kernel(const __grid_constant__ PairArgs a) {
 static size_t se_smem_bytes(uint32_t nw_max, uint32_t wd) { return (size_t)(BLOCK_THREADS / wd) * scratch_words(nw_max) * 8u; }
 static size_t pe_smem_bytes(uint32_t nw_max, uint32_t top_k, uint32_t wd) {
   return (size_t)(BLOCK_THREADS / wd) * (scratch_words(nw_max) + top_k + 1u) * 8u;
+}
+
+static size_t pe_log_smem_bytes(uint32_t nw_max, uint32_t wd) {
+  return (size_t)(BLOCK_THREADS / wd) * (scratch_words(nw_max) + (LOG_MAX_MM + 2u) / 2u) * 8u;
 }
 
 template <class K>
@@ -591,12 +677,36 @@ static int launch_se(walt_engine* e, const ReadSrc& src, uint32_t n, int ag, uin
   return WALT_OK;
 }
 
+// first phase of the two-phase form for one mate
+static int launch_pe_log(walt_engine* e, const ReadSrc& src, uint32_t n, int ag, uint32_t m, uint32_t b, uint32_t top_k,
+                         HeapEntry* d_log, uint32_t* d_nlog, uint32_t* d_queue, cudaStream_t st) {
+  // (zero_fill belongs to the second phase here)
+  if (src.max_len > MAX_READ_LEN) return fail(WALT_EINVAL, "read longer than 1024 bases");
+  PeArgs a;
+  fill_common(e, a, src, n, ag, m, b, d_queue);
+  a.top_k = top_k; a.ranked = nullptr; a.n_ranked = nullptr;
+  a.log = d_log; a.n_log = d_nlog; a.log_slots = pe_log_slots(top_k, m); a.zero_fill = 0u;
+  const uint32_t wd = e->group_width;
+  const size_t smem = pe_log_smem_bytes(a.nw_max, wd);
+  uint32_t grid = 0;
+  auto kernel = src.packed ? (wd == 8u ? pe_log_kernel<8, true> : wd == 16u ? pe_log_kernel<16, true> : pe_log_kernel<32, true>)
+                           : (wd == 8u ? pe_log_kernel<8, false> : wd == 16u ? pe_log_kernel<16, false> : pe_log_kernel<32, false>);
+  int rc = grid_for(e, kernel, smem, n, wd, &grid);
+  if (rc) return rc;
+  WALT_CUDA_TRY(cudaMemsetAsync(d_queue, 0, 4, st));
+  kernel<<<grid, BLOCK_THREADS, smem, st>>>(a);
+  WALT_CUDA_TRY(cudaGetLastError());
+  e->stats.n_kernel_launches++;
+  return WALT_OK;
+}
+
 static int launch_pe_mate(walt_engine* e, const ReadSrc& src, uint32_t n, int ag, uint32_t m, uint32_t b, uint32_t top_k,
-                          walt_cand* d_ranked, uint32_t* d_nranked, uint32_t* d_queue, cudaStream_t st) {
+                          walt_cand* d_ranked, uint32_t* d_nranked, uint32_t* d_queue, cudaStream_t st, bool zero_fill) {
   if (src.max_len > MAX_READ_LEN) return fail(WALT_EINVAL, "read longer than 1024 bases");
   PeArgs a;
   fill_common(e, a, src, n, ag, m, b, d_queue);
   a.top_k = top_k; a.ranked = d_ranked; a.n_ranked = d_nranked;
+  a.log = nullptr; a.n_log = nullptr; a.log_slots = 0; a.zero_fill = zero_fill ? 1u : 0u;
   const uint32_t wd = e->group_width;
   const size_t smem = pe_smem_bytes(a.nw_max, top_k, wd);
   uint32_t grid = 0;
@@ -702,6 +812,7 @@ int walt_engine_create(walt_engine** out, int device) {
   // undocumented tuning knobs for experiments (defaults are what bench.py measures)
   if (const char* v = getenv("WALT_MIN_BLOCKS")) e->min_blocks = atoi(v);
   if (const char* v = getenv("WALT_PE_SIDE")) e->pe_side = atoi(v);
+  if (const char* v = getenv("WALT_PE_LOGGED")) e->pe_logged = atoi(v);
   if (const char* v = getenv("WALT_CHUNK_SHARE")) e->chunk_share = (uint32_t)std::max(1, atoi(v));
   if (const char* v = getenv("WALT_L2_FETCH")) WALT_CUDA_TRY(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(v)));
   uint32_t p = 1;
@@ -1131,22 +1242,46 @@ int walt_engine_map_se_packed(walt_engine* e, const uint8_t* packed, const uint6
 
 // ---- paired end ---------------------------------------------------------------------------
 // device layout of one chunk's paired-end scratch inside a slot's d_pe allocation
+constexpr uint32_t HEAP_LOCAL_CAP = 64;   // top_k up to this: pe_heap_kernel keeps its heap in local memory
+
+static bool pe_two_phase(const walt_engine* e, uint32_t m) { return e->pe_logged && m <= LOG_MAX_MM; }
+
 struct PeScratch {
   walt_pair* pairs; walt_pe_result* compact; walt_cand* r1; walt_cand* r2; uint32_t* n1; uint32_t* n2;
+  // two-phase form: per-mate logs and their lengths, heaps for top_k > HEAP_LOCAL_CAP
+  HeapEntry* log1; HeapEntry* log2; uint32_t* nlog1; uint32_t* nlog2; HeapEntry* heaps;
 };
-static size_t pe_scratch_bytes(uint32_t cn, uint32_t top_k) {
-  return (size_t)cn * sizeof(walt_pe_result) + (size_t)cn * sizeof(walt_pair) + 2u * (size_t)cn * top_k * sizeof(walt_cand) +
-         2u * (size_t)cn * 4u + 256u;
+// bytes of scratch one pair needs (sizes the chunks)
+static size_t pe_pair_bytes(uint32_t top_k, uint32_t m, bool two_phase) {
+  size_t b = sizeof(walt_pe_result) + sizeof(walt_pair) + 2u * (size_t)top_k * sizeof(walt_cand) + 2u * 4u;
+  if (two_phase) {
+    b += 2u * (size_t)pe_log_slots(top_k, m) * sizeof(HeapEntry) + 2u * 4u;
+    if (top_k > HEAP_LOCAL_CAP) b += 2u * (size_t)top_k * sizeof(HeapEntry);
+  }
+  return b;
 }
-static PeScratch carve_pe(void* base, uint32_t cn, uint32_t top_k) {
+static size_t pe_scratch_bytes(uint32_t cn, uint32_t top_k, uint32_t m, bool two_phase) {
+  return (size_t)cn * pe_pair_bytes(top_k, m, two_phase) + 512u;
+}
+static PeScratch carve_pe(void* base, uint32_t cn, uint32_t top_k, uint32_t m, bool two_phase) {
   PeScratch p;
   char* c = (char*)base;
-  p.compact = (walt_pe_result*)c; c += (((size_t)cn * sizeof(walt_pe_result)) + 15u) & ~(size_t)15u;
-  p.pairs = (walt_pair*)c;        c += (size_t)cn * sizeof(walt_pair);
-  p.r1 = (walt_cand*)c;           c += (size_t)cn * top_k * sizeof(walt_cand);
-  p.r2 = (walt_cand*)c;           c += (size_t)cn * top_k * sizeof(walt_cand);
-  p.n1 = (uint32_t*)c;            c += (size_t)cn * 4u;
-  p.n2 = (uint32_t*)c;
+  auto take = [&](size_t bytes) { char* at = c; c += (bytes + 15u) & ~(size_t)15u; return at; };
+  p.compact = (walt_pe_result*)take((size_t)cn * sizeof(walt_pe_result));
+  p.pairs = (walt_pair*)take((size_t)cn * sizeof(walt_pair));
+  p.r1 = (walt_cand*)take((size_t)cn * top_k * sizeof(walt_cand));
+  p.r2 = (walt_cand*)take((size_t)cn * top_k * sizeof(walt_cand));
+  p.n1 = (uint32_t*)take((size_t)cn * 4u);
+  p.n2 = (uint32_t*)take((size_t)cn * 4u);
+  p.log1 = p.log2 = p.heaps = nullptr; p.nlog1 = p.nlog2 = nullptr;
+  if (two_phase) {
+    const size_t slots = pe_log_slots(top_k, m);
+    p.log1 = (HeapEntry*)take((size_t)cn * slots * sizeof(HeapEntry));
+    p.log2 = (HeapEntry*)take((size_t)cn * slots * sizeof(HeapEntry));
+    p.nlog1 = (uint32_t*)take((size_t)cn * 4u);
+    p.nlog2 = (uint32_t*)take((size_t)cn * 4u);
+    if (top_k > HEAP_LOCAL_CAP) p.heaps = (HeapEntry*)take(2u * (size_t)cn * top_k * sizeof(HeapEntry));
+  }
   return p;
 }
 
@@ -1163,11 +1298,29 @@ static int launch_pe_chunk(walt_engine* e, const ReadSrc& m1, const ReadSrc& m2,
     WALT_CUDA_TRY(cudaEventRecord(e->fork, st));
     WALT_CUDA_TRY(cudaStreamWaitEvent(st2, e->fork, 0));
   }
-  if ((rc = launch_pe_mate(e, m1, cn, 0, m, b, top_k, ps.r1, ps.n1, q, st))) return rc;
-  if ((rc = launch_pe_mate(e, m2, cn, 1, m, b, top_k, ps.r2, ps.n2, q + 1, st2))) return rc;
+  const bool two_phase = ps.log1 != nullptr;
+  if (two_phase) {
+    if ((rc = launch_pe_log(e, m1, cn, 0, m, b, top_k, ps.log1, ps.nlog1, q, st))) return rc;
+    if ((rc = launch_pe_log(e, m2, cn, 1, m, b, top_k, ps.log2, ps.nlog2, q + 1, st2))) return rc;
+  } else {
+    if ((rc = launch_pe_mate(e, m1, cn, 0, m, b, top_k, ps.r1, ps.n1, q, st, want_pairs))) return rc;
+    if ((rc = launch_pe_mate(e, m2, cn, 1, m, b, top_k, ps.r2, ps.n2, q + 1, st2, want_pairs))) return rc;
+  }
   if (e->pe_side) {
     WALT_CUDA_TRY(cudaEventRecord(e->join, st2));
     WALT_CUDA_TRY(cudaStreamWaitEvent(st, e->join, 0));
+  }
+  if (two_phase) {
+    HeapArgs h;
+    h.log[0] = ps.log1; h.log[1] = ps.log2; h.n_log[0] = ps.nlog1; h.n_log[1] = ps.nlog2;
+    h.ranked[0] = ps.r1; h.ranked[1] = ps.r2; h.n_ranked[0] = ps.n1; h.n_ranked[1] = ps.n2;
+    h.heaps = ps.heaps; h.n = cn; h.top_k = top_k; h.log_slots = pe_log_slots(top_k, m);
+    h.zero_fill = want_pairs ? 1u : 0u;   // only walt_engine_map_pe hands the lists themselves to the host
+    const uint32_t blocks = (2u * cn + 127u) / 128u;
+    if (top_k <= HEAP_LOCAL_CAP) pe_heap_kernel<HEAP_LOCAL_CAP><<<blocks, 128, 0, st>>>(h);
+    else pe_heap_kernel<0><<<blocks, 128, 0, st>>>(h);
+    WALT_CUDA_TRY(cudaGetLastError());
+    e->stats.n_kernel_launches++;
   }
   const uint64_t* d_offs1 = m1.d_offs; const uint64_t* d_offs2 = m2.d_offs;
   const uint32_t ulen1 = m1.uniform_len, ulen2 = m2.uniform_len;
@@ -1194,8 +1347,11 @@ static int map_pe_host(walt_engine* e, const char* seqs1, const uint64_t* offs1,
   e->stats = walt_stats{};
   WALT_CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, 3 * 8, e->slot[0].stream));
   WALT_CUDA_TRY(cudaStreamSynchronize(e->slot[0].stream));
-  // chunk so that the ranked lists of a slot stay below ~1 GiB
-  const uint32_t chunk = std::max<uint32_t>(1024u, std::min<uint32_t>(e->chunk_reads ? e->chunk_reads : (1u << 18), (1u << 30) / (2u * top_k * 12u)));
+  // chunk so that a slot's scratch (ranked lists, and the candidate logs of the two-phase form)
+  // stays below ~1.5 GiB
+  const bool two_phase = pe_two_phase(e, m);
+  const uint32_t chunk = std::max<uint32_t>(1024u, (uint32_t)std::min<uint64_t>(e->chunk_reads ? e->chunk_reads : (1u << 18),
+                                                                                (3ull << 29) / pe_pair_bytes(top_k, m, two_phase)));
   uint32_t k = 0, short1 = 0, short2 = 0;
   AheadScans scans(offs1, offs2, n, chunk);
   for (uint32_t r0 = 0; r0 < n; r0 += chunk, ++k) {
@@ -1214,8 +1370,8 @@ static int map_pe_host(walt_engine* e, const char* seqs1, const uint64_t* offs1,
     chunk_bytes(offs2, r0, cn, packed, &sb2, &se2);
     if ((rc = reserve(&s.d_seqs, &s.seqs_cap, (size_t)(se1 - sb1) + 16u))) return rc;
     if ((rc = reserve(&s.d_seqs2, &s.seqs2_cap, (size_t)(se2 - sb2) + 16u))) return rc;
-    if ((rc = reserve_bytes(&s.d_pe, &s.pe_cap, pe_scratch_bytes(cn, top_k)))) return rc;
-    const PeScratch ps = carve_pe(s.d_pe, cn, top_k);
+    if ((rc = reserve_bytes(&s.d_pe, &s.pe_cap, pe_scratch_bytes(cn, top_k, m, two_phase)))) return rc;
+    const PeScratch ps = carve_pe(s.d_pe, cn, top_k, m, two_phase);
     if (se1 > sb1) WALT_CUDA_TRY(cudaMemcpyAsync(s.d_seqs, seqs1 + sb1, se1 - sb1, cudaMemcpyHostToDevice, s.stream));
     if (se2 > sb2) WALT_CUDA_TRY(cudaMemcpyAsync(s.d_seqs2, seqs2 + sb2, se2 - sb2, cudaMemcpyHostToDevice, s.stream));
     if (!s1.uniform_len) {
@@ -1324,11 +1480,19 @@ int walt_engine_map_pe_device(walt_engine* e, const void* d_seqs1, const void* d
   size_t free_b = 0, total_b = 0;
   WALT_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
   const uint64_t budget = std::max<uint64_t>(s.pe_cap, std::min<uint64_t>(8ull << 30, std::max<uint64_t>(1ull << 30, free_b / 4)));
-  const uint32_t chunk = std::max<uint32_t>(1024u, (uint32_t)std::min<uint64_t>(n, budget / (2ull * top_k * 12ull + 128ull)));
-  if ((rc = reserve_bytes(&s.d_pe, &s.pe_cap, pe_scratch_bytes(chunk, top_k)))) return rc;
+  const bool two_phase = pe_two_phase(e, max_mismatches);
+  uint32_t chunk = std::max<uint32_t>(1024u, (uint32_t)std::min<uint64_t>(n, budget / pe_pair_bytes(top_k, max_mismatches, two_phase)));
+  if (n > chunk) {   // equal chunks: no short last launch
+    const uint32_t k = (n + chunk - 1u) / chunk;
+    chunk = (n + k - 1u) / k;
+  }
+  if (getenv("WALT_DEBUG"))
+    fprintf(stderr, "[walt debug] map_pe_device: free %.2f GB, budget %.2f GB, chunk %u pairs, two_phase %d\n", free_b / 1e9,
+            budget / 1e9, chunk, (int)two_phase);
+  if ((rc = reserve_bytes(&s.d_pe, &s.pe_cap, pe_scratch_bytes(chunk, top_k, max_mismatches, two_phase)))) return rc;
   for (uint32_t r0 = 0; r0 < n; r0 += chunk) {
     const uint32_t cn = std::min<uint32_t>(chunk, n - r0);
-    const PeScratch ps = carve_pe(s.d_pe, cn, top_k);
+    const PeScratch ps = carve_pe(s.d_pe, cn, top_k, max_mismatches, two_phase);
     // absolute offsets: read r of the chunk is global read r0 + r, addressed from the buffer start
     const ReadSrc m1{s1, o1 + r0, 0, 0, r0, max_read_len, false}, m2{s2, o2 + r0, 0, 0, r0, max_read_len, false};
     if ((rc = launch_pe_chunk(e, m1, m2, cn, max_mismatches, b, top_k, frag_range, pbat, ps, false,

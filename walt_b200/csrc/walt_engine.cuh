@@ -79,6 +79,7 @@ struct walt_engine {
   cudaStream_t side_stream = nullptr;        // second mate kernel of a paired-end chunk
   cudaEvent_t fork = nullptr, join = nullptr;
   uint32_t chunk_share = 1;                  // chunk kernels of a host batch that share the SMs (see grid_for)
+  int pe_logged = 1;                         // 1: two-phase paired-end (candidate log + per-thread heap replay)
   int pe_side = 1;                           // 0: both mate kernels on the caller's stream
   uint32_t* d_flags = nullptr;               // [0] non-ACGT flag, [1] work-queue head, [2..3] spare,
                                              // [4..4+N_SLOTS) SE chunk queues, then 2 per slot for PE
