@@ -949,7 +949,10 @@ WALT_HD void seed_lookup(W& w, const SubIndexView& ix, const ChromView& cv, cons
   // chain of dependent gathers -- entry, then genome window -- so every lane keeps SLOTS_AHEAD
   // of them in flight: the entries of a block are loaded together and their windows prefetched
   // before the first is compared.  Candidates reach the sink in slot order, WD at a time.
-  constexpr uint32_t SLOTS_AHEAD = 4;
+#ifndef WALT_SLOTS_AHEAD
+#define WALT_SLOTS_AHEAD 4
+#endif
+  constexpr uint32_t SLOTS_AHEAD = WALT_SLOTS_AHEAD;
   for (uint32_t base = first; base < last_excl; base += WD * SLOTS_AHEAD) {
     uint32_t e[SLOTS_AHEAD];
     WALT_UNROLL
@@ -1246,6 +1249,11 @@ WALT_HD void forward_position(const uint32_t* __restrict__ starts, uint32_t pos,
 
 struct PairResult { uint32_t best_times; int32_t best_i, best_j; int32_t frag; };
 
+// The chromosome and forward start of every mate-2 candidate are pure functions of the candidate;
+// the reference recomputes them inside the O(k^2) loop (paired.cpp:486-499), here they are
+// computed once per candidate when the list is short enough for a local array (top_k <= 64).
+constexpr uint32_t PAIR_PRECOMPUTE = 64;
+
 template <class GetCand>
 WALT_HD PairResult pair_candidates(const ChromView& cv, GetCand get1, uint32_t n1, uint32_t len1,
                                    GetCand get2, uint32_t n2, uint32_t len2,
@@ -1253,6 +1261,17 @@ WALT_HD PairResult pair_candidates(const ChromView& cv, GetCand get1, uint32_t n
   PairResult r; r.best_times = 0u; r.best_i = -1; r.best_j = -1; r.frag = 0;
   uint32_t min_mm = max_mismatches;
   uint64_t best_pos = 0;
+  uint32_t chr2[PAIR_PRECOMPUTE], start2[PAIR_PRECOMPUTE];
+  const bool pre = n2 <= PAIR_PRECOMPUTE && n1 > 1u;
+  if (pre) {
+    for (uint32_t j = 0; j < n2; ++j) {
+      const RankedCand bb = get2(j);
+      uint32_t s2, e2;
+      chr2[j] = chrom_of(cv.starts, cv.n_chr, bb.pos);
+      forward_position(cv.starts, bb.pos, bb.strand, chr2[j], len2, s2, e2);
+      start2[j] = s2;
+    }
+  }
   for (int32_t i = (int32_t)n1 - 1; i >= 0; --i) {
     const RankedCand a = get1((uint32_t)i);
     const uint32_t c1 = chrom_of(cv.starts, cv.n_chr, a.pos);
@@ -1263,10 +1282,11 @@ WALT_HD PairResult pair_candidates(const ChromView& cv, GetCand get1, uint32_t n
       if (a.strand == bb.strand) continue;
       const uint32_t sum = a.mm + bb.mm;
       if (sum > min_mm) break;
-      const uint32_t c2 = chrom_of(cv.starts, cv.n_chr, bb.pos);
+      const uint32_t c2 = pre ? chr2[j] : chrom_of(cv.starts, cv.n_chr, bb.pos);
       if (c1 != c2) continue;
       uint32_t s2, e2;
-      forward_position(cv.starts, bb.pos, bb.strand, c2, len2, s2, e2);
+      if (pre) { s2 = start2[j]; e2 = s2 + len2; }
+      else forward_position(cv.starts, bb.pos, bb.strand, c2, len2, s2, e2);
       const int32_t frag = a.strand == '+' ? (int32_t)(e2 - s1) : (int32_t)(e1 - s2);
       if (frag <= 0 || frag > frag_range) continue;
       const uint64_t cur = ((uint64_t)a.pos << 32) + bb.pos;
