@@ -450,7 +450,7 @@ def cli_leg(device, genome_mb, n_reads, rl, workdir=None, keep=False):
             stages = [l for l in err.splitlines() if l.startswith("[walt timing]")]
         out["ours_s"] = min(runs)
         out["ours_runs_s"] = [round(x, 3) for x in runs]
-        out["ours_stages"] = stages[-1] if stages else None
+        out["ours_stages"] = stages if stages else None
         out["ours_reads_per_s"] = n_reads / min(runs)
         d_ours = digest(o_out)
         ms_ours = open(o_out + ".mapstats", "rb").read()
@@ -738,7 +738,7 @@ def main():
                     help="se = configs[1] (the bench line), se_ag = configs[2], pe = configs[3], pe_stress = configs[4], "
                          "cli = the walt program on files against the reference program")
     ap.add_argument("--cli-genome-mb", type=float, default=300.0)
-    ap.add_argument("--cli-reads", type=int, default=5_000_000)
+    ap.add_argument("--cli-reads", type=int, default=10_000_000)
     ap.add_argument("--no-cli", action="store_true", help="skip the files-in/files-out leg of the default run")
     ap.add_argument("--reads", type=int, default=0, help="reads (pairs) per GPU; default 10 M reads / 5 M pairs")
     ap.add_argument("--read-len", type=int, default=150)

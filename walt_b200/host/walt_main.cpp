@@ -398,6 +398,7 @@ int main(int argc, const char** argv) {
     if (!se.empty()) mask |= (s.ag || s.pbat) ? (1u << WALT_GA10 | 1u << WALT_GA11) : (1u << WALT_CT00 | 1u << WALT_CT01);
     if (!pe1.empty()) mask |= 0xFu;
     Engines eng;
+    const auto t_index = std::chrono::steady_clock::now();
     if (mask) {
       eng.e.resize(s.gpus, nullptr);
       for (uint32_t i = 0; i < s.gpus; ++i) engine_check(walt_engine_create(&eng.e[i], (int)i));
@@ -411,6 +412,9 @@ int main(int argc, const char** argv) {
         });
       for (auto& t : th) t.join();
       for (uint32_t i = 0; i < s.gpus; ++i) if (rc[i]) throw std::runtime_error("walt engine: " + err[i]);
+      if (getenv("WALT_TIMING"))
+        fprintf(stderr, "[walt timing] engine start + index residency (%u GPU%s): %.3f s\n", s.gpus, s.gpus > 1 ? "s" : "",
+                StageClock::since(t_index));
     }
 
     size_t oi = 0;
