@@ -173,6 +173,28 @@ def test_pe_golden(engine, width):
                 assert (t, bi.value, bj.value) == (pr[j]["best_times"], pr[j]["best_i"], pr[j]["best_j"]), j
 
 
+@pytest.mark.parametrize("m,k", [(6, 100), (16, 50), (15, 70), (2, 300)])
+def test_pe_heap_variants_vs_oracle(engine, m, k):
+    """The corners of the two-phase paired-end form against the C oracle: top_k above the local-heap
+    capacity of the replay kernel (heaps in global scratch), the largest -m the candidate log
+    supports (15) and the single-kernel fallback beyond it (16)."""
+    hdr, _ = goldenio.genome()
+    z = goldenio.load("pe.npz")
+    for width in (8, 32):
+        engine.set_group_width(width)
+        b1, o1 = refio.pack_reads(z["m1"])
+        b2, o2 = refio.pack_reads(z["m2"])
+        r = engine.map_pe(b1, o1, b2, o2, m=m, top_k=k, frag_range=1000)
+        c, _, _ = engine.map_pe_compact(b1, o1, b2, o2, m=m, top_k=k, frag_range=1000)
+        assert np.array_equal(c["pair"], r["pairs"])
+        for mate, ag in ((1, False), (2, True)):
+            ranked, sizes = refio.oracle_pe_mate(hdr, goldenio.se_pair(ag), z[f"m{mate}"], ag, m=m, top_k=k)
+            assert np.array_equal(sizes, r[f"n{mate}"]), (m, k, mate)
+            for f in ("genome_pos", "mismatch", "strand"):
+                assert np.array_equal(ranked[f], r[f"ranked{mate}"][f]), (m, k, mate, f)
+    engine.set_group_width(8)
+
+
 def test_pe_pbat_is_mate_swap(engine):
     z = goldenio.load("pe.npz")
     b1, o1 = refio.pack_reads(z["m1"])

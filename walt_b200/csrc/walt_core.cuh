@@ -968,6 +968,34 @@ WALT_HD void seed_lookup(W& w, const SubIndexView& ix, const ChromView& cv, cons
         WALT_PREFETCH(g0 + nw);
       }
     }
+#ifndef WALT_ROLLED_COMPARE
+#define WALT_ROLLED_COMPARE 1
+#endif
+#if WALT_ROLLED_COMPARE && WALT_SLOTS_AHEAD == 4
+    // One copy of the compare / bounds / sink code instead of four.  With the body unrolled the
+    // repeat path was bound by instruction fetch (stalled_no_instruction 19.7 cycles per issue:
+    // the four groups of a warp run this loop out of step, each fetching its own stream through a
+    // ~25 KB body); rolled, configs[4] went from 215 to 149 ms per 5 M pairs.
+    WALT_NO_UNROLL
+    for (uint32_t u = 0; u < SLOTS_AHEAD; ++u) {
+      if (base + u * WD >= last_excl) break;                 // uniform
+      const uint32_t eu = u == 0u ? e[0] : u == 1u ? e[1] : u == 2u ? e[2] : e[3];
+      bool valid = base + u * WD + lane < last_excl;
+      uint32_t g = 0, mm = 0;
+      if (valid) {
+        WindowResult r = compare_window(ix.genome, (uint64_t)eu + PAD_BASES - seed_i, R, VM, SM, nw);
+        mm = r.mismatches;
+        ctr.candidates++;
+        valid = sink.may_take(mm);
+      }
+      if (valid) {
+        const uint32_t chr = chrom_of(cv.starts, cv.n_chr, eu);
+        g = eu - seed_i;
+        valid = (eu - cv.starts[chr] >= seed_i) && !(g + read_len >= cv.starts[chr + 1u]);
+      }
+      sink.consume(w, valid, mm, g, strand);
+    }
+#else
     WALT_UNROLL
     for (uint32_t u = 0; u < SLOTS_AHEAD; ++u) {
       if (base + u * WD >= last_excl) break;                 // uniform
@@ -987,6 +1015,7 @@ WALT_HD void seed_lookup(W& w, const SubIndexView& ix, const ChromView& cv, cons
       }
       sink.consume(w, valid, mm, g, strand);
     }
+#endif
   }
 }
 
