@@ -971,7 +971,7 @@ WALT_HD void seed_lookup(W& w, const SubIndexView& ix, const ChromView& cv, cons
 #ifndef WALT_ROLLED_COMPARE
 #define WALT_ROLLED_COMPARE 1
 #endif
-#if WALT_ROLLED_COMPARE && WALT_SLOTS_AHEAD == 4
+#if WALT_ROLLED_COMPARE
     // One copy of the compare / bounds / sink code instead of four.  With the body unrolled the
     // repeat path was bound by instruction fetch (stalled_no_instruction 19.7 cycles per issue:
     // the four groups of a warp run this loop out of step, each fetching its own stream through a
@@ -979,7 +979,9 @@ WALT_HD void seed_lookup(W& w, const SubIndexView& ix, const ChromView& cv, cons
     WALT_NO_UNROLL
     for (uint32_t u = 0; u < SLOTS_AHEAD; ++u) {
       if (base + u * WD >= last_excl) break;                 // uniform
-      const uint32_t eu = u == 0u ? e[0] : u == 1u ? e[1] : u == 2u ? e[2] : e[3];
+      uint32_t eu = e[0];   // e[] lives in registers: select, do not index
+      WALT_UNROLL
+      for (uint32_t q = 1; q < SLOTS_AHEAD; ++q) eu = u == q ? e[q] : eu;
       bool valid = base + u * WD + lane < last_excl;
       uint32_t g = 0, mm = 0;
       if (valid) {
