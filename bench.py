@@ -480,7 +480,7 @@ def run_cli(args):
             "config": {"workload": f"walt -i <{r['genome_mb']:g} Mb index> -r <{r['reads']} SE {r['read_len']} bp reads> -sam -u -a "
                                    f"-m {M} -b {B}; reference: the unmodified walt -t <cores> on the same files"},
             "cli": r}
-    print(json.dumps(line))
+    emit(json.dumps(line))
     return 0
 
 
@@ -492,7 +492,7 @@ def run_reference(args):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import refio
     if not refio.have_reference():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref was not built (no /root/reference at build time)"}))
+        emit(json.dumps({"impl": "reference", "unavailable": "oracle/_ref was not built (no /root/reference at build time)"}))
         return 0
     wl = Workload(args, local, 0)
     hidx = wl.host_index()
@@ -517,7 +517,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(json.dumps(line))
     return 0
 
 
@@ -607,7 +607,7 @@ def run_ours(args):
     if args.no_e2e:   # kernel experiments only: not a bench line
         sampler.stop(windows)
         if rank == 0:
-            print(json.dumps({"experiment": True, "workload": wl.kind, "kernel_ms": float(np.mean(step_ms)),
+            emit(json.dumps({"experiment": True, "workload": wl.kind, "kernel_ms": float(np.mean(step_ms)),
                               "per_s": n * 1e3 / float(np.mean(step_ms)),
                               "env": {k: v for k, v in os.environ.items() if k.startswith("WALT_")}}))
         return 0
@@ -718,7 +718,7 @@ def run_ours(args):
                 line["cli"] = cli_leg(local, args.cli_genome_mb, args.cli_reads, rl)
             except Exception as ex:   # the bench line stands without it
                 line["cli"] = {"error": str(ex)[-300:]}
-        print(json.dumps(line))
+        emit(json.dumps(line))
     for h in (h_reads, h_reads2, h_offs, h_out, h_pk, h_pk2):
         if h is not None:
             h.free()
@@ -727,7 +727,19 @@ def run_ours(args):
     return 0
 
 
+_RESULT_OUT = None
+
+
+def emit(text):
+    """The one JSON line goes to the process's real stdout; everything else that native code writes
+    to fd 1 while the bench runs (NCCL's version banner, for one) has been pointed at stderr."""
+    out = _RESULT_OUT or sys.stdout
+    out.write(text + "\n")
+    out.flush()
+
+
 def main():
+    global _RESULT_OUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -747,6 +759,9 @@ def main():
     ap.add_argument("--group-width", type=int, default=8, help="lanes that own one read (8, 16, 32)")
     ap.add_argument("--table-depth", type=int, default=0, help="prefix-table depth (0 = auto)")
     args = ap.parse_args()
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.reads <= 0:
