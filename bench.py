@@ -64,6 +64,28 @@ def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this rank (and so the first-touch placement of its pinned host buffers) to the CPUs NVML
+    reports as local to its GPU: with several ranks per box the host<->device copies otherwise cross
+    sockets.  Returns the number of CPUs bound to, or None if nothing was changed."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[gpu_index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else gpu_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        local = {c for c in range(ncpu) if (int(words[c // 64]) >> (c % 64)) & 1}
+        allowed = os.sched_getaffinity(0) & local
+        if allowed and allowed != os.sched_getaffinity(0):
+            os.sched_setaffinity(0, allowed)
+            return len(allowed)
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """SM clock and throttle reasons sampled through NVML every few milliseconds on a background
     thread while the timed regions run (the nvidia-smi loop of B200_PROFILING.md cannot sample a
@@ -535,6 +557,7 @@ def run_ours(args):
         dist = None
         torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
+    numa_cpus = bind_to_gpu_numa_node(local) if world > 1 else None
     wl = Workload(args, local, rank)
     e, n, rl = wl.e, wl.n, wl.rl
     pe = wl.is_pe
@@ -698,6 +721,7 @@ def run_ours(args):
                 "config": config_dict(args, {"index_build_s": round(wl.t_index, 1), "hbm_index_bytes": e.hbm_bytes(),
                                              "table_depth": [e.subindex_info(w)["depth"] for w in wl.which],
                                              "group_width": args.group_width,
+                                             "rank0_cpus_local_to_gpu": numa_cpus,
                                              "index_tie_order": {"rule": "std::sort replay (byte-identical to reference makedb)",
                                                                  **wl.build_info}}),
                 "clocks": clocks,
