@@ -705,7 +705,7 @@ def run_ours(args):
         peak, peak_kind = measured_peak_gbs()
         kernel_s = float(np.mean(step_ms)) / 1e3
         roof = None
-        kname = "pe_map_kernel" if pe else "se_map_kernel"
+        kname = "pe_log_kernel" if pe else "se_map_kernel"
         if alg is not None:
             achieved = alg["total"] * n / kernel_s / 1e9
             roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -714,7 +714,7 @@ def run_ours(args):
                     "algorithmic_bytes_per_read": alg, "kernel_ms": kernel_s * 1e3,
                     "note": "algorithmic bytes follow SURVEY.md 8(d) (the reference's binary-search probes); "
                             "achieved/frac are that figure over the step's device time"
-                            + (" (two pe_map_kernel launches + pair_kernel per chunk)" if pe else "")}
+                            + (" (per chunk: pe_log_kernel for each mate, pe_heap_kernel, pair_kernel)" if pe else "")}
         line = {"metric": metric, "value": total / t_dev, "unit": unit, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
