@@ -86,6 +86,8 @@ typedef struct {
 const char* walt_last_error(void);
 
 /* ---- engine lifetime ----------------------------------------------------------------- */
+/* CUDA devices visible to the process (0 if there is none or the driver cannot be reached). */
+int walt_device_count(void);
 int walt_engine_create(walt_engine** out, int device);
 void walt_engine_destroy(walt_engine* e);
 

@@ -54,12 +54,15 @@ def test_walt_cli_matches_reference(case, dbindex, tmp_path):
     _compare(str(tmp_path), os.path.join(CLI, case["name"]), case["files"])
 
 
-def test_walt_cli_two_gpus_worth_of_sharding(dbindex, tmp_path):
-    """-gpus 1 with tiny -N (multi-batch) is covered above; here the per-GPU range split is
-    exercised on one device by asking for more shards than reads per batch would need."""
-    case = next(c for c in CASES if c["name"] == "se_smallN")
+@pytest.mark.parametrize("name", ["se_smallN", "se_sam", "pe_smallN", "pe_sam", "pe_clip_k3"])
+def test_walt_cli_sharded_over_engines(dbindex, tmp_path, name):
+    """-gpus 3: every batch is cut into three contiguous ranges, each mapped by its own engine
+    (walt_main.cpp: packed + lo, offs + lo) and written back into its slice of the batch's result
+    array.  With fewer devices than shards the engines share devices, so the split is exercised on
+    a one-GPU box as well; the bytes must not depend on it."""
+    case = next(c for c in CASES if c["name"] == name)
     args = [a if not a.endswith(".fastq") else os.path.join(CLI, a) for a in case["args"]]
-    r = _run(["-i", dbindex, "-o", str(tmp_path / "out")] + args)
+    r = _run(["-i", dbindex, "-o", str(tmp_path / "out"), "-gpus", "3"] + args)
     assert r.returncode == 0, r.stderr.decode()[-2000:]
     _compare(str(tmp_path), os.path.join(CLI, case["name"]), case["files"])
 

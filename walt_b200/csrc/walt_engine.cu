@@ -794,6 +794,11 @@ extern "C" {
 
 const char* walt_last_error(void) { return g_error.c_str(); }
 
+int walt_device_count(void) {
+  int n = 0;
+  return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
 int walt_engine_create(walt_engine** out, int device) {
   if (!out) return fail(WALT_EINVAL, "out is NULL");
   *out = nullptr;

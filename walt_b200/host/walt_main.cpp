@@ -401,7 +401,12 @@ int main(int argc, const char** argv) {
     const auto t_index = std::chrono::steady_clock::now();
     if (mask) {
       eng.e.resize(s.gpus, nullptr);
-      for (uint32_t i = 0; i < s.gpus; ++i) engine_check(walt_engine_create(&eng.e[i], (int)i));
+      // one engine (one index replica) per shard; with more shards than devices they share devices
+      const int n_dev = walt_device_count();
+      if (n_dev > 0 && s.gpus > (uint32_t)n_dev)
+        std::cerr << "[-gpus " << s.gpus << " on " << n_dev << " visible device(s): shards share devices]" << std::endl;
+      for (uint32_t i = 0; i < s.gpus; ++i)
+        engine_check(walt_engine_create(&eng.e[i], n_dev > 0 ? (int)(i % (uint32_t)n_dev) : (int)i));
       std::vector<int> rc(s.gpus, 0);
       std::vector<std::string> err(s.gpus);
       std::vector<std::thread> th;
