@@ -88,14 +88,17 @@ def _swap_mate_lines(sam_bytes):
 
 
 @pytest.mark.reference
-def test_pbat_equals_reference_with_mates_swapped(dbindex, tmp_path):
+@pytest.mark.parametrize("clip", [[], ["-C", "AGATCGGAAGAGC:TCGGAAGAGCACA", "-m", "8"]], ids=["plain", "clip_m8"])
+def test_pbat_equals_reference_with_mates_swapped(dbindex, tmp_path, clip):
+    """-P against its derived oracle; with -C T_adaptor:A_adaptor the T-rich adaptor
+    belongs to the C->T mate, which is the SECOND file under PBAT (configs[4]: -P -C ... -m 8)."""
     if not refio.have_reference():
         pytest.skip("oracle/_ref not built")
     f1, f2 = os.path.join(CLI, "pe_reads_1.fastq"), os.path.join(CLI, "pe_reads_2.fastq")
     ref_out = str(tmp_path / "ref.sam")
-    refio.ref_walt(["-i", dbindex, "-1", f2, "-2", f1, "-o", ref_out, "-sam", "-u", "-a", "-k", "10", "-L", "500"])
+    refio.ref_walt(["-i", dbindex, "-1", f2, "-2", f1, "-o", ref_out, "-sam", "-u", "-a", "-k", "10", "-L", "500"] + clip)
     r = _run(["-i", dbindex, "-1", f1, "-2", f2, "-P", "-o", str(tmp_path / "our.sam"), "-sam", "-u", "-a", "-k", "10",
-              "-L", "500"])
+              "-L", "500"] + clip)
     assert r.returncode == 0, r.stderr.decode()[-2000:]
     want = _swap_mate_lines(open(ref_out, "rb").read())
     got = open(str(tmp_path / "our.sam"), "rb").read()
