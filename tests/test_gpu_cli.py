@@ -118,6 +118,34 @@ def test_pbat_equals_reference_with_mates_swapped(dbindex, tmp_path, clip):
         assert open(str(tmp_path / "a.mr") + sfx, "rb").read() == open(str(tmp_path / "p.mr") + sfx, "rb").read()
 
 
+@pytest.mark.reference
+@pytest.mark.parametrize("one_output", [False, True])
+def test_file_lists_match_reference(dbindex, tmp_path, one_output):
+    """Comma-separated read-file lists, single-end and paired-end inputs in one run, one output per
+    input or one shared output (walt.cpp:205-233, 255-273): every file both programs write must be
+    identical.  The reference is run here, next to ours."""
+    if not refio.have_reference():
+        pytest.skip("oracle/_ref not built")
+    se = ",".join(os.path.join(CLI, f) for f in ("se_reads.fastq", "crlf_reads.fastq"))
+    opts = ["-i", dbindex, "-r", se, "-1", os.path.join(CLI, "pe_reads_1.fastq"), "-2", os.path.join(CLI, "pe_reads_2.fastq"),
+            "-sam", "-u", "-N", "700"]
+    dirs = {}
+    for who in ("ref", "ours"):
+        d = tmp_path / who
+        d.mkdir()
+        outs = str(d / "all.sam") if one_output else ",".join(str(d / f"o{i}.sam") for i in range(3))
+        if who == "ref":
+            refio.ref_walt(opts + ["-o", outs])
+        else:
+            r = _run(opts + ["-o", outs])
+            assert r.returncode == 0, r.stderr.decode()[-2000:]
+        dirs[who] = d
+    names = sorted(os.listdir(dirs["ref"]))
+    assert names == sorted(os.listdir(dirs["ours"])) and len(names) >= (2 if one_output else 6)
+    for f in names:
+        assert open(dirs["ref"] / f, "rb").read() == open(dirs["ours"] / f, "rb").read(), f
+
+
 def test_cli_errors(dbindex, tmp_path):
     f = os.path.join(CLI, "se_reads.fastq")
     out = str(tmp_path / "o")
