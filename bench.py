@@ -492,16 +492,82 @@ def cli_leg(device, genome_mb, n_reads, rl, workdir=None, keep=False):
             shutil.rmtree(work, ignore_errors=True)
 
 
+def makedb_leg(device, genome_mb, repeats=False):
+    """`walt_b200/bin/makedb` against the unmodified `oracle/_ref/makedb` on the same FASTA file:
+    whole-process wall clock of each, the five index files compared byte for byte."""
+    import shutil
+    import subprocess
+    import tempfile
+    import torch
+    from walt_b200 import engine as eng
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import refio
+    import synth
+    total = int(genome_mb * 1e6)
+    lengths = chrom_lengths(total)
+    work = tempfile.mkdtemp(prefix="walt_makedb_", dir=os.environ.get("WALT_BENCH_TMP") or None)
+    out = {"genome_mb": genome_mb, "repeat_heavy": bool(repeats)}
+    try:
+        # the genome comes from the device generator so that it matches the other workloads' model
+        d = torch.empty(eng.packed_genome_bytes(total), dtype=torch.uint8, device=f"cuda:{device}")
+        eng.synth_genome_device(device, total, 9, d.data_ptr(), repeats=repeats)
+        words = d.cpu().numpy().view(np.uint64)[1:]      # word 0 is the pad; first base in the top bits
+        codes = np.zeros(words.size * 32, np.uint8)
+        w = words.astype(np.uint64)
+        for i in range(32):
+            codes[i::32] = ((w >> np.uint64(62 - 2 * i)) & np.uint64(3)).astype(np.uint8)
+        seq = np.frombuffer(b"ACGT", np.uint8)[codes[:total]]
+        del d, w, codes
+        torch.cuda.empty_cache()
+        chroms, at = [], 0
+        for i, ln in enumerate(lengths):
+            chroms.append((f"chr{i + 1}", seq[at:at + int(ln)]))
+            at += int(ln)
+        fa = os.path.join(work, "genome.fa")
+        synth.write_fasta(fa, chroms)
+        out["fasta_bytes"] = os.path.getsize(fa)
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(device))
+        ours = os.path.join(work, "ours.dbindex")
+        t = time.perf_counter()
+        r = subprocess.run([os.path.join(ROOT, "walt_b200", "bin", "makedb"), "-c", fa, "-o", ours],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+        out["ours_s"] = time.perf_counter() - t
+        if r.returncode != 0:
+            raise RuntimeError("makedb failed: " + r.stderr.decode()[-400:])
+        out["index_bytes"] = sum(os.path.getsize(ours + sfx) for sfx in ("", "_CT00", "_CT01", "_GA10", "_GA11"))
+        if refio.have_reference():
+            ref = os.path.join(work, "ref.dbindex")
+            t = time.perf_counter()
+            refio.ref_makedb(fa, ref)
+            out["reference_s"] = time.perf_counter() - t
+            out["speedup"] = out["reference_s"] / out["ours_s"]
+            same = True
+            for sfx in ("", "_CT00", "_CT01", "_GA10", "_GA11"):
+                a, b = ours + sfx, ref + sfx
+                same = same and os.path.getsize(a) == os.path.getsize(b) and \
+                    subprocess.run(["cmp", "-s", a, b]).returncode == 0
+            out["files_identical"] = bool(same)
+        return out
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
 def run_cli(args):
     rank, local, world = dist_env()
     if rank != 0:
         return 0
     r = cli_leg(local, args.cli_genome_mb, args.cli_reads, args.read_len)
+    mk = None
+    if args.makedb_genome_mb > 0:
+        try:
+            mk = makedb_leg(local, args.makedb_genome_mb, repeats=args.makedb_repeats)
+        except Exception as ex:
+            mk = {"error": str(ex)[-300:]}
     line = {"metric": "reads mapped/sec, walt program: .dbindex + FASTQ files in, SAM file out (process wall clock)",
             "value": r["ours_reads_per_s"], "unit": "reads/s", "n_gpus": 1, "higher_is_better": True, "data": "synthetic",
             "config": {"workload": f"walt -i <{r['genome_mb']:g} Mb index> -r <{r['reads']} SE {r['read_len']} bp reads> -sam -u -a "
                                    f"-m {M} -b {B}; reference: the unmodified walt -t <cores> on the same files"},
-            "cli": r}
+            "cli": r, "makedb": mk}
     emit(json.dumps(line))
     return 0
 
@@ -775,6 +841,9 @@ def main():
                          "cli = the walt program on files against the reference program")
     ap.add_argument("--cli-genome-mb", type=float, default=300.0)
     ap.add_argument("--cli-reads", type=int, default=10_000_000)
+    ap.add_argument("--makedb-genome-mb", type=float, default=50.0,
+                    help="--workload cli: also run makedb against the reference makedb on a genome of this size (0 = skip)")
+    ap.add_argument("--makedb-repeats", action="store_true", help="... on the repeat-heavy genome model (tied suffixes)")
     ap.add_argument("--no-cli", action="store_true", help="skip the files-in/files-out leg of the default run")
     ap.add_argument("--reads", type=int, default=0, help="reads (pairs) per GPU; default 10 M reads / 5 M pairs")
     ap.add_argument("--read-len", type=int, default=150)
