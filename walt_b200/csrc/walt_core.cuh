@@ -35,12 +35,12 @@
 
 #if defined(__CUDACC__)
 #define WALT_HD __host__ __device__ __forceinline__
-#define WALT_HD_NOINLINE __host__ __device__ __noinline__
+#define WALT_HD_NOINLINE inline __host__ __device__ __noinline__
 #define WALT_UNROLL _Pragma("unroll")
 #define WALT_NO_UNROLL _Pragma("unroll 1")
 #else
 #define WALT_HD inline
-#define WALT_HD_NOINLINE
+#define WALT_HD_NOINLINE inline
 #define WALT_UNROLL
 #define WALT_NO_UNROLL
 #endif
@@ -403,7 +403,7 @@ WALT_HD bool load_read(W& w, const char* __restrict__ seq, uint32_t read_len, bo
 
 // Verification / seed masks for every shift (depend on read_len only).
 template <class W>
-WALT_HD void build_masks(W& w, uint32_t read_len, ReadScratch& sc) {
+WALT_HD_NOINLINE void build_masks(W& w, uint32_t read_len, ReadScratch& sc) {   // once per read length: out of the hot loop
   const uint32_t lane = w.lane();
   const uint32_t nw = (read_len + 31u) >> 5;
   const uint32_t spr = seed_repeats(read_len);
@@ -792,7 +792,7 @@ WALT_HD bool lookup_is_affected(W& w, const SubIndexView& ix, const uint64_t* R,
   return affected;
 }
 // The same test by a single lane.
-WALT_HD bool lane_is_affected(const SubIndexView& ix, const uint64_t* R, uint32_t seed_i, uint32_t seed_len,
+WALT_HD_NOINLINE bool lane_is_affected(const SubIndexView& ix, const uint64_t* R, uint32_t seed_i, uint32_t seed_len,
                               uint32_t key12) {
   uint32_t t0, t1;
   taint_slots(ix, key12, t0, t1);
