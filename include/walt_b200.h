@@ -180,6 +180,10 @@ int walt_engine_set_table_depth(walt_engine* e, int depth);
 int walt_engine_set_chunk_reads(walt_engine* e, uint32_t n);
 /* Lanes of a warp that cooperate on one read: 8 (default; four reads per warp), 16 or 32. */
 int walt_engine_set_group_width(walt_engine* e, uint32_t lanes);
+/* 1 (default): a read whose ordered fold reaches a lookup that needs more than one lane (a long run of
+ * equal seeds = repeats, or a bucket next to a chromosome end) is parked by the mapping kernel and
+ * finished by a second kernel with a whole warp per read; 0: every read is finished by its group. */
+int walt_engine_set_defer(walt_engine* e, int on);
 
 /* ---- pinned host memory for batch buffers --------------------------------------------- */
 void* walt_host_alloc(size_t bytes);

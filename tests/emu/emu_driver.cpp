@@ -315,11 +315,11 @@ void se_lane(WarpEmu* w, uint32_t lane, void* arg) {
   for (uint32_t r = j->lo; r < j->hi; ++r) {
     BestState st;
     uint32_t len = (uint32_t)(j->offs[r + 1] - j->offs[r]);
-    bool ok = j->packed
+    bool ok = MAP_OK == (j->packed
                   ? map_read_se<EmuWarp<WD>, true>(W, ix2, cv, j->e->p3, cfg, j->seqs + (j->offs[r] >> 2) + r, len,
                                                    j->ag != 0, j->m, sc, cached, st, ctr)
                   : map_read_se<EmuWarp<WD>, false>(W, ix2, cv, j->e->p3, cfg, j->seqs + j->offs[r], len, j->ag != 0,
-                                                    j->m, sc, cached, st, ctr);
+                                                    j->m, sc, cached, st, ctr));
     if (lane == 0) {
       if (!ok) *j->bad = 1;
       j->out[r].genome_pos = st.pos; j->out[r].times = st.times; j->out[r].mismatch = st.mm;
@@ -356,13 +356,13 @@ void pe_lane(WarpEmu* w, uint32_t lane, void* arg) {
     bool ok;
     if (j->logged) {
       uint32_t n_log = 0;
-      ok = map_read_pe_logged(W, ix2, cv, j->e->p3, cfg, j->seqs + j->offs[r], len, j->ag != 0, j->m,
-                              j->top_k, sc, cached, j->log, j->hist, n_log, ctr);
+      ok = MAP_OK == map_read_pe_logged(W, ix2, cv, j->e->p3, cfg, j->seqs + j->offs[r], len, j->ag != 0, j->m,
+                                        j->top_k, sc, cached, j->log, j->hist, n_log, ctr);
       W.sync();
       if (lane == 0) replay_heap_log(j->log, n_log, j->top_k, j->heap, hsize);   // second kernel: one thread per read
     } else {
-      ok = map_read_pe(W, ix2, cv, j->e->p3, cfg, j->seqs + j->offs[r], len, j->ag != 0, j->m,
-                       j->top_k, sc, cached, j->heap, hsize, ctr);
+      ok = MAP_OK == map_read_pe(W, ix2, cv, j->e->p3, cfg, j->seqs + j->offs[r], len, j->ag != 0, j->m,
+                                 j->top_k, sc, cached, j->heap, hsize, ctr);
     }
     if (lane == 0) {
       if (!ok) *j->bad = 1;

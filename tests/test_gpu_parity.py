@@ -195,6 +195,75 @@ def test_pe_heap_variants_vs_oracle(engine, m, k):
     engine.set_group_width(8)
 
 
+@pytest.fixture(scope="module")
+def repeat_world():
+    """high-copy repeat families: hundreds of candidates per lookup (tests/test_repeat_emu.py runs the
+    same genome on the CPU harness)"""
+    import walt_b200
+    chroms = synth.make_repeat_genome([90000, 60000, 30000], seed=23, n_families=5, fam_len=(170, 420),
+                                      copies=(60, 260), divergence=0.006, repeat_frac=0.7)
+    hdr, subs = refio.build_index_with_oracle(chroms)
+    e = walt_b200.Engine(0)
+    e.set_chromosomes(hdr.lengths, hdr.names)
+    for w, sfx in enumerate(refio.SUFFIXES):
+        e.load_subindex(w, subs[sfx].seq, subs[sfx].counter, subs[sfx].index)
+    yield chroms, hdr, subs, e
+    e.close()
+
+
+def _acgt(reads):
+    out = reads.copy()
+    out[out == ord("N")] = ord("A")
+    return out
+
+
+@pytest.mark.parametrize("defer,width", [(1, 8), (0, 8), (1, 32), (0, 32), (1, 16)])
+def test_se_repeats_vs_oracle(repeat_world, defer, width):
+    """parked reads finished by the warp-per-read kernel (quad verification) == every read finished
+    by its group == the oracle"""
+    chroms, hdr, subs, e = repeat_world
+    e.set_defer(defer)
+    e.set_group_width(width)
+    try:
+        for rl, m, b in ((150, 6, 5000), (150, 6, 40), (100, 4, 5000), (200, 8, 5000), (192, 6, 5000), (193, 6, 5000)):
+            for ag, pair in ((False, ("_CT00", "_CT01")), (True, ("_GA10", "_GA11"))):
+                reads = _acgt(synth.simulate_se_reads(chroms, 3000, rl, seed=31 + rl + m, a_rich=ag))
+                ctr = refio.WoCounters()
+                want = refio.oracle_se_map(hdr, tuple(subs[s] for s in pair), reads, ag=ag, m=m, b=b, counters=ctr)
+                buf, offs = refio.pack_reads(reads)
+                got, _ = e.map_se(buf, offs, ag=ag, m=m, b=b)
+                _cmp_best(got, want, (defer, width, rl, m, b, ag))
+                if b == 5000:
+                    assert ctr.asdict()["n_cand"] > 20 * len(reads)
+                if defer:
+                    assert e.stats()["n_kernel_launches"] == 2
+    finally:
+        e.set_defer(1)
+        e.set_group_width(8)
+
+
+@pytest.mark.parametrize("defer,width", [(1, 8), (0, 8), (1, 32)])
+def test_pe_repeats_vs_oracle(repeat_world, defer, width):
+    chroms, hdr, subs, e = repeat_world
+    e.set_defer(defer)
+    e.set_group_width(width)
+    try:
+        m1, m2 = synth.simulate_pe_reads(chroms, 3000, 150, seed=41)
+        m1, m2 = _acgt(m1), _acgt(m2)
+        b1, o1 = refio.pack_reads(m1)
+        b2, o2 = refio.pack_reads(m2)
+        for m, k, b in ((8, 50, 5000), (6, 10, 5000), (8, 50, 60), (3, 2, 5000), (15, 20, 5000), (8, 100, 5000)):
+            r = e.map_pe(b1, o1, b2, o2, m=m, b=b, top_k=k, frag_range=1000)
+            for mate, reads, ag, pair in ((1, m1, False, ("_CT00", "_CT01")), (2, m2, True, ("_GA10", "_GA11"))):
+                want, sizes = refio.oracle_pe_mate(hdr, tuple(subs[s] for s in pair), reads, ag, m=m, b=b, top_k=k)
+                assert np.array_equal(r[f"n{mate}"], sizes), (m, k, b, mate)
+                for f in ("genome_pos", "mismatch", "strand"):
+                    assert np.array_equal(r[f"ranked{mate}"][f], want[f]), (m, k, b, mate, f)
+    finally:
+        e.set_defer(1)
+        e.set_group_width(8)
+
+
 def test_pe_pbat_is_mate_swap(engine):
     z = goldenio.load("pe.npz")
     b1, o1 = refio.pack_reads(z["m1"])

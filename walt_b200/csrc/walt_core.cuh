@@ -706,41 +706,71 @@ struct LogSink {
     return full && ((top_mm == 0u && seed_i >= 1u) || (top_mm == 1u && seed_i >= 2u));
   }
   WALT_HD bool may_take(uint32_t mm) const { return mm <= max_mm && (size < cap || mm < top_mm); }
-  // one candidate that passed may_take against the CURRENT state; arguments are group-uniform
-  WALT_HD void take_one(W& w, uint32_t g, uint32_t mm, uint32_t strand) {
-    if (size < cap) {
-      if (w.lane() == 0u) hist[mm]++;
-      top_mm = (size == 0u || mm > top_mm) ? mm : top_mm;
-      ++size;
-    } else {
-      if (w.lane() == 0u) { hist[top_mm]--; hist[mm]++; }
-      w.sync();
-      uint32_t t = top_mm;
-      while (t > 0u && hist[t] == 0u) --t;   // mm < top_mm went in, so some counter at or below is set
-      top_mm = t;
-      w.sync();                              // the next event's writer must not run ahead of these reads
-    }
-    if (w.lane() == 0u) {
-      HeapEntry v; v.pos = g; v.mm_strand = mm | (strand == '-' ? 0x10000u : 0u);
-      log[n_log] = v;
-    }
-    ++n_log;
-  }
+  // Candidates of lanes (ascending = index order) with valid set.  The reference pushes them one by
+  // one (paired.hpp:60-67); here whole prefixes of the batch are taken per step, which is the same
+  // thing because the state only changes in two ways:
+  //  * not full: every candidate with mm <= max_mm is kept, so the first `cap - size` of them are
+  //    taken together;
+  //  * full: a candidate is kept iff mm < top_mm, and each take removes one entry with mm == top_mm.
+  //    top_mm therefore stays put for the next hist[top_mm] takes: the first hist[top_mm] lanes
+  //    with mm < top_mm are taken together, every lane in front of the last of them that was not
+  //    taken has been turned away for good (top_mm only falls), and only then is top_mm lowered.
+  // Log slots, histogram counters and top_mm end up exactly as after the one-by-one loop.
   WALT_HD void consume(W& w, bool valid, uint32_t mm, uint32_t g, uint32_t strand) {
-    uint32_t take = w.ballot(valid && may_take(mm));   // a superset: the state only gets stricter
-    while (take) {
-      int src = ffs32(take) - 1;
-      take &= take - 1u;
-      const uint32_t cg = w.shfl(g, src);
-      const uint32_t cm = w.shfl(mm, src);
-      if (may_take(cm)) take_one(w, cg, cm, strand);
+    uint32_t pending = w.ballot(valid && may_take(mm));   // a superset: the state only gets stricter
+    if (!pending) return;
+    const uint32_t lane = w.lane();
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t sbit = strand == '-' ? 0x10000u : 0u;
+    while (pending) {
+      const bool mine = ((pending >> lane) & 1u) != 0u;
+      const bool was_full = size >= cap;
+      uint32_t T;
+      if (!was_full) {
+        T = w.ballot(mine && popc32(pending & lt) < cap - size);
+      } else {
+        const uint32_t P = w.ballot(mine && mm < top_mm);
+        if (!P) break;
+        T = w.ballot(((P >> lane) & 1u) != 0u && popc32(P & lt) < hist[top_mm]);   // hist[top_mm] >= 1
+      }
+      const bool in_t = ((T >> lane) & 1u) != 0u;
+      const uint32_t n_t = popc32(T);
+      const int last = 31 - clz32(T);
+      if (in_t) {
+        HeapEntry v; v.pos = g; v.mm_strand = mm | sbit;
+        log[n_log + popc32(T & lt)] = v;
+      }
+      uint32_t mx = 0u;   // largest mismatch count among the taken
+      if (n_t == 1u) {
+        mx = w.shfl(mm, last);
+        if (lane == 0u) hist[mx]++;
+      } else {
+        for (uint32_t v = 0; v <= max_mm; ++v) {
+          const uint32_t c = popc32(w.ballot(in_t && mm == v));
+          if (c) { mx = v; if (lane == 0u) hist[v] += c; }
+        }
+      }
+      n_log += n_t;
+      if (!was_full) {
+        top_mm = (size == 0u || mx > top_mm) ? mx : top_mm;
+        size += n_t;
+      } else {
+        if (lane == 0u) hist[top_mm] -= n_t;
+        w.sync();
+        uint32_t t = top_mm;
+        while (t > 0u && hist[t] == 0u) --t;   // something below went in, so a counter at or below is set
+        top_mm = t;
+      }
+      w.sync();                                // the next step's writer must not run ahead of these reads
+      pending &= ~((2u << last) - 1u);         // lanes up to the last taken one are settled
     }
   }
+  // n candidates (all with mm <= max_mm, index order) found by one lookup lane
   WALT_HD void push_list(W& w, const LaneCand* c, uint32_t n, uint32_t strand) {
-    for (uint32_t k = 0; k < n; ++k) {
-      const LaneCand v = c[k];
-      if (may_take(v.mm)) take_one(w, v.g, v.mm, strand);
-    }
+    const uint32_t lane = w.lane();
+    LaneCand v; v.g = 0u; v.mm = 0u;
+    if (lane < n) v = c[lane];
+    consume(w, lane < n, v.mm, v.g, strand);
   }
 };
 
@@ -825,6 +855,167 @@ WALT_HD void kary_narrow(W& w, uint32_t& l, uint32_t& h, Pred below) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// warp-wide verification of a run of index slots (repeats)
+// ------------------------------------------------------------------------------------------
+// Four lanes (a quad) own one candidate: lane q loads the q-th aligned 16 bytes (64 bases) of the
+// 64-byte block that holds the candidate's window, so one 128-bit load instruction of the warp
+// fetches eight whole windows, each from a single cache line (a lane-per-candidate loop touches 32
+// lines per instruction, and the L1 serves about one line per two cycles).  A window of up to
+// WIDE_MAX_READ bases starting anywhere in the first 64 bases of the block fits its 256 bases.
+// Lane q compares read bases [64q, 64q + 64): its genome bases straddle its own and the next
+// lane's 16 bytes (four shuffles), are aligned with two select levels and four funnel shifts, and
+// the read words / masks of block q stay in registers for the whole run.
+constexpr uint32_t WIDE_MAX_READ = 192;
+
+struct Quad32 { uint32_t b[4]; };   // 64 bases in base order, 16 per word, first base on top
+
+WALT_HD Quad32 load_genome16(const uint64_t* __restrict__ genome, uint64_t unit16) {
+  Quad32 r;
+#if defined(__CUDA_ARCH__)
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(genome) + unit16);   // little-endian u64 pairs
+  r.b[0] = v.y; r.b[1] = v.x; r.b[2] = v.w; r.b[3] = v.z;
+#else
+  const uint64_t w0 = genome[2u * unit16], w1 = genome[2u * unit16 + 1u];
+  r.b[0] = (uint32_t)(w0 >> 32); r.b[1] = (uint32_t)w0; r.b[2] = (uint32_t)(w1 >> 32); r.b[3] = (uint32_t)w1;
+#endif
+  return r;
+}
+// high word of (hi:lo) << n, n in [0, 31]
+WALT_HD uint32_t funnel_left(uint32_t hi, uint32_t lo, uint32_t n) {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_l(lo, hi, n);
+#else
+  return n ? ((hi << n) | (lo >> (32u - n))) : hi;
+#endif
+}
+// 64-base block q of a packed array of nw words (zero beyond it), as four words in base order
+WALT_HD Quad32 read_block(const uint64_t* a, uint32_t q, uint32_t nw) {
+  const uint64_t w0 = 2u * q < nw ? a[2u * q] : 0ull, w1 = 2u * q + 1u < nw ? a[2u * q + 1u] : 0ull;
+  Quad32 r;
+  r.b[0] = (uint32_t)(w0 >> 32); r.b[1] = (uint32_t)w0; r.b[2] = (uint32_t)(w1 >> 32); r.b[3] = (uint32_t)w1;
+  return r;
+}
+
+// One block of 32 consecutive slots in flight: lane L holds slot base + L; quad c verifies slots
+// base + 4c + u in step u (u = 0..3), so after the four steps lane 4c + u picks step u's result and
+// again holds slot base + L -- lane order is slot order, which is what the sinks consume.
+struct WideBlock {
+  Entry en;          // this lane's slot (zero past the end)
+  Quad32 g[4];       // this lane's 16 bytes of the four candidates of its quad
+  uint32_t sh;       // their alignments inside the 64-base unit, 8 bits each
+};
+
+template <class W>
+WALT_HD Entry wide_load_entry(W& w, const SubIndexView& ix, uint32_t base, uint32_t last_excl) {
+  const uint32_t slot = base + w.lane();
+  Entry en; en.pos = 0u; en.fp = 0u;
+  if (slot < last_excl && base < last_excl) en = ix.entries[slot];
+  return en;
+}
+template <class W>
+WALT_HD void wide_load_genome(W& w, const SubIndexView& ix, uint32_t seed_i, WideBlock& blk) {
+  const uint32_t lane = w.lane(), q = lane & 3u, c4 = lane & ~3u;
+  blk.sh = 0u;
+  WALT_UNROLL
+  for (uint32_t u = 0; u < 4u; ++u) {
+    const uint32_t e = w.shfl(blk.en.pos, (int)(c4 + u));       // slot 0 of a finished run: genome start, harmless
+    const uint64_t gp = (uint64_t)e + PAD_BASES - seed_i;
+    blk.g[u] = load_genome16(ix.genome, (gp >> 6) + q);
+    blk.sh |= ((uint32_t)gp & 63u) << (8u * u);
+  }
+}
+// mismatches of the lane's own slot over the verification mask (low 16 bits) + 0x10000 per quad lane
+// that saw a difference on a cared position (0 in the upper half <=> seed-equal)
+template <class W>
+WALT_HD uint32_t wide_compare(W& w, const WideBlock& blk, const Quad32& Rq, const Quad32& VMq, const Quad32& SMq) {
+  const uint32_t lane = w.lane(), q = lane & 3u;
+  uint32_t mine = 0u;
+  WALT_UNROLL
+  for (uint32_t u = 0; u < 4u; ++u) {
+    uint32_t B[8];
+    WALT_UNROLL
+    for (uint32_t i = 0; i < 4u; ++i) { B[i] = blk.g[u].b[i]; B[4u + i] = w.shfl(blk.g[u].b[i], (int)((lane + 1u) & 31u)); }
+    const uint32_t s = (blk.sh >> (8u * u)) & 63u;   // bases; 2s bits = (s >> 4) words + (2s & 31) bits
+    const uint32_t off = s >> 4, bit = (2u * s) & 31u;
+    uint32_t t[6], v[5];
+    WALT_UNROLL
+    for (uint32_t i = 0; i < 6u; ++i) t[i] = (off & 2u) ? B[i + 2u] : B[i];
+    WALT_UNROLL
+    for (uint32_t i = 0; i < 5u; ++i) v[i] = (off & 1u) ? t[i + 1u] : t[i];
+    uint32_t mm = 0u, sd = 0u;
+    WALT_UNROLL
+    for (uint32_t i = 0; i < 4u; ++i) {
+      const uint32_t x = funnel_left(v[i], v[i + 1u], bit) ^ Rq.b[i];
+      const uint32_t d = x | (x >> 1);
+      mm += popc32(d & VMq.b[i]);
+      sd |= d & SMq.b[i];
+    }
+    mm += sd ? 0x10000u : 0u;
+    mm += w.shfl(mm, (int)(lane ^ 1u));
+    mm += w.shfl(mm, (int)(lane ^ 2u));
+    mine = q == u ? mm : mine;
+  }
+  return mine;
+}
+
+// Feed the candidates of slots [first, last_excl) to the sink in slot order.  by_fp: the candidates
+// are the leading slots whose fingerprint lies in [fp_lo, fp_lo + fp_span] (a prefix of the range:
+// fingerprints are sorted inside a table range) and, of those, the seed-equal ones -- the
+// reference's narrowed region; otherwise every slot is a candidate.  W::WIDTH == 32 and
+// read_len <= WIDE_MAX_READ.  Three blocks are in flight: entries of the block after next, genome
+// of the next, compare + sink of the current one.
+template <class W, class Sink>
+WALT_HD void verify_run_wide(W& w, const SubIndexView& ix, const ChromView& cv, const ReadScratch& sc, uint32_t read_len,
+                             uint32_t seed_i, uint32_t strand, uint32_t first, uint32_t last_excl, bool by_fp,
+                             uint32_t fp_lo, uint32_t fp_span, Sink& sink, Counters& ctr) {
+  const uint32_t lane = w.lane(), q = lane & 3u;
+  const uint32_t nw = (read_len + 31u) >> 5;
+  const Quad32 Rq = read_block(sc.R, q, nw);
+  const Quad32 VMq = read_block(sc.VM + seed_i * sc.nw, q, nw);
+  Quad32 SMq = read_block(sc.SM + seed_i * sc.nw, q, nw);
+  if (!by_fp) { SMq.b[0] = SMq.b[1] = SMq.b[2] = SMq.b[3] = 0u; }
+  auto in_run = [&](const Entry& en, uint32_t base) {
+    return base + lane < last_excl && base < last_excl && (!by_fp || en.fp - fp_lo <= fp_span);   // unsigned: also rejects fp < fp_lo
+  };
+  uint32_t base = first;
+  WideBlock cur, nxt;
+  cur.en = wide_load_entry(w, ix, base, last_excl);
+  nxt.en = wide_load_entry(w, ix, base + 32u, last_excl);
+  uint32_t ok = w.ballot(in_run(cur.en, base));
+  if (!ok) return;
+  if (!((ok >> lane) & 1u)) cur.en.pos = 0u;
+  wide_load_genome(w, ix, seed_i, cur);
+  for (;;) {
+    // stage the following blocks (the run goes on only if every slot of this block was in it)
+    const bool more = ok == 0xFFFFFFFFu && base + 32u < last_excl;
+    uint32_t ok_next = 0u;
+    Entry en_after; en_after.pos = 0u; en_after.fp = 0u;
+    if (more) {
+      en_after = wide_load_entry(w, ix, base + 64u, last_excl);
+      ok_next = w.ballot(in_run(nxt.en, base + 32u));
+      if (!((ok_next >> lane) & 1u)) nxt.en.pos = 0u;
+      if (ok_next) wide_load_genome(w, ix, seed_i, nxt);
+    }
+    // this block
+    const uint32_t r = wide_compare(w, cur, Rq, VMq, SMq);
+    const uint32_t mm = r & 0xFFFFu;
+    bool valid = ((ok >> lane) & 1u) != 0u && (r >> 16) == 0u;
+    if (valid) ctr.candidates++;
+    valid = valid && sink.may_take(mm);
+    uint32_t g = 0u;
+    if (valid) {   // bounds, mapping.cpp:281-286
+      const uint32_t e = cur.en.pos;
+      const uint32_t chr = chrom_of(cv.starts, cv.n_chr, e);
+      g = e - seed_i;
+      valid = (e - cv.starts[chr] >= seed_i) && !(g + read_len >= cv.starts[chr + 1u]);
+    }
+    sink.consume(w, valid, mm, g, strand);
+    if (!ok_next) break;
+    cur = nxt; ok = ok_next; nxt.en = en_after; base += 32u;
+  }
+}
+
 template <class W, class Sink>
 WALT_HD void seed_lookup(W& w, const SubIndexView& ix, const ChromView& cv, const Pow3& p3,
                          const MapConfig& cfg, const ReadScratch& sc, uint32_t read_len,
@@ -893,7 +1084,21 @@ WALT_HD void seed_lookup(W& w, const SubIndexView& ix, const ChromView& cv, cons
     // the run of matches starts at f0; it is complete if it stops before the chunk does, or
     // the chunk reaches the end of the table range
     const bool complete = (f0 + n_match < h) || (h == hi);
-    if (complete) {
+    if (WD == 32u && read_len <= WIDE_MAX_READ && !(complete && n_match > cfg.b)) {
+      // Whole warp on one lookup (the kernels that take over parked reads): the fingerprint run
+      // that starts at f0 is streamed through the quad verification, eight windows per load
+      // instruction; seed equality is checked per candidate, so no equal-range search on the
+      // genome is needed.  The narrowed region (what -b applies to, mapping.cpp:275-277) is a
+      // subset of the run: a run of at most b slots passes the filter whatever it holds.
+      if (complete && n_match == 0u) return;
+      bool longer = false;   // does the run reach past b slots?
+      if (!complete && (uint64_t)f0 + cfg.b < hi) longer = ix.entries[f0 + cfg.b].fp - fp_lo <= fp_span;
+      if (!longer) {
+        verify_run_wide(w, ix, cv, sc, read_len, seed_i, strand, f0, complete ? f0 + n_match : hi, true, fp_lo, fp_span,
+                        sink, ctr);
+        return;
+      }
+    } else if (complete) {
       if (n_match == 0u) return;
       // 2a. common case: the lanes already hold the candidates -- one genome window each
       const bool cand = ((match >> lane) & 1u) != 0u;
@@ -952,6 +1157,10 @@ WALT_HD void seed_lookup(W& w, const SubIndexView& ix, const ChromView& cv, cons
 #ifndef WALT_SLOTS_AHEAD
 #define WALT_SLOTS_AHEAD 4
 #endif
+  if (WD == 32u && read_len <= WIDE_MAX_READ) {
+    verify_run_wide(w, ix, cv, sc, read_len, seed_i, strand, first, last_excl, false, 0u, 0u, sink, ctr);
+    return;
+  }
   constexpr uint32_t SLOTS_AHEAD = WALT_SLOTS_AHEAD;
   for (uint32_t base = first; base < last_excl; base += WD * SLOTS_AHEAD) {
     uint32_t e[SLOTS_AHEAD];
@@ -1129,11 +1338,15 @@ WALT_HD bool lane_lookup(const SubIndexView& ix, const ChromView& cv, const Pow3
 // ------------------------------------------------------------------------------------------
 // whole reads
 // ------------------------------------------------------------------------------------------
+// What became of a read: mapped; holds a non-ACGT byte; or PARKed -- its ordered fold reached a
+// lookup that needs the whole group (repeats, tainted buckets) and the caller asked for such reads
+// to be handed to the warp-per-read kernel instead (nothing of the read's result is valid then).
+enum MapStatus : uint32_t { MAP_OK = 0u, MAP_BAD = 1u, MAP_PARKED = 2u };
+
 // SingleEndMapping for both strand passes of one read (mapping.cpp:486-500 order: all shifts
 // on the '+' sub-index, then all shifts on the '-' sub-index, state carried across).
-// Returns false if the read holds a non-ACGT byte.
-template <class W, bool PACKED = false>
-WALT_HD bool map_read_se(W& w, const SubIndexView* ix2, const ChromView& cv, const Pow3& p3,
+template <class W, bool PACKED = false, bool PARK = false>
+WALT_HD MapStatus map_read_se(W& w, const SubIndexView* ix2, const ChromView& cv, const Pow3& p3,
                          const MapConfig& cfg, const char* seq, uint32_t read_len, bool ag,
                          uint32_t max_mismatches, ReadScratch& sc, uint32_t& cached_len,
                          BestState& out, Counters& ctr) {
@@ -1141,8 +1354,9 @@ WALT_HD bool map_read_se(W& w, const SubIndexView* ix2, const ChromView& cv, con
   BestSink<W> sink;
   sink.st.pos = 0u; sink.st.times = 0u; sink.st.mm = max_mismatches; sink.st.strand = '+';
   out = sink.st;
-  if (read_len < MIN_READ_LEN) return true;
-  if (!load_read<W, PACKED>(w, seq, read_len, ag, sc)) return false;
+  const Counters ctr_in = ctr;
+  if (read_len < MIN_READ_LEN) return MAP_OK;
+  if (!load_read<W, PACKED>(w, seq, read_len, ag, sc)) return MAP_BAD;
   if (cached_len != read_len) { build_masks(w, read_len, sc); cached_len = read_len; }
   // every lookup lane runs its own lookup and summarises it: minimum, how many candidates
   // share it, the first and the last of them (all the ordered fold needs, see BestSink::apply)
@@ -1174,6 +1388,7 @@ WALT_HD bool map_read_se(W& w, const SubIndexView* ix2, const ChromView& cv, con
     const uint32_t strand = s ? '-' : '+';
     if (sink.stop_before_shift(seed_i)) continue;
     if ((coop_mask >> j) & 1u) {
+      if (PARK) { ctr = ctr_in; w.sync(); return MAP_PARKED; }   // the kernel that takes the read over counts its work
       replay_lookup(w, ix2[s], cv, p3, cfg, sc, read_len, seed_i, strand, sink, ctr);
     } else {
       sink.apply(w.shfl(mn, (int)j), w.shfl(cnt, (int)j), w.shfl(g_first, (int)j), w.shfl(g_last, (int)j), strand);
@@ -1181,19 +1396,20 @@ WALT_HD bool map_read_se(W& w, const SubIndexView* ix2, const ChromView& cv, con
   }
   out = sink.st;
   w.sync();  // scratch is reused by the next read
-  return true;
+  return MAP_OK;
 }
 
 // PairEndMapping for both strand passes of one mate (paired.cpp:650-671) into `sink` (reset by the
 // caller; its state persists across the two passes).
-template <class W, bool PACKED, class SinkT>
-WALT_HD bool map_read_pe_into(W& w, const SubIndexView* ix2, const ChromView& cv, const Pow3& p3,
+template <class W, bool PACKED, bool PARK, class SinkT>
+WALT_HD MapStatus map_read_pe_into(W& w, const SubIndexView* ix2, const ChromView& cv, const Pow3& p3,
                               const MapConfig& cfg, const char* seq, uint32_t read_len, bool ag,
                               uint32_t max_mismatches, ReadScratch& sc, uint32_t& cached_len, SinkT& sink,
                               Counters& ctr) {
   static_assert(W::WIDTH >= LOOKUP_LANES, "a group needs one lane per lookup");
-  if (read_len < MIN_READ_LEN) return true;
-  if (!load_read<W, PACKED>(w, seq, read_len, ag, sc)) return false;
+  const Counters ctr_in = ctr;
+  if (read_len < MIN_READ_LEN) return MAP_OK;
+  if (!load_read<W, PACKED>(w, seq, read_len, ag, sc)) return MAP_BAD;
   if (cached_len != read_len) { build_masks(w, read_len, sc); cached_len = read_len; }
   // lookup lanes leave their candidates (index order) in the group's scratch; they reach the
   // sink in reference order
@@ -1226,6 +1442,7 @@ WALT_HD bool map_read_pe_into(W& w, const SubIndexView* ix2, const ChromView& cv
     const uint32_t strand = s ? '-' : '+';
     if (sink.stop_before_shift(seed_i)) continue;
     if ((coop_mask >> j) & 1u) {
+      if (PARK) { ctr = ctr_in; w.sync(); return MAP_PARKED; }
       replay_lookup(w, ix2[s], cv, p3, cfg, sc, read_len, seed_i, strand, sink, ctr);
     } else {
       const uint32_t nj = w.shfl(n_mine, (int)j);
@@ -1233,36 +1450,36 @@ WALT_HD bool map_read_pe_into(W& w, const SubIndexView* ix2, const ChromView& cv
     }
   }
   w.sync();
-  return true;
+  return MAP_OK;
 }
 
 // ... with the heap maintained in place by lane 0.  On return heap[0..size) is the libstdc++ heap array.
 template <class W, bool PACKED = false>
-WALT_HD bool map_read_pe(W& w, const SubIndexView* ix2, const ChromView& cv, const Pow3& p3,
+WALT_HD MapStatus map_read_pe(W& w, const SubIndexView* ix2, const ChromView& cv, const Pow3& p3,
                          const MapConfig& cfg, const char* seq, uint32_t read_len, bool ag,
                          uint32_t max_mismatches, uint32_t top_k, ReadScratch& sc,
                          uint32_t& cached_len, HeapEntry* heap, uint32_t& heap_size, Counters& ctr) {
   HeapSink<W> sink;
   sink.heap = heap; sink.size = 0u; sink.cap = top_k; sink.top_mm = 0u; sink.max_mm = max_mismatches;
   heap_size = 0u;
-  const bool ok = map_read_pe_into<W, PACKED>(w, ix2, cv, p3, cfg, seq, read_len, ag, max_mismatches, sc, cached_len, sink, ctr);
+  const MapStatus st = map_read_pe_into<W, PACKED, false>(w, ix2, cv, p3, cfg, seq, read_len, ag, max_mismatches, sc, cached_len, sink, ctr);
   heap_size = sink.size;
-  return ok;
+  return st;
 }
 
 // ... logging the heap-changing candidates for replay_heap_log (max_mismatches <= LOG_MAX_MM; `log`
 // holds pe_log_slots(top_k, max_mismatches) entries, `hist` max_mismatches + 1 counters).
-template <class W, bool PACKED = false>
-WALT_HD bool map_read_pe_logged(W& w, const SubIndexView* ix2, const ChromView& cv, const Pow3& p3,
+template <class W, bool PACKED = false, bool PARK = false>
+WALT_HD MapStatus map_read_pe_logged(W& w, const SubIndexView* ix2, const ChromView& cv, const Pow3& p3,
                                 const MapConfig& cfg, const char* seq, uint32_t read_len, bool ag,
                                 uint32_t max_mismatches, uint32_t top_k, ReadScratch& sc,
                                 uint32_t& cached_len, HeapEntry* log, uint32_t* hist, uint32_t& n_log, Counters& ctr) {
   LogSink<W> sink;
   sink.log = log; sink.hist = hist; sink.cap = top_k; sink.max_mm = max_mismatches;
   sink.reset(w);
-  const bool ok = map_read_pe_into<W, PACKED>(w, ix2, cv, p3, cfg, seq, read_len, ag, max_mismatches, sc, cached_len, sink, ctr);
+  const MapStatus st = map_read_pe_into<W, PACKED, PARK>(w, ix2, cv, p3, cfg, seq, read_len, ag, max_mismatches, sc, cached_len, sink, ctr);
   n_log = sink.n_log;
-  return ok;
+  return st;
 }
 
 // ------------------------------------------------------------------------------------------

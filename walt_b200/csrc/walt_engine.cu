@@ -277,9 +277,18 @@ struct SeArgs {
   uint32_t max_mismatches;
   walt_best* out;
   uint32_t* flags;        // [0] non-ACGT
-  uint32_t* queue;        // work-queue head (zeroed before launch)
+  uint32_t* queue;        // [0] work-queue head, [1] number of parked reads, [2] queue head of the kernel that takes them over (zeroed before launch)
+  uint32_t* parked;       // read numbers of the parked reads (MODE 1 writes, MODE 2 reads)
   unsigned long long* counters;  // optional
 };
+
+// Kernel modes.  MAP_ALL: every read is finished where it is.  MAP_PARK: a read whose ordered fold
+// reaches a lookup that needs the whole group (a long fingerprint run = repeats, or a tainted
+// bucket) is dropped and its number appended to the parked list, so that the sub-warp groups never
+// leave the converged fast path.  MAP_TAKE (a whole warp per read): maps the parked reads, repeats
+// streamed through the warp-wide quad verification (verify_run_wide, walt_core.cuh).
+enum : int { MAP_ALL = 0, MAP_PARK = 1, MAP_TAKE = 2 };
+constexpr uint32_t TAKE_BLOCKS_PER_SM = 2;   // the take-over kernels get 128 registers
 
 // The groups of a warp take consecutive reads with one queue ticket and walk the read loop
 // together, so the warp stays converged through the common phases (pack, keys, table and entry
@@ -347,9 +356,23 @@ __device__ __forceinline__ void flush_counters(const HwGroup<WD>& w, const Count
   }
 }
 
-template <uint32_t WD, bool PACKED>
-__global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS_PER_SM)
+// append the reads of this warp's groups that were parked in this round (one atomic per warp)
+template <uint32_t WD>
+__device__ __forceinline__ void park_reads(const HwGroup<WD>& w, bool parked, uint32_t r, uint32_t* queue, uint32_t* list) {
+  const uint32_t l = threadIdx.x & 31u;
+  const uint32_t pm = __ballot_sync(0xFFFFFFFFu, parked && w.lane() == 0u);
+  if (!pm) return;
+  const int leader = __ffs((int)pm) - 1;
+  uint32_t at = 0;
+  if ((int)l == leader) at = atomicAdd(queue + 1, (uint32_t)__popc(pm));
+  at = __shfl_sync(0xFFFFFFFFu, at, leader);
+  if (parked && w.lane() == 0u) list[at + (uint32_t)__popc(pm & ((1u << l) - 1u))] = r;
+}
+
+template <uint32_t WD, bool PACKED, int MODE>
+__global__ void __launch_bounds__(BLOCK_THREADS, MODE == MAP_TAKE ? TAKE_BLOCKS_PER_SM : MIN_BLOCKS_PER_SM)
 se_map_kernel(const __grid_constant__ SeArgs a) {
+  static_assert(MODE != MAP_TAKE || WD == 32u, "parked reads are taken over by whole warps");
   extern __shared__ uint64_t smem[];
   __shared__ BlockTally tally;
   tally_init(tally);
@@ -360,25 +383,31 @@ se_map_kernel(const __grid_constant__ SeArgs a) {
   uint32_t cached_len = 0;
   Counters ctr{0u, 0u, 0u};
   bool bad = false;
+  const uint32_t n = MODE == MAP_TAKE ? *reinterpret_cast<volatile const uint32_t*>(a.queue + 1) : a.n;
+  uint32_t* const queue = MODE == MAP_TAKE ? a.queue + 2 : a.queue;
   for (uint32_t round = TICKET_ROUNDS, base = 0;; ++round) {
-    if (round == TICKET_ROUNDS) { base = next_ticket<WD>(a.queue); round = 0; }
+    if (round == TICKET_ROUNDS) { base = next_ticket<WD>(queue); round = 0; }
     const uint32_t first = base + round * (32u / WD);
-    if (first >= a.n) break;                            // warp-uniform: past the batch
-    const uint32_t r = first + (threadIdx.x & 31u) / WD;
-    if (r < a.n) {
+    if (first >= n) break;                              // warp-uniform: past the batch
+    uint32_t r = first + (threadIdx.x & 31u) / WD;
+    bool parked = false;
+    if (r < n) {
+      if (MODE == MAP_TAKE) r = a.parked[r];
       uint32_t len;
       const char* seq = read_at<PACKED>(a, r, len);
       BestState st;
-      bool ok = map_read_se<HwGroup<WD>, PACKED>(w, a.ix, a.cv, a.p3, a.cfg, seq, len, a.ag != 0u,
-                            a.max_mismatches, sc, cached_len, st, ctr);
-      bad |= !ok;
-      if (lane == 0) {
+      const MapStatus ms = map_read_se<HwGroup<WD>, PACKED, MODE == MAP_PARK>(w, a.ix, a.cv, a.p3, a.cfg, seq, len, a.ag != 0u,
+                                                                            a.max_mismatches, sc, cached_len, st, ctr);
+      bad |= ms == MAP_BAD;
+      parked = ms == MAP_PARKED;
+      if (lane == 0 && !parked) {
         uint4 o;
         o.x = st.pos; o.y = st.times; o.z = st.mm; o.w = st.strand & 0xFFu;
         *reinterpret_cast<uint4*>(a.out + r) = o;
       }
     }
     __syncwarp();
+    if (MODE == MAP_PARK) park_reads(w, parked, r, a.queue, a.parked);
   }
   flush_counters(w, ctr, bad, tally, a.flags, a.counters);
 }
@@ -405,15 +434,17 @@ struct PeArgs {
   uint32_t log_slots;
   uint32_t zero_fill;     // the ranked lists travel to the host: define (zero) their unused slots
   uint32_t* flags;
-  uint32_t* queue;
+  uint32_t* queue;        // see SeArgs
+  uint32_t* parked;
   unsigned long long* counters;
 };
 
 // Two-phase form, first phase: PairEndMapping (paired.cpp:106-201) for one mate batch with the
 // heap-changing candidates logged (LogSink, walt_core.cuh); pe_heap_kernel finishes the job.
-template <uint32_t WD, bool PACKED>
-__global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS_PER_SM)
+template <uint32_t WD, bool PACKED, int MODE>
+__global__ void __launch_bounds__(BLOCK_THREADS, MODE == MAP_TAKE ? TAKE_BLOCKS_PER_SM : MIN_BLOCKS_PER_SM)
 pe_log_kernel(const __grid_constant__ PeArgs a) {
+  static_assert(MODE != MAP_TAKE || WD == 32u, "parked reads are taken over by whole warps");
   extern __shared__ uint64_t smem[];
   __shared__ BlockTally tally;
   tally_init(tally);
@@ -427,21 +458,28 @@ pe_log_kernel(const __grid_constant__ PeArgs a) {
   uint32_t cached_len = 0;
   Counters ctr{0u, 0u, 0u};
   bool bad = false;
+  const uint32_t n = MODE == MAP_TAKE ? *reinterpret_cast<volatile const uint32_t*>(a.queue + 1) : a.n;
+  uint32_t* const queue = MODE == MAP_TAKE ? a.queue + 2 : a.queue;
   for (uint32_t round = TICKET_ROUNDS, base = 0;; ++round) {
-    if (round == TICKET_ROUNDS) { base = next_ticket<WD>(a.queue); round = 0; }
+    if (round == TICKET_ROUNDS) { base = next_ticket<WD>(queue); round = 0; }
     const uint32_t first = base + round * (32u / WD);
-    if (first >= a.n) break;
-    const uint32_t r = first + (threadIdx.x & 31u) / WD;
-    if (r < a.n) {
+    if (first >= n) break;
+    uint32_t r = first + (threadIdx.x & 31u) / WD;
+    bool parked = false;
+    if (r < n) {
+      if (MODE == MAP_TAKE) r = a.parked[r];
       uint32_t len;
       const char* seq = read_at<PACKED>(a, r, len);
       uint32_t n_log = 0;
-      bool ok = map_read_pe_logged<HwGroup<WD>, PACKED>(w, a.ix, a.cv, a.p3, a.cfg, seq, len, a.ag != 0u,
-                            a.max_mismatches, a.top_k, sc, cached_len, a.log + (size_t)r * a.log_slots, hist, n_log, ctr);
-      bad |= !ok;
-      if (lane == 0) a.n_log[r] = n_log;
+      const MapStatus ms = map_read_pe_logged<HwGroup<WD>, PACKED, MODE == MAP_PARK>(
+          w, a.ix, a.cv, a.p3, a.cfg, seq, len, a.ag != 0u, a.max_mismatches, a.top_k, sc, cached_len,
+          a.log + (size_t)r * a.log_slots, hist, n_log, ctr);
+      bad |= ms == MAP_BAD;
+      parked = ms == MAP_PARKED;
+      if (lane == 0 && !parked) a.n_log[r] = n_log;
     }
     __syncwarp();
+    if (MODE == MAP_PARK) park_reads(w, parked, r, a.queue, a.parked);
   }
   flush_counters(w, ctr, bad, tally, a.flags, a.counters);
 }
@@ -513,9 +551,9 @@ pe_map_kernel(const __grid_constant__ PeArgs a) {
       uint32_t len;
       const char* seq = read_at<PACKED>(a, r, len);
       uint32_t hsize = 0;
-      bool ok = map_read_pe<HwGroup<WD>, PACKED>(w, a.ix, a.cv, a.p3, a.cfg, seq, len, a.ag != 0u,
-                            a.max_mismatches, a.top_k, sc, cached_len, heap, hsize, ctr);
-      bad |= !ok;
+      const MapStatus ms = map_read_pe<HwGroup<WD>, PACKED>(w, a.ix, a.cv, a.p3, a.cfg, seq, len, a.ag != 0u,
+                                                          a.max_mismatches, a.top_k, sc, cached_len, heap, hsize, ctr);
+      bad |= ms == MAP_BAD;
       if (lane == 0) {
         walt_cand* dst = a.ranked + (size_t)r * a.top_k;
         uint32_t c = 0, sz = hsize;
@@ -643,6 +681,13 @@ struct ReadSrc {
   bool packed;
 };
 
+// queue block i of the engine: four words {work-queue head, parked reads, take-over queue head, spare}
+// 0: device-resident SE; 1..N_SLOTS: SE host chunks; then two (one per mate) for device-resident PE
+// and two per slot for PE host chunks
+static uint32_t* queue_block(walt_engine* e, uint32_t i) { return e->d_flags + 16u + 4u * i; }
+constexpr uint32_t QB_SE_DEVICE = 0, QB_SE_SLOT = 1, QB_PE_DEVICE = 1 + N_SLOTS, QB_PE_SLOT = 3 + N_SLOTS;
+constexpr uint32_t N_FLAG_WORDS = 16u + 4u * (QB_PE_SLOT + 2u * N_SLOTS);
+
 template <class Args>
 static void fill_common(walt_engine* e, Args& a, const ReadSrc& src, uint32_t n, int ag, uint32_t m, uint32_t b,
                         uint32_t* d_queue) {
@@ -653,50 +698,93 @@ static void fill_common(walt_engine* e, Args& a, const ReadSrc& src, uint32_t n,
   a.seqs = src.d_seqs; a.offs = src.d_offs; a.seq_base = src.seq_base; a.n = n; a.uniform_len = src.uniform_len;
   a.read_base = src.read_base;
   a.nw_max = std::max<uint32_t>(1u, (src.max_len + 31u) / 32u);
-  a.ag = ag ? 1u : 0u; a.max_mismatches = m; a.flags = e->d_flags; a.queue = d_queue;
+  a.ag = ag ? 1u : 0u; a.max_mismatches = m; a.flags = e->d_flags; a.queue = d_queue; a.parked = nullptr;
   a.counters = e->d_counters;
 }
 
+// grid of a kernel that takes over parked reads: persistent, a whole warp per read
+template <class K>
+static int take_grid(walt_engine* e, K kernel, size_t smem, uint32_t* grid) {
+  int per_sm = 0;
+  WALT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  WALT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)BLOCK_THREADS, smem));
+  if (per_sm < 1) return fail(WALT_ECUDA, "take-over kernel does not fit on an SM");
+  *grid = (uint32_t)per_sm * (uint32_t)e->sm_count;
+  return WALT_OK;
+}
+
+// d_parked != NULL (room for n read numbers): reads that need their whole group are parked by the
+// first kernel and mapped by a second one, a warp per read (see MAP_PARK / MAP_TAKE)
 static int launch_se(walt_engine* e, const ReadSrc& src, uint32_t n, int ag, uint32_t m, uint32_t b, walt_best* d_out,
-                     uint32_t* d_queue, cudaStream_t st, uint32_t share = 1) {
+                     uint32_t* d_queue, uint32_t* d_parked, cudaStream_t st, uint32_t share = 1) {
   if (src.max_len > MAX_READ_LEN) return fail(WALT_EINVAL, "read longer than 1024 bases");
   SeArgs a;
   fill_common(e, a, src, n, ag, m, b, d_queue);
   a.out = d_out;
+  const bool park = e->defer && d_parked != nullptr;
+  a.parked = park ? d_parked : nullptr;
   const uint32_t wd = e->group_width;
   const size_t smem = se_smem_bytes(a.nw_max, wd);
   uint32_t grid = 0;
-  auto kernel = src.packed ? (wd == 8u ? se_map_kernel<8, true> : wd == 16u ? se_map_kernel<16, true> : se_map_kernel<32, true>)
-                           : (wd == 8u ? se_map_kernel<8, false> : wd == 16u ? se_map_kernel<16, false> : se_map_kernel<32, false>);
+  void (*kernel)(SeArgs);
+  if (park)
+    kernel = src.packed ? (wd == 8u ? se_map_kernel<8, true, MAP_PARK> : wd == 16u ? se_map_kernel<16, true, MAP_PARK> : se_map_kernel<32, true, MAP_PARK>)
+                        : (wd == 8u ? se_map_kernel<8, false, MAP_PARK> : wd == 16u ? se_map_kernel<16, false, MAP_PARK> : se_map_kernel<32, false, MAP_PARK>);
+  else
+    kernel = src.packed ? (wd == 8u ? se_map_kernel<8, true, MAP_ALL> : wd == 16u ? se_map_kernel<16, true, MAP_ALL> : se_map_kernel<32, true, MAP_ALL>)
+                        : (wd == 8u ? se_map_kernel<8, false, MAP_ALL> : wd == 16u ? se_map_kernel<16, false, MAP_ALL> : se_map_kernel<32, false, MAP_ALL>);
   int rc = grid_for(e, kernel, smem, n, wd, &grid, share);
   if (rc) return rc;
-  WALT_CUDA_TRY(cudaMemsetAsync(d_queue, 0, 4, st));
+  WALT_CUDA_TRY(cudaMemsetAsync(d_queue, 0, 16, st));
   kernel<<<grid, BLOCK_THREADS, smem, st>>>(a);
   WALT_CUDA_TRY(cudaGetLastError());
   e->stats.n_kernel_launches++;
+  if (park) {
+    void (*take)(SeArgs) = src.packed ? se_map_kernel<32, true, MAP_TAKE> : se_map_kernel<32, false, MAP_TAKE>;
+    const size_t smem2 = se_smem_bytes(a.nw_max, 32u);
+    if ((rc = take_grid(e, take, smem2, &grid))) return rc;
+    take<<<grid, BLOCK_THREADS, smem2, st>>>(a);
+    WALT_CUDA_TRY(cudaGetLastError());
+    e->stats.n_kernel_launches++;
+  }
   return WALT_OK;
 }
 
 // first phase of the two-phase form for one mate
 static int launch_pe_log(walt_engine* e, const ReadSrc& src, uint32_t n, int ag, uint32_t m, uint32_t b, uint32_t top_k,
-                         HeapEntry* d_log, uint32_t* d_nlog, uint32_t* d_queue, cudaStream_t st) {
+                         HeapEntry* d_log, uint32_t* d_nlog, uint32_t* d_queue, uint32_t* d_parked, cudaStream_t st) {
   // (zero_fill belongs to the second phase here)
   if (src.max_len > MAX_READ_LEN) return fail(WALT_EINVAL, "read longer than 1024 bases");
   PeArgs a;
   fill_common(e, a, src, n, ag, m, b, d_queue);
   a.top_k = top_k; a.ranked = nullptr; a.n_ranked = nullptr;
   a.log = d_log; a.n_log = d_nlog; a.log_slots = pe_log_slots(top_k, m); a.zero_fill = 0u;
+  const bool park = e->defer && d_parked != nullptr;
+  a.parked = park ? d_parked : nullptr;
   const uint32_t wd = e->group_width;
   const size_t smem = pe_log_smem_bytes(a.nw_max, wd);
   uint32_t grid = 0;
-  auto kernel = src.packed ? (wd == 8u ? pe_log_kernel<8, true> : wd == 16u ? pe_log_kernel<16, true> : pe_log_kernel<32, true>)
-                           : (wd == 8u ? pe_log_kernel<8, false> : wd == 16u ? pe_log_kernel<16, false> : pe_log_kernel<32, false>);
+  void (*kernel)(PeArgs);
+  if (park)
+    kernel = src.packed ? (wd == 8u ? pe_log_kernel<8, true, MAP_PARK> : wd == 16u ? pe_log_kernel<16, true, MAP_PARK> : pe_log_kernel<32, true, MAP_PARK>)
+                        : (wd == 8u ? pe_log_kernel<8, false, MAP_PARK> : wd == 16u ? pe_log_kernel<16, false, MAP_PARK> : pe_log_kernel<32, false, MAP_PARK>);
+  else
+    kernel = src.packed ? (wd == 8u ? pe_log_kernel<8, true, MAP_ALL> : wd == 16u ? pe_log_kernel<16, true, MAP_ALL> : pe_log_kernel<32, true, MAP_ALL>)
+                        : (wd == 8u ? pe_log_kernel<8, false, MAP_ALL> : wd == 16u ? pe_log_kernel<16, false, MAP_ALL> : pe_log_kernel<32, false, MAP_ALL>);
   int rc = grid_for(e, kernel, smem, n, wd, &grid);
   if (rc) return rc;
-  WALT_CUDA_TRY(cudaMemsetAsync(d_queue, 0, 4, st));
+  WALT_CUDA_TRY(cudaMemsetAsync(d_queue, 0, 16, st));
   kernel<<<grid, BLOCK_THREADS, smem, st>>>(a);
   WALT_CUDA_TRY(cudaGetLastError());
   e->stats.n_kernel_launches++;
+  if (park) {
+    void (*take)(PeArgs) = src.packed ? pe_log_kernel<32, true, MAP_TAKE> : pe_log_kernel<32, false, MAP_TAKE>;
+    const size_t smem2 = pe_log_smem_bytes(a.nw_max, 32u);
+    if ((rc = take_grid(e, take, smem2, &grid))) return rc;
+    take<<<grid, BLOCK_THREADS, smem2, st>>>(a);
+    WALT_CUDA_TRY(cudaGetLastError());
+    e->stats.n_kernel_launches++;
+  }
   return WALT_OK;
 }
 
@@ -818,12 +906,13 @@ int walt_engine_create(walt_engine** out, int device) {
   if (const char* v = getenv("WALT_MIN_BLOCKS")) e->min_blocks = atoi(v);
   if (const char* v = getenv("WALT_PE_SIDE")) e->pe_side = atoi(v);
   if (const char* v = getenv("WALT_PE_LOGGED")) e->pe_logged = atoi(v);
+  if (const char* v = getenv("WALT_DEFER")) e->defer = atoi(v);
   if (const char* v = getenv("WALT_CHUNK_SHARE")) e->chunk_share = (uint32_t)std::max(1, atoi(v));
   if (const char* v = getenv("WALT_L2_FETCH")) WALT_CUDA_TRY(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(v)));
   uint32_t p = 1;
   for (uint32_t i = 0; i <= MAX_DEPTH; ++i) { e->pow3.v[i] = p; p *= 3u; }
-  WALT_CUDA_TRY(cudaMalloc(&e->d_flags, 32 * 4));
-  WALT_CUDA_TRY(cudaMemset(e->d_flags, 0, 32 * 4));
+  WALT_CUDA_TRY(cudaMalloc(&e->d_flags, N_FLAG_WORDS * 4));
+  WALT_CUDA_TRY(cudaMemset(e->d_flags, 0, N_FLAG_WORDS * 4));
   WALT_CUDA_TRY(cudaMalloc(&e->d_counters, 3 * 8));
   WALT_CUDA_TRY(cudaMemset(e->d_counters, 0, 3 * 8));
   for (auto& s : e->slot) {
@@ -844,14 +933,14 @@ void walt_engine_destroy(walt_engine* e) {
   for (auto& s : e->sub) s.release();
   for (auto& s : e->slot) {
     cudaFree(s.d_seqs); cudaFree(s.d_offs); cudaFree(s.d_out); cudaFree(s.d_seqs2); cudaFree(s.d_offs2);
-    cudaFree(s.d_pe);
+    cudaFree(s.d_pe); cudaFree(s.d_park[0]); cudaFree(s.d_park[1]);
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.done) cudaEventDestroy(s.done);
   }
   if (e->side_stream) cudaStreamDestroy(e->side_stream);
   if (e->fork) cudaEventDestroy(e->fork);
   if (e->join) cudaEventDestroy(e->join);
-  cudaFree(e->d_starts); cudaFree(e->d_flags); cudaFree(e->d_counters);
+  cudaFree(e->d_starts); cudaFree(e->d_flags); cudaFree(e->d_counters); cudaFree(e->dev_park[0]); cudaFree(e->dev_park[1]);
   delete e;
 }
 
@@ -1156,6 +1245,12 @@ int walt_engine_set_group_width(walt_engine* e, uint32_t lanes) {
   return WALT_OK;
 }
 
+int walt_engine_set_defer(walt_engine* e, int on) {
+  if (!e || (on != 0 && on != 1)) return fail(WALT_EINVAL, "defer must be 0 or 1");
+  e->defer = on;
+  return WALT_OK;
+}
+
 int walt_engine_set_chunk_reads(walt_engine* e, uint32_t n) {
   if (!e) return fail(WALT_EINVAL, "bad argument");
   e->chunk_reads = n;   // 0 = automatic
@@ -1179,7 +1274,9 @@ int walt_engine_map_se_device(walt_engine* e, const void* d_seqs, const void* d_
   if (n == 0) return WALT_OK;
   e->stats.n_kernel_launches = 0;
   const ReadSrc src{(const char*)d_seqs, (const uint64_t*)d_offs, 0, 0, 0, max_read_len, false};
-  return launch_se(e, src, n, ag_wildcard, max_mismatches, b, (walt_best*)d_out, e->d_flags + 1, (cudaStream_t)cuda_stream);
+  if (e->defer && (rc = reserve(&e->dev_park[0], &e->dev_park_cap[0], (size_t)n))) return rc;
+  return launch_se(e, src, n, ag_wildcard, max_mismatches, b, (walt_best*)d_out, queue_block(e, QB_SE_DEVICE),
+                   e->defer ? e->dev_park[0] : nullptr, (cudaStream_t)cuda_stream);
 }
 
 // Bytes [*b0, *b1) of a batch buffer that hold reads [r0, r0 + cn): ASCII, or the 2-bit packed
@@ -1224,8 +1321,9 @@ static int map_se_host(walt_engine* e, const char* seqs, const uint64_t* offs, u
       WALT_CUDA_TRY(cudaMemcpyAsync(s.d_offs, offs + r0, ((size_t)cn + 1u) * 8u, cudaMemcpyHostToDevice, s.stream));
     }
     const ReadSrc src{s.d_seqs, s.d_offs, offs[r0], sc.uniform_len, 0, sc.max_len, packed};
-    if ((rc = launch_se(e, src, cn, ag_wildcard, max_mismatches, b, (walt_best*)s.d_out, e->d_flags + 4 + (k % N_SLOTS),
-                        s.stream, e->chunk_share)))
+    if (e->defer && (rc = reserve(&s.d_park[0], &s.park_cap[0], (size_t)cn))) return rc;
+    if ((rc = launch_se(e, src, cn, ag_wildcard, max_mismatches, b, (walt_best*)s.d_out, queue_block(e, QB_SE_SLOT + k % N_SLOTS),
+                        e->defer ? s.d_park[0] : nullptr, s.stream, e->chunk_share)))
       return rc;
     WALT_CUDA_TRY(cudaMemcpyAsync(out + r0, s.d_out, (size_t)cn * sizeof(walt_best), cudaMemcpyDeviceToHost, s.stream));
     WALT_CUDA_TRY(cudaEventRecord(s.done, s.stream));
@@ -1293,7 +1391,7 @@ static PeScratch carve_pe(void* base, uint32_t cn, uint32_t top_k, uint32_t m, b
 // both mate kernels + the pairing kernel for one chunk resident on the device
 static int launch_pe_chunk(walt_engine* e, const ReadSrc& m1, const ReadSrc& m2, uint32_t cn, uint32_t m, uint32_t b,
                            uint32_t top_k, int frag_range, int swap, const PeScratch& ps, bool want_pairs,
-                           walt_pe_result* d_compact, uint32_t* q, cudaStream_t st) {
+                           walt_pe_result* d_compact, uint32_t* q, uint32_t* const* d_parked, cudaStream_t st) {
   int rc;
   // mate 1: C->T against _CT00/_CT01; mate 2: G->A against _GA10/_GA11 (paired.cpp:642-672).  The
   // two mate kernels are independent: the second runs on a side stream so that its blocks fill
@@ -1305,11 +1403,11 @@ static int launch_pe_chunk(walt_engine* e, const ReadSrc& m1, const ReadSrc& m2,
   }
   const bool two_phase = ps.log1 != nullptr;
   if (two_phase) {
-    if ((rc = launch_pe_log(e, m1, cn, 0, m, b, top_k, ps.log1, ps.nlog1, q, st))) return rc;
-    if ((rc = launch_pe_log(e, m2, cn, 1, m, b, top_k, ps.log2, ps.nlog2, q + 1, st2))) return rc;
+    if ((rc = launch_pe_log(e, m1, cn, 0, m, b, top_k, ps.log1, ps.nlog1, q, d_parked ? d_parked[0] : nullptr, st))) return rc;
+    if ((rc = launch_pe_log(e, m2, cn, 1, m, b, top_k, ps.log2, ps.nlog2, q + 4, d_parked ? d_parked[1] : nullptr, st2))) return rc;
   } else {
     if ((rc = launch_pe_mate(e, m1, cn, 0, m, b, top_k, ps.r1, ps.n1, q, st, want_pairs))) return rc;
-    if ((rc = launch_pe_mate(e, m2, cn, 1, m, b, top_k, ps.r2, ps.n2, q + 1, st2, want_pairs))) return rc;
+    if ((rc = launch_pe_mate(e, m2, cn, 1, m, b, top_k, ps.r2, ps.n2, q + 4, st2, want_pairs))) return rc;
   }
   if (e->pe_side) {
     WALT_CUDA_TRY(cudaEventRecord(e->join, st2));
@@ -1387,11 +1485,14 @@ static int map_pe_host(walt_engine* e, const char* seqs1, const uint64_t* offs1,
       if ((rc = reserve(&s.d_offs2, &s.offs2_cap, (size_t)cn + 1u))) return rc;
       WALT_CUDA_TRY(cudaMemcpyAsync(s.d_offs2, offs2 + r0, ((size_t)cn + 1u) * 8u, cudaMemcpyHostToDevice, s.stream));
     }
-    uint32_t* q = e->d_flags + 4 + N_SLOTS + 2u * (k % N_SLOTS);
+    uint32_t* q = queue_block(e, QB_PE_SLOT + 2u * (k % N_SLOTS));
     const ReadSrc m1{s.d_seqs, s.d_offs, offs1[r0], s1.uniform_len, 0, s1.max_len, packed};
     const ReadSrc m2{s.d_seqs2, s.d_offs2, offs2[r0], s2.uniform_len, 0, s2.max_len, packed};
+    if (e->defer && two_phase)
+      for (int i = 0; i < 2; ++i)
+        if ((rc = reserve(&s.d_park[i], &s.park_cap[i], (size_t)cn))) return rc;
     if ((rc = launch_pe_chunk(e, m1, m2, cn, m, b, top_k, frag_range, swap, ps, pairs != nullptr,
-                              compact ? ps.compact : nullptr, q, s.stream)))
+                              compact ? ps.compact : nullptr, q, e->defer && two_phase ? s.d_park : nullptr, s.stream)))
       return rc;
     if (ranked1) {
       const size_t rk = (size_t)cn * top_k * sizeof(walt_cand);
@@ -1495,13 +1596,17 @@ int walt_engine_map_pe_device(walt_engine* e, const void* d_seqs1, const void* d
     fprintf(stderr, "[walt debug] map_pe_device: free %.2f GB, budget %.2f GB, chunk %u pairs, two_phase %d\n", free_b / 1e9,
             budget / 1e9, chunk, (int)two_phase);
   if ((rc = reserve_bytes(&s.d_pe, &s.pe_cap, pe_scratch_bytes(chunk, top_k, max_mismatches, two_phase)))) return rc;
+  if (e->defer && two_phase)
+    for (int i = 0; i < 2; ++i)
+      if ((rc = reserve(&e->dev_park[i], &e->dev_park_cap[i], (size_t)chunk))) return rc;
   for (uint32_t r0 = 0; r0 < n; r0 += chunk) {
     const uint32_t cn = std::min<uint32_t>(chunk, n - r0);
     const PeScratch ps = carve_pe(s.d_pe, cn, top_k, max_mismatches, two_phase);
     // absolute offsets: read r of the chunk is global read r0 + r, addressed from the buffer start
     const ReadSrc m1{s1, o1 + r0, 0, 0, r0, max_read_len, false}, m2{s2, o2 + r0, 0, 0, r0, max_read_len, false};
     if ((rc = launch_pe_chunk(e, m1, m2, cn, max_mismatches, b, top_k, frag_range, pbat, ps, false,
-                              (walt_pe_result*)d_out + r0, e->d_flags + 4 + N_SLOTS, st)))
+                              (walt_pe_result*)d_out + r0, queue_block(e, QB_PE_DEVICE), e->defer && two_phase ? e->dev_park : nullptr,
+                              st)))
       return rc;
   }
   return WALT_OK;

@@ -53,6 +53,7 @@ struct BatchSlot {
   char* d_seqs2 = nullptr;     size_t seqs2_cap = 0;
   uint64_t* d_offs2 = nullptr; size_t offs2_cap = 0;
   void* d_pe = nullptr;        size_t pe_cap = 0;     // bytes
+  uint32_t* d_park[2] = {nullptr, nullptr};  size_t park_cap[2] = {0, 0};   // parked-read lists (one per mate)
 };
 
 }  // namespace waltb200
@@ -81,8 +82,11 @@ struct walt_engine {
   uint32_t chunk_share = 1;                  // chunk kernels of a host batch that share the SMs (see grid_for)
   int pe_logged = 1;                         // 1: two-phase paired-end (candidate log + per-thread heap replay)
   int pe_side = 1;                           // 0: both mate kernels on the caller's stream
-  uint32_t* d_flags = nullptr;               // [0] non-ACGT flag, [1] work-queue head, [2..3] spare,
-                                             // [4..4+N_SLOTS) SE chunk queues, then 2 per slot for PE
+  int defer = 1;                             // 1: reads that need their whole group (repeats) are parked by the mapping
+                                             // kernels and finished by a warp-per-read kernel
+  uint32_t* dev_park[2] = {nullptr, nullptr};  size_t dev_park_cap[2] = {0, 0};   // parked lists of the device-resident calls
+  uint32_t* d_flags = nullptr;               // [0] non-ACGT flag, [2..3] index-build scratch, from [16] the queue
+                                             // blocks of the launches in flight (queue_block, walt_engine.cu)
   unsigned long long* d_counters = nullptr;  // lookups, candidates, literal
   walt_stats stats{};
 };

@@ -213,6 +213,9 @@ class Engine:
     def set_group_width(self, lanes):
         self._check(self.L.walt_engine_set_group_width(self.h, C.c_uint32(lanes)))
 
+    def set_defer(self, on):
+        self._check(self.L.walt_engine_set_defer(self.h, C.c_int(int(on))))
+
     def set_chunk_reads(self, n):
         self._check(self.L.walt_engine_set_chunk_reads(self.h, C.c_uint32(n)))
 
