@@ -693,11 +693,14 @@ def run_ours(args):
             for h in hidx.values():
                 L.waltref_index_free(h)
 
+    e.device_stats()
+    device_step()
+    dstats = e.device_stats()    # work counters of one device-resident step
     if args.no_e2e:   # kernel experiments only: not a bench line
         sampler.stop(windows)
         if rank == 0:
             emit(json.dumps({"experiment": True, "workload": wl.kind, "kernel_ms": float(np.mean(step_ms)),
-                              "per_s": n * 1e3 / float(np.mean(step_ms)),
+                              "per_s": n * 1e3 / float(np.mean(step_ms)), "stats": dstats,
                               "env": {k: v for k, v in os.environ.items() if k.startswith("WALT_")}}))
         return 0
     # ---- end-to-end timing through the C ABI with pinned host buffers (`e2e`) ----

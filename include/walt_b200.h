@@ -81,6 +81,7 @@ typedef struct {
   uint64_t n_candidates;   /* candidate windows compared against the genome              */
   uint64_t n_literal;      /* lookups that took the literal IndexRegion emulation        */
   uint64_t n_kernel_launches;
+  uint64_t n_parked;       /* reads handed to the warp-per-read kernels (walt_engine_set_defer)  */
 } walt_stats;
 
 const char* walt_last_error(void);
@@ -169,6 +170,9 @@ int walt_engine_map_pe_device(walt_engine* e, const void* d_seqs1, const void* d
                               void* cuda_stream);
 
 int walt_engine_last_stats(const walt_engine* e, walt_stats* out);
+/* After walt_engine_map_*_device calls: waits for the device, then returns (and clears) the work
+ * counters accumulated since the last call of this function. */
+int walt_engine_device_stats(walt_engine* e, walt_stats* out);
 
 /* Test hook: 0 = table-driven search (default), 1 = literal IndexRegion emulation for every
  * lookup (the in-repo device oracle; same results, slower). */

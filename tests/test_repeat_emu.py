@@ -67,3 +67,33 @@ def test_pe_repeats_logged(world, width, m, k, b):
             assert np.array_equal(ranked[f], want[f]), (m, k, b, f)
         if b == 5000 and k >= 10:
             assert (sizes == k).mean() > 0.1                      # heaps do fill up: the full-heap rule is exercised
+
+
+@pytest.mark.parametrize("m,k,L", [(8, 50, 1000), (6, 10, 400), (8, 50, 160), (3, 2, 1000), (8, 100, 1000)])
+def test_pairing_by_warp_equals_reference_loop(world, m, k, L):
+    """pair_candidates_wide (a warp per pair: three reductions over the valid pairs) against the oracle's
+    restatement of the MergePairedEndResults loop (paired.cpp:472-513) and the thread-per-pair form,
+    on ranked lists full of repeats (ties, duplicates, sums equal to -m)."""
+    import ctypes as C
+    chroms, hdr, subs, e = world
+    m1, m2 = synth.simulate_pe_reads(chroms, 150, 150, seed=77)
+    got = {}
+    for mate, reads, ag, pair in ((1, _acgt(m1), False, ("_CT00", "_CT01")), (2, _acgt(m2), True, ("_GA10", "_GA11"))):
+        ranked, sizes = refio.oracle_pe_mate(hdr, tuple(subs[s] for s in pair), reads, ag, m=m, top_k=k)
+        got[mate] = (ranked, sizes, refio.pack_reads(reads)[1])
+    a = e.pair(got[1][0], got[1][1], got[1][2], got[2][0], got[2][1], got[2][2], k, m, L)
+    b = e.pair_wide(got[1][0], got[1][1], got[1][2], got[2][0], got[2][1], got[2][2], k, m, L)
+    assert np.array_equal(a, b), np.nonzero(a != b)[0][:10]
+    if k >= 50 and L == 1000:
+        assert (a["best_times"] >= 2).sum() > 3 and (a["best_times"] == 1).sum() > 3
+    Lo = refio.oracle_lib()
+    starts = np.ascontiguousarray(hdr.start_index, np.uint32)
+    lengths = np.ascontiguousarray(hdr.lengths, np.uint32)
+    ch = refio.WoChroms(len(lengths), starts.ctypes.data, lengths.ctypes.data)
+    for j in range(len(b)):
+        bi, bj = C.c_int32(-1), C.c_int32(-1)
+        r1 = np.ascontiguousarray(got[1][0][j]); r2 = np.ascontiguousarray(got[2][0][j])
+        t = Lo.wo_pe_pair(C.byref(ch), r1.ctypes.data_as(C.c_void_p), C.c_uint32(int(got[1][1][j])), C.c_uint32(150),
+                          r2.ctypes.data_as(C.c_void_p), C.c_uint32(int(got[2][1][j])), C.c_uint32(150), C.c_uint32(m),
+                          C.c_int(L), C.byref(bi), C.byref(bj))
+        assert (t, bi.value, bj.value) == (b[j]["best_times"], b[j]["best_i"], b[j]["best_j"]), j

@@ -350,50 +350,25 @@ WALT_HD uint32_t digits4(uint32_t code4, bool ag) {
 // Pack + convert one read into sc.R and its base-3 digits into sc.D (group-cooperative).  The
 // read arrives as ASCII (PACKED = false; returns false, uniformly, if a byte is not A/C/G/T) or
 // already 2 bits per base, unconverted (PACKED = true: ceil(read_len / 4) bytes, first base in the
-// top bits of each byte).  A group of W::WIDTH lanes owns the read: with 8 lanes every lane turns
-// 4 consecutive characters into one byte of the packed word (no cross-lane traffic); other widths
-// assemble the word from ballots.
+// top bits of each byte).  A group of W::WIDTH lanes owns the read: every lane turns 4 consecutive
+// characters into one byte of the packed words (no cross-lane traffic).
 template <class W, bool PACKED>
 WALT_HD bool load_read(W& w, const char* __restrict__ seq, uint32_t read_len, bool ag, ReadScratch& sc) {
   const uint32_t lane = w.lane();
   const uint32_t nw = (read_len + 31u) >> 5;
   bool bad = false;
-  if (W::WIDTH == 8u) {
+  {
+    // every lane turns 4 consecutive characters into one byte of the packed words (no cross-lane traffic)
     uint8_t* rb = reinterpret_cast<uint8_t*>(sc.R);
     uint32_t* dw = reinterpret_cast<uint32_t*>(sc.D);
-    for (uint32_t k = 0; k < nw; ++k) {
-      const uint32_t p = 32u * k + 4u * lane;
+    for (uint32_t p = 4u * lane; p < 32u * nw; p += 4u * W::WIDTH) {
       const uint32_t nv = p < read_len ? read_len - p : 0u;
       uint32_t c4;
       if (PACKED) c4 = nv ? packed_codes4((uint8_t)seq[p >> 2], nv, ag) : 0u;
       else c4 = codes4(load4_ascii(seq, p, read_len), nv, ag, bad);
       // bytes c0..c3 (first character lowest) -> c0<<6 | c1<<4 | c2<<2 | c3
-      rb[8u * k + (7u - lane)] = (uint8_t)((c4 * 0x40100401u) >> 24);   // little-endian u64: first base on top
-      dw[8u * k + lane] = digits4(c4, ag);
-    }
-  } else {
-    for (uint32_t k = 0; k < nw; ++k) {
-      uint64_t word = 0;
-      for (uint32_t j = 0; j < 32u / W::WIDTH; ++j) {
-        const uint32_t p = 32u * k + j * W::WIDTH + lane;
-        uint32_t code = 0;
-        if (p < read_len) {
-          if (PACKED) {
-            code = convert_code(((uint32_t)(uint8_t)seq[p >> 2] >> (6u - 2u * (p & 3u))) & 3u, ag);
-          } else {
-            const uint32_t c = (uint8_t)seq[p];
-            bad |= !ascii_is_acgt(c);
-            code = convert_code(ascii_code(c), ag);
-          }
-        }
-        sc.D[p] = (uint8_t)ternary_digit(code, ag);
-        const uint32_t sh = 32u - W::WIDTH;        // ballot bit l -> base j*WIDTH + l of the word
-        const uint32_t hi = brev32(w.ballot((code & 2u) != 0u)) >> sh;
-        const uint32_t lo = brev32(w.ballot((code & 1u) != 0u)) >> sh;
-        const uint64_t part = (spread32(hi) << 1) | spread32(lo);     // 2*WIDTH bits, first base on top
-        word |= part << (64u - 2u * W::WIDTH * (j + 1u));
-      }
-      if (lane == 0) sc.R[k] = word;
+      rb[(p >> 5) * 8u + (7u - ((p & 31u) >> 2))] = (uint8_t)((c4 * 0x40100401u) >> 24);   // little-endian u64: first base on top
+      dw[p >> 2] = digits4(c4, ag);
     }
   }
   bool any_bad = PACKED ? false : w.ballot(bad) != 0u;
@@ -481,6 +456,48 @@ WALT_HD uint32_t literal_char(const uint64_t* __restrict__ genome, uint64_t pos,
   return 1u + packed_base(genome, pos + PAD_BASES);
 }
 
+// LowerBound / UpperBound of mapping.cpp:166-196 over slots [low, high] for the probe value `ch`,
+// same probes, same decisions, same result -- but four levels of the decision tree are probed at
+// once (15 independent entry -> genome load chains in flight instead of one), because a probe is
+// two dependent cache-missing loads and a bucket of 2^18 entries means ~19 of them in a row.  The
+// array is NOT assumed to be sorted (that is the point of the literal replay): the outcomes are the
+// reference's because every value that decides a step is the value the reference would have read.
+template <bool UPPER, class Probe>
+WALT_HD uint32_t literal_bound(uint32_t low, uint32_t high, uint32_t ch, Probe probe) {
+  constexpr uint32_t LEVELS = 4u, NODES = 15u;
+  while (low < high) {
+    uint32_t lo[NODES], hi[NODES], mid[NODES], val[NODES];
+    lo[0] = low; hi[0] = high;
+    WALT_UNROLL
+    for (uint32_t k = 0; k < NODES; ++k) {
+      const bool open = lo[k] < hi[k];
+      mid[k] = UPPER ? lo[k] + (hi[k] - lo[k] + 1u) / 2u : lo[k] + (hi[k] - lo[k]) / 2u;
+      if (2u * k + 2u < NODES) {   // child 2k+1: the comparison held, child 2k+2: it did not
+        if (!open) {
+          lo[2u * k + 1u] = hi[2u * k + 1u] = lo[2u * k + 2u] = hi[2u * k + 2u] = lo[k];
+        } else if (UPPER) {
+          lo[2u * k + 1u] = mid[k]; hi[2u * k + 1u] = hi[k];
+          lo[2u * k + 2u] = lo[k]; hi[2u * k + 2u] = mid[k] - 1u;
+        } else {
+          lo[2u * k + 1u] = lo[k]; hi[2u * k + 1u] = mid[k];
+          lo[2u * k + 2u] = mid[k] + 1u; hi[2u * k + 2u] = hi[k];
+        }
+      }
+    }
+    WALT_UNROLL
+    for (uint32_t k = 0; k < NODES; ++k) val[k] = lo[k] < hi[k] ? probe(mid[k]) : 0u;
+    uint32_t k = 0u;
+    for (uint32_t lvl = 0; lvl < LEVELS && low < high; ++lvl) {   // (low, high) is node k's interval
+      const uint32_t m = mid[k];
+      const bool held = UPPER ? val[k] <= ch : val[k] >= ch;
+      if (UPPER) { if (held) low = m; else high = m - 1u; }
+      else       { if (held) high = m; else low = m + 1u; }
+      k = 2u * k + (held ? 1u : 2u);
+    }
+  }
+  return low;
+}
+
 WALT_HD void literal_index_region(const SubIndexView& ix, uint32_t genome_len, const uint64_t* R,
                                   uint32_t seed_i, uint32_t seed_len, uint32_t& first,
                                   uint32_t& second) {
@@ -488,25 +505,10 @@ WALT_HD void literal_index_region(const SubIndexView& ix, uint32_t genome_len, c
   for (uint32_t p = KEY_WEIGHT; p < seed_len; ++p) {
     const uint32_t cp = 3u * p + 1u;
     const uint32_t ch = 1u + packed_base(R, seed_i + cp);
-    {  // LowerBound
-      uint32_t low = l, high = u;
-      while (low < high) {
-        uint32_t mid = low + (high - low) / 2u;
-        uint32_t c = literal_char(ix.genome, (uint64_t)ix.entries[mid].pos + cp, genome_len);
-        if (c >= ch) high = mid; else low = mid + 1u;
-      }
-      l = low;
-    }
-    {  // UpperBound
-      uint32_t low = l, high = u;
-      while (low < high) {
-        uint32_t mid = low + (high - low + 1u) / 2u;
-        uint32_t c = literal_char(ix.genome, (uint64_t)ix.entries[mid].pos + cp, genome_len);
-        if (c <= ch) low = mid; else high = mid - 1u;
-      }
-      u = low;
-    }
-    if (l == u && ch != literal_char(ix.genome, (uint64_t)ix.entries[l].pos + cp, genome_len)) {
+    auto probe = [&](uint32_t slot) { return literal_char(ix.genome, (uint64_t)ix.entries[slot].pos + cp, genome_len); };
+    l = literal_bound<false>(l, u, ch, probe);
+    u = literal_bound<true>(l, u, ch, probe);
+    if (l == u && ch != probe(l)) {
       first = 1u; second = 0u;
       return;
     }
@@ -963,8 +965,8 @@ WALT_HD uint32_t wide_compare(W& w, const WideBlock& blk, const Quad32& Rq, cons
 // are the leading slots whose fingerprint lies in [fp_lo, fp_lo + fp_span] (a prefix of the range:
 // fingerprints are sorted inside a table range) and, of those, the seed-equal ones -- the
 // reference's narrowed region; otherwise every slot is a candidate.  W::WIDTH == 32 and
-// read_len <= WIDE_MAX_READ.  Three blocks are in flight: entries of the block after next, genome
-// of the next, compare + sink of the current one.
+// read_len <= WIDE_MAX_READ.  The entries of the next block are loaded while the windows of the
+// current one are in flight; other warps of the SM cover the rest of the latency.
 template <class W, class Sink>
 WALT_HD void verify_run_wide(W& w, const SubIndexView& ix, const ChromView& cv, const ReadScratch& sc, uint32_t read_len,
                              uint32_t seed_i, uint32_t strand, uint32_t first, uint32_t last_excl, bool by_fp,
@@ -975,44 +977,119 @@ WALT_HD void verify_run_wide(W& w, const SubIndexView& ix, const ChromView& cv, 
   const Quad32 VMq = read_block(sc.VM + seed_i * sc.nw, q, nw);
   Quad32 SMq = read_block(sc.SM + seed_i * sc.nw, q, nw);
   if (!by_fp) { SMq.b[0] = SMq.b[1] = SMq.b[2] = SMq.b[3] = 0u; }
-  auto in_run = [&](const Entry& en, uint32_t base) {
-    return base + lane < last_excl && base < last_excl && (!by_fp || en.fp - fp_lo <= fp_span);   // unsigned: also rejects fp < fp_lo
-  };
-  uint32_t base = first;
-  WideBlock cur, nxt;
-  cur.en = wide_load_entry(w, ix, base, last_excl);
-  nxt.en = wide_load_entry(w, ix, base + 32u, last_excl);
-  uint32_t ok = w.ballot(in_run(cur.en, base));
-  if (!ok) return;
-  if (!((ok >> lane) & 1u)) cur.en.pos = 0u;
-  wide_load_genome(w, ix, seed_i, cur);
-  for (;;) {
-    // stage the following blocks (the run goes on only if every slot of this block was in it)
-    const bool more = ok == 0xFFFFFFFFu && base + 32u < last_excl;
-    uint32_t ok_next = 0u;
-    Entry en_after; en_after.pos = 0u; en_after.fp = 0u;
-    if (more) {
-      en_after = wide_load_entry(w, ix, base + 64u, last_excl);
-      ok_next = w.ballot(in_run(nxt.en, base + 32u));
-      if (!((ok_next >> lane) & 1u)) nxt.en.pos = 0u;
-      if (ok_next) wide_load_genome(w, ix, seed_i, nxt);
-    }
-    // this block
-    const uint32_t r = wide_compare(w, cur, Rq, VMq, SMq);
+  WideBlock blk;
+  blk.en = wide_load_entry(w, ix, first, last_excl);
+  for (uint32_t base = first; base < last_excl; base += 32u) {
+    const uint32_t ok = w.ballot(base + lane < last_excl && (!by_fp || blk.en.fp - fp_lo <= fp_span));   // unsigned: also rejects fp < fp_lo
+    if (!ok) break;
+    if (!((ok >> lane) & 1u)) blk.en.pos = 0u;
+    wide_load_genome(w, ix, seed_i, blk);
+    const uint32_t e = blk.en.pos;
+    const bool more = ok == 0xFFFFFFFFu;   // the run goes on only if every slot of this block was in it
+    if (more) blk.en = wide_load_entry(w, ix, base + 32u, last_excl);
+    const uint32_t r = wide_compare(w, blk, Rq, VMq, SMq);
     const uint32_t mm = r & 0xFFFFu;
     bool valid = ((ok >> lane) & 1u) != 0u && (r >> 16) == 0u;
     if (valid) ctr.candidates++;
     valid = valid && sink.may_take(mm);
     uint32_t g = 0u;
     if (valid) {   // bounds, mapping.cpp:281-286
-      const uint32_t e = cur.en.pos;
       const uint32_t chr = chrom_of(cv.starts, cv.n_chr, e);
       g = e - seed_i;
       valid = (e - cv.starts[chr] >= seed_i) && !(g + read_len >= cv.starts[chr + 1u]);
     }
     sink.consume(w, valid, mm, g, strand);
-    if (!ok_next) break;
-    cur = nxt; ok = ok_next; nxt.en = en_after; base += 32u;
+    if (!more) break;
+  }
+}
+
+// Exact region [first, last_excl) of one lookup -> sink, in slot order.
+template <class W, class Sink>
+WALT_HD void verify_region(W& w, const SubIndexView& ix, const ChromView& cv, const ReadScratch& sc, uint32_t read_len,
+                           uint32_t seed_i, uint32_t strand, uint32_t first, uint32_t last_excl, Sink& sink, Counters& ctr) {
+  constexpr uint32_t WD = W::WIDTH;
+  const uint32_t lane = w.lane();
+  const uint32_t nw = (read_len + 31u) >> 5;
+  const uint64_t* R = sc.R;
+  const uint64_t* VM = sc.VM + seed_i * sc.nw;
+  const uint64_t* SM = sc.SM + seed_i * sc.nw;
+  // Exact region [first, last_excl): every slot is a candidate.  Long regions (repeats) are a
+  // chain of dependent gathers -- entry, then genome window -- so every lane keeps SLOTS_AHEAD
+  // of them in flight: the entries of a block are loaded together and their windows prefetched
+  // before the first is compared.  Candidates reach the sink in slot order, WD at a time.
+#ifndef WALT_SLOTS_AHEAD
+#define WALT_SLOTS_AHEAD 4
+#endif
+  if (WD == 32u && read_len <= WIDE_MAX_READ) {
+    verify_run_wide(w, ix, cv, sc, read_len, seed_i, strand, first, last_excl, false, 0u, 0u, sink, ctr);
+    return;
+  }
+  constexpr uint32_t SLOTS_AHEAD = WALT_SLOTS_AHEAD;
+  for (uint32_t base = first; base < last_excl; base += WD * SLOTS_AHEAD) {
+    uint32_t e[SLOTS_AHEAD];
+    WALT_UNROLL
+    for (uint32_t u = 0; u < SLOTS_AHEAD; ++u) {
+      const uint32_t slot = base + u * WD + lane;
+      e[u] = slot < last_excl ? ix.entries[slot].pos : 0u;   // 64 readable pad entries behind index[]
+    }
+    WALT_UNROLL
+    for (uint32_t u = 0; u < SLOTS_AHEAD; ++u) {
+      if (base + u * WD + lane < last_excl) {
+        const uint64_t* g0 = ix.genome + (((uint64_t)e[u] + PAD_BASES - seed_i) >> 5);
+        WALT_PREFETCH(g0);
+        WALT_PREFETCH(g0 + nw);
+      }
+    }
+#ifndef WALT_ROLLED_COMPARE
+#define WALT_ROLLED_COMPARE 1
+#endif
+#if WALT_ROLLED_COMPARE
+    // One copy of the compare / bounds / sink code instead of four.  With the body unrolled the
+    // repeat path was bound by instruction fetch (stalled_no_instruction 19.7 cycles per issue:
+    // the four groups of a warp run this loop out of step, each fetching its own stream through a
+    // ~25 KB body); rolled, configs[4] went from 215 to 149 ms per 5 M pairs.
+    WALT_NO_UNROLL
+    for (uint32_t u = 0; u < SLOTS_AHEAD; ++u) {
+      if (base + u * WD >= last_excl) break;                 // uniform
+      uint32_t eu = e[0];   // e[] lives in registers: select, do not index
+      WALT_UNROLL
+      for (uint32_t q = 1; q < SLOTS_AHEAD; ++q) eu = u == q ? e[q] : eu;
+      bool valid = base + u * WD + lane < last_excl;
+      uint32_t g = 0, mm = 0;
+      if (valid) {
+        WindowResult r = compare_window(ix.genome, (uint64_t)eu + PAD_BASES - seed_i, R, VM, SM, nw);
+        mm = r.mismatches;
+        ctr.candidates++;
+        valid = sink.may_take(mm);
+      }
+      if (valid) {
+        const uint32_t chr = chrom_of(cv.starts, cv.n_chr, eu);
+        g = eu - seed_i;
+        valid = (eu - cv.starts[chr] >= seed_i) && !(g + read_len >= cv.starts[chr + 1u]);
+      }
+      sink.consume(w, valid, mm, g, strand);
+    }
+#else
+    WALT_UNROLL
+    for (uint32_t u = 0; u < SLOTS_AHEAD; ++u) {
+      if (base + u * WD >= last_excl) break;                 // uniform
+      bool valid = base + u * WD + lane < last_excl;
+      uint32_t g = 0, mm = 0;
+      if (valid) {
+        WindowResult r = compare_window(ix.genome, (uint64_t)e[u] + PAD_BASES - seed_i, R, VM, SM, nw);
+        mm = r.mismatches;
+        ctr.candidates++;
+        valid = sink.may_take(mm);
+      }
+      if (valid) {
+        // bounds, mapping.cpp:281-286 (all uint32 arithmetic, as the reference)
+        const uint32_t chr = chrom_of(cv.starts, cv.n_chr, e[u]);
+        g = e[u] - seed_i;
+        valid = (e[u] - cv.starts[chr] >= seed_i) && !(g + read_len >= cv.starts[chr + 1u]);
+      }
+      sink.consume(w, valid, mm, g, strand);
+    }
+#endif
   }
 }
 
@@ -1150,84 +1227,7 @@ WALT_HD void seed_lookup(W& w, const SubIndexView& ix, const ChromView& cv, cons
     if (last_excl - first > cfg.b) return;
   }
 
-  // Exact region [first, last_excl): every slot is a candidate.  Long regions (repeats) are a
-  // chain of dependent gathers -- entry, then genome window -- so every lane keeps SLOTS_AHEAD
-  // of them in flight: the entries of a block are loaded together and their windows prefetched
-  // before the first is compared.  Candidates reach the sink in slot order, WD at a time.
-#ifndef WALT_SLOTS_AHEAD
-#define WALT_SLOTS_AHEAD 4
-#endif
-  if (WD == 32u && read_len <= WIDE_MAX_READ) {
-    verify_run_wide(w, ix, cv, sc, read_len, seed_i, strand, first, last_excl, false, 0u, 0u, sink, ctr);
-    return;
-  }
-  constexpr uint32_t SLOTS_AHEAD = WALT_SLOTS_AHEAD;
-  for (uint32_t base = first; base < last_excl; base += WD * SLOTS_AHEAD) {
-    uint32_t e[SLOTS_AHEAD];
-    WALT_UNROLL
-    for (uint32_t u = 0; u < SLOTS_AHEAD; ++u) {
-      const uint32_t slot = base + u * WD + lane;
-      e[u] = slot < last_excl ? ix.entries[slot].pos : 0u;   // 64 readable pad entries behind index[]
-    }
-    WALT_UNROLL
-    for (uint32_t u = 0; u < SLOTS_AHEAD; ++u) {
-      if (base + u * WD + lane < last_excl) {
-        const uint64_t* g0 = ix.genome + (((uint64_t)e[u] + PAD_BASES - seed_i) >> 5);
-        WALT_PREFETCH(g0);
-        WALT_PREFETCH(g0 + nw);
-      }
-    }
-#ifndef WALT_ROLLED_COMPARE
-#define WALT_ROLLED_COMPARE 1
-#endif
-#if WALT_ROLLED_COMPARE
-    // One copy of the compare / bounds / sink code instead of four.  With the body unrolled the
-    // repeat path was bound by instruction fetch (stalled_no_instruction 19.7 cycles per issue:
-    // the four groups of a warp run this loop out of step, each fetching its own stream through a
-    // ~25 KB body); rolled, configs[4] went from 215 to 149 ms per 5 M pairs.
-    WALT_NO_UNROLL
-    for (uint32_t u = 0; u < SLOTS_AHEAD; ++u) {
-      if (base + u * WD >= last_excl) break;                 // uniform
-      uint32_t eu = e[0];   // e[] lives in registers: select, do not index
-      WALT_UNROLL
-      for (uint32_t q = 1; q < SLOTS_AHEAD; ++q) eu = u == q ? e[q] : eu;
-      bool valid = base + u * WD + lane < last_excl;
-      uint32_t g = 0, mm = 0;
-      if (valid) {
-        WindowResult r = compare_window(ix.genome, (uint64_t)eu + PAD_BASES - seed_i, R, VM, SM, nw);
-        mm = r.mismatches;
-        ctr.candidates++;
-        valid = sink.may_take(mm);
-      }
-      if (valid) {
-        const uint32_t chr = chrom_of(cv.starts, cv.n_chr, eu);
-        g = eu - seed_i;
-        valid = (eu - cv.starts[chr] >= seed_i) && !(g + read_len >= cv.starts[chr + 1u]);
-      }
-      sink.consume(w, valid, mm, g, strand);
-    }
-#else
-    WALT_UNROLL
-    for (uint32_t u = 0; u < SLOTS_AHEAD; ++u) {
-      if (base + u * WD >= last_excl) break;                 // uniform
-      bool valid = base + u * WD + lane < last_excl;
-      uint32_t g = 0, mm = 0;
-      if (valid) {
-        WindowResult r = compare_window(ix.genome, (uint64_t)e[u] + PAD_BASES - seed_i, R, VM, SM, nw);
-        mm = r.mismatches;
-        ctr.candidates++;
-        valid = sink.may_take(mm);
-      }
-      if (valid) {
-        // bounds, mapping.cpp:281-286 (all uint32 arithmetic, as the reference)
-        const uint32_t chr = chrom_of(cv.starts, cv.n_chr, e[u]);
-        g = e[u] - seed_i;
-        valid = (e[u] - cv.starts[chr] >= seed_i) && !(g + read_len >= cv.starts[chr + 1u]);
-      }
-      sink.consume(w, valid, mm, g, strand);
-    }
-#endif
-  }
+  verify_region(w, ix, cv, sc, read_len, seed_i, strand, first, last_excl, sink, ctr);
 }
 
 // Out-of-line copy of seed_lookup for the read loops: the cooperative replay is the rare path
@@ -1265,10 +1265,21 @@ WALT_HD void replay_lookup(W& w, const SubIndexView& ix, const ChromView& cv, co
 // (possible literal replay) or more than LANE_RUN_CAP fingerprint-equal slots (repeats).
 // `emit(g, mm)` receives the verified candidates in index order; `discard()` is called if the
 // lookup turns out to be filtered by -b after some were emitted.
+// LANE_GROUP: the whole lookup is the group's job (tainted bucket).  LANE_RUN: more than LANE_RUN_CAP
+// fingerprint-equal slots; `run` then says where the run starts and where its table range ends, so
+// that a whole warp can stream it (run_lookup) without searching again.
+enum LaneResult : uint32_t { LANE_DONE = 0u, LANE_GROUP = 1u, LANE_RUN = 2u, LANE_LIT = 3u };   // LANE_LIT: literal lookup, region known
+struct LaneRun { uint32_t f0, hi, fp_lo; };
+WALT_HD uint32_t lookup_fp_span(const SubIndexView& ix, uint32_t read_len, const Pow3& p3) {
+  const uint32_t seed_len = seed_repeats(read_len);
+  const uint32_t n_fp = seed_len > ix.depth ? (seed_len - ix.depth < FP_DIGITS ? seed_len - ix.depth : FP_DIGITS) : 0u;
+  return p3.v[FP_DIGITS - n_fp] - 1u;
+}
+
 template <class Emit, class Discard>
-WALT_HD bool lane_lookup(const SubIndexView& ix, const ChromView& cv, const Pow3& p3, const MapConfig& cfg,
-                         const ReadScratch& sc, uint32_t read_len, uint32_t seed_i, Emit emit, Discard discard,
-                         Counters& ctr) {
+WALT_HD LaneResult lane_lookup(const SubIndexView& ix, const ChromView& cv, const Pow3& p3, const MapConfig& cfg,
+                               const ReadScratch& sc, uint32_t read_len, uint32_t seed_i, Emit emit, Discard discard,
+                               Counters& ctr, LaneRun& run) {
   const uint32_t seed_len = seed_repeats(read_len);
   const uint32_t nw = (read_len + 31u) >> 5;
   const uint32_t n_pref = ix.depth < seed_len ? ix.depth : seed_len;
@@ -1289,8 +1300,8 @@ WALT_HD bool lane_lookup(const SubIndexView& ix, const ChromView& cv, const Pow3
   // a tainted bucket needs the literal replay only if the read agrees with a tainted position
   // on every seed character inside the chromosome (rare; the replay is the group's job)
   if (((ix.taint_bits[key12 >> 5] >> (key12 & 31u)) & 1u) && lane_is_affected(ix, sc.R, seed_i, seed_len, key12))
-    return false;
-  if (lo == hi) return true;
+    return LANE_GROUP;
+  if (lo == hi) return LANE_DONE;
   ctr.lookups++;
   // first slot of [lo, hi) whose fingerprint is >= fp_lo: bisect down to a LANE_RUN_CAP window
   uint32_t l = lo, h = hi;
@@ -1306,10 +1317,15 @@ WALT_HD bool lane_lookup(const SubIndexView& ix, const ChromView& cv, const Pow3
   WALT_UNROLL
   for (uint32_t k = 0; k < LANE_RUN_CAP; ++k)
     if (l + k < hi && en[k].fp - fp_lo <= fp_span) match |= 1u << k;      // unsigned: also rejects fp < fp_lo
-  if (match == 0u) return true;
+  if (match == 0u) return LANE_DONE;
   // fingerprints are sorted inside a table range, so the matches are one run; it is complete
   // unless it touches the end of the window and the range goes on
-  if ((match >> (LANE_RUN_CAP - 1u)) && l + LANE_RUN_CAP < hi) return false;
+  if ((match >> (LANE_RUN_CAP - 1u)) && l + LANE_RUN_CAP < hi) {
+    run.f0 = l + (uint32_t)ffs32(match) - 1u; run.hi = hi; run.fp_lo = fp_lo;
+    WALT_PREFETCH(ix.entries + run.f0 + LANE_RUN_CAP);          // the streaming pass starts here
+    WALT_PREFETCH(ix.entries + run.f0 + LANE_RUN_CAP + 16u);
+    return LANE_RUN;
+  }
   const uint64_t* R = sc.R;
   const uint64_t* VM = sc.VM + seed_i * sc.nw;
   const uint64_t* SM = sc.SM + seed_i * sc.nw;
@@ -1332,7 +1348,120 @@ WALT_HD bool lane_lookup(const SubIndexView& ix, const ChromView& cv, const Pow3
     }
   }
   if (n_region > cfg.b) discard();   // mapping.cpp:275-277
-  return true;
+  return LANE_DONE;
+}
+
+// A long fingerprint run found by lookup lane j (LANE_RUN), fed to the sink.  A whole warp streams
+// it through the quad verification straight from the run's first slot; narrower groups (and runs
+// that may exceed -b, whose exact region size matters) take the general cooperative lookup.
+template <class W, class Sink>
+WALT_HD void run_lookup(W& w, const SubIndexView& ix, const ChromView& cv, const Pow3& p3, const MapConfig& cfg,
+                        const ReadScratch& sc, uint32_t read_len, uint32_t seed_i, uint32_t strand, const LaneRun& mine,
+                        uint32_t j, Sink& sink, Counters& ctr) {
+  if (W::WIDTH == 32u && read_len <= WIDE_MAX_READ) {
+    const uint32_t f0 = w.shfl(mine.f0, (int)j), hi = w.shfl(mine.hi, (int)j), fp_lo = w.shfl(mine.fp_lo, (int)j);
+    const uint32_t fp_span = lookup_fp_span(ix, read_len, p3);
+    bool longer = false;   // does the run reach past b slots?  (the narrowed region is a subset of the run)
+    if ((uint64_t)f0 + cfg.b < hi) longer = ix.entries[f0 + cfg.b].fp - fp_lo <= fp_span;
+    if (!longer) {
+      verify_run_wide(w, ix, cv, sc, read_len, seed_i, strand, f0, hi, true, fp_lo, fp_span, sink, ctr);
+      return;
+    }
+  }
+  replay_lookup(w, ix, cv, p3, cfg, sc, read_len, seed_i, strand, sink, ctr);
+}
+
+// The long runs of a read are streamed one after the other (the fold is ordered), each a chain
+// entries -> windows of dependent cache misses.  Before the fold, the first block of EVERY run is
+// started: its entries are loaded by the 32 lanes and the lines of their windows prefetched, so
+// that the six chains overlap and the ordered pass finds its first blocks on chip.
+template <class W>
+WALT_HD void prefetch_runs(W& w, const SubIndexView* ix2, uint32_t run_mask, const LaneRun& mine) {
+#if defined(__CUDA_ARCH__)
+  if (W::WIDTH != 32u) return;
+  const uint32_t lane = w.lane();
+  uint32_t e[LOOKUP_LANES];
+  WALT_UNROLL
+  for (uint32_t j = 0; j < LOOKUP_LANES; ++j) {
+    e[j] = 0xFFFFFFFFu;
+    if ((run_mask >> j) & 1u) {
+      const uint32_t slot = w.shfl(mine.f0, (int)j) + lane, hi = w.shfl(mine.hi, (int)j);
+      if (slot < hi) e[j] = ix2[j / 3u].entries[slot].pos;
+    }
+  }
+  WALT_UNROLL
+  for (uint32_t j = 0; j < LOOKUP_LANES; ++j)
+    if (e[j] != 0xFFFFFFFFu)
+      WALT_PREFETCH(reinterpret_cast<const char*>(ix2[j / 3u].genome) + ((((uint64_t)e[j] + PAD_BASES - j % 3u) >> 6) << 4));
+#else
+  (void)w; (void)ix2; (void)run_mask; (void)mine;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------
+// literal regions ahead of the take-over kernel (one THREAD per parked read)
+// ------------------------------------------------------------------------------------------
+// The literal IndexRegion replay is one long chain of dependent loads (two per probe, ~200 probes
+// on a bucket of thousands).  A warp that runs it for one lookup sits idle for a hundred
+// microseconds; run by one thread per parked read, tens of thousands of chains are in flight at
+// once.  For each of the read's six lookups: {LIT_NONE, -} if the lookup is not a literal one,
+// {LIT_EMPTY, -} if its 12-mer bucket is empty, else the inclusive region IndexRegion returns
+// ((1, 0) for a failed search).
+constexpr uint32_t LIT_NONE = 0xFFFFFFFFu;
+constexpr uint32_t LIT_EMPTY = 0xFFFFFFFEu;
+constexpr uint32_t LIT_WORDS = 2u * LOOKUP_LANES;
+
+// pack + convert a read by one thread; false if a byte is not A/C/G/T
+template <bool PACKED>
+WALT_HD bool pack_read_serial(const char* __restrict__ seq, uint32_t read_len, bool ag, uint64_t* R) {
+  const uint32_t nw = (read_len + 31u) >> 5;
+  bool bad = false;
+  for (uint32_t k = 0; k < nw; ++k) {
+    uint64_t word = 0;
+    for (uint32_t p = 32u * k; p < 32u * k + 32u; p += 4u) {   // four characters -> one byte, as load_read does
+      const uint32_t nv = p < read_len ? read_len - p : 0u;
+      uint32_t c4;
+      if (PACKED) c4 = nv ? packed_codes4((uint8_t)seq[p >> 2], nv, ag) : 0u;
+      else c4 = codes4(load4_ascii(seq, p, read_len), nv, ag, bad);
+      word = (word << 8) | ((c4 * 0x40100401u) >> 24);
+    }
+    R[k] = word;
+  }
+  return !bad;
+}
+
+WALT_HD void literal_regions(const SubIndexView* ix2, uint32_t genome_len, const Pow3& p3, const MapConfig& cfg,
+                             const uint64_t* R, uint32_t read_len, uint32_t* out) {
+  const uint32_t seed_len = seed_repeats(read_len);
+  for (uint32_t j = 0; j < LOOKUP_LANES; ++j) {
+    out[2u * j] = LIT_NONE; out[2u * j + 1u] = 0u;
+    if (read_len < MIN_READ_LEN) continue;
+    const SubIndexView& ix = ix2[j / 3u];
+    const uint32_t seed_i = j % 3u;
+    uint32_t key12 = 0u;
+    for (uint32_t i = 0; i < KEY_WEIGHT; ++i)
+      key12 = key12 * 3u + ternary_digit(packed_base(R, seed_i + 3u * i + 1u), ix.ag != 0u);
+    const bool literal = cfg.literal_all != 0u ||
+                         ((((ix.taint_bits[key12 >> 5] >> (key12 & 31u)) & 1u) != 0u) && lane_is_affected(ix, R, seed_i, seed_len, key12));
+    if (!literal) continue;
+    const uint32_t k12_span = p3.v[ix.depth - KEY_WEIGHT];
+    const uint32_t bucket_lo = ix.table[key12 * k12_span], bucket_hi = ix.table[(key12 + 1u) * k12_span];
+    if (bucket_lo == bucket_hi) { out[2u * j] = LIT_EMPTY; continue; }
+    uint32_t f = bucket_lo, l = bucket_hi;
+    literal_index_region(ix, genome_len, R, seed_i, seed_len, f, l);
+    out[2u * j] = f; out[2u * j + 1u] = l;
+  }
+}
+
+// a literal lookup whose region is known (literal_regions): filters and candidates as in seed_lookup
+template <class W, class Sink>
+WALT_HD void lit_lookup(W& w, const SubIndexView& ix, const ChromView& cv, const MapConfig& cfg, const ReadScratch& sc,
+                        uint32_t read_len, uint32_t seed_i, uint32_t strand, uint32_t f, uint32_t l, Sink& sink, Counters& ctr) {
+  if (f == LIT_EMPTY) return;
+  if (w.lane() == 0u) { ctr.lookups++; ctr.literal++; }
+  if (l - f + 1u > cfg.b) return;      // mapping.cpp:275-277 (u32 arithmetic; (1,0) -> 0)
+  if (f > l) return;                   // failed search: empty candidate loop
+  verify_region(w, ix, cv, sc, read_len, seed_i, strand, f, l + 1u, sink, ctr);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1349,7 +1478,7 @@ template <class W, bool PACKED = false, bool PARK = false>
 WALT_HD MapStatus map_read_se(W& w, const SubIndexView* ix2, const ChromView& cv, const Pow3& p3,
                          const MapConfig& cfg, const char* seq, uint32_t read_len, bool ag,
                          uint32_t max_mismatches, ReadScratch& sc, uint32_t& cached_len,
-                         BestState& out, Counters& ctr) {
+                         BestState& out, Counters& ctr, const uint32_t* lit = nullptr) {
   static_assert(W::WIDTH >= LOOKUP_LANES, "a group needs one lane per lookup");
   BestSink<W> sink;
   sink.st.pos = 0u; sink.st.times = 0u; sink.st.mm = max_mismatches; sink.st.strand = '+';
@@ -1361,35 +1490,46 @@ WALT_HD MapStatus map_read_se(W& w, const SubIndexView* ix2, const ChromView& cv
   // every lookup lane runs its own lookup and summarises it: minimum, how many candidates
   // share it, the first and the last of them (all the ordered fold needs, see BestSink::apply)
   const uint32_t lane = w.lane();
-  bool coop = false;
+  LaneResult res = LANE_DONE;
+  LaneRun run; run.f0 = run.hi = run.fp_lo = 0u;
   uint32_t mn = NO_HIT, cnt = 0u, g_first = 0u, g_last = 0u;
+  uint32_t lit_f = LIT_NONE, lit_l = 0u;
   if (lane < LOOKUP_LANES) {
-    if (cfg.literal_all) {
-      coop = true;
+    if (lit) { lit_f = lit[2u * lane]; lit_l = lit[2u * lane + 1u]; }
+    if (lit_f != LIT_NONE) {
+      res = LANE_LIT;
+    } else if (cfg.literal_all) {
+      res = LANE_GROUP;
     } else {
-      coop = !lane_lookup(ix2[lane / 3u], cv, p3, cfg, sc, read_len, lane % 3u,
-                          [&](uint32_t g, uint32_t mmc) {
-                            if (mmc < mn) { mn = mmc; cnt = 1u; g_first = g_last = g; }
-                            else if (mmc == mn) { ++cnt; g_last = g; }
-                          },
-                          [&]() { mn = NO_HIT; cnt = 0u; }, ctr);
+      res = lane_lookup(ix2[lane / 3u], cv, p3, cfg, sc, read_len, lane % 3u,
+                        [&](uint32_t g, uint32_t mmc) {
+                          if (mmc < mn) { mn = mmc; cnt = 1u; g_first = g_last = g; }
+                          else if (mmc == mn) { ++cnt; g_last = g; }
+                        },
+                        [&]() { mn = NO_HIT; cnt = 0u; }, ctr, run);
     }
   }
-  const uint32_t coop_mask = w.ballot(coop);
+  const uint32_t group_mask = w.ballot(res == LANE_GROUP);
+  const uint32_t run_mask = w.ballot(res == LANE_RUN);
+  const uint32_t lit_mask = w.ballot(res == LANE_LIT);
   const uint32_t hit_mask = w.ballot(mn != NO_HIT);
   // ordered fold over the lookups that can change the state.  Skipping a lookup where the
   // reference would have left the shift loop (mapping.cpp:250-256) is the same as its break: the
   // state is untouched by a skip, so the later shifts of that strand are skipped as well.
-  uint32_t todo = (coop_mask | hit_mask) & ((1u << LOOKUP_LANES) - 1u);
+  if (!PARK && run_mask && read_len <= WIDE_MAX_READ) prefetch_runs(w, ix2, run_mask, run);
+  uint32_t todo = (group_mask | run_mask | lit_mask | hit_mask) & ((1u << LOOKUP_LANES) - 1u);
   while (todo) {
     const uint32_t j = (uint32_t)ffs32(todo) - 1u;
     todo &= todo - 1u;
     const uint32_t s = j >= 3u ? 1u : 0u, seed_i = j - 3u * s;
     const uint32_t strand = s ? '-' : '+';
     if (sink.stop_before_shift(seed_i)) continue;
-    if ((coop_mask >> j) & 1u) {
+    if ((lit_mask >> j) & 1u) {
+      lit_lookup(w, ix2[s], cv, cfg, sc, read_len, seed_i, strand, w.shfl(lit_f, (int)j), w.shfl(lit_l, (int)j), sink, ctr);
+    } else if (((group_mask | run_mask) >> j) & 1u) {
       if (PARK) { ctr = ctr_in; w.sync(); return MAP_PARKED; }   // the kernel that takes the read over counts its work
-      replay_lookup(w, ix2[s], cv, p3, cfg, sc, read_len, seed_i, strand, sink, ctr);
+      if ((run_mask >> j) & 1u) run_lookup(w, ix2[s], cv, p3, cfg, sc, read_len, seed_i, strand, run, j, sink, ctr);
+      else replay_lookup(w, ix2[s], cv, p3, cfg, sc, read_len, seed_i, strand, sink, ctr);
     } else {
       sink.apply(w.shfl(mn, (int)j), w.shfl(cnt, (int)j), w.shfl(g_first, (int)j), w.shfl(g_last, (int)j), strand);
     }
@@ -1405,7 +1545,7 @@ template <class W, bool PACKED, bool PARK, class SinkT>
 WALT_HD MapStatus map_read_pe_into(W& w, const SubIndexView* ix2, const ChromView& cv, const Pow3& p3,
                               const MapConfig& cfg, const char* seq, uint32_t read_len, bool ag,
                               uint32_t max_mismatches, ReadScratch& sc, uint32_t& cached_len, SinkT& sink,
-                              Counters& ctr) {
+                              Counters& ctr, const uint32_t* lit = nullptr) {
   static_assert(W::WIDTH >= LOOKUP_LANES, "a group needs one lane per lookup");
   const Counters ctr_in = ctr;
   if (read_len < MIN_READ_LEN) return MAP_OK;
@@ -1414,36 +1554,47 @@ WALT_HD MapStatus map_read_pe_into(W& w, const SubIndexView* ix2, const ChromVie
   // lookup lanes leave their candidates (index order) in the group's scratch; they reach the
   // sink in reference order
   const uint32_t lane = w.lane();
-  bool coop = false;
+  LaneResult res = LANE_DONE;
+  LaneRun run; run.f0 = run.hi = run.fp_lo = 0u;
   uint32_t n_mine = 0u;
+  uint32_t lit_f = LIT_NONE, lit_l = 0u;
   if (lane < LOOKUP_LANES) {
-    if (cfg.literal_all) {
-      coop = true;
+    if (lit) { lit_f = lit[2u * lane]; lit_l = lit[2u * lane + 1u]; }
+    if (lit_f != LIT_NONE) {
+      res = LANE_LIT;
+    } else if (cfg.literal_all) {
+      res = LANE_GROUP;
     } else {
       LaneCand* mine = sc.C + lane * LANE_RUN_CAP;
-      coop = !lane_lookup(ix2[lane / 3u], cv, p3, cfg, sc, read_len, lane % 3u,
-                          [&](uint32_t g, uint32_t mmc) {
-                            if (mmc > max_mismatches) return;          // paired.cpp:191-193
-                            LaneCand c; c.g = g; c.mm = mmc;
-                            mine[n_mine] = c;
-                            ++n_mine;
-                          },
-                          [&]() { n_mine = 0u; }, ctr);
+      res = lane_lookup(ix2[lane / 3u], cv, p3, cfg, sc, read_len, lane % 3u,
+                        [&](uint32_t g, uint32_t mmc) {
+                          if (mmc > max_mismatches) return;          // paired.cpp:191-193
+                          LaneCand c; c.g = g; c.mm = mmc;
+                          mine[n_mine] = c;
+                          ++n_mine;
+                        },
+                        [&]() { n_mine = 0u; }, ctr, run);
     }
   }
-  const uint32_t coop_mask = w.ballot(coop);
+  const uint32_t group_mask = w.ballot(res == LANE_GROUP);
+  const uint32_t run_mask = w.ballot(res == LANE_RUN);
+  const uint32_t lit_mask = w.ballot(res == LANE_LIT);
   const uint32_t hit_mask = w.ballot(n_mine != 0u);
   w.sync();
-  uint32_t todo = (coop_mask | hit_mask) & ((1u << LOOKUP_LANES) - 1u);
+  if (!PARK && run_mask && read_len <= WIDE_MAX_READ) prefetch_runs(w, ix2, run_mask, run);
+  uint32_t todo = (group_mask | run_mask | lit_mask | hit_mask) & ((1u << LOOKUP_LANES) - 1u);
   while (todo) {   // see map_read_se: a skip is the reference's break (paired.cpp:127-137)
     const uint32_t j = (uint32_t)ffs32(todo) - 1u;
     todo &= todo - 1u;
     const uint32_t s = j >= 3u ? 1u : 0u, seed_i = j - 3u * s;
     const uint32_t strand = s ? '-' : '+';
     if (sink.stop_before_shift(seed_i)) continue;
-    if ((coop_mask >> j) & 1u) {
+    if ((lit_mask >> j) & 1u) {
+      lit_lookup(w, ix2[s], cv, cfg, sc, read_len, seed_i, strand, w.shfl(lit_f, (int)j), w.shfl(lit_l, (int)j), sink, ctr);
+    } else if (((group_mask | run_mask) >> j) & 1u) {
       if (PARK) { ctr = ctr_in; w.sync(); return MAP_PARKED; }
-      replay_lookup(w, ix2[s], cv, p3, cfg, sc, read_len, seed_i, strand, sink, ctr);
+      if ((run_mask >> j) & 1u) run_lookup(w, ix2[s], cv, p3, cfg, sc, read_len, seed_i, strand, run, j, sink, ctr);
+      else replay_lookup(w, ix2[s], cv, p3, cfg, sc, read_len, seed_i, strand, sink, ctr);
     } else {
       const uint32_t nj = w.shfl(n_mine, (int)j);
       sink.push_list(w, sc.C + j * LANE_RUN_CAP, nj, strand);
@@ -1473,11 +1624,12 @@ template <class W, bool PACKED = false, bool PARK = false>
 WALT_HD MapStatus map_read_pe_logged(W& w, const SubIndexView* ix2, const ChromView& cv, const Pow3& p3,
                                 const MapConfig& cfg, const char* seq, uint32_t read_len, bool ag,
                                 uint32_t max_mismatches, uint32_t top_k, ReadScratch& sc,
-                                uint32_t& cached_len, HeapEntry* log, uint32_t* hist, uint32_t& n_log, Counters& ctr) {
+                                uint32_t& cached_len, HeapEntry* log, uint32_t* hist, uint32_t& n_log, Counters& ctr,
+                                const uint32_t* lit = nullptr) {
   LogSink<W> sink;
   sink.log = log; sink.hist = hist; sink.cap = top_k; sink.max_mm = max_mismatches;
   sink.reset(w);
-  const MapStatus st = map_read_pe_into<W, PACKED, PARK>(w, ix2, cv, p3, cfg, seq, read_len, ag, max_mismatches, sc, cached_len, sink, ctr);
+  const MapStatus st = map_read_pe_into<W, PACKED, PARK>(w, ix2, cv, p3, cfg, seq, read_len, ag, max_mismatches, sc, cached_len, sink, ctr, lit);
   n_log = sink.n_log;
   return st;
 }
@@ -1544,6 +1696,96 @@ WALT_HD PairResult pair_candidates(const ChromView& cv, GetCand get1, uint32_t n
         r.best_i = i; r.best_j = j; r.best_times++; r.frag = frag;
       }
     }
+  }
+  return r;
+}
+
+// The same pairing by a whole warp, for pairs whose k1 x k2 loop is long (both mates in repeats): a
+// thread-per-pair loop leaves the other 31 lanes of the warp idle for thousands of iterations.
+// The reference's loop is order dependent only through three facts, each a reduction over the
+// VALID pairs (opposite strands, same chromosome, 0 < fragment <= L, mismatch sum <= m; the
+// loop's `break` only skips pairs whose sum exceeds the running minimum):
+//   m*    the smallest mismatch sum;
+//   F     the first valid pair with sum m* in loop order -- its positions become best_pos, unless
+//         m* == m: then no `<` ever fired and best_pos stays 0 (paired.cpp:502-511);
+//   count / L   the valid pairs with sum m* whose positions differ from best_pos, and the last of
+//         them in loop order: best_times = count (+ 1 for F if m* < m), the reported pair is L
+//         (or F if nothing was counted).
+// Lanes own mate-1 candidates; mate 2's chromosome / forward start / strand / mismatches sit in
+// `sm` (3 words per candidate, owned by the warp).  Needs W::WIDTH == 32, max_mismatches <= 127.
+constexpr uint32_t PAIR_WIDE_MIN = 256;   // k1 * k2 above which the warp takes the pair
+template <class W, class GetCand>
+WALT_HD PairResult pair_candidates_wide(W& w, const ChromView& cv, GetCand get1, uint32_t n1, uint32_t len1,
+                                        GetCand get2, uint32_t n2, uint32_t len2, uint32_t max_mismatches,
+                                        int32_t frag_range, uint32_t* sm) {
+  PairResult r; r.best_times = 0u; r.best_i = -1; r.best_j = -1; r.frag = 0;
+  const uint32_t lane = w.lane();
+  uint32_t* start2 = sm; uint32_t* key2 = sm + n2; uint32_t* pos2 = sm + 2u * n2;
+  for (uint32_t j = lane; j < n2; j += 32u) {
+    const RankedCand bb = get2(j);
+    const uint32_t c2 = chrom_of(cv.starts, cv.n_chr, bb.pos);
+    uint32_t s2, e2;
+    forward_position(cv.starts, bb.pos, bb.strand, c2, len2, s2, e2);
+    start2[j] = s2; key2[j] = (c2 << 8) | (bb.strand == '+' ? 0x80u : 0u) | bb.mm; pos2[j] = bb.pos;
+  }
+  w.sync();
+  const uint32_t rounds = (n1 + 31u) / 32u;
+  // visit(i, j, sum, frag) for every valid pair of this lane's candidates with sum <= limit (== limit if exact)
+  auto scan = [&](uint32_t limit, bool exact, auto visit) {
+    for (uint32_t k = 0; k < rounds; ++k) {
+      const uint32_t i = 32u * k + lane;
+      if (i >= n1) continue;
+      const RankedCand a = get1(i);
+      if (a.mm > limit) continue;
+      const uint32_t c1 = chrom_of(cv.starts, cv.n_chr, a.pos);
+      uint32_t s1, e1;
+      forward_position(cv.starts, a.pos, a.strand, c1, len1, s1, e1);
+      const uint32_t want = (c1 << 8) | (a.strand == '+' ? 0u : 0x80u);   // same chromosome, the other strand
+      for (int32_t j = (int32_t)n2 - 1; j >= 0; --j) {
+        const uint32_t kj = key2[j];
+        const uint32_t sum = a.mm + (kj & 0x7Fu);
+        if (sum > limit) break;                       // mismatches only grow towards slot 0
+        if ((kj & ~0x7Fu) != want || (exact && sum != limit)) continue;
+        const uint32_t s2 = start2[j];
+        const int32_t frag = a.strand == '+' ? (int32_t)(s2 + len2 - s1) : (int32_t)(e1 - s2);
+        if (frag <= 0 || frag > frag_range) continue;
+        visit(i, (uint32_t)j, sum, frag);
+      }
+    }
+  };
+  uint32_t mn = NO_HIT;
+  scan(max_mismatches, false, [&](uint32_t, uint32_t, uint32_t sum, int32_t) { mn = sum < mn ? sum : mn; });
+  const uint32_t best = w.reduce_min(mn);
+  if (best == NO_HIT) { w.sync(); return r; }
+  uint32_t first = NO_HIT;
+  scan(best, true, [&](uint32_t i, uint32_t j, uint32_t, int32_t) {
+    const uint32_t order = (n1 - 1u - i) * n2 + (n2 - 1u - j);
+    first = order < first ? order : first;
+  });
+  const uint32_t F = w.reduce_min(first);
+  uint64_t best_pos = 0;
+  if (best < max_mismatches) best_pos = ((uint64_t)get1(n1 - 1u - F / n2).pos << 32) + pos2[n2 - 1u - F % n2];
+  uint32_t cnt = 0u, last_inv = NO_HIT;   // last_inv = ~(largest counted order)
+  scan(best, true, [&](uint32_t i, uint32_t j, uint32_t, int32_t) {
+    if ((((uint64_t)get1(i).pos << 32) + pos2[j]) == best_pos) return;
+    const uint32_t order = (n1 - 1u - i) * n2 + (n2 - 1u - j);
+    ++cnt;
+    last_inv = ~order < last_inv ? ~order : last_inv;
+  });
+  const uint32_t total = w.reduce_add(cnt);
+  const uint32_t L = ~w.reduce_min(last_inv);
+  w.sync();   // `sm` is reused by the warp's next pair
+  r.best_times = total + (best < max_mismatches ? 1u : 0u);
+  if (r.best_times == 0u) return r;
+  const uint32_t win = total ? L : F;
+  r.best_i = (int32_t)(n1 - 1u - win / n2); r.best_j = (int32_t)(n2 - 1u - win % n2);
+  {  // fragment length of the reported pair (GetFragmentLength, paired.cpp:320-331)
+    const RankedCand a = get1((uint32_t)r.best_i), bb = get2((uint32_t)r.best_j);
+    const uint32_t c1 = chrom_of(cv.starts, cv.n_chr, a.pos), c2 = chrom_of(cv.starts, cv.n_chr, bb.pos);
+    uint32_t s1, e1, s2, e2;
+    forward_position(cv.starts, a.pos, a.strand, c1, len1, s1, e1);
+    forward_position(cv.starts, bb.pos, bb.strand, c2, len2, s2, e2);
+    r.frag = a.strand == '+' ? (int32_t)(e2 - s1) : (int32_t)(e1 - s2);
   }
   return r;
 }

@@ -279,6 +279,8 @@ struct SeArgs {
   uint32_t* flags;        // [0] non-ACGT
   uint32_t* queue;        // [0] work-queue head, [1] number of parked reads, [2] queue head of the kernel that takes them over (zeroed before launch)
   uint32_t* parked;       // read numbers of the parked reads (MODE 1 writes, MODE 2 reads)
+  uint32_t* lit;          // literal regions of the first lit_cap parked reads (lit_kernel writes, MODE 2 reads)
+  uint32_t lit_cap;
   unsigned long long* counters;  // optional
 };
 
@@ -287,7 +289,7 @@ struct SeArgs {
 // bucket) is dropped and its number appended to the parked list, so that the sub-warp groups never
 // leave the converged fast path.  MAP_TAKE (a whole warp per read): maps the parked reads, repeats
 // streamed through the warp-wide quad verification (verify_run_wide, walt_core.cuh).
-enum : int { MAP_ALL = 0, MAP_PARK = 1, MAP_TAKE = 2 };
+enum : int { MAP_ALL = 0, MAP_PARK = 1, MAP_TAKE = 2, MAP_TAKE3 = 3 };   // MAP_TAKE3: experiment, 3 CTAs per SM (80 registers)
 constexpr uint32_t TAKE_BLOCKS_PER_SM = 2;   // the take-over kernels get 128 registers
 
 // The groups of a warp take consecutive reads with one queue ticket and walk the read loop
@@ -369,10 +371,35 @@ __device__ __forceinline__ void park_reads(const HwGroup<WD>& w, bool parked, ui
   if (parked && w.lane() == 0u) list[at + (uint32_t)__popc(pm & ((1u << l) - 1u))] = r;
 }
 
+// Between the two: one THREAD per parked read replays the literal IndexRegion searches of its lookups
+// (literal_regions, walt_core.cuh), so that the long chains of dependent loads of tens of thousands of
+// reads are in flight together instead of one per warp.
+template <bool PACKED, class Args>
+__global__ void __launch_bounds__(128)
+lit_kernel(const __grid_constant__ Args a) {
+  uint32_t n = *reinterpret_cast<volatile const uint32_t*>(a.queue + 1);
+  if (n > a.lit_cap) n = a.lit_cap;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    uint32_t len;
+    const char* seq = read_at<PACKED>(a, a.parked[t], len);
+    uint64_t R[MAX_WORDS];
+    uint32_t out[LIT_WORDS];
+    if (len <= MAX_READ_LEN && pack_read_serial<PACKED>(seq, len, a.ag != 0u, R)) {
+      literal_regions(a.ix, a.cv.genome_len, a.p3, a.cfg, R, len, out);
+    } else {   // the take-over kernel reports the bad read
+      for (uint32_t i = 0; i < LIT_WORDS; ++i) out[i] = (i & 1u) ? 0u : LIT_NONE;
+    }
+    uint4* dst = reinterpret_cast<uint4*>(a.lit + (size_t)t * LIT_WORDS);
+    dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+    dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+    dst[2] = make_uint4(out[8], out[9], out[10], out[11]);
+  }
+}
+
 template <uint32_t WD, bool PACKED, int MODE>
-__global__ void __launch_bounds__(BLOCK_THREADS, MODE == MAP_TAKE ? TAKE_BLOCKS_PER_SM : MIN_BLOCKS_PER_SM)
+__global__ void __launch_bounds__(BLOCK_THREADS, MODE == MAP_TAKE ? TAKE_BLOCKS_PER_SM : MODE == MAP_TAKE3 ? 3 : MIN_BLOCKS_PER_SM)
 se_map_kernel(const __grid_constant__ SeArgs a) {
-  static_assert(MODE != MAP_TAKE || WD == 32u, "parked reads are taken over by whole warps");
+  static_assert(MODE < MAP_TAKE || WD == 32u, "parked reads are taken over by whole warps");
   extern __shared__ uint64_t smem[];
   __shared__ BlockTally tally;
   tally_init(tally);
@@ -383,8 +410,12 @@ se_map_kernel(const __grid_constant__ SeArgs a) {
   uint32_t cached_len = 0;
   Counters ctr{0u, 0u, 0u};
   bool bad = false;
-  const uint32_t n = MODE == MAP_TAKE ? *reinterpret_cast<volatile const uint32_t*>(a.queue + 1) : a.n;
-  uint32_t* const queue = MODE == MAP_TAKE ? a.queue + 2 : a.queue;
+  uint32_t n = a.n;
+  if (MODE >= MAP_TAKE) {
+    n = *reinterpret_cast<volatile const uint32_t*>(a.queue + 1);   // what the first kernel parked
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.counters && n) atomicAdd(a.counters + 3, (unsigned long long)n);
+  }
+  uint32_t* const queue = MODE >= MAP_TAKE ? a.queue + 2 : a.queue;
   for (uint32_t round = TICKET_ROUNDS, base = 0;; ++round) {
     if (round == TICKET_ROUNDS) { base = next_ticket<WD>(queue); round = 0; }
     const uint32_t first = base + round * (32u / WD);
@@ -392,12 +423,16 @@ se_map_kernel(const __grid_constant__ SeArgs a) {
     uint32_t r = first + (threadIdx.x & 31u) / WD;
     bool parked = false;
     if (r < n) {
-      if (MODE == MAP_TAKE) r = a.parked[r];
+      const uint32_t* lit = nullptr;
+      if (MODE >= MAP_TAKE) {
+        if (r < a.lit_cap) lit = a.lit + (size_t)r * LIT_WORDS;
+        r = a.parked[r];
+      }
       uint32_t len;
       const char* seq = read_at<PACKED>(a, r, len);
       BestState st;
       const MapStatus ms = map_read_se<HwGroup<WD>, PACKED, MODE == MAP_PARK>(w, a.ix, a.cv, a.p3, a.cfg, seq, len, a.ag != 0u,
-                                                                            a.max_mismatches, sc, cached_len, st, ctr);
+                                                                            a.max_mismatches, sc, cached_len, st, ctr, lit);
       bad |= ms == MAP_BAD;
       parked = ms == MAP_PARKED;
       if (lane == 0 && !parked) {
@@ -436,15 +471,17 @@ struct PeArgs {
   uint32_t* flags;
   uint32_t* queue;        // see SeArgs
   uint32_t* parked;
+  uint32_t* lit;
+  uint32_t lit_cap;
   unsigned long long* counters;
 };
 
 // Two-phase form, first phase: PairEndMapping (paired.cpp:106-201) for one mate batch with the
 // heap-changing candidates logged (LogSink, walt_core.cuh); pe_heap_kernel finishes the job.
 template <uint32_t WD, bool PACKED, int MODE>
-__global__ void __launch_bounds__(BLOCK_THREADS, MODE == MAP_TAKE ? TAKE_BLOCKS_PER_SM : MIN_BLOCKS_PER_SM)
+__global__ void __launch_bounds__(BLOCK_THREADS, MODE == MAP_TAKE ? TAKE_BLOCKS_PER_SM : MODE == MAP_TAKE3 ? 3 : MIN_BLOCKS_PER_SM)
 pe_log_kernel(const __grid_constant__ PeArgs a) {
-  static_assert(MODE != MAP_TAKE || WD == 32u, "parked reads are taken over by whole warps");
+  static_assert(MODE < MAP_TAKE || WD == 32u, "parked reads are taken over by whole warps");
   extern __shared__ uint64_t smem[];
   __shared__ BlockTally tally;
   tally_init(tally);
@@ -458,8 +495,12 @@ pe_log_kernel(const __grid_constant__ PeArgs a) {
   uint32_t cached_len = 0;
   Counters ctr{0u, 0u, 0u};
   bool bad = false;
-  const uint32_t n = MODE == MAP_TAKE ? *reinterpret_cast<volatile const uint32_t*>(a.queue + 1) : a.n;
-  uint32_t* const queue = MODE == MAP_TAKE ? a.queue + 2 : a.queue;
+  uint32_t n = a.n;
+  if (MODE >= MAP_TAKE) {
+    n = *reinterpret_cast<volatile const uint32_t*>(a.queue + 1);   // what the first kernel parked
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.counters && n) atomicAdd(a.counters + 3, (unsigned long long)n);
+  }
+  uint32_t* const queue = MODE >= MAP_TAKE ? a.queue + 2 : a.queue;
   for (uint32_t round = TICKET_ROUNDS, base = 0;; ++round) {
     if (round == TICKET_ROUNDS) { base = next_ticket<WD>(queue); round = 0; }
     const uint32_t first = base + round * (32u / WD);
@@ -467,13 +508,17 @@ pe_log_kernel(const __grid_constant__ PeArgs a) {
     uint32_t r = first + (threadIdx.x & 31u) / WD;
     bool parked = false;
     if (r < n) {
-      if (MODE == MAP_TAKE) r = a.parked[r];
+      const uint32_t* lit = nullptr;
+      if (MODE >= MAP_TAKE) {
+        if (r < a.lit_cap) lit = a.lit + (size_t)r * LIT_WORDS;
+        r = a.parked[r];
+      }
       uint32_t len;
       const char* seq = read_at<PACKED>(a, r, len);
       uint32_t n_log = 0;
       const MapStatus ms = map_read_pe_logged<HwGroup<WD>, PACKED, MODE == MAP_PARK>(
           w, a.ix, a.cv, a.p3, a.cfg, seq, len, a.ag != 0u, a.max_mismatches, a.top_k, sc, cached_len,
-          a.log + (size_t)r * a.log_slots, hist, n_log, ctr);
+          a.log + (size_t)r * a.log_slots, hist, n_log, ctr, lit);
       bad |= ms == MAP_BAD;
       parked = ms == MAP_PARKED;
       if (lane == 0 && !parked) a.n_log[r] = n_log;
@@ -494,29 +539,106 @@ struct HeapArgs {
   walt_cand* ranked[2];
   uint32_t* n_ranked[2];
   HeapEntry* heaps;
+  const uint32_t* parked[2];     // parked-read lists of the two mate launches (NULL: nothing was parked)
+  const uint32_t* n_parked[2];
   uint32_t n, top_k, log_slots;
   uint32_t zero_fill;     // see PeArgs
 };
 
-template <uint32_t LOCAL_CAP>
-__global__ void __launch_bounds__(128)
-pe_heap_kernel(const __grid_constant__ HeapArgs a) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= 2u * a.n) return;
-  const uint32_t mate = t >= a.n ? 1u : 0u, r = t - mate * a.n;
-  HeapEntry local[LOCAL_CAP ? LOCAL_CAP : 1u];
-  HeapEntry* heap = LOCAL_CAP ? local : a.heaps + (size_t)t * a.top_k;
-  uint32_t size = 0;
-  replay_heap_log(a.log[mate] + (size_t)r * a.log_slots, a.n_log[mate][r], a.top_k, heap, size);
-  walt_cand* dst = a.ranked[mate] + (size_t)r * a.top_k;
-  uint32_t c = 0;
-  while (size) {
-    const HeapEntry e = heap_pop(heap, size);
-    walt_cand o;
-    o.genome_pos = e.pos; o.mismatch = he_mm(e); o.strand = (e.mm_strand & 0x10000u) ? '-' : '+';
-    o.pad[0] = o.pad[1] = o.pad[2] = 0;
-    dst[c++] = o;
+// Work items: [0, 2n) every read of both mates whose log is short (reads that were not parked
+// log at most LOOKUP_LANES * LANE_RUN_CAP events); [2n, 2n + parked) the parked reads, i.e. the long
+// logs, next to each other -- so that the lanes of a warp replay logs of similar length.
+constexpr uint32_t HEAP_BLOCK = 128;
+constexpr uint32_t SHORT_LOG = LOOKUP_LANES * LANE_RUN_CAP;
+// one thread's heap inside a block-wide array: slot i of thread t at [i * HEAP_BLOCK + t] (8-byte
+// entries: a warp's accesses never conflict, whatever slots its lanes are at)
+struct StridedHeap {
+  HeapEntry* base;
+  __device__ __forceinline__ HeapEntry& operator[](uint32_t i) const { return base[i * HEAP_BLOCK]; }
+};
+template <class H>
+__device__ __forceinline__ void sift_up_g(H a, uint32_t hole, uint32_t top, HeapEntry v) {
+  while (hole > top) {
+    const uint32_t parent = (hole - 1u) >> 1;
+    const HeapEntry pe = a[parent];
+    if (!(he_mm(pe) < he_mm(v))) break;
+    a[hole] = pe;
+    hole = parent;
   }
+  a[hole] = v;
+}
+template <class H>
+__device__ __forceinline__ void adjust_g(H a, uint32_t hole, uint32_t len, HeapEntry v) {   // stl_heap.h:224-249
+  const uint32_t top = hole;
+  uint32_t child = hole;
+  while (len >= 2u && child < (len - 1u) / 2u) {
+    child = 2u * (child + 1u);
+    HeapEntry c = a[child];
+    const HeapEntry d = a[child - 1u];
+    if (he_mm(c) < he_mm(d)) { --child; c = d; }
+    a[hole] = c;
+    hole = child;
+  }
+  if ((len & 1u) == 0u && len >= 2u && child == (len - 2u) / 2u) {
+    child = 2u * (child + 1u);
+    a[hole] = a[child - 1u];
+    hole = child - 1u;
+  }
+  sift_up_g(a, hole, top, v);
+}
+template <class H>
+__device__ __forceinline__ void push_bounded_g(H a, uint32_t& size, uint32_t cap, HeapEntry v) {   // paired.hpp:60-67
+  if (size < cap) {
+    ++size;
+    sift_up_g(a, size - 1u, 0u, v);
+  } else if (he_mm(v) < he_mm(a[0])) {
+    const uint32_t n = size;
+    if (n > 1u) { const HeapEntry last = a[n - 1u]; a[n - 1u] = a[0]; adjust_g(a, 0u, n - 1u, last); }
+    sift_up_g(a, n - 1u, 0u, v);
+  }
+}
+template <class H>
+__device__ __forceinline__ HeapEntry pop_g(H a, uint32_t& size) {
+  const HeapEntry top = a[0];
+  const uint32_t n = size;
+  if (n > 1u) { const HeapEntry last = a[n - 1u]; a[n - 1u] = a[0]; adjust_g(a, 0u, n - 1u, last); }
+  size = n - 1u;
+  return top;
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(HEAP_BLOCK)
+pe_heap_kernel(const __grid_constant__ HeapArgs a) {
+  extern __shared__ HeapEntry heap_sm[];   // SMEM: top_k * HEAP_BLOCK entries
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t mate, r;
+  if (t < 2u * a.n) {
+    mate = t >= a.n ? 1u : 0u; r = t - mate * a.n;
+    if (a.parked[0] && a.n_log[mate][r] > SHORT_LOG) return;      // a parked read: below
+  } else {
+    if (!a.parked[0]) return;
+    uint32_t u = t - 2u * a.n;
+    const uint32_t p0 = *a.n_parked[0], p1 = *a.n_parked[1];
+    if (u < p0) { mate = 0u; } else { u -= p0; if (u >= p1) return; mate = 1u; }
+    r = a.parked[mate][u];
+    if (a.n_log[mate][r] <= SHORT_LOG) return;                    // done above
+  }
+  const HeapEntry* log = a.log[mate] + (size_t)r * a.log_slots;
+  const uint32_t n_log = a.n_log[mate][r];
+  walt_cand* dst = a.ranked[mate] + (size_t)r * a.top_k;
+  uint32_t size = 0, c = 0;
+  auto run = [&](auto heap) {
+    for (uint32_t i = 0; i < n_log; ++i) push_bounded_g(heap, size, a.top_k, log[i]);
+    while (size) {
+      const HeapEntry e = pop_g(heap, size);
+      walt_cand o;
+      o.genome_pos = e.pos; o.mismatch = he_mm(e); o.strand = (e.mm_strand & 0x10000u) ? '-' : '+';
+      o.pad[0] = o.pad[1] = o.pad[2] = 0;
+      dst[c++] = o;
+    }
+  };
+  if (SMEM) run(StridedHeap{heap_sm + threadIdx.x});
+  else run(a.heaps + ((size_t)mate * a.n + r) * a.top_k);
   a.n_ranked[mate][r] = c;
   if (a.zero_fill) {   // whole-array compares and copies on the host side are deterministic
     uint32_t* z = reinterpret_cast<uint32_t*>(dst + c);
@@ -596,6 +718,7 @@ struct PairArgs {
   uint32_t n, top_k, max_mismatches;
   int32_t frag_range;
   uint32_t swap;
+  uint32_t wide;             // long lists are paired by the whole warp (needs max_mismatches <= 127)
   walt_pair* pairs;          // may be NULL
   walt_pe_result* compact;   // may be NULL
 };
@@ -606,15 +729,44 @@ __device__ __forceinline__ walt_best to_best(const BestState& b) {
   return o;
 }
 
-__global__ void pair_kernel(const __grid_constant__ PairArgs a) {
+// Pairs with short lists are paired by their own thread; the pairs of a warp whose k1 x k2 loop is
+// long (both mates in repeats) are then taken one after the other by the whole warp
+// (pair_candidates_wide): a lone lane in a 2500-iteration loop costs the warp as much as 32 of them.
+constexpr uint32_t PAIR_BLOCK = 128;
+__global__ void __launch_bounds__(PAIR_BLOCK)
+pair_kernel(const __grid_constant__ PairArgs a) {
+  extern __shared__ uint32_t pair_sm[];   // 3 * top_k words per warp (wide path only)
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= a.n) return;
-  const uint32_t len1 = a.ulen1 ? a.ulen1 : (uint32_t)(a.offs1[p + 1] - a.offs1[p]);
-  const uint32_t len2 = a.ulen2 ? a.ulen2 : (uint32_t)(a.offs2[p + 1] - a.offs2[p]);
-  const walt_cand* c1 = a.r1 + (size_t)p * a.top_k;
-  const walt_cand* c2 = a.r2 + (size_t)p * a.top_k;
-  const uint32_t k1 = a.n1[p], k2 = a.n2[p];
-  PairResult r = pair_candidates(a.cv, GetRanked{c1}, k1, len1, GetRanked{c2}, k2, len2, a.max_mismatches, a.frag_range);
+  const bool live = p < a.n;
+  uint32_t len1 = 0, len2 = 0, k1 = 0, k2 = 0;
+  const walt_cand* c1 = a.r1 + (size_t)(live ? p : 0u) * a.top_k;
+  const walt_cand* c2 = a.r2 + (size_t)(live ? p : 0u) * a.top_k;
+  if (live) {
+    len1 = a.ulen1 ? a.ulen1 : (uint32_t)(a.offs1[p + 1] - a.offs1[p]);
+    len2 = a.ulen2 ? a.ulen2 : (uint32_t)(a.offs2[p + 1] - a.offs2[p]);
+    k1 = a.n1[p]; k2 = a.n2[p];
+  }
+  const bool wide = a.wide && k1 * k2 > PAIR_WIDE_MIN;
+  PairResult r; r.best_times = 0u; r.best_i = -1; r.best_j = -1; r.frag = 0;
+  if (live && !wide)
+    r = pair_candidates(a.cv, GetRanked{c1}, k1, len1, GetRanked{c2}, k2, len2, a.max_mismatches, a.frag_range);
+  uint32_t todo = __ballot_sync(0xFFFFFFFFu, wide);
+  if (todo) {
+    HwGroup<32> w;
+    uint32_t* sm = pair_sm + (threadIdx.x / 32u) * 3u * a.top_k;
+    const uint32_t l = threadIdx.x & 31u;
+    while (todo) {
+      const int src = __ffs((int)todo) - 1;
+      todo &= todo - 1u;
+      const uint32_t q = __shfl_sync(0xFFFFFFFFu, p, src);
+      const PairResult t = pair_candidates_wide(w, a.cv, GetRanked{a.r1 + (size_t)q * a.top_k}, __shfl_sync(0xFFFFFFFFu, k1, src),
+                                                __shfl_sync(0xFFFFFFFFu, len1, src), GetRanked{a.r2 + (size_t)q * a.top_k},
+                                                __shfl_sync(0xFFFFFFFFu, k2, src), __shfl_sync(0xFFFFFFFFu, len2, src),
+                                                a.max_mismatches, a.frag_range, sm);
+      if ((int)l == src) r = t;
+    }
+  }
+  if (!live) return;
   walt_pair o; o.best_times = r.best_times; o.frag_len = r.frag;
   o.best_i = a.swap ? r.best_j : r.best_i; o.best_j = a.swap ? r.best_i : r.best_j;
   if (a.pairs) a.pairs[p] = o;
@@ -698,7 +850,7 @@ static void fill_common(walt_engine* e, Args& a, const ReadSrc& src, uint32_t n,
   a.seqs = src.d_seqs; a.offs = src.d_offs; a.seq_base = src.seq_base; a.n = n; a.uniform_len = src.uniform_len;
   a.read_base = src.read_base;
   a.nw_max = std::max<uint32_t>(1u, (src.max_len + 31u) / 32u);
-  a.ag = ag ? 1u : 0u; a.max_mismatches = m; a.flags = e->d_flags; a.queue = d_queue; a.parked = nullptr;
+  a.ag = ag ? 1u : 0u; a.max_mismatches = m; a.flags = e->d_flags; a.queue = d_queue; a.parked = nullptr; a.lit = nullptr; a.lit_cap = 0u;
   a.counters = e->d_counters;
 }
 
@@ -713,16 +865,35 @@ static int take_grid(walt_engine* e, K kernel, size_t smem, uint32_t* grid) {
   return WALT_OK;
 }
 
-// d_parked != NULL (room for n read numbers): reads that need their whole group are parked by the
-// first kernel and mapped by a second one, a warp per read (see MAP_PARK / MAP_TAKE)
+// The second and third kernel of a launch that parks reads (see MAP_PARK / MAP_TAKE, lit_kernel)
+template <class Args>
+static int launch_take(walt_engine* e, const Args& a, bool packed, void (*take)(Args), size_t smem, cudaStream_t st) {
+  int rc;
+  uint32_t grid = 0;
+  if (a.lit_cap) {
+    void (*lk)(Args) = packed ? lit_kernel<true, Args> : lit_kernel<false, Args>;
+    lk<<<(uint32_t)e->sm_count * 8u, 128, 0, st>>>(a);
+    WALT_CUDA_TRY(cudaGetLastError());
+    e->stats.n_kernel_launches++;
+  }
+  if ((rc = take_grid(e, take, smem, &grid))) return rc;
+  take<<<grid, BLOCK_THREADS, smem, st>>>(a);
+  WALT_CUDA_TRY(cudaGetLastError());
+  e->stats.n_kernel_launches++;
+  return WALT_OK;
+}
+
+// park != NULL (list: room for n read numbers; lit: LIT_WORDS words for each of the first lit_cap of
+// them): reads that need their whole group are parked by the first kernel and mapped by a second
+// one, a warp per read
 static int launch_se(walt_engine* e, const ReadSrc& src, uint32_t n, int ag, uint32_t m, uint32_t b, walt_best* d_out,
-                     uint32_t* d_queue, uint32_t* d_parked, cudaStream_t st, uint32_t share = 1) {
+                     uint32_t* d_queue, const ParkBuf* pk, cudaStream_t st, uint32_t share = 1) {
   if (src.max_len > MAX_READ_LEN) return fail(WALT_EINVAL, "read longer than 1024 bases");
   SeArgs a;
   fill_common(e, a, src, n, ag, m, b, d_queue);
   a.out = d_out;
-  const bool park = e->defer && d_parked != nullptr;
-  a.parked = park ? d_parked : nullptr;
+  const bool park = e->defer && pk != nullptr;
+  if (park) { a.parked = pk->list; a.lit = pk->lit; a.lit_cap = pk->lit_cap; }
   const uint32_t wd = e->group_width;
   const size_t smem = se_smem_bytes(a.nw_max, wd);
   uint32_t grid = 0;
@@ -739,28 +910,25 @@ static int launch_se(walt_engine* e, const ReadSrc& src, uint32_t n, int ag, uin
   kernel<<<grid, BLOCK_THREADS, smem, st>>>(a);
   WALT_CUDA_TRY(cudaGetLastError());
   e->stats.n_kernel_launches++;
-  if (park) {
-    void (*take)(SeArgs) = src.packed ? se_map_kernel<32, true, MAP_TAKE> : se_map_kernel<32, false, MAP_TAKE>;
-    const size_t smem2 = se_smem_bytes(a.nw_max, 32u);
-    if ((rc = take_grid(e, take, smem2, &grid))) return rc;
-    take<<<grid, BLOCK_THREADS, smem2, st>>>(a);
-    WALT_CUDA_TRY(cudaGetLastError());
-    e->stats.n_kernel_launches++;
-  }
+  if (park)
+    return launch_take(e, a, src.packed,
+                       e->take_blocks == 3 ? (src.packed ? se_map_kernel<32, true, MAP_TAKE3> : se_map_kernel<32, false, MAP_TAKE3>)
+                                           : (src.packed ? se_map_kernel<32, true, MAP_TAKE> : se_map_kernel<32, false, MAP_TAKE>),
+                       se_smem_bytes(a.nw_max, 32u), st);
   return WALT_OK;
 }
 
 // first phase of the two-phase form for one mate
 static int launch_pe_log(walt_engine* e, const ReadSrc& src, uint32_t n, int ag, uint32_t m, uint32_t b, uint32_t top_k,
-                         HeapEntry* d_log, uint32_t* d_nlog, uint32_t* d_queue, uint32_t* d_parked, cudaStream_t st) {
+                         HeapEntry* d_log, uint32_t* d_nlog, uint32_t* d_queue, const ParkBuf* pk, cudaStream_t st) {
   // (zero_fill belongs to the second phase here)
   if (src.max_len > MAX_READ_LEN) return fail(WALT_EINVAL, "read longer than 1024 bases");
   PeArgs a;
   fill_common(e, a, src, n, ag, m, b, d_queue);
   a.top_k = top_k; a.ranked = nullptr; a.n_ranked = nullptr;
   a.log = d_log; a.n_log = d_nlog; a.log_slots = pe_log_slots(top_k, m); a.zero_fill = 0u;
-  const bool park = e->defer && d_parked != nullptr;
-  a.parked = park ? d_parked : nullptr;
+  const bool park = e->defer && pk != nullptr;
+  if (park) { a.parked = pk->list; a.lit = pk->lit; a.lit_cap = pk->lit_cap; }
   const uint32_t wd = e->group_width;
   const size_t smem = pe_log_smem_bytes(a.nw_max, wd);
   uint32_t grid = 0;
@@ -777,14 +945,11 @@ static int launch_pe_log(walt_engine* e, const ReadSrc& src, uint32_t n, int ag,
   kernel<<<grid, BLOCK_THREADS, smem, st>>>(a);
   WALT_CUDA_TRY(cudaGetLastError());
   e->stats.n_kernel_launches++;
-  if (park) {
-    void (*take)(PeArgs) = src.packed ? pe_log_kernel<32, true, MAP_TAKE> : pe_log_kernel<32, false, MAP_TAKE>;
-    const size_t smem2 = pe_log_smem_bytes(a.nw_max, 32u);
-    if ((rc = take_grid(e, take, smem2, &grid))) return rc;
-    take<<<grid, BLOCK_THREADS, smem2, st>>>(a);
-    WALT_CUDA_TRY(cudaGetLastError());
-    e->stats.n_kernel_launches++;
-  }
+  if (park)
+    return launch_take(e, a, src.packed,
+                       e->take_blocks == 3 ? (src.packed ? pe_log_kernel<32, true, MAP_TAKE3> : pe_log_kernel<32, false, MAP_TAKE3>)
+                                           : (src.packed ? pe_log_kernel<32, true, MAP_TAKE> : pe_log_kernel<32, false, MAP_TAKE>),
+                       pe_log_smem_bytes(a.nw_max, 32u), st);
   return WALT_OK;
 }
 
@@ -823,12 +988,21 @@ static int reserve_bytes(void** p, size_t* cap, size_t need) {
   return reserve(reinterpret_cast<char**>(p), cap, need);
 }
 
+// room for the parked reads of a launch over n reads
+static int reserve_park(walt_engine* e, ParkBuf* pk, uint32_t n) {
+  pk->lit_limit = e->lit_ahead ? LIT_CAP_MAX : 0u;
+  int rc;
+  if ((rc = reserve(&pk->list, &pk->list_cap, (size_t)n))) return rc;
+  pk->lit_cap = std::min<uint32_t>(n, pk->lit_limit);
+  return reserve(&pk->lit, &pk->lit_words, (size_t)pk->lit_cap * LIT_WORDS);
+}
+
 static int fetch_status(walt_engine* e) {
   uint32_t f = 0;
   WALT_CUDA_TRY(cudaMemcpy(&f, e->d_flags, 4, cudaMemcpyDeviceToHost));
-  unsigned long long c[3];
+  unsigned long long c[4];
   WALT_CUDA_TRY(cudaMemcpy(c, e->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
-  e->stats.n_lookups = c[0]; e->stats.n_candidates = c[1]; e->stats.n_literal = c[2];
+  e->stats.n_lookups = c[0]; e->stats.n_candidates = c[1]; e->stats.n_literal = c[2]; e->stats.n_parked = c[3];
   if (f & 1u) {
     cudaMemset(e->d_flags, 0, 4);
     return fail(WALT_ENONACGT, "[ERROR: NON-ACGT NUCLEOTIDE] in a read handed to the mapping engine");
@@ -907,14 +1081,18 @@ int walt_engine_create(walt_engine** out, int device) {
   if (const char* v = getenv("WALT_PE_SIDE")) e->pe_side = atoi(v);
   if (const char* v = getenv("WALT_PE_LOGGED")) e->pe_logged = atoi(v);
   if (const char* v = getenv("WALT_DEFER")) e->defer = atoi(v);
+  if (const char* v = getenv("WALT_TAKE_BLOCKS")) e->take_blocks = atoi(v);
+  if (const char* v = getenv("WALT_LIT")) e->lit_ahead = atoi(v);
+  if (const char* v = getenv("WALT_PAIR_WIDE")) e->pair_wide = atoi(v);
+  if (const char* v = getenv("WALT_HEAP_SMEM")) e->heap_smem = atoi(v);
   if (const char* v = getenv("WALT_CHUNK_SHARE")) e->chunk_share = (uint32_t)std::max(1, atoi(v));
   if (const char* v = getenv("WALT_L2_FETCH")) WALT_CUDA_TRY(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(v)));
   uint32_t p = 1;
   for (uint32_t i = 0; i <= MAX_DEPTH; ++i) { e->pow3.v[i] = p; p *= 3u; }
   WALT_CUDA_TRY(cudaMalloc(&e->d_flags, N_FLAG_WORDS * 4));
   WALT_CUDA_TRY(cudaMemset(e->d_flags, 0, N_FLAG_WORDS * 4));
-  WALT_CUDA_TRY(cudaMalloc(&e->d_counters, 3 * 8));
-  WALT_CUDA_TRY(cudaMemset(e->d_counters, 0, 3 * 8));
+  WALT_CUDA_TRY(cudaMalloc(&e->d_counters, 4 * 8));
+  WALT_CUDA_TRY(cudaMemset(e->d_counters, 0, 4 * 8));
   for (auto& s : e->slot) {
     WALT_CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     WALT_CUDA_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
@@ -933,14 +1111,16 @@ void walt_engine_destroy(walt_engine* e) {
   for (auto& s : e->sub) s.release();
   for (auto& s : e->slot) {
     cudaFree(s.d_seqs); cudaFree(s.d_offs); cudaFree(s.d_out); cudaFree(s.d_seqs2); cudaFree(s.d_offs2);
-    cudaFree(s.d_pe); cudaFree(s.d_park[0]); cudaFree(s.d_park[1]);
+    cudaFree(s.d_pe);
+    for (auto& p : s.park) { cudaFree(p.list); cudaFree(p.lit); }
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.done) cudaEventDestroy(s.done);
   }
   if (e->side_stream) cudaStreamDestroy(e->side_stream);
   if (e->fork) cudaEventDestroy(e->fork);
   if (e->join) cudaEventDestroy(e->join);
-  cudaFree(e->d_starts); cudaFree(e->d_flags); cudaFree(e->d_counters); cudaFree(e->dev_park[0]); cudaFree(e->dev_park[1]);
+  cudaFree(e->d_starts); cudaFree(e->d_flags); cudaFree(e->d_counters);
+  for (auto& p : e->dev_park) { cudaFree(p.list); cudaFree(p.lit); }
   delete e;
 }
 
@@ -1257,6 +1437,19 @@ int walt_engine_set_chunk_reads(walt_engine* e, uint32_t n) {
   return WALT_OK;
 }
 
+int walt_engine_device_stats(walt_engine* e, walt_stats* out) {
+  if (!e || !out) return fail(WALT_EINVAL, "bad argument");
+  int rc = ensure_device(e);
+  if (rc) return rc;
+  WALT_CUDA_TRY(cudaDeviceSynchronize());
+  const uint64_t launches = e->stats.n_kernel_launches;
+  if ((rc = fetch_status(e))) return rc;
+  WALT_CUDA_TRY(cudaMemset(e->d_counters, 0, 4 * 8));
+  *out = e->stats;
+  out->n_kernel_launches = launches;
+  return WALT_OK;
+}
+
 int walt_engine_last_stats(const walt_engine* e, walt_stats* out) {
   if (!e || !out) return fail(WALT_EINVAL, "bad argument");
   *out = e->stats;
@@ -1274,9 +1467,9 @@ int walt_engine_map_se_device(walt_engine* e, const void* d_seqs, const void* d_
   if (n == 0) return WALT_OK;
   e->stats.n_kernel_launches = 0;
   const ReadSrc src{(const char*)d_seqs, (const uint64_t*)d_offs, 0, 0, 0, max_read_len, false};
-  if (e->defer && (rc = reserve(&e->dev_park[0], &e->dev_park_cap[0], (size_t)n))) return rc;
+  if (e->defer && (rc = reserve_park(e, &e->dev_park[0], n))) return rc;
   return launch_se(e, src, n, ag_wildcard, max_mismatches, b, (walt_best*)d_out, queue_block(e, QB_SE_DEVICE),
-                   e->defer ? e->dev_park[0] : nullptr, (cudaStream_t)cuda_stream);
+                   e->defer ? &e->dev_park[0] : nullptr, (cudaStream_t)cuda_stream);
 }
 
 // Bytes [*b0, *b1) of a batch buffer that hold reads [r0, r0 + cn): ASCII, or the 2-bit packed
@@ -1293,7 +1486,7 @@ static int map_se_host(walt_engine* e, const char* seqs, const uint64_t* offs, u
   if (rc) return rc;
   if ((rc = check_pair(e, ag_wildcard))) return rc;
   e->stats = walt_stats{};
-  WALT_CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, 3 * 8, e->slot[0].stream));
+  WALT_CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, 4 * 8, e->slot[0].stream));
   WALT_CUDA_TRY(cudaStreamSynchronize(e->slot[0].stream));
   uint32_t k = 0, total_short = 0;
   // chunk size: ASCII batches are PCIe-bound and like a short pipeline fill; packed batches are
@@ -1321,9 +1514,9 @@ static int map_se_host(walt_engine* e, const char* seqs, const uint64_t* offs, u
       WALT_CUDA_TRY(cudaMemcpyAsync(s.d_offs, offs + r0, ((size_t)cn + 1u) * 8u, cudaMemcpyHostToDevice, s.stream));
     }
     const ReadSrc src{s.d_seqs, s.d_offs, offs[r0], sc.uniform_len, 0, sc.max_len, packed};
-    if (e->defer && (rc = reserve(&s.d_park[0], &s.park_cap[0], (size_t)cn))) return rc;
+    if (e->defer && (rc = reserve_park(e, &s.park[0], cn))) return rc;
     if ((rc = launch_se(e, src, cn, ag_wildcard, max_mismatches, b, (walt_best*)s.d_out, queue_block(e, QB_SE_SLOT + k % N_SLOTS),
-                        e->defer ? s.d_park[0] : nullptr, s.stream, e->chunk_share)))
+                        e->defer ? &s.park[0] : nullptr, s.stream, e->chunk_share)))
       return rc;
     WALT_CUDA_TRY(cudaMemcpyAsync(out + r0, s.d_out, (size_t)cn * sizeof(walt_best), cudaMemcpyDeviceToHost, s.stream));
     WALT_CUDA_TRY(cudaEventRecord(s.done, s.stream));
@@ -1345,28 +1538,30 @@ int walt_engine_map_se_packed(walt_engine* e, const uint8_t* packed, const uint6
 
 // ---- paired end ---------------------------------------------------------------------------
 // device layout of one chunk's paired-end scratch inside a slot's d_pe allocation
-constexpr uint32_t HEAP_LOCAL_CAP = 64;   // top_k up to this: pe_heap_kernel keeps its heap in local memory
+// pe_heap_kernel keeps its heaps in shared memory while two blocks fit on an SM (top_k <= 100), else in global scratch
+constexpr uint32_t HEAP_SMEM_TOPK = 100;
+static bool heaps_in_smem(const walt_engine* e, uint32_t top_k) { return e->heap_smem && top_k <= HEAP_SMEM_TOPK; }
 
 static bool pe_two_phase(const walt_engine* e, uint32_t m) { return e->pe_logged && m <= LOG_MAX_MM; }
 
 struct PeScratch {
   walt_pair* pairs; walt_pe_result* compact; walt_cand* r1; walt_cand* r2; uint32_t* n1; uint32_t* n2;
-  // two-phase form: per-mate logs and their lengths, heaps for top_k > HEAP_LOCAL_CAP
+  // two-phase form: per-mate logs and their lengths, heaps when they do not fit shared memory
   HeapEntry* log1; HeapEntry* log2; uint32_t* nlog1; uint32_t* nlog2; HeapEntry* heaps;
 };
 // bytes of scratch one pair needs (sizes the chunks)
-static size_t pe_pair_bytes(uint32_t top_k, uint32_t m, bool two_phase) {
+static size_t pe_pair_bytes(uint32_t top_k, uint32_t m, bool two_phase, bool gheaps) {
   size_t b = sizeof(walt_pe_result) + sizeof(walt_pair) + 2u * (size_t)top_k * sizeof(walt_cand) + 2u * 4u;
   if (two_phase) {
     b += 2u * (size_t)pe_log_slots(top_k, m) * sizeof(HeapEntry) + 2u * 4u;
-    if (top_k > HEAP_LOCAL_CAP) b += 2u * (size_t)top_k * sizeof(HeapEntry);
+    if (gheaps) b += 2u * (size_t)top_k * sizeof(HeapEntry);
   }
   return b;
 }
-static size_t pe_scratch_bytes(uint32_t cn, uint32_t top_k, uint32_t m, bool two_phase) {
-  return (size_t)cn * pe_pair_bytes(top_k, m, two_phase) + 512u;
+static size_t pe_scratch_bytes(uint32_t cn, uint32_t top_k, uint32_t m, bool two_phase, bool gheaps) {
+  return (size_t)cn * pe_pair_bytes(top_k, m, two_phase, gheaps) + 512u;
 }
-static PeScratch carve_pe(void* base, uint32_t cn, uint32_t top_k, uint32_t m, bool two_phase) {
+static PeScratch carve_pe(void* base, uint32_t cn, uint32_t top_k, uint32_t m, bool two_phase, bool gheaps) {
   PeScratch p;
   char* c = (char*)base;
   auto take = [&](size_t bytes) { char* at = c; c += (bytes + 15u) & ~(size_t)15u; return at; };
@@ -1383,7 +1578,7 @@ static PeScratch carve_pe(void* base, uint32_t cn, uint32_t top_k, uint32_t m, b
     p.log2 = (HeapEntry*)take((size_t)cn * slots * sizeof(HeapEntry));
     p.nlog1 = (uint32_t*)take((size_t)cn * 4u);
     p.nlog2 = (uint32_t*)take((size_t)cn * 4u);
-    if (top_k > HEAP_LOCAL_CAP) p.heaps = (HeapEntry*)take(2u * (size_t)cn * top_k * sizeof(HeapEntry));
+    if (gheaps) p.heaps = (HeapEntry*)take(2u * (size_t)cn * top_k * sizeof(HeapEntry));
   }
   return p;
 }
@@ -1391,7 +1586,7 @@ static PeScratch carve_pe(void* base, uint32_t cn, uint32_t top_k, uint32_t m, b
 // both mate kernels + the pairing kernel for one chunk resident on the device
 static int launch_pe_chunk(walt_engine* e, const ReadSrc& m1, const ReadSrc& m2, uint32_t cn, uint32_t m, uint32_t b,
                            uint32_t top_k, int frag_range, int swap, const PeScratch& ps, bool want_pairs,
-                           walt_pe_result* d_compact, uint32_t* q, uint32_t* const* d_parked, cudaStream_t st) {
+                           walt_pe_result* d_compact, uint32_t* q, const ParkBuf* pk, cudaStream_t st) {
   int rc;
   // mate 1: C->T against _CT00/_CT01; mate 2: G->A against _GA10/_GA11 (paired.cpp:642-672).  The
   // two mate kernels are independent: the second runs on a side stream so that its blocks fill
@@ -1403,8 +1598,8 @@ static int launch_pe_chunk(walt_engine* e, const ReadSrc& m1, const ReadSrc& m2,
   }
   const bool two_phase = ps.log1 != nullptr;
   if (two_phase) {
-    if ((rc = launch_pe_log(e, m1, cn, 0, m, b, top_k, ps.log1, ps.nlog1, q, d_parked ? d_parked[0] : nullptr, st))) return rc;
-    if ((rc = launch_pe_log(e, m2, cn, 1, m, b, top_k, ps.log2, ps.nlog2, q + 4, d_parked ? d_parked[1] : nullptr, st2))) return rc;
+    if ((rc = launch_pe_log(e, m1, cn, 0, m, b, top_k, ps.log1, ps.nlog1, q, pk ? pk : nullptr, st))) return rc;
+    if ((rc = launch_pe_log(e, m2, cn, 1, m, b, top_k, ps.log2, ps.nlog2, q + 4, pk ? pk + 1 : nullptr, st2))) return rc;
   } else {
     if ((rc = launch_pe_mate(e, m1, cn, 0, m, b, top_k, ps.r1, ps.n1, q, st, want_pairs))) return rc;
     if ((rc = launch_pe_mate(e, m2, cn, 1, m, b, top_k, ps.r2, ps.n2, q + 4, st2, want_pairs))) return rc;
@@ -1419,9 +1614,21 @@ static int launch_pe_chunk(walt_engine* e, const ReadSrc& m1, const ReadSrc& m2,
     h.ranked[0] = ps.r1; h.ranked[1] = ps.r2; h.n_ranked[0] = ps.n1; h.n_ranked[1] = ps.n2;
     h.heaps = ps.heaps; h.n = cn; h.top_k = top_k; h.log_slots = pe_log_slots(top_k, m);
     h.zero_fill = want_pairs ? 1u : 0u;   // only walt_engine_map_pe hands the lists themselves to the host
-    const uint32_t blocks = (2u * cn + 127u) / 128u;
-    if (top_k <= HEAP_LOCAL_CAP) pe_heap_kernel<HEAP_LOCAL_CAP><<<blocks, 128, 0, st>>>(h);
-    else pe_heap_kernel<0><<<blocks, 128, 0, st>>>(h);
+    const bool parked = pk != nullptr && e->defer;
+    for (int i = 0; i < 2; ++i) {
+      h.parked[i] = parked ? pk[i].list : nullptr;
+      h.n_parked[i] = q + 4 * i + 1;
+    }
+    // SMEM: heaps of top_k entries per thread in shared memory (local memory heaps of 16 resident blocks thrash the L1)
+    const bool smem = ps.heaps == nullptr;
+    const uint32_t blocks = (2u * cn + (parked ? 2u * cn : 0u) + HEAP_BLOCK - 1u) / HEAP_BLOCK;
+    if (smem) {
+      const size_t bytes = (size_t)top_k * HEAP_BLOCK * sizeof(HeapEntry);
+      WALT_CUDA_TRY(cudaFuncSetAttribute(pe_heap_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      pe_heap_kernel<true><<<blocks, HEAP_BLOCK, bytes, st>>>(h);
+    } else {
+      pe_heap_kernel<false><<<blocks, HEAP_BLOCK, 0, st>>>(h);
+    }
     WALT_CUDA_TRY(cudaGetLastError());
     e->stats.n_kernel_launches++;
   }
@@ -1433,7 +1640,8 @@ static int launch_pe_chunk(walt_engine* e, const ReadSrc& m1, const ReadSrc& m2,
   a.r2 = ps.r2; a.n2 = ps.n2; a.offs2 = d_offs2; a.ulen2 = ulen2;
   a.n = cn; a.top_k = top_k; a.max_mismatches = m; a.frag_range = frag_range; a.swap = swap ? 1u : 0u;
   a.pairs = want_pairs ? ps.pairs : nullptr; a.compact = d_compact;
-  pair_kernel<<<(cn + 127u) / 128u, 128, 0, st>>>(a);
+  a.wide = (e->pair_wide && m <= 127u) ? 1u : 0u;
+  pair_kernel<<<(cn + PAIR_BLOCK - 1u) / PAIR_BLOCK, PAIR_BLOCK, (PAIR_BLOCK / 32u) * 3u * top_k * 4u, st>>>(a);
   WALT_CUDA_TRY(cudaGetLastError());
   e->stats.n_kernel_launches++;
   return WALT_OK;
@@ -1448,13 +1656,14 @@ static int map_pe_host(walt_engine* e, const char* seqs1, const uint64_t* offs1,
                        walt_pe_result* compact, uint32_t* n_short1, uint32_t* n_short2) {
   int rc;
   e->stats = walt_stats{};
-  WALT_CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, 3 * 8, e->slot[0].stream));
+  WALT_CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, 4 * 8, e->slot[0].stream));
   WALT_CUDA_TRY(cudaStreamSynchronize(e->slot[0].stream));
   // chunk so that a slot's scratch (ranked lists, and the candidate logs of the two-phase form)
   // stays below ~1.5 GiB
   const bool two_phase = pe_two_phase(e, m);
+  const bool gheaps = two_phase && !heaps_in_smem(e, top_k);
   const uint32_t chunk = std::max<uint32_t>(1024u, (uint32_t)std::min<uint64_t>(e->chunk_reads ? e->chunk_reads : (1u << 18),
-                                                                                (3ull << 29) / pe_pair_bytes(top_k, m, two_phase)));
+                                                                                (3ull << 29) / pe_pair_bytes(top_k, m, two_phase, gheaps)));
   uint32_t k = 0, short1 = 0, short2 = 0;
   AheadScans scans(offs1, offs2, n, chunk);
   for (uint32_t r0 = 0; r0 < n; r0 += chunk, ++k) {
@@ -1473,8 +1682,8 @@ static int map_pe_host(walt_engine* e, const char* seqs1, const uint64_t* offs1,
     chunk_bytes(offs2, r0, cn, packed, &sb2, &se2);
     if ((rc = reserve(&s.d_seqs, &s.seqs_cap, (size_t)(se1 - sb1) + 16u))) return rc;
     if ((rc = reserve(&s.d_seqs2, &s.seqs2_cap, (size_t)(se2 - sb2) + 16u))) return rc;
-    if ((rc = reserve_bytes(&s.d_pe, &s.pe_cap, pe_scratch_bytes(cn, top_k, m, two_phase)))) return rc;
-    const PeScratch ps = carve_pe(s.d_pe, cn, top_k, m, two_phase);
+    if ((rc = reserve_bytes(&s.d_pe, &s.pe_cap, pe_scratch_bytes(cn, top_k, m, two_phase, gheaps)))) return rc;
+    const PeScratch ps = carve_pe(s.d_pe, cn, top_k, m, two_phase, gheaps);
     if (se1 > sb1) WALT_CUDA_TRY(cudaMemcpyAsync(s.d_seqs, seqs1 + sb1, se1 - sb1, cudaMemcpyHostToDevice, s.stream));
     if (se2 > sb2) WALT_CUDA_TRY(cudaMemcpyAsync(s.d_seqs2, seqs2 + sb2, se2 - sb2, cudaMemcpyHostToDevice, s.stream));
     if (!s1.uniform_len) {
@@ -1490,9 +1699,9 @@ static int map_pe_host(walt_engine* e, const char* seqs1, const uint64_t* offs1,
     const ReadSrc m2{s.d_seqs2, s.d_offs2, offs2[r0], s2.uniform_len, 0, s2.max_len, packed};
     if (e->defer && two_phase)
       for (int i = 0; i < 2; ++i)
-        if ((rc = reserve(&s.d_park[i], &s.park_cap[i], (size_t)cn))) return rc;
+        if ((rc = reserve_park(e, &s.park[i], cn))) return rc;
     if ((rc = launch_pe_chunk(e, m1, m2, cn, m, b, top_k, frag_range, swap, ps, pairs != nullptr,
-                              compact ? ps.compact : nullptr, q, e->defer && two_phase ? s.d_park : nullptr, s.stream)))
+                              compact ? ps.compact : nullptr, q, e->defer && two_phase ? s.park : nullptr, s.stream)))
       return rc;
     if (ranked1) {
       const size_t rk = (size_t)cn * top_k * sizeof(walt_cand);
@@ -1587,7 +1796,8 @@ int walt_engine_map_pe_device(walt_engine* e, const void* d_seqs1, const void* d
   WALT_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
   const uint64_t budget = std::max<uint64_t>(s.pe_cap, std::min<uint64_t>(8ull << 30, std::max<uint64_t>(1ull << 30, free_b / 4)));
   const bool two_phase = pe_two_phase(e, max_mismatches);
-  uint32_t chunk = std::max<uint32_t>(1024u, (uint32_t)std::min<uint64_t>(n, budget / pe_pair_bytes(top_k, max_mismatches, two_phase)));
+  const bool gheaps = two_phase && !heaps_in_smem(e, top_k);
+  uint32_t chunk = std::max<uint32_t>(1024u, (uint32_t)std::min<uint64_t>(n, budget / pe_pair_bytes(top_k, max_mismatches, two_phase, gheaps)));
   if (n > chunk) {   // equal chunks: no short last launch
     const uint32_t k = (n + chunk - 1u) / chunk;
     chunk = (n + k - 1u) / k;
@@ -1595,13 +1805,13 @@ int walt_engine_map_pe_device(walt_engine* e, const void* d_seqs1, const void* d
   if (getenv("WALT_DEBUG"))
     fprintf(stderr, "[walt debug] map_pe_device: free %.2f GB, budget %.2f GB, chunk %u pairs, two_phase %d\n", free_b / 1e9,
             budget / 1e9, chunk, (int)two_phase);
-  if ((rc = reserve_bytes(&s.d_pe, &s.pe_cap, pe_scratch_bytes(chunk, top_k, max_mismatches, two_phase)))) return rc;
+  if ((rc = reserve_bytes(&s.d_pe, &s.pe_cap, pe_scratch_bytes(chunk, top_k, max_mismatches, two_phase, gheaps)))) return rc;
   if (e->defer && two_phase)
     for (int i = 0; i < 2; ++i)
-      if ((rc = reserve(&e->dev_park[i], &e->dev_park_cap[i], (size_t)chunk))) return rc;
+      if ((rc = reserve_park(e, &e->dev_park[i], chunk))) return rc;
   for (uint32_t r0 = 0; r0 < n; r0 += chunk) {
     const uint32_t cn = std::min<uint32_t>(chunk, n - r0);
-    const PeScratch ps = carve_pe(s.d_pe, cn, top_k, max_mismatches, two_phase);
+    const PeScratch ps = carve_pe(s.d_pe, cn, top_k, max_mismatches, two_phase, gheaps);
     // absolute offsets: read r of the chunk is global read r0 + r, addressed from the buffer start
     const ReadSrc m1{s1, o1 + r0, 0, 0, r0, max_read_len, false}, m2{s2, o2 + r0, 0, 0, r0, max_read_len, false};
     if ((rc = launch_pe_chunk(e, m1, m2, cn, max_mismatches, b, top_k, frag_range, pbat, ps, false,

@@ -41,6 +41,15 @@ struct DeviceSubIndex {
 };
 
 constexpr uint32_t N_SLOTS = 3;   // host chunks in flight (copy in / map / copy out)
+constexpr uint32_t LIT_CAP_MAX = 1u << 22;   // parked reads of one launch whose literal regions are computed ahead
+
+// device buffers of a launch that parks reads: their numbers, and the literal regions of the first
+// lit_cap of them (the rest replay their literal lookups inside the take-over kernel)
+struct ParkBuf {
+  uint32_t* list = nullptr;  size_t list_cap = 0;
+  uint32_t* lit = nullptr;   size_t lit_words = 0;
+  uint32_t lit_cap = 0, lit_limit = 0;
+};
 
 // one in-flight chunk of a host batch
 struct BatchSlot {
@@ -53,7 +62,7 @@ struct BatchSlot {
   char* d_seqs2 = nullptr;     size_t seqs2_cap = 0;
   uint64_t* d_offs2 = nullptr; size_t offs2_cap = 0;
   void* d_pe = nullptr;        size_t pe_cap = 0;     // bytes
-  uint32_t* d_park[2] = {nullptr, nullptr};  size_t park_cap[2] = {0, 0};   // parked-read lists (one per mate)
+  ParkBuf park[2];             // one per mate
 };
 
 }  // namespace waltb200
@@ -84,7 +93,11 @@ struct walt_engine {
   int pe_side = 1;                           // 0: both mate kernels on the caller's stream
   int defer = 1;                             // 1: reads that need their whole group (repeats) are parked by the mapping
                                              // kernels and finished by a warp-per-read kernel
-  uint32_t* dev_park[2] = {nullptr, nullptr};  size_t dev_park_cap[2] = {0, 0};   // parked lists of the device-resident calls
+  waltb200::ParkBuf dev_park[2];             // ... of the device-resident calls
+  int take_blocks = 2;                       // experiment: CTAs per SM of the take-over kernels (2 or 3)
+  int lit_ahead = 1;                         // 1: literal regions of parked reads are computed by lit_kernel
+  int pair_wide = 1;                         // 1: pairs with long lists are paired by a whole warp
+  int heap_smem = 1;                         // 1: pe_heap_kernel keeps its heaps in shared memory when they fit
   uint32_t* d_flags = nullptr;               // [0] non-ACGT flag, [2..3] index-build scratch, from [16] the queue
                                              // blocks of the launches in flight (queue_block, walt_engine.cu)
   unsigned long long* d_counters = nullptr;  // lookups, candidates, literal

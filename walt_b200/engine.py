@@ -23,7 +23,7 @@ PAIR_DT = np.dtype([("best_times", np.uint32), ("best_i", np.int32), ("best_j", 
                     ("frag_len", np.int32)])
 PE_RESULT_DT = np.dtype([("pair", PAIR_DT), ("c1", CAND_DT), ("c2", CAND_DT), ("single1", BEST_DT),
                          ("single2", BEST_DT)])
-STATS_FIELDS = ("n_lookups", "n_candidates", "n_literal", "n_kernel_launches")
+STATS_FIELDS = ("n_lookups", "n_candidates", "n_literal", "n_kernel_launches", "n_parked")
 
 _ROOT = os.path.dirname(os.path.abspath(__file__))
 _lib = None
@@ -220,8 +220,14 @@ class Engine:
         self._check(self.L.walt_engine_set_chunk_reads(self.h, C.c_uint32(n)))
 
     def stats(self):
-        a = (C.c_uint64 * 4)()
+        a = (C.c_uint64 * len(STATS_FIELDS))()
         self._check(self.L.walt_engine_last_stats(self.h, a))
+        return dict(zip(STATS_FIELDS, (int(x) for x in a)))
+
+    def device_stats(self):
+        """work counters of the device-resident calls since the last call (waits for the device)"""
+        a = (C.c_uint64 * len(STATS_FIELDS))()
+        self._check(self.L.walt_engine_device_stats(self.h, a))
         return dict(zip(STATS_FIELDS, (int(x) for x in a)))
 
     # ---- mapping ----
