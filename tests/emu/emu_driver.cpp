@@ -309,7 +309,7 @@ void se_lane(WarpEmu* w, uint32_t lane, void* arg) {
   EmuWarp<WD> W{w, lane};
   SubIndexView ix2[2] = {j->e->sub[j->ag ? 2 : 0].view(), j->e->sub[j->ag ? 3 : 1].view()};
   ChromView cv = j->e->cv();
-  MapConfig cfg; cfg.b = j->b; cfg.literal_all = j->literal;
+  MapConfig cfg; cfg.b = j->b; cfg.literal_all = j->literal; cfg.lit_levels = j->prelit > 1 ? (uint32_t)j->prelit : 1u;
   const uint32_t nwmax = (j->max_len + 31) / 32;
   ReadScratch sc = carve_scratch(j->scratch, nwmax ? nwmax : 1);
   uint32_t cached = *j->cached_len;  // lane-private copy, kept uniform
@@ -358,7 +358,7 @@ void pe_lane(WarpEmu* w, uint32_t lane, void* arg) {
   EmuWarp<WD> W{w, lane};
   SubIndexView ix2[2] = {j->e->sub[j->ag ? 2 : 0].view(), j->e->sub[j->ag ? 3 : 1].view()};
   ChromView cv = j->e->cv();
-  MapConfig cfg; cfg.b = j->b; cfg.literal_all = j->literal;
+  MapConfig cfg; cfg.b = j->b; cfg.literal_all = j->literal; cfg.lit_levels = j->prelit > 1 ? (uint32_t)j->prelit : 1u;
   const uint32_t nwmax = (j->max_len + 31) / 32;
   ReadScratch sc = carve_scratch(j->scratch, nwmax ? nwmax : 1);
   uint32_t cached = 0;

@@ -462,9 +462,10 @@ WALT_HD uint32_t literal_char(const uint64_t* __restrict__ genome, uint64_t pos,
 // two dependent cache-missing loads and a bucket of 2^18 entries means ~19 of them in a row.  The
 // array is NOT assumed to be sorted (that is the point of the literal replay): the outcomes are the
 // reference's because every value that decides a step is the value the reference would have read.
-template <bool UPPER, class Probe>
+// LEVELS trades chain length against loads: L levels cost 2^L - 1 probes instead of L.
+template <bool UPPER, uint32_t LEVELS, class Probe>
 WALT_HD uint32_t literal_bound(uint32_t low, uint32_t high, uint32_t ch, Probe probe) {
-  constexpr uint32_t LEVELS = 4u, NODES = 15u;
+  constexpr uint32_t NODES = (1u << LEVELS) - 1u;
   while (low < high) {
     uint32_t lo[NODES], hi[NODES], mid[NODES], val[NODES];
     lo[0] = low; hi[0] = high;
@@ -498,16 +499,16 @@ WALT_HD uint32_t literal_bound(uint32_t low, uint32_t high, uint32_t ch, Probe p
   return low;
 }
 
-WALT_HD void literal_index_region(const SubIndexView& ix, uint32_t genome_len, const uint64_t* R,
-                                  uint32_t seed_i, uint32_t seed_len, uint32_t& first,
-                                  uint32_t& second) {
+template <uint32_t LEVELS>
+WALT_HD void literal_index_region_l(const SubIndexView& ix, uint32_t genome_len, const uint64_t* R,
+                                    uint32_t seed_i, uint32_t seed_len, uint32_t& first, uint32_t& second) {
   uint32_t l = first, u = second - 1u;
   for (uint32_t p = KEY_WEIGHT; p < seed_len; ++p) {
     const uint32_t cp = 3u * p + 1u;
     const uint32_t ch = 1u + packed_base(R, seed_i + cp);
     auto probe = [&](uint32_t slot) { return literal_char(ix.genome, (uint64_t)ix.entries[slot].pos + cp, genome_len); };
-    l = literal_bound<false>(l, u, ch, probe);
-    u = literal_bound<true>(l, u, ch, probe);
+    l = literal_bound<false, LEVELS>(l, u, ch, probe);
+    u = literal_bound<true, LEVELS>(l, u, ch, probe);
     if (l == u && ch != probe(l)) {
       first = 1u; second = 0u;
       return;
@@ -515,6 +516,14 @@ WALT_HD void literal_index_region(const SubIndexView& ix, uint32_t genome_len, c
   }
   if (l > u) { first = 1u; second = 0u; return; }
   first = l; second = u;
+}
+// `levels` of the decision tree probed per step: 1 (the plain search), 2 or 3
+WALT_HD void literal_index_region(const SubIndexView& ix, uint32_t genome_len, const uint64_t* R,
+                                  uint32_t seed_i, uint32_t seed_len, uint32_t& first,
+                                  uint32_t& second, uint32_t levels = 1u) {
+  if (levels >= 3u) literal_index_region_l<3u>(ix, genome_len, R, seed_i, seed_len, first, second);
+  else if (levels == 2u) literal_index_region_l<2u>(ix, genome_len, R, seed_i, seed_len, first, second);
+  else literal_index_region_l<1u>(ix, genome_len, R, seed_i, seed_len, first, second);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -789,6 +798,7 @@ WALT_HD void replay_heap_log(const HeapEntry* log, uint32_t n_log, uint32_t cap,
 struct MapConfig {
   uint32_t b;            // -b
   uint32_t literal_all;  // test hook: replay IndexRegion literally for every lookup
+  uint32_t lit_levels;   // literal_regions: levels of the search tree probed per step (0/1 = plain search)
 };
 
 // Slots [t0, t1) of the taint list that hold positions whose 12-mer key is key12 (its filter bit
@@ -1321,10 +1331,24 @@ WALT_HD LaneResult lane_lookup(const SubIndexView& ix, const ChromView& cv, cons
   // fingerprints are sorted inside a table range, so the matches are one run; it is complete
   // unless it touches the end of the window and the range goes on
   if ((match >> (LANE_RUN_CAP - 1u)) && l + LANE_RUN_CAP < hi) {
-    run.f0 = l + (uint32_t)ffs32(match) - 1u; run.hi = hi; run.fp_lo = fp_lo;
-    WALT_PREFETCH(ix.entries + run.f0 + LANE_RUN_CAP);          // the streaming pass starts here
-    WALT_PREFETCH(ix.entries + run.f0 + LANE_RUN_CAP + 16u);
-    return LANE_RUN;
+    // ... then the window is moved onto the run's first slot (a lone hit in the window's last slot
+    // is the common case on T-rich keys, whose table ranges hold many slots), and only a run that
+    // fills it AND goes on is somebody else's job
+    const uint32_t f0 = l + (uint32_t)ffs32(match) - 1u;
+    if (f0 != l) {
+      l = f0;
+      WALT_UNROLL
+      for (uint32_t k = 0; k < LANE_RUN_CAP; ++k) en[k] = ix.entries[l + k];
+      match = 0u;
+      WALT_UNROLL
+      for (uint32_t k = 0; k < LANE_RUN_CAP; ++k)
+        if (l + k < hi && en[k].fp - fp_lo <= fp_span) match |= 1u << k;
+    }
+    if (match == (1u << LANE_RUN_CAP) - 1u && l + LANE_RUN_CAP < hi && ix.entries[l + LANE_RUN_CAP].fp - fp_lo <= fp_span) {
+      run.f0 = l; run.hi = hi; run.fp_lo = fp_lo;
+      WALT_PREFETCH(ix.entries + run.f0 + LANE_RUN_CAP + 16u);   // the streaming pass starts here
+      return LANE_RUN;
+    }
   }
   const uint64_t* R = sc.R;
   const uint64_t* VM = sc.VM + seed_i * sc.nw;
@@ -1448,7 +1472,7 @@ WALT_HD void literal_regions(const SubIndexView* ix2, uint32_t genome_len, const
     const uint32_t bucket_lo = ix.table[key12 * k12_span], bucket_hi = ix.table[(key12 + 1u) * k12_span];
     if (bucket_lo == bucket_hi) { out[2u * j] = LIT_EMPTY; continue; }
     uint32_t f = bucket_lo, l = bucket_hi;
-    literal_index_region(ix, genome_len, R, seed_i, seed_len, f, l);
+    literal_index_region(ix, genome_len, R, seed_i, seed_len, f, l, cfg.lit_levels);
     out[2u * j] = f; out[2u * j + 1u] = l;
   }
 }
@@ -1470,7 +1494,7 @@ WALT_HD void lit_lookup(W& w, const SubIndexView& ix, const ChromView& cv, const
 // What became of a read: mapped; holds a non-ACGT byte; or PARKed -- its ordered fold reached a
 // lookup that needs the whole group (repeats, tainted buckets) and the caller asked for such reads
 // to be handed to the warp-per-read kernel instead (nothing of the read's result is valid then).
-enum MapStatus : uint32_t { MAP_OK = 0u, MAP_BAD = 1u, MAP_PARKED = 2u };
+enum MapStatus : uint32_t { MAP_OK = 0u, MAP_BAD = 1u, MAP_PARKED = 2u, MAP_PARKED_LIT = 3u };   // _LIT: some lookup of the read is a literal one
 
 // SingleEndMapping for both strand passes of one read (mapping.cpp:486-500 order: all shifts
 // on the '+' sub-index, then all shifts on the '-' sub-index, state carried across).
@@ -1527,7 +1551,7 @@ WALT_HD MapStatus map_read_se(W& w, const SubIndexView* ix2, const ChromView& cv
     if ((lit_mask >> j) & 1u) {
       lit_lookup(w, ix2[s], cv, cfg, sc, read_len, seed_i, strand, w.shfl(lit_f, (int)j), w.shfl(lit_l, (int)j), sink, ctr);
     } else if (((group_mask | run_mask) >> j) & 1u) {
-      if (PARK) { ctr = ctr_in; w.sync(); return MAP_PARKED; }   // the kernel that takes the read over counts its work
+      if (PARK) { ctr = ctr_in; w.sync(); return group_mask ? MAP_PARKED_LIT : MAP_PARKED; }   // the kernel that takes the read over counts its work
       if ((run_mask >> j) & 1u) run_lookup(w, ix2[s], cv, p3, cfg, sc, read_len, seed_i, strand, run, j, sink, ctr);
       else replay_lookup(w, ix2[s], cv, p3, cfg, sc, read_len, seed_i, strand, sink, ctr);
     } else {
@@ -1592,7 +1616,7 @@ WALT_HD MapStatus map_read_pe_into(W& w, const SubIndexView* ix2, const ChromVie
     if ((lit_mask >> j) & 1u) {
       lit_lookup(w, ix2[s], cv, cfg, sc, read_len, seed_i, strand, w.shfl(lit_f, (int)j), w.shfl(lit_l, (int)j), sink, ctr);
     } else if (((group_mask | run_mask) >> j) & 1u) {
-      if (PARK) { ctr = ctr_in; w.sync(); return MAP_PARKED; }
+      if (PARK) { ctr = ctr_in; w.sync(); return group_mask ? MAP_PARKED_LIT : MAP_PARKED; }
       if ((run_mask >> j) & 1u) run_lookup(w, ix2[s], cv, p3, cfg, sc, read_len, seed_i, strand, run, j, sink, ctr);
       else replay_lookup(w, ix2[s], cv, p3, cfg, sc, read_len, seed_i, strand, sink, ctr);
     } else {

@@ -277,7 +277,7 @@ struct SeArgs {
   uint32_t max_mismatches;
   walt_best* out;
   uint32_t* flags;        // [0] non-ACGT
-  uint32_t* queue;        // [0] work-queue head, [1] number of parked reads, [2] queue head of the kernel that takes them over (zeroed before launch)
+  uint32_t* queue;        // [0] work-queue head, [1] parked reads without / [3] with a literal lookup, [2] / [4] queue heads of the kernels that take them over (zeroed before launch)
   uint32_t* parked;       // read numbers of the parked reads (MODE 1 writes, MODE 2 reads)
   uint32_t* lit;          // literal regions of the first lit_cap parked reads (lit_kernel writes, MODE 2 reads)
   uint32_t lit_cap;
@@ -289,7 +289,10 @@ struct SeArgs {
 // bucket) is dropped and its number appended to the parked list, so that the sub-warp groups never
 // leave the converged fast path.  MAP_TAKE (a whole warp per read): maps the parked reads, repeats
 // streamed through the warp-wide quad verification (verify_run_wide, walt_core.cuh).
-enum : int { MAP_ALL = 0, MAP_PARK = 1, MAP_TAKE = 2, MAP_TAKE3 = 3 };   // MAP_TAKE3: experiment, 3 CTAs per SM (80 registers)
+// Parked reads come in two kinds, kept at the two ends of the parked list: reads with a long run and no
+// literal lookup (front; MAP_TAKE maps them at once) and reads with a literal lookup (back; lit_kernel
+// first replays their IndexRegion searches, on a side stream and beside MAP_TAKE, then MAP_TAKE_LIT maps them).
+enum : int { MAP_ALL = 0, MAP_PARK = 1, MAP_TAKE = 2, MAP_TAKE_LIT = 3 };
 constexpr uint32_t TAKE_BLOCKS_PER_SM = 2;   // the take-over kernels get 128 registers
 
 // The groups of a warp take consecutive reads with one queue ticket and walk the read loop
@@ -358,18 +361,33 @@ __device__ __forceinline__ void flush_counters(const HwGroup<WD>& w, const Count
   }
 }
 
-// append the reads of this warp's groups that were parked in this round (one atomic per warp)
+// append the reads of this warp's groups that were parked in this round (one atomic per warp and kind):
+// reads without a literal lookup from the front of the list, the others from its back
 template <uint32_t WD>
-__device__ __forceinline__ void park_reads(const HwGroup<WD>& w, bool parked, uint32_t r, uint32_t* queue, uint32_t* list) {
+__device__ __forceinline__ void park_reads(const HwGroup<WD>& w, MapStatus ms, uint32_t r, uint32_t* queue, uint32_t* list, uint32_t n) {
   const uint32_t l = threadIdx.x & 31u;
-  const uint32_t pm = __ballot_sync(0xFFFFFFFFu, parked && w.lane() == 0u);
-  if (!pm) return;
-  const int leader = __ffs((int)pm) - 1;
-  uint32_t at = 0;
-  if ((int)l == leader) at = atomicAdd(queue + 1, (uint32_t)__popc(pm));
-  at = __shfl_sync(0xFFFFFFFFu, at, leader);
-  if (parked && w.lane() == 0u) list[at + (uint32_t)__popc(pm & ((1u << l) - 1u))] = r;
+  const bool mine = w.lane() == 0u;
+  const uint32_t pm = __ballot_sync(0xFFFFFFFFu, mine && ms == MAP_PARKED);
+  const uint32_t pl = __ballot_sync(0xFFFFFFFFu, mine && ms == MAP_PARKED_LIT);
+  if (pm) {
+    const int leader = __ffs((int)pm) - 1;
+    uint32_t at = 0;
+    if ((int)l == leader) at = atomicAdd(queue + 1, (uint32_t)__popc(pm));
+    at = __shfl_sync(0xFFFFFFFFu, at, leader);
+    if (mine && ms == MAP_PARKED) list[at + (uint32_t)__popc(pm & ((1u << l) - 1u))] = r;
+  }
+  if (pl) {
+    const int leader = __ffs((int)pl) - 1;
+    uint32_t at = 0;
+    if ((int)l == leader) at = atomicAdd(queue + 3, (uint32_t)__popc(pl));
+    at = __shfl_sync(0xFFFFFFFFu, at, leader);
+    if (mine && ms == MAP_PARKED_LIT) list[n - 1u - (at + (uint32_t)__popc(pl & ((1u << l) - 1u)))] = r;
+  }
 }
+
+// Read number of parked item t.  MAP_TAKE: front of the list; MAP_TAKE_LIT / lit_kernel: its back.
+template <class Args>
+__device__ __forceinline__ uint32_t parked_at(const Args& a, uint32_t t, bool back) { return a.parked[back ? a.n - 1u - t : t]; }
 
 // Between the two: one THREAD per parked read replays the literal IndexRegion searches of its lookups
 // (literal_regions, walt_core.cuh), so that the long chains of dependent loads of tens of thousands of
@@ -377,11 +395,11 @@ __device__ __forceinline__ void park_reads(const HwGroup<WD>& w, bool parked, ui
 template <bool PACKED, class Args>
 __global__ void __launch_bounds__(128)
 lit_kernel(const __grid_constant__ Args a) {
-  uint32_t n = *reinterpret_cast<volatile const uint32_t*>(a.queue + 1);
+  uint32_t n = *reinterpret_cast<volatile const uint32_t*>(a.queue + 3);
   if (n > a.lit_cap) n = a.lit_cap;
   for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
     uint32_t len;
-    const char* seq = read_at<PACKED>(a, a.parked[t], len);
+    const char* seq = read_at<PACKED>(a, parked_at(a, t, true), len);
     uint64_t R[MAX_WORDS];
     uint32_t out[LIT_WORDS];
     if (len <= MAX_READ_LEN && pack_read_serial<PACKED>(seq, len, a.ag != 0u, R)) {
@@ -397,7 +415,7 @@ lit_kernel(const __grid_constant__ Args a) {
 }
 
 template <uint32_t WD, bool PACKED, int MODE>
-__global__ void __launch_bounds__(BLOCK_THREADS, MODE == MAP_TAKE ? TAKE_BLOCKS_PER_SM : MODE == MAP_TAKE3 ? 3 : MIN_BLOCKS_PER_SM)
+__global__ void __launch_bounds__(BLOCK_THREADS, MODE >= MAP_TAKE ? TAKE_BLOCKS_PER_SM : MIN_BLOCKS_PER_SM)
 se_map_kernel(const __grid_constant__ SeArgs a) {
   static_assert(MODE < MAP_TAKE || WD == 32u, "parked reads are taken over by whole warps");
   extern __shared__ uint64_t smem[];
@@ -412,37 +430,35 @@ se_map_kernel(const __grid_constant__ SeArgs a) {
   bool bad = false;
   uint32_t n = a.n;
   if (MODE >= MAP_TAKE) {
-    n = *reinterpret_cast<volatile const uint32_t*>(a.queue + 1);   // what the first kernel parked
+    n = *reinterpret_cast<volatile const uint32_t*>(a.queue + (MODE == MAP_TAKE_LIT ? 3 : 1));   // what the first kernel parked
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.counters && n) atomicAdd(a.counters + 3, (unsigned long long)n);
   }
-  uint32_t* const queue = MODE >= MAP_TAKE ? a.queue + 2 : a.queue;
+  uint32_t* const queue = MODE == MAP_TAKE_LIT ? a.queue + 4 : MODE == MAP_TAKE ? a.queue + 2 : a.queue;
   for (uint32_t round = TICKET_ROUNDS, base = 0;; ++round) {
     if (round == TICKET_ROUNDS) { base = next_ticket<WD>(queue); round = 0; }
     const uint32_t first = base + round * (32u / WD);
     if (first >= n) break;                              // warp-uniform: past the batch
     uint32_t r = first + (threadIdx.x & 31u) / WD;
-    bool parked = false;
+    MapStatus status = MAP_OK;
     if (r < n) {
       const uint32_t* lit = nullptr;
-      if (MODE >= MAP_TAKE) {
-        if (r < a.lit_cap) lit = a.lit + (size_t)r * LIT_WORDS;
-        r = a.parked[r];
-      }
+      if (MODE == MAP_TAKE_LIT && r < a.lit_cap) lit = a.lit + (size_t)r * LIT_WORDS;
+      if (MODE >= MAP_TAKE) r = parked_at(a, r, MODE == MAP_TAKE_LIT);
       uint32_t len;
       const char* seq = read_at<PACKED>(a, r, len);
       BestState st;
       const MapStatus ms = map_read_se<HwGroup<WD>, PACKED, MODE == MAP_PARK>(w, a.ix, a.cv, a.p3, a.cfg, seq, len, a.ag != 0u,
                                                                             a.max_mismatches, sc, cached_len, st, ctr, lit);
       bad |= ms == MAP_BAD;
-      parked = ms == MAP_PARKED;
-      if (lane == 0 && !parked) {
+      status = ms;
+      if (lane == 0 && ms < MAP_PARKED) {
         uint4 o;
         o.x = st.pos; o.y = st.times; o.z = st.mm; o.w = st.strand & 0xFFu;
         *reinterpret_cast<uint4*>(a.out + r) = o;
       }
     }
     __syncwarp();
-    if (MODE == MAP_PARK) park_reads(w, parked, r, a.queue, a.parked);
+    if (MODE == MAP_PARK) park_reads(w, status, r, a.queue, a.parked, a.n);
   }
   flush_counters(w, ctr, bad, tally, a.flags, a.counters);
 }
@@ -479,7 +495,7 @@ struct PeArgs {
 // Two-phase form, first phase: PairEndMapping (paired.cpp:106-201) for one mate batch with the
 // heap-changing candidates logged (LogSink, walt_core.cuh); pe_heap_kernel finishes the job.
 template <uint32_t WD, bool PACKED, int MODE>
-__global__ void __launch_bounds__(BLOCK_THREADS, MODE == MAP_TAKE ? TAKE_BLOCKS_PER_SM : MODE == MAP_TAKE3 ? 3 : MIN_BLOCKS_PER_SM)
+__global__ void __launch_bounds__(BLOCK_THREADS, MODE >= MAP_TAKE ? TAKE_BLOCKS_PER_SM : MIN_BLOCKS_PER_SM)
 pe_log_kernel(const __grid_constant__ PeArgs a) {
   static_assert(MODE < MAP_TAKE || WD == 32u, "parked reads are taken over by whole warps");
   extern __shared__ uint64_t smem[];
@@ -497,22 +513,20 @@ pe_log_kernel(const __grid_constant__ PeArgs a) {
   bool bad = false;
   uint32_t n = a.n;
   if (MODE >= MAP_TAKE) {
-    n = *reinterpret_cast<volatile const uint32_t*>(a.queue + 1);   // what the first kernel parked
+    n = *reinterpret_cast<volatile const uint32_t*>(a.queue + (MODE == MAP_TAKE_LIT ? 3 : 1));   // what the first kernel parked
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.counters && n) atomicAdd(a.counters + 3, (unsigned long long)n);
   }
-  uint32_t* const queue = MODE >= MAP_TAKE ? a.queue + 2 : a.queue;
+  uint32_t* const queue = MODE == MAP_TAKE_LIT ? a.queue + 4 : MODE == MAP_TAKE ? a.queue + 2 : a.queue;
   for (uint32_t round = TICKET_ROUNDS, base = 0;; ++round) {
     if (round == TICKET_ROUNDS) { base = next_ticket<WD>(queue); round = 0; }
     const uint32_t first = base + round * (32u / WD);
     if (first >= n) break;
     uint32_t r = first + (threadIdx.x & 31u) / WD;
-    bool parked = false;
+    MapStatus status = MAP_OK;
     if (r < n) {
       const uint32_t* lit = nullptr;
-      if (MODE >= MAP_TAKE) {
-        if (r < a.lit_cap) lit = a.lit + (size_t)r * LIT_WORDS;
-        r = a.parked[r];
-      }
+      if (MODE == MAP_TAKE_LIT && r < a.lit_cap) lit = a.lit + (size_t)r * LIT_WORDS;
+      if (MODE >= MAP_TAKE) r = parked_at(a, r, MODE == MAP_TAKE_LIT);
       uint32_t len;
       const char* seq = read_at<PACKED>(a, r, len);
       uint32_t n_log = 0;
@@ -520,11 +534,11 @@ pe_log_kernel(const __grid_constant__ PeArgs a) {
           w, a.ix, a.cv, a.p3, a.cfg, seq, len, a.ag != 0u, a.max_mismatches, a.top_k, sc, cached_len,
           a.log + (size_t)r * a.log_slots, hist, n_log, ctr, lit);
       bad |= ms == MAP_BAD;
-      parked = ms == MAP_PARKED;
-      if (lane == 0 && !parked) a.n_log[r] = n_log;
+      status = ms;
+      if (lane == 0 && ms < MAP_PARKED) a.n_log[r] = n_log;
     }
     __syncwarp();
-    if (MODE == MAP_PARK) park_reads(w, parked, r, a.queue, a.parked);
+    if (MODE == MAP_PARK) park_reads(w, status, r, a.queue, a.parked, a.n);
   }
   flush_counters(w, ctr, bad, tally, a.flags, a.counters);
 }
@@ -540,7 +554,7 @@ struct HeapArgs {
   uint32_t* n_ranked[2];
   HeapEntry* heaps;
   const uint32_t* parked[2];     // parked-read lists of the two mate launches (NULL: nothing was parked)
-  const uint32_t* n_parked[2];
+  const uint32_t* queue[2];      // their queue blocks: [1] reads at the front of the list, [3] at its back
   uint32_t n, top_k, log_slots;
   uint32_t zero_fill;     // see PeArgs
 };
@@ -618,8 +632,8 @@ pe_heap_kernel(const __grid_constant__ HeapArgs a) {
   } else {
     if (!a.parked[0]) return;
     uint32_t u = t - 2u * a.n;
-    const uint32_t p0 = *a.n_parked[0], p1 = *a.n_parked[1];
-    if (u < p0) { mate = 0u; } else { u -= p0; if (u >= p1) return; mate = 1u; }
+    mate = u >= a.n ? 1u : 0u; u -= mate * a.n;
+    if (u >= a.queue[mate][1] && u < a.n - a.queue[mate][3]) return;   // between the two ends of the list
     r = a.parked[mate][u];
     if (a.n_log[mate][r] <= SHORT_LOG) return;                    // done above
   }
@@ -833,12 +847,13 @@ struct ReadSrc {
   bool packed;
 };
 
-// queue block i of the engine: four words {work-queue head, parked reads, take-over queue head, spare}
+// queue block i of the engine: QUEUE_WORDS words (see SeArgs::queue)
 // 0: device-resident SE; 1..N_SLOTS: SE host chunks; then two (one per mate) for device-resident PE
 // and two per slot for PE host chunks
-static uint32_t* queue_block(walt_engine* e, uint32_t i) { return e->d_flags + 16u + 4u * i; }
+constexpr uint32_t QUEUE_WORDS = 8;
+static uint32_t* queue_block(walt_engine* e, uint32_t i) { return e->d_flags + 16u + QUEUE_WORDS * i; }
 constexpr uint32_t QB_SE_DEVICE = 0, QB_SE_SLOT = 1, QB_PE_DEVICE = 1 + N_SLOTS, QB_PE_SLOT = 3 + N_SLOTS;
-constexpr uint32_t N_FLAG_WORDS = 16u + 4u * (QB_PE_SLOT + 2u * N_SLOTS);
+constexpr uint32_t N_FLAG_WORDS = 16u + 8u * (QB_PE_SLOT + 2u * N_SLOTS);
 
 template <class Args>
 static void fill_common(walt_engine* e, Args& a, const ReadSrc& src, uint32_t n, int ag, uint32_t m, uint32_t b,
@@ -846,7 +861,7 @@ static void fill_common(walt_engine* e, Args& a, const ReadSrc& src, uint32_t n,
   const int base = ag ? WALT_GA10 : WALT_CT00;
   a.ix[0] = e->sub[base].view(base); a.ix[1] = e->sub[base + 1].view(base + 1);
   a.cv = chrom_view(e); a.p3 = e->pow3;
-  a.cfg.b = b; a.cfg.literal_all = e->search_mode == 1 ? 1u : 0u;
+  a.cfg.b = b; a.cfg.literal_all = e->search_mode == 1 ? 1u : 0u; a.cfg.lit_levels = e->lit_levels;
   a.seqs = src.d_seqs; a.offs = src.d_offs; a.seq_base = src.seq_base; a.n = n; a.uniform_len = src.uniform_len;
   a.read_base = src.read_base;
   a.nw_max = std::max<uint32_t>(1u, (src.max_len + 31u) / 32u);
@@ -865,21 +880,34 @@ static int take_grid(walt_engine* e, K kernel, size_t smem, uint32_t* grid) {
   return WALT_OK;
 }
 
-// The second and third kernel of a launch that parks reads (see MAP_PARK / MAP_TAKE, lit_kernel)
+// The kernels behind one that parks reads: lit_kernel on the side stream of the launch, MAP_TAKE beside
+// it on the launch's own stream, then MAP_TAKE_LIT
 template <class Args>
-static int launch_take(walt_engine* e, const Args& a, bool packed, void (*take)(Args), size_t smem, cudaStream_t st) {
+static int launch_take(walt_engine* e, const Args& a, bool packed, void (*take)(Args), void (*take_lit)(Args), size_t smem,
+                       const ParkBuf* pk, cudaStream_t st) {
   int rc;
   uint32_t grid = 0;
+  const bool side = a.lit_cap && pk->lit_stream;
   if (a.lit_cap) {
+    cudaStream_t ls = side ? pk->lit_stream : st;
+    if (side) {
+      WALT_CUDA_TRY(cudaEventRecord(pk->fork, st));
+      WALT_CUDA_TRY(cudaStreamWaitEvent(ls, pk->fork, 0));
+    }
     void (*lk)(Args) = packed ? lit_kernel<true, Args> : lit_kernel<false, Args>;
-    lk<<<(uint32_t)e->sm_count * 8u, 128, 0, st>>>(a);
+    lk<<<(uint32_t)e->sm_count * 8u, 128, 0, ls>>>(a);
     WALT_CUDA_TRY(cudaGetLastError());
+    if (side) WALT_CUDA_TRY(cudaEventRecord(pk->join, ls));
     e->stats.n_kernel_launches++;
   }
   if ((rc = take_grid(e, take, smem, &grid))) return rc;
   take<<<grid, BLOCK_THREADS, smem, st>>>(a);
   WALT_CUDA_TRY(cudaGetLastError());
-  e->stats.n_kernel_launches++;
+  if (side) WALT_CUDA_TRY(cudaStreamWaitEvent(st, pk->join, 0));
+  if ((rc = take_grid(e, take_lit, smem, &grid))) return rc;
+  take_lit<<<grid, BLOCK_THREADS, smem, st>>>(a);
+  WALT_CUDA_TRY(cudaGetLastError());
+  e->stats.n_kernel_launches += 2;
   return WALT_OK;
 }
 
@@ -906,15 +934,14 @@ static int launch_se(walt_engine* e, const ReadSrc& src, uint32_t n, int ag, uin
                         : (wd == 8u ? se_map_kernel<8, false, MAP_ALL> : wd == 16u ? se_map_kernel<16, false, MAP_ALL> : se_map_kernel<32, false, MAP_ALL>);
   int rc = grid_for(e, kernel, smem, n, wd, &grid, share);
   if (rc) return rc;
-  WALT_CUDA_TRY(cudaMemsetAsync(d_queue, 0, 16, st));
+  WALT_CUDA_TRY(cudaMemsetAsync(d_queue, 0, 4 * QUEUE_WORDS, st));
   kernel<<<grid, BLOCK_THREADS, smem, st>>>(a);
   WALT_CUDA_TRY(cudaGetLastError());
   e->stats.n_kernel_launches++;
   if (park)
-    return launch_take(e, a, src.packed,
-                       e->take_blocks == 3 ? (src.packed ? se_map_kernel<32, true, MAP_TAKE3> : se_map_kernel<32, false, MAP_TAKE3>)
-                                           : (src.packed ? se_map_kernel<32, true, MAP_TAKE> : se_map_kernel<32, false, MAP_TAKE>),
-                       se_smem_bytes(a.nw_max, 32u), st);
+    return launch_take(e, a, src.packed, src.packed ? se_map_kernel<32, true, MAP_TAKE> : se_map_kernel<32, false, MAP_TAKE>,
+                       src.packed ? se_map_kernel<32, true, MAP_TAKE_LIT> : se_map_kernel<32, false, MAP_TAKE_LIT>,
+                       se_smem_bytes(a.nw_max, 32u), pk, st);
   return WALT_OK;
 }
 
@@ -941,15 +968,14 @@ static int launch_pe_log(walt_engine* e, const ReadSrc& src, uint32_t n, int ag,
                         : (wd == 8u ? pe_log_kernel<8, false, MAP_ALL> : wd == 16u ? pe_log_kernel<16, false, MAP_ALL> : pe_log_kernel<32, false, MAP_ALL>);
   int rc = grid_for(e, kernel, smem, n, wd, &grid);
   if (rc) return rc;
-  WALT_CUDA_TRY(cudaMemsetAsync(d_queue, 0, 16, st));
+  WALT_CUDA_TRY(cudaMemsetAsync(d_queue, 0, 4 * QUEUE_WORDS, st));
   kernel<<<grid, BLOCK_THREADS, smem, st>>>(a);
   WALT_CUDA_TRY(cudaGetLastError());
   e->stats.n_kernel_launches++;
   if (park)
-    return launch_take(e, a, src.packed,
-                       e->take_blocks == 3 ? (src.packed ? pe_log_kernel<32, true, MAP_TAKE3> : pe_log_kernel<32, false, MAP_TAKE3>)
-                                           : (src.packed ? pe_log_kernel<32, true, MAP_TAKE> : pe_log_kernel<32, false, MAP_TAKE>),
-                       pe_log_smem_bytes(a.nw_max, 32u), st);
+    return launch_take(e, a, src.packed, src.packed ? pe_log_kernel<32, true, MAP_TAKE> : pe_log_kernel<32, false, MAP_TAKE>,
+                       src.packed ? pe_log_kernel<32, true, MAP_TAKE_LIT> : pe_log_kernel<32, false, MAP_TAKE_LIT>,
+                       pe_log_smem_bytes(a.nw_max, 32u), pk, st);
   return WALT_OK;
 }
 
@@ -994,6 +1020,11 @@ static int reserve_park(walt_engine* e, ParkBuf* pk, uint32_t n) {
   int rc;
   if ((rc = reserve(&pk->list, &pk->list_cap, (size_t)n))) return rc;
   pk->lit_cap = std::min<uint32_t>(n, pk->lit_limit);
+  if (pk->lit_cap && e->lit_side && !pk->lit_stream) {
+    WALT_CUDA_TRY(cudaStreamCreateWithFlags(&pk->lit_stream, cudaStreamNonBlocking));
+    WALT_CUDA_TRY(cudaEventCreateWithFlags(&pk->fork, cudaEventDisableTiming));
+    WALT_CUDA_TRY(cudaEventCreateWithFlags(&pk->join, cudaEventDisableTiming));
+  }
   return reserve(&pk->lit, &pk->lit_words, (size_t)pk->lit_cap * LIT_WORDS);
 }
 
@@ -1081,7 +1112,8 @@ int walt_engine_create(walt_engine** out, int device) {
   if (const char* v = getenv("WALT_PE_SIDE")) e->pe_side = atoi(v);
   if (const char* v = getenv("WALT_PE_LOGGED")) e->pe_logged = atoi(v);
   if (const char* v = getenv("WALT_DEFER")) e->defer = atoi(v);
-  if (const char* v = getenv("WALT_TAKE_BLOCKS")) e->take_blocks = atoi(v);
+  if (const char* v = getenv("WALT_LIT_SIDE")) e->lit_side = atoi(v);
+  if (const char* v = getenv("WALT_LIT_LEVELS")) e->lit_levels = (uint32_t)atoi(v);
   if (const char* v = getenv("WALT_LIT")) e->lit_ahead = atoi(v);
   if (const char* v = getenv("WALT_PAIR_WIDE")) e->pair_wide = atoi(v);
   if (const char* v = getenv("WALT_HEAP_SMEM")) e->heap_smem = atoi(v);
@@ -1112,7 +1144,7 @@ void walt_engine_destroy(walt_engine* e) {
   for (auto& s : e->slot) {
     cudaFree(s.d_seqs); cudaFree(s.d_offs); cudaFree(s.d_out); cudaFree(s.d_seqs2); cudaFree(s.d_offs2);
     cudaFree(s.d_pe);
-    for (auto& p : s.park) { cudaFree(p.list); cudaFree(p.lit); }
+    for (auto& p : s.park) p.release();
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.done) cudaEventDestroy(s.done);
   }
@@ -1120,7 +1152,7 @@ void walt_engine_destroy(walt_engine* e) {
   if (e->fork) cudaEventDestroy(e->fork);
   if (e->join) cudaEventDestroy(e->join);
   cudaFree(e->d_starts); cudaFree(e->d_flags); cudaFree(e->d_counters);
-  for (auto& p : e->dev_park) { cudaFree(p.list); cudaFree(p.lit); }
+  for (auto& p : e->dev_park) p.release();
   delete e;
 }
 
@@ -1599,10 +1631,10 @@ static int launch_pe_chunk(walt_engine* e, const ReadSrc& m1, const ReadSrc& m2,
   const bool two_phase = ps.log1 != nullptr;
   if (two_phase) {
     if ((rc = launch_pe_log(e, m1, cn, 0, m, b, top_k, ps.log1, ps.nlog1, q, pk ? pk : nullptr, st))) return rc;
-    if ((rc = launch_pe_log(e, m2, cn, 1, m, b, top_k, ps.log2, ps.nlog2, q + 4, pk ? pk + 1 : nullptr, st2))) return rc;
+    if ((rc = launch_pe_log(e, m2, cn, 1, m, b, top_k, ps.log2, ps.nlog2, q + QUEUE_WORDS, pk ? pk + 1 : nullptr, st2))) return rc;
   } else {
     if ((rc = launch_pe_mate(e, m1, cn, 0, m, b, top_k, ps.r1, ps.n1, q, st, want_pairs))) return rc;
-    if ((rc = launch_pe_mate(e, m2, cn, 1, m, b, top_k, ps.r2, ps.n2, q + 4, st2, want_pairs))) return rc;
+    if ((rc = launch_pe_mate(e, m2, cn, 1, m, b, top_k, ps.r2, ps.n2, q + QUEUE_WORDS, st2, want_pairs))) return rc;
   }
   if (e->pe_side) {
     WALT_CUDA_TRY(cudaEventRecord(e->join, st2));
@@ -1617,7 +1649,7 @@ static int launch_pe_chunk(walt_engine* e, const ReadSrc& m1, const ReadSrc& m2,
     const bool parked = pk != nullptr && e->defer;
     for (int i = 0; i < 2; ++i) {
       h.parked[i] = parked ? pk[i].list : nullptr;
-      h.n_parked[i] = q + 4 * i + 1;
+      h.queue[i] = q + QUEUE_WORDS * i;
     }
     // SMEM: heaps of top_k entries per thread in shared memory (local memory heaps of 16 resident blocks thrash the L1)
     const bool smem = ps.heaps == nullptr;

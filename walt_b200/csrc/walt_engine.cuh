@@ -49,6 +49,15 @@ struct ParkBuf {
   uint32_t* list = nullptr;  size_t list_cap = 0;
   uint32_t* lit = nullptr;   size_t lit_words = 0;
   uint32_t lit_cap = 0, lit_limit = 0;
+  cudaStream_t lit_stream = nullptr;          // lit_kernel runs here, beside the first take-over kernel
+  cudaEvent_t fork = nullptr, join = nullptr;
+  void release() {
+    cudaFree(list); cudaFree(lit);
+    if (lit_stream) cudaStreamDestroy(lit_stream);
+    if (fork) cudaEventDestroy(fork);
+    if (join) cudaEventDestroy(join);
+    *this = ParkBuf();
+  }
 };
 
 // one in-flight chunk of a host batch
@@ -94,7 +103,8 @@ struct walt_engine {
   int defer = 1;                             // 1: reads that need their whole group (repeats) are parked by the mapping
                                              // kernels and finished by a warp-per-read kernel
   waltb200::ParkBuf dev_park[2];             // ... of the device-resident calls
-  int take_blocks = 2;                       // experiment: CTAs per SM of the take-over kernels (2 or 3)
+  int lit_side = 1;                          // 1: lit_kernel on a side stream, beside the first take-over kernel
+  uint32_t lit_levels = 2;                   // levels of the literal search tree probed per step (literal_bound)
   int lit_ahead = 1;                         // 1: literal regions of parked reads are computed by lit_kernel
   int pair_wide = 1;                         // 1: pairs with long lists are paired by a whole warp
   int heap_smem = 1;                         // 1: pe_heap_kernel keeps its heaps in shared memory when they fit
