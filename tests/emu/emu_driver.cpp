@@ -174,7 +174,7 @@ struct EmuWarp {
 // ------------------------------------------------------------------------------------------
 struct EmuSubIndex {
   std::vector<uint64_t> genome;
-  std::vector<uint32_t> index, table, taint_bits, taint_rank, taint_start, taint_key, taint_pos, taint_len;
+  std::vector<uint32_t> index, table, taint_bits, taint_rank, taint_start, taint_key, taint_pos, taint_len, taint_slot;
   std::vector<Entry> entries;
   uint32_t depth = 0, ag = 0;
   uint32_t unsorted = 0;
@@ -182,7 +182,7 @@ struct EmuSubIndex {
     SubIndexView v;
     v.genome = genome.data(); v.entries = entries.data(); v.table = table.data();
     v.taint_bits = taint_bits.data(); v.taint_rank = taint_rank.data(); v.taint_start = taint_start.data();
-    v.taint_pos = taint_pos.data(); v.taint_len = taint_len.data();
+    v.taint_pos = taint_pos.data(); v.taint_len = taint_len.data(); v.taint_slot = taint_slot.data();
     v.n_taint = (uint32_t)taint_key.size(); v.index_size = (uint32_t)index.size();
     v.depth = depth; v.ag = ag;
     return v;
@@ -281,6 +281,15 @@ int emu_engine_load_subindex(void* h, int which, const char* seq, const uint32_t
     s.taint_key.push_back(x.first); s.taint_pos.push_back(x.second.first); s.taint_len.push_back(x.second.second);
   }
   build_taint_directory(s.taint_key, s.taint_bits, s.taint_rank, s.taint_start);
+  // slots of the tainted positions == what table_keys_kernel records on the device
+  s.taint_slot.assign(s.taint_pos.size() + 1, 0xFFFFFFFFu);
+  for (uint32_t i = 0; i < index_size; ++i) {
+    const uint32_t en = s.index[i];
+    const uint32_t chr = chrom_of(cv.starts, cv.n_chr, en);
+    if (cv.starts[chr + 1] - en > TAINT_SPAN) continue;
+    for (size_t t = 0; t < s.taint_pos.size(); ++t)
+      if (s.taint_pos[t] == en) s.taint_slot[t] = i;
+  }
   return s.unsorted ? 2 : 0;
 }
 
@@ -309,7 +318,7 @@ void se_lane(WarpEmu* w, uint32_t lane, void* arg) {
   EmuWarp<WD> W{w, lane};
   SubIndexView ix2[2] = {j->e->sub[j->ag ? 2 : 0].view(), j->e->sub[j->ag ? 3 : 1].view()};
   ChromView cv = j->e->cv();
-  MapConfig cfg; cfg.b = j->b; cfg.literal_all = j->literal; cfg.lit_levels = j->prelit > 1 ? (uint32_t)j->prelit : 1u;
+  MapConfig cfg; cfg.b = j->b; cfg.literal_all = j->literal;
   const uint32_t nwmax = (j->max_len + 31) / 32;
   ReadScratch sc = carve_scratch(j->scratch, nwmax ? nwmax : 1);
   uint32_t cached = *j->cached_len;  // lane-private copy, kept uniform
@@ -358,7 +367,7 @@ void pe_lane(WarpEmu* w, uint32_t lane, void* arg) {
   EmuWarp<WD> W{w, lane};
   SubIndexView ix2[2] = {j->e->sub[j->ag ? 2 : 0].view(), j->e->sub[j->ag ? 3 : 1].view()};
   ChromView cv = j->e->cv();
-  MapConfig cfg; cfg.b = j->b; cfg.literal_all = j->literal; cfg.lit_levels = j->prelit > 1 ? (uint32_t)j->prelit : 1u;
+  MapConfig cfg; cfg.b = j->b; cfg.literal_all = j->literal;
   const uint32_t nwmax = (j->max_len + 31) / 32;
   ReadScratch sc = carve_scratch(j->scratch, nwmax ? nwmax : 1);
   uint32_t cached = 0;

@@ -28,10 +28,10 @@ def _cmp_best(got, want):
 
 
 @pytest.mark.parametrize("literal,width,prelit", [(False, 32, False), (True, 32, False), (False, 8, False), (True, 8, False),
-                                                  (False, 16, False), (False, 32, True), (True, 32, True), (True, 8, True), (True, 32, 2), (True, 8, 3)])
+                                                  (False, 16, False), (False, 32, True), (True, 32, True), (True, 8, True)])
 def test_se_emu_matches_reference(engine, literal, width, prelit):
     """prelit: the literal regions come from literal_regions() (one lane, ahead of the read), as they do
-    for parked reads on the device; 2, 3: with that many levels of the search tree probed per step"""
+    for parked reads on the device"""
     for name, ag in (("se_ct.npz", False), ("se_ga.npz", True)):
         z = goldenio.load(name)
         buf, offs = refio.pack_reads(z["reads"])
@@ -92,7 +92,7 @@ def test_se_emu_packed_input(engine, width):
 
 
 @pytest.mark.parametrize("depth,width,prelit", [(0, 32, False), (12, 32, False), (13, 8, False), (16, 8, False), (0, 8, False),
-                                                (12, 16, False), (0, 32, True), (13, 8, True), (0, 8, 2), (12, 32, 3)])
+                                                (12, 16, False), (0, 32, True), (13, 8, True)])
 def test_se_edge_emu(depth, width, prelit):
     hdr, subs = goldenio.genome()
     e = emu.EmuEngine(hdr.lengths)

@@ -184,6 +184,7 @@ struct SubIndexView {
   const uint32_t* taint_start; // per distinct tainted key (rank order): first slot in taint_pos/len, + end
   const uint32_t* taint_pos;   // their genome positions
   const uint32_t* taint_len;   // chromosome end - position
+  const uint32_t* taint_slot;  // their slots in `entries` (0xFFFFFFFF: not an index entry)
   uint32_t n_taint;
   uint32_t index_size;
   uint32_t depth;
@@ -456,74 +457,94 @@ WALT_HD uint32_t literal_char(const uint64_t* __restrict__ genome, uint64_t pos,
   return 1u + packed_base(genome, pos + PAD_BASES);
 }
 
-// LowerBound / UpperBound of mapping.cpp:166-196 over slots [low, high] for the probe value `ch`,
-// same probes, same decisions, same result -- but four levels of the decision tree are probed at
-// once (15 independent entry -> genome load chains in flight instead of one), because a probe is
-// two dependent cache-missing loads and a bucket of 2^18 entries means ~19 of them in a row.  The
-// array is NOT assumed to be sorted (that is the point of the literal replay): the outcomes are the
-// reference's because every value that decides a step is the value the reference would have read.
-// LEVELS trades chain length against loads: L levels cost 2^L - 1 probes instead of L.
-template <bool UPPER, uint32_t LEVELS, class Probe>
-WALT_HD uint32_t literal_bound(uint32_t low, uint32_t high, uint32_t ch, Probe probe) {
-  constexpr uint32_t NODES = (1u << LEVELS) - 1u;
+// LowerBound / UpperBound of mapping.cpp:166-196 over slots [low, high] for the probe value `ch`;
+// probe(slot) is the genome character the reference reads for that slot, as an ordered code.
+template <class Probe>
+WALT_HD uint32_t literal_lower(uint32_t low, uint32_t high, uint32_t ch, Probe probe) {
   while (low < high) {
-    uint32_t lo[NODES], hi[NODES], mid[NODES], val[NODES];
-    lo[0] = low; hi[0] = high;
-    WALT_UNROLL
-    for (uint32_t k = 0; k < NODES; ++k) {
-      const bool open = lo[k] < hi[k];
-      mid[k] = UPPER ? lo[k] + (hi[k] - lo[k] + 1u) / 2u : lo[k] + (hi[k] - lo[k]) / 2u;
-      if (2u * k + 2u < NODES) {   // child 2k+1: the comparison held, child 2k+2: it did not
-        if (!open) {
-          lo[2u * k + 1u] = hi[2u * k + 1u] = lo[2u * k + 2u] = hi[2u * k + 2u] = lo[k];
-        } else if (UPPER) {
-          lo[2u * k + 1u] = mid[k]; hi[2u * k + 1u] = hi[k];
-          lo[2u * k + 2u] = lo[k]; hi[2u * k + 2u] = mid[k] - 1u;
-        } else {
-          lo[2u * k + 1u] = lo[k]; hi[2u * k + 1u] = mid[k];
-          lo[2u * k + 2u] = mid[k] + 1u; hi[2u * k + 2u] = hi[k];
-        }
-      }
-    }
-    WALT_UNROLL
-    for (uint32_t k = 0; k < NODES; ++k) val[k] = lo[k] < hi[k] ? probe(mid[k]) : 0u;
-    uint32_t k = 0u;
-    for (uint32_t lvl = 0; lvl < LEVELS && low < high; ++lvl) {   // (low, high) is node k's interval
-      const uint32_t m = mid[k];
-      const bool held = UPPER ? val[k] <= ch : val[k] >= ch;
-      if (UPPER) { if (held) low = m; else high = m - 1u; }
-      else       { if (held) high = m; else low = m + 1u; }
-      k = 2u * k + (held ? 1u : 2u);
-    }
+    const uint32_t mid = low + (high - low) / 2u;
+    if (probe(mid) >= ch) high = mid; else low = mid + 1u;
   }
   return low;
 }
+template <class Probe>
+WALT_HD uint32_t literal_upper(uint32_t low, uint32_t high, uint32_t ch, Probe probe) {
+  while (low < high) {
+    const uint32_t mid = low + (high - low + 1u) / 2u;
+    if (probe(mid) <= ch) low = mid; else high = mid - 1u;
+  }
+  return low;
+}
+// one character of IndexRegion (mapping.cpp:198-222): false if the search fails here
+template <class Probe>
+WALT_HD bool literal_step(uint32_t& l, uint32_t& u, uint32_t ch, Probe probe) {
+  l = literal_lower(l, u, ch, probe);
+  u = literal_upper(l, u, ch, probe);
+  return !(l == u && ch != probe(l));
+}
 
-template <uint32_t LEVELS>
-WALT_HD void literal_index_region_l(const SubIndexView& ix, uint32_t genome_len, const uint64_t* R,
-                                    uint32_t seed_i, uint32_t seed_len, uint32_t& first, uint32_t& second) {
+// Slots [t0, t1) of the taint list that hold positions whose 12-mer key is key12 (its filter bit
+// is known to be set).
+WALT_HD void taint_slots(const SubIndexView& ix, uint32_t key12, uint32_t& t0, uint32_t& t1) {
+  const uint32_t word = key12 >> 5, bit = key12 & 31u;
+  const uint32_t idx = ix.taint_rank[word] + popc32(ix.taint_bits[word] & ((1u << bit) - 1u));
+  t0 = ix.taint_start[idx]; t1 = ix.taint_start[idx + 1u];
+}
+// inverse of ternary_digit: the converted code of a base-3 digit (CT {A,G,T}, GA {A,C,T})
+WALT_HD uint32_t digit_code(uint32_t d, bool ag) { return ag ? (d == 2u ? 3u : d) : (d == 0u ? 0u : d + 1u); }
+
+// IndexRegion (mapping.cpp:198-222) replayed literally over the 12-mer bucket [first, second) of
+// key12: same probes, same decisions, same result -- but most probes are answered without touching
+// the entry or the genome.  Every probe asks for seed character p of the entry in some slot.  All
+// entries but the tainted ones (whose probed characters may lie past their chromosome's end: the
+// bucket's slice of the taint list, with their slots) were sorted by exactly the characters the
+// reference reads, so for such a slot
+//   * p < depth: inside the table range of the read's first p characters the character is given
+//     by where the slot lies between the four table boundaries of the range's three sub-ranges
+//     (four independent loads per CHARACTER instead of two dependent ones per probe);
+//   * depth <= p < depth + FP_DIGITS: it is a digit of the entry's fingerprint (one load);
+// everything else (tainted slots, slots outside the range, later characters) is read as the
+// reference reads it.  On a bucket of 2^18 entries this turns ~400 dependent pairs of cache
+// misses into about a dozen.
+WALT_HD void literal_index_region(const SubIndexView& ix, uint32_t genome_len, const Pow3& p3, const uint64_t* R,
+                                  uint32_t seed_i, uint32_t seed_len, uint32_t key12, uint32_t& first,
+                                  uint32_t& second) {
+  const bool ag = ix.ag != 0u;
+  uint32_t t0 = 0u, t1 = 0u;
+  if ((ix.taint_bits[key12 >> 5] >> (key12 & 31u)) & 1u) taint_slots(ix, key12, t0, t1);
+  auto tainted = [&](uint32_t slot) {
+    for (uint32_t t = t0; t < t1; ++t) if (ix.taint_slot[t] == slot) return true;
+    return false;
+  };
   uint32_t l = first, u = second - 1u;
-  for (uint32_t p = KEY_WEIGHT; p < seed_len; ++p) {
+  uint32_t prefix = key12;
+  bool ok = true;
+  for (uint32_t p = KEY_WEIGHT; p < seed_len && ok; ++p) {
     const uint32_t cp = 3u * p + 1u;
-    const uint32_t ch = 1u + packed_base(R, seed_i + cp);
-    auto probe = [&](uint32_t slot) { return literal_char(ix.genome, (uint64_t)ix.entries[slot].pos + cp, genome_len); };
-    l = literal_bound<false, LEVELS>(l, u, ch, probe);
-    u = literal_bound<true, LEVELS>(l, u, ch, probe);
-    if (l == u && ch != probe(l)) {
-      first = 1u; second = 0u;
-      return;
+    const uint32_t code = packed_base(R, seed_i + cp);
+    const uint32_t ch = 1u + code;
+    auto read_it = [&](uint32_t slot) { return literal_char(ix.genome, (uint64_t)ix.entries[slot].pos + cp, genome_len); };
+    if (p < ix.depth) {
+      const uint32_t s = p3.v[ix.depth - 1u - p];
+      const uint32_t b0 = ix.table[3u * prefix * s], b1 = ix.table[(3u * prefix + 1u) * s],
+                     b2 = ix.table[(3u * prefix + 2u) * s], b3 = ix.table[(3u * prefix + 3u) * s];
+      ok = literal_step(l, u, ch, [&](uint32_t slot) {
+        if (slot < b0 || slot >= b3 || tainted(slot)) return read_it(slot);
+        return 1u + digit_code((slot >= b1 ? 1u : 0u) + (slot >= b2 ? 1u : 0u), ag);
+      });
+      prefix = 3u * prefix + ternary_digit(code, ag);
+    } else if (p < ix.depth + FP_DIGITS) {
+      const uint32_t div = p3.v[FP_DIGITS - 1u - (p - ix.depth)];
+      ok = literal_step(l, u, ch, [&](uint32_t slot) {
+        if (tainted(slot)) return read_it(slot);
+        return 1u + digit_code((ix.entries[slot].fp / div) % 3u, ag);
+      });
+    } else {
+      ok = literal_step(l, u, ch, read_it);
     }
   }
-  if (l > u) { first = 1u; second = 0u; return; }
+  if (!ok || l > u) { first = 1u; second = 0u; return; }
   first = l; second = u;
-}
-// `levels` of the decision tree probed per step: 1 (the plain search), 2 or 3
-WALT_HD void literal_index_region(const SubIndexView& ix, uint32_t genome_len, const uint64_t* R,
-                                  uint32_t seed_i, uint32_t seed_len, uint32_t& first,
-                                  uint32_t& second, uint32_t levels = 1u) {
-  if (levels >= 3u) literal_index_region_l<3u>(ix, genome_len, R, seed_i, seed_len, first, second);
-  else if (levels == 2u) literal_index_region_l<2u>(ix, genome_len, R, seed_i, seed_len, first, second);
-  else literal_index_region_l<1u>(ix, genome_len, R, seed_i, seed_len, first, second);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -798,16 +819,8 @@ WALT_HD void replay_heap_log(const HeapEntry* log, uint32_t n_log, uint32_t cap,
 struct MapConfig {
   uint32_t b;            // -b
   uint32_t literal_all;  // test hook: replay IndexRegion literally for every lookup
-  uint32_t lit_levels;   // literal_regions: levels of the search tree probed per step (0/1 = plain search)
 };
 
-// Slots [t0, t1) of the taint list that hold positions whose 12-mer key is key12 (its filter bit
-// is known to be set).
-WALT_HD void taint_slots(const SubIndexView& ix, uint32_t key12, uint32_t& t0, uint32_t& t1) {
-  const uint32_t word = key12 >> 5, bit = key12 & 31u;
-  const uint32_t idx = ix.taint_rank[word] + popc32(ix.taint_bits[word] & ((1u << bit) - 1u));
-  t0 = ix.taint_start[idx]; t1 = ix.taint_start[idx + 1u];
-}
 
 // Is there a tainted entry in this 12-mer bucket whose in-chromosome seed characters all
 // match the read (so that the reference's search would look at its out-of-chromosome bytes)?
@@ -1151,7 +1164,7 @@ WALT_HD void seed_lookup(W& w, const SubIndexView& ix, const ChromView& cv, cons
     if (bucket_lo == bucket_hi) return;
     if (lane == 0u) { ctr.lookups++; ctr.literal++; }
     uint32_t f = bucket_lo, s = bucket_hi;
-    literal_index_region(ix, cv.genome_len, R, seed_i, seed_len, f, s);
+    literal_index_region(ix, cv.genome_len, p3, R, seed_i, seed_len, key12, f, s);
     if (s - f + 1u > cfg.b) return;      // mapping.cpp:275-277 (u32 arithmetic; (1,0) -> 0)
     if (f > s) return;                   // failed search: empty candidate loop
     first = f; last_excl = s + 1u;
@@ -1271,11 +1284,23 @@ WALT_HD void replay_lookup(W& w, const SubIndexView& ix, const ChromView& cv, co
 // candidates are folded, so six lanes of the group run them concurrently -- one dependent chain
 // table -> entries -> genome window per lane instead of six in sequence -- and only the fold
 // (with the reference's early exits, mapping.cpp:248-257 / paired.cpp:127-137) is ordered.
-// A lane gives up (returns false) when the lookup needs the group: a tainted 12-mer bucket
-// (possible literal replay) or more than LANE_RUN_CAP fingerprint-equal slots (repeats).
+// A lane gives up when the lookup needs the group: more than LANE_RUN_CAP candidate slots (repeats).
+// A lookup that needs the literal IndexRegion replay (tainted bucket) is replayed by its lane.
 // `emit(g, mm)` receives the verified candidates in index order; `discard()` is called if the
 // lookup turns out to be filtered by -b after some were emitted.
-// LANE_GROUP: the whole lookup is the group's job (tainted bucket).  LANE_RUN: more than LANE_RUN_CAP
+// The literal IndexRegion replay for one lookup by one lane: false if the 12-mer bucket is empty, else
+// the inclusive region ((1, 0) for a failed search).
+WALT_HD_NOINLINE bool lane_literal_region(const SubIndexView& ix, uint32_t genome_len, const Pow3& p3, const uint64_t* R,
+                                          uint32_t seed_i, uint32_t seed_len, uint32_t key12, uint32_t& f, uint32_t& t) {
+  const uint32_t k12_span = p3.v[ix.depth - KEY_WEIGHT];
+  const uint32_t bucket_lo = ix.table[key12 * k12_span], bucket_hi = ix.table[(key12 + 1u) * k12_span];
+  if (bucket_lo == bucket_hi) return false;
+  f = bucket_lo; t = bucket_hi;
+  literal_index_region(ix, genome_len, p3, R, seed_i, seed_len, key12, f, t);
+  return true;
+}
+
+// LANE_GROUP: the whole lookup is the group's job (a literal region of more than LANE_RUN_CAP slots).  LANE_RUN: more than LANE_RUN_CAP
 // fingerprint-equal slots; `run` then says where the run starts and where its table range ends, so
 // that a whole warp can stream it (run_lookup) without searching again.
 enum LaneResult : uint32_t { LANE_DONE = 0u, LANE_GROUP = 1u, LANE_RUN = 2u, LANE_LIT = 3u };   // LANE_LIT: literal lookup, region known
@@ -1308,46 +1333,61 @@ WALT_HD LaneResult lane_lookup(const SubIndexView& ix, const ChromView& cv, cons
 
   const uint32_t lo = ix.table[lo_key], hi = ix.table[hi_key];
   // a tainted bucket needs the literal replay only if the read agrees with a tainted position
-  // on every seed character inside the chromosome (rare; the replay is the group's job)
-  if (((ix.taint_bits[key12 >> 5] >> (key12 & 31u)) & 1u) && lane_is_affected(ix, sc.R, seed_i, seed_len, key12))
-    return LANE_GROUP;
-  if (lo == hi) return LANE_DONE;
-  ctr.lookups++;
-  // first slot of [lo, hi) whose fingerprint is >= fp_lo: bisect down to a LANE_RUN_CAP window
+  // on every seed character inside the chromosome (rare) ...
+  bool literal = false;
   uint32_t l = lo, h = hi;
-  // (the window [l, l + CAP) must hold slot h unless h is the end of the range)
-  while (h - l > LANE_RUN_CAP || (h - l == LANE_RUN_CAP && h < hi)) {
-    const uint32_t mid = l + ((h - l) >> 1);
-    if (ix.entries[mid].fp < fp_lo) l = mid + 1u; else h = mid;
-  }
   Entry en[LANE_RUN_CAP];
-  WALT_UNROLL
-  for (uint32_t k = 0; k < LANE_RUN_CAP; ++k) en[k] = ix.entries[l + k];   // 64 readable pad entries behind index[]
   uint32_t match = 0u;
-  WALT_UNROLL
-  for (uint32_t k = 0; k < LANE_RUN_CAP; ++k)
-    if (l + k < hi && en[k].fp - fp_lo <= fp_span) match |= 1u << k;      // unsigned: also rejects fp < fp_lo
-  if (match == 0u) return LANE_DONE;
-  // fingerprints are sorted inside a table range, so the matches are one run; it is complete
-  // unless it touches the end of the window and the range goes on
-  if ((match >> (LANE_RUN_CAP - 1u)) && l + LANE_RUN_CAP < hi) {
-    // ... then the window is moved onto the run's first slot (a lone hit in the window's last slot
-    // is the common case on T-rich keys, whose table ranges hold many slots), and only a run that
-    // fills it AND goes on is somebody else's job
-    const uint32_t f0 = l + (uint32_t)ffs32(match) - 1u;
-    if (f0 != l) {
-      l = f0;
-      WALT_UNROLL
-      for (uint32_t k = 0; k < LANE_RUN_CAP; ++k) en[k] = ix.entries[l + k];
-      match = 0u;
-      WALT_UNROLL
-      for (uint32_t k = 0; k < LANE_RUN_CAP; ++k)
-        if (l + k < hi && en[k].fp - fp_lo <= fp_span) match |= 1u << k;
+  if (((ix.taint_bits[key12 >> 5] >> (key12 & 31u)) & 1u) && lane_is_affected(ix, sc.R, seed_i, seed_len, key12)) {
+    // ... which this lane does on its own (a chain of dependent loads that the other warps of the SM
+    // cover); only a literal region longer than LANE_RUN_CAP goes to the group
+    uint32_t f, t;
+    if (!lane_literal_region(ix, cv.genome_len, p3, sc.R, seed_i, seed_len, key12, f, t)) return LANE_DONE;   // empty bucket
+    if (f <= t && t - f + 1u <= cfg.b && t - f + 1u > LANE_RUN_CAP) return LANE_GROUP;
+    ctr.lookups++; ctr.literal++;
+    if (t - f + 1u > cfg.b || f > t) return LANE_DONE;      // mapping.cpp:275-277 (u32 arithmetic; (1,0) -> 0); failed search
+    literal = true;
+    l = f;
+    match = (1u << (t - f + 1u)) - 1u;                      // every slot of the region is a candidate
+    WALT_UNROLL
+    for (uint32_t k = 0; k < LANE_RUN_CAP; ++k) en[k] = ix.entries[l + k];
+  }
+  if (!literal) {
+    if (lo == hi) return LANE_DONE;
+    ctr.lookups++;
+    // first slot of [lo, hi) whose fingerprint is >= fp_lo: bisect down to a LANE_RUN_CAP window
+    // (the window [l, l + CAP) must hold slot h unless h is the end of the range)
+    while (h - l > LANE_RUN_CAP || (h - l == LANE_RUN_CAP && h < hi)) {
+      const uint32_t mid = l + ((h - l) >> 1);
+      if (ix.entries[mid].fp < fp_lo) l = mid + 1u; else h = mid;
     }
-    if (match == (1u << LANE_RUN_CAP) - 1u && l + LANE_RUN_CAP < hi && ix.entries[l + LANE_RUN_CAP].fp - fp_lo <= fp_span) {
-      run.f0 = l; run.hi = hi; run.fp_lo = fp_lo;
-      WALT_PREFETCH(ix.entries + run.f0 + LANE_RUN_CAP + 16u);   // the streaming pass starts here
-      return LANE_RUN;
+    WALT_UNROLL
+    for (uint32_t k = 0; k < LANE_RUN_CAP; ++k) en[k] = ix.entries[l + k];   // 64 readable pad entries behind index[]
+    WALT_UNROLL
+    for (uint32_t k = 0; k < LANE_RUN_CAP; ++k)
+      if (l + k < hi && en[k].fp - fp_lo <= fp_span) match |= 1u << k;      // unsigned: also rejects fp < fp_lo
+    if (match == 0u) return LANE_DONE;
+    // fingerprints are sorted inside a table range, so the matches are one run; it is complete
+    // unless it touches the end of the window and the range goes on
+    if ((match >> (LANE_RUN_CAP - 1u)) && l + LANE_RUN_CAP < hi) {
+      // ... then the window is moved onto the run's first slot (a lone hit in the window's last slot
+      // is the common case on T-rich keys, whose table ranges hold many slots), and only a run that
+      // fills it AND goes on is somebody else's job
+      const uint32_t f0 = l + (uint32_t)ffs32(match) - 1u;
+      if (f0 != l) {
+        l = f0;
+        WALT_UNROLL
+        for (uint32_t k = 0; k < LANE_RUN_CAP; ++k) en[k] = ix.entries[l + k];
+        match = 0u;
+        WALT_UNROLL
+        for (uint32_t k = 0; k < LANE_RUN_CAP; ++k)
+          if (l + k < hi && en[k].fp - fp_lo <= fp_span) match |= 1u << k;
+      }
+      if (match == (1u << LANE_RUN_CAP) - 1u && l + LANE_RUN_CAP < hi && ix.entries[l + LANE_RUN_CAP].fp - fp_lo <= fp_span) {
+        run.f0 = l; run.hi = hi; run.fp_lo = fp_lo;
+        WALT_PREFETCH(ix.entries + run.f0 + LANE_RUN_CAP + 16u);   // the streaming pass starts here
+        return LANE_RUN;
+      }
     }
   }
   const uint64_t* R = sc.R;
@@ -1362,8 +1402,10 @@ WALT_HD LaneResult lane_lookup(const SubIndexView& ix, const ChromView& cv, cons
     WALT_UNROLL
     for (uint32_t q = 0; q < LANE_RUN_CAP; ++q) if (q == k) e = en[q].pos;
     const WindowResult r = compare_window(ix.genome, (uint64_t)e + PAD_BASES - seed_i, R, VM, SM, nw);
-    if (!r.seed_equal) continue;
-    ++n_region;
+    if (!literal) {
+      if (!r.seed_equal) continue;
+      ++n_region;
+    }
     const uint32_t chr = chrom_of(cv.starts, cv.n_chr, e);   // bounds, mapping.cpp:281-286
     const uint32_t g = e - seed_i;
     if ((e - cv.starts[chr] >= seed_i) && !(g + read_len >= cv.starts[chr + 1u])) {
@@ -1472,7 +1514,7 @@ WALT_HD void literal_regions(const SubIndexView* ix2, uint32_t genome_len, const
     const uint32_t bucket_lo = ix.table[key12 * k12_span], bucket_hi = ix.table[(key12 + 1u) * k12_span];
     if (bucket_lo == bucket_hi) { out[2u * j] = LIT_EMPTY; continue; }
     uint32_t f = bucket_lo, l = bucket_hi;
-    literal_index_region(ix, genome_len, R, seed_i, seed_len, f, l, cfg.lit_levels);
+    literal_index_region(ix, genome_len, p3, R, seed_i, seed_len, key12, f, l);
     out[2u * j] = f; out[2u * j + 1u] = l;
   }
 }

@@ -64,10 +64,10 @@ struct HwGroup {
 SubIndexView DeviceSubIndex::view(int which) const {
   SubIndexView v;
   v.genome = genome; v.entries = entries; v.table = table; v.taint_bits = taint_bits;
-  // one allocation: filter bits | rank per word | start per distinct key (+1) | pos | len
+  // one allocation: filter bits | rank per word | start per distinct key (+1) | pos | len | slot
   const size_t words = (N_KEY12 + 31u) / 32u;
   v.taint_rank = taint_bits + words; v.taint_start = taint_bits + 2 * words;
-  v.taint_pos = v.taint_start + n_taint_keys + 1u; v.taint_len = v.taint_pos + n_taint;
+  v.taint_pos = v.taint_start + n_taint_keys + 1u; v.taint_len = v.taint_pos + n_taint; v.taint_slot = v.taint_len + n_taint;
   v.n_taint = n_taint; v.index_size = index_size; v.depth = depth; v.ag = which >= 2 ? 1u : 0u;
   return v;
 }
@@ -137,9 +137,11 @@ __global__ void pack_ascii_kernel(const uint8_t* __restrict__ ascii, uint64_t n_
 }
 
 // per slot: table key (first `depth` seed characters) and the {position, fingerprint} entry
+// ... and, for the few positions on the taint list, the slot they sit in (literal_index_region)
 __global__ void table_keys_kernel(const uint64_t* __restrict__ genome, const uint32_t* __restrict__ index,
                                   uint32_t index_size, uint32_t depth, uint32_t ag, ChromView cv, Pow3 p3,
-                                  uint32_t* __restrict__ keys, Entry* __restrict__ entries) {
+                                  uint32_t* __restrict__ keys, Entry* __restrict__ entries, SubIndexView tv,
+                                  uint32_t* __restrict__ taint_slot) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= index_size) return;
   const uint32_t e = index[i];
@@ -148,6 +150,15 @@ __global__ void table_keys_kernel(const uint64_t* __restrict__ genome, const uin
   keys[i] = entry_table_key(genome, e, ce, depth, ag != 0u, p3);
   Entry en; en.pos = e; en.fp = entry_fingerprint(genome, e, ce, depth, ag != 0u, p3);
   entries[i] = en;
+  if (ce - e <= TAINT_SPAN) {
+    const uint32_t key12 = entry_key12(genome, e, ag != 0u, p3);
+    if ((tv.taint_bits[key12 >> 5] >> (key12 & 31u)) & 1u) {
+      uint32_t t0, t1;
+      taint_slots(tv, key12, t0, t1);
+      for (uint32_t t = t0; t < t1; ++t)
+        if (tv.taint_pos[t] == e) taint_slot[t] = (uint32_t)i;
+    }
+  }
 }
 
 // table[k] = first slot whose key >= k, for k in [0, n_keys]; slot i owns (key[i-1], key[i]]
@@ -230,6 +241,7 @@ int finalize_subindex(walt_engine* e, int which) {
     flat.insert(flat.end(), start.begin(), start.end());
     for (uint32_t i = 0; i < s.n_taint; ++i) flat.push_back(std::get<1>(t[i]));
     for (uint32_t i = 0; i < s.n_taint; ++i) flat.push_back(std::get<2>(t[i]));
+    flat.insert(flat.end(), (size_t)s.n_taint + 1u, 0xFFFFFFFFu);   // slots: filled by table_keys_kernel
     WALT_CUDA_TRY(cudaMalloc(&s.taint_bits, flat.size() * 4u));
     WALT_CUDA_TRY(cudaMemcpy(s.taint_bits, flat.data(), flat.size() * 4u, cudaMemcpyHostToDevice));
     s.bytes += flat.size() * 4u;
@@ -239,7 +251,8 @@ int finalize_subindex(walt_engine* e, int which) {
   const uint32_t T = 256;
   if (s.index_size)
     table_keys_kernel<<<(uint32_t)(((uint64_t)s.index_size + T - 1) / T), T>>>(
-        s.genome, s.index, s.index_size, s.depth, which >= 2 ? 1u : 0u, chrom_view(e), e->pow3, keys, s.entries);
+        s.genome, s.index, s.index_size, s.depth, which >= 2 ? 1u : 0u, chrom_view(e), e->pow3, keys, s.entries,
+        s.view(which), const_cast<uint32_t*>(s.view(which).taint_slot));
   WALT_CUDA_TRY(cudaMemset(e->d_flags + 2, 0, 4));
   table_fill_kernel<<<(uint32_t)(((uint64_t)s.index_size + 1u + T - 1) / T), T>>>(keys, s.index_size, n_keys, s.table,
                                                                                  e->d_flags + 2);
@@ -630,7 +643,7 @@ pe_heap_kernel(const __grid_constant__ HeapArgs a) {
     mate = t >= a.n ? 1u : 0u; r = t - mate * a.n;
     if (a.parked[0] && a.n_log[mate][r] > SHORT_LOG) return;      // a parked read: below
   } else {
-    if (!a.parked[0]) return;
+    if (!a.parked[0] || t >= 4u * a.n) return;
     uint32_t u = t - 2u * a.n;
     mate = u >= a.n ? 1u : 0u; u -= mate * a.n;
     if (u >= a.queue[mate][1] && u < a.n - a.queue[mate][3]) return;   // between the two ends of the list
@@ -861,7 +874,7 @@ static void fill_common(walt_engine* e, Args& a, const ReadSrc& src, uint32_t n,
   const int base = ag ? WALT_GA10 : WALT_CT00;
   a.ix[0] = e->sub[base].view(base); a.ix[1] = e->sub[base + 1].view(base + 1);
   a.cv = chrom_view(e); a.p3 = e->pow3;
-  a.cfg.b = b; a.cfg.literal_all = e->search_mode == 1 ? 1u : 0u; a.cfg.lit_levels = e->lit_levels;
+  a.cfg.b = b; a.cfg.literal_all = e->search_mode == 1 ? 1u : 0u;
   a.seqs = src.d_seqs; a.offs = src.d_offs; a.seq_base = src.seq_base; a.n = n; a.uniform_len = src.uniform_len;
   a.read_base = src.read_base;
   a.nw_max = std::max<uint32_t>(1u, (src.max_len + 31u) / 32u);
@@ -1113,7 +1126,6 @@ int walt_engine_create(walt_engine** out, int device) {
   if (const char* v = getenv("WALT_PE_LOGGED")) e->pe_logged = atoi(v);
   if (const char* v = getenv("WALT_DEFER")) e->defer = atoi(v);
   if (const char* v = getenv("WALT_LIT_SIDE")) e->lit_side = atoi(v);
-  if (const char* v = getenv("WALT_LIT_LEVELS")) e->lit_levels = (uint32_t)atoi(v);
   if (const char* v = getenv("WALT_LIT")) e->lit_ahead = atoi(v);
   if (const char* v = getenv("WALT_PAIR_WIDE")) e->pair_wide = atoi(v);
   if (const char* v = getenv("WALT_HEAP_SMEM")) e->heap_smem = atoi(v);

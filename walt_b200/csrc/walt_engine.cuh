@@ -104,7 +104,6 @@ struct walt_engine {
                                              // kernels and finished by a warp-per-read kernel
   waltb200::ParkBuf dev_park[2];             // ... of the device-resident calls
   int lit_side = 1;                          // 1: lit_kernel on a side stream, beside the first take-over kernel
-  uint32_t lit_levels = 2;                   // levels of the literal search tree probed per step (literal_bound)
   int lit_ahead = 1;                         // 1: literal regions of parked reads are computed by lit_kernel
   int pair_wide = 1;                         // 1: pairs with long lists are paired by a whole warp
   int heap_smem = 1;                         // 1: pe_heap_kernel keeps its heaps in shared memory when they fit
