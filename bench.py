@@ -17,9 +17,9 @@ pinned host buffers, host<->device copies inside the timed region.  Multi-GPU: o
 GPU (torchrun), full index replica per GPU, reads sharded, no collective on the data path
 ("weak" scaling: 10 M reads per GPU); barrier + max over ranks.
 
-`--workload se_ag` (configs[2]: A-rich reads, -A, the _GA10/_GA11 pair) and `--workload pe`
-(configs[3]: 5 M pairs 2x150 bp, -k 50 -L 1000, all four sub-indexes) measure the other
-full-size configurations with the same contract; the default line is configs[1].
+`--workload se_small | se_ag | pe | pe_stress` (configs[0], [2], [3], [4]) measure the other
+configurations with the same contract; the default line is configs[1] and carries a `configs` block
+with the device-resident timing, roofline and reference parity of the other four at full size.
 
 `--impl reference` times the UNMODIFIED reference (oracle/_ref/libwaltref.so, the reference's
 own SingleEndMapping object code under OpenMP with every host core) on a bounded sample of the
@@ -44,16 +44,26 @@ sys.path.insert(0, ROOT)
 
 HG19_MB = [249.25, 243.20, 198.02, 191.15, 180.92, 171.12, 159.14, 146.36, 141.21, 135.53, 135.01, 133.85,
            115.17, 107.35, 102.53, 90.35, 81.20, 78.08, 59.13, 63.03, 48.13, 51.30, 155.27, 59.37]
-METRICS = {"se": ("reads mapped/sec (SE 150bp, hg19-size synthetic)", "reads/s"),
+METRICS = {"se_small": ("reads mapped/sec (SE 100bp, 10 Mb synthetic genome)", "reads/s"),
+           "se": ("reads mapped/sec (SE 150bp, hg19-size synthetic)", "reads/s"),
            "se_ag": ("reads mapped/sec (SE 150bp -A, hg19-size synthetic)", "reads/s"),
            "pe": ("read pairs mapped/sec (PE 2x150bp -k 50 -L 1000, hg19-size synthetic)", "pairs/s"),
            "pe_stress": ("read pairs mapped/sec (PBAT PE 2x150bp -P -m 8 -b 5000, repeat-heavy synthetic genome, "
                          "30% adaptor read-through)", "pairs/s")}
-MISMATCHES = {"se": 6, "se_ag": 6, "pe": 6, "pe_stress": 8}
+MISMATCHES = {"se_small": 6, "se": 6, "se_ag": 6, "pe": 6, "pe_stress": 8}
+# genome (Mb), reads (pairs) per GPU, read length of BASELINE.json's configs[0..4]
+FULL_SIZE = {"se_small": (10.0, 100_000, 100), "se": (3100.0, 10_000_000, 150), "se_ag": (3100.0, 10_000_000, 150),
+             "pe": (3100.0, 5_000_000, 150), "pe_stress": (3100.0, 5_000_000, 150)}
+CONFIG_NO = {"se_small": 0, "se": 1, "se_ag": 2, "pe": 3, "pe_stress": 4}
 M, B, TOP_K, FRAG = 6, 5000, 50, 1000
 
 
-def chrom_lengths(total_bases):
+def chrom_lengths(total_bases, kind="se"):
+    if kind == "se_small":     # four chromosomes
+        w = np.array([0.4, 0.3, 0.2, 0.1])
+        lens = np.floor(w * total_bases).astype(np.int64)
+        lens[0] += total_bases - lens.sum()
+        return lens.astype(np.uint32)
     w = np.array(HG19_MB) / np.sum(HG19_MB)
     lens = np.floor(w * total_bases).astype(np.int64)
     lens[0] += total_bases - lens.sum()
@@ -145,13 +155,23 @@ class ClockSampler:
                 "samples": len(rows), "how": "NVML, sampled every 4 ms inside the timed regions"}
 
 
-def committed_traffic(kernel, n_reads, genome_mb):
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of
-    this same command (profiles/traffic.json); None when the workload differs from the captured one."""
+def kernel_source_hash():
+    """sha256 (16 hex digits) of the CUDA sources the mapping kernels are compiled from"""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("walt_core.cuh", "walt_engine.cu"):
+        h.update(open(os.path.join(ROOT, "walt_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def committed_traffic(kind, n_reads, genome_mb):
+    """DRAM bytes per step (all mapping kernels of one device-resident step) from the committed
+    `ncu --set full` capture of this same command (profiles/traffic.json) -- only if that capture was
+    taken on the kernel sources that are being measured now (source hash) and on the same workload."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]
-        if t["reads_per_launch"] == n_reads and abs(t["genome_mb"] - genome_mb) < 1e-6:
-            return t["dram_bytes_per_launch"]
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kind]
+        if t["reads_per_step"] == n_reads and abs(t["genome_mb"] - genome_mb) < 1e-6 and t["source_sha16"] == kernel_source_hash():
+            return t
     except Exception:
         pass
     return None
@@ -179,22 +199,24 @@ def algorithmic_bytes(ctr, n_reads, rl, pe=False):
 class Workload:
     """Per-rank synthetic genome, resident index and read batch."""
 
-    def __init__(self, args, device, rank):
+    def __init__(self, args, device, rank, kind=None, genome_mb=None, reads=None, read_len=None):
         import torch
         import walt_b200
         from walt_b200 import engine as eng
         self.torch, self.eng = torch, eng
         self.device = device
-        self.kind = getattr(args, "workload", "se")
+        self.kind = kind or getattr(args, "workload", "se")
+        self.genome_mb = float(genome_mb if genome_mb is not None else args.genome_mb)
         self.ag = self.kind == "se_ag"
         self.is_pe = self.kind in ("pe", "pe_stress")
         self.pbat = self.kind == "pe_stress"
         self.m = MISMATCHES[self.kind]
-        self.which = {"se": (0, 1), "se_ag": (2, 3), "pe": (0, 1, 2, 3), "pe_stress": (0, 1, 2, 3)}[self.kind]
-        self.n, self.rl = args.reads, args.read_len
-        total = int(args.genome_mb * 1e6)
-        self.lengths = chrom_lengths(total)
-        self.names = [f"chr{i + 1}" for i in range(22)] + ["chrX", "chrY"]
+        self.which = {"se_small": (0, 1), "se": (0, 1), "se_ag": (2, 3), "pe": (0, 1, 2, 3), "pe_stress": (0, 1, 2, 3)}[self.kind]
+        self.n, self.rl = int(reads if reads is not None else args.reads), int(read_len if read_len is not None else args.read_len)
+        total = int(self.genome_mb * 1e6)
+        self.lengths = chrom_lengths(total, self.kind)
+        self.names = [f"chr{i + 1}" for i in range(len(self.lengths))] if self.kind == "se_small" else \
+            [f"chr{i + 1}" for i in range(22)] + ["chrX", "chrY"]
         t0 = time.time()
         self.e = walt_b200.Engine(device)
         self.e.set_group_width(args.group_width)
@@ -237,9 +259,12 @@ class Workload:
                                  ag=self.ag, m=self.m, b=B, stream=stream)
 
     def launches_per_step(self):
-        if not self.is_pe:
-            return 1
-        return self.e.stats()["n_kernel_launches"]   # launches of the last device call (3 per chunk)
+        return self.e.stats()["n_kernel_launches"]   # launches of the last device call
+
+    def close(self):
+        self.e.close()
+        self.d_reads = self.d_reads2 = self.d_offs = self.d_out = None
+        self.torch.cuda.empty_cache()
 
     def host_index(self):
         """Export the resident sub-indexes into reference-owned Genome/HashTable objects."""
@@ -339,38 +364,63 @@ def oracle_counters(wl, hidx, n):
 
 
 def parity_vs_reference(wl, n, ref_result):
-    """Fields of the engine's results that differ from the unmodified reference's on the first n
-    reads (pairs).  PE compares the drained heaps (through the full-list entry point)."""
+    """Fields of the results the TIMED device-resident call left in wl.d_out that differ from the
+    unmodified reference's on the first n reads (pairs).  SE: BestMatch.  PE: the walt_pe_result of
+    walt_engine_map_pe_device against what MergePairedEndResults (paired.cpp:438-570; oracle
+    restatement wo_pe_result_batch) derives from the drained heaps of the reference's
+    PairEndMapping (libwaltref.so): pairing result, winning candidates, GetBestMatch4Single."""
     import refio
     if not wl.is_pe:
         got = wl.d_out[: n * 16].cpu().numpy().view(refio.BEST_DT)
         return sum(int((got[f] != ref_result[f]).sum()) for f in ("genome_pos", "times", "mismatch", "strand"))
-    n = min(n, 200000)
-    b1, o1 = wl.sample_reads(n, 1)
-    b2, o2 = wl.sample_reads(n, 2)
-    r = wl.e.map_pe(b1, o1, b2, o2, m=wl.m, b=B, top_k=TOP_K, frag_range=FRAG)
+    Lo = refio.oracle_lib()
+    starts = np.concatenate([[0], np.cumsum(wl.lengths.astype(np.uint64))]).astype(np.uint32)
+    lengths = np.ascontiguousarray(wl.lengths, np.uint32)
+    chroms = refio.WoChroms(len(lengths), starts.ctypes.data, lengths.ctypes.data)
+    offs = np.arange(n + 1, dtype=np.uint64) * np.uint64(wl.rl)
+    (r1, s1), (r2, s2) = ref_result[1], ref_result[2]          # bisulfite roles: 1 = C->T mate, 2 = G->A mate
+    want = np.zeros(n, dtype=wl.out_dt)
+    Lo.wo_pe_result_batch(C.byref(chroms), r1.ctypes.data_as(C.c_void_p), s1.ctypes.data_as(C.c_void_p),
+                          offs.ctypes.data_as(C.c_void_p), r2.ctypes.data_as(C.c_void_p), s2.ctypes.data_as(C.c_void_p),
+                          offs.ctypes.data_as(C.c_void_p), C.c_uint32(n), C.c_uint32(TOP_K), C.c_uint32(wl.m), C.c_int(FRAG),
+                          want.ctypes.data_as(C.c_void_p))
+    if wl.pbat:   # derived oracle (SURVEY.md 8(c)): the reference on exchanged mates, per-mate fields handed back
+        sw = want.copy()
+        sw["pair"]["best_i"], sw["pair"]["best_j"] = want["pair"]["best_j"], want["pair"]["best_i"]
+        sw["c1"], sw["c2"], sw["single1"], sw["single2"] = want["c2"], want["c1"], want["single2"], want["single1"]
+        want = sw
+    got = wl.d_out[: n * wl.out_dt.itemsize].cpu().numpy().view(wl.out_dt)
     bad = 0
-    for mate in (1, 2):
-        ranked, sizes = ref_result[mate]
-        bad += int((r[f"n{mate}"] != sizes[:n]).sum())
-        for f in ("genome_pos", "mismatch", "strand"):
-            bad += int((r[f"ranked{mate}"][f] != ranked[:n][f]).sum())
+    for f in ("best_times", "best_i", "best_j", "frag_len"):
+        bad += int((got["pair"][f] != want["pair"][f]).sum())
+    for rec, fields in (("c1", ("genome_pos", "mismatch", "strand")), ("c2", ("genome_pos", "mismatch", "strand")),
+                        ("single1", ("genome_pos", "times", "mismatch", "strand")),
+                        ("single2", ("genome_pos", "times", "mismatch", "strand"))):
+        for f in fields:
+            bad += int((got[rec][f] != want[rec][f]).sum())
     return bad
 
 
+def workload_text(kind, genome_mb, reads, read_len):
+    return {"se_small": f"configs[0]: {genome_mb:g} Mb synthetic genome (4 chr), {reads} SE {read_len} bp bisulfite reads per GPU, "
+                        f"-m {M} -b {B}",
+            "se": f"configs[1]: {genome_mb:g} Mb synthetic genome (24 chr, hg19 profile), {reads} SE "
+                  f"{read_len} bp bisulfite reads per GPU, -m {M} -b {B}",
+            "se_ag": f"configs[2]: {genome_mb:g} Mb synthetic genome (24 chr, hg19 profile), {reads} A-rich SE "
+                     f"{read_len} bp reads per GPU, -A -m {M} -b {B}",
+            "pe": f"configs[3]: {genome_mb:g} Mb synthetic genome (24 chr, hg19 profile), {reads} pairs "
+                  f"2x{read_len} bp per GPU, -m {M} -b {B} -k {TOP_K} -L {FRAG}",
+            "pe_stress": f"configs[4]: {genome_mb:g} Mb repeat-heavy synthetic genome (2000 repeat families, ~40 % of "
+                         f"the bases), {reads} PBAT pairs 2x{read_len} bp per GPU, 30 % adaptor read-through "
+                         f"(as clipped by -C), -P -m 8 -b {B} -k {TOP_K} -L {FRAG}"}[kind]
+
+
 def config_dict(args, extra=None):
-    what = {"se": f"configs[1]: {args.genome_mb:g} Mb synthetic genome (24 chr, hg19 profile), {args.reads} SE "
-                  f"{args.read_len} bp bisulfite reads per GPU, -m {M} -b {B}",
-            "se_ag": f"configs[2]: {args.genome_mb:g} Mb synthetic genome (24 chr, hg19 profile), {args.reads} A-rich SE "
-                     f"{args.read_len} bp reads per GPU, -A -m {M} -b {B}",
-            "pe": f"configs[3]: {args.genome_mb:g} Mb synthetic genome (24 chr, hg19 profile), {args.reads} pairs "
-                  f"2x{args.read_len} bp per GPU, -m {M} -b {B} -k {TOP_K} -L {FRAG}",
-            "pe_stress": f"configs[4]: {args.genome_mb:g} Mb repeat-heavy synthetic genome (2000 repeat families, ~40 % of "
-                         f"the bases), {args.reads} PBAT pairs 2x{args.read_len} bp per GPU, 30 % adaptor read-through "
-                         f"(as clipped by -C), -P -m 8 -b {B} -k {TOP_K} -L {FRAG}"}[args.workload]
-    d = {"workload": what, "genome_mb": args.genome_mb, "reads_per_gpu": args.reads, "read_len": args.read_len,
+    d = {"workload": workload_text(args.workload, args.genome_mb, args.reads, args.read_len), "genome_mb": args.genome_mb,
+         "reads_per_gpu": args.reads, "read_len": args.read_len,
          "max_mismatches": MISMATCHES[args.workload], "bucket_limit": B, "parallelism": f"reads sharded x{args.gpus}, index replicated",
-         "l2": "inputs larger than L2 (index >= 13 GB per strand randomly gathered, >= 1.5 GB of reads streamed per step)"}
+         "l2": "inputs larger than L2 (index >= 13 GB per strand randomly gathered, >= 1.5 GB of reads streamed per step)"
+               if args.genome_mb >= 500 else "L2 flushed between timed steps (a 256 MB buffer is rewritten)"}
     if extra:
         d.update(extra)
     return d
@@ -399,7 +449,7 @@ def write_fastq_fixed(path, seqs, n, rl):
             f.write(a.tobytes())
 
 
-def cli_leg(device, genome_mb, n_reads, rl, workdir=None, keep=False):
+def cli_leg(device, genome_mb, n_reads, rl, workdir=None, keep=False, small=False):
     """makedb-equivalent on the device -> .dbindex files; synthetic FASTQ; then `walt_b200/bin/walt`
     and the unmodified reference `oracle/_ref/walt -t <cores>` on the same files, wall clock of each
     whole process (index load, FASTQ parse, mapping, SAM formatting), outputs compared byte for byte."""
@@ -414,8 +464,8 @@ def cli_leg(device, genome_mb, n_reads, rl, workdir=None, keep=False):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import refio
     total = int(genome_mb * 1e6)
-    lengths = chrom_lengths(total)
-    names = [f"chr{i + 1}" for i in range(22)] + ["chrX", "chrY"]
+    lengths = chrom_lengths(total, "se_small" if small else "se")
+    names = [f"chr{i + 1}" for i in range(len(lengths))] if small else [f"chr{i + 1}" for i in range(22)] + ["chrX", "chrY"]
     work = tempfile.mkdtemp(prefix="walt_cli_", dir=workdir or os.environ.get("WALT_BENCH_TMP") or None)
     out = {"genome_mb": genome_mb, "reads": n_reads, "read_len": rl}
     try:
@@ -609,6 +659,175 @@ def run_reference(args):
     return 0
 
 
+def time_device_steps(wl, steps, warmup, stream, barrier, flush_l2=False):
+    """W untimed steps, then K timed ones (CUDA events on the launching stream).  flush_l2: the index of
+    the workload fits the L2, so a 256 MB buffer is rewritten between the steps and every step is timed
+    by its own pair of events; otherwise one pair of events brackets the K steps back to back."""
+    import torch
+    for _ in range(warmup):
+        wl.device_step(stream.cuda_stream)
+    barrier()
+    t0 = time.perf_counter()
+    if flush_l2:
+        junk = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{wl.device}")
+        step_ms = []
+        for _ in range(steps):
+            junk.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            wl.device_step(stream.cuda_stream)
+            b.record(stream)
+            torch.cuda.synchronize()
+            step_ms.append(a.elapsed_time(b))
+        barrier()
+        return step_ms, sum(step_ms) / 1e3, (t0, time.perf_counter())
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    evs[0].record(stream)
+    for i in range(steps):
+        wl.device_step(stream.cuda_stream)
+        evs[i + 1].record(stream)
+    barrier()
+    step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+    return step_ms, evs[0].elapsed_time(evs[-1]) / 1e3, (t0, time.perf_counter())
+
+
+def own_floor_bytes(stats, n, rl, pe):
+    """Sector-level minimum of the table/fingerprint design for the work the engine did (its own lookup
+    and candidate counters): per lookup one 32-byte sector of the prefix table and one of the entry
+    array, per candidate the two sectors its 150-base window spans plus its 8-byte entry, per read the
+    read itself and its result."""
+    io = (2 * rl + 72) if pe else (rl + 16)
+    return (64.0 * stats["n_lookups"] + 72.0 * stats["n_candidates"]) / n + io
+
+
+def side_legs(wl, unit, ref_seconds, want_baseline):
+    """Rank 0, not timed: the C oracle's work counters (algorithmic bytes), the parity of the results
+    the timed device-resident step left on the device against the oracle and the unmodified reference,
+    and the reference's OpenMP loops on a bounded sample (the CPU baseline)."""
+    import refio
+    out = {"alg": None, "parity": None, "cpu_baseline": None}
+    if not refio.have_reference():
+        return out
+    n, pe = wl.n, wl.is_pe
+    hidx = wl.host_index()
+    try:
+        ns = min(20000, n)
+        ctr, obest = oracle_counters(wl, hidx, ns)
+        out["alg"] = algorithmic_bytes(ctr, ns, wl.rl, pe)
+        out["alg"]["candidates_per_read"] = ctr["n_cand"] / ns
+        parity = {"sample_reads": ns}
+        if not pe:
+            got = wl.d_out[: ns * 16].cpu().numpy().view(refio.BEST_DT)
+            parity["fields_differing_vs_oracle"] = sum(int((got[f] != obest[f]).sum())
+                                                       for f in ("genome_pos", "times", "mismatch", "strand"))
+            parity["unique_frac"] = float((got["times"] == 1).mean())
+        else:
+            got = wl.d_out[: ns * wl.out_dt.itemsize].cpu().numpy().view(wl.out_dt)
+            parity["unique_pair_frac"] = float((got["pair"]["best_times"] == 1).mean())
+        threads = os.cpu_count() or 1
+        cal_n = min(50000, n)
+        t_cal, _ = reference_pass(wl, hidx, cal_n, threads)
+        cn = int(max(cal_n, min(n, cal_n * ref_seconds / max(t_cal, 1e-6))))
+        if pe:
+            cn = max(cn, min(n, 1_000_000))     # the timed paired-end path is checked on at least a million pairs
+        t_ref, rres = reference_pass(wl, hidx, cn, threads)
+        parity["reference_sample_reads"] = cn
+        parity["fields_differing_vs_reference"] = parity_vs_reference(wl, cn, rres)
+        parity["what"] = ("walt_pe_result of the timed walt_engine_map_pe_device call vs MergePairedEndResults on the "
+                          "reference's drained heaps" if pe else "BestMatch of the timed walt_engine_map_se_device call vs the "
+                          "reference's SingleEndMapping")
+        out["parity"] = parity
+        base = {"value": cn / t_ref, "unit": unit, "cores": threads, "kind": "reference",
+                "sample": f"first {cn} {'pairs' if pe else 'reads'} of the batch, every strand pass, "
+                          f"OpenMP loops of the unmodified reference (oracle/_ref/libwaltref.so), {t_ref:.1f} s"}
+        out["cpu_baseline"] = base if want_baseline else {"value": base["value"], "cores": threads}
+    finally:
+        L = refio.ref_lib()
+        for h in hidx.values():
+            L.waltref_index_free(h)
+    return out
+
+
+def roofline_dict(wl, alg, kernel_s, dstats, genome_mb):
+    """HBM roofline of one device-resident step.  `frac` follows SURVEY.md 8(d): the ALGORITHMIC bytes of
+    the reference's method (its ~110 binary-search probes per lookup) over the step's device time -- a
+    reference-equivalent throughput, not a statement about the memory system.  `dram_frac` is the
+    honest utilisation: DRAM bytes of the committed same-source ncu capture over the same time;
+    `own_floor_bytes` is the sector-level minimum of what this design has to touch."""
+    peak, peak_kind = measured_peak_gbs()
+    n, pe = wl.n, wl.is_pe
+    achieved = alg["total"] * n / kernel_s / 1e9
+    t = committed_traffic(wl.kind, n, genome_mb)
+    floor = own_floor_bytes(dstats, n, wl.rl, pe) if dstats else None
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": t["dram_bytes_per_step"] if t else None, "peak_kind": peak_kind,
+            "kernel": "pe_log_kernel (park / take-over) + pe_heap_kernel + pair_kernel" if pe else "se_map_kernel (park / take-over)",
+            "kernel_ms": kernel_s * 1e3, "algorithmic_bytes_per_read": alg,
+            "seeding": {"algorithmic_bytes_per_read": alg["seed"], "share": alg["seed"] / alg["total"]},
+            "verification": {"algorithmic_bytes_per_read": alg["verify"], "share": alg["verify"] / alg["total"],
+                             "candidates_per_read": alg.get("candidates_per_read"),
+                             "note": "seeding and verification run fused in the mapping kernels, so they share the "
+                                     "step's time; `bench.py --workload verify` times verification alone"},
+            "dram_frac": (t["dram_bytes_per_step"] / kernel_s / 1e9 / peak) if t else None,
+            "dram_bytes_per_read": (t["dram_bytes_per_step"] / n) if t else None,
+            "traffic_source": (t.get("source") if t else
+                               "no ncu capture of these kernel sources (hash %s) on this workload in profiles/traffic.json"
+                               % kernel_source_hash()),
+            "own_floor_bytes": floor,
+            "own_floor_frac": (floor * n / kernel_s / 1e9 / peak) if floor else None,
+            "engine_counters_per_step": dstats,
+            "note": "frac = SURVEY.md 8(d) algorithmic bytes (the reference's binary-search probes) / device time / "
+                    "measured copy bandwidth; dram_frac = measured DRAM bytes (ncu, same kernel sources) / device time / "
+                    "the same peak; own_floor = 64 B per lookup + 72 B per candidate + the read and its result"}
+    return roof
+
+
+def other_configs(args, local, stream, barrier):
+    """configs[0], [2], [3], [4] at full size on rank 0's GPU: device-resident timing, roofline,
+    parity of the timed path against the reference.  Each builds its own genome and index."""
+    out = []
+    for kind in ("se_small", "se_ag", "pe", "pe_stress"):
+        gmb, nreads, rl = FULL_SIZE[kind]
+        scale = float(os.environ.get("WALT_BENCH_SCALE", "1"))   # flow tests only: shrink the other configurations
+        if scale != 1.0 and kind != "se_small":
+            gmb, nreads = gmb * scale, int(nreads * scale)
+        entry = {"config": CONFIG_NO[kind], "workload": workload_text(kind, gmb, nreads, rl)}
+        try:
+            t0 = time.time()
+            wl = Workload(args, local, 0, kind=kind, genome_mb=gmb, reads=nreads, read_len=rl)
+            metric, unit = METRICS[kind]
+            small = gmb < 500
+            step_ms, t_dev, _ = time_device_steps(wl, args.steps, args.warmup, stream, barrier, flush_l2=small)
+            launches = args.steps * wl.launches_per_step()
+            wl.e.device_stats()
+            wl.device_step(stream.cuda_stream)
+            dstats = wl.e.device_stats()
+            kernel_s = float(np.mean(step_ms)) / 1e3
+            entry.update({"metric": metric, "value": nreads * args.steps / t_dev, "unit": unit, "ms_per_step": 1e3 * t_dev / args.steps,
+                          "steps": args.steps, "warmup": args.warmup, "gpu_launches": launches,
+                          "index_build_s": round(wl.t_index, 1), "hbm_index_bytes": wl.e.hbm_bytes(),
+                          "l2": "flushed between timed steps" if small else "inputs larger than L2"})
+            legs = side_legs(wl, unit, 5.0, False)
+            if legs["alg"] is not None:
+                r = roofline_dict(wl, legs["alg"], kernel_s, dstats, gmb)
+                entry["roofline"] = {k: r[k] for k in ("frac", "achieved", "dram_frac", "traffic", "own_floor_bytes", "own_floor_frac",
+                                                       "kernel_ms", "algorithmic_bytes_per_read")}
+            entry["parity_check"] = legs["parity"]
+            entry["fields_differing_vs_reference"] = (legs["parity"] or {}).get("fields_differing_vs_reference")
+            entry["reference"] = legs["cpu_baseline"]
+            wl.close()
+            if kind == "se_small":   # files in -> files out at configs[0] size, against the reference program
+                try:
+                    entry["cli"] = cli_leg(local, gmb, nreads, rl, small=True)
+                except Exception as ex:
+                    entry["cli"] = {"error": str(ex)[-300:]}
+            entry["wall_s"] = round(time.time() - t0, 1)
+        except Exception as ex:
+            entry["error"] = str(ex)[-400:]
+        out.append(entry)
+    return out
+
+
 def run_ours(args):
     import torch
     rank, local, world = dist_env()
@@ -628,6 +847,7 @@ def run_ours(args):
     e, n, rl = wl.e, wl.n, wl.rl
     pe = wl.is_pe
     stream = torch.cuda.current_stream()
+    small = args.genome_mb < 500
 
     def barrier():
         torch.cuda.synchronize()
@@ -635,67 +855,25 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def device_step():
-        wl.device_step(stream.cuda_stream)
-
     # ---- device-resident timing (`value`) ----
-    for _ in range(args.warmup):
-        device_step()
     sampler = ClockSampler(local)
     sampler.start()
-    barrier()
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    w0 = sampler.mark()
-    evs[0].record(stream)
-    for i in range(args.steps):
-        device_step()
-        evs[i + 1].record(stream)
-    barrier()
-    windows = [(w0, sampler.mark())]
-    step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
-    t_dev = evs[0].elapsed_time(evs[-1]) / 1e3
+    step_ms, t_dev, win = time_device_steps(wl, args.steps, args.warmup, stream, barrier, flush_l2=small)
+    windows = [win]
     launches_dev = args.steps * wl.launches_per_step()   # kernels of the timed device-resident steps
+    e.device_stats()
+    wl.device_step(stream.cuda_stream)
+    dstats = e.device_stats()    # work counters of one device-resident step (its results stay in wl.d_out)
 
-    # ---- side legs on rank 0 (not timed): oracle counters, parity spot check, CPU baseline ----
-    cpu_baseline, alg, parity = None, None, None
+    # ---- side legs on rank 0 (not timed): oracle counters, parity of the timed path, CPU baseline ----
+    legs = {"alg": None, "parity": None, "cpu_baseline": None}
     if rank == 0 and not args.no_cpu:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import refio
-        device_step()
-        torch.cuda.synchronize()
-        hidx = wl.host_index() if refio.have_reference() else None
-        if hidx is not None:
-            ns = min(20000, n)
-            ctr, obest = oracle_counters(wl, hidx, ns)
-            alg = algorithmic_bytes(ctr, ns, rl, pe)
-            parity = {"sample_reads": ns}
-            if not pe:
-                got = wl.d_out[: ns * 16].cpu().numpy().view(refio.BEST_DT)
-                parity["fields_differing_vs_oracle"] = sum(int((got[f] != obest[f]).sum())
-                                                           for f in ("genome_pos", "times", "mismatch", "strand"))
-                parity["unique_frac"] = float((got["times"] == 1).mean())
-            else:
-                got = wl.d_out[: ns * wl.out_dt.itemsize].cpu().numpy().view(wl.out_dt)
-                parity["unique_pair_frac"] = float((got["pair"]["best_times"] == 1).mean())
-            if world == 1:
-                threads = os.cpu_count() or 1
-                cal_n = min(50000, n)
-                t_cal, _ = reference_pass(wl, hidx, cal_n, threads)
-                cn = int(max(cal_n, min(n, cal_n * 12.0 / max(t_cal, 1e-6))))
-                t_ref, rres = reference_pass(wl, hidx, cn, threads)
-                parity["reference_sample_reads"] = cn if not pe else min(cn, 200000)
-                parity["fields_differing_vs_reference"] = parity_vs_reference(wl, cn, rres)
-                cpu_baseline = {"value": cn / t_ref, "unit": unit, "cores": threads, "kind": "reference",
-                                "sample": f"first {cn} {'pairs' if pe else 'reads'} of the batch, every strand pass, "
-                                          f"OpenMP loops of the unmodified reference (oracle/_ref/libwaltref.so), "
-                                          f"{t_ref:.1f} s"}
-            L = refio.ref_lib()
-            for h in hidx.values():
-                L.waltref_index_free(h)
+        legs = side_legs(wl, unit, 12.0 if world == 1 else 2.0, world == 1)
+        if world > 1:
+            legs["cpu_baseline"] = None
+    alg, parity, cpu_baseline = legs["alg"], legs["parity"], legs["cpu_baseline"]
 
-    e.device_stats()
-    device_step()
-    dstats = e.device_stats()    # work counters of one device-resident step
     if args.no_e2e:   # kernel experiments only: not a bench line
         sampler.stop(windows)
         if rank == 0:
@@ -732,8 +910,7 @@ def run_ours(args):
     t_e2e = time.perf_counter() - t0
     windows.append((t0, t0 + t_e2e))
     launches_e2e = e.stats()["n_kernel_launches"]
-    nb = 1000 * wl.out_dt.itemsize
-    same = bool(np.array_equal(h_out.array[:1000].view(np.uint8), wl.d_out[:nb].cpu().numpy()))
+    same = bool(np.array_equal(h_out.array.view(np.uint8), wl.d_out.cpu().numpy()))
     ascii_out = h_out.array.copy()
 
     # ---- the same call on 2-bit packed host batches (walt_engine_map_se_packed; `e2e_packed`) ----
@@ -769,21 +946,13 @@ def run_ours(args):
 
     from walt_b200.sharding import max_over_ranks
     t_dev, t_e2e, t_pk = max_over_ranks([t_dev, t_e2e, t_pk], dist, dev)
+    for h in (h_reads, h_reads2, h_offs, h_out, h_pk, h_pk2):
+        if h is not None:
+            h.free()
     if rank == 0:
         total = n * world * args.steps
-        peak, peak_kind = measured_peak_gbs()
         kernel_s = float(np.mean(step_ms)) / 1e3
-        roof = None
-        kname = "pe_log_kernel" if pe else "se_map_kernel"
-        if alg is not None:
-            achieved = alg["total"] * n / kernel_s / 1e9
-            roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": committed_traffic(kname if pe else "se_map_kernel" + ("_ag" if wl.ag else ""), n, args.genome_mb),
-                    "peak_kind": peak_kind, "kernel": kname,
-                    "algorithmic_bytes_per_read": alg, "kernel_ms": kernel_s * 1e3,
-                    "note": "algorithmic bytes follow SURVEY.md 8(d) (the reference's binary-search probes); "
-                            "achieved/frac are that figure over the step's device time"
-                            + (" (per chunk: pe_log_kernel for each mate, pe_heap_kernel, pair_kernel)" if pe else "")}
+        roof = roofline_dict(wl, alg, kernel_s, dstats, args.genome_mb) if alg is not None else None
         line = {"metric": metric, "value": total / t_dev, "unit": unit, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -791,6 +960,7 @@ def run_ours(args):
                                              "table_depth": [e.subindex_info(w)["depth"] for w in wl.which],
                                              "group_width": args.group_width,
                                              "rank0_cpus_local_to_gpu": numa_cpus,
+                                             "kernel_source_sha16": kernel_source_hash(),
                                              "index_tie_order": {"rule": "std::sort replay (byte-identical to reference makedb)",
                                                                  **wl.build_info}}),
                 "clocks": clocks,
@@ -805,16 +975,17 @@ def run_ours(args):
                                "input": "2-bit packed reads (walt_pack_reads, packed by the loader outside the timed region)"},
                 "gpu_launches": launches_dev,
                 "roofline": roof, "cpu_baseline": cpu_baseline, "parity_check": parity}
-        if world == 1 and not pe and not args.no_cpu and not args.no_cli:
-            # files in -> files out through the walt program, next to the reference program (not a timed step)
-            try:
-                line["cli"] = cli_leg(local, args.cli_genome_mb, args.cli_reads, rl)
-            except Exception as ex:   # the bench line stands without it
-                line["cli"] = {"error": str(ex)[-300:]}
+        if world == 1 and args.workload == "se" and not args.no_cpu:
+            wl.close()
+            if not args.no_configs:
+                line["configs"] = other_configs(args, local, stream, barrier)
+            if not args.no_cli:
+                # files in -> files out through the walt program, next to the reference program (not a timed step)
+                try:
+                    line["cli"] = cli_leg(local, args.cli_genome_mb, args.cli_reads, rl)
+                except Exception as ex:   # the bench line stands without it
+                    line["cli"] = {"error": str(ex)[-300:]}
         emit(json.dumps(line))
-    for h in (h_reads, h_reads2, h_offs, h_out, h_pk, h_pk2):
-        if h is not None:
-            h.free()
     if dist is not None:
         dist.destroy_process_group()
     return 0
@@ -838,10 +1009,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--genome-mb", type=float, default=3100.0)
-    ap.add_argument("--workload", default="se", choices=["se", "se_ag", "pe", "pe_stress", "cli"],
-                    help="se = configs[1] (the bench line), se_ag = configs[2], pe = configs[3], pe_stress = configs[4], "
-                         "cli = the walt program on files against the reference program")
+    ap.add_argument("--genome-mb", type=float, default=0.0, help="default: the configuration's full size (3100; 10 for se_small)")
+    ap.add_argument("--workload", default="se", choices=["se_small", "se", "se_ag", "pe", "pe_stress", "cli"],
+                    help="se = configs[1] (the bench line), se_small = configs[0], se_ag = configs[2], pe = configs[3], "
+                         "pe_stress = configs[4], cli = the walt program on files against the reference program")
+    ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (the other four configurations) of the default run")
     ap.add_argument("--cli-genome-mb", type=float, default=300.0)
     ap.add_argument("--cli-reads", type=int, default=10_000_000)
     ap.add_argument("--makedb-genome-mb", type=float, default=50.0,
@@ -849,7 +1021,7 @@ def main():
     ap.add_argument("--makedb-repeats", action="store_true", help="... on the repeat-heavy genome model (tied suffixes)")
     ap.add_argument("--no-cli", action="store_true", help="skip the files-in/files-out leg of the default run")
     ap.add_argument("--reads", type=int, default=0, help="reads (pairs) per GPU; default 10 M reads / 5 M pairs")
-    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--read-len", type=int, default=0, help="default: 150 (100 for se_small)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the oracle/reference side legs")
     ap.add_argument("--no-e2e", action="store_true", help="kernel experiment: print the device timing only")
     ap.add_argument("--group-width", type=int, default=8, help="lanes that own one read (8, 16, 32)")
@@ -860,8 +1032,13 @@ def main():
     os.dup2(2, 1)
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    full = FULL_SIZE.get(args.workload, FULL_SIZE["se"])
+    if args.genome_mb <= 0:
+        args.genome_mb = full[0]
     if args.reads <= 0:
-        args.reads = 5_000_000 if args.workload.startswith("pe") else 10_000_000
+        args.reads = full[1]
+    if args.read_len <= 0:
+        args.read_len = full[2]
     if args.workload == "cli":
         sys.exit(run_cli(args))
     sys.exit(run_reference(args) if args.impl == "reference" else run_ours(args))

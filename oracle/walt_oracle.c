@@ -398,6 +398,32 @@ void wo_best_for_single(const wo_cand* ranked, uint32_t n, uint32_t max_mismatch
   }
 }
 
+/* per pair: what MergePairedEndResults (paired.cpp:438-570) takes from the ranked lists */
+void wo_pe_result_batch(const wo_chroms* g, const wo_cand* ranked1, const uint32_t* n1, const uint64_t* offs1,
+                        const wo_cand* ranked2, const uint32_t* n2, const uint64_t* offs2, uint32_t n, uint32_t top_k,
+                        uint32_t max_mismatches, int frag_range, wo_pe_result* out) {
+#pragma omp parallel for schedule(dynamic, 256)
+  for (long p = 0; p < (long)n; ++p) {
+    const wo_cand* r1 = ranked1 + (size_t)p * top_k;
+    const wo_cand* r2 = ranked2 + (size_t)p * top_k;
+    const uint32_t len1 = (uint32_t)(offs1[p + 1] - offs1[p]), len2 = (uint32_t)(offs2[p + 1] - offs2[p]);
+    wo_pe_result* o = &out[p];
+    memset(o, 0, sizeof *o);
+    int32_t bi, bj;
+    o->best_times = wo_pe_pair(g, r1, n1[p], len1, r2, n2[p], len2, max_mismatches, frag_range, &bi, &bj);
+    o->best_i = bi; o->best_j = bj;
+    if (o->best_times >= 1) {
+      o->c1 = r1[bi]; o->c2 = r2[bj];
+      memset(o->c1.pad, 0, sizeof o->c1.pad); memset(o->c2.pad, 0, sizeof o->c2.pad);
+      const uint32_t c1 = wo_chrom_id(g->start_index, g->n_chr + 1, r1[bi].genome_pos);
+      const uint32_t c2 = wo_chrom_id(g->start_index, g->n_chr + 1, r2[bj].genome_pos);
+      o->frag_len = wo_fragment_length(g, &r1[bi], len1, &r2[bj], len2, c1, c2);
+    }
+    wo_best_for_single(r1, n1[p], max_mismatches, &o->single1);
+    wo_best_for_single(r2, n2[p], max_mismatches, &o->single2);
+  }
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* index builder, reference.cpp:192-300                                                 */
 /* ------------------------------------------------------------------------------------ */

@@ -122,6 +122,18 @@ uint32_t wo_pe_pair(const wo_chroms* g, const wo_cand* r1, uint32_t n1, uint32_t
 /* GetBestMatch4Single (paired.cpp:296-318) */
 void wo_best_for_single(const wo_cand* ranked, uint32_t n, uint32_t max_mismatches, wo_best* out);
 
+/* Everything MergePairedEndResults derives per pair from the two ranked lists (pairing loop,
+ * the winning candidates, each mate's GetBestMatch4Single), in the fixed 72-byte layout of
+ * walt_pe_result (include/walt_b200.h), for n pairs whose lists are top_k apart.  Threads: OpenMP. */
+typedef struct {
+  uint32_t best_times; int32_t best_i, best_j, frag_len;
+  wo_cand c1, c2;
+  wo_best single1, single2;
+} wo_pe_result;
+void wo_pe_result_batch(const wo_chroms* g, const wo_cand* ranked1, const uint32_t* n1, const uint64_t* offs1,
+                        const wo_cand* ranked2, const uint32_t* n2, const uint64_t* offs2, uint32_t n, uint32_t top_k,
+                        uint32_t max_mismatches, int frag_range, wo_pe_result* out);
+
 /* GetFragmentLength (paired.cpp:320-331) */
 int wo_fragment_length(const wo_chroms* g, const wo_cand* r1, uint32_t len1, const wo_cand* r2,
                        uint32_t len2, uint32_t chr1, uint32_t chr2);

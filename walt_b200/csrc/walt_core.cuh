@@ -506,9 +506,11 @@ WALT_HD uint32_t digit_code(uint32_t d, bool ag) { return ag ? (d == 2u ? 3u : d
 // everything else (tainted slots, slots outside the range, later characters) is read as the
 // reference reads it.  On a bucket of 2^18 entries this turns ~400 dependent pairs of cache
 // misses into about a dozen.
-WALT_HD void literal_index_region(const SubIndexView& ix, uint32_t genome_len, const Pow3& p3, const uint64_t* R,
+// bail: give up (return false, first/second untouched) once the region still holds more than `bail`
+// slots past the table's characters -- a repeat, whose long search is not a single lane's job.
+WALT_HD bool literal_index_region(const SubIndexView& ix, uint32_t genome_len, const Pow3& p3, const uint64_t* R,
                                   uint32_t seed_i, uint32_t seed_len, uint32_t key12, uint32_t& first,
-                                  uint32_t& second) {
+                                  uint32_t& second, uint32_t bail = 0xFFFFFFFFu) {
   const bool ag = ix.ag != 0u;
   uint32_t t0 = 0u, t1 = 0u;
   if ((ix.taint_bits[key12 >> 5] >> (key12 & 31u)) & 1u) taint_slots(ix, key12, t0, t1);
@@ -534,6 +536,7 @@ WALT_HD void literal_index_region(const SubIndexView& ix, uint32_t genome_len, c
       });
       prefix = 3u * prefix + ternary_digit(code, ag);
     } else if (p < ix.depth + FP_DIGITS) {
+      if (u - l > bail && u >= l) return false;
       const uint32_t div = p3.v[FP_DIGITS - 1u - (p - ix.depth)];
       ok = literal_step(l, u, ch, [&](uint32_t slot) {
         if (tainted(slot)) return read_it(slot);
@@ -543,8 +546,9 @@ WALT_HD void literal_index_region(const SubIndexView& ix, uint32_t genome_len, c
       ok = literal_step(l, u, ch, read_it);
     }
   }
-  if (!ok || l > u) { first = 1u; second = 0u; return; }
+  if (!ok || l > u) { first = 1u; second = 0u; return true; }
   first = l; second = u;
+  return true;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1288,16 +1292,16 @@ WALT_HD void replay_lookup(W& w, const SubIndexView& ix, const ChromView& cv, co
 // A lookup that needs the literal IndexRegion replay (tainted bucket) is replayed by its lane.
 // `emit(g, mm)` receives the verified candidates in index order; `discard()` is called if the
 // lookup turns out to be filtered by -b after some were emitted.
-// The literal IndexRegion replay for one lookup by one lane: false if the 12-mer bucket is empty, else
-// the inclusive region ((1, 0) for a failed search).
-WALT_HD_NOINLINE bool lane_literal_region(const SubIndexView& ix, uint32_t genome_len, const Pow3& p3, const uint64_t* R,
-                                          uint32_t seed_i, uint32_t seed_len, uint32_t key12, uint32_t& f, uint32_t& t) {
+// The literal IndexRegion replay for one lookup by one lane: 0 if the 12-mer bucket is empty, 1 with
+// the inclusive region ((1, 0) for a failed search), 2 if the region stays long (a repeat).
+constexpr uint32_t LANE_LITERAL_BAIL = 1024;
+WALT_HD_NOINLINE uint32_t lane_literal_region(const SubIndexView& ix, uint32_t genome_len, const Pow3& p3, const uint64_t* R,
+                                              uint32_t seed_i, uint32_t seed_len, uint32_t key12, uint32_t& f, uint32_t& t) {
   const uint32_t k12_span = p3.v[ix.depth - KEY_WEIGHT];
   const uint32_t bucket_lo = ix.table[key12 * k12_span], bucket_hi = ix.table[(key12 + 1u) * k12_span];
-  if (bucket_lo == bucket_hi) return false;
+  if (bucket_lo == bucket_hi) return 0u;
   f = bucket_lo; t = bucket_hi;
-  literal_index_region(ix, genome_len, p3, R, seed_i, seed_len, key12, f, t);
-  return true;
+  return literal_index_region(ix, genome_len, p3, R, seed_i, seed_len, key12, f, t, LANE_LITERAL_BAIL) ? 1u : 2u;
 }
 
 // LANE_GROUP: the whole lookup is the group's job (a literal region of more than LANE_RUN_CAP slots).  LANE_RUN: more than LANE_RUN_CAP
@@ -1342,8 +1346,9 @@ WALT_HD LaneResult lane_lookup(const SubIndexView& ix, const ChromView& cv, cons
     // ... which this lane does on its own (a chain of dependent loads that the other warps of the SM
     // cover); only a literal region longer than LANE_RUN_CAP goes to the group
     uint32_t f, t;
-    if (!lane_literal_region(ix, cv.genome_len, p3, sc.R, seed_i, seed_len, key12, f, t)) return LANE_DONE;   // empty bucket
-    if (f <= t && t - f + 1u <= cfg.b && t - f + 1u > LANE_RUN_CAP) return LANE_GROUP;
+    const uint32_t how = lane_literal_region(ix, cv.genome_len, p3, sc.R, seed_i, seed_len, key12, f, t);
+    if (how == 0u) return LANE_DONE;   // empty bucket
+    if (how == 2u || (f <= t && t - f + 1u <= cfg.b && t - f + 1u > LANE_RUN_CAP)) return LANE_GROUP;
     ctr.lookups++; ctr.literal++;
     if (t - f + 1u > cfg.b || f > t) return LANE_DONE;      // mapping.cpp:275-277 (u32 arithmetic; (1,0) -> 0); failed search
     literal = true;
