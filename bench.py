@@ -44,15 +44,17 @@ sys.path.insert(0, ROOT)
 
 HG19_MB = [249.25, 243.20, 198.02, 191.15, 180.92, 171.12, 159.14, 146.36, 141.21, 135.53, 135.01, 133.85,
            115.17, 107.35, 102.53, 90.35, 81.20, 78.08, 59.13, 63.03, 48.13, 51.30, 155.27, 59.37]
-METRICS = {"se_small": ("reads mapped/sec (SE 100bp, 10 Mb synthetic genome)", "reads/s"),
+VERIFY = {"n_families": 278, "rep_pct": 64, "div_per_mille": 2, "genome_seed": 21}   # ~4500 copies per family at 1000 Mb
+METRICS = {"verify": ("candidates verified/sec by verify_kernel (SE 150bp, ~4500 candidates per seed lookup, -b 5000)", "candidates/s"),
+           "se_small": ("reads mapped/sec (SE 100bp, 10 Mb synthetic genome)", "reads/s"),
            "se": ("reads mapped/sec (SE 150bp, hg19-size synthetic)", "reads/s"),
            "se_ag": ("reads mapped/sec (SE 150bp -A, hg19-size synthetic)", "reads/s"),
            "pe": ("read pairs mapped/sec (PE 2x150bp -k 50 -L 1000, hg19-size synthetic)", "pairs/s"),
            "pe_stress": ("read pairs mapped/sec (PBAT PE 2x150bp -P -m 8 -b 5000, repeat-heavy synthetic genome, "
                          "30% adaptor read-through)", "pairs/s")}
-MISMATCHES = {"se_small": 6, "se": 6, "se_ag": 6, "pe": 6, "pe_stress": 8}
+MISMATCHES = {"verify": 6, "se_small": 6, "se": 6, "se_ag": 6, "pe": 6, "pe_stress": 8}
 # genome (Mb), reads (pairs) per GPU, read length of BASELINE.json's configs[0..4]
-FULL_SIZE = {"se_small": (10.0, 100_000, 100), "se": (3100.0, 10_000_000, 150), "se_ag": (3100.0, 10_000_000, 150),
+FULL_SIZE = {"verify": (1000.0, 8192, 150), "se_small": (10.0, 100_000, 100), "se": (3100.0, 10_000_000, 150), "se_ag": (3100.0, 10_000_000, 150),
              "pe": (3100.0, 5_000_000, 150), "pe_stress": (3100.0, 5_000_000, 150)}
 CONFIG_NO = {"se_small": 0, "se": 1, "se_ag": 2, "pe": 3, "pe_stress": 4}
 M, B, TOP_K, FRAG = 6, 5000, 50, 1000
@@ -211,7 +213,7 @@ class Workload:
         self.is_pe = self.kind in ("pe", "pe_stress")
         self.pbat = self.kind == "pe_stress"
         self.m = MISMATCHES[self.kind]
-        self.which = {"se_small": (0, 1), "se": (0, 1), "se_ag": (2, 3), "pe": (0, 1, 2, 3), "pe_stress": (0, 1, 2, 3)}[self.kind]
+        self.which = {"verify": (0, 1), "se_small": (0, 1), "se": (0, 1), "se_ag": (2, 3), "pe": (0, 1, 2, 3), "pe_stress": (0, 1, 2, 3)}[self.kind]
         self.n, self.rl = int(reads if reads is not None else args.reads), int(read_len if read_len is not None else args.read_len)
         total = int(self.genome_mb * 1e6)
         self.lengths = chrom_lengths(total, self.kind)
@@ -224,7 +226,11 @@ class Workload:
         self.e.set_chromosomes(self.lengths, self.names)
         dev = f"cuda:{device}"
         d_fwd = torch.empty(eng.packed_genome_bytes(total), dtype=torch.uint8, device=dev)
-        eng.synth_genome_device(device, total, 3, d_fwd.data_ptr(), repeats=self.kind == "pe_stress")
+        if self.kind == "verify":
+            eng.synth_verify_genome_device(device, total, VERIFY["genome_seed"], VERIFY["n_families"], VERIFY["rep_pct"],
+                                           VERIFY["div_per_mille"], d_fwd.data_ptr())
+        else:
+            eng.synth_genome_device(device, total, 3, d_fwd.data_ptr(), repeats=self.kind == "pe_stress")
         self.e.build_from_device_genome(d_fwd.data_ptr(), which=self.which)
         torch.cuda.synchronize()
         self.t_index = time.time() - t0
@@ -239,6 +245,9 @@ class Workload:
             t_rich, a_rich = (self.d_reads2, self.d_reads) if self.pbat else (self.d_reads, self.d_reads2)
             self.e.synth_pairs_device(d_fwd.data_ptr(), self.n, self.rl, 5 + 1000 * rank, t_rich.data_ptr(),
                                       a_rich.data_ptr(), readthrough_pct=30 if self.kind == "pe_stress" else 0)
+        elif self.kind == "verify":
+            self.e.synth_verify_reads_device(d_fwd.data_ptr(), self.n, self.rl, 4 + 1000 * rank, VERIFY["genome_seed"],
+                                             VERIFY["n_families"], VERIFY["rep_pct"], self.d_reads.data_ptr())
         else:
             self.e.synth_reads_device(d_fwd.data_ptr(), self.n, self.rl, 4 + 1000 * rank, self.ag, self.d_reads.data_ptr())
         del d_fwd
@@ -402,7 +411,10 @@ def parity_vs_reference(wl, n, ref_result):
 
 
 def workload_text(kind, genome_mb, reads, read_len):
-    return {"se_small": f"configs[0]: {genome_mb:g} Mb synthetic genome (4 chr), {reads} SE {read_len} bp bisulfite reads per GPU, "
+    return {"verify": f"verification micro-benchmark: {genome_mb:g} Mb synthetic genome, {VERIFY['rep_pct']} % of its 512-base tiles "
+                      f"copies of {VERIFY['n_families']} families of 400 bases ({VERIFY['div_per_mille']} substitutions per 1000 bases), "
+                      f"{reads} SE {read_len} bp bisulfite reads from inside copies per step, -m {M} -b {B}",
+            "se_small": f"configs[0]: {genome_mb:g} Mb synthetic genome (4 chr), {reads} SE {read_len} bp bisulfite reads per GPU, "
                         f"-m {M} -b {B}",
             "se": f"configs[1]: {genome_mb:g} Mb synthetic genome (24 chr, hg19 profile), {reads} SE "
                   f"{read_len} bp bisulfite reads per GPU, -m {M} -b {B}",
@@ -622,6 +634,18 @@ def run_cli(args):
     return 0
 
 
+def run_verify(args):
+    import torch
+    rank, local, world = dist_env()
+    if rank != 0:
+        return 0
+    torch.cuda.set_device(local)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    stream = torch.cuda.current_stream()
+    emit(json.dumps(verify_leg(args, local, stream, torch.cuda.synchronize)))
+    return 0
+
+
 def run_reference(args):
     rank, local, world = dist_env()
     if rank != 0:
@@ -780,6 +804,61 @@ def roofline_dict(wl, alg, kernel_s, dstats, genome_mb):
                     "measured copy bandwidth; dram_frac = measured DRAM bytes (ncu, same kernel sources) / device time / "
                     "the same peak; own_floor = 64 B per lookup + 72 B per candidate + the read and its result"}
     return roof
+
+
+def verify_leg(args, local, stream, barrier, steps=None, warmup=None):
+    """Verification alone (north_star's ">= 50 % of HBM roofline on verification"): reads
+    whose six seed lookups each meet thousands of candidates.  The engine parks them; verify_kernel then
+    checks every candidate of every run, a warp per 32 slots -- that kernel's launches are timed by CUDA
+    events on the stream it runs on (walt_engine_set_kernel_timing) and the slots it verified counted on
+    the device.  bytes_verify = slots * (4 + ceil(rl / 4)) as in SURVEY.md 8(d)."""
+    import refio
+    gmb, nreads, rl = FULL_SIZE["verify"]
+    steps, warmup = steps or args.steps, warmup or args.warmup
+    wl = Workload(args, local, 0, kind="verify", genome_mb=gmb, reads=nreads, read_len=rl)
+    e = wl.e
+    e.set_kernel_timing(True)
+    for _ in range(warmup):
+        wl.device_step(stream.cuda_stream)
+    e.device_stats()
+    step_ms, t_dev, _ = time_device_steps(wl, steps, 0, stream, barrier)
+    st = e.device_stats()
+    peak, peak_kind = measured_peak_gbs()
+    t_verify = st["verify_ns"] / 1e9
+    slots = st["n_verify_slots"]
+    per = 4 + -(-rl // 4)
+    out = {"workload": workload_text("verify", gmb, nreads, rl), "steps": steps, "warmup": warmup,
+           "metric": METRICS["verify"][0], "value": slots / t_verify if t_verify else None, "unit": METRICS["verify"][1],
+           "verify_kernel_ms_per_step": 1e3 * t_verify / steps, "step_ms": float(np.mean(step_ms)),
+           "slots_verified_per_step": slots // steps, "slots_per_read": slots / steps / nreads, "reads_parked_per_step": st["n_parked"] // steps,
+           "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak, "peak_kind": peak_kind,
+                        "achieved": slots * per / t_verify / 1e9 if t_verify else None,
+                        "frac": slots * per / t_verify / 1e9 / peak if t_verify else None,
+                        "algorithmic_bytes_per_candidate": per,
+                        "traffic": None, "dram_frac": None,
+                        "how": "device time of the verify_kernel launches (CUDA events on their stream) over the timed steps; "
+                               "slots counted by the kernel"},
+           "index_build_s": round(wl.t_index, 1)}
+    t = committed_traffic("verify", nreads, gmb)
+    if t and t_verify:
+        out["roofline"]["traffic"] = t["dram_bytes_per_step"]
+        out["roofline"]["dram_frac"] = t["dram_bytes_per_step"] * steps / t_verify / 1e9 / peak
+    if not args.no_cpu and refio.have_reference():   # parity of the whole step (park, verify, fold) on a sample
+        try:
+            hidx = wl.host_index()
+            ns = min(512, nreads)
+            ctr, obest = oracle_counters(wl, hidx, ns)
+            got = wl.d_out[: ns * 16].cpu().numpy().view(refio.BEST_DT)
+            out["parity_check"] = {"sample_reads": ns, "candidates_per_read_oracle": ctr["n_cand"] / ns,
+                                   "fields_differing_vs_oracle": sum(int((got[f] != obest[f]).sum())
+                                                                     for f in ("genome_pos", "times", "mismatch", "strand"))}
+            L = refio.ref_lib()
+            for h in hidx.values():
+                L.waltref_index_free(h)
+        except Exception as ex:
+            out["parity_check"] = {"error": str(ex)[-300:]}
+    wl.close()
+    return out
 
 
 def other_configs(args, local, stream, barrier):
@@ -979,6 +1058,10 @@ def run_ours(args):
             wl.close()
             if not args.no_configs:
                 line["configs"] = other_configs(args, local, stream, barrier)
+                try:
+                    line["verify"] = verify_leg(args, local, stream, barrier)
+                except Exception as ex:
+                    line["verify"] = {"error": str(ex)[-300:]}
             if not args.no_cli:
                 # files in -> files out through the walt program, next to the reference program (not a timed step)
                 try:
@@ -1010,7 +1093,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--genome-mb", type=float, default=0.0, help="default: the configuration's full size (3100; 10 for se_small)")
-    ap.add_argument("--workload", default="se", choices=["se_small", "se", "se_ag", "pe", "pe_stress", "cli"],
+    ap.add_argument("--workload", default="se", choices=["se_small", "se", "se_ag", "pe", "pe_stress", "cli", "verify"],
                     help="se = configs[1] (the bench line), se_small = configs[0], se_ag = configs[2], pe = configs[3], "
                          "pe_stress = configs[4], cli = the walt program on files against the reference program")
     ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (the other four configurations) of the default run")
@@ -1041,6 +1124,8 @@ def main():
         args.read_len = full[2]
     if args.workload == "cli":
         sys.exit(run_cli(args))
+    if args.workload == "verify":
+        sys.exit(run_verify(args))
     sys.exit(run_reference(args) if args.impl == "reference" else run_ours(args))
 
 

@@ -81,7 +81,9 @@ typedef struct {
   uint64_t n_candidates;   /* candidate windows compared against the genome              */
   uint64_t n_literal;      /* lookups that took the literal IndexRegion emulation        */
   uint64_t n_kernel_launches;
-  uint64_t n_parked;       /* reads handed to the warp-per-read kernels (walt_engine_set_defer)  */
+  uint64_t n_parked;       /* reads finished by the kernels behind the first (walt_engine_set_defer) */
+  uint64_t n_verify_slots; /* index slots verified by verify_kernel (runs of parked reads)        */
+  uint64_t verify_ns;      /* device time of its launches (walt_engine_set_kernel_timing)         */
 } walt_stats;
 
 const char* walt_last_error(void);
@@ -188,6 +190,9 @@ int walt_engine_set_group_width(walt_engine* e, uint32_t lanes);
  * equal seeds = repeats, or a bucket next to a chromosome end) is parked by the mapping kernel and
  * finished by a second kernel with a whole warp per read; 0: every read is finished by its group. */
 int walt_engine_set_defer(walt_engine* e, int on);
+/* 1: CUDA events around the verify_kernel launches of the device-resident calls; their sum comes back
+ * in walt_stats.verify_ns from walt_engine_device_stats (how bench.py times verification alone). */
+int walt_engine_set_kernel_timing(walt_engine* e, int on);
 
 /* ---- pinned host memory for batch buffers --------------------------------------------- */
 void* walt_host_alloc(size_t bytes);
@@ -218,19 +223,6 @@ int walt_engine_last_build_info(const walt_engine* e, uint64_t* n_tied_slots, ui
  * Any pointer may be NULL. */
 int walt_engine_export_subindex(walt_engine* e, int which, char* sequence, uint32_t* counter,
                                 uint32_t* index, uint32_t* index_size);
-
-/* ---- synthetic workloads (bench only; SURVEY.md 8(d) shapes) ---------------------------- */
-int walt_synth_genome_device(int device, uint64_t n_bases, uint64_t seed, void* d_packed_out);
-int walt_synth_reads_device(walt_engine* e, const void* d_packed_genome, uint32_t n_reads, uint32_t read_len,
-                            uint64_t seed, int a_rich, void* d_seqs_out /* n_reads*read_len ASCII */);
-/* Directional paired-end library: fragments N(300,50) clipped to [read_len, 1000]; mate 1 is the
- * T-rich 5' end, mate 2 the reverse complement of the 3' end (A-rich).  `readthrough_pct` percent
- * of the pairs have an insert shorter than the read, followed by random bases (what the loader's
- * adaptor clipping + N replacement leaves, mapping.cpp:92-103). */
-int walt_synth_pairs_device(walt_engine* e, const void* d_packed_genome, uint32_t n_pairs, uint32_t read_len,
-                            uint64_t seed, uint32_t readthrough_pct, void* d_seqs1_out, void* d_seqs2_out);
-/* Repeat-heavy genome (configs[4]): ~40 % of the bases are copies of 2000 repeat families. */
-int walt_synth_repeat_genome_device(int device, uint64_t n_bases, uint64_t seed, void* d_packed_out);
 
 #ifdef __cplusplus
 }

@@ -1536,6 +1536,192 @@ WALT_HD void lit_lookup(W& w, const SubIndexView& ix, const ChromView& cv, const
 }
 
 // ------------------------------------------------------------------------------------------
+// parked reads: what the lane phase found, flat verification of their runs, ordered fold
+// ------------------------------------------------------------------------------------------
+// A read that a sub-warp group cannot finish (its fold reaches a long run) is PARKED: its lanes
+// write down what they found -- per lookup either the verified candidates or the run (first slot,
+// length) -- and reserve one 32-candidate block after the other of a launch-wide scratch for the
+// runs.  A second kernel then verifies ALL blocks of ALL parked reads, a warp per block, with no
+// order and no state (verify_block: eight windows per load instruction, thousands of blocks in
+// flight), leaving one byte per slot: the mismatch count, or MM_NONE.  A third kernel folds each
+// parked read in reference order from its record and those bytes (fold_parked_*), touching the
+// index only for the few candidates a sink still takes.
+constexpr uint32_t PARK_WORDS = 64;          // words per parked read: [0] read, [1] blocks, [2 + 10 j ..) lookup j
+constexpr uint32_t PARK_LOOKUP_WORDS = 10;   // [0] kind | n << 8, then the data of the kind
+constexpr uint32_t PK_NONE = 0u, PK_CANDS = 1u, PK_RUN = 2u, PK_GROUP = 3u;
+constexpr uint32_t MM_NONE = 0xFFu;
+
+// no parking: every read is finished where it is (CPU harness, MAP_ALL kernels)
+struct NoPark {
+  static constexpr bool ENABLED = false;
+  template <class W> WALT_HD uint32_t* claim(W&, uint32_t, bool, uint32_t&, uint32_t&) { return nullptr; }
+  WALT_HD uint32_t* block_desc(uint32_t) { return nullptr; }
+};
+
+// Length of the fingerprint run that starts at run.f0, by one lane: doubling steps, then bisection.
+// Returns b + 1 as soon as the run is known to be longer than b.
+WALT_HD uint32_t run_length(const SubIndexView& ix, const LaneRun& run, uint32_t fp_span, uint32_t b) {
+  const uint64_t limit64 = (uint64_t)run.f0 + b + 1u;
+  const uint32_t limit = limit64 < run.hi ? (uint32_t)limit64 : run.hi;   // slots [f0, limit) matter
+  auto in_run = [&](uint32_t slot) { return ix.entries[slot].fp - run.fp_lo <= fp_span; };
+  uint32_t good = run.f0 + LANE_RUN_CAP;      // slots up to here are known to match (lane_lookup)
+  uint32_t step = LANE_RUN_CAP;
+  uint32_t bad = limit;                       // first slot known not to match (or the limit)
+  while (good + step < limit) {
+    if (in_run(good + step)) { good += step; step *= 2u; } else { bad = good + step; break; }
+  }
+  // invariant: good matches, bad does not (or is the limit): first non-matching slot in (good, bad]
+  uint32_t lo = good + 1u, hi = bad;
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (in_run(mid)) lo = mid + 1u; else hi = mid;
+  }
+  return lo - run.f0;
+}
+
+// The narrowed region inside a fingerprint run longer than -b, by one lane: the run is sorted by the
+// seed characters, so the slots whose seed characters all equal the read's are a stretch [first,
+// first + n) of it, found by two bisections (compare_seed).  The run's end comes from bisection too.
+WALT_HD_NOINLINE uint32_t exact_region(const SubIndexView& ix, const LaneRun& run, uint32_t fp_span, const ReadScratch& sc,
+                                       uint32_t read_len, uint32_t seed_i, uint32_t& first) {
+  const uint32_t nws = (3u * seed_repeats(read_len) + seed_i + 31u) >> 5;
+  const uint64_t* SM = sc.SM + seed_i * sc.nw;
+  uint32_t lo = run.f0, hi = run.hi;     // end of the run: first slot of [f0, hi) whose fingerprint is beyond
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (ix.entries[mid].fp - run.fp_lo <= fp_span) lo = mid + 1u; else hi = mid;
+  }
+  const uint32_t end = lo;
+  auto cmp = [&](uint32_t slot) { return compare_seed(ix.genome, (uint64_t)ix.entries[slot].pos + PAD_BASES - seed_i, sc.R, SM, nws); };
+  lo = run.f0; hi = end;                 // first slot that is not smaller than the read
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (cmp(mid) < 0) lo = mid + 1u; else hi = mid;
+  }
+  first = lo;
+  hi = end;                              // first slot that is larger
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (cmp(mid) <= 0) lo = mid + 1u; else hi = mid;
+  }
+  return lo - first;
+}
+
+// One block of 32 slots of a parked run: slot `first + lane` of [first, last_excl), read and masks in
+// `sc`.  out[lane] = mismatches over the verification mask if the slot is seed-equal, else MM_NONE.
+template <class W>
+WALT_HD void verify_block(W& w, const SubIndexView& ix, const ReadScratch& sc, uint32_t read_len, uint32_t seed_i,
+                          uint32_t first, uint32_t last_excl, uint8_t* out, Counters& ctr) {
+  const uint32_t lane = w.lane(), q = lane & 3u;
+  const uint32_t nw = (read_len + 31u) >> 5;
+  const Quad32 Rq = read_block(sc.R, q, nw);
+  const Quad32 VMq = read_block(sc.VM + seed_i * sc.nw, q, nw);
+  const Quad32 SMq = read_block(sc.SM + seed_i * sc.nw, q, nw);
+  WideBlock blk;
+  blk.en = wide_load_entry(w, ix, first, last_excl);
+  wide_load_genome(w, ix, seed_i, blk);
+  const uint32_t r = wide_compare(w, blk, Rq, VMq, SMq);
+  const bool cand = first + lane < last_excl && (r >> 16) == 0u;
+  if (cand) ctr.candidates++;
+  out[lane] = (uint8_t)(cand ? (r & 0xFFFFu) : MM_NONE);
+}
+
+// A parked run in the ordered fold: its bytes, 32 at a time; the entry is read only for the slots a
+// sink still takes.
+template <class W, class Sink>
+WALT_HD void fold_run(W& w, const SubIndexView& ix, const ChromView& cv, uint32_t read_len, uint32_t seed_i,
+                      uint32_t strand, uint32_t f0, uint32_t count, const uint8_t* bytes, Sink& sink) {
+  const uint32_t lane = w.lane();
+  for (uint32_t base = 0; base < count; base += 32u) {
+    const uint32_t mm = base + lane < count ? bytes[base + lane] : MM_NONE;
+    bool valid = mm != MM_NONE && sink.may_take(mm);
+    uint32_t g = 0u;
+    if (valid) {   // bounds, mapping.cpp:281-286
+      const uint32_t e = ix.entries[f0 + base + lane].pos;
+      const uint32_t chr = chrom_of(cv.starts, cv.n_chr, e);
+      g = e - seed_i;
+      valid = (e - cv.starts[chr] >= seed_i) && !(g + read_len >= cv.starts[chr + 1u]);
+    }
+    sink.consume(w, valid, mm, g, strand);
+  }
+}
+
+// The lanes of a group write the record of their read (see above).  `res`, `run`: what the lane's
+// lookup came to; write_cands(rec) stores a lane's verified candidates and returns their number.
+// Reads that the flat path cannot take (longer than WIDE_MAX_READ, no room left) go on the list of
+// the warp-per-read kernel instead (park.claim sees to that).
+template <class W, class Park, class WriteCands>
+WALT_HD void park_read(W& w, const SubIndexView* ix2, const Pow3& p3, const MapConfig& cfg, const ReadScratch& sc,
+                       uint32_t read_len, LaneResult res, const LaneRun& run, Park& park, WriteCands write_cands) {
+  const uint32_t lane = w.lane();
+  const bool legacy = read_len > WIDE_MAX_READ;
+  uint32_t kind = PK_NONE, count = 0u, first = run.f0;
+  bool skip = false;
+  if (lane < LOOKUP_LANES && !legacy) {
+    if (res == LANE_RUN) {
+      count = run_length(ix2[lane / 3u], run, lookup_fp_span(ix2[lane / 3u], read_len, p3), cfg.b);
+      kind = PK_RUN;
+      if (count > cfg.b) {
+        // the run may exceed -b, so the size of the narrowed region (the seed-equal slots, a contiguous
+        // stretch of the run) matters: this lane finds it by bisection on the seed characters
+        first = run.f0;
+        count = exact_region(ix2[lane / 3u], run, lookup_fp_span(ix2[lane / 3u], read_len, p3), sc, read_len, lane % 3u, first);
+        if (count > cfg.b || count == 0u) { kind = PK_NONE; count = 0u; skip = true; }   // mapping.cpp:275-277: the lookup is dropped
+      }
+    } else if (res == LANE_GROUP) {
+      kind = PK_GROUP;
+    }
+  }
+  // a lookup that needs the cooperative replay (a literal region, a run that may exceed -b) sends the
+  // whole read to the warp-per-read kernel: the fold kernels stay free of that code
+  const bool whole = legacy || w.ballot(kind == PK_GROUP) != 0u;
+  const uint32_t blocks = (count + 31u) >> 5;
+  uint32_t before = 0u, total = 0u;
+  for (uint32_t k = 0; k < LOOKUP_LANES; ++k) {
+    const uint32_t bk = w.shfl(blocks, (int)k);
+    if (k < lane) before += bk;
+    total += bk;
+  }
+  uint32_t blk0 = 0u, t = 0u;
+  uint32_t* rec = park.claim(w, total, whole, blk0, t);    // group-uniform; NULL: the read went on the other list
+  if (rec) {
+    if (lane == 0u) rec[1] = total;                        // rec[0] (the read's number) is claim()'s
+    if (lane < LOOKUP_LANES) {
+      uint32_t* mine = rec + 2u + PARK_LOOKUP_WORDS * lane;
+      if (kind == PK_RUN) {
+        mine[1] = first; mine[2] = count; mine[3] = blk0 + before;
+        for (uint32_t k = 0; k < blocks; ++k) {
+          uint32_t* d = park.block_desc(blk0 + before + k);
+          d[0] = t; d[1] = lane | (k << 3);
+        }
+      } else if (kind == PK_NONE && !skip) {
+        const uint32_t n = write_cands(mine);
+        if (n) kind = PK_CANDS | (n << 8);
+      }
+      mine[0] = kind;
+    }
+  }
+  w.sync();
+}
+
+// ... and the fold of a parked read from its record (cands(rec, strand): the verified candidates of a
+// lookup go to the sink as in map_read_*).
+template <class W, class Sink, class Cands>
+WALT_HD void fold_parked(W& w, const SubIndexView* ix2, const ChromView& cv, uint32_t read_len, const uint32_t* rec,
+                         const uint8_t* bytes, Sink& sink, Cands cands) {
+  for (uint32_t j = 0; j < LOOKUP_LANES; ++j) {
+    const uint32_t* mine = rec + 2u + PARK_LOOKUP_WORDS * j;
+    const uint32_t kind = mine[0] & 0xFFu;
+    if (kind == PK_NONE) continue;
+    const uint32_t s = j >= 3u ? 1u : 0u, seed_i = j - 3u * s;
+    const uint32_t strand = s ? '-' : '+';
+    if (sink.stop_before_shift(seed_i)) continue;
+    if (kind == PK_CANDS) cands(mine, strand);
+    else if (kind == PK_RUN) fold_run(w, ix2[s], cv, read_len, seed_i, strand, mine[1], mine[2], bytes + 32u * (size_t)mine[3], sink);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // whole reads
 // ------------------------------------------------------------------------------------------
 // What became of a read: mapped; holds a non-ACGT byte; or PARKed -- its ordered fold reached a
@@ -1545,11 +1731,12 @@ enum MapStatus : uint32_t { MAP_OK = 0u, MAP_BAD = 1u, MAP_PARKED = 2u, MAP_PARK
 
 // SingleEndMapping for both strand passes of one read (mapping.cpp:486-500 order: all shifts
 // on the '+' sub-index, then all shifts on the '-' sub-index, state carried across).
-template <class W, bool PACKED = false, bool PARK = false>
+template <class W, bool PACKED = false, class Park = NoPark>
 WALT_HD MapStatus map_read_se(W& w, const SubIndexView* ix2, const ChromView& cv, const Pow3& p3,
                          const MapConfig& cfg, const char* seq, uint32_t read_len, bool ag,
                          uint32_t max_mismatches, ReadScratch& sc, uint32_t& cached_len,
-                         BestState& out, Counters& ctr, const uint32_t* lit = nullptr) {
+                         BestState& out, Counters& ctr, const uint32_t* lit = nullptr, Park park = Park()) {
+  constexpr bool PARK = Park::ENABLED;
   static_assert(W::WIDTH >= LOOKUP_LANES, "a group needs one lane per lookup");
   BestSink<W> sink;
   sink.st.pos = 0u; sink.st.times = 0u; sink.st.mm = max_mismatches; sink.st.strand = '+';
@@ -1598,7 +1785,15 @@ WALT_HD MapStatus map_read_se(W& w, const SubIndexView* ix2, const ChromView& cv
     if ((lit_mask >> j) & 1u) {
       lit_lookup(w, ix2[s], cv, cfg, sc, read_len, seed_i, strand, w.shfl(lit_f, (int)j), w.shfl(lit_l, (int)j), sink, ctr);
     } else if (((group_mask | run_mask) >> j) & 1u) {
-      if (PARK) { ctr = ctr_in; w.sync(); return group_mask ? MAP_PARKED_LIT : MAP_PARKED; }   // the kernel that takes the read over counts its work
+      if (PARK) {   // the kernels that take the read over count its work
+        ctr = ctr_in;
+        park_read(w, ix2, p3, cfg, sc, read_len, res, run, park, [&](uint32_t* rec) {
+          if (mn == NO_HIT) return 0u;
+          rec[1] = mn; rec[2] = cnt; rec[3] = g_first; rec[4] = g_last;
+          return 1u;
+        });
+        return MAP_PARKED;
+      }
       if ((run_mask >> j) & 1u) run_lookup(w, ix2[s], cv, p3, cfg, sc, read_len, seed_i, strand, run, j, sink, ctr);
       else replay_lookup(w, ix2[s], cv, p3, cfg, sc, read_len, seed_i, strand, sink, ctr);
     } else {
@@ -1612,11 +1807,12 @@ WALT_HD MapStatus map_read_se(W& w, const SubIndexView* ix2, const ChromView& cv
 
 // PairEndMapping for both strand passes of one mate (paired.cpp:650-671) into `sink` (reset by the
 // caller; its state persists across the two passes).
-template <class W, bool PACKED, bool PARK, class SinkT>
+template <class W, bool PACKED, class Park, class SinkT>
 WALT_HD MapStatus map_read_pe_into(W& w, const SubIndexView* ix2, const ChromView& cv, const Pow3& p3,
                               const MapConfig& cfg, const char* seq, uint32_t read_len, bool ag,
                               uint32_t max_mismatches, ReadScratch& sc, uint32_t& cached_len, SinkT& sink,
-                              Counters& ctr, const uint32_t* lit = nullptr) {
+                              Counters& ctr, const uint32_t* lit = nullptr, Park park = Park()) {
+  constexpr bool PARK = Park::ENABLED;
   static_assert(W::WIDTH >= LOOKUP_LANES, "a group needs one lane per lookup");
   const Counters ctr_in = ctr;
   if (read_len < MIN_READ_LEN) return MAP_OK;
@@ -1663,7 +1859,15 @@ WALT_HD MapStatus map_read_pe_into(W& w, const SubIndexView* ix2, const ChromVie
     if ((lit_mask >> j) & 1u) {
       lit_lookup(w, ix2[s], cv, cfg, sc, read_len, seed_i, strand, w.shfl(lit_f, (int)j), w.shfl(lit_l, (int)j), sink, ctr);
     } else if (((group_mask | run_mask) >> j) & 1u) {
-      if (PARK) { ctr = ctr_in; w.sync(); return group_mask ? MAP_PARKED_LIT : MAP_PARKED; }
+      if (PARK) {
+        ctr = ctr_in;
+        park_read(w, ix2, p3, cfg, sc, read_len, res, run, park, [&](uint32_t* rec) {
+          const LaneCand* c = sc.C + lane * LANE_RUN_CAP;
+          for (uint32_t k = 0; k < n_mine; ++k) { rec[1u + 2u * k] = c[k].g; rec[2u + 2u * k] = c[k].mm; }
+          return n_mine;
+        });
+        return MAP_PARKED;
+      }
       if ((run_mask >> j) & 1u) run_lookup(w, ix2[s], cv, p3, cfg, sc, read_len, seed_i, strand, run, j, sink, ctr);
       else replay_lookup(w, ix2[s], cv, p3, cfg, sc, read_len, seed_i, strand, sink, ctr);
     } else {
@@ -1684,23 +1888,23 @@ WALT_HD MapStatus map_read_pe(W& w, const SubIndexView* ix2, const ChromView& cv
   HeapSink<W> sink;
   sink.heap = heap; sink.size = 0u; sink.cap = top_k; sink.top_mm = 0u; sink.max_mm = max_mismatches;
   heap_size = 0u;
-  const MapStatus st = map_read_pe_into<W, PACKED, false>(w, ix2, cv, p3, cfg, seq, read_len, ag, max_mismatches, sc, cached_len, sink, ctr);
+  const MapStatus st = map_read_pe_into<W, PACKED, NoPark>(w, ix2, cv, p3, cfg, seq, read_len, ag, max_mismatches, sc, cached_len, sink, ctr);
   heap_size = sink.size;
   return st;
 }
 
 // ... logging the heap-changing candidates for replay_heap_log (max_mismatches <= LOG_MAX_MM; `log`
 // holds pe_log_slots(top_k, max_mismatches) entries, `hist` max_mismatches + 1 counters).
-template <class W, bool PACKED = false, bool PARK = false>
+template <class W, bool PACKED = false, class Park = NoPark>
 WALT_HD MapStatus map_read_pe_logged(W& w, const SubIndexView* ix2, const ChromView& cv, const Pow3& p3,
                                 const MapConfig& cfg, const char* seq, uint32_t read_len, bool ag,
                                 uint32_t max_mismatches, uint32_t top_k, ReadScratch& sc,
                                 uint32_t& cached_len, HeapEntry* log, uint32_t* hist, uint32_t& n_log, Counters& ctr,
-                                const uint32_t* lit = nullptr) {
+                                const uint32_t* lit = nullptr, Park park = Park()) {
   LogSink<W> sink;
   sink.log = log; sink.hist = hist; sink.cap = top_k; sink.max_mm = max_mismatches;
   sink.reset(w);
-  const MapStatus st = map_read_pe_into<W, PACKED, PARK>(w, ix2, cv, p3, cfg, seq, read_len, ag, max_mismatches, sc, cached_len, sink, ctr, lit);
+  const MapStatus st = map_read_pe_into<W, PACKED, Park>(w, ix2, cv, p3, cfg, seq, read_len, ag, max_mismatches, sc, cached_len, sink, ctr, lit, park);
   n_log = sink.n_log;
   return st;
 }

@@ -274,6 +274,15 @@ constexpr uint32_t WARPS_PER_BLOCK = 8;
 constexpr uint32_t BLOCK_THREADS = WARPS_PER_BLOCK * 32;
 constexpr uint32_t MIN_BLOCKS_PER_SM = 4;   // caps the kernels at 64 registers (the out-of-line replay may spill)
 
+// device buffers of a launch that parks reads (see "parked reads" in walt_core.cuh)
+struct ParkView {
+  uint32_t* recs;       // PARK_WORDS words per parked read with a record (first rec_cap of them)
+  uint32_t* desc;       // two words per verification block: record number, lookup | block << 3
+  uint8_t* bytes;       // 32 per verification block: what verify_kernel leaves for the fold
+  uint32_t* list;       // read numbers of the parked reads WITHOUT a record (MAP_TAKE maps them)
+  uint32_t rec_cap, cap_blocks;
+};
+
 struct SeArgs {
   SubIndexView ix[2];   // '+' then '-' sub-index
   ChromView cv;
@@ -290,22 +299,21 @@ struct SeArgs {
   uint32_t max_mismatches;
   walt_best* out;
   uint32_t* flags;        // [0] non-ACGT
-  uint32_t* queue;        // [0] work-queue head, [1] parked reads without / [3] with a literal lookup, [2] / [4] queue heads of the kernels that take them over (zeroed before launch)
-  uint32_t* parked;       // read numbers of the parked reads (MODE 1 writes, MODE 2 reads)
-  uint32_t* lit;          // literal regions of the first lit_cap parked reads (lit_kernel writes, MODE 2 reads)
-  uint32_t lit_cap;
+  uint32_t* queue;        // QUEUE_WORDS words, zeroed before launch: [0] work-queue head, [1] parked reads with a record,
+                          // [2] queue head of MAP_TAKE, [3] reads on its list, [5] verification blocks reserved,
+                          // [6] / [7] queue heads of verify_kernel / the fold kernels
+  ParkView park;          // where parked reads go (MAP_PARK writes, the kernels behind it read)
   unsigned long long* counters;  // optional
 };
 
 // Kernel modes.  MAP_ALL: every read is finished where it is.  MAP_PARK: a read whose ordered fold
-// reaches a lookup that needs the whole group (a long fingerprint run = repeats, or a tainted
-// bucket) is dropped and its number appended to the parked list, so that the sub-warp groups never
-// leave the converged fast path.  MAP_TAKE (a whole warp per read): maps the parked reads, repeats
-// streamed through the warp-wide quad verification (verify_run_wide, walt_core.cuh).
-// Parked reads come in two kinds, kept at the two ends of the parked list: reads with a long run and no
-// literal lookup (front; MAP_TAKE maps them at once) and reads with a literal lookup (back; lit_kernel
-// first replays their IndexRegion searches, on a side stream and beside MAP_TAKE, then MAP_TAKE_LIT maps them).
-enum : int { MAP_ALL = 0, MAP_PARK = 1, MAP_TAKE = 2, MAP_TAKE_LIT = 3 };
+// reaches a lookup that needs more than one lane (a long fingerprint run = repeats) is parked, so that the
+// sub-warp groups never leave the converged fast path: its lanes write a record of what they found and
+// reserve verification blocks for its runs (DevPark, park_read).  verify_kernel then verifies every block,
+// a warp per block and no order; se_fold_kernel / pe_fold_kernel fold every parked read from its record.
+// MAP_TAKE (a whole warp per read, from scratch) maps the parked reads that got no record (no room, reads
+// longer than WIDE_MAX_READ) -- and all of them when the flat path is switched off.
+enum : int { MAP_ALL = 0, MAP_PARK = 1, MAP_TAKE = 2 };
 constexpr uint32_t TAKE_BLOCKS_PER_SM = 2;   // the take-over kernels get 128 registers
 
 // The groups of a warp take consecutive reads with one queue ticket and walk the read loop
@@ -374,58 +382,38 @@ __device__ __forceinline__ void flush_counters(const HwGroup<WD>& w, const Count
   }
 }
 
-// append the reads of this warp's groups that were parked in this round (one atomic per warp and kind):
-// reads without a literal lookup from the front of the list, the others from its back
-template <uint32_t WD>
-__device__ __forceinline__ void park_reads(const HwGroup<WD>& w, MapStatus ms, uint32_t r, uint32_t* queue, uint32_t* list, uint32_t n) {
-  const uint32_t l = threadIdx.x & 31u;
-  const bool mine = w.lane() == 0u;
-  const uint32_t pm = __ballot_sync(0xFFFFFFFFu, mine && ms == MAP_PARKED);
-  const uint32_t pl = __ballot_sync(0xFFFFFFFFu, mine && ms == MAP_PARKED_LIT);
-  if (pm) {
-    const int leader = __ffs((int)pm) - 1;
-    uint32_t at = 0;
-    if ((int)l == leader) at = atomicAdd(queue + 1, (uint32_t)__popc(pm));
-    at = __shfl_sync(0xFFFFFFFFu, at, leader);
-    if (mine && ms == MAP_PARKED) list[at + (uint32_t)__popc(pm & ((1u << l) - 1u))] = r;
-  }
-  if (pl) {
-    const int leader = __ffs((int)pl) - 1;
-    uint32_t at = 0;
-    if ((int)l == leader) at = atomicAdd(queue + 3, (uint32_t)__popc(pl));
-    at = __shfl_sync(0xFFFFFFFFu, at, leader);
-    if (mine && ms == MAP_PARKED_LIT) list[n - 1u - (at + (uint32_t)__popc(pl & ((1u << l) - 1u)))] = r;
-  }
-}
-
-// Read number of parked item t.  MAP_TAKE: front of the list; MAP_TAKE_LIT / lit_kernel: its back.
-template <class Args>
-__device__ __forceinline__ uint32_t parked_at(const Args& a, uint32_t t, bool back) { return a.parked[back ? a.n - 1u - t : t]; }
-
-// Between the two: one THREAD per parked read replays the literal IndexRegion searches of its lookups
-// (literal_regions, walt_core.cuh), so that the long chains of dependent loads of tens of thousands of
-// reads are in flight together instead of one per warp.
-template <bool PACKED, class Args>
-__global__ void __launch_bounds__(128)
-lit_kernel(const __grid_constant__ Args a) {
-  uint32_t n = *reinterpret_cast<volatile const uint32_t*>(a.queue + 3);
-  if (n > a.lit_cap) n = a.lit_cap;
-  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-    uint32_t len;
-    const char* seq = read_at<PACKED>(a, parked_at(a, t, true), len);
-    uint64_t R[MAX_WORDS];
-    uint32_t out[LIT_WORDS];
-    if (len <= MAX_READ_LEN && pack_read_serial<PACKED>(seq, len, a.ag != 0u, R)) {
-      literal_regions(a.ix, a.cv.genome_len, a.p3, a.cfg, R, len, out);
-    } else {   // the take-over kernel reports the bad read
-      for (uint32_t i = 0; i < LIT_WORDS; ++i) out[i] = (i & 1u) ? 0u : LIT_NONE;
+// Parking policy of the MAP_PARK kernels (walt_core.cuh: park_read).  claim(): a record and `total`
+// verification blocks for read r, or -- no room, or a read the flat path cannot take -- a place on
+// the MAP_TAKE list.
+struct DevPark {
+  static constexpr bool ENABLED = true;
+  ParkView v;
+  uint32_t* queue;
+  uint32_t r;
+  template <class W>
+  __device__ __forceinline__ uint32_t* claim(W& w, uint32_t total, bool legacy, uint32_t& blk0, uint32_t& t) {
+    uint32_t at = 0xFFFFFFFFu, b0 = 0u;
+    if (w.lane() == 0u) {
+      if (!legacy && v.rec_cap) {
+        at = atomicAdd(queue + 1, 1u);
+        if (at < v.rec_cap) {
+          b0 = atomicAdd(queue + 5, total);
+          if ((uint64_t)b0 + total > v.cap_blocks) {   // no room for its blocks: a dead record, dead descriptors
+            v.recs[(size_t)at * PARK_WORDS] = 0xFFFFFFFFu; at = 0xFFFFFFFFu;
+            for (uint32_t blk = b0; blk < v.cap_blocks && blk - b0 < total; ++blk) v.desc[2u * (size_t)blk] = 0xFFFFFFFFu;
+          }
+        } else {
+          at = 0xFFFFFFFFu;
+        }
+      }
+      if (at == 0xFFFFFFFFu) v.list[atomicAdd(queue + 3, 1u)] = r;
+      else v.recs[(size_t)at * PARK_WORDS] = r;
     }
-    uint4* dst = reinterpret_cast<uint4*>(a.lit + (size_t)t * LIT_WORDS);
-    dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
-    dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
-    dst[2] = make_uint4(out[8], out[9], out[10], out[11]);
+    at = w.shfl(at, 0); blk0 = w.shfl(b0, 0); t = at;
+    return at == 0xFFFFFFFFu ? nullptr : v.recs + (size_t)at * PARK_WORDS;
   }
-}
+  __device__ __forceinline__ uint32_t* block_desc(uint32_t blk) const { return v.desc + 2u * (size_t)blk; }
+};
 
 template <uint32_t WD, bool PACKED, int MODE>
 __global__ void __launch_bounds__(BLOCK_THREADS, MODE >= MAP_TAKE ? TAKE_BLOCKS_PER_SM : MIN_BLOCKS_PER_SM)
@@ -442,28 +430,29 @@ se_map_kernel(const __grid_constant__ SeArgs a) {
   Counters ctr{0u, 0u, 0u};
   bool bad = false;
   uint32_t n = a.n;
-  if (MODE >= MAP_TAKE) {
-    n = *reinterpret_cast<volatile const uint32_t*>(a.queue + (MODE == MAP_TAKE_LIT ? 3 : 1));   // what the first kernel parked
+  if (MODE == MAP_TAKE) {
+    n = *reinterpret_cast<volatile const uint32_t*>(a.queue + 3);   // the parked reads without a record
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.counters && n) atomicAdd(a.counters + 3, (unsigned long long)n);
   }
-  uint32_t* const queue = MODE == MAP_TAKE_LIT ? a.queue + 4 : MODE == MAP_TAKE ? a.queue + 2 : a.queue;
+  uint32_t* const queue = MODE == MAP_TAKE ? a.queue + 2 : a.queue;
   for (uint32_t round = TICKET_ROUNDS, base = 0;; ++round) {
     if (round == TICKET_ROUNDS) { base = next_ticket<WD>(queue); round = 0; }
     const uint32_t first = base + round * (32u / WD);
     if (first >= n) break;                              // warp-uniform: past the batch
     uint32_t r = first + (threadIdx.x & 31u) / WD;
-    MapStatus status = MAP_OK;
     if (r < n) {
-      const uint32_t* lit = nullptr;
-      if (MODE == MAP_TAKE_LIT && r < a.lit_cap) lit = a.lit + (size_t)r * LIT_WORDS;
-      if (MODE >= MAP_TAKE) r = parked_at(a, r, MODE == MAP_TAKE_LIT);
+      if (MODE == MAP_TAKE) r = a.park.list[r];
       uint32_t len;
       const char* seq = read_at<PACKED>(a, r, len);
       BestState st;
-      const MapStatus ms = map_read_se<HwGroup<WD>, PACKED, MODE == MAP_PARK>(w, a.ix, a.cv, a.p3, a.cfg, seq, len, a.ag != 0u,
-                                                                            a.max_mismatches, sc, cached_len, st, ctr, lit);
+      MapStatus ms;
+      if (MODE == MAP_PARK)
+        ms = map_read_se<HwGroup<WD>, PACKED, DevPark>(w, a.ix, a.cv, a.p3, a.cfg, seq, len, a.ag != 0u, a.max_mismatches, sc,
+                                                        cached_len, st, ctr, nullptr, DevPark{a.park, a.queue, r});
+      else
+        ms = map_read_se<HwGroup<WD>, PACKED>(w, a.ix, a.cv, a.p3, a.cfg, seq, len, a.ag != 0u, a.max_mismatches, sc,
+                                               cached_len, st, ctr);
       bad |= ms == MAP_BAD;
-      status = ms;
       if (lane == 0 && ms < MAP_PARKED) {
         uint4 o;
         o.x = st.pos; o.y = st.times; o.z = st.mm; o.w = st.strand & 0xFFu;
@@ -471,7 +460,6 @@ se_map_kernel(const __grid_constant__ SeArgs a) {
       }
     }
     __syncwarp();
-    if (MODE == MAP_PARK) park_reads(w, status, r, a.queue, a.parked, a.n);
   }
   flush_counters(w, ctr, bad, tally, a.flags, a.counters);
 }
@@ -499,9 +487,7 @@ struct PeArgs {
   uint32_t zero_fill;     // the ranked lists travel to the host: define (zero) their unused slots
   uint32_t* flags;
   uint32_t* queue;        // see SeArgs
-  uint32_t* parked;
-  uint32_t* lit;
-  uint32_t lit_cap;
+  ParkView park;
   unsigned long long* counters;
 };
 
@@ -525,35 +511,276 @@ pe_log_kernel(const __grid_constant__ PeArgs a) {
   Counters ctr{0u, 0u, 0u};
   bool bad = false;
   uint32_t n = a.n;
-  if (MODE >= MAP_TAKE) {
-    n = *reinterpret_cast<volatile const uint32_t*>(a.queue + (MODE == MAP_TAKE_LIT ? 3 : 1));   // what the first kernel parked
+  if (MODE == MAP_TAKE) {
+    n = *reinterpret_cast<volatile const uint32_t*>(a.queue + 3);   // the parked reads without a record
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.counters && n) atomicAdd(a.counters + 3, (unsigned long long)n);
   }
-  uint32_t* const queue = MODE == MAP_TAKE_LIT ? a.queue + 4 : MODE == MAP_TAKE ? a.queue + 2 : a.queue;
+  uint32_t* const queue = MODE == MAP_TAKE ? a.queue + 2 : a.queue;
   for (uint32_t round = TICKET_ROUNDS, base = 0;; ++round) {
     if (round == TICKET_ROUNDS) { base = next_ticket<WD>(queue); round = 0; }
     const uint32_t first = base + round * (32u / WD);
     if (first >= n) break;
     uint32_t r = first + (threadIdx.x & 31u) / WD;
-    MapStatus status = MAP_OK;
     if (r < n) {
-      const uint32_t* lit = nullptr;
-      if (MODE == MAP_TAKE_LIT && r < a.lit_cap) lit = a.lit + (size_t)r * LIT_WORDS;
-      if (MODE >= MAP_TAKE) r = parked_at(a, r, MODE == MAP_TAKE_LIT);
+      if (MODE == MAP_TAKE) r = a.park.list[r];
       uint32_t len;
       const char* seq = read_at<PACKED>(a, r, len);
       uint32_t n_log = 0;
-      const MapStatus ms = map_read_pe_logged<HwGroup<WD>, PACKED, MODE == MAP_PARK>(
-          w, a.ix, a.cv, a.p3, a.cfg, seq, len, a.ag != 0u, a.max_mismatches, a.top_k, sc, cached_len,
-          a.log + (size_t)r * a.log_slots, hist, n_log, ctr, lit);
+      MapStatus ms;
+      if (MODE == MAP_PARK)
+        ms = map_read_pe_logged<HwGroup<WD>, PACKED, DevPark>(w, a.ix, a.cv, a.p3, a.cfg, seq, len, a.ag != 0u, a.max_mismatches,
+                                                               a.top_k, sc, cached_len, a.log + (size_t)r * a.log_slots, hist, n_log,
+                                                               ctr, nullptr, DevPark{a.park, a.queue, r});
+      else
+        ms = map_read_pe_logged<HwGroup<WD>, PACKED>(w, a.ix, a.cv, a.p3, a.cfg, seq, len, a.ag != 0u, a.max_mismatches, a.top_k,
+                                                      sc, cached_len, a.log + (size_t)r * a.log_slots, hist, n_log, ctr);
       bad |= ms == MAP_BAD;
-      status = ms;
       if (lane == 0 && ms < MAP_PARKED) a.n_log[r] = n_log;
     }
     __syncwarp();
-    if (MODE == MAP_PARK) park_reads(w, status, r, a.queue, a.parked, a.n);
   }
   flush_counters(w, ctr, bad, tally, a.flags, a.counters);
+}
+
+// ------------------------------------------------------------------------------------------
+// parked reads: flat verification and fold
+// ------------------------------------------------------------------------------------------
+// A warp per verification block, blocks handed out by tickets: no order, no state, one gather per
+// candidate -- the part of the path that runs at memory speed.  `bench.py --workload verify` times it.
+constexpr uint32_t VERIFY_TICKET = 16;   // consecutive blocks per ticket (usually of one run: the read is set up once)
+constexpr uint32_t VERIFY_WORDS = 12;    // 32-bit words (16 bases each) of a read of up to WIDE_MAX_READ bases
+constexpr uint32_t VERIFY_ROW = 20;      // words per candidate in a window tile: 16 + 4 of padding (conflict-free 128-bit rows)
+constexpr uint32_t VERIFY_WARP_WORDS = 3u * VERIFY_WORDS + 2u * 32u * VERIFY_ROW;
+// per-warp shared memory of verify_kernel: the read scratch, the read / verification mask / seed mask of the
+// current lookup as 32-bit words in base order, and two window tiles (one being filled, one being compared)
+static size_t verify_smem_bytes(uint32_t nw_max) {
+  return (size_t)WARPS_PER_BLOCK * (scratch_words(nw_max) * 8u + VERIFY_WARP_WORDS * 4u);
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// The windows are FETCHED four lanes per candidate -- eight whole 64-byte blocks per instruction, each from
+// one cache line (a lane-per-candidate load touches 32 lines per instruction and the L1 serves about one line
+// per two cycles) -- by asynchronous copies straight into a 32 x 16-word tile in shared memory, and COMPARED
+// one lane per candidate from that tile (alignment selects, funnel shifts and mask loads once per candidate
+// instead of once per 16 bases).  Two tiles per warp: the windows of block i + 1 are on their way while block i
+// is compared, the entries of block i + 2 while those are issued.
+template <bool PACKED, class Args>
+__global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS_PER_SM)
+verify_kernel(const __grid_constant__ Args a) {
+  extern __shared__ uint64_t smem[];
+  __shared__ BlockTally tally;
+  tally_init(tally);
+  HwGroup<32> w;
+  const uint32_t lane = w.lane(), q = lane & 3u, c4 = lane & ~3u;
+  const uint32_t warp = threadIdx.x / 32u;
+  ReadScratch sc = carve_scratch(smem + (size_t)warp * scratch_words(a.nw_max), a.nw_max);
+  uint32_t* const masks = reinterpret_cast<uint32_t*>(smem + (size_t)WARPS_PER_BLOCK * scratch_words(a.nw_max)) +
+                          (size_t)warp * VERIFY_WARP_WORDS;
+  uint32_t* const tiles = masks + 3u * VERIFY_WORDS;
+  const uint32_t tiles_sa = (uint32_t)__cvta_generic_to_shared(tiles);
+  uint32_t cached_len = 0, slots = 0;
+  Counters ctr{0u, 0u, 0u};
+  uint32_t n_blocks = *reinterpret_cast<volatile const uint32_t*>(a.queue + 5);
+  if (n_blocks > a.park.cap_blocks) n_blocks = a.park.cap_blocks;
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0u) base = atomicAdd(a.queue + 6, VERIFY_TICKET);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= n_blocks) break;
+    // lane i describes block base + i: record, lookup, first slot, end of the run (dead: nothing to do)
+    uint32_t d_t = 0xFFFFFFFFu, d_j = 0u, d_r = 0u, d_first = 0u, d_end = 0u;
+    if (lane < VERIFY_TICKET && base + lane < n_blocks) {
+      d_t = a.park.desc[2u * (size_t)(base + lane)];
+      if (d_t != 0xFFFFFFFFu) {                           // else: reserved by a read that found no room
+        const uint32_t word = a.park.desc[2u * (size_t)(base + lane) + 1u];
+        const uint32_t* rec = a.park.recs + (size_t)d_t * PARK_WORDS;
+        const uint32_t* mine = rec + 2u + PARK_LOOKUP_WORDS * (word & 7u);
+        d_j = word & 7u; d_r = rec[0]; d_first = mine[1] + 32u * (word >> 3); d_end = mine[1] + mine[2];
+      }
+    }
+    // this lane's entry of block i (0 for the slots past the end of a run and for dead blocks)
+    auto entry_of = [&](uint32_t i) -> uint32_t {
+      if (i >= VERIFY_TICKET) return 0u;
+      const uint32_t first = __shfl_sync(0xFFFFFFFFu, d_first, (int)i), end = __shfl_sync(0xFFFFFFFFu, d_end, (int)i);
+      const uint32_t j = __shfl_sync(0xFFFFFFFFu, d_j, (int)i);
+      return first + lane < end ? a.ix[j / 3u].entries[first + lane].pos : 0u;
+    };
+    // the windows of block i, straight into tile i & 1: step u fetches the 64-byte block of slot 4c + u, 16 bytes per lane
+    auto fetch = [&](uint32_t i, uint32_t e) {
+      if (i < VERIFY_TICKET) {
+        const uint32_t j = __shfl_sync(0xFFFFFFFFu, d_j, (int)i);
+        const uint64_t* genome = a.ix[j / 3u].genome;
+        const uint32_t sa = tiles_sa + ((i & 1u) * 32u * VERIFY_ROW + 4u * q) * 4u;
+#pragma unroll
+        for (uint32_t u = 0; u < 4u; ++u) {
+          const uint64_t gp = (uint64_t)__shfl_sync(0xFFFFFFFFu, e, (int)(c4 + u)) + PAD_BASES - j % 3u;
+          cp_async16(sa + (c4 + u) * VERIFY_ROW * 4u, reinterpret_cast<const uint4*>(genome) + ((gp >> 6) + q));
+        }
+      }
+      cp_async_commit();
+    };
+    uint32_t cur_t = 0xFFFFFFFFu, cur_j = 0xFFFFFFFFu, len = 0u;
+    uint32_t e_cur = entry_of(0), e_next = entry_of(1);
+    fetch(0, e_cur);
+    for (uint32_t i = 0; i < VERIFY_TICKET; ++i) {
+      fetch(i + 1u, e_next);                               // an empty group past the ticket's end
+      const uint32_t e_after = entry_of(i + 2u);
+      const uint32_t t = __shfl_sync(0xFFFFFFFFu, d_t, (int)i);
+      if (t != 0xFFFFFFFFu) {
+        const uint32_t j = __shfl_sync(0xFFFFFFFFu, d_j, (int)i), first = __shfl_sync(0xFFFFFFFFu, d_first, (int)i),
+                       end = __shfl_sync(0xFFFFFFFFu, d_end, (int)i);
+        const uint32_t seed_i = j % 3u;
+        const bool live = first + lane < end;
+        if (t != cur_t) {                                 // another read: pack it
+          const char* seq = read_at<PACKED>(a, __shfl_sync(0xFFFFFFFFu, d_r, (int)i), len);
+          __syncwarp();
+          load_read<HwGroup<32>, PACKED>(w, seq, len, a.ag != 0u, sc);
+          if (cached_len != len) { build_masks(w, len, sc); cached_len = len; }
+        }
+        if (t != cur_t || j != cur_j) {                   // another lookup: read and masks as 32-bit words in base order
+          const uint32_t nw = (len + 31u) >> 5;
+          __syncwarp();
+          if (lane < VERIFY_WORDS) {
+            const uint32_t k = lane >> 1, sh = (lane & 1u) ? 0u : 32u;
+            masks[lane] = k < nw ? (uint32_t)(sc.R[k] >> sh) : 0u;
+            masks[VERIFY_WORDS + lane] = k < nw ? (uint32_t)(sc.VM[seed_i * sc.nw + k] >> sh) : 0u;
+            masks[2u * VERIFY_WORDS + lane] = k < nw ? (uint32_t)(sc.SM[seed_i * sc.nw + k] >> sh) : 0u;
+          }
+          cur_t = t; cur_j = j;
+        }
+        cp_async_wait<1>();                               // block i's windows have landed (block i + 1's may still fly)
+        __syncwarp();
+        const uint32_t* tile = tiles + (i & 1u) * 32u * VERIFY_ROW;
+        uint32_t W[16];
+#pragma unroll
+        for (uint32_t k = 0; k < 4u; ++k) {               // memory order of the packed words: u64 pairs, low half first
+          const uint4 v = *reinterpret_cast<const uint4*>(tile + lane * VERIFY_ROW + 4u * k);
+          W[4u * k] = v.y; W[4u * k + 1u] = v.x; W[4u * k + 2u] = v.w; W[4u * k + 3u] = v.z;
+        }
+        // align the window with read position 0: 2 s bits = (s >> 4) words + (2 s & 31) bits
+        const uint32_t s = (uint32_t)(((uint64_t)e_cur + PAD_BASES - seed_i) & 63u);
+        const uint32_t off = s >> 4, bit = (2u * s) & 31u;
+        uint32_t tt[15], v[13];
+#pragma unroll
+        for (uint32_t k = 0; k < 15u; ++k) tt[k] = (off & 2u) ? (k + 2u < 16u ? W[k + 2u] : 0u) : W[k];
+#pragma unroll
+        for (uint32_t k = 0; k < 13u; ++k) v[k] = (off & 1u) ? tt[k + 1u] : tt[k];
+        uint32_t mm = 0u, sd = 0u;
+#pragma unroll
+        for (uint32_t k4 = 0; k4 < VERIFY_WORDS; k4 += 4u) {
+          const uint4 r4 = *reinterpret_cast<const uint4*>(masks + k4);
+          const uint4 vm4 = *reinterpret_cast<const uint4*>(masks + VERIFY_WORDS + k4);
+          const uint4 sm4 = *reinterpret_cast<const uint4*>(masks + 2u * VERIFY_WORDS + k4);
+          const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w}, vv[4] = {vm4.x, vm4.y, vm4.z, vm4.w}, ss[4] = {sm4.x, sm4.y, sm4.z, sm4.w};
+#pragma unroll
+          for (uint32_t k = 0; k < 4u; ++k) {
+            const uint32_t x = __funnelshift_l(v[k4 + k + 1u], v[k4 + k], bit) ^ rr[k];
+            const uint32_t d = x | (x >> 1);
+            mm += (uint32_t)__popc(d & vv[k]);
+            sd |= d & ss[k];
+          }
+        }
+        const bool cand = live && sd == 0u;
+        if (cand) ctr.candidates++;
+        if (live) ++slots;
+        a.park.bytes[32u * (size_t)(base + i) + lane] = (uint8_t)(cand ? mm : MM_NONE);
+      }
+      __syncwarp();                                       // tile i & 1 is refilled two blocks on
+      e_cur = e_next; e_next = e_after;
+    }
+    cp_async_wait<0>();
+  }
+  slots = __reduce_add_sync(0xFFFFFFFFu, slots);
+  if (lane == 0u && slots && a.counters) atomicAdd(a.counters + 4, (unsigned long long)slots);
+  flush_counters(w, ctr, false, tally, a.flags, a.counters);
+}
+
+// the bytes of all runs of a parked read, on their way before the ordered pass asks for them
+__device__ __forceinline__ void prefetch_run_bytes(const uint32_t* rec, const uint8_t* bytes, uint32_t lane) {
+  for (uint32_t j = 0; j < LOOKUP_LANES; ++j) {
+    const uint32_t* mine = rec + 2u + PARK_LOOKUP_WORDS * j;
+    if ((mine[0] & 0xFFu) != PK_RUN) continue;
+    const uint8_t* p = bytes + 32u * (size_t)mine[3];
+    for (uint32_t off = 128u * lane; off < mine[2]; off += 128u * 32u) WALT_PREFETCH(p + off);
+  }
+}
+
+// A warp per parked read with a record: the ordered fold (fold_parked, walt_core.cuh).
+template <bool PACKED>
+__global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS_PER_SM)
+se_fold_kernel(const __grid_constant__ SeArgs a) {
+  __shared__ BlockTally tally;
+  tally_init(tally);
+  HwGroup<32> w;
+  const uint32_t lane = w.lane();
+  Counters ctr{0u, 0u, 0u};
+  uint32_t n = *reinterpret_cast<volatile const uint32_t*>(a.queue + 1);
+  if (n > a.park.rec_cap) n = a.park.rec_cap;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.counters && n) atomicAdd(a.counters + 3, (unsigned long long)n);
+  for (;;) {
+    const uint32_t t = next_ticket<32>(a.queue + 7);
+    if (t >= n) break;
+    const uint32_t* rec = a.park.recs + (size_t)t * PARK_WORDS;
+    const uint32_t r = rec[0];
+    if (r == 0xFFFFFFFFu) continue;                       // a dead record: the read is on MAP_TAKE's list
+    uint32_t len;
+    read_at<PACKED>(a, r, len);
+    prefetch_run_bytes(rec, a.park.bytes, lane);
+    BestSink<HwGroup<32>> sink;
+    sink.st.pos = 0u; sink.st.times = 0u; sink.st.mm = a.max_mismatches; sink.st.strand = '+';
+    fold_parked(w, a.ix, a.cv, len, rec, a.park.bytes, sink,
+                [&](const uint32_t* m, uint32_t strand) { sink.apply(m[1], m[2], m[3], m[4], strand); });
+    if (lane == 0) {
+      uint4 o;
+      o.x = sink.st.pos; o.y = sink.st.times; o.z = sink.st.mm; o.w = sink.st.strand & 0xFFu;
+      *reinterpret_cast<uint4*>(a.out + r) = o;
+    }
+    __syncwarp();
+  }
+  flush_counters(w, ctr, false, tally, a.flags, a.counters);
+}
+
+template <bool PACKED>
+__global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS_PER_SM)
+pe_fold_kernel(const __grid_constant__ PeArgs a) {
+  __shared__ BlockTally tally;
+  __shared__ uint32_t hists[WARPS_PER_BLOCK][LOG_MAX_MM + 1u];
+  tally_init(tally);
+  HwGroup<32> w;
+  const uint32_t lane = w.lane();
+  uint32_t* hist = hists[threadIdx.x / 32u];
+  Counters ctr{0u, 0u, 0u};
+  uint32_t n = *reinterpret_cast<volatile const uint32_t*>(a.queue + 1);
+  if (n > a.park.rec_cap) n = a.park.rec_cap;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.counters && n) atomicAdd(a.counters + 3, (unsigned long long)n);
+  for (;;) {
+    const uint32_t t = next_ticket<32>(a.queue + 7);
+    if (t >= n) break;
+    const uint32_t* rec = a.park.recs + (size_t)t * PARK_WORDS;
+    const uint32_t r = rec[0];
+    if (r == 0xFFFFFFFFu) continue;
+    uint32_t len;
+    read_at<PACKED>(a, r, len);
+    prefetch_run_bytes(rec, a.park.bytes, lane);
+    LogSink<HwGroup<32>> sink;
+    sink.log = a.log + (size_t)r * a.log_slots; sink.hist = hist; sink.cap = a.top_k; sink.max_mm = a.max_mismatches;
+    sink.reset(w);
+    fold_parked(w, a.ix, a.cv, len, rec, a.park.bytes, sink,
+                [&](const uint32_t* m, uint32_t strand) {
+                  const uint32_t k = m[0] >> 8;
+                  uint32_t g = 0u, mm = 0u;
+                  if (lane < k) { g = m[1u + 2u * lane]; mm = m[2u + 2u * lane]; }
+                  sink.consume(w, lane < k, mm, g, strand);
+                });
+    if (lane == 0) a.n_log[r] = sink.n_log;
+    __syncwarp();
+  }
+  flush_counters(w, ctr, false, tally, a.flags, a.counters);
 }
 
 // Second phase: one THREAD per read replays its log through TopCandidates' heap (paired.hpp:51-74,
@@ -566,15 +793,18 @@ struct HeapArgs {
   walt_cand* ranked[2];
   uint32_t* n_ranked[2];
   HeapEntry* heaps;
-  const uint32_t* parked[2];     // parked-read lists of the two mate launches (NULL: nothing was parked)
-  const uint32_t* queue[2];      // their queue blocks: [1] reads at the front of the list, [3] at its back
+  const uint32_t* list[2];       // parked reads of the two mate launches: MAP_TAKE's lists (NULL: nothing was parked) ...
+  const uint32_t* recs[2];       // ... and the records of the others
+  const uint32_t* queue[2];      // their queue blocks: [1] records, [3] reads on the list
+  uint32_t rec_cap;
   uint32_t n, top_k, log_slots;
   uint32_t zero_fill;     // see PeArgs
 };
 
 // Work items: [0, 2n) every read of both mates whose log is short (reads that were not parked
-// log at most LOOKUP_LANES * LANE_RUN_CAP events); [2n, 2n + parked) the parked reads, i.e. the long
-// logs, next to each other -- so that the lanes of a warp replay logs of similar length.
+// log at most LOOKUP_LANES * LANE_RUN_CAP events); then, per mate, n places for the records and n for
+// MAP_TAKE's list: the parked reads, i.e. the long logs, next to each other -- so that the lanes of a
+// warp replay logs of similar length.
 constexpr uint32_t HEAP_BLOCK = 128;
 constexpr uint32_t SHORT_LOG = LOOKUP_LANES * LANE_RUN_CAP;
 // one thread's heap inside a block-wide array: slot i of thread t at [i * HEAP_BLOCK + t] (8-byte
@@ -641,13 +871,20 @@ pe_heap_kernel(const __grid_constant__ HeapArgs a) {
   uint32_t mate, r;
   if (t < 2u * a.n) {
     mate = t >= a.n ? 1u : 0u; r = t - mate * a.n;
-    if (a.parked[0] && a.n_log[mate][r] > SHORT_LOG) return;      // a parked read: below
+    if (a.list[0] && a.n_log[mate][r] > SHORT_LOG) return;        // a parked read: below
   } else {
-    if (!a.parked[0] || t >= 4u * a.n) return;
+    if (!a.list[0] || t >= 6u * a.n) return;
     uint32_t u = t - 2u * a.n;
-    mate = u >= a.n ? 1u : 0u; u -= mate * a.n;
-    if (u >= a.queue[mate][1] && u < a.n - a.queue[mate][3]) return;   // between the two ends of the list
-    r = a.parked[mate][u];
+    mate = u >= 2u * a.n ? 1u : 0u; u -= mate * 2u * a.n;
+    if (u < a.n) {
+      if (u >= a.queue[mate][1] || u >= a.rec_cap) return;
+      r = a.recs[mate][(size_t)u * PARK_WORDS];
+      if (r == 0xFFFFFFFFu) return;
+    } else {
+      u -= a.n;
+      if (u >= a.queue[mate][3]) return;
+      r = a.list[mate][u];
+    }
     if (a.n_log[mate][r] <= SHORT_LOG) return;                    // done above
   }
   const HeapEntry* log = a.log[mate] + (size_t)r * a.log_slots;
@@ -863,6 +1100,7 @@ struct ReadSrc {
 // queue block i of the engine: QUEUE_WORDS words (see SeArgs::queue)
 // 0: device-resident SE; 1..N_SLOTS: SE host chunks; then two (one per mate) for device-resident PE
 // and two per slot for PE host chunks
+constexpr uint32_t N_COUNTERS = 5;   // lookups, candidates, literal lookups, parked reads, slots verified by verify_kernel
 constexpr uint32_t QUEUE_WORDS = 8;
 static uint32_t* queue_block(walt_engine* e, uint32_t i) { return e->d_flags + 16u + QUEUE_WORDS * i; }
 constexpr uint32_t QB_SE_DEVICE = 0, QB_SE_SLOT = 1, QB_PE_DEVICE = 1 + N_SLOTS, QB_PE_SLOT = 3 + N_SLOTS;
@@ -878,7 +1116,7 @@ static void fill_common(walt_engine* e, Args& a, const ReadSrc& src, uint32_t n,
   a.seqs = src.d_seqs; a.offs = src.d_offs; a.seq_base = src.seq_base; a.n = n; a.uniform_len = src.uniform_len;
   a.read_base = src.read_base;
   a.nw_max = std::max<uint32_t>(1u, (src.max_len + 31u) / 32u);
-  a.ag = ag ? 1u : 0u; a.max_mismatches = m; a.flags = e->d_flags; a.queue = d_queue; a.parked = nullptr; a.lit = nullptr; a.lit_cap = 0u;
+  a.ag = ag ? 1u : 0u; a.max_mismatches = m; a.flags = e->d_flags; a.queue = d_queue; a.park = ParkView{nullptr, nullptr, nullptr, nullptr, 0u, 0u};
   a.counters = e->d_counters;
 }
 
@@ -893,40 +1131,44 @@ static int take_grid(walt_engine* e, K kernel, size_t smem, uint32_t* grid) {
   return WALT_OK;
 }
 
-// The kernels behind one that parks reads: lit_kernel on the side stream of the launch, MAP_TAKE beside
-// it on the launch's own stream, then MAP_TAKE_LIT
+// The kernels behind one that parks reads: verification of every reserved block, the fold of the reads
+// with a record, MAP_TAKE for the rest.  All persistent; each finds out on the device how much there is to do.
 template <class Args>
-static int launch_take(walt_engine* e, const Args& a, bool packed, void (*take)(Args), void (*take_lit)(Args), size_t smem,
-                       const ParkBuf* pk, cudaStream_t st) {
+static int launch_behind_park(walt_engine* e, const Args& a, void (*verify)(Args), void (*fold)(Args), void (*take)(Args),
+                              size_t smem_v, size_t smem_f, size_t smem_t, cudaStream_t st) {
   int rc;
   uint32_t grid = 0;
-  const bool side = a.lit_cap && pk->lit_stream;
-  if (a.lit_cap) {
-    cudaStream_t ls = side ? pk->lit_stream : st;
-    if (side) {
-      WALT_CUDA_TRY(cudaEventRecord(pk->fork, st));
-      WALT_CUDA_TRY(cudaStreamWaitEvent(ls, pk->fork, 0));
+  if (a.park.rec_cap) {
+    if ((rc = take_grid(e, verify, smem_v, &grid))) return rc;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (e->time_kernels) {
+      WALT_CUDA_TRY(cudaEventCreate(&ev0)); WALT_CUDA_TRY(cudaEventCreate(&ev1));
+      WALT_CUDA_TRY(cudaEventRecord(ev0, st));
     }
-    void (*lk)(Args) = packed ? lit_kernel<true, Args> : lit_kernel<false, Args>;
-    lk<<<(uint32_t)e->sm_count * 8u, 128, 0, ls>>>(a);
+    verify<<<grid, BLOCK_THREADS, smem_v, st>>>(a);
     WALT_CUDA_TRY(cudaGetLastError());
-    if (side) WALT_CUDA_TRY(cudaEventRecord(pk->join, ls));
-    e->stats.n_kernel_launches++;
+    if (e->time_kernels) {
+      WALT_CUDA_TRY(cudaEventRecord(ev1, st));
+      e->verify_events.emplace_back(ev0, ev1);
+    }
+    if ((rc = take_grid(e, fold, smem_f, &grid))) return rc;
+    fold<<<grid, BLOCK_THREADS, smem_f, st>>>(a);
+    WALT_CUDA_TRY(cudaGetLastError());
+    e->stats.n_kernel_launches += 2;
   }
-  if ((rc = take_grid(e, take, smem, &grid))) return rc;
-  take<<<grid, BLOCK_THREADS, smem, st>>>(a);
+  if ((rc = take_grid(e, take, smem_t, &grid))) return rc;
+  take<<<grid, BLOCK_THREADS, smem_t, st>>>(a);
   WALT_CUDA_TRY(cudaGetLastError());
-  if (side) WALT_CUDA_TRY(cudaStreamWaitEvent(st, pk->join, 0));
-  if ((rc = take_grid(e, take_lit, smem, &grid))) return rc;
-  take_lit<<<grid, BLOCK_THREADS, smem, st>>>(a);
-  WALT_CUDA_TRY(cudaGetLastError());
-  e->stats.n_kernel_launches += 2;
+  e->stats.n_kernel_launches++;
   return WALT_OK;
 }
 
-// park != NULL (list: room for n read numbers; lit: LIT_WORDS words for each of the first lit_cap of
-// them): reads that need their whole group are parked by the first kernel and mapped by a second
-// one, a warp per read
+static ParkView park_view(const ParkBuf* pk) {
+  return ParkView{pk->recs, pk->desc, pk->bytes, pk->list, pk->rec_cap, pk->cap_blocks};
+}
+
+// pk != NULL (reserve_park): reads that need more than their lookup lanes are parked by the first kernel
+// and finished by the kernels behind it
 static int launch_se(walt_engine* e, const ReadSrc& src, uint32_t n, int ag, uint32_t m, uint32_t b, walt_best* d_out,
                      uint32_t* d_queue, const ParkBuf* pk, cudaStream_t st, uint32_t share = 1) {
   if (src.max_len > MAX_READ_LEN) return fail(WALT_EINVAL, "read longer than 1024 bases");
@@ -934,7 +1176,7 @@ static int launch_se(walt_engine* e, const ReadSrc& src, uint32_t n, int ag, uin
   fill_common(e, a, src, n, ag, m, b, d_queue);
   a.out = d_out;
   const bool park = e->defer && pk != nullptr;
-  if (park) { a.parked = pk->list; a.lit = pk->lit; a.lit_cap = pk->lit_cap; }
+  if (park) a.park = park_view(pk);
   const uint32_t wd = e->group_width;
   const size_t smem = se_smem_bytes(a.nw_max, wd);
   uint32_t grid = 0;
@@ -952,9 +1194,10 @@ static int launch_se(walt_engine* e, const ReadSrc& src, uint32_t n, int ag, uin
   WALT_CUDA_TRY(cudaGetLastError());
   e->stats.n_kernel_launches++;
   if (park)
-    return launch_take(e, a, src.packed, src.packed ? se_map_kernel<32, true, MAP_TAKE> : se_map_kernel<32, false, MAP_TAKE>,
-                       src.packed ? se_map_kernel<32, true, MAP_TAKE_LIT> : se_map_kernel<32, false, MAP_TAKE_LIT>,
-                       se_smem_bytes(a.nw_max, 32u), pk, st);
+    return launch_behind_park(e, a, src.packed ? verify_kernel<true, SeArgs> : verify_kernel<false, SeArgs>,
+                              src.packed ? se_fold_kernel<true> : se_fold_kernel<false>,
+                              src.packed ? se_map_kernel<32, true, MAP_TAKE> : se_map_kernel<32, false, MAP_TAKE>,
+                              verify_smem_bytes(a.nw_max), 0, se_smem_bytes(a.nw_max, 32u), st);
   return WALT_OK;
 }
 
@@ -968,7 +1211,7 @@ static int launch_pe_log(walt_engine* e, const ReadSrc& src, uint32_t n, int ag,
   a.top_k = top_k; a.ranked = nullptr; a.n_ranked = nullptr;
   a.log = d_log; a.n_log = d_nlog; a.log_slots = pe_log_slots(top_k, m); a.zero_fill = 0u;
   const bool park = e->defer && pk != nullptr;
-  if (park) { a.parked = pk->list; a.lit = pk->lit; a.lit_cap = pk->lit_cap; }
+  if (park) a.park = park_view(pk);
   const uint32_t wd = e->group_width;
   const size_t smem = pe_log_smem_bytes(a.nw_max, wd);
   uint32_t grid = 0;
@@ -986,9 +1229,10 @@ static int launch_pe_log(walt_engine* e, const ReadSrc& src, uint32_t n, int ag,
   WALT_CUDA_TRY(cudaGetLastError());
   e->stats.n_kernel_launches++;
   if (park)
-    return launch_take(e, a, src.packed, src.packed ? pe_log_kernel<32, true, MAP_TAKE> : pe_log_kernel<32, false, MAP_TAKE>,
-                       src.packed ? pe_log_kernel<32, true, MAP_TAKE_LIT> : pe_log_kernel<32, false, MAP_TAKE_LIT>,
-                       pe_log_smem_bytes(a.nw_max, 32u), pk, st);
+    return launch_behind_park(e, a, src.packed ? verify_kernel<true, PeArgs> : verify_kernel<false, PeArgs>,
+                              src.packed ? pe_fold_kernel<true> : pe_fold_kernel<false>,
+                              src.packed ? pe_log_kernel<32, true, MAP_TAKE> : pe_log_kernel<32, false, MAP_TAKE>,
+                              verify_smem_bytes(a.nw_max), 0, pe_log_smem_bytes(a.nw_max, 32u), st);
   return WALT_OK;
 }
 
@@ -1029,24 +1273,32 @@ static int reserve_bytes(void** p, size_t* cap, size_t need) {
 
 // room for the parked reads of a launch over n reads
 static int reserve_park(walt_engine* e, ParkBuf* pk, uint32_t n) {
-  pk->lit_limit = e->lit_ahead ? LIT_CAP_MAX : 0u;
   int rc;
   if ((rc = reserve(&pk->list, &pk->list_cap, (size_t)n))) return rc;
-  pk->lit_cap = std::min<uint32_t>(n, pk->lit_limit);
-  if (pk->lit_cap && e->lit_side && !pk->lit_stream) {
-    WALT_CUDA_TRY(cudaStreamCreateWithFlags(&pk->lit_stream, cudaStreamNonBlocking));
-    WALT_CUDA_TRY(cudaEventCreateWithFlags(&pk->fork, cudaEventDisableTiming));
-    WALT_CUDA_TRY(cudaEventCreateWithFlags(&pk->join, cudaEventDisableTiming));
-  }
-  return reserve(&pk->lit, &pk->lit_words, (size_t)pk->lit_cap * LIT_WORDS);
+  pk->rec_cap = e->flat_verify ? std::min<uint32_t>(n, REC_CAP_MAX) : 0u;
+  pk->cap_blocks = e->flat_verify ? (uint32_t)std::min<uint64_t>(BLOCK_CAP_MAX, std::max<uint64_t>(1u << 22, 8ull * n)) : 0u;
+  if (!pk->rec_cap) return WALT_OK;
+  if ((rc = reserve(&pk->recs, &pk->recs_words, (size_t)pk->rec_cap * PARK_WORDS))) return rc;
+  if ((rc = reserve(&pk->desc, &pk->desc_words, (size_t)pk->cap_blocks * 2u))) return rc;
+  return reserve(&pk->bytes, &pk->bytes_cap, (size_t)pk->cap_blocks * 32u);
 }
 
 static int fetch_status(walt_engine* e) {
   uint32_t f = 0;
   WALT_CUDA_TRY(cudaMemcpy(&f, e->d_flags, 4, cudaMemcpyDeviceToHost));
-  unsigned long long c[4];
+  unsigned long long c[N_COUNTERS];
   WALT_CUDA_TRY(cudaMemcpy(c, e->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
   e->stats.n_lookups = c[0]; e->stats.n_candidates = c[1]; e->stats.n_literal = c[2]; e->stats.n_parked = c[3];
+  e->stats.n_verify_slots = c[4];
+  // device time of the verify_kernel launches since the last fetch (walt_engine_set_kernel_timing)
+  double ms = 0.0;
+  for (auto& ev : e->verify_events) {
+    float t = 0.f;
+    if (cudaEventSynchronize(ev.second) == cudaSuccess && cudaEventElapsedTime(&t, ev.first, ev.second) == cudaSuccess) ms += t;
+    cudaEventDestroy(ev.first); cudaEventDestroy(ev.second);
+  }
+  e->verify_events.clear();
+  e->stats.verify_ns = (uint64_t)(ms * 1e6);
   if (f & 1u) {
     cudaMemset(e->d_flags, 0, 4);
     return fail(WALT_ENONACGT, "[ERROR: NON-ACGT NUCLEOTIDE] in a read handed to the mapping engine");
@@ -1125,8 +1377,7 @@ int walt_engine_create(walt_engine** out, int device) {
   if (const char* v = getenv("WALT_PE_SIDE")) e->pe_side = atoi(v);
   if (const char* v = getenv("WALT_PE_LOGGED")) e->pe_logged = atoi(v);
   if (const char* v = getenv("WALT_DEFER")) e->defer = atoi(v);
-  if (const char* v = getenv("WALT_LIT_SIDE")) e->lit_side = atoi(v);
-  if (const char* v = getenv("WALT_LIT")) e->lit_ahead = atoi(v);
+  if (const char* v = getenv("WALT_FLAT")) e->flat_verify = atoi(v);
   if (const char* v = getenv("WALT_PAIR_WIDE")) e->pair_wide = atoi(v);
   if (const char* v = getenv("WALT_HEAP_SMEM")) e->heap_smem = atoi(v);
   if (const char* v = getenv("WALT_CHUNK_SHARE")) e->chunk_share = (uint32_t)std::max(1, atoi(v));
@@ -1135,8 +1386,8 @@ int walt_engine_create(walt_engine** out, int device) {
   for (uint32_t i = 0; i <= MAX_DEPTH; ++i) { e->pow3.v[i] = p; p *= 3u; }
   WALT_CUDA_TRY(cudaMalloc(&e->d_flags, N_FLAG_WORDS * 4));
   WALT_CUDA_TRY(cudaMemset(e->d_flags, 0, N_FLAG_WORDS * 4));
-  WALT_CUDA_TRY(cudaMalloc(&e->d_counters, 4 * 8));
-  WALT_CUDA_TRY(cudaMemset(e->d_counters, 0, 4 * 8));
+  WALT_CUDA_TRY(cudaMalloc(&e->d_counters, N_COUNTERS * 8));
+  WALT_CUDA_TRY(cudaMemset(e->d_counters, 0, N_COUNTERS * 8));
   for (auto& s : e->slot) {
     WALT_CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     WALT_CUDA_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
@@ -1475,6 +1726,12 @@ int walt_engine_set_defer(walt_engine* e, int on) {
   return WALT_OK;
 }
 
+int walt_engine_set_kernel_timing(walt_engine* e, int on) {
+  if (!e) return fail(WALT_EINVAL, "bad argument");
+  e->time_kernels = on != 0;
+  return WALT_OK;
+}
+
 int walt_engine_set_chunk_reads(walt_engine* e, uint32_t n) {
   if (!e) return fail(WALT_EINVAL, "bad argument");
   e->chunk_reads = n;   // 0 = automatic
@@ -1488,7 +1745,7 @@ int walt_engine_device_stats(walt_engine* e, walt_stats* out) {
   WALT_CUDA_TRY(cudaDeviceSynchronize());
   const uint64_t launches = e->stats.n_kernel_launches;
   if ((rc = fetch_status(e))) return rc;
-  WALT_CUDA_TRY(cudaMemset(e->d_counters, 0, 4 * 8));
+  WALT_CUDA_TRY(cudaMemset(e->d_counters, 0, N_COUNTERS * 8));
   *out = e->stats;
   out->n_kernel_launches = launches;
   return WALT_OK;
@@ -1530,7 +1787,7 @@ static int map_se_host(walt_engine* e, const char* seqs, const uint64_t* offs, u
   if (rc) return rc;
   if ((rc = check_pair(e, ag_wildcard))) return rc;
   e->stats = walt_stats{};
-  WALT_CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, 4 * 8, e->slot[0].stream));
+  WALT_CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, N_COUNTERS * 8, e->slot[0].stream));
   WALT_CUDA_TRY(cudaStreamSynchronize(e->slot[0].stream));
   uint32_t k = 0, total_short = 0;
   // chunk size: ASCII batches are PCIe-bound and like a short pipeline fill; packed batches are
@@ -1660,12 +1917,14 @@ static int launch_pe_chunk(walt_engine* e, const ReadSrc& m1, const ReadSrc& m2,
     h.zero_fill = want_pairs ? 1u : 0u;   // only walt_engine_map_pe hands the lists themselves to the host
     const bool parked = pk != nullptr && e->defer;
     for (int i = 0; i < 2; ++i) {
-      h.parked[i] = parked ? pk[i].list : nullptr;
+      h.list[i] = parked ? pk[i].list : nullptr;
+      h.recs[i] = parked ? pk[i].recs : nullptr;
       h.queue[i] = q + QUEUE_WORDS * i;
     }
     // SMEM: heaps of top_k entries per thread in shared memory (local memory heaps of 16 resident blocks thrash the L1)
     const bool smem = ps.heaps == nullptr;
-    const uint32_t blocks = (2u * cn + (parked ? 2u * cn : 0u) + HEAP_BLOCK - 1u) / HEAP_BLOCK;
+    h.rec_cap = parked ? pk[0].rec_cap : 0u;
+    const uint32_t blocks = (2u * cn + (parked ? 4u * cn : 0u) + HEAP_BLOCK - 1u) / HEAP_BLOCK;
     if (smem) {
       const size_t bytes = (size_t)top_k * HEAP_BLOCK * sizeof(HeapEntry);
       WALT_CUDA_TRY(cudaFuncSetAttribute(pe_heap_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -1700,7 +1959,7 @@ static int map_pe_host(walt_engine* e, const char* seqs1, const uint64_t* offs1,
                        walt_pe_result* compact, uint32_t* n_short1, uint32_t* n_short2) {
   int rc;
   e->stats = walt_stats{};
-  WALT_CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, 4 * 8, e->slot[0].stream));
+  WALT_CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, N_COUNTERS * 8, e->slot[0].stream));
   WALT_CUDA_TRY(cudaStreamSynchronize(e->slot[0].stream));
   // chunk so that a slot's scratch (ranked lists, and the candidate logs of the two-phase form)
   // stays below ~1.5 GiB

@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/walt_b200.h"
@@ -41,21 +42,18 @@ struct DeviceSubIndex {
 };
 
 constexpr uint32_t N_SLOTS = 3;   // host chunks in flight (copy in / map / copy out)
-constexpr uint32_t LIT_CAP_MAX = 1u << 22;   // parked reads of one launch whose literal regions are computed ahead
+constexpr uint32_t REC_CAP_MAX = 1u << 21;     // parked reads of one launch that get a record (the rest: MAP_TAKE)
+constexpr uint32_t BLOCK_CAP_MAX = 1u << 23;   // 32-candidate verification blocks of one launch (256 M candidates)
 
-// device buffers of a launch that parks reads: their numbers, and the literal regions of the first
-// lit_cap of them (the rest replay their literal lookups inside the take-over kernel)
+// device buffers of a launch that parks reads (ParkView, walt_engine.cu)
 struct ParkBuf {
-  uint32_t* list = nullptr;  size_t list_cap = 0;
-  uint32_t* lit = nullptr;   size_t lit_words = 0;
-  uint32_t lit_cap = 0, lit_limit = 0;
-  cudaStream_t lit_stream = nullptr;          // lit_kernel runs here, beside the first take-over kernel
-  cudaEvent_t fork = nullptr, join = nullptr;
+  uint32_t* list = nullptr;   size_t list_cap = 0;
+  uint32_t* recs = nullptr;   size_t recs_words = 0;
+  uint32_t* desc = nullptr;   size_t desc_words = 0;
+  uint8_t* bytes = nullptr;   size_t bytes_cap = 0;
+  uint32_t rec_cap = 0, cap_blocks = 0;
   void release() {
-    cudaFree(list); cudaFree(lit);
-    if (lit_stream) cudaStreamDestroy(lit_stream);
-    if (fork) cudaEventDestroy(fork);
-    if (join) cudaEventDestroy(join);
+    cudaFree(list); cudaFree(recs); cudaFree(desc); cudaFree(bytes);
     *this = ParkBuf();
   }
 };
@@ -103,13 +101,14 @@ struct walt_engine {
   int defer = 1;                             // 1: reads that need their whole group (repeats) are parked by the mapping
                                              // kernels and finished by a warp-per-read kernel
   waltb200::ParkBuf dev_park[2];             // ... of the device-resident calls
-  int lit_side = 1;                          // 1: lit_kernel on a side stream, beside the first take-over kernel
-  int lit_ahead = 1;                         // 1: literal regions of parked reads are computed by lit_kernel
+  int flat_verify = 1;                       // 1: parked reads get records, their runs are verified by verify_kernel (0: MAP_TAKE maps them all)
   int pair_wide = 1;                         // 1: pairs with long lists are paired by a whole warp
   int heap_smem = 1;                         // 1: pe_heap_kernel keeps its heaps in shared memory when they fit
   uint32_t* d_flags = nullptr;               // [0] non-ACGT flag, [2..3] index-build scratch, from [16] the queue
                                              // blocks of the launches in flight (queue_block, walt_engine.cu)
-  unsigned long long* d_counters = nullptr;  // lookups, candidates, literal
+  int time_kernels = 0;                      // 1: CUDA events around every verify_kernel launch (walt_stats.verify_ns)
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> verify_events;
+  unsigned long long* d_counters = nullptr;  // lookups, candidates, literal, parked, verified slots
   walt_stats stats{};
 };
 

@@ -23,7 +23,7 @@ PAIR_DT = np.dtype([("best_times", np.uint32), ("best_i", np.int32), ("best_j", 
                     ("frag_len", np.int32)])
 PE_RESULT_DT = np.dtype([("pair", PAIR_DT), ("c1", CAND_DT), ("c2", CAND_DT), ("single1", BEST_DT),
                          ("single2", BEST_DT)])
-STATS_FIELDS = ("n_lookups", "n_candidates", "n_literal", "n_kernel_launches", "n_parked")
+STATS_FIELDS = ("n_lookups", "n_candidates", "n_literal", "n_kernel_launches", "n_parked", "n_verify_slots", "verify_ns")
 
 _ROOT = os.path.dirname(os.path.abspath(__file__))
 _lib = None
@@ -81,12 +81,35 @@ def packed_genome_bytes(n_bases):
     return int(load_library().walt_packed_genome_bytes(C.c_uint64(n_bases)))
 
 
+_synth = None
+
+
+def synth_library():
+    """libwaltsynth.so: the BENCH-ONLY synthetic workload generators (include/walt_synth.h); not part of the product."""
+    global _synth
+    if _synth is None:
+        load_library()
+        p = os.path.join(_ROOT, "lib", "libwaltsynth.so")
+        if not os.path.exists(p):
+            raise WaltError(-1, f"{p} is missing: build it with `make -C walt_b200/bench`")
+        _synth = C.CDLL(p)
+    return _synth
+
+
 def synth_genome_device(device, n_bases, seed, d_out, repeats=False):
-    L = load_library()
-    fn = L.walt_synth_repeat_genome_device if repeats else L.walt_synth_genome_device
+    S = synth_library()
+    fn = S.walt_synth_repeat_genome_device if repeats else S.walt_synth_genome_device
     rc = fn(C.c_int(device), C.c_uint64(n_bases), C.c_uint64(seed), C.c_void_p(d_out))
     if rc:
-        raise WaltError(rc, L.walt_last_error().decode())
+        raise WaltError(rc, load_library().walt_last_error().decode())
+
+
+def synth_verify_genome_device(device, n_bases, seed, n_families, rep_pct, div_per_mille, d_out):
+    rc = synth_library().walt_synth_verify_genome_device(C.c_int(device), C.c_uint64(n_bases), C.c_uint64(seed),
+                                                         C.c_uint32(n_families), C.c_uint32(rep_pct),
+                                                         C.c_uint32(div_per_mille), C.c_void_p(d_out))
+    if rc:
+        raise WaltError(rc, load_library().walt_last_error().decode())
 
 
 class PinnedArray:
@@ -177,15 +200,20 @@ class Engine:
         return seq, counter, (index[:n] if index is not None else None)
 
     def synth_reads_device(self, d_packed, n_reads, read_len, seed, a_rich, d_out):
-        self._check(self.L.walt_synth_reads_device(self.h, C.c_void_p(d_packed), C.c_uint32(n_reads),
-                                                   C.c_uint32(read_len), C.c_uint64(seed), C.c_int(int(a_rich)),
-                                                   C.c_void_p(d_out)))
+        self._check(synth_library().walt_synth_reads_device(self.h, C.c_void_p(d_packed), C.c_uint32(n_reads),
+                                                            C.c_uint32(read_len), C.c_uint64(seed), C.c_int(int(a_rich)),
+                                                            C.c_void_p(d_out)))
 
     def synth_pairs_device(self, d_packed, n_pairs, read_len, seed, d_out1, d_out2, readthrough_pct=0):
-        self._check(self.L.walt_synth_pairs_device(self.h, C.c_void_p(d_packed), C.c_uint32(n_pairs),
-                                                   C.c_uint32(read_len), C.c_uint64(seed),
-                                                   C.c_uint32(readthrough_pct), C.c_void_p(d_out1),
-                                                   C.c_void_p(d_out2)))
+        self._check(synth_library().walt_synth_pairs_device(self.h, C.c_void_p(d_packed), C.c_uint32(n_pairs),
+                                                            C.c_uint32(read_len), C.c_uint64(seed),
+                                                            C.c_uint32(readthrough_pct), C.c_void_p(d_out1),
+                                                            C.c_void_p(d_out2)))
+
+    def synth_verify_reads_device(self, d_packed, n_reads, read_len, seed, genome_seed, n_families, rep_pct, d_out):
+        self._check(synth_library().walt_synth_verify_reads_device(self.h, C.c_void_p(d_packed), C.c_uint32(n_reads),
+                                                                   C.c_uint32(read_len), C.c_uint64(seed), C.c_uint64(genome_seed),
+                                                                   C.c_uint32(n_families), C.c_uint32(rep_pct), C.c_void_p(d_out)))
 
     def subindex_info(self, which):
         a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
@@ -215,6 +243,9 @@ class Engine:
 
     def set_defer(self, on):
         self._check(self.L.walt_engine_set_defer(self.h, C.c_int(int(on))))
+
+    def set_kernel_timing(self, on):
+        self._check(self.L.walt_engine_set_kernel_timing(self.h, C.c_int(int(on))))
 
     def set_chunk_reads(self, n):
         self._check(self.L.walt_engine_set_chunk_reads(self.h, C.c_uint32(n)))
