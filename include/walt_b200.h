@@ -110,6 +110,12 @@ int walt_engine_load_subindex(walt_engine* e, int which, const char* sequence,
                               const uint32_t* counter /* 4^12+1 */, const uint32_t* index,
                               uint32_t index_size);
 
+/* Index replication between GPUs: everything `src` holds resident (packed genomes, entry arrays, prefix
+ * tables, taint lists, chromosome table) is copied into `dst` device to device (cudaMemcpyPeer: NVLink /
+ * NVSwitch when the devices are peers) -- no file is read again and nothing is rebuilt.  Replaces the
+ * per-GPU repetition of ReadIndex (reference.cpp:324-351, call site mapping.cpp:492). */
+int walt_engine_clone_index(walt_engine* dst, const walt_engine* src);
+
 /* Chromosome table as read from the header (names are NUL-terminated, owned by the engine). */
 int walt_engine_chromosomes(const walt_engine* e, uint32_t* n_chr, const uint32_t** lengths,
                             const uint32_t** start_index, const char* const** names);
@@ -193,6 +199,30 @@ int walt_engine_set_defer(walt_engine* e, int on);
 /* 1: CUDA events around the verify_kernel launches of the device-resident calls; their sum comes back
  * in walt_stats.verify_ns from walt_engine_device_stats (how bench.py times verification alone). */
 int walt_engine_set_kernel_timing(walt_engine* e, int on);
+
+/* ---- several GPUs behind one handle --------------------------------------------------------
+ * A group owns one engine per listed device (reads shard naturally, every GPU
+ * holds a full index replica, there is no collective on the hot path).  walt_group_load_dbindex reads
+ * the files ONCE (into the first device) and replicates with walt_engine_clone_index.  The map calls
+ * cut the batch into n_devices contiguous ranges, one host thread drives each engine, and every range
+ * lands in its slice of the caller's result array: results are in input order whatever the split.
+ * Arguments as in the walt_engine_map_* calls of the same name. */
+typedef struct walt_group walt_group;
+int walt_group_create(walt_group** out, const int* device_ids, int n_devices);
+void walt_group_destroy(walt_group* g);
+int walt_group_size(const walt_group* g);
+walt_engine* walt_group_engine(walt_group* g, int i);     /* for the per-engine setters and queries */
+int walt_group_load_dbindex(walt_group* g, const char* dbindex_path, uint32_t which_mask);
+int walt_group_map_se(walt_group* g, const char* seqs, const uint64_t* offs, uint32_t n, int ag_wildcard,
+                      uint32_t max_mismatches, uint32_t b, walt_best* out, uint32_t* n_short);
+int walt_group_map_se_packed(walt_group* g, const uint8_t* packed, const uint64_t* offs, uint32_t n, int ag_wildcard,
+                             uint32_t max_mismatches, uint32_t b, walt_best* out, uint32_t* n_short);
+int walt_group_map_pe_compact(walt_group* g, const char* seqs1, const uint64_t* offs1, const char* seqs2,
+                              const uint64_t* offs2, uint32_t n, uint32_t max_mismatches, uint32_t b, uint32_t top_k,
+                              int frag_range, int pbat, walt_pe_result* out, uint32_t* n_short1, uint32_t* n_short2);
+int walt_group_map_pe_compact_packed(walt_group* g, const uint8_t* packed1, const uint64_t* offs1, const uint8_t* packed2,
+                                     const uint64_t* offs2, uint32_t n, uint32_t max_mismatches, uint32_t b, uint32_t top_k,
+                                     int frag_range, int pbat, walt_pe_result* out, uint32_t* n_short1, uint32_t* n_short2);
 
 /* ---- pinned host memory for batch buffers --------------------------------------------- */
 void* walt_host_alloc(size_t bytes);

@@ -30,8 +30,9 @@ def dbindex(tmp_path_factory):
     return p
 
 
-def _run(args, cwd=None):
-    return subprocess.run([WALT] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+def _run(args, cwd=None, env=None):
+    return subprocess.run([WALT] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600,
+                          env=dict(os.environ, **env) if env else None)
 
 
 def _compare(got_dir, want_dir, files):
@@ -58,12 +59,38 @@ def test_walt_cli_matches_reference(case, dbindex, tmp_path):
 def test_walt_cli_sharded_over_engines(dbindex, tmp_path, name):
     """-gpus 3: every batch is cut into three contiguous ranges, each mapped by its own engine
     (walt_main.cpp: packed + lo, offs + lo) and written back into its slice of the batch's result
-    array.  With fewer devices than shards the engines share devices, so the split is exercised on
-    a one-GPU box as well; the bytes must not depend on it."""
+    array.  The program clamps -gpus to the visible devices; WALT_SHARE_DEVICES=1 (a test hook for small
+    indexes) lets the shards share devices instead, so the split is exercised on a one-GPU box as well;
+    the bytes must not depend on it."""
     case = next(c for c in CASES if c["name"] == name)
     args = [a if not a.endswith(".fastq") else os.path.join(CLI, a) for a in case["args"]]
-    r = _run(["-i", dbindex, "-o", str(tmp_path / "out"), "-gpus", "3"] + args)
+    r = _run(["-i", dbindex, "-o", str(tmp_path / "out"), "-gpus", "3"] + args, env={"WALT_SHARE_DEVICES": "1"})
     assert r.returncode == 0, r.stderr.decode()[-2000:]
+    _compare(str(tmp_path), os.path.join(CLI, case["name"]), case["files"])
+
+
+def test_walt_cli_gpus_clamped_to_devices(dbindex, tmp_path):
+    """-gpus beyond the visible devices is clamped (no second index replica on one device), same bytes"""
+    case = next(c for c in CASES if c["name"] == "se_sam")
+    args = [a if not a.endswith(".fastq") else os.path.join(CLI, a) for a in case["args"]]
+    r = _run(["-i", dbindex, "-o", str(tmp_path / "out"), "-gpus", "64"] + args)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    assert b"device(s) visible, using" in r.stderr
+    _compare(str(tmp_path), os.path.join(CLI, case["name"]), case["files"])
+
+
+@pytest.mark.parametrize("name", ["se_sam", "pe_sam", "pe_clip_k3"])
+def test_walt_cli_two_physical_gpus(dbindex, tmp_path, name):
+    """-gpus 2 on two physical devices (skipped on a one-GPU box): the second engine gets its index over
+    NVLink from the first (walt_engine_clone_index), the bytes are the reference's."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible devices")
+    case = next(c for c in CASES if c["name"] == name)
+    args = [a if not a.endswith(".fastq") else os.path.join(CLI, a) for a in case["args"]]
+    r = _run(["-i", dbindex, "-o", str(tmp_path / "out"), "-gpus", "2"] + args, env={"WALT_TIMING": "1"})
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    assert b"cloned over" in r.stderr
     _compare(str(tmp_path), os.path.join(CLI, case["name"]), case["files"])
 
 

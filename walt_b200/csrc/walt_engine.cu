@@ -242,6 +242,7 @@ int finalize_subindex(walt_engine* e, int which) {
     for (uint32_t i = 0; i < s.n_taint; ++i) flat.push_back(std::get<1>(t[i]));
     for (uint32_t i = 0; i < s.n_taint; ++i) flat.push_back(std::get<2>(t[i]));
     flat.insert(flat.end(), (size_t)s.n_taint + 1u, 0xFFFFFFFFu);   // slots: filled by table_keys_kernel
+    s.taint_words = flat.size();
     WALT_CUDA_TRY(cudaMalloc(&s.taint_bits, flat.size() * 4u));
     WALT_CUDA_TRY(cudaMemcpy(s.taint_bits, flat.data(), flat.size() * 4u, cudaMemcpyHostToDevice));
     s.bytes += flat.size() * 4u;
@@ -557,8 +558,10 @@ static size_t verify_smem_bytes(uint32_t nw_max) {
   return (size_t)WARPS_PER_BLOCK * (scratch_words(nw_max) * 8u + VERIFY_WARP_WORDS * 4u);
 }
 
+template <int CA>
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gmem));
+  if (CA) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gmem));
+  else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -569,7 +572,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // one lane per candidate from that tile (alignment selects, funnel shifts and mask loads once per candidate
 // instead of once per 16 bases).  Two tiles per warp: the windows of block i + 1 are on their way while block i
 // is compared, the entries of block i + 2 while those are issued.
-template <bool PACKED, class Args>
+template <bool PACKED, class Args, int CA = 1>
 __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS_PER_SM)
 verify_kernel(const __grid_constant__ Args a) {
   extern __shared__ uint64_t smem[];
@@ -593,7 +596,7 @@ verify_kernel(const __grid_constant__ Args a) {
     base = __shfl_sync(0xFFFFFFFFu, base, 0);
     if (base >= n_blocks) break;
     // lane i describes block base + i: record, lookup, first slot, end of the run (dead: nothing to do)
-    uint32_t d_t = 0xFFFFFFFFu, d_j = 0u, d_r = 0u, d_first = 0u, d_end = 0u;
+    uint32_t d_t = 0xFFFFFFFFu, d_j = 0u, d_r = 0u, d_first = 0u, d_end = 0u, d_len = 0u;
     if (lane < VERIFY_TICKET && base + lane < n_blocks) {
       d_t = a.park.desc[2u * (size_t)(base + lane)];
       if (d_t != 0xFFFFFFFFu) {                           // else: reserved by a read that found no room
@@ -601,6 +604,7 @@ verify_kernel(const __grid_constant__ Args a) {
         const uint32_t* rec = a.park.recs + (size_t)d_t * PARK_WORDS;
         const uint32_t* mine = rec + 2u + PARK_LOOKUP_WORDS * (word & 7u);
         d_j = word & 7u; d_r = rec[0]; d_first = mine[1] + 32u * (word >> 3); d_end = mine[1] + mine[2];
+        read_at<PACKED>(a, d_r, d_len);
       }
     }
     // this lane's entry of block i (0 for the slots past the end of a run and for dead blocks)
@@ -613,13 +617,16 @@ verify_kernel(const __grid_constant__ Args a) {
     // the windows of block i, straight into tile i & 1: step u fetches the 64-byte block of slot 4c + u, 16 bytes per lane
     auto fetch = [&](uint32_t i, uint32_t e) {
       if (i < VERIFY_TICKET) {
-        const uint32_t j = __shfl_sync(0xFFFFFFFFu, d_j, (int)i);
+        const uint32_t j = __shfl_sync(0xFFFFFFFFu, d_j, (int)i), rl = __shfl_sync(0xFFFFFFFFu, d_len, (int)i);
         const uint64_t* genome = a.ix[j / 3u].genome;
         const uint32_t sa = tiles_sa + ((i & 1u) * 32u * VERIFY_ROW + 4u * q) * 4u;
 #pragma unroll
         for (uint32_t u = 0; u < 4u; ++u) {
           const uint64_t gp = (uint64_t)__shfl_sync(0xFFFFFFFFu, e, (int)(c4 + u)) + PAD_BASES - j % 3u;
-          cp_async16(sa + (c4 + u) * VERIFY_ROW * 4u, reinterpret_cast<const uint4*>(genome) + ((gp >> 6) + q));
+          // the fourth 16 bytes only if the window reaches them: every other block starts in the middle of a
+          // 32-byte sector, and its last quarter is a third sector
+          if (q < 3u || ((uint32_t)gp & 63u) + rl > 192u)
+            cp_async16<CA>(sa + (c4 + u) * VERIFY_ROW * 4u, reinterpret_cast<const uint4*>(genome) + ((gp >> 6) + q));
         }
       }
       cp_async_commit();
@@ -1194,7 +1201,8 @@ static int launch_se(walt_engine* e, const ReadSrc& src, uint32_t n, int ag, uin
   WALT_CUDA_TRY(cudaGetLastError());
   e->stats.n_kernel_launches++;
   if (park)
-    return launch_behind_park(e, a, src.packed ? verify_kernel<true, SeArgs> : verify_kernel<false, SeArgs>,
+    return launch_behind_park(e, a, e->verify_cg ? (src.packed ? verify_kernel<true, SeArgs, 0> : verify_kernel<false, SeArgs, 0>)
+                                                 : (src.packed ? verify_kernel<true, SeArgs, 1> : verify_kernel<false, SeArgs, 1>),
                               src.packed ? se_fold_kernel<true> : se_fold_kernel<false>,
                               src.packed ? se_map_kernel<32, true, MAP_TAKE> : se_map_kernel<32, false, MAP_TAKE>,
                               verify_smem_bytes(a.nw_max), 0, se_smem_bytes(a.nw_max, 32u), st);
@@ -1229,7 +1237,8 @@ static int launch_pe_log(walt_engine* e, const ReadSrc& src, uint32_t n, int ag,
   WALT_CUDA_TRY(cudaGetLastError());
   e->stats.n_kernel_launches++;
   if (park)
-    return launch_behind_park(e, a, src.packed ? verify_kernel<true, PeArgs> : verify_kernel<false, PeArgs>,
+    return launch_behind_park(e, a, e->verify_cg ? (src.packed ? verify_kernel<true, PeArgs, 0> : verify_kernel<false, PeArgs, 0>)
+                                                 : (src.packed ? verify_kernel<true, PeArgs, 1> : verify_kernel<false, PeArgs, 1>),
                               src.packed ? pe_fold_kernel<true> : pe_fold_kernel<false>,
                               src.packed ? pe_log_kernel<32, true, MAP_TAKE> : pe_log_kernel<32, false, MAP_TAKE>,
                               verify_smem_bytes(a.nw_max), 0, pe_log_smem_bytes(a.nw_max, 32u), st);
@@ -1378,6 +1387,7 @@ int walt_engine_create(walt_engine** out, int device) {
   if (const char* v = getenv("WALT_PE_LOGGED")) e->pe_logged = atoi(v);
   if (const char* v = getenv("WALT_DEFER")) e->defer = atoi(v);
   if (const char* v = getenv("WALT_FLAT")) e->flat_verify = atoi(v);
+  if (const char* v = getenv("WALT_VERIFY_CG")) e->verify_cg = atoi(v);
   if (const char* v = getenv("WALT_PAIR_WIDE")) e->pair_wide = atoi(v);
   if (const char* v = getenv("WALT_HEAP_SMEM")) e->heap_smem = atoi(v);
   if (const char* v = getenv("WALT_CHUNK_SHARE")) e->chunk_share = (uint32_t)std::max(1, atoi(v));
@@ -1469,14 +1479,15 @@ int walt_engine_load_subindex(walt_engine* e, int which, const char* sequence, c
   if ((rc = alloc_packed_genome(e, s))) return rc;
   uint8_t* d_stage = nullptr;
   WALT_CUDA_TRY(cudaMalloc(&d_stage, STAGE_BYTES));
-  WALT_CUDA_TRY(cudaMemset(e->d_flags + 3, 0, 4));
+  if (cudaMemset(e->d_flags + 3, 0, 4) != cudaSuccess) { cudaFree(d_stage); return fail(WALT_ECUDA, "cudaMemset"); }
   for (uint64_t off = 0; off < e->genome_len; off += STAGE_BYTES) {
     const uint64_t n = std::min<uint64_t>(STAGE_BYTES, e->genome_len - off);
     if ((rc = upload_genome_chunk(e, s, which, sequence + off, off, n, d_stage))) { cudaFree(d_stage); return rc; }
   }
   uint32_t bad = 0;
-  WALT_CUDA_TRY(cudaMemcpy(&bad, e->d_flags + 3, 4, cudaMemcpyDeviceToHost));
+  const cudaError_t ce = cudaMemcpy(&bad, e->d_flags + 3, 4, cudaMemcpyDeviceToHost);
   cudaFree(d_stage);
+  if (ce != cudaSuccess) return fail(WALT_ECUDA, std::string("genome check: ") + cudaGetErrorString(ce));
   if (bad) return fail(WALT_EFORMAT, std::to_string(bad) + " genome bytes outside the sub-index's 3-letter alphabet");
   s.index_size = index_size;
   WALT_CUDA_TRY(cudaMalloc(&s.index, ((size_t)index_size + 64u) * 4u));
@@ -1586,8 +1597,10 @@ int walt_engine_load_dbindex(walt_engine* e, const char* path, uint32_t which_ma
     if (!rc && ln) rc = read_exact(f, &nm[0], ln, "chromosome name");
     names.push_back(nm);
   }
-  lengths.resize(n_chr);
-  if (!rc) rc = read_exact(f, lengths.data(), 4u * n_chr, "chromosome lengths");
+  if (!rc) {
+    lengths.resize(n_chr);
+    rc = read_exact(f, lengths.data(), 4u * n_chr, "chromosome lengths");
+  }
   if (!rc) rc = read_exact(f, &genome_len, 4, "genome length");
   if (!rc) rc = read_exact(f, &size_of_index, 4, "index size");
   fclose(f);
@@ -1660,6 +1673,48 @@ int walt_engine_load_dbindex(walt_engine* e, const char* path, uint32_t which_ma
   }
   cudaFree(d_stage);
   return rc;
+}
+
+int walt_engine_clone_index(walt_engine* dst, const walt_engine* src) {
+  if (!dst || !src || dst == src) return fail(WALT_EINVAL, "bad argument");
+  if (!src->d_starts) return fail(WALT_ENOTLOADED, "the source engine holds no index");
+  int rc;
+  std::vector<const char*> names;
+  for (auto& n : src->names) names.push_back(n.c_str());
+  if ((rc = walt_engine_set_chromosomes(dst, src->n_chr, src->lengths.data(), names.data()))) return rc;   // also releases dst's sub-indexes
+  if (dst->device != src->device) {
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, dst->device, src->device);
+    if (can) {
+      const cudaError_t ce = cudaDeviceEnablePeerAccess(src->device, 0);
+      if (ce != cudaSuccess && ce != cudaErrorPeerAccessAlreadyEnabled) return fail(WALT_ECUDA, std::string("peer access: ") + cudaGetErrorString(ce));
+      cudaGetLastError();
+    }
+  }
+  auto pull = [&](void** d, const void* s, size_t bytes) -> int {
+    *d = nullptr;
+    if (!bytes || !s) return WALT_OK;
+    WALT_CUDA_TRY(cudaMalloc(d, bytes));
+    WALT_CUDA_TRY(cudaMemcpyPeer(*d, dst->device, s, src->device, bytes));
+    return WALT_OK;
+  };
+  for (int which = 0; which < 4; ++which) {
+    const DeviceSubIndex& a = src->sub[which];
+    if (!a.loaded) continue;
+    DeviceSubIndex& d = dst->sub[which];
+    d.genome_words = a.genome_words; d.index_size = a.index_size; d.depth = a.depth; d.n_taint = a.n_taint;
+    d.n_taint_keys = a.n_taint_keys; d.taint_words = a.taint_words; d.bytes = a.bytes;
+    if ((rc = pull((void**)&d.genome, a.genome, a.genome_words * 8u)) ||
+        (rc = pull((void**)&d.entries, a.entries, ((size_t)a.index_size + 64u) * sizeof(Entry))) ||
+        (rc = pull((void**)&d.table, a.table, ((size_t)dst->pow3.v[a.depth] + 1u) * 4u)) ||
+        (rc = pull((void**)&d.taint_bits, a.taint_bits, a.taint_words * 4u))) {
+      d.release();
+      return rc;
+    }
+    d.loaded = true;
+  }
+  WALT_CUDA_TRY(cudaDeviceSynchronize());
+  return WALT_OK;
 }
 
 int walt_engine_chromosomes(const walt_engine* e, uint32_t* n_chr, const uint32_t** lengths,
@@ -1780,8 +1835,24 @@ static void chunk_bytes(const uint64_t* offs, uint32_t r0, uint32_t cn, bool pac
   else { *b0 = offs[r0]; *b1 = offs[r0 + cn]; }
 }
 
+// Every copy and kernel the host-batch loops have queued is waited for before an error goes back to the
+// caller: the chunks in flight still read the caller's input and write its output buffers.
+static void drain_slots(walt_engine* e) {
+  for (auto& s : e->slot) cudaStreamSynchronize(s.stream);
+  cudaStreamSynchronize(e->side_stream);
+}
+
+static int map_se_host_loop(walt_engine* e, const char* seqs, const uint64_t* offs, uint32_t n, bool packed, int ag_wildcard,
+                            uint32_t max_mismatches, uint32_t b, walt_best* out, uint32_t* n_short);
 static int map_se_host(walt_engine* e, const char* seqs, const uint64_t* offs, uint32_t n, bool packed, int ag_wildcard,
                        uint32_t max_mismatches, uint32_t b, walt_best* out, uint32_t* n_short) {
+  const int rc = map_se_host_loop(e, seqs, offs, n, packed, ag_wildcard, max_mismatches, b, out, n_short);
+  if (rc && e) { const std::string msg = g_error; drain_slots(e); g_error = msg; }
+  return rc;
+}
+
+static int map_se_host_loop(walt_engine* e, const char* seqs, const uint64_t* offs, uint32_t n, bool packed, int ag_wildcard,
+                            uint32_t max_mismatches, uint32_t b, walt_best* out, uint32_t* n_short) {
   if (!e || !offs || (n && (!seqs || !out))) return fail(WALT_EINVAL, "bad argument");
   int rc = ensure_device(e);
   if (rc) return rc;
@@ -1953,10 +2024,24 @@ static int launch_pe_chunk(walt_engine* e, const ReadSrc& m1, const ReadSrc& m2,
 // Host batch, chunked and pipelined.  Either the full ranked lists (ranked1 != NULL) or the
 // compact per-pair summary (compact != NULL) travel back.  Under PBAT the caller has already
 // exchanged the mates; `swap` makes the pairing kernel hand the per-mate fields back.
+static int map_pe_host_loop(walt_engine* e, const char* seqs1, const uint64_t* offs1, const char* seqs2, const uint64_t* offs2,
+                            uint32_t n, bool packed, uint32_t m, uint32_t b, uint32_t top_k, int frag_range, int swap,
+                            walt_cand* ranked1, uint32_t* n_ranked1, walt_cand* ranked2, uint32_t* n_ranked2, walt_pair* pairs,
+                            walt_pe_result* compact, uint32_t* n_short1, uint32_t* n_short2);
 static int map_pe_host(walt_engine* e, const char* seqs1, const uint64_t* offs1, const char* seqs2, const uint64_t* offs2,
                        uint32_t n, bool packed, uint32_t m, uint32_t b, uint32_t top_k, int frag_range, int swap,
                        walt_cand* ranked1, uint32_t* n_ranked1, walt_cand* ranked2, uint32_t* n_ranked2, walt_pair* pairs,
                        walt_pe_result* compact, uint32_t* n_short1, uint32_t* n_short2) {
+  const int rc = map_pe_host_loop(e, seqs1, offs1, seqs2, offs2, n, packed, m, b, top_k, frag_range, swap, ranked1, n_ranked1,
+                                  ranked2, n_ranked2, pairs, compact, n_short1, n_short2);
+  if (rc) { const std::string msg = g_error; drain_slots(e); g_error = msg; }   // see map_se_host
+  return rc;
+}
+
+static int map_pe_host_loop(walt_engine* e, const char* seqs1, const uint64_t* offs1, const char* seqs2, const uint64_t* offs2,
+                            uint32_t n, bool packed, uint32_t m, uint32_t b, uint32_t top_k, int frag_range, int swap,
+                            walt_cand* ranked1, uint32_t* n_ranked1, walt_cand* ranked2, uint32_t* n_ranked2, walt_pair* pairs,
+                            walt_pe_result* compact, uint32_t* n_short1, uint32_t* n_short2) {
   int rc;
   e->stats = walt_stats{};
   WALT_CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, N_COUNTERS * 8, e->slot[0].stream));

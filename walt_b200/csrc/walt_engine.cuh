@@ -36,6 +36,7 @@ struct DeviceSubIndex {
   uint32_t* taint_bits = nullptr; // one allocation: filter bits | rank | start | pos | len
   uint32_t n_taint = 0;           // tainted positions
   uint32_t n_taint_keys = 0;      // distinct 12-mer keys among them
+  size_t taint_words = 0;         // words of the taint allocation
   uint64_t bytes = 0;
   waltcore::SubIndexView view(int which) const;
   void release();
@@ -106,6 +107,7 @@ struct walt_engine {
   int heap_smem = 1;                         // 1: pe_heap_kernel keeps its heaps in shared memory when they fit
   uint32_t* d_flags = nullptr;               // [0] non-ACGT flag, [2..3] index-build scratch, from [16] the queue
                                              // blocks of the launches in flight (queue_block, walt_engine.cu)
+  int verify_cg = 1;                         // verify_kernel's window copies bypass the L1 (cp.async.cg; measured faster than .ca)
   int time_kernels = 0;                      // 1: CUDA events around every verify_kernel launch (walt_stats.verify_ns)
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> verify_events;
   unsigned long long* d_counters = nullptr;  // lookups, candidates, literal, parked, verified slots

@@ -569,8 +569,10 @@ walt_chroms* walt_chroms_read(const char* path) {
     if (ok && ln) ok = fread(&nm[0], 1, ln, f) == ln;
     c->names.push_back(nm);
   }
-  c->lengths.resize(n);
-  if (ok) ok = fread(c->lengths.data(), 4, n, f) == n;
+  if (ok) {
+    c->lengths.resize(n);
+    ok = fread(c->lengths.data(), 4, n, f) == n;
+  }
   uint32_t glen = 0;
   if (ok) ok = fread(&glen, 4, 1, f) == 1;
   if (ok) ok = fread(&c->size_of_index, 4, 1, f) == 1;

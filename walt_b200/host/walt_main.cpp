@@ -120,13 +120,12 @@ void engine_check(int rc) {
   if (rc != WALT_OK) throw std::runtime_error(std::string("walt engine: ") + walt_last_error());
 }
 
+// the GPUs of a run: one engine per device behind one handle (walt_group, include/walt_b200.h), which cuts
+// every batch into contiguous ranges and keeps the results in input order
 struct Engines {
-  std::vector<walt_engine*> e;
-  ~Engines() { for (auto* p : e) walt_engine_destroy(p); }
+  walt_group* g = nullptr;
+  ~Engines() { walt_group_destroy(g); }
 };
-
-// contiguous split of [0, n) over g workers
-inline uint32_t cut(uint32_t n, uint32_t g, uint32_t i) { return (uint32_t)((uint64_t)n * i / g); }
 
 // stage timings on stderr when WALT_TIMING is set (never part of the outputs)
 struct StageClock {
@@ -157,29 +156,10 @@ Loaded load_batch(walt_fastq* fq, walt_batch* b, uint32_t max_reads, const std::
 
 void map_se_batch(Engines& eng, const walt_batch* b, const uint8_t* packed, const Settings& s, bool ag,
                   std::vector<walt_best>& res, uint32_t& n_short) {
-  const uint32_t n = walt_batch_size(b), g = (uint32_t)eng.e.size();
+  const uint32_t n = walt_batch_size(b);
   res.resize(n);
-  const uint64_t* offs = walt_batch_offsets(b);
-  std::vector<int> rc(g, 0);
-  std::vector<uint32_t> sh(g, 0);
-  std::vector<std::string> err(g);
-  std::vector<std::thread> th;
-  for (uint32_t i = 0; i < g; ++i) {
-    th.emplace_back([&, i]() {
-      const uint32_t lo = cut(n, g, i), hi = cut(n, g, i + 1);
-      if (hi == lo) return;
-      // read j of the batch lives at byte (offs[j] >> 2) + j of `packed`: a shard that starts at
-      // read lo passes the buffer shifted by lo so that its own j = 0 lands on the same byte
-      rc[i] = walt_engine_map_se_packed(eng.e[i], packed + lo, offs + lo, hi - lo, ag ? 1 : 0, s.m, s.b, res.data() + lo, &sh[i]);
-      if (rc[i]) err[i] = walt_last_error();
-    });
-  }
-  for (auto& t : th) t.join();
   n_short = 0;
-  for (uint32_t i = 0; i < g; ++i) {
-    if (rc[i]) throw std::runtime_error("walt engine: " + err[i]);
-    n_short += sh[i];
-  }
+  engine_check(walt_group_map_se_packed(eng.g, packed, walt_batch_offsets(b), n, ag ? 1 : 0, s.m, s.b, res.data(), &n_short));
 }
 
 void process_single_end(Engines& eng, const walt_chroms* chroms, const Settings& s, const std::string& reads,
@@ -268,10 +248,10 @@ void process_paired_end(Engines& eng, const walt_chroms* chroms, const Settings&
     clk.load += std::max(c1.seconds, c2.seconds);
     for (;;) {
       if (c1.n < 0) throw std::runtime_error(c1.err);
+      if (c1.n == 0) break;   // paired.cpp:650-651: the second file is not even read when the first one is exhausted
       if (c2.n < 0) throw std::runtime_error(c2.err);
       if (c1.n != c2.n) { unequal = true; break; }
-      if (c1.n == 0) break;
-      const uint32_t n = (uint32_t)c1.n, g = (uint32_t)eng.e.size();
+      const uint32_t n = (uint32_t)c1.n;
       const bool last = n < s.batch;
       if (!last) {
         next1 = std::async(std::launch::async, load_batch, f1, b1[1 - k], s.batch, ad1);
@@ -279,26 +259,10 @@ void process_paired_end(Engines& eng, const walt_chroms* chroms, const Settings&
       }
       auto t = std::chrono::steady_clock::now();
       res.resize(n);
-      std::vector<int> rc(g, 0);
-      std::vector<uint32_t> s1(g, 0), s2(g, 0);
-      std::vector<std::string> err(g);
-      std::vector<std::thread> th;
-      const uint64_t* o1 = walt_batch_offsets(b1[k]);
-      const uint64_t* o2 = walt_batch_offsets(b2[k]);
-      for (uint32_t i = 0; i < g; ++i) {
-        th.emplace_back([&, i]() {
-          const uint32_t lo = cut(n, g, i), hi = cut(n, g, i + 1);
-          if (hi == lo) return;
-          rc[i] = walt_engine_map_pe_compact_packed(eng.e[i], c1.packed + lo, o1 + lo, c2.packed + lo, o2 + lo, hi - lo, s.m,
-                                                    s.b, s.top_k, s.frag, s.pbat ? 1 : 0, res.data() + lo, &s1[i], &s2[i]);
-          if (rc[i]) err[i] = walt_last_error();
-        });
-      }
-      for (auto& t2 : th) t2.join();
-      for (uint32_t i = 0; i < g; ++i) {
-        if (rc[i]) throw std::runtime_error("walt engine: " + err[i]);
-        walt_pe_writer_add_short(w, s1[i], s2[i]);
-      }
+      uint32_t short1 = 0, short2 = 0;
+      engine_check(walt_group_map_pe_compact_packed(eng.g, c1.packed, walt_batch_offsets(b1[k]), c2.packed, walt_batch_offsets(b2[k]),
+                                                    n, s.m, s.b, s.top_k, s.frag, s.pbat ? 1 : 0, res.data(), &short1, &short2));
+      walt_pe_writer_add_short(w, short1, short2);
       clk.map += StageClock::since(t);
       t = std::chrono::steady_clock::now();
       if (walt_pe_writer_write_compact(w, b1[k], b2[k], res.data(), n))
@@ -400,23 +364,20 @@ int main(int argc, const char** argv) {
     Engines eng;
     const auto t_index = std::chrono::steady_clock::now();
     if (mask) {
-      eng.e.resize(s.gpus, nullptr);
-      // one engine (one index replica) per shard; with more shards than devices they share devices
+      // one engine (one index replica) per shard.  More shards than devices would put several replicas of
+      // the index on one device: the shard count is clamped (WALT_SHARE_DEVICES=1 keeps it, for tests on small indexes)
       const int n_dev = walt_device_count();
-      if (n_dev > 0 && s.gpus > (uint32_t)n_dev)
-        std::cerr << "[-gpus " << s.gpus << " on " << n_dev << " visible device(s): shards share devices]" << std::endl;
-      for (uint32_t i = 0; i < s.gpus; ++i)
-        engine_check(walt_engine_create(&eng.e[i], n_dev > 0 ? (int)(i % (uint32_t)n_dev) : (int)i));
-      std::vector<int> rc(s.gpus, 0);
-      std::vector<std::string> err(s.gpus);
-      std::vector<std::thread> th;
-      for (uint32_t i = 0; i < s.gpus; ++i)
-        th.emplace_back([&, i]() {
-          rc[i] = walt_engine_load_dbindex(eng.e[i], s.index.c_str(), mask);
-          if (rc[i]) err[i] = walt_last_error();
-        });
-      for (auto& t : th) t.join();
-      for (uint32_t i = 0; i < s.gpus; ++i) if (rc[i]) throw std::runtime_error("walt engine: " + err[i]);
+      if (n_dev > 0 && s.gpus > (uint32_t)n_dev && !getenv("WALT_SHARE_DEVICES")) {
+        std::cerr << "[-gpus " << s.gpus << ": only " << n_dev << " device(s) visible, using " << n_dev << "]" << std::endl;
+        s.gpus = (uint32_t)n_dev;
+      }
+      std::vector<int> devs(s.gpus);
+      for (uint32_t i = 0; i < s.gpus; ++i) devs[i] = n_dev > 0 ? (int)(i % (uint32_t)n_dev) : (int)i;
+      engine_check(walt_group_create(&eng.g, devs.data(), (int)s.gpus));
+      // the files are read once; the other devices get their replicas device to device (NVLink / NVSwitch)
+      engine_check(walt_group_load_dbindex(eng.g, s.index.c_str(), mask));
+      if (getenv("WALT_TIMING") && s.gpus > 1)
+        fprintf(stderr, "[walt timing] index read once, cloned over NVLink to %u more device%s\n", s.gpus - 1, s.gpus > 2 ? "s" : "");
       if (getenv("WALT_TIMING"))
         fprintf(stderr, "[walt timing] engine start + index residency (%u GPU%s): %.3f s\n", s.gpus, s.gpus > 1 ? "s" : "",
                 StageClock::since(t_index));
