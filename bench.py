@@ -198,6 +198,24 @@ def algorithmic_bytes(ctr, n_reads, rl, pe=False):
             "total": (seed + verify + io) / n_reads}
 
 
+HOST_INDEX_CACHE = {}
+
+
+def free_host_indexes(hidx=None):
+    """free exported reference indexes: the given ones unless they are cached, or (None) the whole cache"""
+    import refio
+    L = refio.ref_lib()
+    if hidx is None:
+        for h in HOST_INDEX_CACHE.values():
+            L.waltref_index_free(h)
+        HOST_INDEX_CACHE.clear()
+        return
+    cached = {int(h.value) for h in HOST_INDEX_CACHE.values()}
+    for h in hidx.values():
+        if int(h.value) not in cached:
+            L.waltref_index_free(h)
+
+
 class Workload:
     """Per-rank synthetic genome, resident index and read batch."""
 
@@ -276,12 +294,19 @@ class Workload:
         self.torch.cuda.empty_cache()
 
     def host_index(self):
-        """Export the resident sub-indexes into reference-owned Genome/HashTable objects."""
+        """Export the resident sub-indexes into reference-owned Genome/HashTable objects.  The uniform
+        genome of configs[1..3] is the same (same seed, same size, deterministic builder), so its exports
+        are kept for the next configuration (HOST_INDEX_CACHE; freed by free_host_indexes)."""
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import refio
         L = refio.ref_lib()
         out = {}
+        shared = self.kind in ("se", "se_ag", "pe")
         for which in self.which:
+            key = (self.genome_mb, which)
+            if shared and key in HOST_INDEX_CACHE:
+                out[which] = HOST_INDEX_CACHE[key]
+                continue
             info = self.e.subindex_info(which)
             h = C.c_void_p(L.waltref_index_alloc(C.c_uint32(len(self.lengths)),
                                                  self.lengths.ctypes.data_as(C.c_void_p),
@@ -292,6 +317,8 @@ class Workload:
                 self.e.h, C.c_int(which), C.c_void_p(L.waltref_index_sequence(h)),
                 C.c_void_p(L.waltref_index_counter(h)), C.c_void_p(L.waltref_index_index(h)), C.byref(got)))
             out[which] = h
+            if shared:
+                HOST_INDEX_CACHE[(self.genome_mb, which)] = h
         return out
 
     def sample_reads(self, n, mate=1):
@@ -508,6 +535,8 @@ def cli_leg(device, genome_mb, n_reads, rl, workdir=None, keep=False, small=Fals
         out["index_bytes"] = sum(os.path.getsize(idx + s) for s in ("", "_CT00", "_CT01", "_GA10", "_GA11"))
         cores = os.cpu_count() or 1
         opts = ["-i", idx, "-r", fq, "-sam", "-u", "-a", "-m", str(M), "-b", str(B)]
+        n_gpus = int(os.environ.get("WALT_CLI_GPUS", "1"))      # walt -gpus N: index read once, cloned device to device
+        out["gpus"] = n_gpus
 
         def timed(cmd, env=None):
             t = time.perf_counter()
@@ -525,11 +554,13 @@ def cli_leg(device, genome_mb, n_reads, rl, workdir=None, keep=False, small=Fals
             return h.hexdigest(), os.path.getsize(path)
 
         ours_bin = os.path.join(ROOT, "walt_b200", "bin", "walt")
-        env = dict(os.environ, WALT_TIMING="1", CUDA_VISIBLE_DEVICES=str(device))
+        env = dict(os.environ, WALT_TIMING="1")
+        if n_gpus == 1:
+            env["CUDA_VISIBLE_DEVICES"] = str(device)
         o_out = os.path.join(work, "ours.sam")
         runs = []
         for _ in range(2):   # the second run has every input in the page cache (as has the reference's)
-            dt, err = timed([ours_bin] + opts + ["-o", o_out], env)
+            dt, err = timed([ours_bin] + opts + ["-o", o_out] + (["-gpus", str(n_gpus)] if n_gpus > 1 else []), env)
             runs.append(dt)
             stages = [l for l in err.splitlines() if l.startswith("[walt timing]")]
         out["ours_s"] = min(runs)
@@ -766,9 +797,7 @@ def side_legs(wl, unit, ref_seconds, want_baseline):
                           f"OpenMP loops of the unmodified reference (oracle/_ref/libwaltref.so), {t_ref:.1f} s"}
         out["cpu_baseline"] = base if want_baseline else {"value": base["value"], "cores": threads}
     finally:
-        L = refio.ref_lib()
-        for h in hidx.values():
-            L.waltref_index_free(h)
+        free_host_indexes(hidx)
     return out
 
 
@@ -852,9 +881,7 @@ def verify_leg(args, local, stream, barrier, steps=None, warmup=None):
             out["parity_check"] = {"sample_reads": ns, "candidates_per_read_oracle": ctr["n_cand"] / ns,
                                    "fields_differing_vs_oracle": sum(int((got[f] != obest[f]).sum())
                                                                      for f in ("genome_pos", "times", "mismatch", "strand"))}
-            L = refio.ref_lib()
-            for h in hidx.values():
-                L.waltref_index_free(h)
+            free_host_indexes(hidx)
         except Exception as ex:
             out["parity_check"] = {"error": str(ex)[-300:]}
     wl.close()
@@ -865,7 +892,9 @@ def other_configs(args, local, stream, barrier):
     """configs[0], [2], [3], [4] at full size on rank 0's GPU: device-resident timing, roofline,
     parity of the timed path against the reference.  Each builds its own genome and index."""
     out = []
-    for kind in ("se_small", "se_ag", "pe", "pe_stress"):
+    for kind in ("se_ag", "pe", "se_small", "pe_stress"):
+        if kind == "se_small" and HOST_INDEX_CACHE:
+            free_host_indexes()              # the uniform genome's exports are not needed any more
         gmb, nreads, rl = FULL_SIZE[kind]
         scale = float(os.environ.get("WALT_BENCH_SCALE", "1"))   # flow tests only: shrink the other configurations
         if scale != 1.0 and kind != "se_small":
@@ -904,6 +933,8 @@ def other_configs(args, local, stream, barrier):
         except Exception as ex:
             entry["error"] = str(ex)[-400:]
         out.append(entry)
+    free_host_indexes()
+    out.sort(key=lambda c: c["config"])
     return out
 
 

@@ -433,3 +433,42 @@ def test_pe_compact_and_device_paths_match_ranked(engine, pbat):
         torch.cuda.synchronize()
         got = d_out.cpu().numpy().view(PE_RESULT_DT)
         assert np.array_equal(got, comp)
+
+
+def test_group_and_clone_match_single_engine():
+    """walt_group (several engines behind one handle) with replicas made by walt_engine_clone_index: every
+    shard lands in its slice, results equal one engine's.  The engines share device 0 on a one-GPU box and
+    take distinct devices when there are more."""
+    import torch
+    import walt_b200
+    from walt_b200 import host
+    hdr, subs = goldenio.genome()
+    n_dev = max(1, torch.cuda.device_count())
+    devs = [i % n_dev for i in range(3)]
+    g = walt_b200.Group(devs)
+    e0 = g.engines[0]
+    e0.set_chromosomes(hdr.lengths, hdr.names)
+    for w, sfx in enumerate(refio.SUFFIXES):
+        e0.load_subindex(w, subs[sfx].seq, subs[sfx].counter, subs[sfx].index)
+    for e in g.engines[1:]:
+        e.clone_index_from(e0)
+        assert e.hbm_bytes() == e0.hbm_bytes() and e.subindex_info(3) == e0.subindex_info(3)
+    z = goldenio.load("se_ct.npz")
+    buf, offs = refio.pack_reads(z["reads"])
+    out, short = g.map_se(buf, offs, m=6, b=5000)
+    _cmp_best(out, z["best_m6_b5000"], "group ascii")
+    assert short == int(z["short_m6_b5000"])
+    out, _ = g.map_se_packed(host.pack_reads_2bit(buf, offs), offs, m=6, b=5000)
+    _cmp_best(out, z["best_m6_b5000"], "group packed")
+    ze = goldenio.load("se_edge.npz")     # ragged lengths
+    key = [k for k in ze.files if k.startswith("ct_best_")][0]
+    m, b = (int(x[1:]) for x in key[len("ct_best_"):].split("_"))
+    out, _ = g.map_se(ze["buf"], ze["offs"], m=m, b=b)
+    _cmp_best(out, ze[key], "group ragged")
+    zp = goldenio.load("pe.npz")
+    b1, o1 = refio.pack_reads(zp["m1"]); b2, o2 = refio.pack_reads(zp["m2"])
+    want, _, _ = e0.map_pe_compact(b1, o1, b2, o2, m=6, top_k=50, frag_range=1000)
+    got, _, _ = g.map_pe_compact_packed(host.pack_reads_2bit(b1, o1), o1, host.pack_reads_2bit(b2, o2), o2, m=6, top_k=50,
+                                        frag_range=1000)
+    assert np.array_equal(got, want)
+    g.close()

@@ -6,5 +6,5 @@ host program `walt_b200/bin/walt`.  This Python package is a thin ctypes binding
 has no CPU fallback: importing works anywhere, every mapping call needs the CUDA library and
 a device.
 """
-from .engine import (BEST_DT, CAND_DT, PAIR_DT, Engine, WaltError, lib_path, load_library,  # noqa: F401
+from .engine import (BEST_DT, CAND_DT, PAIR_DT, Engine, Group, WaltError, lib_path, load_library,  # noqa: F401
                      pack_reads, CT00, CT01, GA10, GA11)

@@ -1391,6 +1391,8 @@ int walt_engine_create(walt_engine** out, int device) {
   if (const char* v = getenv("WALT_PAIR_WIDE")) e->pair_wide = atoi(v);
   if (const char* v = getenv("WALT_HEAP_SMEM")) e->heap_smem = atoi(v);
   if (const char* v = getenv("WALT_CHUNK_SHARE")) e->chunk_share = (uint32_t)std::max(1, atoi(v));
+  if (const char* v = getenv("WALT_SE_SLOTS")) e->se_slots = (uint32_t)std::min<int>(N_SLOTS, std::max(1, atoi(v)));
+  if (const char* v = getenv("WALT_PE_SLOTS")) e->pe_slots = (uint32_t)std::min<int>(N_SLOTS, std::max(1, atoi(v)));
   if (const char* v = getenv("WALT_L2_FETCH")) WALT_CUDA_TRY(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(v)));
   uint32_t p = 1;
   for (uint32_t i = 0; i <= MAX_DEPTH; ++i) { e->pow3.v[i] = p; p *= 3u; }
@@ -1874,7 +1876,7 @@ static int map_se_host_loop(walt_engine* e, const char* seqs, const uint64_t* of
       return fail(WALT_EINVAL, "read longer than 1024 bases");
     }
     total_short += sc.n_short;
-    BatchSlot& s = e->slot[k % N_SLOTS];
+    BatchSlot& s = e->slot[k % e->se_slots];
     WALT_CUDA_TRY(cudaEventSynchronize(s.done));
     uint64_t sb, se;
     chunk_bytes(offs, r0, cn, packed, &sb, &se);
@@ -1887,7 +1889,7 @@ static int map_se_host_loop(walt_engine* e, const char* seqs, const uint64_t* of
     }
     const ReadSrc src{s.d_seqs, s.d_offs, offs[r0], sc.uniform_len, 0, sc.max_len, packed};
     if (e->defer && (rc = reserve_park(e, &s.park[0], cn))) return rc;
-    if ((rc = launch_se(e, src, cn, ag_wildcard, max_mismatches, b, (walt_best*)s.d_out, queue_block(e, QB_SE_SLOT + k % N_SLOTS),
+    if ((rc = launch_se(e, src, cn, ag_wildcard, max_mismatches, b, (walt_best*)s.d_out, queue_block(e, QB_SE_SLOT + k % e->se_slots),
                         e->defer ? &s.park[0] : nullptr, s.stream, e->chunk_share)))
       return rc;
     WALT_CUDA_TRY(cudaMemcpyAsync(out + r0, s.d_out, (size_t)cn * sizeof(walt_best), cudaMemcpyDeviceToHost, s.stream));
@@ -2063,7 +2065,7 @@ static int map_pe_host_loop(walt_engine* e, const char* seqs1, const uint64_t* o
       return fail(WALT_EINVAL, "read longer than 1024 bases");
     }
     short1 += s1.n_short; short2 += s2.n_short;
-    BatchSlot& s = e->slot[k % N_SLOTS];
+    BatchSlot& s = e->slot[k % e->pe_slots];
     WALT_CUDA_TRY(cudaEventSynchronize(s.done));
     uint64_t sb1, se1, sb2, se2;
     chunk_bytes(offs1, r0, cn, packed, &sb1, &se1);
@@ -2082,7 +2084,7 @@ static int map_pe_host_loop(walt_engine* e, const char* seqs1, const uint64_t* o
       if ((rc = reserve(&s.d_offs2, &s.offs2_cap, (size_t)cn + 1u))) return rc;
       WALT_CUDA_TRY(cudaMemcpyAsync(s.d_offs2, offs2 + r0, ((size_t)cn + 1u) * 8u, cudaMemcpyHostToDevice, s.stream));
     }
-    uint32_t* q = queue_block(e, QB_PE_SLOT + 2u * (k % N_SLOTS));
+    uint32_t* q = queue_block(e, QB_PE_SLOT + 2u * (k % e->pe_slots));
     const ReadSrc m1{s.d_seqs, s.d_offs, offs1[r0], s1.uniform_len, 0, s1.max_len, packed};
     const ReadSrc m2{s.d_seqs2, s.d_offs2, offs2[r0], s2.uniform_len, 0, s2.max_len, packed};
     if (e->defer && two_phase)

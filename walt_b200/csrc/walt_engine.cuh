@@ -42,7 +42,7 @@ struct DeviceSubIndex {
   void release();
 };
 
-constexpr uint32_t N_SLOTS = 3;   // host chunks in flight (copy in / map / copy out)
+constexpr uint32_t N_SLOTS = 8;   // most host chunks in flight (copy in / map / copy out); see walt_engine::se_slots, pe_slots
 constexpr uint32_t REC_CAP_MAX = 1u << 21;     // parked reads of one launch that get a record (the rest: MAP_TAKE)
 constexpr uint32_t BLOCK_CAP_MAX = 1u << 23;   // 32-candidate verification blocks of one launch (256 M candidates)
 
@@ -96,6 +96,9 @@ struct walt_engine {
   waltb200::BatchSlot slot[waltb200::N_SLOTS];
   cudaStream_t side_stream = nullptr;        // second mate kernel of a paired-end chunk
   cudaEvent_t fork = nullptr, join = nullptr;
+  uint32_t se_slots = 6, pe_slots = 3;       // chunks in flight of the single-end / paired-end host batches: the kernels behind
+                                             // a parking kernel wait for SM room, so a chunk's results leave late -- more chunks
+                                             // in flight keep the copy engines busy meanwhile
   uint32_t chunk_share = 1;                  // chunk kernels of a host batch that share the SMs (see grid_for)
   int pe_logged = 1;                         // 1: two-phase paired-end (candidate log + per-thread heap replay)
   int pe_side = 1;                           // 0: both mate kernels on the caller's stream

@@ -53,12 +53,24 @@ int walt_group_create(walt_group** out, const int* device_ids, int n_devices) {
   if (!out || n_devices < 1 || !device_ids) return fail(WALT_EINVAL, "bad argument");
   *out = nullptr;
   walt_group* g = new walt_group;
-  for (int i = 0; i < n_devices; ++i) {
-    walt_engine* e = nullptr;
-    const int rc = walt_engine_create(&e, device_ids[i]);
-    if (rc) { walt_group_destroy(g); return rc; }
-    g->e.push_back(e);
-  }
+  g->e.assign((size_t)n_devices, nullptr);
+  // one thread per device: a CUDA context takes about a second to come up, eight of them in a row eight
+  std::vector<int> rcs((size_t)n_devices, 0);
+  std::vector<std::string> err((size_t)n_devices);
+  std::vector<std::thread> th;
+  for (int i = 0; i < n_devices; ++i)
+    th.emplace_back([&, i]() {
+      rcs[i] = walt_engine_create(&g->e[i], device_ids[i]);
+      if (rcs[i]) err[i] = walt_last_error();
+    });
+  for (auto& t : th) t.join();
+  for (int i = 0; i < n_devices; ++i)
+    if (rcs[i]) {
+      const int rc = rcs[i];
+      const std::string msg = err[i];
+      walt_group_destroy(g);
+      return fail(rc, msg);
+    }
   *out = g;
   return WALT_OK;
 }

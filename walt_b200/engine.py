@@ -133,11 +133,14 @@ class PinnedArray:
 
 
 class Engine:
-    def __init__(self, device=0):
+    def __init__(self, device=0, handle=None):
+        """handle: wrap an engine that somebody else owns (a member of a Group)"""
         self.L = load_library()
-        h = C.c_void_p()
-        self._check(self.L.walt_engine_create(C.byref(h), C.c_int(device)))
-        self.h = h
+        self.owned = handle is None
+        if handle is None:
+            handle = C.c_void_p()
+            self._check(self.L.walt_engine_create(C.byref(handle), C.c_int(device)))
+        self.h = handle
         self.device = device
 
     def _check(self, rc):
@@ -146,8 +149,13 @@ class Engine:
 
     def close(self):
         if getattr(self, "h", None):
-            self.L.walt_engine_destroy(self.h)
+            if self.owned:
+                self.L.walt_engine_destroy(self.h)
             self.h = None
+
+    def clone_index_from(self, src):
+        """walt_engine_clone_index: every resident sub-index of `src`, device to device"""
+        self._check(self.L.walt_engine_clone_index(self.h, src.h))
 
     def __del__(self):
         try:
@@ -358,3 +366,68 @@ class Engine:
                                                      C.c_uint32(max_read_len), C.c_uint32(m), C.c_uint32(b),
                                                      C.c_uint32(top_k), C.c_int(frag_range), C.c_int(int(pbat)),
                                                      C.c_void_p(d_out), C.c_void_p(stream)))
+
+
+class Group:
+    """walt_group: one engine per device behind one handle (include/walt_b200.h, "several GPUs")."""
+
+    def __init__(self, devices):
+        self.L = load_library()
+        self.L.walt_group_engine.restype = C.c_void_p
+        ids = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self.L.walt_group_create(C.byref(h), ids, C.c_int(len(devices)))
+        if rc:
+            raise WaltError(rc, self.L.walt_last_error().decode())
+        self.h = h
+        self.devices = list(devices)
+        self.engines = [Engine(d, handle=C.c_void_p(self.L.walt_group_engine(self.h, C.c_int(i)))) for i, d in enumerate(devices)]
+
+    def _check(self, rc):
+        if rc != 0:
+            raise WaltError(rc, self.L.walt_last_error().decode())
+
+    def load_dbindex(self, path, which=(0, 1)):
+        mask = sum(1 << w for w in which)
+        self._check(self.L.walt_group_load_dbindex(self.h, path.encode(), C.c_uint32(mask)))
+
+    def map_se_packed(self, packed, offs, ag=False, m=6, b=5000, out=None):
+        n = offs.size - 1
+        if out is None:
+            out = np.zeros(n, dtype=BEST_DT)
+        short = C.c_uint32()
+        self._check(self.L.walt_group_map_se_packed(self.h, _p(packed), _p(offs), C.c_uint32(n), C.c_int(int(ag)), C.c_uint32(m),
+                                                    C.c_uint32(b), _p(out), C.byref(short)))
+        return out, short.value
+
+    def map_se(self, buf, offs, ag=False, m=6, b=5000, out=None):
+        n = offs.size - 1
+        if out is None:
+            out = np.zeros(n, dtype=BEST_DT)
+        short = C.c_uint32()
+        self._check(self.L.walt_group_map_se(self.h, _p(buf), _p(offs), C.c_uint32(n), C.c_int(int(ag)), C.c_uint32(m),
+                                             C.c_uint32(b), _p(out), C.byref(short)))
+        return out, short.value
+
+    def map_pe_compact_packed(self, p1, o1, p2, o2, m=6, b=5000, top_k=50, frag_range=1000, pbat=False, out=None):
+        n = o1.size - 1
+        if out is None:
+            out = np.zeros(n, dtype=PE_RESULT_DT)
+        s1, s2 = C.c_uint32(), C.c_uint32()
+        self._check(self.L.walt_group_map_pe_compact_packed(self.h, _p(p1), _p(o1), _p(p2), _p(o2), C.c_uint32(n), C.c_uint32(m),
+                                                            C.c_uint32(b), C.c_uint32(top_k), C.c_int(frag_range), C.c_int(int(pbat)),
+                                                            _p(out), C.byref(s1), C.byref(s2)))
+        return out, s1.value, s2.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            for e in self.engines:
+                e.close()
+            self.L.walt_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
