@@ -219,7 +219,7 @@ def free_host_indexes(hidx=None):
 class Workload:
     """Per-rank synthetic genome, resident index and read batch."""
 
-    def __init__(self, args, device, rank, kind=None, genome_mb=None, reads=None, read_len=None):
+    def __init__(self, args, device, rank, kind=None, genome_mb=None, reads=None, read_len=None, verify=None):
         import torch
         import walt_b200
         from walt_b200 import engine as eng
@@ -227,6 +227,7 @@ class Workload:
         self.device = device
         self.kind = kind or getattr(args, "workload", "se")
         self.genome_mb = float(genome_mb if genome_mb is not None else args.genome_mb)
+        self.verify = dict(VERIFY, **(verify or {}))
         self.ag = self.kind == "se_ag"
         self.is_pe = self.kind in ("pe", "pe_stress")
         self.pbat = self.kind == "pe_stress"
@@ -245,8 +246,8 @@ class Workload:
         dev = f"cuda:{device}"
         d_fwd = torch.empty(eng.packed_genome_bytes(total), dtype=torch.uint8, device=dev)
         if self.kind == "verify":
-            eng.synth_verify_genome_device(device, total, VERIFY["genome_seed"], VERIFY["n_families"], VERIFY["rep_pct"],
-                                           VERIFY["div_per_mille"], d_fwd.data_ptr())
+            eng.synth_verify_genome_device(device, total, self.verify["genome_seed"], self.verify["n_families"], self.verify["rep_pct"],
+                                           self.verify["div_per_mille"], d_fwd.data_ptr())
         else:
             eng.synth_genome_device(device, total, 3, d_fwd.data_ptr(), repeats=self.kind == "pe_stress")
         self.e.build_from_device_genome(d_fwd.data_ptr(), which=self.which)
@@ -264,8 +265,8 @@ class Workload:
             self.e.synth_pairs_device(d_fwd.data_ptr(), self.n, self.rl, 5 + 1000 * rank, t_rich.data_ptr(),
                                       a_rich.data_ptr(), readthrough_pct=30 if self.kind == "pe_stress" else 0)
         elif self.kind == "verify":
-            self.e.synth_verify_reads_device(d_fwd.data_ptr(), self.n, self.rl, 4 + 1000 * rank, VERIFY["genome_seed"],
-                                             VERIFY["n_families"], VERIFY["rep_pct"], self.d_reads.data_ptr())
+            self.e.synth_verify_reads_device(d_fwd.data_ptr(), self.n, self.rl, 4 + 1000 * rank, self.verify["genome_seed"],
+                                             self.verify["n_families"], self.verify["rep_pct"], self.d_reads.data_ptr())
         else:
             self.e.synth_reads_device(d_fwd.data_ptr(), self.n, self.rl, 4 + 1000 * rank, self.ag, self.d_reads.data_ptr())
         del d_fwd
@@ -836,6 +837,26 @@ def roofline_dict(wl, alg, kernel_s, dstats, genome_mb):
 
 
 def verify_leg(args, local, stream, barrier, steps=None, warmup=None):
+    """the micro-benchmark proper, plus two variants that show what bounds it: longer reads (more algorithmic
+    bytes per 32-byte sector moved) and a repeat set that fits the L2 (windows come from the L2, only the
+    entry array streams from HBM)"""
+    out = verify_one(args, local, stream, barrier, steps, warmup)
+    out["variants"] = []
+    for name, kw in (("reads of 192 bases (the longest the verification kernel takes)", {"read_len": 192}),
+                     ("half the repeat copies (139 families, 32 % of the tiles: their windows fit the 126 MB L2)",
+                      {"verify": {"n_families": 139, "rep_pct": 32}})):
+        try:
+            v = verify_one(args, local, stream, barrier, steps, warmup, parity=False, **kw)
+            out["variants"].append({"what": name, "value": v["value"], "verify_kernel_ms_per_step": v["verify_kernel_ms_per_step"],
+                                    "slots_per_read": v["slots_per_read"], "frac": v["roofline"]["frac"],
+                                    "achieved": v["roofline"]["achieved"],
+                                    "algorithmic_bytes_per_candidate": v["roofline"]["algorithmic_bytes_per_candidate"]})
+        except Exception as ex:
+            out["variants"].append({"what": name, "error": str(ex)[-200:]})
+    return out
+
+
+def verify_one(args, local, stream, barrier, steps=None, warmup=None, parity=True, read_len=None, verify=None):
     """Verification alone (north_star's ">= 50 % of HBM roofline on verification"): reads
     whose six seed lookups each meet thousands of candidates.  The engine parks them; verify_kernel then
     checks every candidate of every run, a warp per 32 slots -- that kernel's launches are timed by CUDA
@@ -843,8 +864,9 @@ def verify_leg(args, local, stream, barrier, steps=None, warmup=None):
     the device.  bytes_verify = slots * (4 + ceil(rl / 4)) as in SURVEY.md 8(d)."""
     import refio
     gmb, nreads, rl = FULL_SIZE["verify"]
+    rl = read_len or rl
     steps, warmup = steps or args.steps, warmup or args.warmup
-    wl = Workload(args, local, 0, kind="verify", genome_mb=gmb, reads=nreads, read_len=rl)
+    wl = Workload(args, local, 0, kind="verify", genome_mb=gmb, reads=nreads, read_len=rl, verify=verify)
     e = wl.e
     e.set_kernel_timing(True)
     for _ in range(warmup):
@@ -872,7 +894,7 @@ def verify_leg(args, local, stream, barrier, steps=None, warmup=None):
     if t and t_verify:
         out["roofline"]["traffic"] = t["dram_bytes_per_step"]
         out["roofline"]["dram_frac"] = t["dram_bytes_per_step"] * steps / t_verify / 1e9 / peak
-    if not args.no_cpu and refio.have_reference():   # parity of the whole step (park, verify, fold) on a sample
+    if parity and not args.no_cpu and refio.have_reference():   # parity of the whole step (park, verify, fold) on a sample
         try:
             hidx = wl.host_index()
             ns = min(512, nreads)

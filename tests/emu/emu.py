@@ -44,25 +44,23 @@ class EmuEngine:
     def depth(self, which):
         return int(self.L.emu_engine_depth(self.h, C.c_int(which)))
 
-    def map_se(self, buf, offs, best_dtype, ag=False, m=6, b=5000, literal=False, threads=8, width=32, packed=False,
-               prelit=False):
+    def map_se(self, buf, offs, best_dtype, ag=False, m=6, b=5000, literal=False, threads=8, width=32, packed=False):
         n = len(offs) - 1
         out = np.zeros(n, dtype=best_dtype)
         ctr = np.zeros(3, dtype=np.uint64)
         rc = self.L.emu_map_se(self.h, _p(buf), _p(offs), C.c_uint32(n), C.c_int(int(ag)), C.c_uint32(m),
                                C.c_uint32(b), C.c_int(int(literal)), _p(out), C.c_int(threads), _p(ctr),
-                               C.c_uint32(width), C.c_int(int(packed)), C.c_int(int(prelit)))
+                               C.c_uint32(width), C.c_int(int(packed)))
         return rc, out, ctr
 
     def map_pe_mate(self, buf, offs, cand_dtype, ag, m=6, b=5000, top_k=50, literal=False, threads=8, width=32,
-                    logged=False, prelit=False):
+                    logged=False):
         n = len(offs) - 1
         ranked = np.zeros((n, top_k), dtype=cand_dtype)
         sizes = np.zeros(n, dtype=np.uint32)
         rc = self.L.emu_map_pe_mate(self.h, _p(buf), _p(offs), C.c_uint32(n), C.c_int(int(ag)),
                                     C.c_uint32(m), C.c_uint32(b), C.c_uint32(top_k), C.c_int(int(literal)),
-                                    _p(ranked), _p(sizes), C.c_int(threads), C.c_uint32(width), C.c_int(int(logged)),
-                                    C.c_int(int(prelit)))
+                                    _p(ranked), _p(sizes), C.c_int(threads), C.c_uint32(width), C.c_int(int(logged)))
         return rc, ranked, sizes
 
     def pair(self, r1, n1, offs1, r2, n2, offs2, top_k, m, frag_range):

@@ -308,8 +308,6 @@ struct SeJob {
   int ag; uint32_t m, b; int literal; emu_best* out; uint32_t max_len;
   uint64_t* scratch; uint32_t* cached_len; Counters* ctr; int* bad;
   int packed;   // seqs is the 2-bit form of walt_pack_reads (include/walt_host.h)
-  int prelit;   // literal regions computed ahead by one lane (what the device's literal kernel does for parked reads)
-  uint32_t* lit;
 };
 
 template <uint32_t WD>
@@ -327,20 +325,9 @@ void se_lane(WarpEmu* w, uint32_t lane, void* arg) {
     BestState st;
     uint32_t len = (uint32_t)(j->offs[r + 1] - j->offs[r]);
     const char* seq = j->packed ? j->seqs + (j->offs[r] >> 2) + r : j->seqs + j->offs[r];
-    const uint32_t* lit = nullptr;
-    if (j->prelit) {
-      if (lane == 0) {
-        uint64_t R[MAX_WORDS];
-        const bool good = j->packed ? pack_read_serial<true>(seq, len, j->ag != 0, R) : pack_read_serial<false>(seq, len, j->ag != 0, R);
-        if (good) literal_regions(ix2, cv.genome_len, j->e->p3, cfg, R, len, j->lit);
-        else for (uint32_t i = 0; i < LIT_WORDS; ++i) j->lit[i] = i & 1u ? 0u : LIT_NONE;
-      }
-      W.sync();
-      lit = j->lit;
-    }
     bool ok = MAP_OK == (j->packed
-                  ? map_read_se<EmuWarp<WD>, true>(W, ix2, cv, j->e->p3, cfg, seq, len, j->ag != 0, j->m, sc, cached, st, ctr, lit)
-                  : map_read_se<EmuWarp<WD>, false>(W, ix2, cv, j->e->p3, cfg, seq, len, j->ag != 0, j->m, sc, cached, st, ctr, lit));
+                  ? map_read_se<EmuWarp<WD>, true>(W, ix2, cv, j->e->p3, cfg, seq, len, j->ag != 0, j->m, sc, cached, st, ctr)
+                  : map_read_se<EmuWarp<WD>, false>(W, ix2, cv, j->e->p3, cfg, seq, len, j->ag != 0, j->m, sc, cached, st, ctr));
     if (lane == 0) {
       if (!ok) *j->bad = 1;
       j->out[r].genome_pos = st.pos; j->out[r].times = st.times; j->out[r].mismatch = st.mm;
@@ -358,7 +345,6 @@ struct PeJob {
   int ag; uint32_t m, b, top_k; int literal; emu_cand* ranked; uint32_t* n_ranked; uint32_t max_len;
   uint64_t* scratch; HeapEntry* heap; int* bad;
   int logged; HeapEntry* log; uint32_t* hist;   // two-phase form: LogSink + replay_heap_log
-  int prelit; uint32_t* lit;                    // see SeJob (logged form only)
 };
 
 template <uint32_t WD>
@@ -378,18 +364,8 @@ void pe_lane(WarpEmu* w, uint32_t lane, void* arg) {
     bool ok;
     if (j->logged) {
       uint32_t n_log = 0;
-      const uint32_t* lit = nullptr;
-      if (j->prelit) {
-        if (lane == 0) {
-          uint64_t R[MAX_WORDS];
-          if (pack_read_serial<false>(j->seqs + j->offs[r], len, j->ag != 0, R)) literal_regions(ix2, cv.genome_len, j->e->p3, cfg, R, len, j->lit);
-          else for (uint32_t i = 0; i < LIT_WORDS; ++i) j->lit[i] = i & 1u ? 0u : LIT_NONE;
-        }
-        W.sync();
-        lit = j->lit;
-      }
       ok = MAP_OK == map_read_pe_logged(W, ix2, cv, j->e->p3, cfg, j->seqs + j->offs[r], len, j->ag != 0, j->m,
-                                        j->top_k, sc, cached, j->log, j->hist, n_log, ctr, lit);
+                                        j->top_k, sc, cached, j->log, j->hist, n_log, ctr);
       W.sync();
       if (lane == 0) replay_heap_log(j->log, n_log, j->top_k, j->heap, hsize);   // second kernel: one thread per read
     } else {
@@ -461,8 +437,7 @@ extern "C" {
 
 // returns 0 ok; 1 = warp primitives diverged (bug); 5 = non-ACGT read
 int emu_map_se(void* h, const char* seqs, const uint64_t* offs, uint32_t n, int ag, uint32_t m,
-               uint32_t b, int literal, emu_best* out, int threads, uint64_t* counters3, uint32_t width, int packed,
-               int prelit) {
+               uint32_t b, int literal, emu_best* out, int threads, uint64_t* counters3, uint32_t width, int packed) {
   if (width != 8 && width != 16 && width != 32) return 1;
   EmuEngine* e = (EmuEngine*)h;
   uint32_t max_len = 1;
@@ -473,8 +448,7 @@ int emu_map_se(void* h, const char* seqs, const uint64_t* offs, uint32_t n, int 
   int div = run_parallel<SeJob>(n, threads, width, [&](WarpEmu* w, uint32_t lo, uint32_t hi) {
     std::vector<uint64_t> scratch(scratch_words((max_len + 31) / 32) + 8);
     uint32_t cached = 0; Counters ctr{0, 0, 0}; int b_ = 0;
-    uint32_t lit[LIT_WORDS];
-    SeJob j{e, seqs, offs, lo, hi, ag, m, b, literal, out, max_len, scratch.data(), &cached, &ctr, &b_, packed, prelit, lit};
+    SeJob j{e, seqs, offs, lo, hi, ag, m, b, literal, out, max_len, scratch.data(), &cached, &ctr, &b_, packed};
     w->run(width == 8 ? se_lane<8> : width == 16 ? se_lane<16> : se_lane<32>, &j);
     if (b_) bad = 1;
     c0 += ctr.lookups; c1 += ctr.candidates; c2 += ctr.literal;
@@ -486,7 +460,7 @@ int emu_map_se(void* h, const char* seqs, const uint64_t* offs, uint32_t n, int 
 
 int emu_map_pe_mate(void* h, const char* seqs, const uint64_t* offs, uint32_t n, int ag, uint32_t m,
                     uint32_t b, uint32_t top_k, int literal, emu_cand* ranked, uint32_t* n_ranked,
-                    int threads, uint32_t width, int logged, int prelit) {
+                    int threads, uint32_t width, int logged) {
   if (width != 8 && width != 16 && width != 32) return 1;
   if (logged && m > LOG_MAX_MM) return 1;
   EmuEngine* e = (EmuEngine*)h;
@@ -499,9 +473,8 @@ int emu_map_pe_mate(void* h, const char* seqs, const uint64_t* offs, uint32_t n,
     std::vector<HeapEntry> heap(top_k + 1), log(pe_log_slots(top_k, m) + 1);
     std::vector<uint32_t> hist(m + 2);
     int b_ = 0;
-    uint32_t lit[LIT_WORDS];
     PeJob j{e, seqs, offs, lo, hi, ag, m, b, top_k, literal, ranked, n_ranked, max_len, scratch.data(), heap.data(), &b_,
-            logged, log.data(), hist.data(), prelit, lit};
+            logged, log.data(), hist.data()};
     w->run(width == 8 ? pe_lane<8> : width == 16 ? pe_lane<16> : pe_lane<32>, &j);
     if (b_) bad = 1;
   });

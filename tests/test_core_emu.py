@@ -27,17 +27,14 @@ def _cmp_best(got, want):
         assert bad.size == 0, (f, bad[:5], got[bad[:5]], want[bad[:5]])
 
 
-@pytest.mark.parametrize("literal,width,prelit", [(False, 32, False), (True, 32, False), (False, 8, False), (True, 8, False),
-                                                  (False, 16, False), (False, 32, True), (True, 32, True), (True, 8, True)])
-def test_se_emu_matches_reference(engine, literal, width, prelit):
-    """prelit: the literal regions come from literal_regions() (one lane, ahead of the read), as they do
-    for parked reads on the device"""
+@pytest.mark.parametrize("literal,width", [(False, 32), (True, 32), (False, 8), (True, 8), (False, 16)])
+def test_se_emu_matches_reference(engine, literal, width):
     for name, ag in (("se_ct.npz", False), ("se_ga.npz", True)):
         z = goldenio.load(name)
         buf, offs = refio.pack_reads(z["reads"])
         for key in [k for k in z.files if k.startswith("best_")]:
             m, b = (int(x[1:]) for x in key[5:].split("_"))
-            rc, out, ctr = engine.map_se(buf, offs, refio.BEST_DT, ag=ag, m=m, b=b, literal=literal, width=width, prelit=prelit)
+            rc, out, ctr = engine.map_se(buf, offs, refio.BEST_DT, ag=ag, m=m, b=b, literal=literal, width=width)
             assert rc == 0
             _cmp_best(out, z[key])
             if literal:
@@ -91,9 +88,8 @@ def test_se_emu_packed_input(engine, width):
     _cmp_best(out, z[key])
 
 
-@pytest.mark.parametrize("depth,width,prelit", [(0, 32, False), (12, 32, False), (13, 8, False), (16, 8, False), (0, 8, False),
-                                                (12, 16, False), (0, 32, True), (13, 8, True)])
-def test_se_edge_emu(depth, width, prelit):
+@pytest.mark.parametrize("depth,width", [(0, 32), (12, 32), (13, 8), (16, 8), (0, 8), (12, 16)])
+def test_se_edge_emu(depth, width):
     hdr, subs = goldenio.genome()
     e = emu.EmuEngine(hdr.lengths)
     for w, sfx in enumerate(refio.SUFFIXES):
@@ -102,16 +98,15 @@ def test_se_edge_emu(depth, width, prelit):
     for ag, pre in ((False, "ct_best_"), (True, "ga_best_")):
         for key in [k for k in z.files if k.startswith(pre)]:
             m, b = (int(x[1:]) for x in key[len(pre):].split("_"))
-            rc, out, _ = e.map_se(z["buf"], z["offs"], refio.BEST_DT, ag=ag, m=m, b=b, width=width, prelit=prelit)
+            rc, out, _ = e.map_se(z["buf"], z["offs"], refio.BEST_DT, ag=ag, m=m, b=b, width=width)
             assert rc == 0
             _cmp_best(out, z[key])
     e.close()
 
 
-@pytest.mark.parametrize("logged,prelit", [(False, False), (True, False), (True, True)],
-                         ids=["heap-in-kernel", "logged+replay", "logged+replay+prelit"])
+@pytest.mark.parametrize("logged", [False, True], ids=["heap-in-kernel", "logged+replay"])
 @pytest.mark.parametrize("width", [32, 8])
-def test_pe_emu_matches_reference(engine, width, logged, prelit):
+def test_pe_emu_matches_reference(engine, width, logged):
     hdr, _ = goldenio.genome()
     z = goldenio.load("pe.npz")
     L = refio.oracle_lib()
@@ -122,8 +117,7 @@ def test_pe_emu_matches_reference(engine, width, logged, prelit):
         got = {}
         for mate, ag in ((1, False), (2, True)):
             buf, offs = refio.pack_reads(z[f"m{mate}"])
-            rc, ranked, sizes = engine.map_pe_mate(buf, offs, refio.CAND_DT, ag, m=m, top_k=k, width=width, logged=logged,
-                                                   prelit=prelit)
+            rc, ranked, sizes = engine.map_pe_mate(buf, offs, refio.CAND_DT, ag, m=m, top_k=k, width=width, logged=logged)
             assert rc == 0
             assert np.array_equal(sizes, z[f"sizes{mate}_m{m}_k{k}"])
             want = z[f"ranked{mate}_m{m}_k{k}"]

@@ -48,7 +48,7 @@ def test_se_repeats(world, width, literal, rl, m, b):
             assert ctr.asdict()["n_cand"] > (20 if rl >= 100 else 5) * len(reads)      # the workload is repeat-bound
         buf, offs = refio.pack_reads(reads)
         # literal: every lookup through literal_index_region (table boundaries / fingerprints / genome)
-        rc, got, _ = e.map_se(buf, offs, refio.BEST_DT, ag=ag, m=m, b=b, width=width, literal=literal, prelit=literal)
+        rc, got, _ = e.map_se(buf, offs, refio.BEST_DT, ag=ag, m=m, b=b, width=width, literal=literal)
         assert rc == 0
         _cmp_best(got, want)
 

@@ -1307,7 +1307,7 @@ WALT_HD_NOINLINE uint32_t lane_literal_region(const SubIndexView& ix, uint32_t g
 // LANE_GROUP: the whole lookup is the group's job (a literal region of more than LANE_RUN_CAP slots).  LANE_RUN: more than LANE_RUN_CAP
 // fingerprint-equal slots; `run` then says where the run starts and where its table range ends, so
 // that a whole warp can stream it (run_lookup) without searching again.
-enum LaneResult : uint32_t { LANE_DONE = 0u, LANE_GROUP = 1u, LANE_RUN = 2u, LANE_LIT = 3u };   // LANE_LIT: literal lookup, region known
+enum LaneResult : uint32_t { LANE_DONE = 0u, LANE_GROUP = 1u, LANE_RUN = 2u };
 struct LaneRun { uint32_t f0, hi, fp_lo; };
 WALT_HD uint32_t lookup_fp_span(const SubIndexView& ix, uint32_t read_len, const Pow3& p3) {
   const uint32_t seed_len = seed_repeats(read_len);
@@ -1470,80 +1470,14 @@ WALT_HD void prefetch_runs(W& w, const SubIndexView* ix2, uint32_t run_mask, con
 }
 
 // ------------------------------------------------------------------------------------------
-// literal regions ahead of the take-over kernel (one THREAD per parked read)
-// ------------------------------------------------------------------------------------------
-// The literal IndexRegion replay is one long chain of dependent loads (two per probe, ~200 probes
-// on a bucket of thousands).  A warp that runs it for one lookup sits idle for a hundred
-// microseconds; run by one thread per parked read, tens of thousands of chains are in flight at
-// once.  For each of the read's six lookups: {LIT_NONE, -} if the lookup is not a literal one,
-// {LIT_EMPTY, -} if its 12-mer bucket is empty, else the inclusive region IndexRegion returns
-// ((1, 0) for a failed search).
-constexpr uint32_t LIT_NONE = 0xFFFFFFFFu;
-constexpr uint32_t LIT_EMPTY = 0xFFFFFFFEu;
-constexpr uint32_t LIT_WORDS = 2u * LOOKUP_LANES;
-
-// pack + convert a read by one thread; false if a byte is not A/C/G/T
-template <bool PACKED>
-WALT_HD bool pack_read_serial(const char* __restrict__ seq, uint32_t read_len, bool ag, uint64_t* R) {
-  const uint32_t nw = (read_len + 31u) >> 5;
-  bool bad = false;
-  for (uint32_t k = 0; k < nw; ++k) {
-    uint64_t word = 0;
-    for (uint32_t p = 32u * k; p < 32u * k + 32u; p += 4u) {   // four characters -> one byte, as load_read does
-      const uint32_t nv = p < read_len ? read_len - p : 0u;
-      uint32_t c4;
-      if (PACKED) c4 = nv ? packed_codes4((uint8_t)seq[p >> 2], nv, ag) : 0u;
-      else c4 = codes4(load4_ascii(seq, p, read_len), nv, ag, bad);
-      word = (word << 8) | ((c4 * 0x40100401u) >> 24);
-    }
-    R[k] = word;
-  }
-  return !bad;
-}
-
-WALT_HD void literal_regions(const SubIndexView* ix2, uint32_t genome_len, const Pow3& p3, const MapConfig& cfg,
-                             const uint64_t* R, uint32_t read_len, uint32_t* out) {
-  const uint32_t seed_len = seed_repeats(read_len);
-  for (uint32_t j = 0; j < LOOKUP_LANES; ++j) {
-    out[2u * j] = LIT_NONE; out[2u * j + 1u] = 0u;
-    if (read_len < MIN_READ_LEN) continue;
-    const SubIndexView& ix = ix2[j / 3u];
-    const uint32_t seed_i = j % 3u;
-    uint32_t key12 = 0u;
-    for (uint32_t i = 0; i < KEY_WEIGHT; ++i)
-      key12 = key12 * 3u + ternary_digit(packed_base(R, seed_i + 3u * i + 1u), ix.ag != 0u);
-    const bool literal = cfg.literal_all != 0u ||
-                         ((((ix.taint_bits[key12 >> 5] >> (key12 & 31u)) & 1u) != 0u) && lane_is_affected(ix, R, seed_i, seed_len, key12));
-    if (!literal) continue;
-    const uint32_t k12_span = p3.v[ix.depth - KEY_WEIGHT];
-    const uint32_t bucket_lo = ix.table[key12 * k12_span], bucket_hi = ix.table[(key12 + 1u) * k12_span];
-    if (bucket_lo == bucket_hi) { out[2u * j] = LIT_EMPTY; continue; }
-    uint32_t f = bucket_lo, l = bucket_hi;
-    literal_index_region(ix, genome_len, p3, R, seed_i, seed_len, key12, f, l);
-    out[2u * j] = f; out[2u * j + 1u] = l;
-  }
-}
-
-// a literal lookup whose region is known (literal_regions): filters and candidates as in seed_lookup
-template <class W, class Sink>
-WALT_HD void lit_lookup(W& w, const SubIndexView& ix, const ChromView& cv, const MapConfig& cfg, const ReadScratch& sc,
-                        uint32_t read_len, uint32_t seed_i, uint32_t strand, uint32_t f, uint32_t l, Sink& sink, Counters& ctr) {
-  if (f == LIT_EMPTY) return;
-  if (w.lane() == 0u) { ctr.lookups++; ctr.literal++; }
-  if (l - f + 1u > cfg.b) return;      // mapping.cpp:275-277 (u32 arithmetic; (1,0) -> 0)
-  if (f > l) return;                   // failed search: empty candidate loop
-  verify_region(w, ix, cv, sc, read_len, seed_i, strand, f, l + 1u, sink, ctr);
-}
-
-// ------------------------------------------------------------------------------------------
 // parked reads: what the lane phase found, flat verification of their runs, ordered fold
 // ------------------------------------------------------------------------------------------
 // A read that a sub-warp group cannot finish (its fold reaches a long run) is PARKED: its lanes
 // write down what they found -- per lookup either the verified candidates or the run (first slot,
 // length) -- and reserve one 32-candidate block after the other of a launch-wide scratch for the
 // runs.  A second kernel then verifies ALL blocks of ALL parked reads, a warp per block, with no
-// order and no state (verify_block: eight windows per load instruction, thousands of blocks in
-// flight), leaving one byte per slot: the mismatch count, or MM_NONE.  A third kernel folds each
+// order and no state (verify_kernel, walt_engine.cu: eight windows per copy instruction, thousands of
+// blocks in flight), leaving one byte per slot: the mismatch count, or MM_NONE.  A third kernel folds each
 // parked read in reference order from its record and those bytes (fold_parked_*), touching the
 // index only for the few candidates a sink still takes.
 constexpr uint32_t PARK_WORDS = 64;          // words per parked read: [0] read, [1] blocks, [2 + 10 j ..) lookup j
@@ -1605,25 +1539,6 @@ WALT_HD_NOINLINE uint32_t exact_region(const SubIndexView& ix, const LaneRun& ru
     if (cmp(mid) <= 0) lo = mid + 1u; else hi = mid;
   }
   return lo - first;
-}
-
-// One block of 32 slots of a parked run: slot `first + lane` of [first, last_excl), read and masks in
-// `sc`.  out[lane] = mismatches over the verification mask if the slot is seed-equal, else MM_NONE.
-template <class W>
-WALT_HD void verify_block(W& w, const SubIndexView& ix, const ReadScratch& sc, uint32_t read_len, uint32_t seed_i,
-                          uint32_t first, uint32_t last_excl, uint8_t* out, Counters& ctr) {
-  const uint32_t lane = w.lane(), q = lane & 3u;
-  const uint32_t nw = (read_len + 31u) >> 5;
-  const Quad32 Rq = read_block(sc.R, q, nw);
-  const Quad32 VMq = read_block(sc.VM + seed_i * sc.nw, q, nw);
-  const Quad32 SMq = read_block(sc.SM + seed_i * sc.nw, q, nw);
-  WideBlock blk;
-  blk.en = wide_load_entry(w, ix, first, last_excl);
-  wide_load_genome(w, ix, seed_i, blk);
-  const uint32_t r = wide_compare(w, blk, Rq, VMq, SMq);
-  const bool cand = first + lane < last_excl && (r >> 16) == 0u;
-  if (cand) ctr.candidates++;
-  out[lane] = (uint8_t)(cand ? (r & 0xFFFFu) : MM_NONE);
 }
 
 // A parked run in the ordered fold: its bytes, 32 at a time; the entry is read only for the slots a
@@ -1735,7 +1650,7 @@ template <class W, bool PACKED = false, class Park = NoPark>
 WALT_HD MapStatus map_read_se(W& w, const SubIndexView* ix2, const ChromView& cv, const Pow3& p3,
                          const MapConfig& cfg, const char* seq, uint32_t read_len, bool ag,
                          uint32_t max_mismatches, ReadScratch& sc, uint32_t& cached_len,
-                         BestState& out, Counters& ctr, const uint32_t* lit = nullptr, Park park = Park()) {
+                         BestState& out, Counters& ctr, Park park = Park()) {
   constexpr bool PARK = Park::ENABLED;
   static_assert(W::WIDTH >= LOOKUP_LANES, "a group needs one lane per lookup");
   BestSink<W> sink;
@@ -1751,12 +1666,8 @@ WALT_HD MapStatus map_read_se(W& w, const SubIndexView* ix2, const ChromView& cv
   LaneResult res = LANE_DONE;
   LaneRun run; run.f0 = run.hi = run.fp_lo = 0u;
   uint32_t mn = NO_HIT, cnt = 0u, g_first = 0u, g_last = 0u;
-  uint32_t lit_f = LIT_NONE, lit_l = 0u;
   if (lane < LOOKUP_LANES) {
-    if (lit) { lit_f = lit[2u * lane]; lit_l = lit[2u * lane + 1u]; }
-    if (lit_f != LIT_NONE) {
-      res = LANE_LIT;
-    } else if (cfg.literal_all) {
+    if (cfg.literal_all) {
       res = LANE_GROUP;
     } else {
       res = lane_lookup(ix2[lane / 3u], cv, p3, cfg, sc, read_len, lane % 3u,
@@ -1769,22 +1680,19 @@ WALT_HD MapStatus map_read_se(W& w, const SubIndexView* ix2, const ChromView& cv
   }
   const uint32_t group_mask = w.ballot(res == LANE_GROUP);
   const uint32_t run_mask = w.ballot(res == LANE_RUN);
-  const uint32_t lit_mask = w.ballot(res == LANE_LIT);
   const uint32_t hit_mask = w.ballot(mn != NO_HIT);
   // ordered fold over the lookups that can change the state.  Skipping a lookup where the
   // reference would have left the shift loop (mapping.cpp:250-256) is the same as its break: the
   // state is untouched by a skip, so the later shifts of that strand are skipped as well.
   if (!PARK && run_mask && read_len <= WIDE_MAX_READ) prefetch_runs(w, ix2, run_mask, run);
-  uint32_t todo = (group_mask | run_mask | lit_mask | hit_mask) & ((1u << LOOKUP_LANES) - 1u);
+  uint32_t todo = (group_mask | run_mask | hit_mask) & ((1u << LOOKUP_LANES) - 1u);
   while (todo) {
     const uint32_t j = (uint32_t)ffs32(todo) - 1u;
     todo &= todo - 1u;
     const uint32_t s = j >= 3u ? 1u : 0u, seed_i = j - 3u * s;
     const uint32_t strand = s ? '-' : '+';
     if (sink.stop_before_shift(seed_i)) continue;
-    if ((lit_mask >> j) & 1u) {
-      lit_lookup(w, ix2[s], cv, cfg, sc, read_len, seed_i, strand, w.shfl(lit_f, (int)j), w.shfl(lit_l, (int)j), sink, ctr);
-    } else if (((group_mask | run_mask) >> j) & 1u) {
+    if (((group_mask | run_mask) >> j) & 1u) {
       if (PARK) {   // the kernels that take the read over count its work
         ctr = ctr_in;
         park_read(w, ix2, p3, cfg, sc, read_len, res, run, park, [&](uint32_t* rec) {
@@ -1811,7 +1719,7 @@ template <class W, bool PACKED, class Park, class SinkT>
 WALT_HD MapStatus map_read_pe_into(W& w, const SubIndexView* ix2, const ChromView& cv, const Pow3& p3,
                               const MapConfig& cfg, const char* seq, uint32_t read_len, bool ag,
                               uint32_t max_mismatches, ReadScratch& sc, uint32_t& cached_len, SinkT& sink,
-                              Counters& ctr, const uint32_t* lit = nullptr, Park park = Park()) {
+                              Counters& ctr, Park park = Park()) {
   constexpr bool PARK = Park::ENABLED;
   static_assert(W::WIDTH >= LOOKUP_LANES, "a group needs one lane per lookup");
   const Counters ctr_in = ctr;
@@ -1824,12 +1732,8 @@ WALT_HD MapStatus map_read_pe_into(W& w, const SubIndexView* ix2, const ChromVie
   LaneResult res = LANE_DONE;
   LaneRun run; run.f0 = run.hi = run.fp_lo = 0u;
   uint32_t n_mine = 0u;
-  uint32_t lit_f = LIT_NONE, lit_l = 0u;
   if (lane < LOOKUP_LANES) {
-    if (lit) { lit_f = lit[2u * lane]; lit_l = lit[2u * lane + 1u]; }
-    if (lit_f != LIT_NONE) {
-      res = LANE_LIT;
-    } else if (cfg.literal_all) {
+    if (cfg.literal_all) {
       res = LANE_GROUP;
     } else {
       LaneCand* mine = sc.C + lane * LANE_RUN_CAP;
@@ -1845,20 +1749,17 @@ WALT_HD MapStatus map_read_pe_into(W& w, const SubIndexView* ix2, const ChromVie
   }
   const uint32_t group_mask = w.ballot(res == LANE_GROUP);
   const uint32_t run_mask = w.ballot(res == LANE_RUN);
-  const uint32_t lit_mask = w.ballot(res == LANE_LIT);
   const uint32_t hit_mask = w.ballot(n_mine != 0u);
   w.sync();
   if (!PARK && run_mask && read_len <= WIDE_MAX_READ) prefetch_runs(w, ix2, run_mask, run);
-  uint32_t todo = (group_mask | run_mask | lit_mask | hit_mask) & ((1u << LOOKUP_LANES) - 1u);
+  uint32_t todo = (group_mask | run_mask | hit_mask) & ((1u << LOOKUP_LANES) - 1u);
   while (todo) {   // see map_read_se: a skip is the reference's break (paired.cpp:127-137)
     const uint32_t j = (uint32_t)ffs32(todo) - 1u;
     todo &= todo - 1u;
     const uint32_t s = j >= 3u ? 1u : 0u, seed_i = j - 3u * s;
     const uint32_t strand = s ? '-' : '+';
     if (sink.stop_before_shift(seed_i)) continue;
-    if ((lit_mask >> j) & 1u) {
-      lit_lookup(w, ix2[s], cv, cfg, sc, read_len, seed_i, strand, w.shfl(lit_f, (int)j), w.shfl(lit_l, (int)j), sink, ctr);
-    } else if (((group_mask | run_mask) >> j) & 1u) {
+    if (((group_mask | run_mask) >> j) & 1u) {
       if (PARK) {
         ctr = ctr_in;
         park_read(w, ix2, p3, cfg, sc, read_len, res, run, park, [&](uint32_t* rec) {
@@ -1900,11 +1801,11 @@ WALT_HD MapStatus map_read_pe_logged(W& w, const SubIndexView* ix2, const ChromV
                                 const MapConfig& cfg, const char* seq, uint32_t read_len, bool ag,
                                 uint32_t max_mismatches, uint32_t top_k, ReadScratch& sc,
                                 uint32_t& cached_len, HeapEntry* log, uint32_t* hist, uint32_t& n_log, Counters& ctr,
-                                const uint32_t* lit = nullptr, Park park = Park()) {
+                                Park park = Park()) {
   LogSink<W> sink;
   sink.log = log; sink.hist = hist; sink.cap = top_k; sink.max_mm = max_mismatches;
   sink.reset(w);
-  const MapStatus st = map_read_pe_into<W, PACKED, Park>(w, ix2, cv, p3, cfg, seq, read_len, ag, max_mismatches, sc, cached_len, sink, ctr, lit, park);
+  const MapStatus st = map_read_pe_into<W, PACKED, Park>(w, ix2, cv, p3, cfg, seq, read_len, ag, max_mismatches, sc, cached_len, sink, ctr, park);
   n_log = sink.n_log;
   return st;
 }

@@ -449,7 +449,7 @@ se_map_kernel(const __grid_constant__ SeArgs a) {
       MapStatus ms;
       if (MODE == MAP_PARK)
         ms = map_read_se<HwGroup<WD>, PACKED, DevPark>(w, a.ix, a.cv, a.p3, a.cfg, seq, len, a.ag != 0u, a.max_mismatches, sc,
-                                                        cached_len, st, ctr, nullptr, DevPark{a.park, a.queue, r});
+                                                        cached_len, st, ctr, DevPark{a.park, a.queue, r});
       else
         ms = map_read_se<HwGroup<WD>, PACKED>(w, a.ix, a.cv, a.p3, a.cfg, seq, len, a.ag != 0u, a.max_mismatches, sc,
                                                cached_len, st, ctr);
@@ -531,7 +531,7 @@ pe_log_kernel(const __grid_constant__ PeArgs a) {
       if (MODE == MAP_PARK)
         ms = map_read_pe_logged<HwGroup<WD>, PACKED, DevPark>(w, a.ix, a.cv, a.p3, a.cfg, seq, len, a.ag != 0u, a.max_mismatches,
                                                                a.top_k, sc, cached_len, a.log + (size_t)r * a.log_slots, hist, n_log,
-                                                               ctr, nullptr, DevPark{a.park, a.queue, r});
+                                                               ctr, DevPark{a.park, a.queue, r});
       else
         ms = map_read_pe_logged<HwGroup<WD>, PACKED>(w, a.ix, a.cv, a.p3, a.cfg, seq, len, a.ag != 0u, a.max_mismatches, a.top_k,
                                                       sc, cached_len, a.log + (size_t)r * a.log_slots, hist, n_log, ctr);
