@@ -24,6 +24,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <functional>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -638,6 +639,8 @@ verify_kernel(const __grid_constant__ Args a) {
       fetch(i + 1u, e_next);                               // an empty group past the ticket's end
       const uint32_t e_after = entry_of(i + 2u);
       const uint32_t t = __shfl_sync(0xFFFFFFFFu, d_t, (int)i);
+      cp_async_wait<1>();                                 // block i's windows have landed (block i + 1's may still fly)
+      __syncwarp();
       if (t != 0xFFFFFFFFu) {
         const uint32_t j = __shfl_sync(0xFFFFFFFFu, d_j, (int)i), first = __shfl_sync(0xFFFFFFFFu, d_first, (int)i),
                        end = __shfl_sync(0xFFFFFFFFu, d_end, (int)i);
@@ -659,9 +662,8 @@ verify_kernel(const __grid_constant__ Args a) {
             masks[2u * VERIFY_WORDS + lane] = k < nw ? (uint32_t)(sc.SM[seed_i * sc.nw + k] >> sh) : 0u;
           }
           cur_t = t; cur_j = j;
+          __syncwarp();
         }
-        cp_async_wait<1>();                               // block i's windows have landed (block i + 1's may still fly)
-        __syncwarp();
         const uint32_t* tile = tiles + (i & 1u) * 32u * VERIFY_ROW;
         uint32_t W[16];
 #pragma unroll
@@ -1067,10 +1069,26 @@ static size_t pe_log_smem_bytes(uint32_t nw_max, uint32_t wd) {
   return (size_t)(BLOCK_THREADS / wd) * (scratch_words(nw_max) + (LOG_MAX_MM + 2u) / 2u) * 8u;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is state of the function on its device, shared by every engine
+// (and host thread) of the process that runs on that device: it is only ever raised, under a lock, so a
+// launch of one engine never finds the limit lowered by another engine's smaller batch.
+static int allow_dynamic_smem(const void* kernel, size_t smem) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> allowed;
+  int dev = 0;
+  WALT_CUDA_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& have = allowed[{dev, kernel}];
+  if (smem <= have) return WALT_OK;
+  WALT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  have = smem;
+  return WALT_OK;
+}
+
 template <class K>
 static int grid_for(walt_engine* e, K kernel, size_t smem, uint32_t n, uint32_t wd, uint32_t* grid, uint32_t share = 1) {
   int per_sm = 0;
-  WALT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (int rc = allow_dynamic_smem((const void*)kernel, smem)) return rc;
   WALT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)BLOCK_THREADS, smem));
   if (per_sm < 1) return fail(WALT_ECUDA, "mapping kernel does not fit on an SM");
   // persistent: a multiple of the SM count.  share > 1: this launch is one of several chunk kernels in
@@ -1131,7 +1149,7 @@ static void fill_common(walt_engine* e, Args& a, const ReadSrc& src, uint32_t n,
 template <class K>
 static int take_grid(walt_engine* e, K kernel, size_t smem, uint32_t* grid) {
   int per_sm = 0;
-  WALT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (int rc = allow_dynamic_smem((const void*)kernel, smem)) return rc;
   WALT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)BLOCK_THREADS, smem));
   if (per_sm < 1) return fail(WALT_ECUDA, "take-over kernel does not fit on an SM");
   *grid = (uint32_t)per_sm * (uint32_t)e->sm_count;
@@ -2000,7 +2018,7 @@ static int launch_pe_chunk(walt_engine* e, const ReadSrc& m1, const ReadSrc& m2,
     const uint32_t blocks = (2u * cn + (parked ? 4u * cn : 0u) + HEAP_BLOCK - 1u) / HEAP_BLOCK;
     if (smem) {
       const size_t bytes = (size_t)top_k * HEAP_BLOCK * sizeof(HeapEntry);
-      WALT_CUDA_TRY(cudaFuncSetAttribute(pe_heap_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      if (int rc = allow_dynamic_smem((const void*)pe_heap_kernel<true>, bytes)) return rc;
       pe_heap_kernel<true><<<blocks, HEAP_BLOCK, bytes, st>>>(h);
     } else {
       pe_heap_kernel<false><<<blocks, HEAP_BLOCK, 0, st>>>(h);
