@@ -49,6 +49,10 @@ void walt_batch_free(walt_batch* b);
  * non-ACGT character replaced by "ACGT"[rand() % 4] in file order).  Returns the number of
  * reads loaded, or -1 on error. */
 int64_t walt_fastq_next_batch(walt_fastq* f, walt_batch* b, uint32_t max_reads, const char* adaptor);
+/* The same in pieces: a batch of N reads loaded as consecutive parts is the same batch if the first part
+ * restarts the rand() stream (restart_rand != 0) and the others carry it on -- the parts can then be
+ * mapped and written while the next ones are loaded (walt_main.cpp). */
+int64_t walt_fastq_next_part(walt_fastq* f, walt_batch* b, uint32_t max_reads, const char* adaptor, int restart_rand);
 uint32_t walt_batch_size(const walt_batch* b);
 /* concatenated sequences + offsets[n+1]: the layout walt_engine_map_se/pe take */
 const char* walt_batch_seqs(const walt_batch* b);

@@ -31,6 +31,7 @@ def load_library():
         L.walt_chroms_name.restype = C.c_char_p
         L.walt_chroms_lengths.restype = C.POINTER(C.c_uint32)
         L.walt_fastq_next_batch.restype = C.c_int64
+        L.walt_fastq_next_part.restype = C.c_int64
         L.walt_batch_size.restype = C.c_uint32
         L.walt_chroms_count.restype = C.c_uint32
         L.walt_clip_adaptor.restype = C.c_size_t
@@ -98,6 +99,16 @@ class Batch:
         seqs = np.ctypeslib.as_array(C.cast(self.L.walt_batch_seqs(self.h), C.POINTER(C.c_uint8)), shape=(total,))
         return seqs, offs
 
+    def packed(self):
+        """-> the loader's 2-bit form of the batch (uint8 view, walt_pack_reads layout), valid until the next load"""
+        n = len(self)
+        offs = np.ctypeslib.as_array(C.cast(self.L.walt_batch_offsets(self.h), C.POINTER(C.c_uint64)), shape=(n + 1,))
+        nbytes = int(self.L.walt_packed_reads_bytes(_p(offs), C.c_uint32(n)))
+        ptr = self.L.walt_batch_packed(self.h)
+        if not ptr:
+            raise _err()
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(nbytes,))
+
     def name(self, i):
         return self.L.walt_batch_name(self.h, C.c_uint32(i)).decode()
 
@@ -120,6 +131,13 @@ class Fastq:
 
     def next_batch(self, batch, max_reads, adaptor=""):
         n = self.L.walt_fastq_next_batch(self.h, batch.h, C.c_uint32(max_reads), adaptor.encode())
+        if n < 0:
+            raise _err()
+        return int(n)
+
+    def next_part(self, batch, max_reads, adaptor="", restart_rand=False):
+        """A batch in pieces: the first part restarts the rand() stream of the N replacement, the others carry it on."""
+        n = self.L.walt_fastq_next_part(self.h, batch.h, C.c_uint32(max_reads), adaptor.encode(), C.c_int(1 if restart_rand else 0))
         if n < 0:
             raise _err()
         return int(n)

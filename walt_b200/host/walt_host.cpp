@@ -28,6 +28,9 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include <algorithm>
 #include <atomic>
@@ -92,7 +95,7 @@ struct Sink {
   uint64_t file_off = 0;
   char* buf = nullptr;
   size_t n = 0, cap = 0;
-  bool write_failed = false;
+  std::atomic<bool> write_failed{false};
   Sink() = default;
   Sink(const Sink&) = delete;
   Sink& operator=(const Sink&) = delete;
@@ -129,16 +132,26 @@ struct Sink {
     if (fd >= 0 && n) { if (!write_all(fd, buf, n, file_off)) write_failed = true; file_off += n; n = 0; }
   }
   void maybe_flush() { if (fd >= 0 && n > (1u << 20) - 4096) flush(); }   // no file: an in-memory block
-  // a block formatted elsewhere goes behind everything written so far.  (Writes to one file
-  // serialise on the inode lock, so handing them to more threads gains nothing: the committing
-  // thread writes while the worker threads format the following blocks.)
-  void append_block(Sink& block) {
+  // A block formatted elsewhere goes behind everything written so far -- in two steps, so that only the
+  // first one is ordered: reserve() (blocks in input order, one at a time) gives the block its place in
+  // the file, write_reserved() (any thread, any order, concurrently) puts it there.  One writer thread
+  // moves about 1 GB/s into the page cache (5 GB/s on the GPU boxes) whatever formats the blocks;
+  // writes at known offsets from several threads add up on the file systems that let them.
+  Sink* dest = nullptr;    // of a block: the file it was reserved in
+  uint64_t at = 0;         // ... and where
+  void reserve(Sink& block) {
+    block.dest = nullptr;
     if (!block.n) return;
     if (fd < 0) { memcpy(room(block.n), block.buf, block.n); n += block.n; return; }
     flush();
-    if (!write_all(fd, block.buf, block.n, file_off)) write_failed = true;
+    block.dest = this; block.at = file_off;
     file_off += block.n;
   }
+  void write_reserved() {
+    if (dest && n && !write_all(dest->fd, buf, n, at)) dest->write_failed = true;
+    dest = nullptr;
+  }
+  void append_block(Sink& block) { reserve(block); block.write_reserved(); }
   bool close() {
     flush();
     if (fd >= 0 && ::close(fd) != 0) write_failed = true;
@@ -187,6 +200,13 @@ struct walt_fastq {
   bool mapped = false;
   std::vector<char> heap;
   double bytes_per_line = 90.0; // running estimate, sizes the window scanned for one batch
+  struct random_data rd;        // the rand() stream of toACGT (srand(0) at the start of every batch, mapping.cpp:73)
+  char rd_state[128];
+  walt_fastq() { restart_rand(); }
+  void restart_rand() {
+    memset(&rd, 0, sizeof rd);
+    initstate_r(0, rd_state, sizeof rd_state, &rd);
+  }
 };
 
 // uninitialised growable byte buffer (std::string would zero-fill gigabytes on resize)
@@ -209,12 +229,26 @@ struct RawBuf {
   }
 };
 
+// n + 1 offsets, uninitialised like RawBuf (a std::vector would zero 80 MB per array of a 10 M read batch on one thread)
+struct OffBuf {
+  RawBuf raw;
+  OffBuf() { resize(1); (*this)[0] = 0; }
+  bool resize(size_t n) { return raw.size_to(n * sizeof(uint64_t)); }
+  uint64_t& operator[](size_t i) { return reinterpret_cast<uint64_t*>(raw.p)[i]; }
+  const uint64_t& operator[](size_t i) const { return reinterpret_cast<const uint64_t*>(raw.p)[i]; }
+  const uint64_t* data() const { return reinterpret_cast<const uint64_t*>(raw.p); }
+};
+
 struct walt_batch {
   RawBuf seqs, quals, names, packed;                   // names/quals hold NUL-terminated copies
-  std::vector<uint64_t> seq_off, qual_off, name_off;   // n + 1 each
-  bool have_packed = false;                            // 2-bit form of seqs (walt_batch_packed), built on demand
+  OffBuf seq_off, qual_off, name_off;                  // n + 1 each
+  bool have_packed = false;                            // 2-bit form of seqs (walt_batch_packed): the loader leaves it behind
   uint32_t n = 0;
-  void clear() { seqs.n = quals.n = names.n = packed.n = 0; have_packed = false; seq_off.assign(1, 0); qual_off.assign(1, 0); name_off.assign(1, 0); n = 0; }
+  void clear() {
+    seqs.n = quals.n = names.n = packed.n = 0; have_packed = false; n = 0;
+    seq_off.resize(1); qual_off.resize(1); name_off.resize(1);
+    seq_off[0] = qual_off[0] = name_off[0] = 0;
+  }
   const char* seq(uint32_t i) const { return seqs.p + seq_off[i]; }
   uint32_t seq_len(uint32_t i) const { return (uint32_t)(seq_off[i + 1] - seq_off[i]); }
   const char* qual(uint32_t i) const { return quals.p + qual_off[i]; }
@@ -343,64 +377,72 @@ void sam_header(Sink& o, const walt_chroms& g) {
 
 namespace {
 
-// Formats reads [0, n) in blocks on worker threads and commits the blocks in input order on
-// the calling thread, which therefore overlaps the file writes with the formatting.
+// Formats reads [0, n) in blocks on worker threads; the blocks get their places in the files in input
+// order, and are written there by whichever thread got them their place.
 //   make()            -> a fresh block-local output (in-memory sinks, zeroed counters)
-//   fmt(block, lo, hi)   formats reads [lo, hi) into it        (worker threads)
-//   commit(block)        appends it to the files / totals      (calling thread, ascending order)
-template <class Block, class Make, class Fmt, class Commit>
-void ordered_blocks(uint32_t n, Make make, Fmt fmt, Commit commit) {
+//   reset(block)         ... the same from a used one (its buffers keep their pages)
+//   fmt(block, lo, hi)   formats reads [lo, hi) into it                           (any thread)
+//   reserve(block)       file offsets for its sinks, its counters into the totals (ascending order, one at a time)
+//   write(block)         its sinks into the files at those offsets                (any thread)
+template <class Block, class Make, class Reset, class Fmt, class Reserve, class Write>
+void ordered_blocks(uint32_t n, Make make, Reset reset, Fmt fmt, Reserve reserve, Write write) {
   const uint32_t BLOCK = g_block_reads.load();
   const size_t nb = ((size_t)n + BLOCK - 1) / BLOCK;
   const size_t T = std::min<size_t>(host_threads(), nb);
   if (T <= 1) {
+    std::unique_ptr<Block> bl;
     for (size_t k = 0; k < nb; ++k) {
-      std::unique_ptr<Block> bl(make());
+      if (bl) reset(*bl); else bl.reset(make());
       fmt(*bl, (uint32_t)(k * BLOCK), (uint32_t)std::min<size_t>(n, (k + 1) * BLOCK));
-      commit(*bl);
+      reserve(*bl);
+      write(*bl);
     }
     return;
   }
   std::mutex mu;
-  std::condition_variable cv_ready, cv_room;
-  std::map<size_t, std::unique_ptr<Block>> ready;
+  std::condition_variable cv_room;
+  std::map<size_t, std::unique_ptr<Block>> ready;      // formatted, waiting for the blocks before them
+  std::vector<std::unique_ptr<Block>> spare;           // written: their buffers are reused
   size_t next_commit = 0;
   std::atomic<size_t> next_task{0};
   const size_t window = 4 * T;   // blocks formatted ahead of the commit point (bounds memory)
-  std::vector<std::thread> th;
-  for (size_t t = 0; t < T; ++t)
-    th.emplace_back([&]() {
-      for (;;) {
-        const size_t k = next_task.fetch_add(1);
-        if (k >= nb) return;
-        {
-          std::unique_lock<std::mutex> lk(mu);
-          cv_room.wait(lk, [&]() { return k < next_commit + window; });
-        }
-        std::unique_ptr<Block> bl(make());
-        fmt(*bl, (uint32_t)(k * BLOCK), (uint32_t)std::min<size_t>(n, (k + 1) * BLOCK));
-        {
-          std::lock_guard<std::mutex> lk(mu);
-          ready[k] = std::move(bl);
-        }
-        cv_ready.notify_one();
+  auto body = [&]() {
+    std::vector<std::unique_ptr<Block>> mine;
+    for (;;) {
+      const size_t k = next_task.fetch_add(1);
+      if (k >= nb) return;
+      std::unique_ptr<Block> bl;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_room.wait(lk, [&]() { return k < next_commit + window; });
+        if (!spare.empty()) { bl = std::move(spare.back()); spare.pop_back(); }
       }
-    });
-  for (size_t k = 0; k < nb; ++k) {
-    std::unique_ptr<Block> bl;
-    {
-      std::unique_lock<std::mutex> lk(mu);
-      cv_ready.wait(lk, [&]() { return ready.count(k) != 0; });
-      bl = std::move(ready[k]);
-      ready.erase(k);
+      if (bl) reset(*bl); else bl.reset(make());
+      fmt(*bl, (uint32_t)(k * BLOCK), (uint32_t)std::min<size_t>(n, (k + 1) * BLOCK));
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        ready[k] = std::move(bl);
+        // the thread that completes the prefix gives every block of it its place ...
+        for (auto it = ready.find(next_commit); it != ready.end(); it = ready.find(next_commit)) {
+          reserve(*it->second);
+          mine.push_back(std::move(it->second));
+          ready.erase(it);
+          ++next_commit;
+        }
+      }
+      if (mine.empty()) continue;
+      cv_room.notify_all();
+      for (auto& m : mine) write(*m);                  // ... and writes them, beside the other threads' writes
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto& m : mine) spare.push_back(std::move(m));
+      }
+      mine.clear();
     }
-    commit(*bl);
-    {
-      std::lock_guard<std::mutex> lk(mu);
-      next_commit = k + 1;
-    }
-    cv_room.notify_all();
-  }
+  };
+  std::vector<std::thread> th;
+  for (size_t t = 1; t < T; ++t) th.emplace_back(body);
+  body();
   for (auto& t : th) t.join();
 }
 
@@ -409,10 +451,12 @@ void add_stats(SingleStats& a, const SingleStats& b) {
 }
 // block-local twin of a SingleOut: same flags, in-memory side files, zero counters
 void local_twin(SingleOut& l, const SingleOut& of) { l.ambiguous = of.ambiguous; l.unmapped = of.unmapped; l.sam = of.sam; }
-void commit_twin(SingleOut& to, SingleOut& l) {
-  to.famb.append_block(l.famb); to.funm.append_block(l.funm);
+void reset_twin(SingleOut& l) { l.famb.n = l.funm.n = 0; l.st = SingleStats(); }
+void reserve_twin(SingleOut& to, SingleOut& l) {
+  to.famb.reserve(l.famb); to.funm.reserve(l.funm);
   add_stats(to.st, l.st);
 }
+void write_twin(SingleOut& l) { l.famb.write_reserved(); l.funm.write_reserved(); }
 
 struct SeBlock { Sink out; SingleOut so; };
 
@@ -689,12 +733,94 @@ struct RecRef {            // the four lines of one record inside the file
   uint16_t name_len, seq_len, qual_len;
 };
 
+// Every surviving piece of [p, end) in file order, emit(start, len): what next_line() returns in a loop, found
+// 16 bytes at a time.  The common piece -- a newline within 999 bytes, no NUL in front of it -- never
+// leaves the vector loop; anything else goes through next_piece().  `end` is a physical line start or
+// the end of the file; 16-byte loads stay in front of `safe_end` (the end of the file).
+template <class Emit>
+void scan_pieces(const char* p, const char* end, const char* safe_end, Emit&& emit) {
+  const char* line = p;
+  auto exact = [&]() {
+    Piece pc;
+    next_piece(line, end, pc);
+    if (pc.len) emit(pc.s, pc.len);
+    line = pc.next;
+  };
+#if defined(__SSE2__)
+  const __m128i nl = _mm_set1_epi8('\n'), zero = _mm_setzero_si128();
+  for (const char* b = p; b < end && b + 16 <= safe_end; b += 16) {
+    const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(b));
+    unsigned m = (unsigned)_mm_movemask_epi8(_mm_or_si128(_mm_cmpeq_epi8(v, nl), _mm_cmpeq_epi8(v, zero)));
+    while (m) {
+      const char* q = b + __builtin_ctz(m);
+      m &= m - 1;
+      if (q >= end) break;
+      while (q >= line) {     // (q < line: inside a piece that took the exact path)
+        if (*q == '\n' && (size_t)(q - line) < LINE_CAP - 1) {
+          if (q != line) emit(line, (uint32_t)(q - line));
+          line = q + 1;
+        } else {
+          exact();              // a NUL, or a piece that fgets cuts off: it may end in front of q
+        }
+      }
+    }
+    while (line < end && (size_t)(b + 16 - line) >= LINE_CAP - 1) exact();   // 999 bytes without a newline
+  }
+#else
+  (void)safe_end;
+#endif
+  while (line < end) exact();
+}
+
+// 16 sequence bytes at a time: a bit for every byte that is not A, C, G or T
+inline unsigned not_acgt16(const char* s) {
+#if defined(__SSE2__)
+  const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s));
+  const __m128i ok = _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(v, _mm_set1_epi8('A')), _mm_cmpeq_epi8(v, _mm_set1_epi8('C'))),
+                                  _mm_or_si128(_mm_cmpeq_epi8(v, _mm_set1_epi8('G')), _mm_cmpeq_epi8(v, _mm_set1_epi8('T'))));
+  return ~(unsigned)_mm_movemask_epi8(ok) & 0xFFFFu;
+#else
+  unsigned m = 0;
+  for (unsigned t = 0; t < 16; ++t) { const char c = s[t]; if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T')) m |= 1u << t; }
+  return m;
+#endif
+}
+
+struct Mark { uint64_t at, packed_at; uint32_t shift; };   // a character toACGT replaces: where in seqs, where in the 2-bit form
+
+inline uint32_t codes_of4(uint32_t w) {       // see walt_pack_reads
+  const uint32_t x = (w >> 1) & 0x03030303u;
+  return x ^ ((x >> 1) & 0x01010101u);
+}
+// the 2-bit form of one read, whatever its bytes are (a byte that is not ACGT leaves two bits that its Mark overwrites)
+inline void pack_one(const char* s, uint32_t len, uint8_t* o) {
+  uint32_t i = 0;
+  for (; i + 4 <= len; i += 4) {
+    uint32_t w;
+    memcpy(&w, s + i, 4);
+    *o++ = (uint8_t)((codes_of4(w) * 0x40100401u) >> 24);
+  }
+  if (i < len) {
+    unsigned v = 0;
+    for (uint32_t t = 0; i + t < len; ++t) {
+      const unsigned c = (unsigned char)s[i + t], x = (c >> 1) & 3u;
+      v |= (x ^ (x >> 1)) << (6u - 2u * t);
+    }
+    *o = (uint8_t)v;
+  }
+}
+
 }  // namespace
 
 extern "C" {
 
 int64_t walt_fastq_next_batch(walt_fastq* fq, walt_batch* b, uint32_t max_reads, const char* adaptor) {
+  return walt_fastq_next_part(fq, b, max_reads, adaptor, 1);
+}
+
+int64_t walt_fastq_next_part(walt_fastq* fq, walt_batch* b, uint32_t max_reads, const char* adaptor, int restart_rand) {
   if (!fq || !b) return fail("bad argument");
+  if (restart_rand) fq->restart_rand();
   b->clear();
   const uint64_t lim = (uint64_t)max_reads * 4u;   // lines, mapping.cpp:78
   const bool clip = adaptor && adaptor[0];
@@ -702,11 +828,12 @@ int64_t walt_fastq_next_batch(walt_fastq* fq, walt_batch* b, uint32_t max_reads,
   const char* const base = fq->data;
   const char* const file_end = base + fq->size;
 
-  // ---- 1. a window [lo, hi) that holds the batch's lines, split at physical line starts ----
+  // ---- 1. a window [lo, hi) that holds the batch's lines, cut at physical line starts; every chunk lists its lines ----
   const char* lo = base + fq->pos;
   const char* hi = lo;
   std::vector<const char*> cut;       // chunk boundaries, cut.front() == lo, cut.back() == hi
   std::vector<uint64_t> first_line;   // index of the first surviving line of each chunk (+ total)
+  std::vector<std::vector<uint64_t>> lines;   // per chunk: (start - lo) << 16 | length, for every surviving piece
   uint64_t total = 0;
   double want = (double)lim * fq->bytes_per_line * 1.1 + 65536.0;
   for (;;) {
@@ -728,16 +855,14 @@ int64_t walt_fastq_next_batch(walt_fastq* fq, walt_batch* b, uint32_t max_reads,
       }
       cut[i] = c;
     }
-    std::vector<uint64_t> cnt(K, 0);
+    lines.assign(K, std::vector<uint64_t>());
     parallel_tasks(K, [&](size_t i) {
-      const char* p = cut[i];
-      Piece pc;
-      uint64_t c = 0;
-      while (next_line(p, cut[i + 1], pc)) ++c;
-      cnt[i] = c;
+      std::vector<uint64_t>& out = lines[i];
+      out.reserve((size_t)((double)(cut[i + 1] - cut[i]) / fq->bytes_per_line * 1.05) + 16u);
+      scan_pieces(cut[i], cut[i + 1], file_end, [&](const char* st, uint32_t len) { out.push_back((uint64_t)(st - lo) << 16 | len); });
     });
     first_line.assign(K + 1, 0);
-    for (size_t i = 0; i < K; ++i) first_line[i + 1] = first_line[i] + cnt[i];
+    for (size_t i = 0; i < K; ++i) first_line[i + 1] = first_line[i] + lines[i].size();
     total = first_line[K];
     if (total >= lim || hi == file_end) break;
     want *= 2.0;
@@ -747,99 +872,117 @@ int64_t walt_fastq_next_batch(walt_fastq* fq, walt_batch* b, uint32_t max_reads,
   const uint64_t n_rec = take / 4u;   // a trailing partial record is never committed (mapping.cpp:104-108)
   if (total) fq->bytes_per_line = std::max(16.0, (double)(hi - lo) / (double)total);
 
-  // where the next batch starts: behind line take-1 (behind the window if it was used up)
-  if (take == total) {
-    fq->pos = (size_t)(hi - base);
-  } else {
-    size_t j = 0;
-    while (first_line[j + 1] <= take - 1) ++j;
-    const char* p = cut[j];
-    Piece pc;
-    for (uint64_t k = first_line[j]; k <= take - 1; ++k) next_line(p, cut[j + 1], pc);
-    fq->pos = (size_t)(pc.next - base);
-  }
+  // line g of the window (g < total), looked for from chunk c on
+  auto line_at = [&](uint64_t g, size_t c) -> uint64_t {
+    while (g >= first_line[c + 1]) ++c;
+    return lines[c][(size_t)(g - first_line[c])];
+  };
+  // where the next batch starts: at the first line behind the ones taken (the empty pieces in between are
+  // skipped either way), behind the window if it was used up
+  fq->pos = take == total ? (size_t)(hi - base) : (size_t)(lo - base) + (size_t)(line_at(take, 0) >> 16);
   if (n_rec == 0) return 0;
 
-  // ---- 2. record table: every chunk emits the records that START in it ----
+  // ---- 2. record table: every chunk emits the records that START in it, and how much room they need ----
   std::vector<std::vector<RecRef>> recs(K);
+  struct Room { uint64_t seq = 0, qual = 0, name = 0; };
+  std::vector<Room> room(K + 1);
   parallel_tasks(K, [&](size_t i) {
     const uint64_t g0 = first_line[i], g1 = std::min<uint64_t>(first_line[i + 1], n_rec * 4u);
     uint64_t g = g0 + (4u - g0 % 4u) % 4u;   // first record boundary at or behind the chunk start
     if (g >= g1) return;
-    const char* p = cut[i];
-    Piece pc;
-    for (uint64_t k = g0; k < g; ++k) next_line(p, hi, pc);
     std::vector<RecRef>& out = recs[i];
     out.reserve((size_t)((g1 - g + 3u) / 4u));
+    Room rm;
     for (; g < g1; g += 4u) {
-      Piece l0, l1, l2, l3;
-      next_line(p, hi, l0); next_line(p, hi, l1); next_line(p, hi, l2); next_line(p, hi, l3);
+      const uint64_t l0 = lines[i][(size_t)(g - g0)];
+      const bool inside = g + 3u < first_line[i + 1];   // (the last record of a chunk may end in the next ones)
+      const uint64_t l1 = inside ? lines[i][(size_t)(g + 1 - g0)] : line_at(g + 1, i);
+      const uint64_t l3 = inside ? lines[i][(size_t)(g + 3 - g0)] : line_at(g + 3, i);
+      const char* s0 = lo + (l0 >> 16);
+      const uint32_t len0 = (uint32_t)(l0 & 0xFFFFu);
       // mapping.cpp:86-92: substr(1) or substr(1, space_pos - 1); a leading space makes the count npos
-      const char* sp = (const char*)memchr(l0.s, ' ', l0.len);
-      const uint32_t name_end = (sp && sp != l0.s) ? (uint32_t)(sp - l0.s) : l0.len;
+      const char* sp = (const char*)memchr(s0, ' ', len0);
+      const uint32_t name_end = (sp && sp != s0) ? (uint32_t)(sp - s0) : len0;
       RecRef r;
-      r.name = (uint64_t)(l0.s + 1 - base);
+      r.name = (uint64_t)(s0 + 1 - base);
       r.name_len = (uint16_t)(name_end - 1u);
-      r.seq_delta = (uint32_t)(l1.s - (l0.s + 1)); r.seq_len = (uint16_t)l1.len;
-      r.qual_delta = (uint32_t)(l3.s - (l0.s + 1)); r.qual_len = (uint16_t)l3.len;
+      r.seq_delta = (uint32_t)((l1 >> 16) - (l0 >> 16) - 1u); r.seq_len = (uint16_t)(l1 & 0xFFFFu);
+      r.qual_delta = (uint32_t)((l3 >> 16) - (l0 >> 16) - 1u); r.qual_len = (uint16_t)(l3 & 0xFFFFu);
       out.push_back(r);
+      rm.seq += r.seq_len; rm.qual += (uint64_t)r.qual_len + 1u; rm.name += (uint64_t)r.name_len + 1u;
     }
+    room[i] = rm;
   });
+  lines.clear(); lines.shrink_to_fit();
 
-  // ---- 3. output offsets (serial prefix sums), then the copies in parallel ----
+  // ---- 3. where every chunk's records go (a prefix sum over the chunks), then offsets, copies, the 2-bit form
+  //         and the characters toACGT will replace, chunk by chunk in parallel ----
   b->n = (uint32_t)n_rec;
-  b->seq_off.resize(n_rec + 1); b->qual_off.resize(n_rec + 1); b->name_off.resize(n_rec + 1);
   std::vector<size_t> rec_base(K + 1, 0);
   {
-    uint64_t so = 0, qo = 0, no = 0;
-    size_t j = 0;
+    Room at;
     for (size_t i = 0; i < K; ++i) {
-      rec_base[i] = j;
-      for (const RecRef& r : recs[i]) {
-        b->seq_off[j] = so; b->qual_off[j] = qo; b->name_off[j] = no;
-        so += r.seq_len; qo += (uint64_t)r.qual_len + 1u; no += (uint64_t)r.name_len + 1u;
-        ++j;
-      }
+      const Room mine = room[i];
+      room[i] = at;
+      at.seq += mine.seq; at.qual += mine.qual; at.name += mine.name;
+      rec_base[i + 1] = rec_base[i] + recs[i].size();
     }
-    rec_base[K] = j;
-    b->seq_off[j] = so; b->qual_off[j] = qo; b->name_off[j] = no;
-    if (j != n_rec) return fail("internal error: FASTQ record table out of step");
-    if (!b->seqs.size_to(so) || !b->quals.size_to(qo) || !b->names.size_to(no)) return fail("ERROR: could not allocate memory");
+    room[K] = at;
+    if (rec_base[K] != n_rec) return fail("internal error: FASTQ record table out of step");
+    if (!b->seq_off.resize(n_rec + 1) || !b->qual_off.resize(n_rec + 1) || !b->name_off.resize(n_rec + 1) ||
+        !b->seqs.size_to(at.seq) || !b->quals.size_to(at.qual) || !b->names.size_to(at.name) ||
+        !b->packed.size_to((at.seq >> 2) + n_rec + 16u))
+      return fail("ERROR: could not allocate memory");
+    b->seq_off[n_rec] = at.seq; b->qual_off[n_rec] = at.qual; b->name_off[n_rec] = at.name;
   }
-  std::vector<std::vector<uint64_t>> marks(K);   // offsets in b->seqs of the characters toACGT replaces
+  std::vector<std::vector<Mark>> marks(K);
   parallel_tasks(K, [&](size_t i) {
     size_t j = rec_base[i];
-    std::vector<uint64_t>& mk = marks[i];
+    Room at = room[i];
+    std::vector<Mark>& mk = marks[i];
+    uint8_t* const packed = reinterpret_cast<uint8_t*>(b->packed.p);
     for (const RecRef& r : recs[i]) {
+      b->seq_off[j] = at.seq; b->qual_off[j] = at.qual; b->name_off[j] = at.name;
       const char* nm = base + r.name;
-      char* dn = b->names.p + b->name_off[j];
+      char* dn = b->names.p + at.name;
       memcpy(dn, nm, r.name_len); dn[r.name_len] = 0;
-      char* dq = b->quals.p + b->qual_off[j];
+      char* dq = b->quals.p + at.qual;
       memcpy(dq, nm + r.qual_delta, r.qual_len); dq[r.qual_len] = 0;
-      char* ds = b->seqs.p + b->seq_off[j];
-      memcpy(ds, nm + r.seq_delta, r.seq_len);
-      if (clip) walt_clip_adaptor(adaptor, ds, r.seq_len);
-      for (uint32_t t = 0; t < r.seq_len; ++t) {
+      char* ds = b->seqs.p + at.seq;
+      const uint32_t len = r.seq_len;
+      memcpy(ds, nm + r.seq_delta, len);
+      if (clip) walt_clip_adaptor(adaptor, ds, len);
+      // read j of the 2-bit form: ceil(len / 4) bytes from byte (offset >> 2) + j, zeros up to the next read's
+      const uint64_t pk = (at.seq >> 2) + j, pk_next = ((at.seq + len) >> 2) + j + 1u;
+      pack_one(ds, len, packed + pk);
+      for (uint64_t z = pk + (len + 3u) / 4u; z < pk_next; ++z) packed[z] = 0;
+      uint32_t t = 0;
+      for (; t + 16u <= len; t += 16u)
+        for (unsigned m = not_acgt16(ds + t); m; m &= m - 1) {
+          const uint32_t u = t + (uint32_t)__builtin_ctz(m);
+          mk.push_back(Mark{at.seq + u, pk + (u >> 2), 6u - 2u * (u & 3u)});
+        }
+      for (; t < len; ++t) {
         const char c = ds[t];
-        if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T')) mk.push_back(b->seq_off[j] + t);
+        if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T')) mk.push_back(Mark{at.seq + t, pk + (t >> 2), 6u - 2u * (t & 3u)});
       }
+      at.seq += len; at.qual += (uint64_t)r.qual_len + 1u; at.name += (uint64_t)r.name_len + 1u;
       ++j;
     }
   });
+  memset(b->packed.p + b->packed.n - 16, 0, 16);
 
-  // ---- 4. toACGT (util.hpp:156-163) in file order on the srand(0) stream (mapping.cpp:73) ----
-  {
-    struct random_data rd;
-    char state[128];
-    memset(&rd, 0, sizeof rd);
-    initstate_r(0, state, sizeof state, &rd);
-    for (size_t i = 0; i < K; ++i)
-      for (const uint64_t at : marks[i]) {
-        int32_t r = 0;
-        random_r(&rd, &r);
-        b->seqs.p[at] = "ACGT"[r % 4];
-      }
-  }
+  // ---- 4. toACGT (util.hpp:156-163) in file order on the batch's rand() stream (mapping.cpp:73) ----
+  for (size_t i = 0; i < K; ++i)
+    for (const Mark& mk : marks[i]) {
+      int32_t r = 0;
+      random_r(&fq->rd, &r);
+      const unsigned code = (unsigned)(r % 4);               // codes A0 C1 G2 T3 are the indices of "ACGT"
+      b->seqs.p[mk.at] = "ACGT"[code];
+      uint8_t& byte = reinterpret_cast<uint8_t*>(b->packed.p)[mk.packed_at];
+      byte = (uint8_t)((byte & ~(3u << mk.shift)) | (code << mk.shift));
+    }
+  b->have_packed = true;
   return b->n;
 }
 
@@ -849,10 +992,6 @@ uint64_t walt_packed_reads_bytes(const uint64_t* offs, uint32_t n) { return (off
 // into the lower: x = (c >> 1) & 3, code = x ^ (x >> 1).  Four letters at a time: the four codes sit
 // in the low bits of the four bytes of a word; one multiply gathers them into a byte, first letter
 // in the top bits.  Validation is the same arithmetic run backwards ("ACGT"[code] == letter).
-static inline uint32_t codes_of4(uint32_t w) {
-  const uint32_t x = (w >> 1) & 0x03030303u;
-  return x ^ ((x >> 1) & 0x01010101u);
-}
 static inline uint32_t letters_of4(uint32_t code) {   // "ACGT"[code] per byte: 0x41 + {0, 2, 6, 0x13}
   const uint32_t lo = code & 0x01010101u, hi = (code >> 1) & 0x01010101u;
   return 0x41414141u + lo * 2u + hi * 6u + (lo & hi) * 0x0Bu;
@@ -941,6 +1080,7 @@ int walt_se_writer_write(walt_se_writer* w, const walt_batch* b, const walt_best
   ordered_blocks<SeBlock>(
       n,
       [&]() { SeBlock* bl = new SeBlock; local_twin(bl->so, w->so); return bl; },
+      [&](SeBlock& bl) { bl.out.n = 0; reset_twin(bl.so); },
       [&](SeBlock& bl, uint32_t lo, uint32_t hi) {
         for (uint32_t j = lo; j < hi; ++j) {
           bl.so.st.update(res[j].times);
@@ -948,7 +1088,8 @@ int walt_se_writer_write(walt_se_writer* w, const walt_batch* b, const walt_best
           else mr_single(bl.out, bl.so, *w->g, res[j], b->name(j), b->name_len(j), b->seq(j), b->qual(j), b->seq_len(j), b->qual_len(j), w->ag);
         }
       },
-      [&](SeBlock& bl) { w->out.append_block(bl.out); commit_twin(w->so, bl.so); });
+      [&](SeBlock& bl) { w->out.reserve(bl.out); reserve_twin(w->so, bl.so); },
+      [&](SeBlock& bl) { bl.out.write_reserved(); write_twin(bl.so); });
   return 0;
 }
 
@@ -1056,12 +1197,18 @@ static PeOut* pe_block(const walt_pe_writer* w) {
   bl->frag_count.assign(w->o.frag_count.size(), 0);
   return bl;
 }
-static void pe_commit(walt_pe_writer* w, PeOut& bl) {
-  w->o.out.append_block(bl.out);
-  commit_twin(w->o.so1, bl.so1); commit_twin(w->o.so2, bl.so2);
+static void pe_reset(PeOut& bl) {
+  bl.out.n = 0; reset_twin(bl.so1); reset_twin(bl.so2);
+  bl.unique_pairs = bl.ambiguous_pairs = bl.unmapped_pairs = 0;
+  std::fill(bl.frag_count.begin(), bl.frag_count.end(), 0u);
+}
+static void pe_reserve(walt_pe_writer* w, PeOut& bl) {
+  w->o.out.reserve(bl.out);
+  reserve_twin(w->o.so1, bl.so1); reserve_twin(w->o.so2, bl.so2);
   w->o.unique_pairs += bl.unique_pairs; w->o.ambiguous_pairs += bl.ambiguous_pairs; w->o.unmapped_pairs += bl.unmapped_pairs;
   for (size_t i = 0; i < bl.frag_count.size(); ++i) w->o.frag_count[i] += bl.frag_count[i];
 }
+static void pe_write(PeOut& bl) { bl.out.write_reserved(); write_twin(bl.so1); write_twin(bl.so2); }
 
 int walt_pe_writer_write_compact(walt_pe_writer* w, const walt_batch* b1, const walt_batch* b2, const walt_pe_result* res,
                                  uint32_t n) {
@@ -1069,8 +1216,9 @@ int walt_pe_writer_write_compact(walt_pe_writer* w, const walt_batch* b1, const 
   w->total_pairs += n;
   ordered_blocks<PeOut>(
       n, [&]() { return pe_block(w); },
+      pe_reset,
       [&](PeOut& bl, uint32_t lo, uint32_t hi) { for (uint32_t j = lo; j < hi; ++j) write_pair(w, bl, b1, b2, j, res[j]); },
-      [&](PeOut& bl) { pe_commit(w, bl); });
+      [&](PeOut& bl) { pe_reserve(w, bl); }, pe_write);
   return 0;
 }
 
@@ -1080,7 +1228,7 @@ int walt_pe_writer_write(walt_pe_writer* w, const walt_batch* b1, const walt_bat
   if (!w || !b1 || !b2 || n > b1->n || n > b2->n) return fail("bad argument");
   w->total_pairs += n;
   ordered_blocks<PeOut>(
-      n, [&]() { return pe_block(w); },
+      n, [&]() { return pe_block(w); }, pe_reset,
       [&](PeOut& bl, uint32_t lo, uint32_t hi) {
         for (uint32_t j = lo; j < hi; ++j) {
           // the summary the device computes in the compact path, derived here from the ranked lists
@@ -1095,7 +1243,7 @@ int walt_pe_writer_write(walt_pe_writer* w, const walt_batch* b1, const walt_bat
           write_pair(w, bl, b1, b2, j, r);
         }
       },
-      [&](PeOut& bl) { pe_commit(w, bl); });
+      [&](PeOut& bl) { pe_reserve(w, bl); }, pe_write);
   return 0;
 }
 

@@ -4,8 +4,9 @@
 // -C -A -b -k -L -sam -v -t, single-dash long names, comma separated file lists, one shared or
 // one-per-input output name, truncation of outputs at start, exit codes) plus -P/-pbat and
 // -gpus.  The batch drivers (mapping.cpp:421-526, paired.cpp:572-713) become:
-//   load index ONCE into HBM -> per batch { load FASTQ (walt_host) -> walt_engine_map_se/pe on
-//   the GPU(s) -> write SAM/MR (walt_host) } -> mapstats.
+//   load index ONCE into HBM (beside the first reads' load) -> per part of a batch, three parts under way
+//   at a time { load FASTQ (walt_host) | walt_group_map_se/pe on the GPU(s) | write SAM/MR (walt_host) }
+//   -> mapstats.
 // Mapping has no CPU implementation here: without a CUDA device the program exits 1.
 #include <stdio.h>
 #include <stdlib.h>
@@ -13,6 +14,9 @@
 #include <sys/stat.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
 #include <fstream>
 #include <iostream>
 #include <sstream>
@@ -20,6 +24,8 @@
 #include <string>
 #include <chrono>
 #include <future>
+#include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -121,13 +127,21 @@ void engine_check(int rc) {
 }
 
 // the GPUs of a run: one engine per device behind one handle (walt_group, include/walt_b200.h), which cuts
-// every batch into contiguous ranges and keeps the results in input order
+// every batch into contiguous ranges and keeps the results in input order.  The engines start
+// (contexts, index files into HBM, replicas) on a thread of their own while the first reads are loaded:
+// ready() is called in front of the first mapping call.
 struct Engines {
   walt_group* g = nullptr;
-  ~Engines() { walt_group_destroy(g); }
+  std::future<void> start;
+  void ready() { if (start.valid()) start.get(); }
+  ~Engines() {
+    if (start.valid()) start.wait();
+    walt_group_destroy(g);
+  }
 };
 
-// stage timings on stderr when WALT_TIMING is set (never part of the outputs)
+// stage timings on stderr when WALT_TIMING is set (never part of the outputs).  The three stages run
+// beside each other on consecutive parts of a batch: each figure is the time its stage was busy.
 struct StageClock {
   bool on = getenv("WALT_TIMING") != nullptr;
   double load = 0, map = 0, write = 0;
@@ -135,31 +149,147 @@ struct StageClock {
   static double since(std::chrono::steady_clock::time_point a) {
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count();
   }
-  void report(const char* what, uint64_t n) const {
-    if (on) fprintf(stderr, "[walt timing] %s: %llu reads, load %.3f s (overlapped with map+write after the first batch), map %.3f s, "
-                            "write %.3f s, total %.3f s, %u host threads\n", what, (unsigned long long)n, load, map, write,
-                    since(t0), walt_host_threads());
+  void report(const char* what, uint64_t n, uint32_t part) const {
+    if (on) fprintf(stderr, "[walt timing] %s: %llu reads in parts of %u, stages overlapped: load %.3f s, map %.3f s (with the wait "
+                            "for the engines), write %.3f s, total %.3f s, %u host threads\n", what, (unsigned long long)n, part,
+                    load, map, write, since(t0), walt_host_threads());
   }
 };
 
-// one loaded batch: the ASCII reads (for the writers) and their 2-bit form (what crosses PCIe)
-struct Loaded { int64_t n = 0; const uint8_t* packed = nullptr; std::string err; double seconds = 0; };
-Loaded load_batch(walt_fastq* fq, walt_batch* b, uint32_t max_reads, const std::string& adaptor) {
-  Loaded l;
-  const auto t = std::chrono::steady_clock::now();
-  l.n = walt_fastq_next_batch(fq, b, max_reads, adaptor.c_str());
-  if (l.n < 0) l.err = walt_host_last_error();
-  if (l.n > 0 && !(l.packed = walt_batch_packed(b))) { l.n = -1; l.err = walt_host_last_error(); }
-  l.seconds = StageClock::since(t);
-  return l;
+// A blocking queue between two stages; close() lets every waiting and later pop() return nullptr.
+template <class T>
+struct Chan {
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<T*> q;
+  bool closed = false, drain = false;
+  void push(T* v) { { std::lock_guard<std::mutex> lk(mu); q.push_back(v); } cv.notify_one(); }
+  T* pop() {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&]() { return closed || !q.empty(); });
+    if (q.empty() || (closed && !drain)) return nullptr;
+    T* v = q.front(); q.pop_front();
+    return v;
+  }
+  // drain_first: what was pushed before is still handed out
+  void close(bool drain_first = false) { { std::lock_guard<std::mutex> lk(mu); closed = true; drain = drain_first; } cv.notify_all(); }
+};
+
+// One part of a batch on its way through load -> map -> write: the reads of one file (two for pairs) as
+// ASCII (for the writers) and in 2-bit form (what crosses PCIe), and the results.
+struct Part {
+  walt_batch* b[2] = {nullptr, nullptr};
+  const uint8_t* packed[2] = {nullptr, nullptr};
+  int64_t n[2] = {0, 0};
+  bool first = false;            // the first part of a batch
+  bool last = false;             // a file ended in this part: nothing follows
+  std::string err;
+  std::vector<walt_best> best;
+  std::vector<walt_pe_result> pairs;
+  uint32_t n_short[2] = {0, 0};
+  explicit Part(int files) { for (int i = 0; i < files; ++i) b[i] = walt_batch_create(); }
+  ~Part() { walt_batch_free(b[0]); walt_batch_free(b[1]); }
+};
+
+// reads per part: a batch (-N reads: one srand(0) stream, mapping.cpp:73) is loaded, mapped and written in
+// parts of this many reads, three parts under way at a time
+uint32_t part_reads(const Settings& s) {
+  const char* v = getenv("WALT_PART_READS");
+  const unsigned long p = v ? strtoul(v, nullptr, 10) : (1ul << 20);
+  return (uint32_t)std::max<unsigned long>(1ul, std::min<unsigned long>(p, std::max<uint32_t>(1u, s.batch)));
 }
 
-void map_se_batch(Engines& eng, const walt_batch* b, const uint8_t* packed, const Settings& s, bool ag,
-                  std::vector<walt_best>& res, uint32_t& n_short) {
-  const uint32_t n = walt_batch_size(b);
-  res.resize(n);
-  n_short = 0;
-  engine_check(walt_group_map_se_packed(eng.g, packed, walt_batch_offsets(b), n, ag ? 1 : 0, s.m, s.b, res.data(), &n_short));
+// The batch loop of both modes (mapping.cpp:421-526, paired.cpp:572-713) as three stages on their own threads:
+//   load   : the next part of each file (both files of a pair side by side)
+//   map    : the calling thread, the engines
+//   write  : the part's lines behind everything written so far
+// `map` returns false to end the run early (paired-end files of unequal length).
+template <class MapFn, class WriteFn>
+uint64_t run_parts(const Settings& s, int files, walt_fastq* const* fq, const std::string* adaptor, StageClock& clk,
+                   MapFn map, WriteFn write) {
+  constexpr int N_PARTS = 4;
+  const uint32_t P = part_reads(s);
+  std::vector<std::unique_ptr<Part>> parts;
+  Chan<Part> free_q, loaded_q, mapped_q;
+  for (int i = 0; i < N_PARTS; ++i) { parts.emplace_back(new Part(files)); free_q.push(parts.back().get()); }
+  std::string write_err;
+  std::atomic<bool> write_failed{false};
+
+  std::thread loader([&]() {
+    uint32_t left = s.batch;                       // reads of the current batch still to load
+    auto load = [&](Part* p, int f, uint32_t want, bool first) {
+      p->n[f] = walt_fastq_next_part(fq[f], p->b[f], want, adaptor[f].c_str(), first ? 1 : 0);
+      if (p->n[f] < 0) p->err = walt_host_last_error();
+      if (p->n[f] > 0 && !(p->packed[f] = walt_batch_packed(p->b[f]))) { p->n[f] = -1; p->err = walt_host_last_error(); }
+    };
+    for (;;) {
+      Part* p = free_q.pop();
+      if (!p) return;
+      const auto t = std::chrono::steady_clock::now();
+      const uint32_t want = std::min(P, left);
+      const bool first = left == s.batch;
+      p->err.clear();
+      p->first = first;
+      // (the order in which two files are read only matters for their rand() streams, and each file has its own)
+      std::future<void> other;
+      if (files == 2) other = std::async(std::launch::async, load, p, 1, want, first);
+      load(p, 0, want, first);
+      if (other.valid()) other.get();
+      clk.load += StageClock::since(t);
+      const bool bad = p->n[0] < 0 || (files == 2 && p->n[1] < 0);
+      p->last = bad || p->n[0] < (int64_t)want || (files == 2 && p->n[1] < (int64_t)want);
+      left -= (uint32_t)std::max<int64_t>(0, std::min<int64_t>(p->n[0], left));
+      if (left == 0) left = s.batch;
+      const bool stop = p->last;
+      loaded_q.push(p);
+      if (stop) return;
+    }
+  });
+  std::thread writer([&]() {
+    for (;;) {
+      Part* p = mapped_q.pop();
+      if (!p) return;
+      if (!write_failed) {
+        const auto t = std::chrono::steady_clock::now();
+        try { write(*p); } catch (const std::exception& e) { write_err = e.what(); write_failed = true; }
+        clk.write += StageClock::since(t);
+      }
+      free_q.push(p);
+    }
+  });
+  auto shut = [&]() {
+    free_q.close(); loaded_q.close();
+    loader.join();
+    mapped_q.close(true);   // the writer first finishes what it was handed
+    writer.join();
+  };
+
+  uint64_t total = 0;
+  try {
+    for (;;) {
+      Part* p = loaded_q.pop();
+      if (!p) break;
+      if (p->n[0] < 0 || (files == 2 && p->n[1] < 0)) throw std::runtime_error(p->err);
+      // paired.cpp:650-651: when the first file has no further batch the second one is not looked at -- but
+      // inside a batch its extra reads are a count that differs (map reports it)
+      if (p->n[0] == 0 && (files == 1 || p->first || p->n[1] == 0)) break;
+      if (write_failed) break;
+      const auto t = std::chrono::steady_clock::now();
+      const bool go = map(*p);
+      clk.map += StageClock::since(t);
+      if (!go) break;
+      total += (uint64_t)p->n[0];
+      const bool last = p->last;
+      mapped_q.push(p);
+      if (last) break;
+    }
+  } catch (...) {
+    shut();
+    throw;
+  }
+  shut();
+  if (write_failed) throw std::runtime_error(write_err);
+  return total;
 }
 
 void process_single_end(Engines& eng, const walt_chroms* chroms, const Settings& s, const std::string& reads,
@@ -170,123 +300,83 @@ void process_single_end(Engines& eng, const walt_chroms* chroms, const Settings&
   walt_se_writer* w = walt_se_writer_open(output.c_str(), chroms, ag, s.ambiguous, s.unmapped, s.sam);
   if (!w) { walt_fastq_close(fq); throw std::runtime_error(walt_host_last_error()); }
   if (s.verbose) std::cerr << "input_file: " << reads << std::endl << "output_file: " << output << std::endl;
-  // two batches: the next one is loaded (and packed) while the current one is mapped and written
-  walt_batch* bb[2] = {walt_batch_create(), walt_batch_create()};
-  std::vector<walt_best> res;
   StageClock clk;
   uint64_t total = 0;
-  std::future<Loaded> next;
   try {
-    int k = 0;
-    Loaded cur = load_batch(fq, bb[0], s.batch, s.adaptor);
-    clk.load += cur.seconds;
-    for (;;) {
-      if (cur.n < 0) throw std::runtime_error(cur.err);
-      if (cur.n == 0) break;
-      const bool last = (uint32_t)cur.n < s.batch;
-      if (!last) next = std::async(std::launch::async, load_batch, fq, bb[1 - k], s.batch, s.adaptor);
-      uint32_t n_short = 0;
-      auto t = std::chrono::steady_clock::now();
-      map_se_batch(eng, bb[k], cur.packed, s, ag, res, n_short);
-      clk.map += StageClock::since(t);
-      t = std::chrono::steady_clock::now();
-      walt_se_writer_add_short(w, n_short);
-      if (walt_se_writer_write(w, bb[k], res.data(), (uint32_t)cur.n)) throw std::runtime_error(walt_host_last_error());
-      clk.write += StageClock::since(t);
-      total += (uint64_t)cur.n;
-      if (last) break;
-      cur = next.get();
-      clk.load += cur.seconds;
-      k = 1 - k;
-    }
+    total = run_parts(
+        s, 1, &fq, &s.adaptor, clk,
+        [&](Part& p) {
+          const uint32_t n = (uint32_t)p.n[0];
+          p.best.resize(n);
+          p.n_short[0] = 0;
+          eng.ready();
+          engine_check(walt_group_map_se_packed(eng.g, p.packed[0], walt_batch_offsets(p.b[0]), n, ag ? 1 : 0, s.m, s.b,
+                                                p.best.data(), &p.n_short[0]));
+          return true;
+        },
+        [&](Part& p) {
+          walt_se_writer_add_short(w, p.n_short[0]);
+          if (walt_se_writer_write(w, p.b[0], p.best.data(), (uint32_t)p.n[0])) throw std::runtime_error(walt_host_last_error());
+        });
   } catch (...) {
-    if (next.valid()) next.wait();
-    walt_batch_free(bb[0]); walt_batch_free(bb[1]); walt_fastq_close(fq); walt_se_writer_close(w);
+    walt_fastq_close(fq); walt_se_writer_close(w);
     throw;
   }
-  walt_batch_free(bb[0]); walt_batch_free(bb[1]);
   walt_fastq_close(fq);
   if (walt_se_writer_close(w)) throw std::runtime_error(walt_host_last_error());
-  clk.report("single-end", total);
+  clk.report("single-end", total, part_reads(s));
 }
 
 void process_paired_end(Engines& eng, const walt_chroms* chroms, const Settings& s, const std::string& reads1,
                         const std::string& reads2, const std::string& output) {
-  std::string ad1 = s.adaptor, ad2 = s.adaptor;   // extract_adaptors, util.hpp:221-233
+  std::string ad[2] = {s.adaptor, s.adaptor};   // extract_adaptors, util.hpp:221-233
   const size_t sep = s.adaptor.find(':');
   if (s.adaptor.rfind(':') != sep) throw std::runtime_error("ERROR: adaptor format \"T_adaptor[:A_adaptor]\"");
-  if (sep != std::string::npos) { ad1 = s.adaptor.substr(0, sep); ad2 = s.adaptor.substr(sep + 1); }
-  if (s.pbat) std::swap(ad1, ad2);   // the T-rich adaptor belongs to the C->T mate, which is mate 2 under PBAT
-  walt_fastq* f1 = walt_fastq_open(reads1.c_str());
-  if (!f1) throw std::runtime_error("cannot open input file " + reads1);
-  walt_fastq* f2 = walt_fastq_open(reads2.c_str());
-  if (!f2) { walt_fastq_close(f1); throw std::runtime_error("cannot open input file " + reads2); }
+  if (sep != std::string::npos) { ad[0] = s.adaptor.substr(0, sep); ad[1] = s.adaptor.substr(sep + 1); }
+  if (s.pbat) std::swap(ad[0], ad[1]);   // the T-rich adaptor belongs to the C->T mate, which is mate 2 under PBAT
+  walt_fastq* fq[2] = {walt_fastq_open(reads1.c_str()), nullptr};
+  if (!fq[0]) throw std::runtime_error("cannot open input file " + reads1);
+  fq[1] = walt_fastq_open(reads2.c_str());
+  if (!fq[1]) { walt_fastq_close(fq[0]); throw std::runtime_error("cannot open input file " + reads2); }
   walt_pe_writer* w = walt_pe_writer_open(output.c_str(), chroms, s.m, s.top_k, s.frag, s.ambiguous, s.unmapped, s.sam, s.pbat);
-  if (!w) { walt_fastq_close(f1); walt_fastq_close(f2); throw std::runtime_error(walt_host_last_error()); }
+  if (!w) { walt_fastq_close(fq[0]); walt_fastq_close(fq[1]); throw std::runtime_error(walt_host_last_error()); }
   fprintf(stderr, "[MAPPING PAIRED-END READS FROM THE FOLLOWING TWO FILES]\n   %s (AND)\n   %s\n", reads1.c_str(), reads2.c_str());
   fprintf(stderr, "[OUTPUT MAPPING RESULTS TO %s]\n", output.c_str());
-  // two pairs of batches: both mate files of the next batch are loaded concurrently while the
-  // current batch is mapped and written
-  walt_batch* b1[2] = {walt_batch_create(), walt_batch_create()};
-  walt_batch* b2[2] = {walt_batch_create(), walt_batch_create()};
-  std::vector<walt_pe_result> res;
   bool unequal = false;
   StageClock clk;
   uint64_t total = 0;
-  std::future<Loaded> next1, next2;
-  auto free_all = [&]() {
-    for (int i = 0; i < 2; ++i) { walt_batch_free(b1[i]); walt_batch_free(b2[i]); }
-    walt_fastq_close(f1); walt_fastq_close(f2);
-  };
   try {
-    int k = 0;
-    // (the order in which the two files are read only matters for the rand() stream, which every
-    // load restarts from srand(0), mapping.cpp:73)
-    next1 = std::async(std::launch::async, load_batch, f1, b1[0], s.batch, ad1);
-    Loaded c2 = load_batch(f2, b2[0], s.batch, ad2);
-    Loaded c1 = next1.get();
-    clk.load += std::max(c1.seconds, c2.seconds);
-    for (;;) {
-      if (c1.n < 0) throw std::runtime_error(c1.err);
-      if (c1.n == 0) break;   // paired.cpp:650-651: the second file is not even read when the first one is exhausted
-      if (c2.n < 0) throw std::runtime_error(c2.err);
-      if (c1.n != c2.n) { unequal = true; break; }
-      const uint32_t n = (uint32_t)c1.n;
-      const bool last = n < s.batch;
-      if (!last) {
-        next1 = std::async(std::launch::async, load_batch, f1, b1[1 - k], s.batch, ad1);
-        next2 = std::async(std::launch::async, load_batch, f2, b2[1 - k], s.batch, ad2);
-      }
-      auto t = std::chrono::steady_clock::now();
-      res.resize(n);
-      uint32_t short1 = 0, short2 = 0;
-      engine_check(walt_group_map_pe_compact_packed(eng.g, c1.packed, walt_batch_offsets(b1[k]), c2.packed, walt_batch_offsets(b2[k]),
-                                                    n, s.m, s.b, s.top_k, s.frag, s.pbat ? 1 : 0, res.data(), &short1, &short2));
-      walt_pe_writer_add_short(w, short1, short2);
-      clk.map += StageClock::since(t);
-      t = std::chrono::steady_clock::now();
-      if (walt_pe_writer_write_compact(w, b1[k], b2[k], res.data(), n))
-        throw std::runtime_error(walt_host_last_error());
-      clk.write += StageClock::since(t);
-      total += n;
-      if (last) break;
-      c1 = next1.get(); c2 = next2.get();
-      clk.load += std::max(c1.seconds, c2.seconds);
-      k = 1 - k;
-    }
+    total = run_parts(
+        s, 2, fq, ad, clk,
+        [&](Part& p) {
+          // paired.cpp:673-677.  (The reference compares the two counts of a whole batch before it maps any of
+          // it; here the parts of the batch in front of the one where a file ends have been written by then.)
+          if (p.n[0] != p.n[1]) { unequal = true; return false; }
+          const uint32_t n = (uint32_t)p.n[0];
+          p.pairs.resize(n);
+          p.n_short[0] = p.n_short[1] = 0;
+          eng.ready();
+          engine_check(walt_group_map_pe_compact_packed(eng.g, p.packed[0], walt_batch_offsets(p.b[0]), p.packed[1],
+                                                        walt_batch_offsets(p.b[1]), n, s.m, s.b, s.top_k, s.frag, s.pbat ? 1 : 0,
+                                                        p.pairs.data(), &p.n_short[0], &p.n_short[1]));
+          return true;
+        },
+        [&](Part& p) {
+          walt_pe_writer_add_short(w, p.n_short[0], p.n_short[1]);
+          if (walt_pe_writer_write_compact(w, p.b[0], p.b[1], p.pairs.data(), (uint32_t)p.n[0]))
+            throw std::runtime_error(walt_host_last_error());
+        });
   } catch (...) {
-    if (next1.valid()) next1.wait();
-    if (next2.valid()) next2.wait();
-    free_all(); walt_pe_writer_close(w);
+    walt_fastq_close(fq[0]); walt_fastq_close(fq[1]); walt_pe_writer_close(w);
     throw;
   }
-  free_all();
+  walt_fastq_close(fq[0]); walt_fastq_close(fq[1]);
   if (unequal) {   // paired.cpp:673-677: exits without writing mapstats
     fprintf(stderr, "The number of reads in paired-end files should be the same.\n");
     exit(EXIT_FAILURE);
   }
   if (walt_pe_writer_close(w)) throw std::runtime_error(walt_host_last_error());
-  clk.report("paired-end", total);
+  clk.report("paired-end", total, part_reads(s));
 }
 
 }  // namespace
@@ -362,25 +452,28 @@ int main(int argc, const char** argv) {
     if (!se.empty()) mask |= (s.ag || s.pbat) ? (1u << WALT_GA10 | 1u << WALT_GA11) : (1u << WALT_CT00 | 1u << WALT_CT01);
     if (!pe1.empty()) mask |= 0xFu;
     Engines eng;
-    const auto t_index = std::chrono::steady_clock::now();
     if (mask) {
-      // one engine (one index replica) per shard.  More shards than devices would put several replicas of
-      // the index on one device: the shard count is clamped (WALT_SHARE_DEVICES=1 keeps it, for tests on small indexes)
-      const int n_dev = walt_device_count();
-      if (n_dev > 0 && s.gpus > (uint32_t)n_dev && !getenv("WALT_SHARE_DEVICES")) {
-        std::cerr << "[-gpus " << s.gpus << ": only " << n_dev << " device(s) visible, using " << n_dev << "]" << std::endl;
-        s.gpus = (uint32_t)n_dev;
-      }
-      std::vector<int> devs(s.gpus);
-      for (uint32_t i = 0; i < s.gpus; ++i) devs[i] = n_dev > 0 ? (int)(i % (uint32_t)n_dev) : (int)i;
-      engine_check(walt_group_create(&eng.g, devs.data(), (int)s.gpus));
-      // the files are read once; the other devices get their replicas device to device (NVLink / NVSwitch)
-      engine_check(walt_group_load_dbindex(eng.g, s.index.c_str(), mask));
-      if (getenv("WALT_TIMING") && s.gpus > 1)
-        fprintf(stderr, "[walt timing] index read once, cloned over NVLink to %u more device%s\n", s.gpus - 1, s.gpus > 2 ? "s" : "");
-      if (getenv("WALT_TIMING"))
-        fprintf(stderr, "[walt timing] engine start + index residency (%u GPU%s): %.3f s\n", s.gpus, s.gpus > 1 ? "s" : "",
-                StageClock::since(t_index));
+      eng.start = std::async(std::launch::async, [&eng, &s, mask]() {
+        const auto t_index = std::chrono::steady_clock::now();
+        // one engine (one index replica) per shard.  More shards than devices would put several replicas of
+        // the index on one device: the shard count is clamped (WALT_SHARE_DEVICES=1 keeps it, for tests on small indexes)
+        uint32_t gpus = s.gpus;
+        const int n_dev = walt_device_count();
+        if (n_dev > 0 && gpus > (uint32_t)n_dev && !getenv("WALT_SHARE_DEVICES")) {
+          std::cerr << "[-gpus " << gpus << ": only " << n_dev << " device(s) visible, using " << n_dev << "]" << std::endl;
+          gpus = (uint32_t)n_dev;
+        }
+        std::vector<int> devs(gpus);
+        for (uint32_t i = 0; i < gpus; ++i) devs[i] = n_dev > 0 ? (int)(i % (uint32_t)n_dev) : (int)i;
+        engine_check(walt_group_create(&eng.g, devs.data(), (int)gpus));
+        // the files are read once; the other devices get their replicas device to device (NVLink / NVSwitch)
+        engine_check(walt_group_load_dbindex(eng.g, s.index.c_str(), mask));
+        if (getenv("WALT_TIMING") && gpus > 1)
+          fprintf(stderr, "[walt timing] index read once, cloned over NVLink to %u more device%s\n", gpus - 1, gpus > 2 ? "s" : "");
+        if (getenv("WALT_TIMING"))
+          fprintf(stderr, "[walt timing] engine start + index residency (%u GPU%s), beside the first reads' load: %.3f s\n", gpus,
+                  gpus > 1 ? "s" : "", StageClock::since(t_index));
+      });
     }
 
     size_t oi = 0;
@@ -388,6 +481,7 @@ int main(int argc, const char** argv) {
     for (auto& f : se) process_single_end(eng, chroms, s, f, outs[oi++]);
     if (s.verbose) std::cerr << "n_pe_read_files: " << pe1.size() << std::endl;
     for (size_t i = 0; i < pe1.size(); ++i) process_paired_end(eng, chroms, s, pe1[i], pe2[i], outs[oi++]);
+    eng.ready();   // (a run without a single read still reports an engine that could not start)
     walt_chroms_free(chroms);
   } catch (const std::runtime_error& e) {
     std::cerr << e.what() << std::endl;
