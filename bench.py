@@ -570,6 +570,14 @@ def cli_leg(device, genome_mb, n_reads, rl, workdir=None, keep=False, small=Fals
         out["ours_reads_per_s"] = n_reads / min(runs)
         d_ours = digest(o_out)
         ms_ours = open(o_out + ".mapstats", "rb").read()
+        # experiments on the same files: WALT_CLI_VARIANTS="NAME=VALUE,NAME=VALUE;..." -> one more run per setting
+        for spec in filter(None, os.environ.get("WALT_CLI_VARIANTS", "").split(";")):
+            v_env = dict(env, **dict(kv.split("=", 1) for kv in spec.split(",")))
+            v_out = os.path.join(work, "variant.sam")
+            dt, err = timed([ours_bin] + opts + ["-o", v_out] + (["-gpus", str(n_gpus)] if n_gpus > 1 else []), v_env)
+            out.setdefault("variants", []).append({"env": spec, "s": round(dt, 3), "identical": digest(v_out) == d_ours,
+                                                   "stages": [l for l in err.splitlines() if l.startswith("[walt timing]")]})
+            os.remove(v_out)
         out["sam_bytes"] = d_ours[1]
         if refio.have_reference():
             r_out = os.path.join(work, "ref.sam")

@@ -170,8 +170,41 @@ struct Sink {
     n += (size_t)k;
   }
   void i32(int32_t v) { if (v < 0) { ch('-'); u32((uint32_t)(-(int64_t)v)); } else u32((uint32_t)v); }
-  void revcomp(const char* s, size_t k) { char* o = room(k); for (size_t i = 0; i < k; ++i) o[i] = g_comp.t[(unsigned char)s[k - 1 - i]]; n += k; }
-  void rev(const char* s, size_t k) { char* o = room(k); for (size_t i = 0; i < k; ++i) o[i] = s[k - 1 - i]; n += k; }
+  // reversed (and complemented) copies, 16 bytes at a time: half of all output lines are '-' strand
+#if defined(__SSE2__)
+  static __m128i reversed16(__m128i v) {
+    v = _mm_or_si128(_mm_srli_epi16(v, 8), _mm_slli_epi16(v, 8));                  // bytes of every 16-bit lane
+    v = _mm_shufflelo_epi16(v, _MM_SHUFFLE(0, 1, 2, 3));
+    v = _mm_shufflehi_epi16(v, _MM_SHUFFLE(0, 1, 2, 3));
+    return _mm_shuffle_epi32(v, _MM_SHUFFLE(1, 0, 3, 2));
+  }
+  static __m128i complemented16(__m128i v) {   // A <-> T is ^ 0x15, C <-> G is ^ 0x04, anything else stays
+    const __m128i at = _mm_or_si128(_mm_cmpeq_epi8(v, _mm_set1_epi8('A')), _mm_cmpeq_epi8(v, _mm_set1_epi8('T')));
+    const __m128i cg = _mm_or_si128(_mm_cmpeq_epi8(v, _mm_set1_epi8('C')), _mm_cmpeq_epi8(v, _mm_set1_epi8('G')));
+    return _mm_xor_si128(v, _mm_or_si128(_mm_and_si128(at, _mm_set1_epi8(0x15)), _mm_and_si128(cg, _mm_set1_epi8(0x04))));
+  }
+#endif
+  void revcomp(const char* s, size_t k) {
+    char* o = room(k);
+    size_t i = 0;
+#if defined(__SSE2__)
+    for (; i + 16 <= k; i += 16)
+      _mm_storeu_si128(reinterpret_cast<__m128i*>(o + i),
+                       complemented16(reversed16(_mm_loadu_si128(reinterpret_cast<const __m128i*>(s + k - 16 - i)))));
+#endif
+    for (; i < k; ++i) o[i] = g_comp.t[(unsigned char)s[k - 1 - i]];
+    n += k;
+  }
+  void rev(const char* s, size_t k) {
+    char* o = room(k);
+    size_t i = 0;
+#if defined(__SSE2__)
+    for (; i + 16 <= k; i += 16)
+      _mm_storeu_si128(reinterpret_cast<__m128i*>(o + i), reversed16(_mm_loadu_si128(reinterpret_cast<const __m128i*>(s + k - 16 - i))));
+#endif
+    for (; i < k; ++i) o[i] = s[k - 1 - i];
+    n += k;
+  }
 };
 
 }  // namespace
