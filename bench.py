@@ -1023,6 +1023,7 @@ def run_ours(args):
         return 0
     # ---- end-to-end timing through the C ABI with pinned host buffers (`e2e`) ----
     from walt_b200.engine import PinnedArray
+    from walt_b200.sharding import max_over_ranks
     h_offs = PinnedArray((n + 1,), np.uint64)
     h_offs.array[:] = np.arange(n + 1, dtype=np.uint64) * np.uint64(rl)
     h_out = PinnedArray((n,), wl.out_dt)
@@ -1080,11 +1081,55 @@ def run_ours(args):
     torch.cuda.synchronize()
     t_pk = time.perf_counter() - t0
     windows.append((t0, t0 + t_pk))
-    clocks = sampler.stop(windows)
     same_pk = bool(np.array_equal(h_out.array.view(np.uint8), ascii_out.view(np.uint8)))
+
+    # ---- a ragged batch (reads of 100..150 bases): the offsets array crosses PCIe too and the kernels take every
+    #      length from it (`e2e_ragged`; single-end, the first 2 M reads cut to pseudo-random lengths) ----
+    ragged = None
+    if not pe and world == 1:
+        try:
+            nr = min(n, 2_000_000)
+            lens = (100 + (np.arange(nr, dtype=np.uint64) * np.uint64(2654435761) >> np.uint64(7)) % np.uint64(rl - 99)).astype(np.int64)
+            r_offs = PinnedArray((nr + 1,), np.uint64)
+            r_offs.array[0] = 0
+            r_offs.array[1:] = np.cumsum(lens).astype(np.uint64)
+            r_reads = PinnedArray((int(r_offs.array[nr]),), np.uint8)
+            keep = (np.arange(rl, dtype=np.int64)[None, :] < lens[:, None])
+            r_reads.array[:] = h_reads.array[: nr * rl].reshape(nr, rl)[keep]
+            del keep
+            r_pk = PinnedArray((int(r_offs.array[nr] >> np.uint64(2)) + nr + 16,), np.uint8)
+            wh.pack_reads_2bit(r_reads.array, r_offs.array, out=r_pk.array)
+            r_out = PinnedArray((nr,), wl.out_dt)
+            r_steps = max(2, min(args.steps, 5))
+            times = {}
+            for name, call in (("ascii", lambda: e.map_se(r_reads.array, r_offs.array, ag=wl.ag, m=wl.m, b=B, out=r_out.array)),
+                               ("packed", lambda: e.map_se_packed(r_pk.array, r_offs.array, ag=wl.ag, m=wl.m, b=B, out=r_out.array))):
+                call()
+                if name == "ascii":
+                    r_first = r_out.array.copy()
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(r_steps):
+                    call()
+                torch.cuda.synchronize()
+                times[name] = time.perf_counter() - t0
+                windows.append((t0, t0 + times[name]))
+            t_ra, t_rp = times["ascii"], times["packed"]
+            ragged = {"value": nr * world * r_steps / t_ra, "unit": unit, "packed_value": nr * world * r_steps / t_rp,
+                      "reads_per_step": nr, "steps": r_steps, "read_lengths": f"100..{rl}, mean {float(lens.mean()):.1f}",
+                      "h2d_bytes_per_step": int(r_reads.array.size + 8 * (nr + 1)),
+                      "h2d_bytes_per_step_packed": int(r_pk.array.size + 8 * (nr + 1)), "d2h_bytes_per_step": int(16 * nr),
+                      "ms_per_step": 1e3 * t_ra / r_steps, "ms_per_step_packed": 1e3 * t_rp / r_steps,
+                      "packed_equals_ascii": bool(np.array_equal(r_out.array.view(np.uint8), r_first.view(np.uint8))),
+                      "mapped_frac": float((r_first["times"] >= 1).mean()),
+                      "what": "walt_engine_map_se / _packed on a batch whose reads differ in length: offsets (8 B per read) travel with the reads"}
+            for h in (r_offs, r_reads, r_pk, r_out):
+                h.free()
+        except Exception as ex:      # an extra leg must not take the line down
+            ragged = {"error": str(ex)[-300:]}
+    clocks = sampler.stop(windows)
     barrier()
 
-    from walt_b200.sharding import max_over_ranks
     t_dev, t_e2e, t_pk = max_over_ranks([t_dev, t_e2e, t_pk], dist, dev)
     for h in (h_reads, h_reads2, h_offs, h_out, h_pk, h_pk2):
         if h is not None:
@@ -1113,6 +1158,7 @@ def run_ours(args):
                                "d2h_bytes_per_step": int(wl.out_dt.itemsize * n), "ms_per_step": 1e3 * t_pk / args.steps,
                                "identical_to_e2e_result": same_pk,
                                "input": "2-bit packed reads (walt_pack_reads, packed by the loader outside the timed region)"},
+                "e2e_ragged": ragged,
                 "gpu_launches": launches_dev,
                 "roofline": roof, "cpu_baseline": cpu_baseline, "parity_check": parity}
         if world == 1 and args.workload == "se" and not args.no_cpu:
