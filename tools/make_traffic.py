@@ -7,7 +7,8 @@
 
 (tools/gpu_round.sh) runs 3 warm-up steps, the timed step and one more whose work counters are read.  A
 single-end step starts with the parking kernel se_map_kernel<.., 1>, a paired-end step ends with pair_kernel;
-the step that is summed is the FOURTH one (the timed one; all steps do the same work).  For `verify` only
+the step that is summed is the FOURTH one (the timed one; all steps do the same work; a paired-end step
+is several sub-launches of pairs, each with its own pair_kernel).  For `verify` only
 the verify_kernel launches of that step count (its roofline line divides by their device time alone).
 
     python tools/make_traffic.py gpurun_out/TAG          -> writes profiles/traffic.json, prints a summary
@@ -25,6 +26,7 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 KINDS = ("se", "se_ag", "pe", "pe_stress", "verify")
+N_STEPS = 5    # --warmup 3 --steps 1 and the step whose work counters are read
 
 
 def launches(path):
@@ -83,7 +85,16 @@ def main(prefix):
             print(f"{kind}: no {path}")
             continue
         ls = launches(path)
-        steps = steps_of(ls, kind in ("pe", "pe_stress"))
+        paired = kind in ("pe", "pe_stress")
+        steps = steps_of(ls, paired)
+        if paired:
+            # a paired-end device call runs as several sub-launches of pairs (each ends with its pair_kernel):
+            # the capture holds N_STEPS whole steps, so every step is len / N_STEPS consecutive sub-launches
+            if len(steps) % N_STEPS:
+                print(f"{kind}: {len(steps)} sub-launches do not make {N_STEPS} steps in {path}")
+                continue
+            per_step = len(steps) // N_STEPS
+            steps = [sum(steps[i * per_step:(i + 1) * per_step], []) for i in range(N_STEPS)]
         if len(steps) < 4:
             print(f"{kind}: only {len(steps)} steps in {path}")
             continue

@@ -4,7 +4,7 @@
 // -C -A -b -k -L -sam -v -t, single-dash long names, comma separated file lists, one shared or
 // one-per-input output name, truncation of outputs at start, exit codes) plus -P/-pbat and
 // -gpus.  The batch drivers (mapping.cpp:421-526, paired.cpp:572-713) become:
-//   load index ONCE into HBM (beside the first reads' load) -> per part of a batch, three parts under way
+//   load index ONCE into HBM -> per part of a batch, three parts under way
 //   at a time { load FASTQ (walt_host) | walt_group_map_se/pe on the GPU(s) | write SAM/MR (walt_host) }
 //   -> mapstats.
 // Mapping has no CPU implementation here: without a CUDA device the program exits 1.
@@ -127,17 +127,13 @@ void engine_check(int rc) {
 }
 
 // the GPUs of a run: one engine per device behind one handle (walt_group, include/walt_b200.h), which cuts
-// every batch into contiguous ranges and keeps the results in input order.  The engines start
-// (contexts, index files into HBM, replicas) on a thread of their own while the first reads are loaded:
-// ready() is called in front of the first mapping call.
+// every batch into contiguous ranges and keeps the results in input order.  (Starting the engines
+// beside the first reads' load was measured and dropped: context creation and the pinned / device
+// allocations serialise with the loader's page faults on the process's address-space lock, and the index
+// residency went from 0.64 s to 0.7 - 1.5 s to hide a first part's load of 0.04 s.)
 struct Engines {
   walt_group* g = nullptr;
-  std::future<void> start;
-  void ready() { if (start.valid()) start.get(); }
-  ~Engines() {
-    if (start.valid()) start.wait();
-    walt_group_destroy(g);
-  }
+  ~Engines() { walt_group_destroy(g); }
 };
 
 // stage timings on stderr when WALT_TIMING is set (never part of the outputs).  The three stages run
@@ -150,8 +146,8 @@ struct StageClock {
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count();
   }
   void report(const char* what, uint64_t n, uint32_t part) const {
-    if (on) fprintf(stderr, "[walt timing] %s: %llu reads in parts of %u, stages overlapped: load %.3f s, map %.3f s (with the wait "
-                            "for the engines), write %.3f s, total %.3f s, %u host threads\n", what, (unsigned long long)n, part,
+    if (on) fprintf(stderr, "[walt timing] %s: %llu reads in parts of %u, stages overlapped: load %.3f s, map %.3f s, "
+                            "write %.3f s, total %.3f s, %u host threads\n", what, (unsigned long long)n, part,
                     load, map, write, since(t0), walt_host_threads());
   }
 };
@@ -309,7 +305,6 @@ void process_single_end(Engines& eng, const walt_chroms* chroms, const Settings&
           const uint32_t n = (uint32_t)p.n[0];
           p.best.resize(n);
           p.n_short[0] = 0;
-          eng.ready();
           engine_check(walt_group_map_se_packed(eng.g, p.packed[0], walt_batch_offsets(p.b[0]), n, ag ? 1 : 0, s.m, s.b,
                                                 p.best.data(), &p.n_short[0]));
           return true;
@@ -355,7 +350,6 @@ void process_paired_end(Engines& eng, const walt_chroms* chroms, const Settings&
           const uint32_t n = (uint32_t)p.n[0];
           p.pairs.resize(n);
           p.n_short[0] = p.n_short[1] = 0;
-          eng.ready();
           engine_check(walt_group_map_pe_compact_packed(eng.g, p.packed[0], walt_batch_offsets(p.b[0]), p.packed[1],
                                                         walt_batch_offsets(p.b[1]), n, s.m, s.b, s.top_k, s.frag, s.pbat ? 1 : 0,
                                                         p.pairs.data(), &p.n_short[0], &p.n_short[1]));
@@ -453,27 +447,24 @@ int main(int argc, const char** argv) {
     if (!pe1.empty()) mask |= 0xFu;
     Engines eng;
     if (mask) {
-      eng.start = std::async(std::launch::async, [&eng, &s, mask]() {
-        const auto t_index = std::chrono::steady_clock::now();
-        // one engine (one index replica) per shard.  More shards than devices would put several replicas of
-        // the index on one device: the shard count is clamped (WALT_SHARE_DEVICES=1 keeps it, for tests on small indexes)
-        uint32_t gpus = s.gpus;
-        const int n_dev = walt_device_count();
-        if (n_dev > 0 && gpus > (uint32_t)n_dev && !getenv("WALT_SHARE_DEVICES")) {
-          std::cerr << "[-gpus " << gpus << ": only " << n_dev << " device(s) visible, using " << n_dev << "]" << std::endl;
-          gpus = (uint32_t)n_dev;
-        }
-        std::vector<int> devs(gpus);
-        for (uint32_t i = 0; i < gpus; ++i) devs[i] = n_dev > 0 ? (int)(i % (uint32_t)n_dev) : (int)i;
-        engine_check(walt_group_create(&eng.g, devs.data(), (int)gpus));
-        // the files are read once; the other devices get their replicas device to device (NVLink / NVSwitch)
-        engine_check(walt_group_load_dbindex(eng.g, s.index.c_str(), mask));
-        if (getenv("WALT_TIMING") && gpus > 1)
-          fprintf(stderr, "[walt timing] index read once, cloned over NVLink to %u more device%s\n", gpus - 1, gpus > 2 ? "s" : "");
-        if (getenv("WALT_TIMING"))
-          fprintf(stderr, "[walt timing] engine start + index residency (%u GPU%s), beside the first reads' load: %.3f s\n", gpus,
-                  gpus > 1 ? "s" : "", StageClock::since(t_index));
-      });
+      const auto t_index = std::chrono::steady_clock::now();
+      // one engine (one index replica) per shard.  More shards than devices would put several replicas of
+      // the index on one device: the shard count is clamped (WALT_SHARE_DEVICES=1 keeps it, for tests on small indexes)
+      const int n_dev = walt_device_count();
+      if (n_dev > 0 && s.gpus > (uint32_t)n_dev && !getenv("WALT_SHARE_DEVICES")) {
+        std::cerr << "[-gpus " << s.gpus << ": only " << n_dev << " device(s) visible, using " << n_dev << "]" << std::endl;
+        s.gpus = (uint32_t)n_dev;
+      }
+      std::vector<int> devs(s.gpus);
+      for (uint32_t i = 0; i < s.gpus; ++i) devs[i] = n_dev > 0 ? (int)(i % (uint32_t)n_dev) : (int)i;
+      engine_check(walt_group_create(&eng.g, devs.data(), (int)s.gpus));
+      // the files are read once; the other devices get their replicas device to device (NVLink / NVSwitch)
+      engine_check(walt_group_load_dbindex(eng.g, s.index.c_str(), mask));
+      if (getenv("WALT_TIMING") && s.gpus > 1)
+        fprintf(stderr, "[walt timing] index read once, cloned over NVLink to %u more device%s\n", s.gpus - 1, s.gpus > 2 ? "s" : "");
+      if (getenv("WALT_TIMING"))
+        fprintf(stderr, "[walt timing] engine start + index residency (%u GPU%s): %.3f s\n", s.gpus, s.gpus > 1 ? "s" : "",
+                StageClock::since(t_index));
     }
 
     size_t oi = 0;
@@ -481,7 +472,6 @@ int main(int argc, const char** argv) {
     for (auto& f : se) process_single_end(eng, chroms, s, f, outs[oi++]);
     if (s.verbose) std::cerr << "n_pe_read_files: " << pe1.size() << std::endl;
     for (size_t i = 0; i < pe1.size(); ++i) process_paired_end(eng, chroms, s, pe1[i], pe2[i], outs[oi++]);
-    eng.ready();   // (a run without a single read still reports an engine that could not start)
     walt_chroms_free(chroms);
   } catch (const std::runtime_error& e) {
     std::cerr << e.what() << std::endl;
