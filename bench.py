@@ -531,6 +531,9 @@ def cli_leg(device, genome_mb, n_reads, rl, workdir=None, keep=False, small=Fals
         del d_fwd, d_reads
         e.close()
         torch.cuda.empty_cache()
+        if os.environ.get("WALT_CLI_SYNC", "0") != "0":
+            os.sync()     # experiment: set-up wrote ~10 GB; wait for the write-back before any program is timed on those
+                          # files (measured: no help -- profiles/r02_bench_cli_startup_split.json)
         out["setup_s"] = round(time.time() - t0, 1)
         out["fastq_bytes"] = os.path.getsize(fq)
         out["index_bytes"] = sum(os.path.getsize(idx + s) for s in ("", "_CT00", "_CT01", "_GA10", "_GA11"))

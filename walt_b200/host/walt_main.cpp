@@ -458,13 +458,14 @@ int main(int argc, const char** argv) {
       std::vector<int> devs(s.gpus);
       for (uint32_t i = 0; i < s.gpus; ++i) devs[i] = n_dev > 0 ? (int)(i % (uint32_t)n_dev) : (int)i;
       engine_check(walt_group_create(&eng.g, devs.data(), (int)s.gpus));
+      const double t_create = StageClock::since(t_index);
       // the files are read once; the other devices get their replicas device to device (NVLink / NVSwitch)
       engine_check(walt_group_load_dbindex(eng.g, s.index.c_str(), mask));
       if (getenv("WALT_TIMING") && s.gpus > 1)
         fprintf(stderr, "[walt timing] index read once, cloned over NVLink to %u more device%s\n", s.gpus - 1, s.gpus > 2 ? "s" : "");
       if (getenv("WALT_TIMING"))
-        fprintf(stderr, "[walt timing] engine start + index residency (%u GPU%s): %.3f s\n", s.gpus, s.gpus > 1 ? "s" : "",
-                StageClock::since(t_index));
+        fprintf(stderr, "[walt timing] engine start + index residency (%u GPU%s): %.3f s (contexts %.3f s, index %.3f s)\n", s.gpus,
+                s.gpus > 1 ? "s" : "", StageClock::since(t_index), t_create, StageClock::since(t_index) - t_create);
     }
 
     size_t oi = 0;
