@@ -179,7 +179,7 @@ struct Part {
   int64_t n[2] = {0, 0};
   bool first = false;            // the first part of a batch
   bool last = false;             // a file ended in this part: nothing follows
-  std::string err;
+  std::string err[2];
   std::vector<walt_best> best;
   std::vector<walt_pe_result> pairs;
   uint32_t n_short[2] = {0, 0};
@@ -213,10 +213,15 @@ uint64_t run_parts(const Settings& s, int files, walt_fastq* const* fq, const st
 
   std::thread loader([&]() {
     uint32_t left = s.batch;                       // reads of the current batch still to load
-    auto load = [&](Part* p, int f, uint32_t want, bool first) {
-      p->n[f] = walt_fastq_next_part(fq[f], p->b[f], want, adaptor[f].c_str(), first ? 1 : 0);
-      if (p->n[f] < 0) p->err = walt_host_last_error();
-      if (p->n[f] > 0 && !(p->packed[f] = walt_batch_packed(p->b[f]))) { p->n[f] = -1; p->err = walt_host_last_error(); }
+    auto load = [&](Part* p, int f, uint32_t want, bool first) {   // (each file has its own error text: two threads)
+      try {
+        p->n[f] = walt_fastq_next_part(fq[f], p->b[f], want, adaptor[f].c_str(), first ? 1 : 0);
+        if (p->n[f] < 0) p->err[f] = walt_host_last_error();
+        if (p->n[f] > 0 && !(p->packed[f] = walt_batch_packed(p->b[f]))) { p->n[f] = -1; p->err[f] = walt_host_last_error(); }
+      } catch (const std::exception& e) {   // bad_alloc on the loader's own tables
+        p->n[f] = -1;
+        p->err[f] = std::string("ERROR: could not load reads: ") + e.what();
+      }
     };
     for (;;) {
       Part* p = free_q.pop();
@@ -224,7 +229,7 @@ uint64_t run_parts(const Settings& s, int files, walt_fastq* const* fq, const st
       const auto t = std::chrono::steady_clock::now();
       const uint32_t want = std::min(P, left);
       const bool first = left == s.batch;
-      p->err.clear();
+      p->err[0].clear(); p->err[1].clear();
       p->first = first;
       // (the order in which two files are read only matters for their rand() streams, and each file has its own)
       std::future<void> other;
@@ -265,7 +270,8 @@ uint64_t run_parts(const Settings& s, int files, walt_fastq* const* fq, const st
     for (;;) {
       Part* p = loaded_q.pop();
       if (!p) break;
-      if (p->n[0] < 0 || (files == 2 && p->n[1] < 0)) throw std::runtime_error(p->err);
+      if (p->n[0] < 0) throw std::runtime_error(p->err[0]);
+      if (files == 2 && p->n[1] < 0) throw std::runtime_error(p->err[1]);
       // paired.cpp:650-651: when the first file has no further batch the second one is not looked at -- but
       // inside a batch its extra reads are a count that differs (map reports it)
       if (p->n[0] == 0 && (files == 1 || p->first || p->n[1] == 0)) break;
