@@ -158,7 +158,7 @@ struct Sink {
     fd = -1;
     return !write_failed;
   }
-  void str(const char* s, size_t k) { memcpy(room(k), s, k); n += k; }
+  void str(const char* s, size_t k) { if (k) { memcpy(room(k), s, k); n += k; } }
   template <size_t N> void lit(const char (&s)[N]) { memcpy(room(N - 1), s, N - 1); n += N - 1; }
   void str(const std::string& s) { str(s.data(), s.size()); }
   void ch(char c) { *room(1) = c; ++n; }
