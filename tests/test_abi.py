@@ -9,8 +9,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
-    src = open(os.path.join(ROOT, "include", "walt_b200.h")).read()
+def declared_symbols(header="walt_b200.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(walt_[a-z0-9_]+)\s*\(", src)))
 
@@ -22,6 +22,19 @@ def test_header_symbols_are_exported():
     assert len(names) >= 20
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
+
+
+def test_every_header_has_its_library():
+    """include/walt_host.h -> libwalthost.so (pure host code), include/walt_synth.h -> libwaltsynth.so (bench only)."""
+    for header, lib, at_least in (("walt_host.h", "libwalthost.so", 25), ("walt_synth.h", "libwaltsynth.so", 5)):
+        L = C.CDLL(os.path.join(ROOT, "walt_b200", "lib", lib))
+        names = declared_symbols(header)
+        assert len(names) >= at_least, (header, names)
+        missing = [n for n in names if not hasattr(L, n)]
+        assert not missing, (header, missing)
+    # the product library exports no generator
+    import walt_b200
+    assert not [n for n in declared_symbols("walt_synth.h") if hasattr(walt_b200.load_library(), n)]
 
 
 def test_no_cpu_fallback():
